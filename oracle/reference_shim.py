@@ -1,0 +1,114 @@
+"""Import the UNMODIFIED reference (``/root/reference/{overiva,auxiva_pca,ive}.py``) in-process.
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/overiva_oracle.py``).  The reference cannot be imported
+as-is in this image:
+
+1. it imports ``pyroomacoustics.bss.projection_back`` (overiva.py:25, ive.py:30,
+   auxiva_pca.py:27) and pyroomacoustics is not installed -> a stub module exposing the
+   oracle's ``projection_back`` formula is placed in ``sys.modules``;
+2. ``overiva.py:182`` calls ``np.linalg.solve(A (F,M,M), b (F,M))`` with numpy-1.x "stack of
+   vectors" semantics, which numpy >= 2 rejects -> ``numpy.linalg.solve`` is wrapped for the
+   duration of each reference call.
+
+The reference tree stays read-only and nothing is copied from it.  ``/root/reference`` does
+not exist on the GPU box, so everything here is optional: ``available()`` says whether the
+real files can be used.
+"""
+from __future__ import annotations
+
+import contextlib
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+REFERENCE_DIR = os.environ.get("OVERIVA_REFERENCE_DIR", "/root/reference")
+
+_modules = {}
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_DIR, "overiva.py"))
+
+
+def _install_pra_stub():
+    if "pyroomacoustics" in sys.modules and not getattr(
+        sys.modules["pyroomacoustics"], "_oiva_stub", False
+    ):
+        return  # a real pyroomacoustics is installed: use it
+    from oracle.overiva_oracle import projection_back
+
+    def _projection_back(Y, ref, clip_up=None, clip_down=None):
+        return projection_back(Y, ref)
+
+    pra = types.ModuleType("pyroomacoustics")
+    pra._oiva_stub = True
+    bss = types.ModuleType("pyroomacoustics.bss")
+    bss.projection_back = _projection_back
+    pra.bss = bss
+    sys.modules["pyroomacoustics"] = pra
+    sys.modules["pyroomacoustics.bss"] = bss
+
+
+@contextlib.contextmanager
+def numpy1_solve():
+    """numpy-1.x rule: ``b.ndim == a.ndim - 1`` means a stack of vectors."""
+    orig = np.linalg.solve
+
+    def solve(a, b):
+        a_ = np.asarray(a)
+        b_ = np.asarray(b)
+        if a_.ndim > 2 and b_.ndim == a_.ndim - 1:
+            return orig(a_, b_[..., None])[..., 0]
+        return orig(a, b)
+
+    np.linalg.solve = solve
+    try:
+        yield
+    finally:
+        np.linalg.solve = orig
+
+
+def _load(name):
+    """Load ``/root/reference/<name>.py`` under a private module name (the repo root has its own
+    drop-in ``overiva.py`` etc., so the plain import name must not be used)."""
+    if name in _modules:
+        return _modules[name]
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_DIR)
+    _install_pra_stub()
+    path = os.path.join(REFERENCE_DIR, name + ".py")
+    spec = importlib.util.spec_from_file_location("_reference_" + name, path)
+    mod = importlib.util.module_from_spec(spec)
+    if name == "auxiva_pca":
+        # auxiva_pca.py:28 does ``from overiva import overiva``: point it at the real one
+        saved = sys.modules.get("overiva")
+        sys.modules["overiva"] = _load("overiva")
+        try:
+            spec.loader.exec_module(mod)
+        finally:
+            if saved is not None:
+                sys.modules["overiva"] = saved
+            else:
+                del sys.modules["overiva"]
+    else:
+        spec.loader.exec_module(mod)
+    _modules[name] = mod
+    return mod
+
+
+def ref_overiva(X, **kwargs):
+    with numpy1_solve():
+        return _load("overiva").overiva(X, **kwargs)
+
+
+def ref_auxiva_pca(X, **kwargs):
+    with numpy1_solve():
+        return _load("auxiva_pca").auxiva_pca(X, **kwargs)
+
+
+def ref_ogive(X, **kwargs):
+    with numpy1_solve():
+        return _load("ive").ogive(X, **kwargs)

@@ -1,0 +1,138 @@
+"""Seeded synthetic inputs for the OverIVA path (CMU ARCTIC / pyroomacoustics are not available
+offline -- BASELINE.json ``north_star``; recipe in SURVEY.md section 8d, which mirrors the mixing
+rules of the reference's sweep driver ``overiva_sim.py:114-192``).
+
+Two generators:
+
+* :func:`convolutive_mixture` -- time-domain: Laplacian sources with a speech-like block envelope,
+  random exponentially decaying RIRs (RT60 0.3 s), 10 interferers at SINR 10 dB, sensor noise at
+  SNR 60 dB; returns the mixture and the per-source images so SDR/SIR can be evaluated.
+* :func:`stft_domain_mixture` -- draws X directly in the STFT domain (complex super-Gaussian
+  sources times a random per-bin mixing matrix plus a noise floor); used for large throughput
+  runs where minutes of host-side convolution would dominate set-up.
+
+Plus the STFT pair used by the reference's drivers (frame 4096, hop 2048, Hann analysis window:
+``overiva_oneshot.py:156-158,293-295``), here without padding: ``T = (N - frame)//hop + 1``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+FRAME = 4096
+HOP = 2048
+
+
+def n_frames(n_samples: int, frame: int = FRAME, hop: int = HOP) -> int:
+    return (n_samples - frame) // hop + 1
+
+
+def stft(x, frame: int = FRAME, hop: int = HOP):
+    """x: (N, M) real -> X: (T, F, M) complex128, Hann analysis window, no padding."""
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        x = x[:, None]
+    T = n_frames(x.shape[0], frame, hop)
+    win = np.hanning(frame + 1)[:-1]  # periodic Hann (perfect reconstruction at 50 % overlap)
+    idx = np.arange(frame)[None, :] + hop * np.arange(T)[:, None]
+    frames = x[idx, :] * win[None, :, None]  # (T, frame, M)
+    return np.fft.rfft(frames, axis=1).astype(np.complex128)
+
+
+def istft(X, frame: int = FRAME, hop: int = HOP):
+    """X: (T, F, K) -> (N, K); overlap-add with a rectangular synthesis window, which is the
+    matched synthesis for a periodic Hann at 50 % overlap (sum of shifted windows == 1)."""
+    X = np.asarray(X)
+    T = X.shape[0]
+    frames = np.fft.irfft(X, n=frame, axis=1)  # (T, frame, K)
+    out = np.zeros(((T - 1) * hop + frame, X.shape[2]))
+    for t in range(T):
+        out[t * hop : t * hop + frame] += frames[t]
+    return out
+
+
+def _speechlike(rng, n, fs, env_shape=0.5, env_block=0.25):
+    """i.i.d. Laplace(0,1) samples times a piece-wise constant (250 ms) Gamma(0.5) envelope."""
+    blk = max(1, int(env_block * fs))
+    env = rng.gamma(env_shape, 1.0 / env_shape, size=n // blk + 1)
+    env = np.repeat(env, blk)[:n]
+    return rng.laplace(0.0, 1.0, size=n) * env
+
+
+def _rir(rng, fs, rt60=0.3, length=None):
+    if length is None:
+        length = int(rt60 * fs)
+    n = np.arange(length)
+    h = rng.standard_normal(length) * np.exp(-6.9 * n / (rt60 * fs)) * 0.1
+    d = int(rng.integers(1, 41))
+    h[:d] = 0.0
+    h[d] = 1.0  # dominant direct-path tap
+    return h
+
+
+def convolutive_mixture(
+    seed,
+    n_mics,
+    n_targets,
+    duration=15.0,
+    fs=16000,
+    n_interferers=10,
+    sinr_db=10.0,
+    snr_db=60.0,
+    rt60=0.3,
+    env_shape=0.5,
+    env_block=0.25,
+):
+    """Returns ``(mix (N, M), images (n_targets, N, M))`` -- ``images[k]`` is target k as recorded
+    at every microphone (the quantity SDR/SIR are evaluated against, as the reference's drivers do
+    with ``premix``: ``overiva_sim.py:163-200``)."""
+    rng = np.random.default_rng(seed)
+    n = int(duration * fs)
+    n_src = n_targets + n_interferers
+    L = int(rt60 * fs)
+    nfft = 1 << int(np.ceil(np.log2(n + L)))
+    premix = np.empty((n_src, n_mics, n))
+    for s in range(n_src):
+        sig = _speechlike(rng, n, fs, env_shape, env_block)
+        S = np.fft.rfft(sig, nfft)
+        for m in range(n_mics):
+            H = np.fft.rfft(_rir(rng, fs, rt60, L), nfft)
+            premix[s, m] = np.fft.irfft(S * H, nfft)[:n]
+    premix /= np.std(premix[:, 0, :], axis=1)[:, None, None]  # unit variance at the ref mic
+    var_total = float(n_targets)
+    sigma_n = np.sqrt(10 ** (-snr_db / 10) * var_total)
+    sigma_i = np.sqrt(max(0.0, 10 ** (-sinr_db / 10) * var_total - sigma_n**2) / n_interferers)
+    premix[n_targets:] *= sigma_i
+    background = premix[n_targets:].sum(axis=0) + sigma_n * rng.standard_normal((n_mics, n))
+    mix = premix[:n_targets].sum(axis=0) + background
+    images = premix[:n_targets].transpose(0, 2, 1).copy()
+    return mix.T.copy(), images
+
+
+def stft_domain_mixture(seed, n_frames, n_freq, n_mics, n_src, noise_db=-30.0, dtype=np.complex128):
+    """X (T, F, M) drawn directly in the STFT domain: ``n_src`` super-Gaussian sources with a
+    shared per-frame activity (so the IVA source model has something to find), a random complex
+    mixing matrix per bin, and white complex noise ``noise_db`` below the sources -- the noise
+    floor keeps every bin's covariance well conditioned."""
+    rng = np.random.default_rng(seed)
+    T, F, M, K = n_frames, n_freq, n_mics, n_src
+    act = rng.gamma(0.5, 1.0, size=(T, 1, K)) + 0.05
+    S = (rng.standard_normal((T, F, K)) + 1j * rng.standard_normal((T, F, K))) * act
+    A = rng.standard_normal((F, M, K)) + 1j * rng.standard_normal((F, M, K))
+    X = np.einsum("fmk,tfk->tfm", A, S)
+    sig = 10 ** (noise_db / 20) * np.sqrt(K)
+    X += sig * (rng.standard_normal((T, F, M)) + 1j * rng.standard_normal((T, F, M)))
+    return X.astype(dtype)
+
+
+def small_test_mixture(seed, n_mics, n_targets, n_samples=2700, fs=8000, frame=64, hop=32,
+                       n_interferers=4, rt60=0.02, env_shape=2.0, env_block=0.02,
+                       dtype=np.complex128):
+    """A small but *realistic* (time-domain convolutive, then STFT) input for parity tests:
+    ``X (T, F, M)`` with ``T = (n_samples - frame)//hop + 1`` and ``F = frame//2 + 1``.  Real STFTs of
+    convolutive mixtures keep the reference well conditioned for both source models (a 1e-15 relative
+    perturbation of X moves W by ~1e-14 after 20 iterations), which direct STFT-domain draws do not
+    guarantee for the gauss model."""
+    mix, _ = convolutive_mixture(seed, n_mics, n_targets, duration=n_samples / fs, fs=fs,
+                                 n_interferers=n_interferers, rt60=rt60,
+                                 env_shape=env_shape, env_block=env_block)
+    return stft(mix, frame, hop).astype(dtype)
