@@ -1,0 +1,220 @@
+/*
+ * overiva_b200 -- C ABI of the B200-native OverIVA demixing loop (liboveriva_b200.so).
+ *
+ * The reference (onolab-tmu/overiva) is pure Python/NumPy and has no FFI layer: its drop-in boundary
+ * is the Python call signature overiva()/auxiva_pca()/ogive() (overiva.py:28-38, auxiva_pca.py:30,
+ * ive.py:33-45).  The Python host layer in overiva_b200/ keeps those signatures and drives this
+ * library through ctypes.  Every entry point below replaces one NumPy/LAPACK step of the reference;
+ * the file:line of the step it replaces is given with each declaration (paths relative to the
+ * reference repository).
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no C++/torch types.  All data pointers are DEVICE pointers unless the
+ *    name says host.  `stream` is a cudaStream_t passed as void* (NULL = default stream).  All calls
+ *    are asynchronous on that stream and return 0 (OIVA_OK) or a negative OIVA_ERR_* / positive
+ *    cudaError_t; oiva_last_error() gives a thread-local message.
+ *  - complex numbers are interleaved (re, im).  "c128" = two doubles, "c64" = two floats.  `dtype`
+ *    (OIVA_C128 / OIVA_C64) is the storage type of X and Y only; covariances, demixing matrices and all
+ *    on-chip arithmetic are fp64 in both modes.
+ *  - shapes: B mixtures, T frames, F bins, M channels (1..16), K sources (1..M); R = B*F "rows".
+ *  - numerical failure (singular pivot / non-finite value; the reference raises
+ *    numpy.linalg.LinAlgError from overiva.py:98,182) is reported through a device status word that the
+ *    caller reads back when convenient: bit 0 = singular pivot, bit 1 = non-finite result.
+ */
+#ifndef OVERIVA_B200_H
+#define OVERIVA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OIVA_OK 0
+#define OIVA_ERR_INVALID (-1)
+#define OIVA_ERR_NOMEM (-2)
+#define OIVA_ERR_STATE (-3)
+
+#define OIVA_C128 0
+#define OIVA_C64 1
+
+#define OIVA_MODEL_LAPLACE 0 /* r = 2 sqrt(sum_f |y|^2)          overiva.py:152-153 */
+#define OIVA_MODEL_GAUSS 1   /* r = sum_f |y|^2 / F               overiva.py:154-155 */
+#define OIVA_MODEL_NONE 2    /* any other string: r stays 0 (then clamped), as in the reference */
+#define OIVA_MODEL_OGIVE_LAPLACE 3 /* r = sqrt(sum_f |y|^2 / F), no gamma rescale  ive.py:204-205 */
+#define OIVA_MODEL_OGIVE_GAUSS 4   /* r = sum_f |y|^2 / F, no gamma rescale        ive.py:207-208 */
+
+#define OIVA_INIT_EYE 0 /* overiva.py:111-114 */
+#define OIVA_INIT_EIG 1 /* overiva.py:103-109 */
+#define OIVA_INIT_W0 2  /* overiva.py:116-117 */
+
+#define OIVA_STATUS_SINGULAR 1
+#define OIVA_STATUS_NONFINITE 2
+
+int oiva_version(void);
+const char* oiva_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout helpers (host-side arithmetic only, no GPU needed).
+ * The loop streams a planar, frame-contiguous copy of X ("Xp", see csrc/common.cuh): per row
+ * (b, f), nT tiles of [2*M planes][TT frames].  oiva_tile_frames() returns TT for a given problem
+ * (TT == T when a whole row fits one shared-memory stage, else a multiple of 32); phi / r2 buffers
+ * use the padded frame pitch oiva_frame_pitch() (multiple of 32).
+ * ---------------------------------------------------------------------------------------------- */
+int oiva_tile_frames(int n_frames, int n_chan, int dtype);
+int oiva_frame_pitch(int n_frames, int n_chan, int dtype);
+size_t oiva_planar_bytes(int n_batch, int n_frames, int n_freq, int n_chan, int dtype);
+/* number of bin chunks per mixture used for the partial sums of the source-model statistic */
+int oiva_power_chunks(int n_batch, int n_freq);
+
+/* ------------------------------------------------------------------------------------------------
+ * Kernels (one per step of the reference loop).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* X (B,T,F,M) interleaved complex -> planar rows Xp.      replaces: overiva.py:131-132 (swapaxes+copy) */
+int oiva_relayout(const void* X, void* Xp, int n_batch, int n_frames, int n_freq, int n_chan, int dtype,
+                  void* stream);
+
+/* V[row][k] = (1/T) sum_t phi[b][k][t] x x^H  (Hermitian, both triangles written), V: (R,K,M,M) c128.
+ * phi: (B,K,Tp) inverse source-model weights, or NULL with n_src = 1 for the plain covariance.
+ * replaces: overiva.py:179 (all K sources in one pass over X) and overiva.py:87 / ive.py:97 /
+ * auxiva_pca.py:71 (phi == NULL). */
+int oiva_weighted_cov(const void* Xp, const double* phi, void* V, int n_batch, int n_frames, int n_freq,
+                      int n_chan, int n_src, int dtype, void* stream);
+
+/* r2part[b][chunk][k][t] = sum_{f in chunk} |w_k(f)^H x(f,t)|^2.  W: (R,M,w_cols) c128, columns :K used
+ * (w_cols = M for the W_hat matrices of the plan, K for plain (R,M,K) filters).
+ * replaces: overiva.py:140 (demix) + the norm over frequency at overiva.py:152-155 / ive.py:204-208;
+ * Y is never materialised inside the loop. */
+int oiva_demix_power(const void* Xp, const void* W, int w_cols, double* r2part, int n_chunks, int n_batch,
+                     int n_frames, int n_freq, int n_chan, int n_src, int dtype, void* stream);
+
+/* r2[b][k][t] = sum_chunks r2part (fixed order, deterministic).  Used on its own by the
+ * frequency-sharded driver, which all-reduces r2 across ranks before oiva_source_model(n_chunks=1). */
+int oiva_sum_partials(const double* r2part, int n_chunks, double* r2, int n_batch, int n_frames, int n_chan,
+                      int n_src, int dtype, void* stream);
+
+/* source model + scale normalisation + clamp + inverse: overiva.py:152-173 (ive.py:204-214 for the
+ * OGIVE models).  phi (B,K,Tp) <- 1/max(r/gamma, 1e-15); wscale (B,K) <- 1/gamma (laplace),
+ * 1/sqrt(gamma) (gauss), 1 (others): the factor W must be MULTIPLIED by (overiva.py:161-167).
+ * n_freq_total is the F the gauss model divides by (the full F when bins are sharded across GPUs). */
+int oiva_source_model(const double* r2part, int n_chunks, double* phi, double* wscale, int n_batch,
+                      int n_frames, int n_chan, int n_src, int n_freq_total, int model, int dtype,
+                      void* stream);
+
+/* One sweep over the K sources, per bin, in order:  W[:, :K] *= wscale;  for s: w_s = (What^H V_s)^-1 e_s;
+ * w_s /= sqrt(w_s^H V_s w_s);  J = (W^H C E1)^-1 (W^H C E2).   What (R,M,M) c128 in place.
+ * replaces: overiva.py:161-167 (W rescale), :181-182 (zgemm + zgesv), :185-186, :189-190 (:96-98). */
+int oiva_ip_update(void* What, const void* V, const void* C, const double* wscale, int* status,
+                   int n_batch, int n_freq, int n_chan, int n_src, void* stream);
+
+/* Build What (R,M,M): W from eye / eigenvectors / W0, then J and the -I block.
+ * evecs: (R,M,M) from oiva_eigh (ascending; used when mode == OIVA_INIT_EIG: w_k = conj(v_{M-K+k})).
+ * W0: (R,M,K) c128 (mode == OIVA_INIT_W0).                    replaces: overiva.py:89-123 */
+int oiva_init_demix(void* What, const void* C, const void* W0, const void* evecs, int mode, int* status,
+                    int n_rows, int n_chan, int n_src, void* stream);
+
+/* Hermitian eigendecomposition per row (cyclic Jacobi, fp64): evals (R,M) ascending, evecs (R,M,M) with
+ * eigenvectors in columns.  lapack_phase != 0 rotates each eigenvector so that its largest-magnitude
+ * component is real positive (what zgeev, i.e. np.linalg.eig, returns).
+ * replaces: overiva.py:106 / ive.py:110 (np.linalg.eig) and auxiva_pca.py:75 (np.linalg.eigh). */
+int oiva_eigh(const void* C, double* evals, void* evecs, int* status, int n_rows, int n_chan,
+              int lapack_phase, void* stream);
+
+/* W: (R,M,w_cols) c128.  Weff (R,M,K) c128 = W[:, :, k] * z_k with z_k = (w_k^H C e_0)/(w_k^H C w_k) (1 if the denominator is 0)
+ * when proj_back != 0, else a plain copy of the W columns.
+ * replaces: pyroomacoustics.bss.projection_back as called at overiva.py:197-199 (no pass over Y needed:
+ * sum_t conj(x_0) y_k = T w_k^H C e_0 and sum_t |y_k|^2 = T w_k^H C w_k). */
+int oiva_projback_filters(const void* W, int w_cols, const void* C, void* Weff, int n_rows, int n_chan,
+                          int n_src, int proj_back, void* stream);
+
+/* Y (B,T,F,K) interleaved complex (dtype) = Weff^H x.       replaces: overiva.py:192-199 */
+int oiva_demix_output(const void* Xp, const void* Weff, void* Y, int n_batch, int n_frames, int n_freq,
+                      int n_chan, int n_src, int dtype, void* stream);
+
+/* Xr planar rows (K channels) = E_K^H x with E_K (R,M,K) c128 -- the PCA projection of
+ * auxiva_pca.py:79-81 written directly in the planar layout the loop streams. */
+int oiva_project_rows(const void* Xp, const void* E, void* Xr, int n_batch, int n_frames, int n_freq,
+                      int n_chan, int n_src, int dtype, void* stream);
+
+/* C (R,M,M) <- small dense helpers used by the wrappers: Wout (R,M,K) = E (R,M,Kr) @ Wr (R,Kr,K) */
+int oiva_compose_filters(const void* E, const void* Wr, void* Wout, int n_rows, int n_chan, int n_red,
+                         int n_src, void* stream);
+
+/* OGIVE per-bin update (ive.py:132-140, 216-241): from V (R,1,M,M) and the state (w, a, lambda_a),
+ * one masked w-step / a-step with the orthogonal constraints; delta_max[0] <- max_f ||delta_f|| via an
+ * atomic max on its bit pattern (caller zeroes it).  do_a: (R,) uint8 mask (1 = a-step bin). */
+int oiva_ogive_update(void* w, void* a, double* lambda_a, const void* V, const void* C, const void* Cinv,
+                      const uint8_t* do_a, double step_size, double* delta_max, int n_rows, int n_chan,
+                      void* stream);
+/* OGIVE set-up: Cinv = C^-1 (ive.py:98), a from w (ive.py:132-135,168), switching criterion masks
+ * (ive.py:142-161).  cnorm (R,) = ||C||_F. */
+int oiva_ogive_setup(const void* C, void* Cinv, double* cnorm, int* status, int n_rows, int n_chan, void* stream);
+int oiva_ogive_a_from_w(const void* w, void* a, const void* C, int n_rows, int n_chan, void* stream);
+int oiva_ogive_switching(const void* a, const void* C, const double* cnorm, uint8_t* do_a, int n_rows,
+                         int n_chan, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Plan: the whole overiva() call on device pointers (what the Python entry points use).
+ * The plan owns no device memory: the caller provides one workspace block.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct oiva_plan oiva_plan_t;
+
+typedef struct oiva_plan_desc {
+    int n_batch;      /* B independent mixtures                                        */
+    int n_frames;     /* T                                                             */
+    int n_freq;       /* F bins held by this plan (a shard of the full F when sharded) */
+    int n_freq_total; /* F of the whole mixture (gauss model divisor); 0 => n_freq     */
+    int n_chan;       /* M                                                             */
+    int n_src;        /* K                                                             */
+    int model;        /* OIVA_MODEL_*                                                  */
+    int dtype;        /* OIVA_C128 / OIVA_C64: storage of X and Y                      */
+    int flags;        /* reserved, 0                                                   */
+} oiva_plan_desc;
+
+int oiva_plan_create(oiva_plan_t** plan, const oiva_plan_desc* desc);
+void oiva_plan_destroy(oiva_plan_t* plan);
+size_t oiva_plan_workspace_bytes(const oiva_plan_t* plan);
+int oiva_plan_bind(oiva_plan_t* plan, void* workspace, size_t bytes);
+
+/* relayout X and compute the input covariance C                    overiva.py:87,131-132 */
+int oiva_plan_load(oiva_plan_t* plan, const void* X, void* stream);
+/* alternative to oiva_plan_load: the caller has written planar rows into oiva_plan_planar() (e.g. with
+ * oiva_project_rows); computes the covariance of those rows and marks the plan loaded. */
+int oiva_plan_adopt_planar(oiva_plan_t* plan, void* stream);
+/* initialise What (mode OIVA_INIT_*; W0 (B,F,M,K) c128 or NULL)    overiva.py:89-123 */
+int oiva_plan_init(oiva_plan_t* plan, int mode, const void* W0, void* stream);
+/* n_iter epochs of the loop                                        overiva.py:138-190 */
+int oiva_plan_iterate(oiva_plan_t* plan, int n_iter, void* stream);
+/* the two halves of one epoch, for the frequency-sharded driver: power() leaves the partial
+ * statistic summed over this plan's bins in r2 (oiva_plan_r2()); the caller all-reduces it across
+ * ranks; update() then runs source model + weighted covariance + IP sweep from r2. */
+int oiva_plan_power(oiva_plan_t* plan, void* stream);
+int oiva_plan_update(oiva_plan_t* plan, void* stream);
+double* oiva_plan_r2(oiva_plan_t* plan);   /* (B,K,Tp) doubles */
+size_t oiva_plan_r2_elems(const oiva_plan_t* plan);
+/* final demix (+ projection back) into Y (B,T,F,K)                 overiva.py:192-199 */
+int oiva_plan_output(oiva_plan_t* plan, int proj_back, void* Y, void* stream);
+/* copy the filters W (B,F,M,K) c128 (contiguous) out of What       overiva.py:201-202 */
+int oiva_plan_filters(oiva_plan_t* plan, void* W, void* stream);
+/* device pointers into the workspace (for tests and wrappers) */
+void* oiva_plan_what(oiva_plan_t* plan);   /* (R,M,M) c128 */
+void* oiva_plan_cov(oiva_plan_t* plan);    /* (R,M,M) c128 */
+void* oiva_plan_planar(oiva_plan_t* plan); /* planar rows  */
+int* oiva_plan_status_ptr(oiva_plan_t* plan);
+/* synchronises the stream and returns the status word (0 = fine) */
+int oiva_plan_status(oiva_plan_t* plan, void* stream);
+/* number of kernels launched by this plan since creation (bench.py's gpu_launches) */
+long long oiva_plan_launch_count(const oiva_plan_t* plan);
+
+/* Convenience: the complete call with HOST buffers (pinned or pageable): H2D of X (B,T,F,M), the loop,
+ * D2H of Y (B,T,F,K) [and W (B,F,M,K) c128 if W_host != NULL].  Allocates and frees its own device memory.
+ * Returns the status word (>0) on numerical failure. */
+int oiva_overiva_host(const void* X_host, void* Y_host, void* W_host, const void* W0_host,
+                      const oiva_plan_desc* desc, int n_iter, int proj_back, int init_mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OVERIVA_B200_H */

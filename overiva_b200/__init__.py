@@ -1,0 +1,13 @@
+"""overiva_b200 -- B200-native (sm_100a) implementation of the OverIVA / AuxIVA / OGIVE demixing loop.
+
+Drop-in entry points (same signatures as onolab-tmu/overiva):
+
+    from overiva_b200 import overiva, auxiva, auxiva_pca, ogive
+
+plus ``overiva_batch`` for many independent mixtures and ``overiva_b200.distributed`` for the
+multi-GPU drivers.  See DESIGN.md / INTEGRATION.md.
+"""
+from .core import DemixPlan, auxiva, auxiva_pca, ogive, overiva, overiva_batch  # noqa: F401
+
+__all__ = ["overiva", "auxiva", "auxiva_pca", "ogive", "overiva_batch", "DemixPlan"]
+__version__ = "0.1.0"

@@ -1,0 +1,437 @@
+"""Python host layer: the reference's entry points on top of the CUDA library.
+
+``overiva``, ``auxiva_pca`` and ``ogive`` keep the exact signatures, argument meaning, return shapes
+and error behaviour of ``overiva.py:28-38``, ``auxiva_pca.py:30`` and ``ive.py:33-45`` of
+onolab-tmu/overiva; ``auxiva`` is ``overiva`` with ``n_src`` omitted (``overiva_oneshot.py:301-309``).
+Inputs may be numpy arrays (result: numpy), CPU torch tensors (result: CPU torch tensors, pinned when
+the input is pinned) or CUDA torch tensors (result: CUDA tensors, nothing leaves the device).
+
+All arithmetic happens in hand-written sm_100a kernels reached through the C ABI
+(``include/overiva_b200.h``); PyTorch only provides device memory, streams and (for the multi-GPU
+drivers) ``torch.distributed``.  There is no CPU path: without a CUDA device or without the built
+library every function raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+_MODELS = {"laplace": L.MODEL_LAPLACE, "gauss": L.MODEL_GAUSS}
+_OGIVE_MODELS = {"laplace": L.MODEL_OGIVE_LAPLACE, "gauss": L.MODEL_OGIVE_GAUSS}
+
+
+def _require_cuda(device=None):
+    if not torch.cuda.is_available():
+        raise RuntimeError("overiva_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class _Input:
+    """Normalises the three accepted input kinds to a contiguous CUDA tensor and remembers how to
+    hand results back in the caller's kind."""
+
+    def __init__(self, X, device=None):
+        self.kind = "numpy"
+        self.pinned = False
+        if isinstance(X, torch.Tensor):
+            self.kind = "cuda" if X.is_cuda else "cpu"
+            self.pinned = (not X.is_cuda) and X.is_pinned()
+            t = X
+        else:
+            X = np.asarray(X)
+            if not np.iscomplexobj(X):
+                raise TypeError("X must be a complex STFT array, got dtype %s" % X.dtype)
+            if X.dtype not in (np.complex128, np.complex64):
+                X = X.astype(np.complex128)
+            t = torch.from_numpy(np.ascontiguousarray(X))
+        if t.dtype not in (torch.complex128, torch.complex64):
+            raise TypeError("X must be complex64 or complex128, got %s" % t.dtype)
+        self.device = _require_cuda(t.device if t.is_cuda else device)
+        self.dev = t.to(self.device, non_blocking=True).contiguous()
+        self.dtype = t.dtype
+
+    def give_back(self, t, dtype=None):
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        if self.kind == "cuda":
+            return t
+        if self.pinned:
+            out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            out.copy_(t, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        else:
+            out = t.cpu()
+        return out.numpy() if self.kind == "numpy" else out
+
+
+class DemixPlan:
+    """Thin owner of an ``oiva_plan_t`` plus its workspace tensor (one per (shape, K, model, dtype))."""
+
+    def __init__(self, n_batch, n_frames, n_freq, n_chan, n_src, model, dtype, device, n_freq_total=0):
+        self.lib = L.load()
+        self.device = torch.device(device)
+        self.B, self.T, self.F, self.M, self.K = n_batch, n_frames, n_freq, n_chan, n_src
+        self.cdtype = dtype
+        self.code = L.C64 if dtype == torch.complex64 else L.C128
+        self.desc = L.PlanDesc(n_batch, n_frames, n_freq, n_freq_total, n_chan, n_src, model, self.code, 0)
+        h = C.c_void_p()
+        L.check(self.lib.oiva_plan_create(C.byref(h), C.byref(self.desc)), "oiva_plan_create")
+        self.h = h
+        nbytes = self.lib.oiva_plan_workspace_bytes(h)
+        with torch.cuda.device(self.device):
+            self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        L.check(self.lib.oiva_plan_bind(h, _ptr(self.ws), nbytes), "oiva_plan_bind")
+        self.Tp = self.lib.oiva_frame_pitch(n_frames, n_chan, self.code)
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h is not None and getattr(self, "lib", None) is not None:
+            self.lib.oiva_plan_destroy(h)
+
+    # -- views into the workspace -----------------------------------------------------------------
+    def _view(self, ptr, nbytes, dtype, shape):
+        off = ptr - self.ws.data_ptr()
+        return self.ws[off : off + nbytes].view(dtype).view(shape)
+
+    @property
+    def r2(self):
+        """(B, K, Tp) float64: the source-model statistic summed over this plan's bins (all-reduced by the
+        frequency-sharded driver between ``power()`` and ``update()``)."""
+        n = self.lib.oiva_plan_r2_elems(self.h)
+        return self._view(self.lib.oiva_plan_r2(self.h), n * 8, torch.float64, (self.B, self.K, self.Tp))
+
+    @property
+    def what(self):
+        n = self.B * self.F * self.M * self.M
+        return self._view(self.lib.oiva_plan_what(self.h), n * 16, torch.complex128, (self.B, self.F, self.M, self.M))
+
+    @property
+    def cov(self):
+        n = self.B * self.F * self.M * self.M
+        return self._view(self.lib.oiva_plan_cov(self.h), n * 16, torch.complex128, (self.B, self.F, self.M, self.M))
+
+    @property
+    def planar_ptr(self):
+        return self.lib.oiva_plan_planar(self.h)
+
+    # -- steps ------------------------------------------------------------------------------------
+    def load(self, X):
+        assert X.is_cuda and X.is_contiguous() and X.dtype == self.cdtype
+        assert tuple(X.shape) == (self.B, self.T, self.F, self.M), (tuple(X.shape), (self.B, self.T, self.F, self.M))
+        L.check(self.lib.oiva_plan_load(self.h, _ptr(X), _stream_ptr(self.device)), "oiva_plan_load")
+
+    def adopt_planar(self):
+        L.check(self.lib.oiva_plan_adopt_planar(self.h, _stream_ptr(self.device)), "oiva_plan_adopt_planar")
+
+    def init(self, mode, W0=None):
+        if W0 is not None:
+            assert W0.is_cuda and W0.is_contiguous() and W0.dtype == torch.complex128
+            assert tuple(W0.shape) == (self.B, self.F, self.M, self.K)
+        L.check(self.lib.oiva_plan_init(self.h, mode, _ptr(W0), _stream_ptr(self.device)), "oiva_plan_init")
+
+    def iterate(self, n_iter):
+        if n_iter > 0:
+            L.check(self.lib.oiva_plan_iterate(self.h, int(n_iter), _stream_ptr(self.device)), "oiva_plan_iterate")
+
+    def power(self):
+        L.check(self.lib.oiva_plan_power(self.h, _stream_ptr(self.device)), "oiva_plan_power")
+
+    def update(self):
+        L.check(self.lib.oiva_plan_update(self.h, _stream_ptr(self.device)), "oiva_plan_update")
+
+    def output(self, proj_back, out=None):
+        if out is None:
+            out = torch.empty((self.B, self.T, self.F, self.K), dtype=self.cdtype, device=self.device)
+        L.check(self.lib.oiva_plan_output(self.h, int(bool(proj_back)), _ptr(out), _stream_ptr(self.device)),
+                "oiva_plan_output")
+        return out
+
+    def filters(self):
+        W = torch.empty((self.B, self.F, self.M, self.K), dtype=torch.complex128, device=self.device)
+        L.check(self.lib.oiva_plan_filters(self.h, _ptr(W), _stream_ptr(self.device)), "oiva_plan_filters")
+        return W
+
+    def status(self):
+        return self.lib.oiva_plan_status(self.h, _stream_ptr(self.device))
+
+    def raise_on_failure(self):
+        """The reference raises ``numpy.linalg.LinAlgError('Singular matrix')`` out of overiva.py:98,182."""
+        st = self.status()
+        if st < 0:
+            L.check(st, "oiva_plan_status")
+        if st & L.STATUS_SINGULAR:
+            raise np.linalg.LinAlgError("Singular matrix")
+        if st & L.STATUS_NONFINITE:
+            raise np.linalg.LinAlgError("non-finite value in the demixing matrices")
+
+    @property
+    def launches(self):
+        return int(self.lib.oiva_plan_launch_count(self.h))
+
+
+def _model_code(model, table=_MODELS):
+    try:
+        return table[model]
+    except (KeyError, TypeError):
+        # the reference silently leaves r at zero for an unknown model string and returns NaNs;
+        # failing loudly is the one deliberate deviation from it
+        raise ValueError("unknown source model %r (expected 'laplace' or 'gauss')" % (model,))
+
+
+def _prepare_W0(W0, B, F, M, K, device):
+    """overiva.py:116-117: ``W[:, :, :] = W0`` broadcasts W0 into (F, M, K)."""
+    if isinstance(W0, torch.Tensor):
+        W0 = W0.detach().cpu().numpy()
+    W0 = np.asarray(W0)
+    W0 = np.broadcast_to(W0, (B, F, M, K)) if W0.ndim == 4 else np.broadcast_to(W0, (F, M, K))[None].repeat(B, 0)
+    return torch.from_numpy(np.ascontiguousarray(W0.astype(np.complex128))).to(device)
+
+
+def _run_overiva(Xd, n_src, n_iter, proj_back, W0, model, init_eig, return_filters, callback, cb_wrap,
+                 n_freq_total=0):
+    """Xd: (B, T, F, M) CUDA tensor.  Returns (Y (B,T,F,K), W (B,F,M,K) or None, plan)."""
+    B, T, F, M = Xd.shape
+    if n_src is None:
+        n_src = M  # overiva.py:83-84
+    n_src = int(n_src)
+    if not (1 <= n_src <= M):
+        raise ValueError("n_src=%d must be in 1..n_chan=%d" % (n_src, M))
+    if M > 16:
+        raise ValueError("at most 16 channels are supported, got %d" % M)
+    plan = DemixPlan(B, T, F, M, n_src, _model_code(model), Xd.dtype, Xd.device, n_freq_total)
+    plan.load(Xd)
+    if W0 is not None:
+        plan.init(L.INIT_W0, _prepare_W0(W0, B, F, M, n_src, Xd.device))
+    else:
+        plan.init(L.INIT_EIG if init_eig else L.INIT_EYE)
+    if callback is None:
+        plan.iterate(n_iter)
+    else:
+        # overiva.py:142-148: every 10th epoch, before that epoch's update, with the projected-back estimate
+        epoch = 0
+        while epoch < n_iter:
+            if epoch % 10 == 0:
+                plan.raise_on_failure()
+                callback(cb_wrap(plan.output(proj_back)))
+            step = min(10 - epoch % 10, n_iter - epoch)
+            plan.iterate(step)
+            epoch += step
+    Y = plan.output(proj_back)
+    W = plan.filters() if return_filters else None
+    plan.raise_on_failure()
+    return Y, W, plan
+
+
+def overiva(X, n_src=None, n_iter=20, proj_back=True, W0=None, model="laplace", init_eig=False,
+            return_filters=False, callback=None):
+    """Drop-in for ``overiva.overiva`` (overiva.py:28-204).
+
+    X: (n_frames, n_freq, n_chan) complex.  Returns Y (n_frames, n_freq, n_src) of X's dtype and, if
+    ``return_filters``, also W (n_freq, n_chan, n_src).
+    """
+    if getattr(X, "ndim", 0) != 3:
+        raise ValueError("X must have shape (n_frames, n_freq, n_chan)")
+    inp = _Input(X)
+    with torch.cuda.device(inp.device):
+        Y, W, _ = _run_overiva(inp.dev[None], n_src, n_iter, proj_back, W0, model, init_eig, return_filters,
+                               callback, lambda y: inp.give_back(y[0]))
+        Yo = inp.give_back(Y[0])
+        if return_filters:
+            return Yo, inp.give_back(W[0], inp.dtype)
+        return Yo
+
+
+def auxiva(X, n_iter=20, proj_back=True, W0=None, model="laplace", init_eig=False, return_filters=False,
+           callback=None):
+    """Determined AuxIVA: ``overiva`` with ``n_src`` omitted (README.md:178-180, overiva_oneshot.py:301-309)."""
+    return overiva(X, None, n_iter, proj_back, W0, model, init_eig, return_filters, callback)
+
+
+def overiva_batch(X, n_src=None, n_iter=20, proj_back=True, W0=None, model="laplace", init_eig=False,
+                  return_filters=False):
+    """Many independent mixtures at once: X (B, n_frames, n_freq, n_chan) -> Y (B, n_frames, n_freq, n_src)
+    [, W (B, n_freq, n_chan, n_src)].  The role of the reference's task farm (``overiva_sim.py`` +
+    ``rrtools``) for mixtures of one shape; every mixture is processed exactly as ``overiva`` would."""
+    if getattr(X, "ndim", 0) != 4:
+        raise ValueError("X must have shape (n_batch, n_frames, n_freq, n_chan)")
+    inp = _Input(X)
+    with torch.cuda.device(inp.device):
+        Y, W, _ = _run_overiva(inp.dev, n_src, n_iter, proj_back, W0, model, init_eig, return_filters, None, None)
+        Yo = inp.give_back(Y)
+        if return_filters:
+            return Yo, inp.give_back(W, inp.dtype)
+        return Yo
+
+
+def auxiva_pca(X, n_src=None, **kwargs):
+    """Drop-in for ``auxiva_pca.auxiva_pca`` (auxiva_pca.py:30-92): PCA to ``n_src`` channels, determined
+    AuxIVA on the reduced signal, projection back onto the ORIGINAL microphone 0.
+
+    As in the reference, ``proj_back`` must be present in kwargs (it is popped unconditionally,
+    auxiva_pca.py:86, and the projection back is always applied), the remaining kwargs go to ``overiva``,
+    and ``return_filters=True`` is not supported (the reference fails on it with a TypeError).
+    """
+    if getattr(X, "ndim", 0) != 3:
+        raise ValueError("X must have shape (n_frames, n_freq, n_chan)")
+    kwargs = dict(kwargs)
+    kwargs.pop("proj_back")  # KeyError if absent, exactly like auxiva_pca.py:86
+    if kwargs.pop("return_filters", False):
+        raise TypeError("auxiva_pca does not support return_filters=True")
+    n_iter = kwargs.pop("n_iter", 20)
+    W0 = kwargs.pop("W0", None)
+    model = kwargs.pop("model", "laplace")
+    init_eig = kwargs.pop("init_eig", False)
+    callback = kwargs.pop("callback", None)
+    if "n_src" in kwargs or kwargs:
+        raise TypeError("overiva() got an unexpected keyword argument %r" % sorted(kwargs)[0])
+    inp = _Input(X)
+    T, F, M = inp.dev.shape
+    K = M if n_src is None else int(n_src)
+    if not (1 <= K <= M):
+        raise ValueError("n_src=%d must be in 1..n_chan=%d" % (K, M))
+    lib = L.load()
+    dev = inp.device
+    with torch.cuda.device(dev):
+        st = _stream_ptr(dev)
+        code = L.C64 if inp.dtype == torch.complex64 else L.C128
+        full = DemixPlan(1, T, F, M, K, _model_code(model), inp.dtype, dev)
+        full.load(inp.dev[None])
+        if K < M:
+            # eigh of the input covariance, keep the K principal eigenvectors      auxiva_pca.py:71-81
+            evals = torch.empty((F, M), dtype=torch.float64, device=dev)
+            evecs = torch.empty((F, M, M), dtype=torch.complex128, device=dev)
+            L.check(lib.oiva_eigh(_ptr(full.cov), _ptr(evals), _ptr(evecs), lib.oiva_plan_status_ptr(full.h), F, M, 0,
+                                  st), "oiva_eigh")
+            E = evecs[:, :, M - K :].contiguous()
+            red = DemixPlan(1, T, F, K, K, _model_code(model), inp.dtype, dev)
+            L.check(lib.oiva_project_rows(full.planar_ptr, _ptr(E), red.planar_ptr, 1, T, F, M, K, code, st),
+                    "oiva_project_rows")
+            red.adopt_planar()
+        else:
+            E, red = None, full
+        if W0 is not None:
+            red.init(L.INIT_W0, _prepare_W0(W0, 1, F, K, K, dev))
+        else:
+            red.init(L.INIT_EIG if init_eig else L.INIT_EYE)
+        epoch = 0
+        if callback is None:
+            red.iterate(n_iter)
+        else:
+            while epoch < n_iter:  # inner overiva runs with proj_back=False (auxiva_pca.py:87)
+                if epoch % 10 == 0:
+                    red.raise_on_failure()
+                    callback(inp.give_back(red.output(False)[0]))
+                step = min(10 - epoch % 10, n_iter - epoch)
+                red.iterate(step)
+                epoch += step
+        Wr = red.filters()  # (1, F, K, K)
+        if E is not None:
+            Wfull = torch.empty((F, M, K), dtype=torch.complex128, device=dev)
+            L.check(lib.oiva_compose_filters(_ptr(E), _ptr(Wr), _ptr(Wfull), F, M, K, K, st), "oiva_compose_filters")
+        else:
+            Wfull = Wr[0].contiguous()
+        # projection back on the original mic 0 through the full covariance        auxiva_pca.py:89-90
+        Weff = torch.empty((F, M, K), dtype=torch.complex128, device=dev)
+        L.check(lib.oiva_projback_filters(_ptr(Wfull), K, _ptr(full.cov), _ptr(Weff), F, M, K, 1, st),
+                "oiva_projback_filters")
+        Y = torch.empty((1, T, F, K), dtype=inp.dtype, device=dev)
+        L.check(lib.oiva_demix_output(full.planar_ptr, _ptr(Weff), _ptr(Y), 1, T, F, M, K, code, st),
+                "oiva_demix_output")
+        red.raise_on_failure()
+        if red is not full:
+            full.raise_on_failure()
+        return inp.give_back(Y[0])
+
+
+def ogive(X, n_iter=4000, step_size=0.1, tol=1e-3, update="demix", proj_back=True, W0=None, model="laplace",
+          init_eig=False, return_filters=False, callback=None):
+    """Drop-in for ``ive.ogive`` (ive.py:33-256): orthogonally constrained gradient extraction of ONE source.
+
+    Returns Y (n_frames, n_freq, 1) and, if ``return_filters``, w (n_freq, n_chan, 1).  The per-iteration
+    statistic is obtained from the shared weighted-covariance kernel (x_psi = V w / (w^H V w)); the stopping
+    rule ``max_f ||delta_f|| < tol`` (ive.py:238-241) is evaluated every iteration, so the loop ends at the
+    same epoch as the reference.
+    """
+    if getattr(X, "ndim", 0) != 3:
+        raise ValueError("X must have shape (n_frames, n_freq, n_chan)")
+    inp = _Input(X)
+    T, F, M = inp.dev.shape
+    lib = L.load()
+    dev = inp.device
+    mcode = _model_code(model, _OGIVE_MODELS)
+    with torch.cuda.device(dev):
+        st = _stream_ptr(dev)
+        code = L.C64 if inp.dtype == torch.complex64 else L.C128
+        plan = DemixPlan(1, T, F, M, 1, mcode, inp.dtype, dev)
+        plan.load(inp.dev[None])
+        status = lib.oiva_plan_status_ptr(plan.h)
+        Cx = plan.cov  # (1, F, M, M)
+        c128 = dict(dtype=torch.complex128, device=dev)
+        Cinv = torch.empty((F, M, M), **c128)
+        cnorm = torch.empty((F,), dtype=torch.float64, device=dev)
+        L.check(lib.oiva_ogive_setup(_ptr(Cx), _ptr(Cinv), _ptr(cnorm), status, F, M, st), "oiva_ogive_setup")
+        w = torch.zeros((F, M), **c128)
+        a = torch.zeros((F, M), **c128)
+        lam = torch.zeros((F,), dtype=torch.float64, device=dev)
+        if W0 is not None:  # ive.py:129-130: w[:, :] = W0 with w of shape (F, M, 1)
+            w.copy_(_prepare_W0(W0, 1, F, M, 1, dev)[0, :, :, 0])
+        elif init_eig:  # ive.py:110-123: the un-conjugated leading eigenvector of np.linalg.eig
+            evals = torch.empty((F, M), dtype=torch.float64, device=dev)
+            evecs = torch.empty((F, M, M), **c128)
+            L.check(lib.oiva_eigh(_ptr(Cx), _ptr(evals), _ptr(evecs), status, F, M, 1, st), "oiva_eigh")
+            w.copy_(evecs[:, :, M - 1])
+        else:
+            w[:, 0] = 1.0  # ive.py:125-127
+        L.check(lib.oiva_ogive_a_from_w(_ptr(w), _ptr(a), _ptr(Cx), F, M, st), "oiva_ogive_a_from_w")  # ive.py:168
+        do_a = torch.full((F,), 1 if update == "mix" else 0, dtype=torch.uint8, device=dev)  # ive.py:170-175
+        nch = lib.oiva_power_chunks(1, F)
+        Tp = plan.Tp
+        r2part = torch.empty((nch, Tp), dtype=torch.float64, device=dev)
+        phi = torch.empty((Tp,), dtype=torch.float64, device=dev)
+        V = torch.empty((F, M, M), **c128)
+        dmax = torch.zeros((1,), dtype=torch.float64, device=dev)
+
+        def project(wcur):
+            Weff = torch.empty((F, M, 1), **c128)
+            L.check(lib.oiva_projback_filters(_ptr(wcur), 1, _ptr(Cx), _ptr(Weff), F, M, 1, int(bool(proj_back)), st),
+                    "oiva_projback_filters")
+            Y = torch.empty((1, T, F, 1), dtype=inp.dtype, device=dev)
+            L.check(lib.oiva_demix_output(plan.planar_ptr, _ptr(Weff), _ptr(Y), 1, T, F, M, 1, code, st),
+                    "oiva_demix_output")
+            return Y[0]
+
+        for epoch in range(int(n_iter)):
+            if update == "switching" and epoch % 10 == 0:  # ive.py:187-188
+                L.check(lib.oiva_ogive_switching(_ptr(a), _ptr(Cx), _ptr(cnorm), _ptr(do_a), F, M, st),
+                        "oiva_ogive_switching")
+            if callback is not None and epoch % 100 == 0:  # ive.py:194-200
+                callback(inp.give_back(project(w)))
+            L.check(lib.oiva_demix_power(plan.planar_ptr, _ptr(w), 1, _ptr(r2part), nch, 1, T, F, M, 1, code, st),
+                    "oiva_demix_power")
+            L.check(lib.oiva_source_model(_ptr(r2part), nch, _ptr(phi), None, 1, T, M, 1, F, mcode, code, st),
+                    "oiva_source_model")
+            L.check(lib.oiva_weighted_cov(plan.planar_ptr, _ptr(phi), _ptr(V), 1, T, F, M, 1, code, st),
+                    "oiva_weighted_cov")
+            dmax.zero_()
+            L.check(lib.oiva_ogive_update(_ptr(w), _ptr(a), _ptr(lam), _ptr(V), _ptr(Cx), _ptr(Cinv), _ptr(do_a),
+                                          float(step_size), _ptr(dmax), F, M, st), "oiva_ogive_update")
+            if float(dmax.item()) < tol:  # ive.py:238-241 (one scalar D2H per epoch)
+                break
+        Y = project(w)
+        plan.raise_on_failure()
+        Yo = inp.give_back(Y)
+        if return_filters:
+            return Yo, inp.give_back(w[:, :, None].contiguous(), inp.dtype)
+        return Yo

@@ -1,0 +1,84 @@
+// C entry point of the weighted-covariance kernel (include/overiva_b200.h: oiva_weighted_cov).
+#include <stdlib.h>
+
+#include "cov.cuh"
+
+namespace oiva {
+#define OIVA_DECL(M) int cov_launch_m##M(int dtype, int KC, int use_tma, const CovParams& p, cudaStream_t st);
+OIVA_DECL(1) OIVA_DECL(2) OIVA_DECL(3) OIVA_DECL(4) OIVA_DECL(5) OIVA_DECL(6) OIVA_DECL(7) OIVA_DECL(8)
+OIVA_DECL(9) OIVA_DECL(10) OIVA_DECL(11) OIVA_DECL(12) OIVA_DECL(13) OIVA_DECL(14) OIVA_DECL(15) OIVA_DECL(16)
+#undef OIVA_DECL
+
+// phi == NULL: a device buffer of ones (grown on demand, per device) stands in for the weights
+static double* g_ones[64] = {nullptr};
+static size_t g_ones_n[64] = {0};
+__global__ void k_fill(double* p, size_t n, double v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+static int get_ones(size_t n, cudaStream_t st, const double** out) {
+    int dev = 0;
+    OIVA_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (g_ones_n[dev] < n) {
+        // a previous, smaller buffer may still be in use by queued kernels: keep it alive (tiny leak by design)
+        double* q = nullptr;
+        OIVA_CUDA_CHECK(cudaMalloc(&q, n * sizeof(double)));
+        k_fill<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q, n, 1.0);
+        OIVA_LAUNCH_CHECK();
+        g_ones[dev] = q;
+        g_ones_n[dev] = n;
+    }
+    *out = g_ones[dev];
+    return OIVA_OK;
+}
+}  // namespace oiva
+
+extern "C" int oiva_weighted_cov(const void* Xp, const double* phi, void* V, int n_batch, int n_frames, int n_freq,
+                                 int n_chan, int n_src, int dtype, void* stream) {
+    using namespace oiva;
+    OIVA_REQUIRE(Xp && V, "oiva_weighted_cov: null pointer");
+    OIVA_REQUIRE(n_batch > 0 && n_frames > 0 && n_freq > 0 && n_chan >= 1 && n_chan <= OIVA_MAX_M && n_src >= 1,
+                 "oiva_weighted_cov: bad shape B=%d T=%d F=%d M=%d K=%d", n_batch, n_frames, n_freq, n_chan, n_src);
+    OIVA_REQUIRE(phi || n_src == 1, "oiva_weighted_cov: phi == NULL needs n_src == 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    CovParams p;
+    p.Xp = Xp;
+    p.V = (double*)V;
+    p.L = oiva_make_layout(n_frames, n_chan, dtype);
+    p.R = n_batch * n_freq;
+    p.F = n_freq;
+    p.K = n_src;
+    p.invT = 1.0 / (double)n_frames;
+    p.nsplit = 1;
+    p.stages = 3;
+    p.xpitch = p.ppitch = 0;
+    if (phi) {
+        p.phi = phi;
+    } else {
+        const double* ones = nullptr;
+        int rc = get_ones((size_t)p.L.frame_pitch(), st, &ones);
+        if (rc) return rc;
+        p.phi = ones;
+        p.F = p.R + 1;  // every row maps to "mixture 0": the ones buffer holds one (K=1, Tp) block
+    }
+    const char* env = getenv("OIVA_COV_NO_TMA");
+    const int use_tma = !(env && *env && *env != '0');
+    int k0 = 0;
+    while (k0 < n_src) {
+        int rem = n_src - k0;
+        int KC = rem >= 4 ? 4 : (rem >= 2 ? 2 : 1);
+        p.k0 = k0;
+        int rc = OIVA_ERR_INVALID;
+        switch (n_chan) {
+#define OIVA_CASE(M) case M: rc = cov_launch_m##M(dtype, KC, use_tma, p, st); break;
+            OIVA_CASE(1) OIVA_CASE(2) OIVA_CASE(3) OIVA_CASE(4) OIVA_CASE(5) OIVA_CASE(6) OIVA_CASE(7) OIVA_CASE(8)
+            OIVA_CASE(9) OIVA_CASE(10) OIVA_CASE(11) OIVA_CASE(12) OIVA_CASE(13) OIVA_CASE(14) OIVA_CASE(15)
+            OIVA_CASE(16)
+#undef OIVA_CASE
+        }
+        if (rc) return rc;
+        k0 += KC;
+    }
+    return OIVA_OK;
+}

@@ -1,0 +1,304 @@
+// The whole overiva() call on device pointers: a plan carves one caller-provided workspace and sequences
+// the kernels (include/overiva_b200.h, "Plan" section).  Mirrors overiva.py:80-204 step by step.
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+struct oiva_plan {
+    oiva_plan_desc d;
+    int n_freq_total;
+    long long R;
+    RowLayout L;
+    int Tp, NCH;
+    int es;  // bytes per real element of X / Y
+    // workspace offsets
+    size_t off_xp, off_c, off_what, off_v, off_weff, off_r2part, off_r2, off_phi, off_wscale, off_evals, off_status;
+    size_t ws_bytes;
+    unsigned char* ws;
+    long long launches;
+    bool loaded, inited;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" int oiva_plan_create(oiva_plan_t** out, const oiva_plan_desc* desc) {
+    OIVA_REQUIRE(out && desc, "oiva_plan_create: null pointer");
+    const oiva_plan_desc& d = *desc;
+    OIVA_REQUIRE(d.n_batch > 0 && d.n_batch <= 65535 && d.n_frames > 0 && d.n_freq > 0, "oiva_plan_create: bad shape B=%d T=%d F=%d",
+                 d.n_batch, d.n_frames, d.n_freq);
+    OIVA_REQUIRE(d.n_chan >= 1 && d.n_chan <= OIVA_MAX_M, "oiva_plan_create: n_chan=%d not in 1..16", d.n_chan);
+    OIVA_REQUIRE(d.n_src >= 1 && d.n_src <= d.n_chan, "oiva_plan_create: n_src=%d not in 1..n_chan=%d", d.n_src,
+                 d.n_chan);
+    OIVA_REQUIRE(d.dtype == OIVA_C128 || d.dtype == OIVA_C64, "oiva_plan_create: bad dtype %d", d.dtype);
+    OIVA_REQUIRE(d.model >= OIVA_MODEL_LAPLACE && d.model <= OIVA_MODEL_OGIVE_GAUSS, "oiva_plan_create: bad model %d",
+                 d.model);
+    OIVA_REQUIRE((long long)d.n_batch * d.n_freq < (1ll << 31), "oiva_plan_create: too many rows");
+    oiva_plan* p = (oiva_plan*)calloc(1, sizeof(oiva_plan));
+    if (!p) {
+        oiva_set_error("oiva_plan_create: out of host memory");
+        return OIVA_ERR_NOMEM;
+    }
+    p->d = d;
+    p->n_freq_total = d.n_freq_total > 0 ? d.n_freq_total : d.n_freq;
+    p->R = (long long)d.n_batch * d.n_freq;
+    p->L = oiva_make_layout(d.n_frames, d.n_chan, d.dtype);
+    p->Tp = p->L.frame_pitch();
+    p->NCH = oiva_power_chunks(d.n_batch, d.n_freq);
+    p->es = d.dtype == OIVA_C64 ? 4 : 8;
+    const size_t M = d.n_chan, K = d.n_src, R = (size_t)p->R, B = d.n_batch;
+    size_t o = 0;
+    p->off_xp = o;      o += align_up(R * p->L.row_elems() * p->es);
+    p->off_c = o;       o += align_up(R * M * M * 16);
+    p->off_what = o;    o += align_up(R * M * M * 16);
+    p->off_v = o;       o += align_up(R * (K > 1 ? K : 1) * M * M * 16);  // also holds eigenvectors at init
+    p->off_weff = o;    o += align_up(R * M * K * 16);
+    p->off_r2part = o;  o += align_up(B * p->NCH * K * p->Tp * 8);
+    p->off_r2 = o;      o += align_up(B * K * p->Tp * 8);
+    p->off_phi = o;     o += align_up(B * K * p->Tp * 8);
+    p->off_wscale = o;  o += align_up(B * K * 8);
+    p->off_evals = o;   o += align_up(R * M * 8);
+    p->off_status = o;  o += align_up(16);
+    p->ws_bytes = o;
+    *out = p;
+    return OIVA_OK;
+}
+
+extern "C" void oiva_plan_destroy(oiva_plan_t* plan) { free(plan); }
+
+extern "C" size_t oiva_plan_workspace_bytes(const oiva_plan_t* plan) { return plan ? plan->ws_bytes : 0; }
+
+extern "C" int oiva_plan_bind(oiva_plan_t* plan, void* workspace, size_t bytes) {
+    OIVA_REQUIRE(plan && workspace, "oiva_plan_bind: null pointer");
+    OIVA_REQUIRE(bytes >= plan->ws_bytes, "oiva_plan_bind: workspace %zu < %zu bytes", bytes, plan->ws_bytes);
+    OIVA_REQUIRE(((uintptr_t)workspace & 255) == 0, "oiva_plan_bind: workspace must be 256-byte aligned");
+    plan->ws = (unsigned char*)workspace;
+    plan->loaded = plan->inited = false;
+    return OIVA_OK;
+}
+
+#define PLAN_READY(p, who)                                                        \
+    OIVA_REQUIRE((p) != nullptr, who ": null plan");                              \
+    if (!(p)->ws) {                                                               \
+        oiva_set_error(who ": no workspace bound");                               \
+        return OIVA_ERR_STATE;                                                    \
+    }
+
+extern "C" void* oiva_plan_what(oiva_plan_t* p) { return (p && p->ws) ? p->ws + p->off_what : nullptr; }
+extern "C" void* oiva_plan_cov(oiva_plan_t* p) { return (p && p->ws) ? p->ws + p->off_c : nullptr; }
+extern "C" void* oiva_plan_planar(oiva_plan_t* p) { return (p && p->ws) ? p->ws + p->off_xp : nullptr; }
+extern "C" int* oiva_plan_status_ptr(oiva_plan_t* p) { return (p && p->ws) ? (int*)(p->ws + p->off_status) : nullptr; }
+extern "C" double* oiva_plan_r2(oiva_plan_t* p) { return (p && p->ws) ? (double*)(p->ws + p->off_r2) : nullptr; }
+extern "C" size_t oiva_plan_r2_elems(const oiva_plan_t* p) {
+    return p ? (size_t)p->d.n_batch * p->d.n_src * p->Tp : 0;
+}
+extern "C" long long oiva_plan_launch_count(const oiva_plan_t* p) { return p ? p->launches : 0; }
+
+extern "C" int oiva_plan_load(oiva_plan_t* p, const void* X, void* stream) {
+    PLAN_READY(p, "oiva_plan_load");
+    OIVA_REQUIRE(X, "oiva_plan_load: null X");
+    const oiva_plan_desc& d = p->d;
+    OIVA_CUDA_CHECK(cudaMemsetAsync(p->ws + p->off_status, 0, 16, (cudaStream_t)stream));
+    int rc = oiva_relayout(X, p->ws + p->off_xp, d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.dtype, stream);
+    if (rc) return rc;
+    // input covariance C = (1/T) sum_t x x^H                                           overiva.py:87
+    rc = oiva_weighted_cov(p->ws + p->off_xp, nullptr, p->ws + p->off_c, d.n_batch, d.n_frames, d.n_freq, d.n_chan, 1,
+                           d.dtype, stream);
+    if (rc) return rc;
+    p->launches += 2;
+    p->loaded = true;
+    p->inited = false;
+    return OIVA_OK;
+}
+
+extern "C" int oiva_plan_adopt_planar(oiva_plan_t* p, void* stream) {
+    PLAN_READY(p, "oiva_plan_adopt_planar");
+    const oiva_plan_desc& d = p->d;
+    OIVA_CUDA_CHECK(cudaMemsetAsync(p->ws + p->off_status, 0, 16, (cudaStream_t)stream));
+    int rc = oiva_weighted_cov(p->ws + p->off_xp, nullptr, p->ws + p->off_c, d.n_batch, d.n_frames, d.n_freq, d.n_chan,
+                               1, d.dtype, stream);
+    if (rc) return rc;
+    p->launches += 1;
+    p->loaded = true;
+    p->inited = false;
+    return OIVA_OK;
+}
+
+extern "C" int oiva_plan_init(oiva_plan_t* p, int mode, const void* W0, void* stream) {
+    PLAN_READY(p, "oiva_plan_init");
+    if (!p->loaded) {
+        oiva_set_error("oiva_plan_init: call oiva_plan_load first");
+        return OIVA_ERR_STATE;
+    }
+    const oiva_plan_desc& d = p->d;
+    int* status = (int*)(p->ws + p->off_status);
+    const void* evecs = nullptr;
+    if (mode == OIVA_INIT_EIG) {
+        // principal eigenvectors of C with np.linalg.eig's phase convention            overiva.py:103-109
+        int rc = oiva_eigh(p->ws + p->off_c, (double*)(p->ws + p->off_evals), p->ws + p->off_v, status, (int)p->R,
+                           d.n_chan, 1, stream);
+        if (rc) return rc;
+        evecs = p->ws + p->off_v;
+        p->launches += 1;
+    }
+    int rc = oiva_init_demix(p->ws + p->off_what, p->ws + p->off_c, W0, evecs, mode, status, (int)p->R, d.n_chan,
+                             d.n_src, stream);
+    if (rc) return rc;
+    p->launches += 1;
+    p->inited = true;
+    return OIVA_OK;
+}
+
+static int plan_power_partials(oiva_plan_t* p, void* stream) {
+    const oiva_plan_desc& d = p->d;
+    int rc = oiva_demix_power(p->ws + p->off_xp, p->ws + p->off_what, d.n_chan, (double*)(p->ws + p->off_r2part), p->NCH,
+                              d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.n_src, d.dtype, stream);
+    if (rc) return rc;
+    p->launches += (d.n_src + 7) / 8;
+    return OIVA_OK;
+}
+
+static int plan_update_from(oiva_plan_t* p, const double* r2src, int nch, void* stream) {
+    const oiva_plan_desc& d = p->d;
+    double* phi = (double*)(p->ws + p->off_phi);
+    double* wscale = (double*)(p->ws + p->off_wscale);
+    int rc = oiva_source_model(r2src, nch, phi, wscale, d.n_batch, d.n_frames, d.n_chan, d.n_src, p->n_freq_total,
+                               d.model, d.dtype, stream);
+    if (rc) return rc;
+    rc = oiva_weighted_cov(p->ws + p->off_xp, phi, p->ws + p->off_v, d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.n_src,
+                           d.dtype, stream);
+    if (rc) return rc;
+    rc = oiva_ip_update(p->ws + p->off_what, p->ws + p->off_v, p->ws + p->off_c, wscale,
+                        (int*)(p->ws + p->off_status), d.n_batch, d.n_freq, d.n_chan, d.n_src, stream);
+    if (rc) return rc;
+    p->launches += 3;
+    return OIVA_OK;
+}
+
+#define PLAN_INITED(p, who)                                                   \
+    PLAN_READY(p, who);                                                       \
+    if (!(p)->inited) {                                                       \
+        oiva_set_error(who ": call oiva_plan_load and oiva_plan_init first"); \
+        return OIVA_ERR_STATE;                                                \
+    }
+
+extern "C" int oiva_plan_iterate(oiva_plan_t* p, int n_iter, void* stream) {
+    PLAN_INITED(p, "oiva_plan_iterate");
+    for (int it = 0; it < n_iter; ++it) {
+        int rc = plan_power_partials(p, stream);
+        if (rc) return rc;
+        rc = plan_update_from(p, (const double*)(p->ws + p->off_r2part), p->NCH, stream);
+        if (rc) return rc;
+    }
+    return OIVA_OK;
+}
+
+extern "C" int oiva_plan_power(oiva_plan_t* p, void* stream) {
+    PLAN_INITED(p, "oiva_plan_power");
+    int rc = plan_power_partials(p, stream);
+    if (rc) return rc;
+    rc = oiva_sum_partials((const double*)(p->ws + p->off_r2part), p->NCH, (double*)(p->ws + p->off_r2), p->d.n_batch,
+                           p->d.n_frames, p->d.n_chan, p->d.n_src, p->d.dtype, stream);
+    if (rc) return rc;
+    p->launches += 1;
+    return OIVA_OK;
+}
+
+extern "C" int oiva_plan_update(oiva_plan_t* p, void* stream) {
+    PLAN_INITED(p, "oiva_plan_update");
+    return plan_update_from(p, (const double*)(p->ws + p->off_r2), 1, stream);
+}
+
+extern "C" int oiva_plan_output(oiva_plan_t* p, int proj_back, void* Y, void* stream) {
+    PLAN_INITED(p, "oiva_plan_output");
+    OIVA_REQUIRE(Y, "oiva_plan_output: null Y");
+    const oiva_plan_desc& d = p->d;
+    int rc = oiva_projback_filters(p->ws + p->off_what, d.n_chan, p->ws + p->off_c, p->ws + p->off_weff, (int)p->R, d.n_chan,
+                                   d.n_src, proj_back, stream);
+    if (rc) return rc;
+    rc = oiva_demix_output(p->ws + p->off_xp, p->ws + p->off_weff, Y, d.n_batch, d.n_frames, d.n_freq, d.n_chan,
+                           d.n_src, d.dtype, stream);
+    if (rc) return rc;
+    p->launches += 2;
+    return OIVA_OK;
+}
+
+extern "C" int oiva_plan_filters(oiva_plan_t* p, void* W, void* stream) {
+    PLAN_INITED(p, "oiva_plan_filters");
+    OIVA_REQUIRE(W, "oiva_plan_filters: null W");
+    const oiva_plan_desc& d = p->d;
+    // plain copy of the W columns: proj_back = 0
+    int rc = oiva_projback_filters(p->ws + p->off_what, d.n_chan, p->ws + p->off_c, W, (int)p->R, d.n_chan, d.n_src, 0, stream);
+    if (rc) return rc;
+    p->launches += 1;
+    return OIVA_OK;
+}
+
+extern "C" int oiva_plan_status(oiva_plan_t* p, void* stream) {
+    PLAN_READY(p, "oiva_plan_status");
+    int h = 0;
+    OIVA_CUDA_CHECK(cudaMemcpyAsync(&h, p->ws + p->off_status, sizeof(int), cudaMemcpyDeviceToHost,
+                                    (cudaStream_t)stream));
+    OIVA_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    return h;
+}
+
+extern "C" int oiva_overiva_host(const void* X_host, void* Y_host, void* W_host, const void* W0_host,
+                                 const oiva_plan_desc* desc, int n_iter, int proj_back, int init_mode) {
+    OIVA_REQUIRE(X_host && Y_host && desc, "oiva_overiva_host: null pointer");
+    OIVA_REQUIRE(init_mode != OIVA_INIT_W0 || W0_host, "oiva_overiva_host: W0 missing");
+    oiva_plan_t* p = nullptr;
+    int rc = oiva_plan_create(&p, desc);
+    if (rc) return rc;
+    const oiva_plan_desc& d = p->d;
+    const size_t ce = d.dtype == OIVA_C64 ? 8 : 16;
+    const size_t xbytes = (size_t)d.n_batch * d.n_frames * d.n_freq * d.n_chan * ce;
+    const size_t ybytes = (size_t)d.n_batch * d.n_frames * d.n_freq * d.n_src * ce;
+    const size_t wbytes = (size_t)p->R * d.n_chan * d.n_src * 16;
+    unsigned char *dX = nullptr, *dY = nullptr, *dW = nullptr, *ws = nullptr;
+    cudaStream_t st = nullptr;
+    int status = OIVA_OK;
+#define HOST_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            oiva_set_error("oiva_overiva_host: %s -> %s", #expr, cudaGetErrorString(_e));           \
+            status = (int)_e;                                                                       \
+            goto done;                                                                              \
+        }                                                                                           \
+    } while (0)
+#define HOST_RC(expr)        \
+    do {                     \
+        status = (expr);     \
+        if (status) goto done; \
+    } while (0)
+    HOST_TRY(cudaStreamCreate(&st));
+    HOST_TRY(cudaMalloc(&dX, xbytes));
+    HOST_TRY(cudaMalloc(&dY, ybytes));
+    HOST_TRY(cudaMalloc(&dW, wbytes));
+    HOST_TRY(cudaMalloc(&ws, p->ws_bytes));
+    HOST_RC(oiva_plan_bind(p, ws, p->ws_bytes));
+    HOST_TRY(cudaMemcpyAsync(dX, X_host, xbytes, cudaMemcpyHostToDevice, st));
+    if (init_mode == OIVA_INIT_W0) HOST_TRY(cudaMemcpyAsync(dW, W0_host, wbytes, cudaMemcpyHostToDevice, st));
+    HOST_RC(oiva_plan_load(p, dX, st));
+    HOST_RC(oiva_plan_init(p, init_mode, init_mode == OIVA_INIT_W0 ? dW : nullptr, st));
+    HOST_RC(oiva_plan_iterate(p, n_iter, st));
+    HOST_RC(oiva_plan_output(p, proj_back, dY, st));
+    HOST_TRY(cudaMemcpyAsync(Y_host, dY, ybytes, cudaMemcpyDeviceToHost, st));
+    if (W_host) {
+        HOST_RC(oiva_plan_filters(p, dW, st));
+        HOST_TRY(cudaMemcpyAsync(W_host, dW, wbytes, cudaMemcpyDeviceToHost, st));
+    }
+    status = oiva_plan_status(p, st);  // synchronises
+done:
+    if (st) cudaStreamSynchronize(st);
+    cudaFree(dX);
+    cudaFree(dY);
+    cudaFree(dW);
+    cudaFree(ws);
+    if (st) cudaStreamDestroy(st);
+    oiva_plan_destroy(p);
+    return status;
+#undef HOST_TRY
+#undef HOST_RC
+}

@@ -1,0 +1,362 @@
+// Per-bin kernels: IP sweep, demixing-matrix initialisation, projection-back scaling, Hermitian eigh.
+// (include/overiva_b200.h: oiva_ip_update, oiva_init_demix, oiva_projback_filters, oiva_eigh,
+//  oiva_compose_filters)
+#include "solve.cuh"
+
+namespace oiva {
+
+constexpr int SOLVE_WARPS = 4;
+
+// ---------------------------------------------------------------------------------------------------
+// IP sweep over the K sources of every bin (overiva.py:161-167 W rescale, :176-190 source loop)
+// ---------------------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(SOLVE_WARPS * 32) k_ip_update(cplx* __restrict__ What, const cplx* __restrict__ V,
+                                                                const cplx* __restrict__ C,
+                                                                const double* __restrict__ wscale, int* status,
+                                                                long long R, int F, int K) {
+    constexpr int G = Grp<M>::G, BINS = Grp<M>::BINS;
+    __shared__ cplx sWall[SOLVE_WARPS * BINS * M * M];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / G, gl = lane % G;
+    const long long row = ((long long)blockIdx.x * SOLVE_WARPS + warp) * BINS + grp;
+    const bool row_ok = row < R;
+    const long long rowc = row_ok ? row : R - 1;
+    cplx* sW = sWall + (size_t)(warp * BINS + grp) * M * M;
+    const bool rv = gl < M;
+
+    if (rv) {
+#pragma unroll
+        for (int c = 0; c < M; ++c) sW[gl * M + c] = What[rowc * M * M + gl * M + c];
+        if (wscale) {
+            const long long b = rowc / F;
+            for (int c = 0; c < K; ++c) sW[gl * M + c] = cscale(sW[gl * M + c], wscale[b * K + c]);
+        }
+    }
+    __syncwarp();
+
+    int singular = 0;
+    for (int s = 0; s < K; ++s) {
+        const cplx* Vs = V + ((size_t)rowc * K + s) * M * M;
+        // row gl of What^H V_s, augmented with e_s
+        cplx A[M + 1];
+#pragma unroll
+        for (int c = 0; c <= M; ++c) A[c] = cmake(0.0, 0.0);
+        if (rv) {
+            for (int j = 0; j < M; ++j) {
+                const cplx a = sW[j * M + gl];
+#pragma unroll
+                for (int c = 0; c < M; ++c) cfmac(A[c], a, ld_nc_c(&Vs[j * M + c]));
+            }
+            if (gl == s) A[M] = cmake(1.0, 0.0);
+        }
+        const int col = gauss_jordan<M, G>(A, M, gl, lane, rv, singular);
+        __syncwarp();
+        if (col >= 0) sW[col * M + s] = A[M];
+        __syncwarp();
+        // normalise: w_s /= sqrt(w_s^H V_s w_s)
+        cplx wi = cmake(0.0, 0.0), u = cmake(0.0, 0.0);
+        if (rv) {
+            wi = sW[gl * M + s];
+#pragma unroll
+            for (int j = 0; j < M; ++j) cfma(u, ld_nc_c(&Vs[gl * M + j]), sW[j * M + s]);
+        }
+        const cplx d = group_sum<G>(cmulc(wi, u));
+        const cplx inv = crecip(csqrt_(d));
+        __syncwarp();
+        if (rv) sW[gl * M + s] = cmul(wi, inv);
+        __syncwarp();
+        if (K < M) update_background<M, G>(sW, C + (size_t)rowc * M * M, K, gl, lane, singular);
+    }
+
+    bool bad = false;
+    if (rv) {
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+            const cplx v = sW[gl * M + c];
+            if (!isfinite(v.x) || !isfinite(v.y)) bad = true;
+            if (row_ok) What[row * M * M + gl * M + c] = v;
+        }
+    }
+    if (row_ok && (singular || bad))
+        atomicOr(status, (singular ? OIVA_STATUS_SINGULAR : 0) | (bad ? OIVA_STATUS_NONFINITE : 0));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// initial W_hat (overiva.py:89-123)
+// ---------------------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(SOLVE_WARPS * 32) k_init_demix(cplx* __restrict__ What, const cplx* __restrict__ C,
+                                                                 const cplx* __restrict__ W0,
+                                                                 const cplx* __restrict__ evecs, int mode, int* status,
+                                                                 long long R, int K) {
+    constexpr int G = Grp<M>::G, BINS = Grp<M>::BINS;
+    __shared__ cplx sWall[SOLVE_WARPS * BINS * M * M];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / G, gl = lane % G;
+    const long long row = ((long long)blockIdx.x * SOLVE_WARPS + warp) * BINS + grp;
+    const bool row_ok = row < R;
+    const long long rowc = row_ok ? row : R - 1;
+    cplx* sW = sWall + (size_t)(warp * BINS + grp) * M * M;
+    const bool rv = gl < M;
+    if (rv) {
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+            cplx v = cmake(0.0, 0.0);
+            if (c < K) {
+                if (mode == OIVA_INIT_W0)
+                    v = W0[((size_t)rowc * M + gl) * K + c];
+                else if (mode == OIVA_INIT_EIG)
+                    v = cconj(evecs[((size_t)rowc * M + gl) * M + (M - K + c)]);
+                else
+                    v = cmake(gl == c ? 1.0 : 0.0, 0.0);
+            }
+            sW[gl * M + c] = v;
+        }
+    }
+    __syncwarp();
+    int singular = 0;
+    if (K < M) {
+        update_background<M, G>(sW, C + (size_t)rowc * M * M, K, gl, lane, singular);
+        if (rv && gl >= K) sW[gl * M + gl] = cmake(-1.0, 0.0);
+        __syncwarp();
+    }
+    if (row_ok && rv) {
+#pragma unroll
+        for (int c = 0; c < M; ++c) What[row * M * M + gl * M + c] = sW[gl * M + c];
+    }
+    if (row_ok && singular) atomicOr(status, OIVA_STATUS_SINGULAR);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// projection back folded into the filters: Weff[:, k] = w_k * z_k, z_k = (w_k^H C e_0)/(w_k^H C w_k)
+// (pyroomacoustics.bss.projection_back as used at overiva.py:197-199); one thread per (row, k)
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_projback_filters(const cplx* __restrict__ What, int wc, const cplx* __restrict__ C,
+                                   cplx* __restrict__ Weff, long long R, int M, int K, int proj_back) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R * K) return;
+    const long long row = i / K;
+    const int k = (int)(i - row * K);
+    const cplx* W = What + (size_t)row * M * wc;
+    const cplx* Cr = C + (size_t)row * M * M;
+    cplx z = cmake(1.0, 0.0);
+    if (proj_back) {
+        cplx num = cmake(0.0, 0.0);
+        double den = 0.0;
+        for (int a = 0; a < M; ++a) {
+            const cplx wa = W[a * wc + k];
+            cfmac(num, wa, Cr[a * M + 0]);
+            cplx cw = cmake(0.0, 0.0);
+            for (int b = 0; b < M; ++b) cfma(cw, Cr[a * M + b], W[b * wc + k]);
+            den += wa.x * cw.x + wa.y * cw.y;  // Re(conj(w_a) (C w)_a)
+        }
+        if (den > 0.0) z = cmake(num.x / den, num.y / den);
+    }
+    for (int a = 0; a < M; ++a) Weff[((size_t)row * M + a) * K + k] = cmul(W[a * wc + k], z);
+}
+
+// Wout (R,M,K) = E (R,M,Kr) @ Wr (R,Kr,Kr)[:, :, :K]  -- auxiva_pca: full-rank filters from the PCA basis
+__global__ void k_compose_filters(const cplx* __restrict__ E, const cplx* __restrict__ Wr, cplx* __restrict__ Wout,
+                                  long long R, int M, int Kr, int K) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R * M * K) return;
+    const long long row = i / (M * K);
+    const int rem = (int)(i - row * M * K);
+    const int m = rem / K, k = rem - m * K;
+    cplx acc = cmake(0.0, 0.0);
+    for (int j = 0; j < Kr; ++j) cfma(acc, E[((size_t)row * M + m) * Kr + j], Wr[((size_t)row * Kr + j) * Kr + k]);
+    Wout[i] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Hermitian eigendecomposition: cyclic Jacobi, one warp per matrix, matrices in shared memory
+// ---------------------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(SOLVE_WARPS * 32) k_eigh(const cplx* __restrict__ C, double* __restrict__ evals,
+                                                           cplx* __restrict__ evecs, int* status, long long R,
+                                                           int lapack_phase) {
+    __shared__ cplx sA[SOLVE_WARPS][M * M];
+    __shared__ cplx sQ[SOLVE_WARPS][M * M];
+    __shared__ int sPerm[SOLVE_WARPS][M];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * SOLVE_WARPS + warp;
+    if (row >= R) return;  // whole warp exits together
+    cplx* A = sA[warp];
+    cplx* Q = sQ[warp];
+    for (int i = lane; i < M * M; i += 32) {
+        A[i] = C[(size_t)row * M * M + i];
+        Q[i] = cmake((i / M == i % M) ? 1.0 : 0.0, 0.0);
+    }
+    __syncwarp();
+    const double eps = 1.1e-16;
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        int rotated = 0;
+        for (int p = 0; p < M - 1; ++p) {
+            for (int q = p + 1; q < M; ++q) {
+                const cplx apq = A[p * M + q];
+                const double app = A[p * M + p].x, aqq = A[q * M + q].x;
+                const double g = hypot(apq.x, apq.y);
+                if (!(g > eps * sqrt(fabs(app * aqq))) || g < 1e-300) continue;  // warp-uniform
+                ++rotated;
+                const cplx ph = cmake(apq.x / g, apq.y / g);
+                const double tau = (aqq - app) / (2.0 * g);
+                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                const double c = 1.0 / sqrt(1.0 + t * t);
+                const double s = t * c;
+                const cplx sphc = cmake(s * ph.x, -s * ph.y);  // s conj(ph)
+                const cplx cphc = cmake(c * ph.x, -c * ph.y);  // c conj(ph)
+                __syncwarp();
+                // A <- A U, Q <- Q U (columns p, q)
+                if (lane < M) {
+                    const int r = lane;
+                    cplx ap = A[r * M + p], aq = A[r * M + q];
+                    A[r * M + p] = csub(cscale(ap, c), cmul(sphc, aq));
+                    A[r * M + q] = cadd(cscale(ap, s), cmul(cphc, aq));
+                    cplx qp = Q[r * M + p], qq = Q[r * M + q];
+                    Q[r * M + p] = csub(cscale(qp, c), cmul(sphc, qq));
+                    Q[r * M + q] = cadd(cscale(qp, s), cmul(cphc, qq));
+                }
+                __syncwarp();
+                // A <- U^H A (rows p, q)
+                if (lane < M) {
+                    const int r = lane;
+                    const cplx sph = cmake(s * ph.x, s * ph.y), cph = cmake(c * ph.x, c * ph.y);
+                    cplx ap = A[p * M + r], aq = A[q * M + r];
+                    A[p * M + r] = csub(cscale(ap, c), cmul(sph, aq));
+                    A[q * M + r] = cadd(cscale(ap, s), cmul(cph, aq));
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    A[p * M + q] = cmake(0.0, 0.0);
+                    A[q * M + p] = cmake(0.0, 0.0);
+                    A[p * M + p].y = 0.0;
+                    A[q * M + q].y = 0.0;
+                }
+                __syncwarp();
+            }
+        }
+        if (rotated == 0) break;
+    }
+    // ascending order of the eigenvalues (stable selection by rank), one lane per eigenvalue
+    if (lane < M) {
+        const double li = A[lane * M + lane].x;
+        int rank = 0;
+        for (int j = 0; j < M; ++j) {
+            const double lj = A[j * M + j].x;
+            if (lj < li || (lj == li && j < lane)) ++rank;
+        }
+        sPerm[warp][rank] = lane;
+        if (!isfinite(li)) atomicOr(status, OIVA_STATUS_NONFINITE);
+    }
+    __syncwarp();
+    if (lane < M) {
+        const int k = lane;  // output column
+        const int src = sPerm[warp][k];
+        evals[(size_t)row * M + k] = A[src * M + src].x;
+        // normalise + phase convention
+        double nrm2 = 0.0, best = -1.0;
+        int ib = 0;
+        for (int i = 0; i < M; ++i) {
+            const cplx v = Q[i * M + src];
+            const double m2 = v.x * v.x + v.y * v.y;
+            nrm2 += m2;
+            if (m2 > best) {
+                best = m2;
+                ib = i;
+            }
+        }
+        const double inrm = 1.0 / sqrt(nrm2);
+        cplx rot = cmake(inrm, 0.0);
+        if (lapack_phase) {
+            const cplx vb = Q[ib * M + src];
+            const double mb = sqrt(best);
+            rot = cmake(vb.x / mb * inrm, -vb.y / mb * inrm);  // conj(v_b)/|v_b| / ||v||
+        }
+        for (int i = 0; i < M; ++i) {
+            cplx v = cmul(Q[i * M + src], rot);
+            if (lapack_phase && i == ib) v.y = 0.0;
+            evecs[((size_t)row * M + i) * M + k] = v;
+        }
+    }
+}
+
+}  // namespace oiva
+
+using namespace oiva;
+
+template <int M>
+static int bins_per_cta() {
+    return SOLVE_WARPS * Grp<M>::BINS;
+}
+
+extern "C" int oiva_ip_update(void* What, const void* V, const void* C, const double* wscale, int* status,
+                              int n_batch, int n_freq, int n_chan, int n_src, void* stream) {
+    OIVA_REQUIRE(What && V && C && status, "oiva_ip_update: null pointer");
+    OIVA_REQUIRE(n_batch > 0 && n_freq > 0 && n_src >= 1 && n_src <= n_chan, "oiva_ip_update: bad shape");
+    const long long R = (long long)n_batch * n_freq;
+    cudaStream_t st = (cudaStream_t)stream;
+    OIVA_DISPATCH_M(n_chan, {
+        const int per = bins_per_cta<M_>();
+        k_ip_update<M_><<<(unsigned)((R + per - 1) / per), SOLVE_WARPS * 32, 0, st>>>(
+            (cplx*)What, (const cplx*)V, (const cplx*)C, wscale, status, R, n_freq, n_src);
+    });
+    OIVA_LAUNCH_CHECK();
+    return OIVA_OK;
+}
+
+extern "C" int oiva_init_demix(void* What, const void* C, const void* W0, const void* evecs, int mode, int* status,
+                               int n_rows, int n_chan, int n_src, void* stream) {
+    OIVA_REQUIRE(What && C && status, "oiva_init_demix: null pointer");
+    OIVA_REQUIRE(n_rows > 0 && n_src >= 1 && n_src <= n_chan, "oiva_init_demix: bad shape");
+    OIVA_REQUIRE(mode != OIVA_INIT_W0 || W0, "oiva_init_demix: W0 missing");
+    OIVA_REQUIRE(mode != OIVA_INIT_EIG || evecs, "oiva_init_demix: eigenvectors missing");
+    const long long R = n_rows;
+    cudaStream_t st = (cudaStream_t)stream;
+    OIVA_DISPATCH_M(n_chan, {
+        const int per = bins_per_cta<M_>();
+        k_init_demix<M_><<<(unsigned)((R + per - 1) / per), SOLVE_WARPS * 32, 0, st>>>(
+            (cplx*)What, (const cplx*)C, (const cplx*)W0, (const cplx*)evecs, mode, status, R, n_src);
+    });
+    OIVA_LAUNCH_CHECK();
+    return OIVA_OK;
+}
+
+extern "C" int oiva_projback_filters(const void* What, int w_cols, const void* C, void* Weff, int n_rows, int n_chan,
+                                     int n_src, int proj_back, void* stream) {
+    OIVA_REQUIRE(What && C && Weff, "oiva_projback_filters: null pointer");
+    OIVA_REQUIRE(w_cols >= n_src, "oiva_projback_filters: w_cols %d < n_src %d", w_cols, n_src);
+    OIVA_REQUIRE(n_rows > 0 && n_chan >= 1 && n_chan <= OIVA_MAX_M && n_src >= 1 && n_src <= n_chan,
+                 "oiva_projback_filters: bad shape");
+    const long long n = (long long)n_rows * n_src;
+    k_projback_filters<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        (const cplx*)What, w_cols, (const cplx*)C, (cplx*)Weff, n_rows, n_chan, n_src, proj_back);
+    OIVA_LAUNCH_CHECK();
+    return OIVA_OK;
+}
+
+extern "C" int oiva_compose_filters(const void* E, const void* Wr, void* Wout, int n_rows, int n_chan, int n_red,
+                                    int n_src, void* stream) {
+    OIVA_REQUIRE(E && Wr && Wout, "oiva_compose_filters: null pointer");
+    OIVA_REQUIRE(n_rows > 0 && n_chan >= 1 && n_red >= 1 && n_src >= 1 && n_src <= n_red,
+                 "oiva_compose_filters: bad shape");
+    const long long n = (long long)n_rows * n_chan * n_src;
+    k_compose_filters<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        (const cplx*)E, (const cplx*)Wr, (cplx*)Wout, n_rows, n_chan, n_red, n_src);
+    OIVA_LAUNCH_CHECK();
+    return OIVA_OK;
+}
+
+extern "C" int oiva_eigh(const void* C, double* evals, void* evecs, int* status, int n_rows, int n_chan,
+                         int lapack_phase, void* stream) {
+    OIVA_REQUIRE(C && evals && evecs && status, "oiva_eigh: null pointer");
+    OIVA_REQUIRE(n_rows > 0, "oiva_eigh: bad shape");
+    const long long R = n_rows;
+    cudaStream_t st = (cudaStream_t)stream;
+    OIVA_DISPATCH_M(n_chan, {
+        k_eigh<M_><<<(unsigned)((R + SOLVE_WARPS - 1) / SOLVE_WARPS), SOLVE_WARPS * 32, 0, st>>>(
+            (const cplx*)C, evals, (cplx*)evecs, status, R, lapack_phase);
+    });
+    OIVA_LAUNCH_CHECK();
+    return OIVA_OK;
+}

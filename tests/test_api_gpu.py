@@ -1,0 +1,142 @@
+"""GPU parity tests of the drop-in entry points (overiva / auxiva / auxiva_pca / ogive / overiva_batch)
+against the golden vectors produced by the unmodified reference and against the numpy oracle.
+
+Tolerances (BASELINE.json north_star): relative Frobenius error <= 1e-10 on W and Y in the fp64 mode
+after 20 iterations; <= 1e-3 in the fp32-storage / fp64-solve mode."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden, rel_err
+from oracle import overiva_oracle as orc
+from overiva_b200.synth import convolutive_mixture, small_test_mixture, stft
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if torch.cuda.is_available():
+    import overiva_b200 as ob
+
+FP64_TOL = 1e-10
+FP32_TOL = 1e-3
+
+
+def _run(case):
+    kw = dict(case["kwargs"])
+    if "W0" in case:
+        kw["W0"] = case["W0"]
+    fn = case["fn"]
+    if fn == "overiva":
+        return ob.overiva(case["X"], return_filters=True, **kw)
+    if fn == "auxiva_pca":
+        return ob.auxiva_pca(case["X"], **kw), None
+    if fn == "ogive":
+        return ob.ogive(case["X"], return_filters=True, **kw)
+    raise ValueError(fn)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_against_reference_golden(name):
+    case = load_golden(name)
+    Y, W = _run(case)
+    c64 = case["X"].dtype == np.complex64
+    tol = FP32_TOL if c64 else max(FP64_TOL, 1e2 * case["sens"])
+    assert Y.shape == case["Y"].shape and Y.dtype == case["Y"].dtype
+    assert np.all(np.isfinite(Y))
+    assert rel_err(Y, case["Y"]) <= tol, "Y"
+    if W is not None:
+        assert W.shape == case["W"].shape and W.dtype == case["W"].dtype
+        assert rel_err(W, case["W"]) <= tol, "W"
+
+
+def test_fp32_storage_mode_vs_fp64_reference():
+    """fp32 storage of X/Y with fp64 covariance + solve: within 1e-3 of the reference run in complex128."""
+    case = load_golden("overiva_laplace_m6k2")
+    X = case["X"]
+    Y, W = ob.overiva(X.astype(np.complex64), return_filters=True, **case["kwargs"])
+    assert Y.dtype == np.complex64
+    assert rel_err(Y.astype(np.complex128), case["Y"]) <= FP32_TOL
+    assert rel_err(W.astype(np.complex128), case["W"]) <= FP32_TOL
+
+
+# BASELINE.json configs at their real STFT shape (F = 2049), on convolutive mixtures, against the oracle
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2", "cfg3_short"])
+def test_baseline_configs_full_bins(cfg):
+    if cfg == "cfg1":  # overiva -m 4 -s 2 -n 20, 15 s @ 16 kHz
+        mix, _ = convolutive_mixture(101, 4, 2, duration=15.0)
+        kw = dict(n_src=2, n_iter=20, model="laplace")
+    elif cfg == "cfg2":  # auxiva determined M = K = 6
+        mix, _ = convolutive_mixture(102, 6, 2, duration=15.0)
+        kw = dict(n_iter=20, model="laplace")
+    else:  # overiva M=8 K=2 gauss init_eig (20 s instead of 60 s to keep the oracle quick)
+        mix, _ = convolutive_mixture(103, 8, 2, duration=20.0)
+        kw = dict(n_src=2, n_iter=20, model="gauss", init_eig=True)
+    X = stft(mix)
+    assert X.shape[1] == 2049
+    Yo, Wo = orc.overiva(X, return_filters=True, **kw)
+    Y, W = ob.overiva(X, return_filters=True, **kw)
+    assert rel_err(Y, Yo) <= FP64_TOL
+    assert rel_err(W, Wo) <= FP64_TOL
+
+
+def test_batch_equals_single_and_is_deterministic():
+    Xs = np.stack([small_test_mixture(200 + b, 6, 2, n_samples=2000, frame=64, hop=32) for b in range(5)])
+    Yb, Wb = ob.overiva_batch(Xs, n_src=2, n_iter=10, return_filters=True)
+    Yb2 = ob.overiva_batch(Xs, n_src=2, n_iter=10)
+    assert np.array_equal(Yb, Yb2)  # fixed reduction orders: bit-reproducible
+    for b in range(5):
+        Y1, W1 = ob.overiva(Xs[b], n_src=2, n_iter=10, return_filters=True)
+        Yo, Wo = orc.overiva(Xs[b], n_src=2, n_iter=10, return_filters=True)
+        assert rel_err(Yb[b], Yo) <= FP64_TOL and rel_err(Wb[b], Wo) <= FP64_TOL
+        assert rel_err(Yb[b], Y1) <= 1e-12
+
+
+def test_cuda_tensor_in_cuda_tensor_out():
+    X = small_test_mixture(210, 4, 2)
+    Xd = torch.from_numpy(X).cuda()
+    Y = ob.overiva(Xd, n_src=2, n_iter=5)
+    assert isinstance(Y, torch.Tensor) and Y.is_cuda and Y.dtype == torch.complex128
+    assert rel_err(Y.cpu().numpy(), orc.overiva(X, n_src=2, n_iter=5)) <= FP64_TOL
+    assert torch.equal(Xd.cpu(), torch.from_numpy(X))  # input not mutated
+
+
+def test_callback_cadence_and_content():
+    X = small_test_mixture(211, 3, 2, n_samples=1200, frame=32, hop=16)
+    got, want = [], []
+    ob.overiva(X, n_src=2, n_iter=25, callback=lambda Y: got.append(np.array(Y)))
+    orc.overiva(X, n_src=2, n_iter=25, callback=lambda Y: want.append(Y.copy()))
+    assert len(got) == len(want) == 3  # epochs 0, 10, 20 (overiva.py:142)
+    for a, b in zip(got, want):
+        assert rel_err(a, b) <= FP64_TOL
+
+
+def test_errors_mirror_the_reference():
+    X = small_test_mixture(212, 3, 2, n_samples=800, frame=32, hop=16)
+    with pytest.raises(ValueError):
+        ob.overiva(X, n_src=4)  # more sources than channels
+    with pytest.raises(KeyError):
+        ob.auxiva_pca(X, n_src=2, n_iter=3)  # proj_back is mandatory in auxiva_pca (auxiva_pca.py:86)
+    # rank-deficient input -> LinAlgError("Singular matrix"), as numpy raises from overiva.py:98/182
+    Xs = X.copy()
+    Xs[:, :, 2] = Xs[:, :, 0]
+    with pytest.raises(np.linalg.LinAlgError):
+        ob.overiva(Xs, n_src=2, n_iter=3)
+
+
+def test_sdr_sir_within_0p1_db_of_oracle():
+    from overiva_b200.metrics import bss_eval
+    from overiva_b200.synth import istft
+
+    mix, images = convolutive_mixture(300, 4, 2, duration=6.0, n_interferers=4)
+    X = stft(mix, 1024, 512)
+    refs = images[:, :, 0]
+    out = {}
+    for name, fn, x in (("oracle", orc.overiva, X), ("gpu64", ob.overiva, X),
+                        ("gpu32", ob.overiva, X.astype(np.complex64))):
+        Y = np.asarray(fn(x, n_src=2, n_iter=20)).astype(np.complex128)
+        y = istft(Y, 1024, 512)
+        sdr, sir, _ = bss_eval(refs, y.T)
+        out[name] = (sdr, sir)
+    for name in ("gpu64", "gpu32"):
+        assert np.max(np.abs(out[name][0] - out["oracle"][0])) < 0.1
+        assert np.max(np.abs(out[name][1] - out["oracle"][1])) < 0.1
+    assert out["oracle"][1].mean() > 3.0  # the algorithm does separate on this synthetic mixture

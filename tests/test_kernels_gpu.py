@@ -1,0 +1,219 @@
+"""GPU parity tests, kernel by kernel, through the C ABI: every CUDA step against the numpy oracle's
+restatement of the reference step it replaces (oracle/overiva_oracle.py).  fp64 bar: 1e-12 here (single
+steps; the end-to-end bar of 1e-10 after 20 iterations is in test_api_gpu.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from oracle import overiva_oracle as orc
+from overiva_b200.synth import small_test_mixture
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if torch.cuda.is_available():
+    import gpu_util as G
+    from overiva_b200 import _lib as L
+
+
+def _mix(seed, M, T_samples=1500, frame=64, dtype=np.complex128, B=1):
+    Xs = [small_test_mixture(seed + b, M, 2, n_samples=T_samples, frame=frame, hop=frame // 2) for b in range(B)]
+    return np.stack(Xs).astype(dtype)
+
+
+# T chosen to cover: one ragged tile (T<128), exactly one tile, several tiles with a ragged tail
+@pytest.mark.parametrize("M,n_samples,dtype", [(4, 1500, np.complex128), (3, 1000, np.complex64), (6, 4200, np.complex128),
+                                                (16, 2300, np.complex128), (5, 4900, np.complex64), (1, 700, np.complex128)])
+def test_relayout(M, n_samples, dtype):
+    X = _mix(1, M, n_samples, 32, dtype, B=2)
+    got = G.planar(X)
+    want = G.planar_expected(X)
+    real = np.float32 if dtype == np.complex64 else np.float64
+    got = got.cpu().numpy().view(real)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)  # pure data movement: bit exact
+
+
+@pytest.mark.parametrize("no_tma", [False, True])
+@pytest.mark.parametrize("M,K,n_samples,dtype", [
+    (4, 2, 1500, np.complex128), (6, 2, 2000, np.complex128), (6, 6, 1200, np.complex128), (2, 1, 900, np.complex128),
+    (3, 3, 4200, np.complex128), (8, 2, 5000, np.complex128), (16, 4, 2300, np.complex128), (5, 5, 1500, np.complex128),
+    (7, 3, 1500, np.complex64), (4, 2, 4500, np.complex64), (12, 8, 1000, np.complex128), (9, 7, 2100, np.complex128),
+])
+def test_weighted_covariance(M, K, n_samples, dtype, no_tma, monkeypatch):
+    if no_tma:
+        monkeypatch.setenv("OIVA_COV_NO_TMA", "1")
+    else:
+        monkeypatch.delenv("OIVA_COV_NO_TMA", raising=False)
+    B = 2
+    X = _mix(2, M, n_samples, 32, dtype, B=B)
+    _, T, F, _ = X.shape
+    rng = np.random.default_rng(5)
+    phi = rng.gamma(1.0, 1.0, size=(B, K, T)) + 0.01
+    code = G.code_of(dtype)
+    Xp = G.planar(X)
+    V = G.weighted_cov(Xp, phi, B, T, F, M, K, code)
+    X128 = X.astype(np.complex128)
+    tol = 1e-12 if dtype == np.complex128 else 1e-12  # products are formed in fp64 in both modes
+    for b in range(B):
+        Xf = np.ascontiguousarray(X128[b].swapaxes(0, 1))
+        for k in range(K):
+            want = orc.weighted_covariance(Xf, phi[b, k])
+            assert rel_err(V[b, :, k], want) < tol, (b, k)
+    # Hermitian by construction, real diagonal
+    assert np.array_equal(V, np.conj(V.swapaxes(-1, -2)))
+    # plain covariance (phi == NULL)
+    C = G.weighted_cov(Xp, None, B, T, F, M, 1, code)
+    for b in range(B):
+        assert rel_err(C[b, :, 0], orc.input_covariance(X128[b])) < tol
+
+
+def test_weighted_covariance_split_rows():
+    """few rows, many tiles: the tiles of a row are split over teams and combined atomically"""
+    M, K = 4, 2
+    X = _mix(3, M, 40000, 16, np.complex128, B=1)[:, :, :3]  # F = 3 bins, T ~ 5000 frames
+    _, T, F, _ = X.shape
+    rng = np.random.default_rng(6)
+    phi = rng.gamma(1.0, 1.0, size=(1, K, T)) + 0.01
+    Xp = G.planar(X)
+    V = G.weighted_cov(Xp, phi, 1, T, F, M, K, L.C128)
+    Xf = np.ascontiguousarray(X[0].swapaxes(0, 1))
+    for k in range(K):
+        assert rel_err(V[0, :, k], orc.weighted_covariance(Xf, phi[0, k])) < 1e-12
+
+
+@pytest.mark.parametrize("M,K,n_samples,dtype", [(4, 2, 1500, np.complex128), (6, 6, 1200, np.complex128),
+                                                  (8, 3, 5000, np.complex128), (16, 4, 2300, np.complex128),
+                                                  (5, 1, 1500, np.complex64), (10, 10, 900, np.complex128)])
+def test_demix_power(M, K, n_samples, dtype):
+    B = 2
+    X = _mix(4, M, n_samples, 32, dtype, B=B)
+    _, T, F, _ = X.shape
+    rng = np.random.default_rng(7)
+    W = rng.standard_normal((B, F, M, M)) + 1j * rng.standard_normal((B, F, M, M))
+    Xp = G.planar(X)
+    r2, part = G.demix_power(Xp, W, B, T, F, M, K, G.code_of(dtype))
+    assert np.all(np.isfinite(part))  # every (chunk, k, t) slot was written, padding included
+    X128 = X.astype(np.complex128)
+    for b in range(B):
+        Xf = np.ascontiguousarray(X128[b].swapaxes(0, 1))
+        want = orc.demix_power(Xf, W[b][:, :, :K])  # (T, K)
+        assert rel_err(r2[b].T, want) < 1e-12
+
+
+@pytest.mark.parametrize("model", ["laplace", "gauss"])
+def test_source_model(model):
+    rng = np.random.default_rng(8)
+    B, K, T, M, F = 3, 2, 173, 4, 65
+    r2 = rng.gamma(1.0, 1.0, size=(B, K, T))
+    r2[0, 0, 5] = 0.0  # exercises the 1e-15 clamp
+    code = {"laplace": L.MODEL_LAPLACE, "gauss": L.MODEL_GAUSS}[model]
+    phi, ws = G.source_model(r2, T, M, F, code, L.C128)
+    for b in range(B):
+        r_inv, w_scale = orc.source_model(r2[b].T, model, F)
+        assert rel_err(phi[b].T, r_inv) < 1e-14
+        assert rel_err(ws[b], 1.0 / w_scale) < 1e-14
+
+
+@pytest.mark.parametrize("M,K", [(4, 2), (6, 2), (6, 6), (3, 3), (2, 1), (8, 2), (5, 4), (16, 4), (16, 16), (1, 1), (9, 3)])
+def test_ip_update_sweep(M, K):
+    X = _mix(9, M, 1500, 32)[0]
+    T, F, _ = X.shape
+    Cx = orc.input_covariance(X)
+    rng = np.random.default_rng(10)
+    What = orc.init_demixing(Cx, K)
+    # perturb W so the sweep starts from a generic point, then restore the structure (J, -I)
+    What[:, :, :K] += 0.2 * (rng.standard_normal((F, M, K)) + 1j * rng.standard_normal((F, M, K)))
+    if K < M:
+        orc.background_update(What, Cx, K)
+    Xf = np.ascontiguousarray(X.swapaxes(0, 1))
+    r_inv = rng.gamma(1.0, 1.0, size=(T, K)) + 0.05
+    wscale = rng.uniform(0.5, 2.0, size=(1, K))
+    V = np.stack([orc.weighted_covariance(Xf, r_inv[:, s]) for s in range(K)], axis=1)  # (F, K, M, M)
+    got, status = G.ip_update(What[None], V[None], Cx[None], wscale, K)
+    want = What.copy()
+    want[:, :, :K] *= wscale[0][None, None, :]
+    for s in range(K):
+        orc.ip_update_source(want, V[:, s], Cx, s, K)
+    assert status == 0
+    assert rel_err(got[0], want) < 1e-11
+
+
+def test_ip_update_flags_singular():
+    M, K, F = 4, 2, 5
+    rng = np.random.default_rng(11)
+    What = np.zeros((1, F, M, M), dtype=np.complex128)
+    V = np.zeros((1, F, K, M, M), dtype=np.complex128)  # singular on purpose
+    Cx = np.tile(np.eye(M, dtype=np.complex128), (1, F, 1, 1))
+    What[0, :, :K, :K] = np.eye(K)
+    _, status = G.ip_update(What, V, Cx, None, K)
+    assert status & L.STATUS_SINGULAR
+
+
+@pytest.mark.parametrize("M,K", [(4, 2), (6, 2), (3, 3), (8, 1), (16, 4)])
+def test_init_demix_eye_and_w0(M, K):
+    X = _mix(12, M, 1200, 32)[0]
+    F = X.shape[1]
+    Cx = orc.input_covariance(X)
+    got, status = G.init_demix(Cx, K, L.INIT_EYE)
+    assert status == 0
+    assert rel_err(got, orc.init_demixing(Cx, K)) < 1e-12
+    rng = np.random.default_rng(13)
+    W0 = rng.standard_normal((F, M, K)) + 1j * rng.standard_normal((F, M, K))
+    got, status = G.init_demix(Cx, K, L.INIT_W0, W0=W0)
+    assert rel_err(got, orc.init_demixing(Cx, K, W0=W0)) < 1e-11
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 4, 6, 8, 11, 16])
+def test_eigh(M):
+    X = _mix(14, M, 1500, 32)[0]
+    Cx = orc.input_covariance(X)
+    ev, vec, status = G.eigh(Cx, lapack_phase=True)
+    assert status == 0
+    want_ev = np.linalg.eigvalsh(Cx)
+    assert np.max(np.abs(ev - want_ev) / np.abs(want_ev).max(axis=1, keepdims=True)) < 1e-13
+    # A v = lambda v, unitary, LAPACK zgeev phase (largest component real positive)
+    resid = Cx @ vec - vec * ev[:, None, :]
+    assert np.linalg.norm(resid) / np.linalg.norm(Cx) < 1e-13
+    eye = np.conj(vec.swapaxes(1, 2)) @ vec
+    assert np.max(np.abs(eye - np.eye(M))) < 1e-13
+    idx = np.argmax(np.abs(vec), axis=1)  # (F, M)
+    big = np.take_along_axis(vec, idx[:, None, :], axis=1)[:, 0, :]
+    assert np.all(big.imag == 0.0) and np.all(big.real > 0.0)
+
+
+@pytest.mark.parametrize("M,K", [(4, 2), (6, 2), (8, 3)])
+def test_init_demix_eig_matches_reference_rule(M, K):
+    """overiva.py:103-109: conj of the top-K eigenvectors of np.linalg.eig, ascending."""
+    X = _mix(15, M, 1500, 32)[0]
+    Cx = orc.input_covariance(X)
+    _, vec, _ = G.eigh(Cx, lapack_phase=True)
+    got, status = G.init_demix(Cx, K, L.INIT_EIG, evecs=vec)
+    assert status == 0
+    assert rel_err(got, orc.init_demixing(Cx, K, init_eig=True)) < 1e-11
+
+
+@pytest.mark.parametrize("M,K,n_samples,dtype,proj_back", [
+    (4, 2, 1500, np.complex128, True), (6, 6, 1200, np.complex128, True), (8, 3, 5000, np.complex128, False),
+    (16, 4, 2300, np.complex128, True), (5, 1, 1500, np.complex64, True), (3, 2, 4300, np.complex64, True)])
+def test_final_demix_and_projection_back(M, K, n_samples, dtype, proj_back):
+    B = 2
+    X = _mix(16, M, n_samples, 32, dtype, B=B)
+    _, T, F, _ = X.shape
+    rng = np.random.default_rng(17)
+    W = rng.standard_normal((B, F, M, M)) + 1j * rng.standard_normal((B, F, M, M))
+    X128 = X.astype(np.complex128)
+    Cx = np.stack([orc.input_covariance(X128[b]) for b in range(B)])
+    Weff = G.projback_filters(W.reshape(B * F, M, M), Cx.reshape(B * F, M, M), K, proj_back)
+    Xp = G.planar(X)
+    Y = G.demix_output(Xp, Weff, B, T, F, M, K, G.code_of(dtype))
+    assert Y.dtype == dtype and np.all(np.isfinite(Y))
+    for b in range(B):
+        Xf = np.ascontiguousarray(X128[b].swapaxes(0, 1))
+        want = orc.demix(Xf, W[b][:, :, :K]).swapaxes(0, 1)
+        if proj_back:
+            z = orc.projection_back(want, X128[b][:, :, 0])
+            want = want * np.conj(z[None])
+        assert rel_err(Y[b], want) < (1e-12 if dtype == np.complex128 else 1e-6)

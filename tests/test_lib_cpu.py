@@ -1,0 +1,120 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/overiva_b200.h
+declares, its host-side helpers and argument validation work without a GPU, and the Python entry points
+fail loudly (no CPU fallback) when CUDA is absent."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from overiva_b200 import _lib as L
+
+HEADER = os.path.join(ROOT, "include", "overiva_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.isfile(L.LIB_PATH):
+        import __graft_entry__ as g
+
+        g.build()
+    return L.load()
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(oiva_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    names = declared_symbols()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(lib, n), "missing export: " + n
+        assert n in L.SIGNATURES, "no ctypes signature for " + n
+    assert sorted(L.SIGNATURES) == names  # nothing bound that the header does not declare
+
+
+def test_header_cites_the_reference_interfaces():
+    src = open(HEADER).read()
+    for cite in ("overiva.py:179", ":181-182", "overiva.py:87", "overiva.py:152-173", "overiva.py:192-199",
+                 "auxiva_pca.py:79-81", "216-241"):
+        assert cite in src, cite
+
+
+def test_layout_helpers(lib):
+    # one ragged tile when T <= tile frames; tiles of 128 (M <= 8) or 64 frames otherwise; no padding in fp64
+    assert lib.oiva_tile_frames(116, 4, L.C128) == 128
+    assert lib.oiva_tile_frames(14061, 16, L.C128) == 64
+    assert lib.oiva_planar_bytes(1, 116, 2049, 4, L.C128) == 116 * 2049 * 4 * 16
+    assert lib.oiva_planar_bytes(3, 467, 10, 8, L.C128) == 3 * 467 * 10 * 8 * 16
+    assert lib.oiva_frame_pitch(116, 4, L.C128) == 128
+    assert lib.oiva_frame_pitch(467, 8, L.C128) == 512
+    # float storage: tiles stay 16-byte multiples (one zero frame of padding when M*T_last is odd)
+    nb = lib.oiva_planar_bytes(1, 61, 1, 3, L.C64)
+    assert nb % 16 == 0 and nb >= 61 * 3 * 8
+    assert 1 <= lib.oiva_power_chunks(1, 2049) <= 2049
+    assert lib.oiva_power_chunks(512, 2049) == 33
+
+
+def test_argument_validation_without_gpu(lib):
+    h = C.c_void_p()
+    bad = L.PlanDesc(1, 100, 10, 0, 17, 2, L.MODEL_LAPLACE, L.C128, 0)  # 17 channels
+    assert lib.oiva_plan_create(C.byref(h), C.byref(bad)) == -1
+    assert b"n_chan" in lib.oiva_last_error()
+    bad = L.PlanDesc(1, 100, 10, 0, 4, 5, L.MODEL_LAPLACE, L.C128, 0)  # more sources than channels
+    assert lib.oiva_plan_create(C.byref(h), C.byref(bad)) == -1
+    ok = L.PlanDesc(2, 116, 2049, 0, 4, 2, L.MODEL_LAPLACE, L.C128, 0)
+    assert lib.oiva_plan_create(C.byref(h), C.byref(ok)) == 0
+    nbytes = lib.oiva_plan_workspace_bytes(h)
+    assert nbytes > 2 * 116 * 2049 * 4 * 16
+    assert lib.oiva_plan_iterate(h, 1, None) == -3  # no workspace bound: state error, not a crash
+    lib.oiva_plan_destroy(h)
+    assert lib.oiva_relayout(None, None, 1, 1, 1, 1, 0, None) == -1
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import overiva_b200 as ob
+
+    X = np.zeros((10, 5, 3), dtype=np.complex128)
+    for fn, kw in ((ob.overiva, {}), (ob.auxiva, {}), (ob.ogive, {}), (ob.auxiva_pca, dict(proj_back=True))):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            fn(X, **kw)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "overiva_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+    for f in ("overiva.py", "auxiva_pca.py", "ive.py"):
+        txt = open(os.path.join(ROOT, f)).read()
+        assert "oracle" not in txt
+
+
+def test_drop_in_modules_expose_reference_signatures():
+    import inspect
+
+    import auxiva_pca as m_pca
+    import ive as m_ive
+    import overiva as m_ov
+
+    sig = inspect.signature(m_ov.overiva)
+    assert list(sig.parameters) == ["X", "n_src", "n_iter", "proj_back", "W0", "model", "init_eig", "return_filters",
+                                    "callback"]  # overiva.py:28-38
+    assert sig.parameters["n_iter"].default == 20 and sig.parameters["model"].default == "laplace"
+    sig = inspect.signature(m_ive.ogive)
+    assert list(sig.parameters) == ["X", "n_iter", "step_size", "tol", "update", "proj_back", "W0", "model", "init_eig",
+                                    "return_filters", "callback"]  # ive.py:33-45
+    assert sig.parameters["n_iter"].default == 4000 and sig.parameters["tol"].default == 1e-3
+    sig = inspect.signature(m_pca.auxiva_pca)
+    assert list(sig.parameters) == ["X", "n_src", "kwargs"]  # auxiva_pca.py:30
