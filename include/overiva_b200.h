@@ -208,6 +208,13 @@ int oiva_plan_status(oiva_plan_t* plan, void* stream);
 /* number of kernels launched by this plan since creation (bench.py's gpu_launches) */
 long long oiva_plan_launch_count(const oiva_plan_t* plan);
 
+/* Optional per-kernel timing for the roofline report: when enabled, CUDA events are recorded on the
+ * launching stream around every launch of the three loop kernels.  oiva_plan_read_timing() (call it after
+ * synchronising the stream) returns the summed milliseconds and launch counts for
+ * [0] weighted covariance, [1] demix power, [2] IP solve, and resets the record. */
+int oiva_plan_enable_timing(oiva_plan_t* plan, int enable);
+int oiva_plan_read_timing(oiva_plan_t* plan, double* ms3, long long* counts3);
+
 /* Convenience: the complete call with HOST buffers (pinned or pageable): H2D of X (B,T,F,M), the loop,
  * D2H of Y (B,T,F,K) [and W (B,F,M,K) c128 if W_host != NULL].  Allocates and frees its own device memory.
  * Returns the status word (>0) on numerical failure. */

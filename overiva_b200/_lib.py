@@ -78,6 +78,8 @@ SIGNATURES = {
     "oiva_plan_status_ptr": (_p, [_p]),
     "oiva_plan_status": (_i, [_p, _p]),
     "oiva_plan_launch_count": (C.c_longlong, [_p]),
+    "oiva_plan_enable_timing": (_i, [_p, _i]),
+    "oiva_plan_read_timing": (_i, [_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "oiva_overiva_host": (_i, [_p, _p, _p, _p, C.POINTER(PlanDesc), _i, _i, _i]),
 }
 

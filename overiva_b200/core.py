@@ -176,6 +176,16 @@ class DemixPlan:
         if st & L.STATUS_NONFINITE:
             raise np.linalg.LinAlgError("non-finite value in the demixing matrices")
 
+    def enable_timing(self, on=True):
+        L.check(self.lib.oiva_plan_enable_timing(self.h, int(on)), "oiva_plan_enable_timing")
+
+    def read_timing(self):
+        """{'cov': (ms, launches), 'power': ..., 'solve': ...} since the last read; synchronise first."""
+        ms = (C.c_double * 3)()
+        n = (C.c_longlong * 3)()
+        L.check(self.lib.oiva_plan_read_timing(self.h, ms, n), "oiva_plan_read_timing")
+        return {k: (ms[i], int(n[i])) for i, k in enumerate(("cov", "power", "solve"))}
+
     @property
     def launches(self):
         return int(self.lib.oiva_plan_launch_count(self.h))

@@ -32,6 +32,19 @@ static int get_ones(size_t n, cudaStream_t st, const double** out) {
     *out = g_ones[dev];
     return OIVA_OK;
 }
+__global__ void k_cov_mirror(double* __restrict__ V, long long R, int K, int k0, int KC, int M) {
+    const long long n = R * KC * M * M;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int j = (int)(idx % M), i = (int)((idx / M) % M);
+    if (i <= j) return;
+    const int k = (int)((idx / ((long long)M * M)) % KC);
+    const long long row = idx / ((long long)M * M * KC);
+    double* base = V + (((size_t)row * K + k0 + k) * M * M) * 2;
+    const double re = base[((size_t)i * M + j) * 2], im = base[((size_t)i * M + j) * 2 + 1];
+    base[((size_t)j * M + i) * 2] = re;
+    base[((size_t)j * M + i) * 2 + 1] = -im;
+}
 }  // namespace oiva
 
 extern "C" int oiva_weighted_cov(const void* Xp, const double* phi, void* V, int n_batch, int n_frames, int n_freq,

@@ -153,8 +153,7 @@ struct CovPart {
                     } else {
                         const double uval = ri ? -val : val;
                         if (atomic) {
-                            atomicAdd(lo, val);
-                            atomicAdd(up, uval);
+                            atomicAdd(lo, val);  // upper triangle mirrored afterwards (k_cov_mirror)
                         } else {
                             *lo = val;
                             *up = uval;
@@ -296,5 +295,9 @@ __global__ void __launch_bounds__(cov_threads(P)) k_cov(const CovParams p, int t
     CovDispatch<ST, M, KC, P, USE_TMA>::run(part, p, team_smem, blockIdx.x * teams_per_cta + team,
                                             gridDim.x * teams_per_cta, lane);
 }
+
+// split-row path only: copy the (atomically accumulated) lower triangle into the upper one so that V is
+// exactly Hermitian; one thread per (row, k, i, j) with i > j
+__global__ void k_cov_mirror(double* __restrict__ V, long long R, int K, int k0, int KC, int M);
 
 }  // namespace oiva

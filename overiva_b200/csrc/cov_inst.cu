@@ -75,6 +75,11 @@ static int launch(CovParams p, cudaStream_t st) {
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, threads, smem, st>>>(p, teams, (int)team_smem);
     OIVA_LAUNCH_CHECK();
+    if (p.nsplit > 1) {
+        const long long n = (long long)p.R * KC * M * M;
+        k_cov_mirror<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.V, p.R, p.K, p.k0, KC, M);
+        OIVA_LAUNCH_CHECK();
+    }
     return OIVA_OK;
 }
 

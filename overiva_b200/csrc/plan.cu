@@ -3,7 +3,17 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
+
+// optional per-kernel timing (bench.py's roofline leg): CUDA events recorded on the launching stream
+// around the launches of the three loop kernels; read back after the caller has synchronised
+enum { TK_COV = 0, TK_POWER = 1, TK_SOLVE = 2, TK_N = 3 };
+struct TimedSpan {
+    cudaEvent_t a, b;
+    int kind;
+};
 
 struct oiva_plan {
     oiva_plan_desc d;
@@ -18,6 +28,40 @@ struct oiva_plan {
     unsigned char* ws;
     long long launches;
     bool loaded, inited;
+    bool timing;
+    std::vector<TimedSpan>* spans;
+    std::vector<cudaEvent_t>* pool;
+};
+
+static cudaEvent_t plan_event(oiva_plan* p) {
+    cudaEvent_t e = nullptr;
+    if (!p->pool->empty()) {
+        e = p->pool->back();
+        p->pool->pop_back();
+    } else {
+        cudaEventCreate(&e);
+    }
+    return e;
+}
+struct SpanGuard {  // records an event pair around a launch sequence when timing is on
+    oiva_plan* p;
+    cudaStream_t st;
+    TimedSpan sp;
+    bool on;
+    SpanGuard(oiva_plan* p_, int kind, void* stream) : p(p_), st((cudaStream_t)stream), on(p_->timing) {
+        if (on) {
+            sp.kind = kind;
+            sp.a = plan_event(p);
+            sp.b = plan_event(p);
+            cudaEventRecord(sp.a, st);
+        }
+    }
+    ~SpanGuard() {
+        if (on) {
+            cudaEventRecord(sp.b, st);
+            p->spans->push_back(sp);
+        }
+    }
 };
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -60,11 +104,51 @@ extern "C" int oiva_plan_create(oiva_plan_t** out, const oiva_plan_desc* desc) {
     p->off_evals = o;   o += align_up(R * M * 8);
     p->off_status = o;  o += align_up(16);
     p->ws_bytes = o;
+    p->spans = new std::vector<TimedSpan>();
+    p->pool = new std::vector<cudaEvent_t>();
     *out = p;
     return OIVA_OK;
 }
 
-extern "C" void oiva_plan_destroy(oiva_plan_t* plan) { free(plan); }
+extern "C" void oiva_plan_destroy(oiva_plan_t* plan) {
+    if (!plan) return;
+    if (plan->spans) {
+        for (auto& s : *plan->spans) {
+            cudaEventDestroy(s.a);
+            cudaEventDestroy(s.b);
+        }
+        delete plan->spans;
+    }
+    if (plan->pool) {
+        for (auto e : *plan->pool) cudaEventDestroy(e);
+        delete plan->pool;
+    }
+    free(plan);
+}
+
+extern "C" int oiva_plan_enable_timing(oiva_plan_t* plan, int enable) {
+    OIVA_REQUIRE(plan != nullptr, "oiva_plan_enable_timing: null plan");
+    plan->timing = enable != 0;
+    return OIVA_OK;
+}
+
+extern "C" int oiva_plan_read_timing(oiva_plan_t* plan, double* ms, long long* counts) {
+    OIVA_REQUIRE(plan && ms && counts, "oiva_plan_read_timing: null pointer");
+    for (int k = 0; k < TK_N; ++k) {
+        ms[k] = 0.0;
+        counts[k] = 0;
+    }
+    for (auto& s : *plan->spans) {
+        float t = 0.f;
+        OIVA_CUDA_CHECK(cudaEventElapsedTime(&t, s.a, s.b));
+        ms[s.kind] += t;
+        counts[s.kind] += 1;
+        plan->pool->push_back(s.a);
+        plan->pool->push_back(s.b);
+    }
+    plan->spans->clear();
+    return OIVA_OK;
+}
 
 extern "C" size_t oiva_plan_workspace_bytes(const oiva_plan_t* plan) { return plan ? plan->ws_bytes : 0; }
 
@@ -151,6 +235,7 @@ extern "C" int oiva_plan_init(oiva_plan_t* p, int mode, const void* W0, void* st
 
 static int plan_power_partials(oiva_plan_t* p, void* stream) {
     const oiva_plan_desc& d = p->d;
+    SpanGuard g(p, TK_POWER, stream);
     int rc = oiva_demix_power(p->ws + p->off_xp, p->ws + p->off_what, d.n_chan, (double*)(p->ws + p->off_r2part), p->NCH,
                               d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.n_src, d.dtype, stream);
     if (rc) return rc;
@@ -165,11 +250,17 @@ static int plan_update_from(oiva_plan_t* p, const double* r2src, int nch, void* 
     int rc = oiva_source_model(r2src, nch, phi, wscale, d.n_batch, d.n_frames, d.n_chan, d.n_src, p->n_freq_total,
                                d.model, d.dtype, stream);
     if (rc) return rc;
-    rc = oiva_weighted_cov(p->ws + p->off_xp, phi, p->ws + p->off_v, d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.n_src,
-                           d.dtype, stream);
+    {
+        SpanGuard g(p, TK_COV, stream);
+        rc = oiva_weighted_cov(p->ws + p->off_xp, phi, p->ws + p->off_v, d.n_batch, d.n_frames, d.n_freq, d.n_chan,
+                               d.n_src, d.dtype, stream);
+    }
     if (rc) return rc;
-    rc = oiva_ip_update(p->ws + p->off_what, p->ws + p->off_v, p->ws + p->off_c, wscale,
-                        (int*)(p->ws + p->off_status), d.n_batch, d.n_freq, d.n_chan, d.n_src, stream);
+    {
+        SpanGuard g(p, TK_SOLVE, stream);
+        rc = oiva_ip_update(p->ws + p->off_what, p->ws + p->off_v, p->ws + p->off_c, wscale,
+                            (int*)(p->ws + p->off_status), d.n_batch, d.n_freq, d.n_chan, d.n_src, stream);
+    }
     if (rc) return rc;
     p->launches += 3;
     return OIVA_OK;
