@@ -16,7 +16,12 @@
  *  - complex numbers are interleaved (re, im).  "c128" = two doubles, "c64" = two floats.  `dtype`
  *    (OIVA_C128 / OIVA_C64) is the storage type of X and Y only; covariances, demixing matrices and all
  *    on-chip arithmetic are fp64 in both modes.
- *  - shapes: B mixtures, T frames, F bins, M channels (1..16), K sources (1..M); R = B*F "rows".
+ *  - shapes: B mixtures, T frames, F bins, M channels (1..16), K sources (1..M); R = B*F "rows"
+ *    (row = b*F + f); NG = ceil(F/32) groups of 32 bins per mixture, G = B*NG; NE = M(M+1)/2.
+ *  - grouped layouts (lane <-> bin, see csrc/common.cuh):
+ *        Xg[gi][t][c][l]   complex<dtype>   samples,   gi = b*NG + f/32, l = f%32 (zero for f >= F)
+ *        Vg[gi][k][e][l]   c128             covariance entry e = i(i+1)/2 + j (i >= j) of source k
+ *    per-frame buffers (phi, r2) have the padded pitch Tp = oiva_frame_pitch(T).
  *  - numerical failure (singular pivot / non-finite value; the reference raises
  *    numpy.linalg.LinAlgError from overiva.py:98,182) is reported through a device status word that the
  *    caller reads back when convenient: bit 0 = singular pivot, bit 1 = non-finite result.
@@ -41,7 +46,7 @@ extern "C" {
 
 #define OIVA_MODEL_LAPLACE 0 /* r = 2 sqrt(sum_f |y|^2)          overiva.py:152-153 */
 #define OIVA_MODEL_GAUSS 1   /* r = sum_f |y|^2 / F               overiva.py:154-155 */
-#define OIVA_MODEL_NONE 2    /* any other string: r stays 0 (then clamped), as in the reference */
+#define OIVA_MODEL_NONE 2    /* any other string: r stays 0, as in the reference */
 #define OIVA_MODEL_OGIVE_LAPLACE 3 /* r = sqrt(sum_f |y|^2 / F), no gamma rescale  ive.py:204-205 */
 #define OIVA_MODEL_OGIVE_GAUSS 4   /* r = sum_f |y|^2 / F, no gamma rescale        ive.py:207-208 */
 
@@ -57,56 +62,58 @@ const char* oiva_last_error(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Layout helpers (host-side arithmetic only, no GPU needed).
- * The loop streams a planar, frame-contiguous copy of X ("Xp", see csrc/common.cuh): per row
- * (b, f), nT tiles of [2*M planes][TT frames].  oiva_tile_frames() returns TT for a given problem
- * (TT == T when a whole row fits one shared-memory stage, else a multiple of 32); phi / r2 buffers
- * use the padded frame pitch oiva_frame_pitch() (multiple of 32).
  * ---------------------------------------------------------------------------------------------- */
-int oiva_tile_frames(int n_frames, int n_chan, int dtype);
-int oiva_frame_pitch(int n_frames, int n_chan, int dtype);
-size_t oiva_planar_bytes(int n_batch, int n_frames, int n_freq, int n_chan, int dtype);
-/* number of bin chunks per mixture used for the partial sums of the source-model statistic */
-int oiva_power_chunks(int n_batch, int n_freq);
+int oiva_bin_groups(int n_freq);  /* NG = ceil(F/32) */
+int oiva_frame_pitch(int n_frames); /* Tp: T rounded up to a multiple of 32 */
+size_t oiva_grouped_bytes(int n_batch, int n_frames, int n_freq, int n_chan, int dtype);   /* bytes of Xg */
+size_t oiva_grouped_cov_bytes(int n_batch, int n_freq, int n_chan, int n_src);             /* bytes of Vg */
 
 /* ------------------------------------------------------------------------------------------------
  * Kernels (one per step of the reference loop).
  * ---------------------------------------------------------------------------------------------- */
 
-/* X (B,T,F,M) interleaved complex -> planar rows Xp.      replaces: overiva.py:131-132 (swapaxes+copy) */
-int oiva_relayout(const void* X, void* Xp, int n_batch, int n_frames, int n_freq, int n_chan, int dtype,
+/* X (B,T,F,M) interleaved complex -> grouped samples Xg.   replaces: overiva.py:131-132 (swapaxes+copy) */
+int oiva_relayout(const void* X, void* Xg, int n_batch, int n_frames, int n_freq, int n_chan, int dtype,
                   void* stream);
 
-/* V[row][k] = (1/T) sum_t phi[b][k][t] x x^H  (Hermitian, both triangles written), V: (R,K,M,M) c128.
+/* Vg[gi][k] = (1/T) sum_t phi[b][k][t] x x^H  (Hermitian: lower triangle stored, grouped layout).
  * phi: (B,K,Tp) inverse source-model weights, or NULL with n_src = 1 for the plain covariance.
  * replaces: overiva.py:179 (all K sources in one pass over X) and overiva.py:87 / ive.py:97 /
  * auxiva_pca.py:71 (phi == NULL). */
-int oiva_weighted_cov(const void* Xp, const double* phi, void* V, int n_batch, int n_frames, int n_freq,
+int oiva_weighted_cov(const void* Xg, const double* phi, void* Vg, int n_batch, int n_frames, int n_freq,
                       int n_chan, int n_src, int dtype, void* stream);
 
-/* r2part[b][chunk][k][t] = sum_{f in chunk} |w_k(f)^H x(f,t)|^2.  W: (R,M,w_cols) c128, columns :K used
- * (w_cols = M for the W_hat matrices of the plan, K for plain (R,M,K) filters).
+/* Vg (grouped lower triangles) -> V (R,K,M,M) c128 full Hermitian matrices, row-major. */
+int oiva_unpack_cov(const void* Vg, void* V, int n_batch, int n_freq, int n_chan, int n_src, void* stream);
+
+/* r2part[b][g][k][t] = sum_{f in group g} |w_k(f)^H x(f,t)|^2 : (B,NG,K,Tp), padding frames written as 0.
+ * W: (R,M,w_cols) c128, columns :K used (w_cols = M for the W_hat matrices of the plan, K for plain
+ * (R,M,K) filters).
  * replaces: overiva.py:140 (demix) + the norm over frequency at overiva.py:152-155 / ive.py:204-208;
  * Y is never materialised inside the loop. */
-int oiva_demix_power(const void* Xp, const void* W, int w_cols, double* r2part, int n_chunks, int n_batch,
-                     int n_frames, int n_freq, int n_chan, int n_src, int dtype, void* stream);
+int oiva_demix_power(const void* Xg, const void* W, int w_cols, double* r2part, int n_batch, int n_frames,
+                     int n_freq, int n_chan, int n_src, int dtype, void* stream);
 
-/* r2[b][k][t] = sum_chunks r2part (fixed order, deterministic).  Used on its own by the
+/* r2[b][k][t] = sum_chunks r2part[b][chunk][k][t] (fixed order, deterministic).  Used on its own by the
  * frequency-sharded driver, which all-reduces r2 across ranks before oiva_source_model(n_chunks=1). */
-int oiva_sum_partials(const double* r2part, int n_chunks, double* r2, int n_batch, int n_frames, int n_chan,
-                      int n_src, int dtype, void* stream);
-
-/* source model + scale normalisation + clamp + inverse: overiva.py:152-173 (ive.py:204-214 for the
- * OGIVE models).  phi (B,K,Tp) <- 1/max(r/gamma, 1e-15); wscale (B,K) <- 1/gamma (laplace),
- * 1/sqrt(gamma) (gauss), 1 (others): the factor W must be MULTIPLIED by (overiva.py:161-167).
- * n_freq_total is the F the gauss model divides by (the full F when bins are sharded across GPUs). */
-int oiva_source_model(const double* r2part, int n_chunks, double* phi, double* wscale, int n_batch,
-                      int n_frames, int n_chan, int n_src, int n_freq_total, int model, int dtype,
+int oiva_sum_partials(const double* r2part, int n_chunks, double* r2, int n_batch, int n_frames, int n_src,
                       void* stream);
 
+/* source model + scale normalisation + clamp + inverse: overiva.py:152-173 (ive.py:204-214 for the
+ * OGIVE models).  r2part: (B,n_chunks,K,Tp).  phi (B,K,Tp) <- 1/max(r/gamma, 1e-15); wscale (B,K) (may be
+ * NULL) <- 1/gamma (laplace), 1/sqrt(gamma) (gauss), 1 (others): the factor W must be MULTIPLIED by
+ * (overiva.py:161-167).  n_freq_total is the F the gauss model divides by (the full F when bins are
+ * sharded across GPUs). */
+int oiva_source_model(const double* r2part, int n_chunks, double* phi, double* wscale, int n_batch,
+                      int n_frames, int n_src, int n_freq_total, int model, void* stream);
+
 /* One sweep over the K sources, per bin, in order:  W[:, :K] *= wscale;  for s: w_s = (What^H V_s)^-1 e_s;
- * w_s /= sqrt(w_s^H V_s w_s);  J = (W^H C E1)^-1 (W^H C E2).   What (R,M,M) c128 in place.
+ * w_s /= sqrt(w_s^H V_s w_s);  J = (W^H C E1)^-1 (W^H C E2).   What (R,M,M) c128 in place, Vg grouped,
+ * C (R,M,M) c128 full, Cg = the same covariance in the grouped lower-triangle layout (may be NULL).
+ * With Cg given and M <= 6 the sweep runs one THREAD per bin (lane <-> bin, in-register LU with partial
+ * pivoting); otherwise a group of next_pow2(M) lanes owns a bin (one matrix row per lane).
  * replaces: overiva.py:161-167 (W rescale), :181-182 (zgemm + zgesv), :185-186, :189-190 (:96-98). */
-int oiva_ip_update(void* What, const void* V, const void* C, const double* wscale, int* status,
+int oiva_ip_update(void* What, const void* Vg, const void* C, const void* Cg, const double* wscale, int* status,
                    int n_batch, int n_freq, int n_chan, int n_src, void* stream);
 
 /* Build What (R,M,M): W from eye / eigenvectors / W0, then J and the -I block.
@@ -122,34 +129,35 @@ int oiva_init_demix(void* What, const void* C, const void* W0, const void* evecs
 int oiva_eigh(const void* C, double* evals, void* evecs, int* status, int n_rows, int n_chan,
               int lapack_phase, void* stream);
 
-/* W: (R,M,w_cols) c128.  Weff (R,M,K) c128 = W[:, :, k] * z_k with z_k = (w_k^H C e_0)/(w_k^H C w_k) (1 if the denominator is 0)
- * when proj_back != 0, else a plain copy of the W columns.
+/* W: (R,M,w_cols) c128.  Weff (R,M,K) c128 = W[:, :, k] * z_k with z_k = (w_k^H C e_0)/(w_k^H C w_k)
+ * (1 if the denominator is 0) when proj_back != 0, else a plain copy of the W columns.
  * replaces: pyroomacoustics.bss.projection_back as called at overiva.py:197-199 (no pass over Y needed:
  * sum_t conj(x_0) y_k = T w_k^H C e_0 and sum_t |y_k|^2 = T w_k^H C w_k). */
 int oiva_projback_filters(const void* W, int w_cols, const void* C, void* Weff, int n_rows, int n_chan,
                           int n_src, int proj_back, void* stream);
 
-/* Y (B,T,F,K) interleaved complex (dtype) = Weff^H x.       replaces: overiva.py:192-199 */
-int oiva_demix_output(const void* Xp, const void* Weff, void* Y, int n_batch, int n_frames, int n_freq,
+/* Y (B,T,F,K) interleaved complex (dtype) = Weff^H x, Weff (R,M,K) c128.   replaces: overiva.py:192-199 */
+int oiva_demix_output(const void* Xg, const void* Weff, void* Y, int n_batch, int n_frames, int n_freq,
                       int n_chan, int n_src, int dtype, void* stream);
 
-/* Xr planar rows (K channels) = E_K^H x with E_K (R,M,K) c128 -- the PCA projection of
- * auxiva_pca.py:79-81 written directly in the planar layout the loop streams. */
-int oiva_project_rows(const void* Xp, const void* E, void* Xr, int n_batch, int n_frames, int n_freq,
+/* Xr = grouped samples (K channels) of E_K^H x with E_K (R,M,K) c128 -- the PCA projection of
+ * auxiva_pca.py:79-81 written directly in the layout the loop streams. */
+int oiva_project_rows(const void* Xg, const void* E, void* Xr, int n_batch, int n_frames, int n_freq,
                       int n_chan, int n_src, int dtype, void* stream);
 
-/* C (R,M,M) <- small dense helpers used by the wrappers: Wout (R,M,K) = E (R,M,Kr) @ Wr (R,Kr,K) */
+/* Wout (R,M,K) = E (R,M,Kr) @ Wr (R,Kr,Kr)[:, :, :K]  (auxiva_pca: filters on the original channels) */
 int oiva_compose_filters(const void* E, const void* Wr, void* Wout, int n_rows, int n_chan, int n_red,
                          int n_src, void* stream);
 
-/* OGIVE per-bin update (ive.py:132-140, 216-241): from V (R,1,M,M) and the state (w, a, lambda_a),
- * one masked w-step / a-step with the orthogonal constraints; delta_max[0] <- max_f ||delta_f|| via an
- * atomic max on its bit pattern (caller zeroes it).  do_a: (R,) uint8 mask (1 = a-step bin). */
+/* OGIVE per-bin update (ive.py:132-140, 216-241): from V (R,M,M) full (oiva_unpack_cov of the K=1 weighted
+ * covariance) and the state (w, a, lambda_a), one masked w-step / a-step with the orthogonal constraints;
+ * delta_max[0] <- max_f ||delta_f|| via an atomic max on its bit pattern (caller zeroes it).
+ * do_a: (R,) uint8 mask (1 = a-step bin). */
 int oiva_ogive_update(void* w, void* a, double* lambda_a, const void* V, const void* C, const void* Cinv,
                       const uint8_t* do_a, double step_size, double* delta_max, int n_rows, int n_chan,
                       void* stream);
-/* OGIVE set-up: Cinv = C^-1 (ive.py:98), a from w (ive.py:132-135,168), switching criterion masks
- * (ive.py:142-161).  cnorm (R,) = ||C||_F. */
+/* OGIVE set-up: Cinv = C^-1 (ive.py:98), cnorm (R,) = ||C||_F (ive.py:99); a from w (ive.py:132-135,168);
+ * switching criterion masks (ive.py:142-161). */
 int oiva_ogive_setup(const void* C, void* Cinv, double* cnorm, int* status, int n_rows, int n_chan, void* stream);
 int oiva_ogive_a_from_w(const void* w, void* a, const void* C, int n_rows, int n_chan, void* stream);
 int oiva_ogive_switching(const void* a, const void* C, const double* cnorm, uint8_t* do_a, int n_rows,
@@ -180,9 +188,9 @@ int oiva_plan_bind(oiva_plan_t* plan, void* workspace, size_t bytes);
 
 /* relayout X and compute the input covariance C                    overiva.py:87,131-132 */
 int oiva_plan_load(oiva_plan_t* plan, const void* X, void* stream);
-/* alternative to oiva_plan_load: the caller has written planar rows into oiva_plan_planar() (e.g. with
- * oiva_project_rows); computes the covariance of those rows and marks the plan loaded. */
-int oiva_plan_adopt_planar(oiva_plan_t* plan, void* stream);
+/* alternative to oiva_plan_load: the caller has written grouped samples into oiva_plan_samples() (e.g.
+ * with oiva_project_rows); computes their covariance and marks the plan loaded. */
+int oiva_plan_adopt_samples(oiva_plan_t* plan, void* stream);
 /* initialise What (mode OIVA_INIT_*; W0 (B,F,M,K) c128 or NULL)    overiva.py:89-123 */
 int oiva_plan_init(oiva_plan_t* plan, int mode, const void* W0, void* stream);
 /* n_iter epochs of the loop                                        overiva.py:138-190 */
@@ -199,9 +207,9 @@ int oiva_plan_output(oiva_plan_t* plan, int proj_back, void* Y, void* stream);
 /* copy the filters W (B,F,M,K) c128 (contiguous) out of What       overiva.py:201-202 */
 int oiva_plan_filters(oiva_plan_t* plan, void* W, void* stream);
 /* device pointers into the workspace (for tests and wrappers) */
-void* oiva_plan_what(oiva_plan_t* plan);   /* (R,M,M) c128 */
-void* oiva_plan_cov(oiva_plan_t* plan);    /* (R,M,M) c128 */
-void* oiva_plan_planar(oiva_plan_t* plan); /* planar rows  */
+void* oiva_plan_what(oiva_plan_t* plan);    /* (R,M,M) c128 */
+void* oiva_plan_cov(oiva_plan_t* plan);     /* (R,M,M) c128, full */
+void* oiva_plan_samples(oiva_plan_t* plan); /* Xg */
 int* oiva_plan_status_ptr(oiva_plan_t* plan);
 /* synchronises the stream and returns the status word (0 = fine) */
 int oiva_plan_status(oiva_plan_t* plan, void* stream);

@@ -38,16 +38,17 @@ _i, _p, _d, _sz = C.c_int, C.c_void_p, C.c_double, C.c_size_t
 SIGNATURES = {
     "oiva_version": (_i, []),
     "oiva_last_error": (C.c_char_p, []),
-    "oiva_tile_frames": (_i, [_i, _i, _i]),
-    "oiva_frame_pitch": (_i, [_i, _i, _i]),
-    "oiva_planar_bytes": (_sz, [_i, _i, _i, _i, _i]),
-    "oiva_power_chunks": (_i, [_i, _i]),
+    "oiva_bin_groups": (_i, [_i]),
+    "oiva_frame_pitch": (_i, [_i]),
+    "oiva_grouped_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "oiva_grouped_cov_bytes": (_sz, [_i, _i, _i, _i]),
     "oiva_relayout": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "oiva_weighted_cov": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
-    "oiva_demix_power": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
-    "oiva_sum_partials": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _p]),
-    "oiva_source_model": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
-    "oiva_ip_update": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "oiva_unpack_cov": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "oiva_demix_power": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "oiva_sum_partials": (_i, [_p, _i, _p, _i, _i, _i, _p]),
+    "oiva_source_model": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "oiva_ip_update": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "oiva_init_demix": (_i, [_p, _p, _p, _p, _i, _p, _i, _i, _i, _p]),
     "oiva_eigh": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "oiva_projback_filters": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _p]),
@@ -63,7 +64,7 @@ SIGNATURES = {
     "oiva_plan_workspace_bytes": (_sz, [_p]),
     "oiva_plan_bind": (_i, [_p, _p, _sz]),
     "oiva_plan_load": (_i, [_p, _p, _p]),
-    "oiva_plan_adopt_planar": (_i, [_p, _p]),
+    "oiva_plan_adopt_samples": (_i, [_p, _p]),
     "oiva_plan_init": (_i, [_p, _i, _p, _p]),
     "oiva_plan_iterate": (_i, [_p, _i, _p]),
     "oiva_plan_power": (_i, [_p, _p]),
@@ -74,7 +75,7 @@ SIGNATURES = {
     "oiva_plan_filters": (_i, [_p, _p, _p]),
     "oiva_plan_what": (_p, [_p]),
     "oiva_plan_cov": (_p, [_p]),
-    "oiva_plan_planar": (_p, [_p]),
+    "oiva_plan_samples": (_p, [_p]),
     "oiva_plan_status_ptr": (_p, [_p]),
     "oiva_plan_status": (_i, [_p, _p]),
     "oiva_plan_launch_count": (C.c_longlong, [_p]),

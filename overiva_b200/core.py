@@ -93,7 +93,7 @@ class DemixPlan:
         with torch.cuda.device(self.device):
             self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         L.check(self.lib.oiva_plan_bind(h, _ptr(self.ws), nbytes), "oiva_plan_bind")
-        self.Tp = self.lib.oiva_frame_pitch(n_frames, n_chan, self.code)
+        self.Tp = self.lib.oiva_frame_pitch(n_frames)
 
     def __del__(self):
         h, self.h = getattr(self, "h", None), None
@@ -123,8 +123,8 @@ class DemixPlan:
         return self._view(self.lib.oiva_plan_cov(self.h), n * 16, torch.complex128, (self.B, self.F, self.M, self.M))
 
     @property
-    def planar_ptr(self):
-        return self.lib.oiva_plan_planar(self.h)
+    def samples_ptr(self):
+        return self.lib.oiva_plan_samples(self.h)
 
     # -- steps ------------------------------------------------------------------------------------
     def load(self, X):
@@ -132,8 +132,8 @@ class DemixPlan:
         assert tuple(X.shape) == (self.B, self.T, self.F, self.M), (tuple(X.shape), (self.B, self.T, self.F, self.M))
         L.check(self.lib.oiva_plan_load(self.h, _ptr(X), _stream_ptr(self.device)), "oiva_plan_load")
 
-    def adopt_planar(self):
-        L.check(self.lib.oiva_plan_adopt_planar(self.h, _stream_ptr(self.device)), "oiva_plan_adopt_planar")
+    def adopt_samples(self):
+        L.check(self.lib.oiva_plan_adopt_samples(self.h, _stream_ptr(self.device)), "oiva_plan_adopt_samples")
 
     def init(self, mode, W0=None):
         if W0 is not None:
@@ -326,9 +326,9 @@ def auxiva_pca(X, n_src=None, **kwargs):
                                   st), "oiva_eigh")
             E = evecs[:, :, M - K :].contiguous()
             red = DemixPlan(1, T, F, K, K, _model_code(model), inp.dtype, dev)
-            L.check(lib.oiva_project_rows(full.planar_ptr, _ptr(E), red.planar_ptr, 1, T, F, M, K, code, st),
+            L.check(lib.oiva_project_rows(full.samples_ptr, _ptr(E), red.samples_ptr, 1, T, F, M, K, code, st),
                     "oiva_project_rows")
-            red.adopt_planar()
+            red.adopt_samples()
         else:
             E, red = None, full
         if W0 is not None:
@@ -357,7 +357,7 @@ def auxiva_pca(X, n_src=None, **kwargs):
         L.check(lib.oiva_projback_filters(_ptr(Wfull), K, _ptr(full.cov), _ptr(Weff), F, M, K, 1, st),
                 "oiva_projback_filters")
         Y = torch.empty((1, T, F, K), dtype=inp.dtype, device=dev)
-        L.check(lib.oiva_demix_output(full.planar_ptr, _ptr(Weff), _ptr(Y), 1, T, F, M, K, code, st),
+        L.check(lib.oiva_demix_output(full.samples_ptr, _ptr(Weff), _ptr(Y), 1, T, F, M, K, code, st),
                 "oiva_demix_output")
         red.raise_on_failure()
         if red is not full:
@@ -406,10 +406,11 @@ def ogive(X, n_iter=4000, step_size=0.1, tol=1e-3, update="demix", proj_back=Tru
             w[:, 0] = 1.0  # ive.py:125-127
         L.check(lib.oiva_ogive_a_from_w(_ptr(w), _ptr(a), _ptr(Cx), F, M, st), "oiva_ogive_a_from_w")  # ive.py:168
         do_a = torch.full((F,), 1 if update == "mix" else 0, dtype=torch.uint8, device=dev)  # ive.py:170-175
-        nch = lib.oiva_power_chunks(1, F)
+        nch = lib.oiva_bin_groups(F)
         Tp = plan.Tp
         r2part = torch.empty((nch, Tp), dtype=torch.float64, device=dev)
         phi = torch.empty((Tp,), dtype=torch.float64, device=dev)
+        Vg = torch.empty(lib.oiva_grouped_cov_bytes(1, F, M, 1), dtype=torch.uint8, device=dev)
         V = torch.empty((F, M, M), **c128)
         dmax = torch.zeros((1,), dtype=torch.float64, device=dev)
 
@@ -418,7 +419,7 @@ def ogive(X, n_iter=4000, step_size=0.1, tol=1e-3, update="demix", proj_back=Tru
             L.check(lib.oiva_projback_filters(_ptr(wcur), 1, _ptr(Cx), _ptr(Weff), F, M, 1, int(bool(proj_back)), st),
                     "oiva_projback_filters")
             Y = torch.empty((1, T, F, 1), dtype=inp.dtype, device=dev)
-            L.check(lib.oiva_demix_output(plan.planar_ptr, _ptr(Weff), _ptr(Y), 1, T, F, M, 1, code, st),
+            L.check(lib.oiva_demix_output(plan.samples_ptr, _ptr(Weff), _ptr(Y), 1, T, F, M, 1, code, st),
                     "oiva_demix_output")
             return Y[0]
 
@@ -428,12 +429,13 @@ def ogive(X, n_iter=4000, step_size=0.1, tol=1e-3, update="demix", proj_back=Tru
                         "oiva_ogive_switching")
             if callback is not None and epoch % 100 == 0:  # ive.py:194-200
                 callback(inp.give_back(project(w)))
-            L.check(lib.oiva_demix_power(plan.planar_ptr, _ptr(w), 1, _ptr(r2part), nch, 1, T, F, M, 1, code, st),
+            L.check(lib.oiva_demix_power(plan.samples_ptr, _ptr(w), 1, _ptr(r2part), 1, T, F, M, 1, code, st),
                     "oiva_demix_power")
-            L.check(lib.oiva_source_model(_ptr(r2part), nch, _ptr(phi), None, 1, T, M, 1, F, mcode, code, st),
+            L.check(lib.oiva_source_model(_ptr(r2part), nch, _ptr(phi), None, 1, T, 1, F, mcode, st),
                     "oiva_source_model")
-            L.check(lib.oiva_weighted_cov(plan.planar_ptr, _ptr(phi), _ptr(V), 1, T, F, M, 1, code, st),
+            L.check(lib.oiva_weighted_cov(plan.samples_ptr, _ptr(phi), _ptr(Vg), 1, T, F, M, 1, code, st),
                     "oiva_weighted_cov")
+            L.check(lib.oiva_unpack_cov(_ptr(Vg), _ptr(V), 1, F, M, 1, st), "oiva_unpack_cov")
             dmax.zero_()
             L.check(lib.oiva_ogive_update(_ptr(w), _ptr(a), _ptr(lam), _ptr(V), _ptr(Cx), _ptr(Cinv), _ptr(do_a),
                                           float(step_size), _ptr(dmax), F, M, st), "oiva_ogive_update")

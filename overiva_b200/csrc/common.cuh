@@ -10,36 +10,39 @@
 #define OIVA_WARP 32
 
 // ----------------------------------------------------------------------------------------------
-// Planar row layout ("Xp") -- how the STFT lives in HBM for the whole loop.
+// Grouped layout ("Xg") -- how the STFT lives in HBM for the whole loop: lane <-> frequency bin.
 //
-// The caller's X is (B, T, F, M) interleaved complex (the reference's (T, F, M), overiva.py:80).
-// The reference itself re-lays it out as (F, T, M) (overiva.py:132); here one relayout kernel writes,
-// for every row = (mixture b, bin f), nT consecutive tiles
-//      tile i : [plane = 2*c + ri][pitch_i frames]           (ST = double or float)
-// with pitch_i = TT (a multiple of 32) for all but the last tile and TL = T - (nT-1)*TT for the last
-// one (ragged: no padding in HBM, so tiling costs no bytes; for float storage TL is bumped by one zero
-// frame when needed to keep every tile a multiple of 16 bytes).  For each channel c a tile holds a
-// plane of real parts followed by a plane of imaginary parts.  Consecutive lanes of a warp read
-// consecutive frames of one plane: every 32-lane load is one contiguous 256 B (fp64) segment,
-// conflict-free in shared memory and fully coalesced in global memory, and a tile is one contiguous
-// block, i.e. exactly one cp.async.bulk (TMA) transaction.
+// The caller's X is (B, T, F, M) interleaved complex (the reference's (T, F, M), overiva.py:80); the
+// reference re-lays it out as (F, T, M) (overiva.py:132).  Here the bins of every mixture are cut into
+// NG = ceil(F/32) groups of 32 consecutive bins (the last group zero-padded) and one relayout kernel writes
+//      Xg[gi = b*NG + g][t][c][l]      complex<ST>,  l = bin % 32
+// Every per-bin quantity of the algorithm (covariances, demixing vectors) is then private to ONE LANE of a
+// warp, so the streaming kernels need no cross-lane reduction for the covariance, a warp load of one
+// (t, c) is 32 consecutive complex numbers (512 B in fp64: conflict-free LDS.128 / fully coalesced LDG.128),
+// ANY range of frames of a group is one contiguous block (= one cp.async.bulk / TMA transaction, no tile
+// structure in memory), and the (T, F, K)-ordered output is written as 32*K consecutive complex numbers
+// per warp.  Weighted covariances use the same grouping: Vg[gi][k][e][l] for the lower-triangle entries
+// e = i(i+1)/2 + j (i >= j).
 // ----------------------------------------------------------------------------------------------
-struct RowLayout {
-    int T;    // frames
-    int TT;   // frames per full tile (multiple of 32)
-    int nT;   // tiles per row
-    int TL;   // allocated frames of the last tile (>= valid frames of the last tile)
-    int M;    // channels
-    __host__ __device__ int pitch(int tile) const { return tile + 1 < nT ? TT : TL; }
-    __host__ __device__ int valid(int tile) const {
-        int v = T - tile * TT;
-        return v < TT ? v : TT;
-    }
-    __host__ __device__ size_t tile_off(int tile) const { return (size_t)tile * 2 * M * TT; }
-    __host__ __device__ size_t row_elems() const { return (size_t)2 * M * ((size_t)(nT - 1) * TT + TL); }
-    __host__ __device__ int frame_pitch() const { return nT * TT; }  // pitch of phi / r2 rows
+#define OIVA_GROUP 32
+struct GroupLayout {
+    int T;   // frames
+    int F;   // bins per mixture
+    int NG;  // groups per mixture = ceil(F / 32)
+    int M;   // channels
+    __host__ __device__ size_t frame_elems() const { return (size_t)M * OIVA_GROUP; }        // complex per frame
+    __host__ __device__ size_t group_elems() const { return (size_t)T * M * OIVA_GROUP; }    // complex per group
+    __host__ __device__ int frame_pitch() const { return ((T + 31) / 32) * 32; }             // phi / r2 rows
 };
-RowLayout oiva_make_layout(int n_frames, int n_chan, int dtype);
+static inline GroupLayout oiva_make_layout(int n_frames, int n_freq, int n_chan) {
+    GroupLayout L;
+    L.T = n_frames;
+    L.F = n_freq;
+    L.NG = (n_freq + OIVA_GROUP - 1) / OIVA_GROUP;
+    L.M = n_chan;
+    return L;
+}
+__host__ __device__ constexpr int oiva_tri(int M) { return M * (M + 1) / 2; }
 
 // ----------------------------------------------------------------------------------------------
 // complex helpers (double2: x = re, y = im)
@@ -110,6 +113,17 @@ __device__ __forceinline__ cplx shfl_xor_c(cplx v, int mask) {
 __device__ __forceinline__ double ld_nc(const double* p) { return __ldg(p); }
 __device__ __forceinline__ double ld_nc(const float* p) { return (double)__ldg(p); }
 __device__ __forceinline__ cplx ld_nc_c(const cplx* p) { return __ldg(p); }
+
+// storage complex type for X / Y: double2 (c128) or float2 (c64); arithmetic is always fp64
+template <typename ST> struct StoreC;
+template <> struct StoreC<double> { typedef double2 type; };
+template <> struct StoreC<float> { typedef float2 type; };
+__device__ __forceinline__ cplx widen(double2 v) { return v; }
+__device__ __forceinline__ cplx widen(float2 v) { return make_double2((double)v.x, (double)v.y); }
+__device__ __forceinline__ void narrow(double2& o, cplx v) { o = v; }
+__device__ __forceinline__ void narrow(float2& o, cplx v) { o = make_float2((float)v.x, (float)v.y); }
+__device__ __forceinline__ cplx ldg_x(const double2* p) { return __ldg(p); }
+__device__ __forceinline__ cplx ldg_x(const float2* p) { return widen(__ldg(p)); }
 
 // ----------------------------------------------------------------------------------------------
 // mbarrier + bulk TMA (cp.async.bulk, 1-D global -> shared) -- sm_90+/sm_100a PTX

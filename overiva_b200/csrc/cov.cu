@@ -4,7 +4,9 @@
 #include "cov.cuh"
 
 namespace oiva {
-#define OIVA_DECL(M) int cov_launch_m##M(int dtype, int KC, int use_tma, const CovParams& p, cudaStream_t st);
+#define OIVA_DECL(M)                                                                                 \
+    int cov_launch_m##M(int dtype, int KC, int use_tma, const CovParams& p, cudaStream_t st);        \
+    int cov_max_kc_m##M();
 OIVA_DECL(1) OIVA_DECL(2) OIVA_DECL(3) OIVA_DECL(4) OIVA_DECL(5) OIVA_DECL(6) OIVA_DECL(7) OIVA_DECL(8)
 OIVA_DECL(9) OIVA_DECL(10) OIVA_DECL(11) OIVA_DECL(12) OIVA_DECL(13) OIVA_DECL(14) OIVA_DECL(15) OIVA_DECL(16)
 #undef OIVA_DECL
@@ -32,40 +34,37 @@ static int get_ones(size_t n, cudaStream_t st, const double** out) {
     *out = g_ones[dev];
     return OIVA_OK;
 }
-__global__ void k_cov_mirror(double* __restrict__ V, long long R, int K, int k0, int KC, int M) {
-    const long long n = R * KC * M * M;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
-    const int j = (int)(idx % M), i = (int)((idx / M) % M);
-    if (i <= j) return;
-    const int k = (int)((idx / ((long long)M * M)) % KC);
-    const long long row = idx / ((long long)M * M * KC);
-    double* base = V + (((size_t)row * K + k0 + k) * M * M) * 2;
-    const double re = base[((size_t)i * M + j) * 2], im = base[((size_t)i * M + j) * 2 + 1];
-    base[((size_t)j * M + i) * 2] = re;
-    base[((size_t)j * M + i) * 2 + 1] = -im;
+
+static int pick_chunk(int rem, int max_kc) {
+    static const int sizes[] = {1, 2, 3, 4, 6, 8};
+    int best = 1;
+    for (int s : sizes) {
+        if (s > max_kc) break;
+        if (s >= rem) return s;  // smallest chunk that covers the remainder in one pass
+        best = s;
+    }
+    return best;  // largest usable chunk; more passes follow
 }
 }  // namespace oiva
 
-extern "C" int oiva_weighted_cov(const void* Xp, const double* phi, void* V, int n_batch, int n_frames, int n_freq,
+extern "C" int oiva_weighted_cov(const void* Xg, const double* phi, void* Vg, int n_batch, int n_frames, int n_freq,
                                  int n_chan, int n_src, int dtype, void* stream) {
     using namespace oiva;
-    OIVA_REQUIRE(Xp && V, "oiva_weighted_cov: null pointer");
+    OIVA_REQUIRE(Xg && Vg, "oiva_weighted_cov: null pointer");
     OIVA_REQUIRE(n_batch > 0 && n_frames > 0 && n_freq > 0 && n_chan >= 1 && n_chan <= OIVA_MAX_M && n_src >= 1,
                  "oiva_weighted_cov: bad shape B=%d T=%d F=%d M=%d K=%d", n_batch, n_frames, n_freq, n_chan, n_src);
     OIVA_REQUIRE(phi || n_src == 1, "oiva_weighted_cov: phi == NULL needs n_src == 1");
     cudaStream_t st = (cudaStream_t)stream;
     CovParams p;
-    p.Xp = Xp;
-    p.V = (double*)V;
-    p.L = oiva_make_layout(n_frames, n_chan, dtype);
-    p.R = n_batch * n_freq;
-    p.F = n_freq;
+    p.Xg = Xg;
+    p.Vg = (cplx*)Vg;
+    p.L = oiva_make_layout(n_frames, n_freq, n_chan);
+    p.G = (long long)n_batch * p.L.NG;
+    p.NGphi = p.L.NG;
     p.K = n_src;
     p.invT = 1.0 / (double)n_frames;
     p.nsplit = 1;
-    p.stages = 3;
-    p.xpitch = p.ppitch = 0;
+    p.stages = 4;
     if (phi) {
         p.phi = phi;
     } else {
@@ -73,14 +72,23 @@ extern "C" int oiva_weighted_cov(const void* Xp, const double* phi, void* V, int
         int rc = get_ones((size_t)p.L.frame_pitch(), st, &ones);
         if (rc) return rc;
         p.phi = ones;
-        p.F = p.R + 1;  // every row maps to "mixture 0": the ones buffer holds one (K=1, Tp) block
+        OIVA_REQUIRE(p.G < (1ll << 31), "oiva_weighted_cov: too many groups");
+        p.NGphi = (int)p.G;  // every group maps to "mixture 0": the ones buffer holds one (K=1, Tp) block
     }
     const char* env = getenv("OIVA_COV_NO_TMA");
     const int use_tma = !(env && *env && *env != '0');
+    int max_kc = 1;
+    switch (n_chan) {
+#define OIVA_CASE(M) case M: max_kc = cov_max_kc_m##M(); break;
+        OIVA_CASE(1) OIVA_CASE(2) OIVA_CASE(3) OIVA_CASE(4) OIVA_CASE(5) OIVA_CASE(6) OIVA_CASE(7) OIVA_CASE(8)
+        OIVA_CASE(9) OIVA_CASE(10) OIVA_CASE(11) OIVA_CASE(12) OIVA_CASE(13) OIVA_CASE(14) OIVA_CASE(15) OIVA_CASE(16)
+#undef OIVA_CASE
+    }
+    if (!use_tma && max_kc > 2) max_kc = 2;
     int k0 = 0;
     while (k0 < n_src) {
-        int rem = n_src - k0;
-        int KC = rem >= 4 ? 4 : (rem >= 2 ? 2 : 1);
+        int KC = pick_chunk(n_src - k0, max_kc);
+        if (!use_tma && KC > n_src - k0) KC = n_src - k0 >= 2 ? 2 : 1;
         p.k0 = k0;
         int rc = OIVA_ERR_INVALID;
         switch (n_chan) {

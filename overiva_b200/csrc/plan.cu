@@ -18,12 +18,12 @@ struct TimedSpan {
 struct oiva_plan {
     oiva_plan_desc d;
     int n_freq_total;
-    long long R;
-    RowLayout L;
-    int Tp, NCH;
+    long long R, G;
+    GroupLayout L;
+    int Tp, NG;
     int es;  // bytes per real element of X / Y
     // workspace offsets
-    size_t off_xp, off_c, off_what, off_v, off_weff, off_r2part, off_r2, off_phi, off_wscale, off_evals, off_status;
+    size_t off_xg, off_c, off_cg, off_what, off_vg, off_weff, off_r2part, off_r2, off_phi, off_wscale, off_evals, off_status;
     size_t ws_bytes;
     unsigned char* ws;
     long long launches;
@@ -65,12 +65,13 @@ struct SpanGuard {  // records an event pair around a launch sequence when timin
 };
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+static size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
 
 extern "C" int oiva_plan_create(oiva_plan_t** out, const oiva_plan_desc* desc) {
     OIVA_REQUIRE(out && desc, "oiva_plan_create: null pointer");
     const oiva_plan_desc& d = *desc;
-    OIVA_REQUIRE(d.n_batch > 0 && d.n_batch <= 65535 && d.n_frames > 0 && d.n_freq > 0, "oiva_plan_create: bad shape B=%d T=%d F=%d",
-                 d.n_batch, d.n_frames, d.n_freq);
+    OIVA_REQUIRE(d.n_batch > 0 && d.n_batch <= 65535 && d.n_frames > 0 && d.n_freq > 0,
+                 "oiva_plan_create: bad shape B=%d T=%d F=%d", d.n_batch, d.n_frames, d.n_freq);
     OIVA_REQUIRE(d.n_chan >= 1 && d.n_chan <= OIVA_MAX_M, "oiva_plan_create: n_chan=%d not in 1..16", d.n_chan);
     OIVA_REQUIRE(d.n_src >= 1 && d.n_src <= d.n_chan, "oiva_plan_create: n_src=%d not in 1..n_chan=%d", d.n_src,
                  d.n_chan);
@@ -86,18 +87,21 @@ extern "C" int oiva_plan_create(oiva_plan_t** out, const oiva_plan_desc* desc) {
     p->d = d;
     p->n_freq_total = d.n_freq_total > 0 ? d.n_freq_total : d.n_freq;
     p->R = (long long)d.n_batch * d.n_freq;
-    p->L = oiva_make_layout(d.n_frames, d.n_chan, d.dtype);
+    p->L = oiva_make_layout(d.n_frames, d.n_freq, d.n_chan);
+    p->NG = p->L.NG;
+    p->G = (long long)d.n_batch * p->NG;
     p->Tp = p->L.frame_pitch();
-    p->NCH = oiva_power_chunks(d.n_batch, d.n_freq);
     p->es = d.dtype == OIVA_C64 ? 4 : 8;
-    const size_t M = d.n_chan, K = d.n_src, R = (size_t)p->R, B = d.n_batch;
+    const size_t M = d.n_chan, K = d.n_src, R = (size_t)p->R, B = d.n_batch, G = (size_t)p->G;
     size_t o = 0;
-    p->off_xp = o;      o += align_up(R * p->L.row_elems() * p->es);
+    p->off_xg = o;      o += align_up(oiva_grouped_bytes(d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.dtype));
     p->off_c = o;       o += align_up(R * M * M * 16);
+    p->off_cg = o;      o += align_up(G * oiva_tri((int)M) * OIVA_GROUP * 16);
     p->off_what = o;    o += align_up(R * M * M * 16);
-    p->off_v = o;       o += align_up(R * (K > 1 ? K : 1) * M * M * 16);  // also holds eigenvectors at init
+    // grouped covariances of the K sources; also scratch for the eigenvectors at init time
+    p->off_vg = o;      o += align_up(max_sz(G * K * oiva_tri((int)M) * OIVA_GROUP * 16, R * M * M * 16));
     p->off_weff = o;    o += align_up(R * M * K * 16);
-    p->off_r2part = o;  o += align_up(B * p->NCH * K * p->Tp * 8);
+    p->off_r2part = o;  o += align_up(B * p->NG * K * p->Tp * 8);
     p->off_r2 = o;      o += align_up(B * K * p->Tp * 8);
     p->off_phi = o;     o += align_up(B * K * p->Tp * 8);
     p->off_wscale = o;  o += align_up(B * K * 8);
@@ -170,7 +174,7 @@ extern "C" int oiva_plan_bind(oiva_plan_t* plan, void* workspace, size_t bytes) 
 
 extern "C" void* oiva_plan_what(oiva_plan_t* p) { return (p && p->ws) ? p->ws + p->off_what : nullptr; }
 extern "C" void* oiva_plan_cov(oiva_plan_t* p) { return (p && p->ws) ? p->ws + p->off_c : nullptr; }
-extern "C" void* oiva_plan_planar(oiva_plan_t* p) { return (p && p->ws) ? p->ws + p->off_xp : nullptr; }
+extern "C" void* oiva_plan_samples(oiva_plan_t* p) { return (p && p->ws) ? p->ws + p->off_xg : nullptr; }
 extern "C" int* oiva_plan_status_ptr(oiva_plan_t* p) { return (p && p->ws) ? (int*)(p->ws + p->off_status) : nullptr; }
 extern "C" double* oiva_plan_r2(oiva_plan_t* p) { return (p && p->ws) ? (double*)(p->ws + p->off_r2) : nullptr; }
 extern "C" size_t oiva_plan_r2_elems(const oiva_plan_t* p) {
@@ -178,31 +182,38 @@ extern "C" size_t oiva_plan_r2_elems(const oiva_plan_t* p) {
 }
 extern "C" long long oiva_plan_launch_count(const oiva_plan_t* p) { return p ? p->launches : 0; }
 
+// input covariance C = (1/T) sum_t x x^H (overiva.py:87): grouped accumulation, then full row-major matrices
+static int plan_input_cov(oiva_plan_t* p, void* stream) {
+    const oiva_plan_desc& d = p->d;
+    int rc = oiva_weighted_cov(p->ws + p->off_xg, nullptr, p->ws + p->off_cg, d.n_batch, d.n_frames, d.n_freq, d.n_chan,
+                               1, d.dtype, stream);
+    if (rc) return rc;
+    rc = oiva_unpack_cov(p->ws + p->off_cg, p->ws + p->off_c, d.n_batch, d.n_freq, d.n_chan, 1, stream);
+    if (rc) return rc;
+    p->launches += 2;
+    return OIVA_OK;
+}
+
 extern "C" int oiva_plan_load(oiva_plan_t* p, const void* X, void* stream) {
     PLAN_READY(p, "oiva_plan_load");
     OIVA_REQUIRE(X, "oiva_plan_load: null X");
     const oiva_plan_desc& d = p->d;
     OIVA_CUDA_CHECK(cudaMemsetAsync(p->ws + p->off_status, 0, 16, (cudaStream_t)stream));
-    int rc = oiva_relayout(X, p->ws + p->off_xp, d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.dtype, stream);
+    int rc = oiva_relayout(X, p->ws + p->off_xg, d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.dtype, stream);
     if (rc) return rc;
-    // input covariance C = (1/T) sum_t x x^H                                           overiva.py:87
-    rc = oiva_weighted_cov(p->ws + p->off_xp, nullptr, p->ws + p->off_c, d.n_batch, d.n_frames, d.n_freq, d.n_chan, 1,
-                           d.dtype, stream);
+    p->launches += 1;
+    rc = plan_input_cov(p, stream);
     if (rc) return rc;
-    p->launches += 2;
     p->loaded = true;
     p->inited = false;
     return OIVA_OK;
 }
 
-extern "C" int oiva_plan_adopt_planar(oiva_plan_t* p, void* stream) {
-    PLAN_READY(p, "oiva_plan_adopt_planar");
-    const oiva_plan_desc& d = p->d;
+extern "C" int oiva_plan_adopt_samples(oiva_plan_t* p, void* stream) {
+    PLAN_READY(p, "oiva_plan_adopt_samples");
     OIVA_CUDA_CHECK(cudaMemsetAsync(p->ws + p->off_status, 0, 16, (cudaStream_t)stream));
-    int rc = oiva_weighted_cov(p->ws + p->off_xp, nullptr, p->ws + p->off_c, d.n_batch, d.n_frames, d.n_freq, d.n_chan,
-                               1, d.dtype, stream);
+    int rc = plan_input_cov(p, stream);
     if (rc) return rc;
-    p->launches += 1;
     p->loaded = true;
     p->inited = false;
     return OIVA_OK;
@@ -219,10 +230,10 @@ extern "C" int oiva_plan_init(oiva_plan_t* p, int mode, const void* W0, void* st
     const void* evecs = nullptr;
     if (mode == OIVA_INIT_EIG) {
         // principal eigenvectors of C with np.linalg.eig's phase convention            overiva.py:103-109
-        int rc = oiva_eigh(p->ws + p->off_c, (double*)(p->ws + p->off_evals), p->ws + p->off_v, status, (int)p->R,
+        int rc = oiva_eigh(p->ws + p->off_c, (double*)(p->ws + p->off_evals), p->ws + p->off_vg, status, (int)p->R,
                            d.n_chan, 1, stream);
         if (rc) return rc;
-        evecs = p->ws + p->off_v;
+        evecs = p->ws + p->off_vg;
         p->launches += 1;
     }
     int rc = oiva_init_demix(p->ws + p->off_what, p->ws + p->off_c, W0, evecs, mode, status, (int)p->R, d.n_chan,
@@ -236,10 +247,10 @@ extern "C" int oiva_plan_init(oiva_plan_t* p, int mode, const void* W0, void* st
 static int plan_power_partials(oiva_plan_t* p, void* stream) {
     const oiva_plan_desc& d = p->d;
     SpanGuard g(p, TK_POWER, stream);
-    int rc = oiva_demix_power(p->ws + p->off_xp, p->ws + p->off_what, d.n_chan, (double*)(p->ws + p->off_r2part), p->NCH,
+    int rc = oiva_demix_power(p->ws + p->off_xg, p->ws + p->off_what, d.n_chan, (double*)(p->ws + p->off_r2part),
                               d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.n_src, d.dtype, stream);
     if (rc) return rc;
-    p->launches += (d.n_src + 7) / 8;
+    p->launches += 1;
     return OIVA_OK;
 }
 
@@ -247,18 +258,18 @@ static int plan_update_from(oiva_plan_t* p, const double* r2src, int nch, void* 
     const oiva_plan_desc& d = p->d;
     double* phi = (double*)(p->ws + p->off_phi);
     double* wscale = (double*)(p->ws + p->off_wscale);
-    int rc = oiva_source_model(r2src, nch, phi, wscale, d.n_batch, d.n_frames, d.n_chan, d.n_src, p->n_freq_total,
-                               d.model, d.dtype, stream);
+    int rc = oiva_source_model(r2src, nch, phi, wscale, d.n_batch, d.n_frames, d.n_src, p->n_freq_total, d.model,
+                               stream);
     if (rc) return rc;
     {
         SpanGuard g(p, TK_COV, stream);
-        rc = oiva_weighted_cov(p->ws + p->off_xp, phi, p->ws + p->off_v, d.n_batch, d.n_frames, d.n_freq, d.n_chan,
+        rc = oiva_weighted_cov(p->ws + p->off_xg, phi, p->ws + p->off_vg, d.n_batch, d.n_frames, d.n_freq, d.n_chan,
                                d.n_src, d.dtype, stream);
     }
     if (rc) return rc;
     {
         SpanGuard g(p, TK_SOLVE, stream);
-        rc = oiva_ip_update(p->ws + p->off_what, p->ws + p->off_v, p->ws + p->off_c, wscale,
+        rc = oiva_ip_update(p->ws + p->off_what, p->ws + p->off_vg, p->ws + p->off_c, p->ws + p->off_cg, wscale,
                             (int*)(p->ws + p->off_status), d.n_batch, d.n_freq, d.n_chan, d.n_src, stream);
     }
     if (rc) return rc;
@@ -278,7 +289,7 @@ extern "C" int oiva_plan_iterate(oiva_plan_t* p, int n_iter, void* stream) {
     for (int it = 0; it < n_iter; ++it) {
         int rc = plan_power_partials(p, stream);
         if (rc) return rc;
-        rc = plan_update_from(p, (const double*)(p->ws + p->off_r2part), p->NCH, stream);
+        rc = plan_update_from(p, (const double*)(p->ws + p->off_r2part), p->NG, stream);
         if (rc) return rc;
     }
     return OIVA_OK;
@@ -288,8 +299,8 @@ extern "C" int oiva_plan_power(oiva_plan_t* p, void* stream) {
     PLAN_INITED(p, "oiva_plan_power");
     int rc = plan_power_partials(p, stream);
     if (rc) return rc;
-    rc = oiva_sum_partials((const double*)(p->ws + p->off_r2part), p->NCH, (double*)(p->ws + p->off_r2), p->d.n_batch,
-                           p->d.n_frames, p->d.n_chan, p->d.n_src, p->d.dtype, stream);
+    rc = oiva_sum_partials((const double*)(p->ws + p->off_r2part), p->NG, (double*)(p->ws + p->off_r2), p->d.n_batch,
+                           p->d.n_frames, p->d.n_src, stream);
     if (rc) return rc;
     p->launches += 1;
     return OIVA_OK;
@@ -304,10 +315,10 @@ extern "C" int oiva_plan_output(oiva_plan_t* p, int proj_back, void* Y, void* st
     PLAN_INITED(p, "oiva_plan_output");
     OIVA_REQUIRE(Y, "oiva_plan_output: null Y");
     const oiva_plan_desc& d = p->d;
-    int rc = oiva_projback_filters(p->ws + p->off_what, d.n_chan, p->ws + p->off_c, p->ws + p->off_weff, (int)p->R, d.n_chan,
-                                   d.n_src, proj_back, stream);
+    int rc = oiva_projback_filters(p->ws + p->off_what, d.n_chan, p->ws + p->off_c, p->ws + p->off_weff, (int)p->R,
+                                   d.n_chan, d.n_src, proj_back, stream);
     if (rc) return rc;
-    rc = oiva_demix_output(p->ws + p->off_xp, p->ws + p->off_weff, Y, d.n_batch, d.n_frames, d.n_freq, d.n_chan,
+    rc = oiva_demix_output(p->ws + p->off_xg, p->ws + p->off_weff, Y, d.n_batch, d.n_frames, d.n_freq, d.n_chan,
                            d.n_src, d.dtype, stream);
     if (rc) return rc;
     p->launches += 2;
@@ -319,7 +330,8 @@ extern "C" int oiva_plan_filters(oiva_plan_t* p, void* W, void* stream) {
     OIVA_REQUIRE(W, "oiva_plan_filters: null W");
     const oiva_plan_desc& d = p->d;
     // plain copy of the W columns: proj_back = 0
-    int rc = oiva_projback_filters(p->ws + p->off_what, d.n_chan, p->ws + p->off_c, W, (int)p->R, d.n_chan, d.n_src, 0, stream);
+    int rc = oiva_projback_filters(p->ws + p->off_what, d.n_chan, p->ws + p->off_c, W, (int)p->R, d.n_chan, d.n_src, 0,
+                                   stream);
     if (rc) return rc;
     p->launches += 1;
     return OIVA_OK;

@@ -1,6 +1,8 @@
 // Per-bin kernels: IP sweep, demixing-matrix initialisation, projection-back scaling, Hermitian eigh.
 // (include/overiva_b200.h: oiva_ip_update, oiva_init_demix, oiva_projback_filters, oiva_eigh,
 //  oiva_compose_filters)
+#include <stdlib.h>
+
 #include "solve.cuh"
 
 namespace oiva {
@@ -11,19 +13,28 @@ constexpr int SOLVE_WARPS = 4;
 // IP sweep over the K sources of every bin (overiva.py:161-167 W rescale, :176-190 source loop)
 // ---------------------------------------------------------------------------------------------------
 template <int M>
-__global__ void __launch_bounds__(SOLVE_WARPS * 32) k_ip_update(cplx* __restrict__ What, const cplx* __restrict__ V,
-                                                                const cplx* __restrict__ C,
-                                                                const double* __restrict__ wscale, int* status,
-                                                                long long R, int F, int K) {
-    constexpr int G = Grp<M>::G, BINS = Grp<M>::BINS;
-    __shared__ cplx sWall[SOLVE_WARPS * BINS * M * M];
+__host__ __device__ constexpr int ip_warps() { return M > 8 ? 2 : 4; }
+
+// V arrives in the grouped lower-triangle layout Vg[gi][k][e][l] written by the covariance kernel.
+template <int M>
+__global__ void __launch_bounds__(ip_warps<M>() * 32) k_ip_update(cplx* __restrict__ What, const cplx* __restrict__ Vg,
+                                                                  const cplx* __restrict__ C,
+                                                                  const double* __restrict__ wscale, int* status,
+                                                                  long long R, int F, int NG, int K) {
+    constexpr int G = Grp<M>::G, BINS = Grp<M>::BINS, WARPS = ip_warps<M>(), NE = oiva_tri(M);
+    __shared__ cplx sWall[WARPS * BINS * M * M];
+    __shared__ cplx sVall[WARPS * BINS * M * M];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / G, gl = lane % G;
-    const long long row = ((long long)blockIdx.x * SOLVE_WARPS + warp) * BINS + grp;
+    const long long row = ((long long)blockIdx.x * WARPS + warp) * BINS + grp;
     const bool row_ok = row < R;
     const long long rowc = row_ok ? row : R - 1;
     cplx* sW = sWall + (size_t)(warp * BINS + grp) * M * M;
+    cplx* Vs = sVall + (size_t)(warp * BINS + grp) * M * M;
     const bool rv = gl < M;
+    const long long bmix = rowc / F;
+    const int fbin = (int)(rowc - bmix * F);
+    const cplx* Vbin = Vg + ((size_t)(bmix * NG + fbin / OIVA_GROUP) * K * NE) * OIVA_GROUP + fbin % OIVA_GROUP;
 
     if (rv) {
 #pragma unroll
@@ -37,7 +48,15 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) k_ip_update(cplx* __restrict
 
     int singular = 0;
     for (int s = 0; s < K; ++s) {
-        const cplx* Vs = V + ((size_t)rowc * K + s) * M * M;
+        // unpack V_s (Hermitian, lower triangle stored) into the bin's shared tile
+        for (int idx = gl; idx < M * M; idx += G) {
+            const int j = idx / M, c = idx - j * M;
+            const int hi = j >= c ? j : c, lo = j >= c ? c : j;
+            cplx v = ld_nc_c(Vbin + ((size_t)s * NE + hi * (hi + 1) / 2 + lo) * OIVA_GROUP);
+            if (j < c) v.y = -v.y;
+            Vs[idx] = v;
+        }
+        __syncwarp();
         // row gl of What^H V_s, augmented with e_s
         cplx A[M + 1];
 #pragma unroll
@@ -46,7 +65,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) k_ip_update(cplx* __restrict
             for (int j = 0; j < M; ++j) {
                 const cplx a = sW[j * M + gl];
 #pragma unroll
-                for (int c = 0; c < M; ++c) cfmac(A[c], a, ld_nc_c(&Vs[j * M + c]));
+                for (int c = 0; c < M; ++c) cfmac(A[c], a, Vs[j * M + c]);
             }
             if (gl == s) A[M] = cmake(1.0, 0.0);
         }
@@ -59,7 +78,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) k_ip_update(cplx* __restrict
         if (rv) {
             wi = sW[gl * M + s];
 #pragma unroll
-            for (int j = 0; j < M; ++j) cfma(u, ld_nc_c(&Vs[gl * M + j]), sW[j * M + s]);
+            for (int j = 0; j < M; ++j) cfma(u, Vs[gl * M + j], sW[j * M + s]);
         }
         const cplx d = group_sum<G>(cmulc(wi, u));
         const cplx inv = crecip(csqrt_(d));
@@ -290,16 +309,29 @@ static int bins_per_cta() {
     return SOLVE_WARPS * Grp<M>::BINS;
 }
 
-extern "C" int oiva_ip_update(void* What, const void* V, const void* C, const double* wscale, int* status,
-                              int n_batch, int n_freq, int n_chan, int n_src, void* stream) {
+namespace oiva {
+int ip_update_tpb(int M, int K, cplx* What, const cplx* Vg, const cplx* Cg, const double* wscale, int* status, int F,
+                  int NG, long long G, cudaStream_t st);
+}
+
+extern "C" int oiva_ip_update(void* What, const void* V, const void* C, const void* Cg, const double* wscale,
+                              int* status, int n_batch, int n_freq, int n_chan, int n_src, void* stream) {
     OIVA_REQUIRE(What && V && C && status, "oiva_ip_update: null pointer");
     OIVA_REQUIRE(n_batch > 0 && n_freq > 0 && n_src >= 1 && n_src <= n_chan, "oiva_ip_update: bad shape");
     const long long R = (long long)n_batch * n_freq;
     cudaStream_t st = (cudaStream_t)stream;
+    const char* env = getenv("OIVA_SOLVER_ROWOWNER");
+    const bool force_rowowner = env && *env && *env != '0';
+    if (Cg && n_chan <= 6 && !force_rowowner) {  // thread-per-bin sweep (solve_tpb.cuh)
+        const int NG = oiva_bin_groups(n_freq);
+        int rc = ip_update_tpb(n_chan, n_src, (cplx*)What, (const cplx*)V, (const cplx*)Cg, wscale, status, n_freq, NG,
+                               (long long)n_batch * NG, st);
+        if (rc != OIVA_ERR_INVALID) return rc;
+    }
     OIVA_DISPATCH_M(n_chan, {
-        const int per = bins_per_cta<M_>();
-        k_ip_update<M_><<<(unsigned)((R + per - 1) / per), SOLVE_WARPS * 32, 0, st>>>(
-            (cplx*)What, (const cplx*)V, (const cplx*)C, wscale, status, R, n_freq, n_src);
+        const int per = ip_warps<M_>() * Grp<M_>::BINS;
+        k_ip_update<M_><<<(unsigned)((R + per - 1) / per), ip_warps<M_>() * 32, 0, st>>>(
+            (cplx*)What, (const cplx*)V, (const cplx*)C, wscale, status, R, n_freq, oiva_bin_groups(n_freq), n_src);
     });
     OIVA_LAUNCH_CHECK();
     return OIVA_OK;

@@ -1,0 +1,30 @@
+// Instantiations + launcher of the thread-per-bin IP sweep (solve_tpb.cuh) for M <= 6, K <= M.
+#include "solve_tpb.cuh"
+
+namespace oiva {
+
+template <int M, int K>
+static int launch_tpb(cplx* What, const cplx* Vg, const cplx* Cg, const double* wscale, int* status, int F, int NG,
+                      long long G, cudaStream_t st) {
+    const long long threads = G * 32;
+    k_ip_update_tpb<M, K><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(What, Vg, Cg, wscale, status, F, NG, G);
+    OIVA_LAUNCH_CHECK();
+    return OIVA_OK;
+}
+
+// returns OIVA_ERR_INVALID (without setting an error) when (M, K) is not covered
+int ip_update_tpb(int M, int K, cplx* What, const cplx* Vg, const cplx* Cg, const double* wscale, int* status, int F,
+                  int NG, long long G, cudaStream_t st) {
+#define OIVA_TPB(M_, K_) \
+    if (M == M_ && K == K_) return launch_tpb<M_, K_>(What, Vg, Cg, wscale, status, F, NG, G, st);
+    OIVA_TPB(1, 1)
+    OIVA_TPB(2, 1) OIVA_TPB(2, 2)
+    OIVA_TPB(3, 1) OIVA_TPB(3, 2) OIVA_TPB(3, 3)
+    OIVA_TPB(4, 1) OIVA_TPB(4, 2) OIVA_TPB(4, 3) OIVA_TPB(4, 4)
+    OIVA_TPB(5, 1) OIVA_TPB(5, 2) OIVA_TPB(5, 3) OIVA_TPB(5, 4) OIVA_TPB(5, 5)
+    OIVA_TPB(6, 1) OIVA_TPB(6, 2) OIVA_TPB(6, 3) OIVA_TPB(6, 4) OIVA_TPB(6, 5) OIVA_TPB(6, 6)
+#undef OIVA_TPB
+    return OIVA_ERR_INVALID;
+}
+
+}  // namespace oiva

@@ -1,183 +1,181 @@
-// Streaming demix kernels (lane <-> frame over the planar rows):
-//   k_demix_power : r2part[b][chunk][k][t] = sum_{f in chunk} |w_k(f)^H x(f,t)|^2     (overiva.py:140,152-155)
-//   k_demix_output: Y[b][t][f][k] = weff_k(f)^H x(f,t)                                 (overiva.py:192-199)
-//   k_project_rows: planar rows of the K-channel signal E_K^H x                        (auxiva_pca.py:79-81)
-// Every element of X is read exactly once, by one lane, as part of a contiguous 256-byte warp segment, so
-// these kernels read global memory directly (no shared-memory staging: there is no reuse to capture).
+// Streaming demix kernels over the grouped layout (lane <-> frequency bin):
+//   k_demix_power : r2part[b][g][k][t] = sum_{32 bins of group g} |w_k(f)^H x(f,t)|^2   (overiva.py:140,152-155)
+//   k_demix_output: Y[b][t][f][k] = weff_k(f)^H x(f,t)                                   (overiva.py:192-199)
+//   k_project_rows: grouped samples of the K-channel signal E_K^H x                      (auxiva_pca.py:79-81)
+// Each lane keeps ITS bin's demixing vectors in registers for the whole frame range, every element of X is
+// read exactly once as part of a 512-byte warp segment, so these kernels read global memory directly (no
+// shared-memory staging: there is no reuse to capture), and the (T,F,K)-ordered output is written as
+// 32*K consecutive complex numbers per warp and frame.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace oiva {
 
-constexpr int STREAM_WARPS = 4;
+constexpr int POWER_FB = 8;  // frames reduced together in the power kernel
 
 struct StreamParams {
-    const void* Xp;
-    const cplx* W;   // filters: element (row, c, k) at W[row*w_row + c*w_c + k]
+    const void* Xg;
+    const cplx* W;   // filters: element (row, c, k) at W[row*w_row + c*w_c + k], row = b*F + f
     long long w_row;
     int w_c;
-    RowLayout L;
-    int F, K, k0;
-    int NCH, NBC;     // chunks per mixture, bins per chunk (power kernel)
-    double* r2part;   // (B, NCH, K, Tp)
+    GroupLayout L;
+    int K;
+    int nsplit;       // frame splits per group (grid.y)
+    double* r2part;   // (B, NG, K, Tp)
     void* Y;          // (B, T, F, K) interleaved complex ST
-    void* Xr;         // planar rows with K channels
-    RowLayout Lr;     // layout of Xr
-    int NBF;          // bins per CTA (output kernel)
+    void* Xr;         // grouped samples with K channels
 };
 
-// load the 2M plane values of one frame
-template <typename ST, int M>
-__device__ __forceinline__ void load_frame(double (&xr)[M], double (&xi)[M], const ST* __restrict__ tile, int pitch,
-                                           int tloc) {
+// this lane's demixing vectors: w[c][k] for KC sources starting at k0 (zero beyond K / beyond F)
+template <int M, int KC>
+__device__ __forceinline__ void load_filters(cplx (&w)[M][KC], const StreamParams& p, long long row, bool bin_ok,
+                                             int k0) {
 #pragma unroll
-    for (int c = 0; c < M; ++c) {
-        xr[c] = ld_nc(tile + (size_t)(2 * c) * pitch + tloc);
-        xi[c] = ld_nc(tile + (size_t)(2 * c + 1) * pitch + tloc);
-    }
+    for (int c = 0; c < M; ++c)
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            w[c][k] = cmake(0.0, 0.0);
+            if (bin_ok && k0 + k < p.K) w[c][k] = ld_nc_c(p.W + row * p.w_row + (size_t)c * p.w_c + k0 + k);
+        }
 }
 
-// y_k = sum_c conj(w[c][k]) x_c for KC sources; sources >= kmax are skipped (y = 0)
+// y_k = sum_c conj(w[c][k]) x_c
 template <int M, int KC>
-__device__ __forceinline__ void demix_frame(double (&yr)[KC], double (&yi)[KC], const double (&xr)[M],
-                                            const double (&xi)[M], const cplx* __restrict__ Wrow, int w_c, int k0,
-                                            int kmax) {
+__device__ __forceinline__ void demix_frame(cplx (&y)[KC], const cplx (&x)[M], const cplx (&w)[M][KC]) {
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
-        yr[k] = 0.0;
-        yi[k] = 0.0;
-        if (k0 + k < kmax) {
+        y[k] = cmake(0.0, 0.0);
 #pragma unroll
-            for (int c = 0; c < M; ++c) {
-                const cplx w = ld_nc_c(Wrow + (size_t)c * w_c + k0 + k);
-                // conj(w) * x = (wr xr + wi xi) + i (wr xi - wi xr)
-                yr[k] = fma(w.x, xr[c], yr[k]);
-                yr[k] = fma(w.y, xi[c], yr[k]);
-                yi[k] = fma(w.x, xi[c], yi[k]);
-                yi[k] = fma(-w.y, xr[c], yi[k]);
-            }
-        }
+        for (int c = 0; c < M; ++c) cfmac(y[k], w[c][k], x[c]);
     }
 }
 
-// grid (NCH, ceil(slots/4), B); warp <-> 32-frame slot, loop over the bins of the chunk
+// grid (G, nsplit), block = 32 * ceil(K/KC): warp w handles sources [w*KC, w*KC+KC) of group blockIdx.x over the
+// frame blocks of its split.  After |y|^2 the 32 lanes (bins) of POWER_FB frames are summed with a transposing
+// butterfly (each exchange halves the live values), the group's partial statistic goes to r2part.
 template <typename ST, int M, int KC>
-__global__ void __launch_bounds__(STREAM_WARPS * 32) k_demix_power(const StreamParams p) {
-    const RowLayout& L = p.L;
+__global__ void __launch_bounds__(512) k_demix_power(const StreamParams p) {
+    typedef typename StoreC<ST>::type XC;
+    const GroupLayout& L = p.L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.z, ch = blockIdx.x;
-    const int slot = blockIdx.y * STREAM_WARPS + warp;
-    const int t = slot * 32 + lane;
+    const long long gi = blockIdx.x;
+    const long long b = gi / L.NG;
+    const int g = (int)(gi - b * L.NG);
+    const int f = g * OIVA_GROUP + lane;
+    const bool bin_ok = f < L.F;
+    const int k0 = warp * KC;
     const int Tp = L.frame_pitch();
-    if (slot * 32 >= Tp) return;
-    const int ti = t / L.TT, tloc = t - ti * L.TT;
-    const bool valid = t < L.T;
-    const int pitch = L.pitch(ti < L.nT ? ti : L.nT - 1);
-    const int f0 = ch * p.NBC;
-    const int f1 = min(p.F, f0 + p.NBC);
-    const ST* Xp = reinterpret_cast<const ST*>(p.Xp);
-    const size_t row_elems = L.row_elems();
-    double acc[KC];
+    cplx w[M][KC];
+    load_filters<M, KC>(w, p, b * L.F + (bin_ok ? f : 0), bin_ok, k0);
+    const XC* xg = reinterpret_cast<const XC*>(p.Xg) + (size_t)gi * L.group_elems();
+    const int nblk = Tp / POWER_FB;  // blocks over the padded frame range: the padding is written as zeros
+    const int blk0 = (int)((long long)nblk * blockIdx.y / p.nsplit);
+    const int blk1 = (int)((long long)nblk * (blockIdx.y + 1) / p.nsplit);
+    for (int blk = blk0; blk < blk1; ++blk) {
+        const int t0 = blk * POWER_FB;
+        double v[KC][POWER_FB];
 #pragma unroll
-    for (int k = 0; k < KC; ++k) acc[k] = 0.0;
-    if (valid) {
-#pragma unroll 2
-        for (int f = f0; f < f1; ++f) {
-            const size_t row = (size_t)b * p.F + f;
-            double xr[M], xi[M], yr[KC], yi[KC];
-            load_frame<ST, M>(xr, xi, Xp + row * row_elems + L.tile_off(ti), pitch, tloc);
-            demix_frame<M, KC>(yr, yi, xr, xi, p.W + row * p.w_row, p.w_c, p.k0, p.K);
+        for (int j = 0; j < POWER_FB; ++j) {
+            cplx x[M], y[KC];
+            const int t = t0 + j;
+            if (t < L.T) {
 #pragma unroll
-            for (int k = 0; k < KC; ++k) acc[k] = fma(yr[k], yr[k], fma(yi[k], yi[k], acc[k]));
-        }
-    }
+                for (int c = 0; c < M; ++c) x[c] = ldg_x(xg + ((size_t)t * M + c) * OIVA_GROUP + lane);
+                demix_frame<M, KC>(y, x, w);
 #pragma unroll
-    for (int k = 0; k < KC; ++k)
-        if (p.k0 + k < p.K) p.r2part[(((size_t)b * p.NCH + ch) * p.K + p.k0 + k) * Tp + t] = acc[k];
-}
-
-// grid (ceil(F/NBF), slots, B); CTA <-> NBF bins x one 32-frame slot; shared-memory transpose so that the
-// (T,F,K)-ordered output is written in contiguous NBF*K-element runs
-template <typename ST, int M, int KC>
-__global__ void __launch_bounds__(STREAM_WARPS * 32) k_demix_output(const StreamParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    typedef typename std::conditional<sizeof(ST) == 8, double2, float2>::type OutC;
-    OutC* tileo = reinterpret_cast<OutC*>(smem_raw);  // [32][NBF*K + 1]
-    const RowLayout& L = p.L;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.z;
-    const int f0 = blockIdx.x * p.NBF;
-    const int nb = min(p.NBF, p.F - f0);
-    const int slot = blockIdx.y;
-    const int t = slot * 32 + lane;
-    const int ti = t / L.TT, tloc = t - ti * L.TT;
-    const bool valid = t < L.T;
-    const int pitch = L.pitch(ti < L.nT ? ti : L.nT - 1);
-    const int opitch = p.NBF * p.K + 1;
-    const ST* Xp = reinterpret_cast<const ST*>(p.Xp);
-    const size_t row_elems = L.row_elems();
-    for (int k0 = 0; k0 < p.K; k0 += KC) {
-        for (int fb = warp; fb < nb; fb += STREAM_WARPS) {
-            const size_t row = (size_t)b * p.F + f0 + fb;
-            double xr[M], xi[M], yr[KC], yi[KC];
-            if (valid) {
-                load_frame<ST, M>(xr, xi, Xp + row * row_elems + L.tile_off(ti), pitch, tloc);
-                demix_frame<M, KC>(yr, yi, xr, xi, p.W + row * p.w_row, p.w_c, k0, p.K);
+                for (int k = 0; k < KC; ++k) v[k][j] = fma(y[k].x, y[k].x, y[k].y * y[k].y);
+            } else {
 #pragma unroll
-                for (int k = 0; k < KC; ++k)
-                    if (k0 + k < p.K) {
-                        OutC o;
-                        o.x = (ST)yr[k];
-                        o.y = (ST)yi[k];
-                        tileo[lane * opitch + fb * p.K + k0 + k] = o;
-                    }
+                for (int k = 0; k < KC; ++k) v[k][j] = 0.0;
             }
         }
-    }
-    __syncthreads();
-    OutC* Y = reinterpret_cast<OutC*>(p.Y);
-    const int run = nb * p.K;
-    for (int i = threadIdx.x; i < 32 * run; i += STREAM_WARPS * 32) {
-        const int tl = i / run, j = i - tl * run;
-        const int tt = slot * 32 + tl;
-        if (tt < L.T) Y[(((size_t)b * L.T + tt) * p.F + f0) * p.K + j] = tileo[tl * opitch + j];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            // 8 -> 4 -> 2 -> 1 values across lane bits 4, 3, 2; then plain sums across bits 1, 0
+#pragma unroll
+            for (int lvl = 0; lvl < 3; ++lvl) {
+                const int H = POWER_FB >> (lvl + 1);
+                const int off = 16 >> lvl;
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int n = 0; n < H; ++n) {
+                    const double lo = v[k][n], hi = v[k][n + H];
+                    const double send = up ? lo : hi;
+                    const double keep = up ? hi : lo;
+                    v[k][n] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            double s = v[k][0];
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            // lanes with (lane & 3) == 0 hold the sum over the 32 bins for frame t0 + (lane >> 2)
+            if ((lane & 3) == 0 && k0 + k < p.K) p.r2part[((size_t)gi * p.K + k0 + k) * Tp + t0 + (lane >> 2)] = s;
+        }
     }
 }
 
-// grid (ceil(R/4), slots): warp <-> (row, slot); writes the K-channel planar row
+// grid (G, nsplit), block = 32 * ceil(K/KC)
 template <typename ST, int M, int KC>
-__global__ void __launch_bounds__(STREAM_WARPS * 32) k_project_rows(const StreamParams p, long long R) {
-    const RowLayout& L = p.L;
-    const RowLayout& Lr = p.Lr;
+__global__ void __launch_bounds__(512) k_demix_output(const StreamParams p) {
+    typedef typename StoreC<ST>::type XC;
+    const GroupLayout& L = p.L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * STREAM_WARPS + warp;
-    if (row >= R) return;
-    const int slot = blockIdx.y;
-    const int t = slot * 32 + lane;
-    const int ti = t / L.TT, tloc = t - ti * L.TT;
-    const bool valid = t < L.T;
-    const int pitch = L.pitch(ti < L.nT ? ti : L.nT - 1);
-    const ST* Xp = reinterpret_cast<const ST*>(p.Xp);
-    ST* Xr = reinterpret_cast<ST*>(p.Xr);
-    // Lr has the same T and hence the same tiling only if TT matches; address through Lr explicitly
-    const int tir = t / Lr.TT, tlocr = t - tir * Lr.TT;
-    if (tir >= Lr.nT) return;
-    const int pitchr = Lr.pitch(tir);
-    if (tlocr >= pitchr) return;
-    double xr[M], xi[M];
+    const long long gi = blockIdx.x;
+    const long long b = gi / L.NG;
+    const int g = (int)(gi - b * L.NG);
+    const int f = g * OIVA_GROUP + lane;
+    const bool bin_ok = f < L.F;
+    const int k0 = warp * KC;
+    cplx w[M][KC];
+    load_filters<M, KC>(w, p, b * L.F + (bin_ok ? f : 0), bin_ok, k0);
+    const XC* xg = reinterpret_cast<const XC*>(p.Xg) + (size_t)gi * L.group_elems();
+    XC* Y = reinterpret_cast<XC*>(p.Y);
+    const int t_begin = (int)((long long)L.T * blockIdx.y / p.nsplit);
+    const int t_end = (int)((long long)L.T * (blockIdx.y + 1) / p.nsplit);
+#pragma unroll 2
+    for (int t = t_begin; t < t_end; ++t) {
+        cplx x[M], y[KC];
 #pragma unroll
-    for (int c = 0; c < M; ++c) xr[c] = xi[c] = 0.0;
-    if (valid) load_frame<ST, M>(xr, xi, Xp + (size_t)row * L.row_elems() + L.tile_off(ti), pitch, tloc);
-    for (int k0 = 0; k0 < p.K; k0 += KC) {
-        double yr[KC], yi[KC];
-        demix_frame<M, KC>(yr, yi, xr, xi, p.W + row * p.w_row, p.w_c, k0, p.K);
+        for (int c = 0; c < M; ++c) x[c] = ldg_x(xg + ((size_t)t * M + c) * OIVA_GROUP + lane);
+        demix_frame<M, KC>(y, x, w);
+        if (bin_ok) {
+            XC* dst = Y + (((size_t)b * L.T + t) * L.F + f) * p.K + k0;
+#pragma unroll
+            for (int k = 0; k < KC; ++k)
+                if (k0 + k < p.K) narrow(dst[k], y[k]);
+        }
+    }
+}
+
+// grid (G, nsplit), block = 32 * ceil(K/KC): writes Xr[gi][t][k][lane]
+template <typename ST, int M, int KC>
+__global__ void __launch_bounds__(512) k_project_rows(const StreamParams p) {
+    typedef typename StoreC<ST>::type XC;
+    const GroupLayout& L = p.L;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long gi = blockIdx.x;
+    const long long b = gi / L.NG;
+    const int g = (int)(gi - b * L.NG);
+    const int f = g * OIVA_GROUP + lane;
+    const bool bin_ok = f < L.F;
+    const int k0 = warp * KC;
+    cplx w[M][KC];
+    load_filters<M, KC>(w, p, b * L.F + (bin_ok ? f : 0), bin_ok, k0);
+    const XC* xg = reinterpret_cast<const XC*>(p.Xg) + (size_t)gi * L.group_elems();
+    XC* xr = reinterpret_cast<XC*>(p.Xr) + (size_t)gi * L.T * p.K * OIVA_GROUP;
+    const int t_begin = (int)((long long)L.T * blockIdx.y / p.nsplit);
+    const int t_end = (int)((long long)L.T * (blockIdx.y + 1) / p.nsplit);
+#pragma unroll 2
+    for (int t = t_begin; t < t_end; ++t) {
+        cplx x[M], y[KC];
+#pragma unroll
+        for (int c = 0; c < M; ++c) x[c] = ldg_x(xg + ((size_t)t * M + c) * OIVA_GROUP + lane);
+        demix_frame<M, KC>(y, x, w);  // zero filters on padded bins => zero samples
 #pragma unroll
         for (int k = 0; k < KC; ++k)
-            if (k0 + k < p.K) {
-                ST* dst = Xr + (size_t)row * Lr.row_elems() + Lr.tile_off(tir);
-                dst[(size_t)(2 * (k0 + k)) * pitchr + tlocr] = (ST)yr[k];
-                dst[(size_t)(2 * (k0 + k) + 1) * pitchr + tlocr] = (ST)yi[k];
-            }
+            if (k0 + k < p.K) narrow(xr[((size_t)t * p.K + k0 + k) * OIVA_GROUP + lane], y[k]);
     }
 }
 

@@ -1,6 +1,4 @@
 // Instantiates the streaming demix kernels for ONE channel count (-DOIVA_M=<M>); see stream.cuh.
-#include <type_traits>
-
 #include "stream.cuh"
 
 #ifndef OIVA_M
@@ -12,66 +10,53 @@ namespace oiva {
 #define OIVA_CAT2(a, b) a##b
 #define OIVA_CAT(a, b) OIVA_CAT2(a, b)
 
-// smallest instantiated source chunk >= min(K, 8)
+// sources per warp: the lane keeps 2*M*KC doubles of filters in registers
+constexpr int kc_cap() { return (24 / OIVA_M) < 1 ? 1 : ((24 / OIVA_M) > 4 ? 4 : (24 / OIVA_M)); }
 static int pick_kc(int K) {
-    if (K <= 1) return 1;
-    if (K == 2) return 2;
-    if (K == 3) return 3;
-    if (K == 4) return 4;
-    return 8;
+    int kc = K < 4 ? K : 4;
+    return kc < kc_cap() ? kc : kc_cap();
 }
 
+static int frame_splits(long long G, int units) {
+    // enough CTAs for ~4 waves of 148 SMs x 4 resident CTAs, never more splits than units of work
+    long long want = (4ll * 148 * 4 + G - 1) / G;
+    if (want < 1) want = 1;
+    if (want > units) want = units;
+    if (want > 65535) want = 65535;
+    return (int)want;
+}
+
+enum { KIND_POWER = 0, KIND_OUTPUT = 1, KIND_PROJECT = 2 };
+
 template <typename ST, int KC>
-static int power_launch(StreamParams p, int n_batch, cudaStream_t st) {
+static int launch(int kind, StreamParams p, long long G, cudaStream_t st) {
     constexpr int M = OIVA_M;
-    const int slots = p.L.frame_pitch() / 32;
-    dim3 grid(p.NCH, oiva_div_up(slots, STREAM_WARPS), n_batch);
-    for (int k0 = 0; k0 < p.K; k0 += KC) {
-        p.k0 = k0;
-        k_demix_power<ST, M, KC><<<grid, STREAM_WARPS * 32, 0, st>>>(p);
+    if constexpr (KC > kc_cap()) {
+        oiva_set_error("stream launch: KC=%d not instantiated for M=%d", KC, M);
+        return OIVA_ERR_INVALID;
+    } else {
+        const int warps = (p.K + KC - 1) / KC;
+        const int units = kind == KIND_POWER ? p.L.frame_pitch() / POWER_FB : p.L.T;
+        p.nsplit = frame_splits(G, units);
+        dim3 grid((unsigned)G, p.nsplit, 1);
+        if (kind == KIND_POWER)
+            k_demix_power<ST, M, KC><<<grid, 32 * warps, 0, st>>>(p);
+        else if (kind == KIND_OUTPUT)
+            k_demix_output<ST, M, KC><<<grid, 32 * warps, 0, st>>>(p);
+        else
+            k_project_rows<ST, M, KC><<<grid, 32 * warps, 0, st>>>(p);
         OIVA_LAUNCH_CHECK();
+        return OIVA_OK;
     }
-    return OIVA_OK;
 }
 
-template <typename ST, int KC>
-static int output_launch(StreamParams p, int n_batch, cudaStream_t st) {
-    constexpr int M = OIVA_M;
-    const int slots = oiva_div_up(p.L.T, 32);
-    dim3 grid(oiva_div_up(p.F, p.NBF), slots, n_batch);
-    const size_t smem = (size_t)32 * (p.NBF * p.K + 1) * 2 * sizeof(ST);
-    k_demix_output<ST, M, KC><<<grid, STREAM_WARPS * 32, smem, st>>>(p);
-    OIVA_LAUNCH_CHECK();
-    return OIVA_OK;
-}
-
-template <typename ST, int KC>
-static int project_launch(StreamParams p, long long R, cudaStream_t st) {
-    constexpr int M = OIVA_M;
-    int fr = p.L.frame_pitch() > p.Lr.frame_pitch() ? p.L.frame_pitch() : p.Lr.frame_pitch();
-    dim3 grid((unsigned)((R + STREAM_WARPS - 1) / STREAM_WARPS), fr / 32, 1);
-    k_project_rows<ST, M, KC><<<grid, STREAM_WARPS * 32, 0, st>>>(p, R);
-    OIVA_LAUNCH_CHECK();
-    return OIVA_OK;
-}
-
-#define OIVA_KC_SWITCH(FN, ...)                                                              \
-    switch (pick_kc(p.K)) {                                                                  \
-        case 1: return dtype == OIVA_C64 ? FN<float, 1>(__VA_ARGS__) : FN<double, 1>(__VA_ARGS__); \
-        case 2: return dtype == OIVA_C64 ? FN<float, 2>(__VA_ARGS__) : FN<double, 2>(__VA_ARGS__); \
-        case 3: return dtype == OIVA_C64 ? FN<float, 3>(__VA_ARGS__) : FN<double, 3>(__VA_ARGS__); \
-        case 4: return dtype == OIVA_C64 ? FN<float, 4>(__VA_ARGS__) : FN<double, 4>(__VA_ARGS__); \
-        default: return dtype == OIVA_C64 ? FN<float, 8>(__VA_ARGS__) : FN<double, 8>(__VA_ARGS__); \
+int OIVA_CAT(stream_launch_m, OIVA_M)(int kind, int dtype, const StreamParams& p, long long G, cudaStream_t st) {
+    switch (pick_kc(p.K)) {
+        case 1: return dtype == OIVA_C64 ? launch<float, 1>(kind, p, G, st) : launch<double, 1>(kind, p, G, st);
+        case 2: return dtype == OIVA_C64 ? launch<float, 2>(kind, p, G, st) : launch<double, 2>(kind, p, G, st);
+        case 3: return dtype == OIVA_C64 ? launch<float, 3>(kind, p, G, st) : launch<double, 3>(kind, p, G, st);
+        default: return dtype == OIVA_C64 ? launch<float, 4>(kind, p, G, st) : launch<double, 4>(kind, p, G, st);
     }
-
-int OIVA_CAT(power_launch_m, OIVA_M)(int dtype, const StreamParams& p, int n_batch, cudaStream_t st) {
-    OIVA_KC_SWITCH(power_launch, p, n_batch, st)
-}
-int OIVA_CAT(output_launch_m, OIVA_M)(int dtype, const StreamParams& p, int n_batch, cudaStream_t st) {
-    OIVA_KC_SWITCH(output_launch, p, n_batch, st)
-}
-int OIVA_CAT(project_launch_m, OIVA_M)(int dtype, const StreamParams& p, long long R, cudaStream_t st) {
-    OIVA_KC_SWITCH(project_launch, p, R, st)
 }
 
 }  // namespace oiva

@@ -1,4 +1,5 @@
-// Error plumbing, layout arithmetic and the (B,T,F,M) -> planar-rows relayout kernel.
+// Error plumbing, layout arithmetic, the (B,T,F,M) -> grouped-layout relayout kernel and the unpacking of
+// grouped lower-triangle covariances into full row-major matrices.
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -15,107 +16,105 @@ void oiva_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* oiva_last_error(void) { return g_err; }
-extern "C" int oiva_version(void) { return 100; }
+extern "C" int oiva_version(void) { return 200; }
 
-// ---- layout arithmetic --------------------------------------------------------------------------
+// ---- layout arithmetic (host only) --------------------------------------------------------------
 static inline int elem_size(int dtype) { return dtype == OIVA_C64 ? 4 : 8; }
 
-RowLayout oiva_make_layout(int n_frames, int n_chan, int dtype) {
-    RowLayout L;
-    L.T = n_frames;
-    L.M = n_chan;
-    L.TT = n_chan <= 8 ? 128 : 64;  // a full tile is <= 16 KB in fp64
-    L.nT = (n_frames + L.TT - 1) / L.TT;
-    if (L.nT < 1) L.nT = 1;
-    int tl = n_frames - (L.nT - 1) * L.TT;
-    // every tile must be a multiple of 16 bytes for the bulk copy (always true in fp64)
-    while (((size_t)2 * n_chan * tl * elem_size(dtype)) % 16 != 0) ++tl;
-    L.TL = tl;
-    return L;
+extern "C" int oiva_bin_groups(int n_freq) { return n_freq > 0 ? (n_freq + OIVA_GROUP - 1) / OIVA_GROUP : 0; }
+
+extern "C" int oiva_frame_pitch(int n_frames) { return n_frames > 0 ? ((n_frames + 31) / 32) * 32 : 0; }
+
+extern "C" size_t oiva_grouped_bytes(int n_batch, int n_frames, int n_freq, int n_chan, int dtype) {
+    if (n_batch <= 0 || n_frames <= 0 || n_freq <= 0 || n_chan <= 0) return 0;
+    return (size_t)n_batch * oiva_bin_groups(n_freq) * n_frames * n_chan * OIVA_GROUP * 2 * elem_size(dtype);
 }
 
-extern "C" int oiva_tile_frames(int n_frames, int n_chan, int dtype) {
-    if (n_frames <= 0 || n_chan <= 0) return 0;
-    return oiva_make_layout(n_frames, n_chan, dtype).TT;
-}
-
-extern "C" int oiva_frame_pitch(int n_frames, int n_chan, int dtype) {
-    if (n_frames <= 0 || n_chan <= 0) return 0;
-    return oiva_make_layout(n_frames, n_chan, dtype).frame_pitch();
-}
-
-extern "C" size_t oiva_planar_bytes(int n_batch, int n_frames, int n_freq, int n_chan, int dtype) {
-    if (n_frames <= 0 || n_chan <= 0) return 0;
-    RowLayout L = oiva_make_layout(n_frames, n_chan, dtype);
-    return (size_t)n_batch * n_freq * L.row_elems() * elem_size(dtype);
-}
-
-extern "C" int oiva_power_chunks(int n_batch, int n_freq) {
-    if (n_batch <= 0 || n_freq <= 0) return 0;
-    long long bins = (long long)n_batch * n_freq;
-    long long per = bins / (148 * 8);
-    if (per < 8) per = 8;
-    if (per > 64) per = 64;
-    return (int)((n_freq + per - 1) / per);
+extern "C" size_t oiva_grouped_cov_bytes(int n_batch, int n_freq, int n_chan, int n_src) {
+    if (n_batch <= 0 || n_freq <= 0 || n_chan <= 0 || n_src <= 0) return 0;
+    return (size_t)n_batch * oiva_bin_groups(n_freq) * n_src * oiva_tri(n_chan) * OIVA_GROUP * 16;
 }
 
 // ---- relayout -----------------------------------------------------------------------------------
-// grid (ceil(F/FB), nT*TT/32, B), 256 threads; smem tile [32][FB*2M + 1]
-template <typename ST>
-__global__ void __launch_bounds__(256) k_relayout(const ST* __restrict__ X, ST* __restrict__ Xp, RowLayout L, int F,
-                                                  int FB) {
+// grid (NG, ceil(T/FT), B), 128 threads = 4 warps; each warp transposes one frame of the group at a time:
+// 32 bins x M channels (contiguous in X) -> M x 32 (contiguous in Xg) through a padded shared tile.
+constexpr int RELAYOUT_FT = 32;  // frames per CTA
+template <typename CT>
+__global__ void __launch_bounds__(128) k_relayout(const CT* __restrict__ X, CT* __restrict__ Xg, GroupLayout L) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ST* tile = reinterpret_cast<ST*>(smem_raw);
-    const int M = L.M, T = L.T;
-    const int f0 = blockIdx.x * FB;
-    const int t0 = blockIdx.y * 32;
-    const int b = blockIdx.z;
-    const int nb = min(FB, F - f0);
-    const int J = nb * 2 * M;
-    const int pitch = FB * 2 * M + 1;
-    const int tid = threadIdx.x;
-
-    for (int i = tid; i < 32 * J; i += 256) {
-        int tl = i / J, j = i - tl * J;
-        int t = t0 + tl;
-        ST v = (ST)0;
-        if (t < T) v = X[(((size_t)b * T + t) * F + f0) * 2 * M + j];
-        tile[tl * pitch + j] = v;
-    }
-    __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31;
-    const int t = t0 + lane;
-    const int ti = t / L.TT;  // t0 is a multiple of 32 and so is TT: the whole block lies in one tile
-    if (ti >= L.nT) return;
-    const int tloc = t - ti * L.TT;
-    const int tp = L.pitch(ti);
-    if (tloc >= tp) return;
-    const size_t row_elems = L.row_elems();
-    for (int j = warp; j < J; j += 8) {
-        int fb = j / (2 * M);
-        int plane = j - fb * 2 * M;  // 2*c + ri
-        size_t row = (size_t)b * F + f0 + fb;
-        Xp[row * row_elems + L.tile_off(ti) + (size_t)plane * tp + tloc] = tile[lane * pitch + j];
+    const int M = L.M, T = L.T, F = L.F;
+    const int pitch = M | 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    CT* tile = reinterpret_cast<CT*>(smem_raw) + (size_t)warp * 32 * pitch;
+    const int g = blockIdx.x, b = blockIdx.z;
+    const int f0 = g * OIVA_GROUP;
+    const int nb = min(OIVA_GROUP, F - f0);
+    const size_t gi = (size_t)b * L.NG + g;
+    const int t_end = min(T, (int)(blockIdx.y + 1) * RELAYOUT_FT);
+    for (int t = blockIdx.y * RELAYOUT_FT + warp; t < t_end; t += 4) {
+        const CT* src = X + (((size_t)b * T + t) * F + f0) * M;
+        for (int e = lane; e < 32 * M; e += 32) {
+            const int l = e / M, c = e - l * M;
+            CT v;
+            v.x = 0;
+            v.y = 0;
+            if (l < nb) v = src[e];
+            tile[l * pitch + c] = v;
+        }
+        __syncwarp();
+        CT* dst = Xg + (gi * T + t) * (size_t)M * OIVA_GROUP;
+        for (int c = 0; c < M; ++c) dst[c * OIVA_GROUP + lane] = tile[lane * pitch + c];
+        __syncwarp();
     }
 }
 
-extern "C" int oiva_relayout(const void* X, void* Xp, int n_batch, int n_frames, int n_freq, int n_chan, int dtype,
+extern "C" int oiva_relayout(const void* X, void* Xg, int n_batch, int n_frames, int n_freq, int n_chan, int dtype,
                              void* stream) {
-    OIVA_REQUIRE(X && Xp, "oiva_relayout: null pointer");
+    OIVA_REQUIRE(X && Xg, "oiva_relayout: null pointer");
     OIVA_REQUIRE(n_batch > 0 && n_frames > 0 && n_freq > 0 && n_chan > 0 && n_chan <= OIVA_MAX_M,
                  "oiva_relayout: bad shape B=%d T=%d F=%d M=%d", n_batch, n_frames, n_freq, n_chan);
     OIVA_REQUIRE(n_batch <= 65535, "oiva_relayout: n_batch %d > 65535", n_batch);
-    RowLayout L = oiva_make_layout(n_frames, n_chan, dtype);
-    int FB = 128 / (2 * n_chan);
-    if (FB < 1) FB = 1;
-    dim3 grid(oiva_div_up(n_freq, FB), L.nT * L.TT / 32, n_batch);
+    GroupLayout L = oiva_make_layout(n_frames, n_freq, n_chan);
+    dim3 grid(L.NG, oiva_div_up(n_frames, RELAYOUT_FT), n_batch);
     OIVA_REQUIRE(grid.y <= 65535, "oiva_relayout: too many frames");
     cudaStream_t st = (cudaStream_t)stream;
-    size_t smem = (size_t)32 * (FB * 2 * n_chan + 1) * elem_size(dtype);
+    const size_t smem = (size_t)4 * 32 * (n_chan | 1) * 2 * elem_size(dtype);
     if (dtype == OIVA_C64)
-        k_relayout<float><<<grid, 256, smem, st>>>((const float*)X, (float*)Xp, L, n_freq, FB);
+        k_relayout<float2><<<grid, 128, smem, st>>>((const float2*)X, (float2*)Xg, L);
     else
-        k_relayout<double><<<grid, 256, smem, st>>>((const double*)X, (double*)Xp, L, n_freq, FB);
+        k_relayout<double2><<<grid, 128, smem, st>>>((const double2*)X, (double2*)Xg, L);
+    OIVA_LAUNCH_CHECK();
+    return OIVA_OK;
+}
+
+// ---- unpack grouped covariances -------------------------------------------------------------------
+// Vg[gi][k][e][l] (lower triangle, bin-interleaved) -> V[row][k][i][j] full Hermitian, row = b*F + f.
+__global__ void k_unpack_cov(const cplx* __restrict__ Vg, cplx* __restrict__ V, int F, int NG, int M, int K,
+                             long long n) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int j = (int)(idx % M), i = (int)((idx / M) % M);
+    const int k = (int)((idx / ((long long)M * M)) % K);
+    const long long row = idx / ((long long)M * M * K);
+    const long long b = row / F;
+    const int f = (int)(row - b * F);
+    const size_t gi = (size_t)b * NG + f / OIVA_GROUP;
+    const int l = f % OIVA_GROUP;
+    const int NE = oiva_tri(M);
+    const int hi = i >= j ? i : j, lo = i >= j ? j : i;
+    cplx v = Vg[((gi * K + k) * NE + (hi * (hi + 1) / 2 + lo)) * OIVA_GROUP + l];
+    if (i < j) v.y = -v.y;
+    if (i == j) v.y = 0.0;
+    V[idx] = v;
+}
+
+extern "C" int oiva_unpack_cov(const void* Vg, void* V, int n_batch, int n_freq, int n_chan, int n_src, void* stream) {
+    OIVA_REQUIRE(Vg && V, "oiva_unpack_cov: null pointer");
+    OIVA_REQUIRE(n_batch > 0 && n_freq > 0 && n_chan >= 1 && n_chan <= OIVA_MAX_M && n_src >= 1,
+                 "oiva_unpack_cov: bad shape");
+    const long long n = (long long)n_batch * n_freq * n_src * n_chan * n_chan;
+    k_unpack_cov<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const cplx*)Vg, (cplx*)V, n_freq, oiva_bin_groups(n_freq), n_chan, n_src, n);
     OIVA_LAUNCH_CHECK();
     return OIVA_OK;
 }

@@ -28,97 +28,103 @@ def to_dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).to(dev())
 
 
-def planar(X):
-    """X: (B, T, F, M) numpy complex -> device planar buffer (uint8 tensor) via oiva_relayout."""
+def grouped(X):
+    """X: (B, T, F, M) numpy complex -> device grouped-sample buffer (uint8 tensor) via oiva_relayout."""
     lib = L.load()
     B, T, F, M = X.shape
     code = code_of(X.dtype)
-    nbytes = lib.oiva_planar_bytes(B, T, F, M, code)
+    nbytes = lib.oiva_grouped_bytes(B, T, F, M, code)
     Xd = to_dev(X)
-    Xp = torch.empty(nbytes, dtype=torch.uint8, device=dev())
-    L.check(lib.oiva_relayout(P(Xd), P(Xp), B, T, F, M, code, stream()), "oiva_relayout")
-    return Xp
+    Xg = torch.empty(nbytes, dtype=torch.uint8, device=dev())
+    L.check(lib.oiva_relayout(P(Xd), P(Xg), B, T, F, M, code, stream()), "oiva_relayout")
+    return Xg
 
 
-def planar_expected(X):
-    """numpy restatement of the planar layout (csrc/common.cuh) for one batch of mixtures."""
-    lib = L.load()
+def grouped_expected(X):
+    """numpy restatement of the grouped layout Xg[b*NG+g][t][c][l] (csrc/common.cuh)."""
     B, T, F, M = X.shape
-    code = code_of(X.dtype)
-    TT = lib.oiva_tile_frames(T, M, code)
-    nT = (T + TT - 1) // TT
-    es = 4 if code == L.C64 else 8
-    real = np.float32 if code == L.C64 else np.float64
-    row_bytes = lib.oiva_planar_bytes(1, T, 1, M, code)
-    TL = row_bytes // (2 * M * es) - (nT - 1) * TT
-    out = np.zeros((B, F, row_bytes // es), dtype=real)
-    for ti in range(nT):
-        t0 = ti * TT
-        pitch = TT if ti + 1 < nT else TL
-        nv = min(TT, T - t0)
-        blk = np.zeros((B, F, 2 * M, pitch), dtype=real)
-        seg = X[:, t0 : t0 + nv]  # (B, nv, F, M)
-        blk[:, :, 0::2, :nv] = seg.real.transpose(0, 2, 3, 1)
-        blk[:, :, 1::2, :nv] = seg.imag.transpose(0, 2, 3, 1)
-        off = ti * 2 * M * TT
-        out[:, :, off : off + 2 * M * pitch] = blk.reshape(B, F, -1)
-    return out.reshape(-1)
+    NG = (F + 31) // 32
+    pad = np.zeros((B, T, NG * 32, M), dtype=X.dtype)
+    pad[:, :, :F] = X
+    # (B, T, NG, 32, M) -> (B, NG, T, M, 32)
+    return np.ascontiguousarray(pad.reshape(B, T, NG, 32, M).transpose(0, 2, 1, 4, 3)).reshape(-1)
 
 
-def weighted_cov(Xp, phi, B, T, F, M, K, code):
-    """phi: (B, K, T) numpy or None -> V (B, F, K, M, M) numpy complex128."""
+def weighted_cov(Xg, phi, B, T, F, M, K, code):
+    """phi: (B, K, T) numpy or None -> V (B, F, K, M, M) numpy complex128 (grouped result unpacked)."""
     lib = L.load()
-    Tp = lib.oiva_frame_pitch(T, M, code)
+    Tp = lib.oiva_frame_pitch(T)
     phid = None
     if phi is not None:
         ph = np.zeros((B, K, Tp))
         ph[:, :, :T] = phi
         phid = to_dev(ph)
+    Vg = torch.full((lib.oiva_grouped_cov_bytes(B, F, M, K) // 8,), float("nan"), dtype=torch.float64, device=dev())
+    L.check(lib.oiva_weighted_cov(P(Xg), P(phid), P(Vg), B, T, F, M, K, code, stream()), "oiva_weighted_cov")
     V = torch.empty((B, F, K, M, M), dtype=torch.complex128, device=dev())
-    L.check(lib.oiva_weighted_cov(P(Xp), P(phid), P(V), B, T, F, M, K, code, stream()), "oiva_weighted_cov")
+    L.check(lib.oiva_unpack_cov(P(Vg), P(V), B, F, M, K, stream()), "oiva_unpack_cov")
     torch.cuda.synchronize()
     return V.cpu().numpy()
 
 
-def demix_power(Xp, W, B, T, F, M, K, code, n_chunks=None):
+def pack_cov(V):
+    """V (B, F, K, M, M) numpy -> device grouped lower-triangle buffer Vg[gi][k][e][l]."""
+    B, F, K, M, _ = V.shape
+    NG = (F + 31) // 32
+    NE = M * (M + 1) // 2
+    out = np.zeros((B, NG, K, NE, 32), dtype=np.complex128)
+    pad = np.zeros((B, NG * 32, K, M, M), dtype=np.complex128)
+    pad[:, :F] = V
+    pad = pad.reshape(B, NG, 32, K, M, M)
+    e = 0
+    for i in range(M):
+        for j in range(i + 1):
+            out[:, :, :, e, :] = pad[:, :, :, :, i, j].transpose(0, 1, 3, 2)
+            e += 1
+    return to_dev(out)
+
+
+def demix_power(Xg, W, B, T, F, M, K, code):
     """W: (B, F, M, Wc) numpy complex128 -> r2 (B, K, T) numpy (partials summed with oiva_sum_partials)."""
     lib = L.load()
-    Tp = lib.oiva_frame_pitch(T, M, code)
-    nch = n_chunks or lib.oiva_power_chunks(B, F)
+    Tp = lib.oiva_frame_pitch(T)
+    nch = lib.oiva_bin_groups(F)
     Wd = to_dev(W.astype(np.complex128))
     part = torch.full((B, nch, K, Tp), np.nan, dtype=torch.float64, device=dev())
-    L.check(lib.oiva_demix_power(P(Xp), P(Wd), W.shape[-1], P(part), nch, B, T, F, M, K, code, stream()),
+    L.check(lib.oiva_demix_power(P(Xg), P(Wd), W.shape[-1], P(part), B, T, F, M, K, code, stream()),
             "oiva_demix_power")
     r2 = torch.empty((B, K, Tp), dtype=torch.float64, device=dev())
-    L.check(lib.oiva_sum_partials(P(part), nch, P(r2), B, T, M, K, code, stream()), "oiva_sum_partials")
+    L.check(lib.oiva_sum_partials(P(part), nch, P(r2), B, T, K, stream()), "oiva_sum_partials")
     torch.cuda.synchronize()
     return r2.cpu().numpy()[:, :, :T], part.cpu().numpy()
 
 
-def source_model(r2, T, M, F_total, model, code):
+def source_model(r2, T, F_total, model):
     """r2 (B, K, T) -> (phi (B,K,T), wscale (B,K))"""
     lib = L.load()
     B, K, _ = r2.shape
-    Tp = lib.oiva_frame_pitch(T, M, code)
+    Tp = lib.oiva_frame_pitch(T)
     part = np.zeros((B, 1, K, Tp))
     part[:, 0, :, :T] = r2
     partd = to_dev(part)
     phi = torch.empty((B, K, Tp), dtype=torch.float64, device=dev())
     ws = torch.empty((B, K), dtype=torch.float64, device=dev())
-    L.check(lib.oiva_source_model(P(partd), 1, P(phi), P(ws), B, T, M, K, F_total, model, code, stream()),
+    L.check(lib.oiva_source_model(P(partd), 1, P(phi), P(ws), B, T, K, F_total, model, stream()),
             "oiva_source_model")
     torch.cuda.synchronize()
     return phi.cpu().numpy()[:, :, :T], ws.cpu().numpy()
 
 
-def ip_update(What, V, Cx, wscale, K):
-    """What (B,F,M,M), V (B,F,K,M,M), Cx (B,F,M,M), wscale (B,K) or None -> (What', status)"""
+def ip_update(What, V, Cx, wscale, K, grouped_c=True):
+    """What (B,F,M,M), V (B,F,K,M,M), Cx (B,F,M,M), wscale (B,K) or None -> (What', status).
+    grouped_c=False withholds the grouped covariance, which selects the row-owner (lane group per bin) sweep."""
     lib = L.load()
     B, F, M, _ = What.shape
-    Wd, Vd, Cd = to_dev(What), to_dev(V), to_dev(Cx)
+    Wd, Vgd, Cd = to_dev(What), pack_cov(V), to_dev(Cx)
+    Cgd = pack_cov(Cx[:, :, None]) if grouped_c else None
     wsd = to_dev(wscale) if wscale is not None else None
     st = torch.zeros(4, dtype=torch.int32, device=dev())
-    L.check(lib.oiva_ip_update(P(Wd), P(Vd), P(Cd), P(wsd), P(st), B, F, M, K, stream()), "oiva_ip_update")
+    L.check(lib.oiva_ip_update(P(Wd), P(Vgd), P(Cd), P(Cgd), P(wsd), P(st), B, F, M, K, stream()), "oiva_ip_update")
     torch.cuda.synchronize()
     return Wd.cpu().numpy(), int(st[0].item())
 
@@ -159,11 +165,11 @@ def projback_filters(W, Cx, K, proj_back):
     return Weff.cpu().numpy()
 
 
-def demix_output(Xp, Weff, B, T, F, M, K, code):
+def demix_output(Xg, Weff, B, T, F, M, K, code):
     lib = L.load()
     Wd = to_dev(Weff)
     dt = torch.complex64 if code == L.C64 else torch.complex128
     Y = torch.full((B, T, F, K), float("nan"), dtype=dt, device=dev())
-    L.check(lib.oiva_demix_output(P(Xp), P(Wd), P(Y), B, T, F, M, K, code, stream()), "oiva_demix_output")
+    L.check(lib.oiva_demix_output(P(Xg), P(Wd), P(Y), B, T, F, M, K, code, stream()), "oiva_demix_output")
     torch.cuda.synchronize()
     return Y.cpu().numpy()

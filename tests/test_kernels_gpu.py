@@ -23,20 +23,18 @@ def _mix(seed, M, T_samples=1500, frame=64, dtype=np.complex128, B=1):
     return np.stack(Xs).astype(dtype)
 
 
-# T chosen to cover: one ragged tile (T<128), exactly one tile, several tiles with a ragged tail
+# shapes cover: F below / at / above a multiple of 32 bins, odd channel counts, float storage
 @pytest.mark.parametrize("M,n_samples,dtype", [(4, 1500, np.complex128), (3, 1000, np.complex64), (6, 4200, np.complex128),
                                                 (16, 2300, np.complex128), (5, 4900, np.complex64), (1, 700, np.complex128)])
 def test_relayout(M, n_samples, dtype):
-    X = _mix(1, M, n_samples, 32, dtype, B=2)
-    got = G.planar(X)
-    want = G.planar_expected(X)
-    real = np.float32 if dtype == np.complex64 else np.float64
-    got = got.cpu().numpy().view(real)
+    X = _mix(1, M, n_samples, 64 if M % 2 == 0 else 32, dtype, B=2)  # F = 33 (two groups, one ragged) or 17
+    got = G.grouped(X).cpu().numpy().view(dtype)
+    want = G.grouped_expected(X)
     assert got.shape == want.shape
     assert np.array_equal(got, want)  # pure data movement: bit exact
 
 
-@pytest.mark.parametrize("no_tma", [False, True])
+@pytest.mark.parametrize("no_tma", [False, True])  # True: the debug path without TMA (complex128, K <= 2 chunks)
 @pytest.mark.parametrize("M,K,n_samples,dtype", [
     (4, 2, 1500, np.complex128), (6, 2, 2000, np.complex128), (6, 6, 1200, np.complex128), (2, 1, 900, np.complex128),
     (3, 3, 4200, np.complex128), (8, 2, 5000, np.complex128), (16, 4, 2300, np.complex128), (5, 5, 1500, np.complex128),
@@ -44,17 +42,19 @@ def test_relayout(M, n_samples, dtype):
 ])
 def test_weighted_covariance(M, K, n_samples, dtype, no_tma, monkeypatch):
     if no_tma:
+        if dtype != np.complex128:
+            pytest.skip("the non-TMA debug path is complex128 only")
         monkeypatch.setenv("OIVA_COV_NO_TMA", "1")
     else:
         monkeypatch.delenv("OIVA_COV_NO_TMA", raising=False)
     B = 2
-    X = _mix(2, M, n_samples, 32, dtype, B=B)
+    X = _mix(2, M, n_samples, 64 if M % 2 == 0 else 32, dtype, B=B)
     _, T, F, _ = X.shape
     rng = np.random.default_rng(5)
     phi = rng.gamma(1.0, 1.0, size=(B, K, T)) + 0.01
     code = G.code_of(dtype)
-    Xp = G.planar(X)
-    V = G.weighted_cov(Xp, phi, B, T, F, M, K, code)
+    Xg = G.grouped(X)
+    V = G.weighted_cov(Xg, phi, B, T, F, M, K, code)
     X128 = X.astype(np.complex128)
     tol = 1e-12 if dtype == np.complex128 else 1e-12  # products are formed in fp64 in both modes
     for b in range(B):
@@ -65,20 +65,20 @@ def test_weighted_covariance(M, K, n_samples, dtype, no_tma, monkeypatch):
     # Hermitian by construction, real diagonal
     assert np.array_equal(V, np.conj(V.swapaxes(-1, -2)))
     # plain covariance (phi == NULL)
-    C = G.weighted_cov(Xp, None, B, T, F, M, 1, code)
+    C = G.weighted_cov(Xg, None, B, T, F, M, 1, code)
     for b in range(B):
         assert rel_err(C[b, :, 0], orc.input_covariance(X128[b])) < tol
 
 
 def test_weighted_covariance_split_rows():
-    """few rows, many tiles: the tiles of a row are split over teams and combined atomically"""
+    """few bins, many frames: the frames of a group are split over teams and combined atomically"""
     M, K = 4, 2
     X = _mix(3, M, 40000, 16, np.complex128, B=1)[:, :, :3]  # F = 3 bins, T ~ 5000 frames
     _, T, F, _ = X.shape
     rng = np.random.default_rng(6)
     phi = rng.gamma(1.0, 1.0, size=(1, K, T)) + 0.01
-    Xp = G.planar(X)
-    V = G.weighted_cov(Xp, phi, 1, T, F, M, K, L.C128)
+    Xg = G.grouped(X)
+    V = G.weighted_cov(Xg, phi, 1, T, F, M, K, L.C128)
     Xf = np.ascontiguousarray(X[0].swapaxes(0, 1))
     for k in range(K):
         assert rel_err(V[0, :, k], orc.weighted_covariance(Xf, phi[0, k])) < 1e-12
@@ -89,12 +89,12 @@ def test_weighted_covariance_split_rows():
                                                   (5, 1, 1500, np.complex64), (10, 10, 900, np.complex128)])
 def test_demix_power(M, K, n_samples, dtype):
     B = 2
-    X = _mix(4, M, n_samples, 32, dtype, B=B)
+    X = _mix(4, M, n_samples, 64 if M % 2 == 0 else 32, dtype, B=B)
     _, T, F, _ = X.shape
     rng = np.random.default_rng(7)
     W = rng.standard_normal((B, F, M, M)) + 1j * rng.standard_normal((B, F, M, M))
-    Xp = G.planar(X)
-    r2, part = G.demix_power(Xp, W, B, T, F, M, K, G.code_of(dtype))
+    Xg = G.grouped(X)
+    r2, part = G.demix_power(Xg, W, B, T, F, M, K, G.code_of(dtype))
     assert np.all(np.isfinite(part))  # every (chunk, k, t) slot was written, padding included
     X128 = X.astype(np.complex128)
     for b in range(B):
@@ -110,16 +110,18 @@ def test_source_model(model):
     r2 = rng.gamma(1.0, 1.0, size=(B, K, T))
     r2[0, 0, 5] = 0.0  # exercises the 1e-15 clamp
     code = {"laplace": L.MODEL_LAPLACE, "gauss": L.MODEL_GAUSS}[model]
-    phi, ws = G.source_model(r2, T, M, F, code, L.C128)
+    phi, ws = G.source_model(r2, T, F, code)
     for b in range(B):
         r_inv, w_scale = orc.source_model(r2[b].T, model, F)
         assert rel_err(phi[b].T, r_inv) < 1e-14
         assert rel_err(ws[b], 1.0 / w_scale) < 1e-14
 
 
-@pytest.mark.parametrize("M,K", [(4, 2), (6, 2), (6, 6), (3, 3), (2, 1), (8, 2), (5, 4), (16, 4), (16, 16), (1, 1), (9, 3)])
-def test_ip_update_sweep(M, K):
-    X = _mix(9, M, 1500, 32)[0]
+@pytest.mark.parametrize("grouped_c", [True, False])  # thread-per-bin sweep (M <= 6) / lane-group-per-bin sweep
+@pytest.mark.parametrize("M,K", [(4, 2), (6, 2), (6, 6), (3, 3), (2, 1), (8, 2), (5, 4), (16, 4), (16, 16), (1, 1), (9, 3),
+                                 (6, 1), (6, 4), (5, 5), (4, 3)])
+def test_ip_update_sweep(M, K, grouped_c):
+    X = _mix(9, M, 1500, 64 if M % 2 == 0 else 32)[0]
     T, F, _ = X.shape
     Cx = orc.input_covariance(X)
     rng = np.random.default_rng(10)
@@ -132,7 +134,7 @@ def test_ip_update_sweep(M, K):
     r_inv = rng.gamma(1.0, 1.0, size=(T, K)) + 0.05
     wscale = rng.uniform(0.5, 2.0, size=(1, K))
     V = np.stack([orc.weighted_covariance(Xf, r_inv[:, s]) for s in range(K)], axis=1)  # (F, K, M, M)
-    got, status = G.ip_update(What[None], V[None], Cx[None], wscale, K)
+    got, status = G.ip_update(What[None], V[None], Cx[None], wscale, K, grouped_c)
     want = What.copy()
     want[:, :, :K] *= wscale[0][None, None, :]
     for s in range(K):
@@ -200,15 +202,15 @@ def test_init_demix_eig_matches_reference_rule(M, K):
     (16, 4, 2300, np.complex128, True), (5, 1, 1500, np.complex64, True), (3, 2, 4300, np.complex64, True)])
 def test_final_demix_and_projection_back(M, K, n_samples, dtype, proj_back):
     B = 2
-    X = _mix(16, M, n_samples, 32, dtype, B=B)
+    X = _mix(16, M, n_samples, 128 if M % 2 == 0 else 32, dtype, B=B)
     _, T, F, _ = X.shape
     rng = np.random.default_rng(17)
     W = rng.standard_normal((B, F, M, M)) + 1j * rng.standard_normal((B, F, M, M))
     X128 = X.astype(np.complex128)
     Cx = np.stack([orc.input_covariance(X128[b]) for b in range(B)])
     Weff = G.projback_filters(W.reshape(B * F, M, M), Cx.reshape(B * F, M, M), K, proj_back)
-    Xp = G.planar(X)
-    Y = G.demix_output(Xp, Weff, B, T, F, M, K, G.code_of(dtype))
+    Xg = G.grouped(X)
+    Y = G.demix_output(Xg, Weff, B, T, F, M, K, G.code_of(dtype))
     assert Y.dtype == dtype and np.all(np.isfinite(Y))
     for b in range(B):
         Xf = np.ascontiguousarray(X128[b].swapaxes(0, 1))

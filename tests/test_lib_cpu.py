@@ -46,18 +46,12 @@ def test_header_cites_the_reference_interfaces():
 
 
 def test_layout_helpers(lib):
-    # one ragged tile when T <= tile frames; tiles of 128 (M <= 8) or 64 frames otherwise; no padding in fp64
-    assert lib.oiva_tile_frames(116, 4, L.C128) == 128
-    assert lib.oiva_tile_frames(14061, 16, L.C128) == 64
-    assert lib.oiva_planar_bytes(1, 116, 2049, 4, L.C128) == 116 * 2049 * 4 * 16
-    assert lib.oiva_planar_bytes(3, 467, 10, 8, L.C128) == 3 * 467 * 10 * 8 * 16
-    assert lib.oiva_frame_pitch(116, 4, L.C128) == 128
-    assert lib.oiva_frame_pitch(467, 8, L.C128) == 512
-    # float storage: tiles stay 16-byte multiples (one zero frame of padding when M*T_last is odd)
-    nb = lib.oiva_planar_bytes(1, 61, 1, 3, L.C64)
-    assert nb % 16 == 0 and nb >= 61 * 3 * 8
-    assert 1 <= lib.oiva_power_chunks(1, 2049) <= 2049
-    assert lib.oiva_power_chunks(512, 2049) == 33
+    # bins are grouped by 32 (lane <-> bin); the last group of a mixture is zero padded
+    assert lib.oiva_bin_groups(2049) == 65 and lib.oiva_bin_groups(32) == 1 and lib.oiva_bin_groups(33) == 2
+    assert lib.oiva_grouped_bytes(1, 116, 2049, 4, L.C128) == 65 * 32 * 116 * 4 * 16
+    assert lib.oiva_grouped_bytes(3, 467, 10, 8, L.C64) == 3 * 32 * 467 * 8 * 8
+    assert lib.oiva_frame_pitch(116) == 128 and lib.oiva_frame_pitch(128) == 128 and lib.oiva_frame_pitch(467) == 480
+    assert lib.oiva_grouped_cov_bytes(2, 2049, 6, 2) == 2 * 65 * 2 * 21 * 32 * 16
 
 
 def test_argument_validation_without_gpu(lib):
