@@ -306,12 +306,13 @@ def run_gpu(args):
         del X, Y
         torch.cuda.empty_cache()
         e2e_steps = max(1, min(steps, 3))
-        for _ in range(1):
-            Yh = ob.overiva_batch(Xh, n_src=K, n_iter=N_ITER, proj_back=True, model=MODEL)
+        Yh = torch.empty((B, T, F, K), dtype=torch.complex128, pin_memory=True)  # caller-owned result buffer
+        for _ in range(2):
+            ob.overiva_batch(Xh, n_src=K, n_iter=N_ITER, proj_back=True, model=MODEL, out=Yh)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            Yh = ob.overiva_batch(Xh, n_src=K, n_iter=N_ITER, proj_back=True, model=MODEL)
+            ob.overiva_batch(Xh, n_src=K, n_iter=N_ITER, proj_back=True, model=MODEL, out=Yh)
         barrier()
         dt = time.perf_counter() - t0
         t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -320,7 +321,9 @@ def run_gpu(args):
         e2e = {
             "value": world * B * DURATION_S / (float(t_e.item()) / e2e_steps), "unit": UNIT,
             "h2d_bytes_per_step": Xh.numel() * 16, "d2h_bytes_per_step": Yh.numel() * 16,
-            "steps": e2e_steps, "api": "overiva_b200.overiva_batch(pinned CPU tensor) -> pinned CPU tensor",
+            "steps": e2e_steps,
+            "api": "overiva_b200.overiva_batch(pinned CPU tensor, out=pinned CPU tensor): chunks of 64 mixtures, "
+                   "H2D / loop / D2H overlapped on three streams",
         }
         assert bool(torch.isfinite(Yh.real).all())
     except RuntimeError as exc:  # e.g. not enough pinnable host memory

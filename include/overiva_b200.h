@@ -83,16 +83,21 @@ int oiva_relayout(const void* X, void* Xg, int n_batch, int n_frames, int n_freq
 int oiva_weighted_cov(const void* Xg, const double* phi, void* Vg, int n_batch, int n_frames, int n_freq,
                       int n_chan, int n_src, int dtype, void* stream);
 
+/* per-bin arrays of n_elems c128 each: row-major (R, n_elems) <-> grouped [gi][n_elems][32] (padded bins: 0).
+ * Inside the loop the demixing matrices live in the grouped form (coalesced for lane <-> bin kernels). */
+int oiva_group_rows(const void* rows, void* grouped, int n_batch, int n_freq, int n_elems, void* stream);
+int oiva_ungroup_rows(const void* grouped, void* rows, int n_batch, int n_freq, int n_elems, void* stream);
+
 /* Vg (grouped lower triangles) -> V (R,K,M,M) c128 full Hermitian matrices, row-major. */
 int oiva_unpack_cov(const void* Vg, void* V, int n_batch, int n_freq, int n_chan, int n_src, void* stream);
 
 /* r2part[b][g][k][t] = sum_{f in group g} |w_k(f)^H x(f,t)|^2 : (B,NG,K,Tp), padding frames written as 0.
- * W: (R,M,w_cols) c128, columns :K used (w_cols = M for the W_hat matrices of the plan, K for plain
- * (R,M,K) filters).
+ * W: per-bin M x w_cols c128 matrices, columns :K used (w_cols = M for W_hat, K for plain filters), either
+ * row-major (R,M,w_cols) (w_grouped = 0) or grouped [gi][M*w_cols][32] (w_grouped = 1, what the plan keeps).
  * replaces: overiva.py:140 (demix) + the norm over frequency at overiva.py:152-155 / ive.py:204-208;
  * Y is never materialised inside the loop. */
-int oiva_demix_power(const void* Xg, const void* W, int w_cols, double* r2part, int n_batch, int n_frames,
-                     int n_freq, int n_chan, int n_src, int dtype, void* stream);
+int oiva_demix_power(const void* Xg, const void* W, int w_cols, int w_grouped, double* r2part, int n_batch,
+                     int n_frames, int n_freq, int n_chan, int n_src, int dtype, void* stream);
 
 /* r2[b][k][t] = sum_chunks r2part[b][chunk][k][t] (fixed order, deterministic).  Used on its own by the
  * frequency-sharded driver, which all-reduces r2 across ranks before oiva_source_model(n_chunks=1). */
@@ -108,12 +113,15 @@ int oiva_source_model(const double* r2part, int n_chunks, double* phi, double* w
                       int n_frames, int n_src, int n_freq_total, int model, void* stream);
 
 /* One sweep over the K sources, per bin, in order:  W[:, :K] *= wscale;  for s: w_s = (What^H V_s)^-1 e_s;
- * w_s /= sqrt(w_s^H V_s w_s);  J = (W^H C E1)^-1 (W^H C E2).   What (R,M,M) c128 in place, Vg grouped,
- * C (R,M,M) c128 full, Cg = the same covariance in the grouped lower-triangle layout (may be NULL).
- * With Cg given and M <= 6 the sweep runs one THREAD per bin (lane <-> bin, in-register LU with partial
- * pivoting); otherwise a group of next_pow2(M) lanes owns a bin (one matrix row per lane).
+ * w_s /= sqrt(w_s^H V_s w_s);  J = (W^H C E1)^-1 (W^H C E2).   Wg: the W_hat matrices in the GROUPED layout
+ * [gi][M*M][32] (oiva_group_rows of the (R,M,M) array), updated in place; Vg grouped; C (R,M,M) c128 full,
+ * Cg = the same covariance in the grouped lower-triangle layout (may be NULL).
+ * With Cg given and M <= 6 the sweep runs one THREAD per bin (lane <-> bin): for K < M the update is
+ * w = V^-1 q with q = W_hat^-H e_s from a K x K pivoted solve and V factorised by Cholesky (same result as
+ * the reference's (W_hat^H V)^-1 e_s, ~3x fewer operations); for K = M an in-register LU with partial
+ * pivoting.  Otherwise a group of next_pow2(M) lanes owns a bin (one matrix row per lane, Gauss-Jordan).
  * replaces: overiva.py:161-167 (W rescale), :181-182 (zgemm + zgesv), :185-186, :189-190 (:96-98). */
-int oiva_ip_update(void* What, const void* Vg, const void* C, const void* Cg, const double* wscale, int* status,
+int oiva_ip_update(void* Wg, const void* Vg, const void* C, const void* Cg, const double* wscale, int* status,
                    int n_batch, int n_freq, int n_chan, int n_src, void* stream);
 
 /* Build What (R,M,M): W from eye / eigenvectors / W0, then J and the -I block.
@@ -207,9 +215,12 @@ int oiva_plan_output(oiva_plan_t* plan, int proj_back, void* Y, void* stream);
 /* copy the filters W (B,F,M,K) c128 (contiguous) out of What       overiva.py:201-202 */
 int oiva_plan_filters(oiva_plan_t* plan, void* W, void* stream);
 /* device pointers into the workspace (for tests and wrappers) */
-void* oiva_plan_what(oiva_plan_t* plan);    /* (R,M,M) c128 */
+void* oiva_plan_what(oiva_plan_t* plan);    /* (R,M,M) c128 row-major; refreshed from the grouped state by
+                                               oiva_plan_init / oiva_plan_output / oiva_plan_filters */
 void* oiva_plan_cov(oiva_plan_t* plan);     /* (R,M,M) c128, full */
 void* oiva_plan_samples(oiva_plan_t* plan); /* Xg */
+/* the status word (4 ints).  The CALLER zeroes it after oiva_plan_bind (the workspace is uninitialised memory);
+ * it then accumulates (atomic OR) over everything the plan runs, across loads, until the caller zeroes it again */
 int* oiva_plan_status_ptr(oiva_plan_t* plan);
 /* synchronises the stream and returns the status word (0 = fine) */
 int oiva_plan_status(oiva_plan_t* plan, void* stream);

@@ -45,7 +45,9 @@ SIGNATURES = {
     "oiva_relayout": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "oiva_weighted_cov": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "oiva_unpack_cov": (_i, [_p, _p, _i, _i, _i, _i, _p]),
-    "oiva_demix_power": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "oiva_demix_power": (_i, [_p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "oiva_group_rows": (_i, [_p, _p, _i, _i, _i, _p]),
+    "oiva_ungroup_rows": (_i, [_p, _p, _i, _i, _i, _p]),
     "oiva_sum_partials": (_i, [_p, _i, _p, _i, _i, _i, _p]),
     "oiva_source_model": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
     "oiva_ip_update": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),

@@ -93,6 +93,8 @@ class DemixPlan:
         with torch.cuda.device(self.device):
             self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         L.check(self.lib.oiva_plan_bind(h, _ptr(self.ws), nbytes), "oiva_plan_bind")
+        off = self.lib.oiva_plan_status_ptr(h) - self.ws.data_ptr()
+        self.ws[off : off + 16].zero_()  # the status word accumulates from here on (see raise_on_failure)
         self.Tp = self.lib.oiva_frame_pitch(n_frames)
 
     def __del__(self):
@@ -269,17 +271,113 @@ def auxiva(X, n_iter=20, proj_back=True, W0=None, model="laplace", init_eig=Fals
     return overiva(X, None, n_iter, proj_back, W0, model, init_eig, return_filters, callback)
 
 
+def _host_pipeline(Xh, n_src, n_iter, proj_back, W0, model, init_eig, return_filters, chunk, out, device):
+    """Host-resident batch through the GPU in chunks: H2D of chunk i+1, the loop on chunk i and D2H of chunk
+    i-1 run concurrently on three streams (PCIe is full duplex), with two device slots per direction.  The
+    whole call then costs about max(PCIe time, compute time) instead of their sum."""
+    B, T, F, M = Xh.shape
+    K = M if n_src is None else int(n_src)
+    if not (1 <= K <= M):
+        raise ValueError("n_src=%d must be in 1..n_chan=%d" % (K, M))
+    dev = device
+    cdt = Xh.dtype
+    code = _model_code(model)
+    Yh = out if out is not None else torch.empty((B, T, F, K), dtype=cdt, pin_memory=True)
+    Wh = torch.empty((B, F, M, K), dtype=torch.complex128, pin_memory=True) if return_filters else None
+    W0d = _prepare_W0(W0, B, F, M, K, dev) if W0 is not None else None
+    main = torch.cuda.current_stream(dev)
+    s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    for st in (s_in, s_cmp, s_out):
+        st.wait_stream(main)
+    n_slots = 2
+    Xd = [torch.empty((chunk, T, F, M), dtype=cdt, device=dev) for _ in range(n_slots)]
+    Yd = [torch.empty((chunk, T, F, K), dtype=cdt, device=dev) for _ in range(n_slots)]
+    Wd = [torch.empty((chunk, F, M, K), dtype=torch.complex128, device=dev) if return_filters else None
+          for _ in range(n_slots)]
+    plans = {}
+
+    def plan_for(nb, slot):
+        key = (nb, slot)
+        if key not in plans:
+            with torch.cuda.stream(s_cmp):
+                plans[key] = DemixPlan(nb, T, F, M, K, code, cdt, dev)
+        return plans[key]
+
+    ev_in = [None] * n_slots   # H2D of the chunk in slot s finished
+    ev_cmp = [None] * n_slots  # compute on slot s finished (X slot reusable, Y slot filled)
+    ev_out = [None] * n_slots  # D2H of slot s finished (Y slot reusable)
+    for i, b0 in enumerate(range(0, B, chunk)):
+        nb = min(chunk, B - b0)
+        slot = i % n_slots
+        with torch.cuda.stream(s_in):
+            if ev_cmp[slot] is not None:
+                s_in.wait_event(ev_cmp[slot])
+            Xd[slot][:nb].copy_(Xh[b0 : b0 + nb], non_blocking=True)
+            ev_in[slot] = s_in.record_event()
+        with torch.cuda.stream(s_cmp):
+            s_cmp.wait_event(ev_in[slot])
+            if ev_out[slot] is not None:
+                s_cmp.wait_event(ev_out[slot])
+            plan = plan_for(nb, slot)
+            plan.load(Xd[slot][:nb])
+            if W0d is not None:
+                plan.init(L.INIT_W0, W0d[b0 : b0 + nb].contiguous())
+            else:
+                plan.init(L.INIT_EIG if init_eig else L.INIT_EYE)
+            plan.iterate(n_iter)
+            plan.output(proj_back, out=Yd[slot][:nb])
+            if return_filters:
+                L.check(plan.lib.oiva_plan_filters(plan.h, _ptr(Wd[slot]), _stream_ptr(dev)), "oiva_plan_filters")
+            ev_cmp[slot] = s_cmp.record_event()
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_cmp[slot])
+            Yh[b0 : b0 + nb].copy_(Yd[slot][:nb], non_blocking=True)
+            if return_filters:
+                Wh[b0 : b0 + nb].copy_(Wd[slot][:nb], non_blocking=True)
+            ev_out[slot] = s_out.record_event()
+    for st in (s_in, s_cmp, s_out):
+        main.wait_stream(st)
+    with torch.cuda.stream(s_cmp):
+        for plan in plans.values():
+            plan.raise_on_failure()  # the status word accumulates over all chunks a plan has processed
+    main.synchronize()
+    return Yh, Wh
+
+
 def overiva_batch(X, n_src=None, n_iter=20, proj_back=True, W0=None, model="laplace", init_eig=False,
-                  return_filters=False):
+                  return_filters=False, chunk=64, out=None):
     """Many independent mixtures at once: X (B, n_frames, n_freq, n_chan) -> Y (B, n_frames, n_freq, n_src)
     [, W (B, n_freq, n_chan, n_src)].  The role of the reference's task farm (``overiva_sim.py`` +
-    ``rrtools``) for mixtures of one shape; every mixture is processed exactly as ``overiva`` would."""
+    ``rrtools``) for mixtures of one shape; every mixture is processed exactly as ``overiva`` would.
+
+    Host inputs (numpy / CPU tensors) with more than ``chunk`` mixtures are streamed through the GPU in chunks
+    with copies and compute overlapped (pin the input for full PCIe speed; ``out`` may be a preallocated pinned
+    (B, T, F, K) tensor to receive Y).  Device inputs are processed in one piece."""
     if getattr(X, "ndim", 0) != 4:
         raise ValueError("X must have shape (n_batch, n_frames, n_freq, n_chan)")
+    is_host = not (isinstance(X, torch.Tensor) and X.is_cuda)
+    if is_host and X.shape[0] > chunk:
+        kind = "cpu" if isinstance(X, torch.Tensor) else "numpy"
+        Xh = X if kind == "cpu" else torch.from_numpy(np.ascontiguousarray(X))
+        if Xh.dtype not in (torch.complex128, torch.complex64):
+            raise TypeError("X must be complex64 or complex128, got %s" % Xh.dtype)
+        dev = _require_cuda()
+        with torch.cuda.device(dev):
+            Yh, Wh = _host_pipeline(Xh.contiguous(), n_src, n_iter, proj_back, W0, model, init_eig, return_filters,
+                                    int(chunk), out, dev)
+        if kind == "numpy":
+            Yh = Yh.numpy()
+            Wh = Wh.numpy().astype(X.dtype) if Wh is not None else None
+        elif Wh is not None:
+            Wh = Wh.to(Xh.dtype)
+        return (Yh, Wh) if return_filters else Yh
     inp = _Input(X)
     with torch.cuda.device(inp.device):
         Y, W, _ = _run_overiva(inp.dev, n_src, n_iter, proj_back, W0, model, init_eig, return_filters, None, None)
         Yo = inp.give_back(Y)
+        if out is not None:
+            out.copy_(Yo if isinstance(Yo, torch.Tensor) else torch.from_numpy(Yo))
+            Yo = out
         if return_filters:
             return Yo, inp.give_back(W, inp.dtype)
         return Yo
@@ -429,7 +527,7 @@ def ogive(X, n_iter=4000, step_size=0.1, tol=1e-3, update="demix", proj_back=Tru
                         "oiva_ogive_switching")
             if callback is not None and epoch % 100 == 0:  # ive.py:194-200
                 callback(inp.give_back(project(w)))
-            L.check(lib.oiva_demix_power(plan.samples_ptr, _ptr(w), 1, _ptr(r2part), 1, T, F, M, 1, code, st),
+            L.check(lib.oiva_demix_power(plan.samples_ptr, _ptr(w), 1, 0, _ptr(r2part), 1, T, F, M, 1, code, st),
                     "oiva_demix_power")
             L.check(lib.oiva_source_model(_ptr(r2part), nch, _ptr(phi), None, 1, T, 1, F, mcode, st),
                     "oiva_source_model")

@@ -23,7 +23,7 @@ struct oiva_plan {
     int Tp, NG;
     int es;  // bytes per real element of X / Y
     // workspace offsets
-    size_t off_xg, off_c, off_cg, off_what, off_vg, off_weff, off_r2part, off_r2, off_phi, off_wscale, off_evals, off_status;
+    size_t off_xg, off_c, off_cg, off_what, off_wg, off_vg, off_weff, off_r2part, off_r2, off_phi, off_wscale, off_evals, off_status;
     size_t ws_bytes;
     unsigned char* ws;
     long long launches;
@@ -98,6 +98,7 @@ extern "C" int oiva_plan_create(oiva_plan_t** out, const oiva_plan_desc* desc) {
     p->off_c = o;       o += align_up(R * M * M * 16);
     p->off_cg = o;      o += align_up(G * oiva_tri((int)M) * OIVA_GROUP * 16);
     p->off_what = o;    o += align_up(R * M * M * 16);
+    p->off_wg = o;      o += align_up(G * M * M * OIVA_GROUP * 16);  // the loop's W_hat, grouped
     // grouped covariances of the K sources; also scratch for the eigenvectors at init time
     p->off_vg = o;      o += align_up(max_sz(G * K * oiva_tri((int)M) * OIVA_GROUP * 16, R * M * M * 16));
     p->off_weff = o;    o += align_up(R * M * K * 16);
@@ -198,7 +199,6 @@ extern "C" int oiva_plan_load(oiva_plan_t* p, const void* X, void* stream) {
     PLAN_READY(p, "oiva_plan_load");
     OIVA_REQUIRE(X, "oiva_plan_load: null X");
     const oiva_plan_desc& d = p->d;
-    OIVA_CUDA_CHECK(cudaMemsetAsync(p->ws + p->off_status, 0, 16, (cudaStream_t)stream));
     int rc = oiva_relayout(X, p->ws + p->off_xg, d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.dtype, stream);
     if (rc) return rc;
     p->launches += 1;
@@ -211,7 +211,6 @@ extern "C" int oiva_plan_load(oiva_plan_t* p, const void* X, void* stream) {
 
 extern "C" int oiva_plan_adopt_samples(oiva_plan_t* p, void* stream) {
     PLAN_READY(p, "oiva_plan_adopt_samples");
-    OIVA_CUDA_CHECK(cudaMemsetAsync(p->ws + p->off_status, 0, 16, (cudaStream_t)stream));
     int rc = plan_input_cov(p, stream);
     if (rc) return rc;
     p->loaded = true;
@@ -239,15 +238,26 @@ extern "C" int oiva_plan_init(oiva_plan_t* p, int mode, const void* W0, void* st
     int rc = oiva_init_demix(p->ws + p->off_what, p->ws + p->off_c, W0, evecs, mode, status, (int)p->R, d.n_chan,
                              d.n_src, stream);
     if (rc) return rc;
-    p->launches += 1;
+    rc = oiva_group_rows(p->ws + p->off_what, p->ws + p->off_wg, d.n_batch, d.n_freq, d.n_chan * d.n_chan, stream);
+    if (rc) return rc;
+    p->launches += 2;
     p->inited = true;
+    return OIVA_OK;
+}
+
+// row-major copy of the loop's grouped W_hat (for projection back / filters / callers)
+static int plan_sync_what(oiva_plan_t* p, void* stream) {
+    const oiva_plan_desc& d = p->d;
+    int rc = oiva_ungroup_rows(p->ws + p->off_wg, p->ws + p->off_what, d.n_batch, d.n_freq, d.n_chan * d.n_chan, stream);
+    if (rc) return rc;
+    p->launches += 1;
     return OIVA_OK;
 }
 
 static int plan_power_partials(oiva_plan_t* p, void* stream) {
     const oiva_plan_desc& d = p->d;
     SpanGuard g(p, TK_POWER, stream);
-    int rc = oiva_demix_power(p->ws + p->off_xg, p->ws + p->off_what, d.n_chan, (double*)(p->ws + p->off_r2part),
+    int rc = oiva_demix_power(p->ws + p->off_xg, p->ws + p->off_wg, d.n_chan, 1, (double*)(p->ws + p->off_r2part),
                               d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.n_src, d.dtype, stream);
     if (rc) return rc;
     p->launches += 1;
@@ -269,7 +279,7 @@ static int plan_update_from(oiva_plan_t* p, const double* r2src, int nch, void* 
     if (rc) return rc;
     {
         SpanGuard g(p, TK_SOLVE, stream);
-        rc = oiva_ip_update(p->ws + p->off_what, p->ws + p->off_vg, p->ws + p->off_c, p->ws + p->off_cg, wscale,
+        rc = oiva_ip_update(p->ws + p->off_wg, p->ws + p->off_vg, p->ws + p->off_c, p->ws + p->off_cg, wscale,
                             (int*)(p->ws + p->off_status), d.n_batch, d.n_freq, d.n_chan, d.n_src, stream);
     }
     if (rc) return rc;
@@ -315,7 +325,9 @@ extern "C" int oiva_plan_output(oiva_plan_t* p, int proj_back, void* Y, void* st
     PLAN_INITED(p, "oiva_plan_output");
     OIVA_REQUIRE(Y, "oiva_plan_output: null Y");
     const oiva_plan_desc& d = p->d;
-    int rc = oiva_projback_filters(p->ws + p->off_what, d.n_chan, p->ws + p->off_c, p->ws + p->off_weff, (int)p->R,
+    int rc = plan_sync_what(p, stream);
+    if (rc) return rc;
+    rc = oiva_projback_filters(p->ws + p->off_what, d.n_chan, p->ws + p->off_c, p->ws + p->off_weff, (int)p->R,
                                    d.n_chan, d.n_src, proj_back, stream);
     if (rc) return rc;
     rc = oiva_demix_output(p->ws + p->off_xg, p->ws + p->off_weff, Y, d.n_batch, d.n_frames, d.n_freq, d.n_chan,
@@ -330,7 +342,9 @@ extern "C" int oiva_plan_filters(oiva_plan_t* p, void* W, void* stream) {
     OIVA_REQUIRE(W, "oiva_plan_filters: null W");
     const oiva_plan_desc& d = p->d;
     // plain copy of the W columns: proj_back = 0
-    int rc = oiva_projback_filters(p->ws + p->off_what, d.n_chan, p->ws + p->off_c, W, (int)p->R, d.n_chan, d.n_src, 0,
+    int rc = plan_sync_what(p, stream);
+    if (rc) return rc;
+    rc = oiva_projback_filters(p->ws + p->off_what, d.n_chan, p->ws + p->off_c, W, (int)p->R, d.n_chan, d.n_src, 0,
                                    stream);
     if (rc) return rc;
     p->launches += 1;
@@ -381,6 +395,7 @@ extern "C" int oiva_overiva_host(const void* X_host, void* Y_host, void* W_host,
     HOST_TRY(cudaMalloc(&dW, wbytes));
     HOST_TRY(cudaMalloc(&ws, p->ws_bytes));
     HOST_RC(oiva_plan_bind(p, ws, p->ws_bytes));
+    HOST_TRY(cudaMemsetAsync(oiva_plan_status_ptr(p), 0, 16, st));
     HOST_TRY(cudaMemcpyAsync(dX, X_host, xbytes, cudaMemcpyHostToDevice, st));
     if (init_mode == OIVA_INIT_W0) HOST_TRY(cudaMemcpyAsync(dW, W0_host, wbytes, cudaMemcpyHostToDevice, st));
     HOST_RC(oiva_plan_load(p, dX, st));

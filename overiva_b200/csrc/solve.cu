@@ -17,7 +17,7 @@ __host__ __device__ constexpr int ip_warps() { return M > 8 ? 2 : 4; }
 
 // V arrives in the grouped lower-triangle layout Vg[gi][k][e][l] written by the covariance kernel.
 template <int M>
-__global__ void __launch_bounds__(ip_warps<M>() * 32) k_ip_update(cplx* __restrict__ What, const cplx* __restrict__ Vg,
+__global__ void __launch_bounds__(ip_warps<M>() * 32) k_ip_update(cplx* __restrict__ Wg, const cplx* __restrict__ Vg,
                                                                   const cplx* __restrict__ C,
                                                                   const double* __restrict__ wscale, int* status,
                                                                   long long R, int F, int NG, int K) {
@@ -35,10 +35,12 @@ __global__ void __launch_bounds__(ip_warps<M>() * 32) k_ip_update(cplx* __restri
     const long long bmix = rowc / F;
     const int fbin = (int)(rowc - bmix * F);
     const cplx* Vbin = Vg + ((size_t)(bmix * NG + fbin / OIVA_GROUP) * K * NE) * OIVA_GROUP + fbin % OIVA_GROUP;
+    // this bin's W_hat inside the grouped array Wg[gi][M*M][32]
+    cplx* Wbin = Wg + ((size_t)(bmix * NG + fbin / OIVA_GROUP) * M * M) * OIVA_GROUP + fbin % OIVA_GROUP;
 
     if (rv) {
 #pragma unroll
-        for (int c = 0; c < M; ++c) sW[gl * M + c] = What[rowc * M * M + gl * M + c];
+        for (int c = 0; c < M; ++c) sW[gl * M + c] = Wbin[(size_t)(gl * M + c) * OIVA_GROUP];
         if (wscale) {
             const long long b = rowc / F;
             for (int c = 0; c < K; ++c) sW[gl * M + c] = cscale(sW[gl * M + c], wscale[b * K + c]);
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(ip_warps<M>() * 32) k_ip_update(cplx* __restri
         for (int c = 0; c < M; ++c) {
             const cplx v = sW[gl * M + c];
             if (!isfinite(v.x) || !isfinite(v.y)) bad = true;
-            if (row_ok) What[row * M * M + gl * M + c] = v;
+            if (row_ok) Wbin[(size_t)(gl * M + c) * OIVA_GROUP] = v;
         }
     }
     if (row_ok && (singular || bad))
@@ -316,6 +318,7 @@ int ip_update_tpb(int M, int K, cplx* What, const cplx* Vg, const cplx* Cg, cons
 
 extern "C" int oiva_ip_update(void* What, const void* V, const void* C, const void* Cg, const double* wscale,
                               int* status, int n_batch, int n_freq, int n_chan, int n_src, void* stream) {
+    // What: the demixing matrices in the GROUPED layout Wg[gi][M*M][32] (oiva_group_rows of the (R,M,M) array)
     OIVA_REQUIRE(What && V && C && status, "oiva_ip_update: null pointer");
     OIVA_REQUIRE(n_batch > 0 && n_freq > 0 && n_src >= 1 && n_src <= n_chan, "oiva_ip_update: bad shape");
     const long long R = (long long)n_batch * n_freq;

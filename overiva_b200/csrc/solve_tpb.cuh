@@ -21,6 +21,20 @@ __device__ __forceinline__ cplx herm_load(const cplx* __restrict__ base, int i, 
     return v;
 }
 
+// this lane's W_hat inside the grouped array Wg[gi][M*M][32]: element idx of the row-major M x M matrix
+struct WLane {
+    cplx* base;
+    __device__ __forceinline__ cplx& operator[](int idx) const { return base[idx * OIVA_GROUP]; }
+};
+
+// acc -= conj(a) * b
+__device__ __forceinline__ void cfms_conj(cplx& acc, cplx a, cplx b) {
+    acc.x = fma(-a.x, b.x, acc.x);
+    acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(-a.x, b.y, acc.y);
+    acc.y = fma(a.y, b.x, acc.y);
+}
+
 __device__ __forceinline__ void cswap_if(bool c, cplx& a, cplx& b) {
     const cplx ta = a, tb = b;
     a.x = c ? tb.x : ta.x;
@@ -82,9 +96,23 @@ __device__ __forceinline__ void lu_solve(cplx (&A)[N][N], cplx (&rhs)[N][NR], bo
     });
 }
 
+// element (i, j) of a Hermitian matrix staged in shared memory as [e][32 lanes] lower-triangle entries
+__device__ __forceinline__ cplx herm_lds(const cplx* sbase, int i, int j) {
+    const int hi = i >= j ? i : j, lo = i >= j ? j : i;
+    cplx v = sbase[(hi * (hi + 1) / 2 + lo) * OIVA_GROUP];
+    if (i < j) v.y = -v.y;
+    return v;
+}
+
+template <bool STAGED>
+__device__ __forceinline__ cplx herm_get(const cplx* base, int i, int j) {
+    if constexpr (STAGED) return herm_lds(base, i, j);
+    else return herm_load(base, i, j);
+}
+
 // OverIVA background refresh for one bin held by one thread: J = (W^H C E1)^-1 (W^H C E2)      overiva.py:96-98
-template <int M, int K>
-__device__ __forceinline__ void background_tpb(cplx* __restrict__ Wm, const cplx* __restrict__ Cb, bool& singular) {
+template <int M, int K, bool STAGED>
+__device__ __forceinline__ void background_tpb(WLane Wm, const cplx* sC, bool& singular) {
     if constexpr (K < M) {
         cplx T1[K][K], T2[K][M - K];
 #pragma unroll
@@ -98,7 +126,7 @@ __device__ __forceinline__ void background_tpb(cplx* __restrict__ Wm, const cplx
         for (int j = 0; j < M; ++j) {
             cplx crow[M];
 #pragma unroll
-            for (int c = 0; c < M; ++c) crow[c] = herm_load(Cb, j, c);
+            for (int c = 0; c < M; ++c) crow[c] = herm_get<STAGED>(sC, j, c);
 #pragma unroll
             for (int i = 0; i < K; ++i) {
                 const cplx a = Wm[j * M + i];
@@ -116,24 +144,183 @@ __device__ __forceinline__ void background_tpb(cplx* __restrict__ Wm, const cplx
     }
 }
 
-// grid: ceil(G*32 / 128) CTAs of 128 threads; thread <-> (group gi, lane = bin % 32)
-template <int M, int K>
-__global__ void __launch_bounds__(128) k_ip_update_tpb(cplx* __restrict__ What, const cplx* __restrict__ Vg,
-                                                       const cplx* __restrict__ Cg, const double* __restrict__ wscale,
-                                                       int* status, int F, int NG, long long G) {
+// ---- one IP update, determined case (K == M): w_s = (W^H V_s)^-1 e_s by LU with partial pivoting ----------
+template <int M, bool STAGED>
+__device__ __forceinline__ void ip_source_full(WLane Wm, const cplx* sV, int s, bool& singular) {
+    cplx A[M][M], rhs[M][1];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+#pragma unroll
+        for (int c = 0; c < M; ++c) A[i][c] = cmake(0.0, 0.0);
+        rhs[i][0] = cmake(i == s ? 1.0 : 0.0, 0.0);
+    }
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        cplx vrow[M];
+#pragma unroll
+        for (int c = 0; c < M; ++c) vrow[c] = herm_get<STAGED>(sV, j, c);
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            const cplx a = Wm[j * M + i];
+#pragma unroll
+            for (int c = 0; c < M; ++c) cfmac(A[i][c], a, vrow[c]);
+        }
+    }
+    lu_solve<M, 1>(A, rhs, singular);
+    // normalise: w /= sqrt(w^H V_s w)                                                   overiva.py:185-186
+    cplx d = cmake(0.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        cplx u = cmake(0.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < M; ++j) cfma(u, herm_get<STAGED>(sV, i, j), rhs[j][0]);
+        cfmac(d, rhs[i][0], u);
+    }
+    const cplx inv = crecip(csqrt_(d));
+#pragma unroll
+    for (int i = 0; i < M; ++i) Wm[i * M + s] = cmul(rhs[i][0], inv);
+}
+
+// ---- one IP update, overdetermined case (K < M) ------------------------------------------------------------
+// (W_hat^H V)^-1 e_s = V^-1 q with q = W_hat^-H e_s.  Because W_hat = [W | (J; -I)], q follows from a K x K
+// system:  q1 = (W1^H + W2^H J^H)^-1 e_s,  q2 = J^H q1   (W1 / W2: top K / bottom M-K rows of W);  then V w = q is
+// solved by Cholesky (V is Hermitian positive definite: no pivoting, no row swaps), and the normalisation needs
+// only w^H V w = w^H q.  ~3x fewer operations than forming W_hat^H V and factorising it, same result.
+template <int M, int K, bool STAGED>
+__device__ __forceinline__ void ip_source_reduced(WLane Wm, const cplx* sV, int s, bool& singular) {
+    constexpr int R = M - K;
+    cplx q[M];
+    {
+        cplx Bm[K][K], e[K][1];
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            e[i][0] = cmake(i == s ? 1.0 : 0.0, 0.0);
+#pragma unroll
+            for (int c = 0; c < K; ++c) Bm[i][c] = cconj(Wm[c * M + i]);  // W1^H
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            cplx jc[K];
+#pragma unroll
+            for (int c = 0; c < K; ++c) jc[c] = cconj(Wm[c * M + K + r]);  // conj(J[c][r])
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                const cplx w2 = Wm[(K + r) * M + i];  // W2[r][i]
+#pragma unroll
+                for (int c = 0; c < K; ++c) cfmac(Bm[i][c], w2, jc[c]);  // += conj(W2[r][i]) conj(J[c][r])
+            }
+        }
+        lu_solve<K, 1>(Bm, e, singular);
+#pragma unroll
+        for (int i = 0; i < K; ++i) q[i] = e[i][0];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+            for (int c = 0; c < K; ++c) cfmac(acc, Wm[c * M + K + r], q[c]);  // conj(J[c][r]) q1[c]
+            q[K + r] = acc;
+        }
+    }
+    // Cholesky V = L L^H in place on the lower triangle (row-major packed: e = i(i+1)/2 + j)
+    cplx Lm[oiva_tri(M)];
+#pragma unroll
+    for (int e = 0; e < oiva_tri(M); ++e) {
+        if constexpr (STAGED) Lm[e] = sV[e * OIVA_GROUP];
+        else Lm[e] = ld_nc_c(sV + (size_t)e * OIVA_GROUP);
+    }
+    double dinv[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        double djj = Lm[j * (j + 1) / 2 + j].x;
+#pragma unroll
+        for (int k = 0; k < j; ++k) {
+            const cplx l = Lm[j * (j + 1) / 2 + k];
+            djj = fma(-l.x, l.x, fma(-l.y, l.y, djj));
+        }
+        if (!(djj > 0.0)) singular = true;  // not positive definite (or NaN)
+        const double ljj = sqrt(djj);
+        dinv[j] = 1.0 / ljj;
+#pragma unroll
+        for (int i = j + 1; i < M; ++i) {
+            cplx v = Lm[i * (i + 1) / 2 + j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) {
+                // v -= L[i][k] conj(L[j][k])
+                const cplx a = Lm[i * (i + 1) / 2 + k], bb = Lm[j * (j + 1) / 2 + k];
+                v.x = fma(-a.x, bb.x, fma(-a.y, bb.y, v.x));
+                v.y = fma(-a.y, bb.x, fma(a.x, bb.y, v.y));
+            }
+            Lm[i * (i + 1) / 2 + j] = cscale(v, dinv[j]);
+        }
+    }
+    // forward: L y = q
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        cplx v = q[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) cfms(v, Lm[i * (i + 1) / 2 + k], q[k]);
+        q[i] = cscale(v, dinv[i]);
+    }
+    // normalisation: w^H V w = w^H L L^H w = |L^H w|^2 = |y|^2 -- available before the back substitution
+    double den = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) den = fma(q[i].x, q[i].x, fma(q[i].y, q[i].y, den));
+    // backward: L^H w = y
+#pragma unroll
+    for (int ii = 0; ii < M; ++ii) {
+        const int i = M - 1 - ii;
+        cplx v = q[i];
+#pragma unroll
+        for (int k = i + 1; k < M; ++k) cfms_conj(v, Lm[k * (k + 1) / 2 + i], q[k]);  // L^H[i][k] = conj(L[k][i])
+        q[i] = cscale(v, dinv[i]);
+    }
+    const double inv = 1.0 / sqrt(den);  // w^H V_s w = |y|^2 is real positive                 overiva.py:185-186
+#pragma unroll
+    for (int i = 0; i < M; ++i) Wm[i * M + s] = cscale(q[i], inv);
+}
+
+constexpr int TPB_WARPS = 4;
+template <int M>
+__host__ __device__ constexpr size_t tpb_warp_smem() { return 2 * (size_t)oiva_tri(M) * OIVA_GROUP * sizeof(cplx) + 128; }
+
+// grid: ceil(G / 4) CTAs of 4 warps; warp <-> group gi, lane <-> bin.  Per warp, the group's covariances
+// Cg[gi] and Vg[gi][s] (each ONE contiguous block of NE*32 complex) are staged in shared memory by 1-D bulk
+// TMA: C and V_0 up front, V_{s+1} as soon as the warp is done with V_s (it lands during the J refresh).
+template <int M, int K, bool STAGED>
+__global__ void __launch_bounds__(TPB_WARPS * 32) k_ip_update_tpb(cplx* __restrict__ Wg, const cplx* __restrict__ Vg,
+                                                                  const cplx* __restrict__ Cg,
+                                                                  const double* __restrict__ wscale, int* status,
+                                                                  int F, int NG, long long G) {
     constexpr int NE = oiva_tri(M);
-    const long long gi = ((long long)blockIdx.x * 128 + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (gi >= G) return;
+    constexpr uint32_t MAT_BYTES = NE * OIVA_GROUP * sizeof(cplx);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long gi = (long long)blockIdx.x * TPB_WARPS + warp;
+    if (gi >= G) return;  // whole warp
+    unsigned char* wsm = smem_raw + (size_t)warp * tpb_warp_smem<M>();
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm);  // [0]: C landed, [1]: V_s landed
     const long long b = gi / NG;
     const int f = (int)(gi - b * NG) * OIVA_GROUP + lane;
-    if (f >= F) return;
-    cplx* Wm = What + ((size_t)b * F + f) * M * M;  // this bin's W_hat, row-major (read back after writes: no __ldg)
-    const cplx* Vb = Vg + (size_t)gi * K * NE * OIVA_GROUP + lane;
-    const cplx* Cb = Cg + (size_t)gi * NE * OIVA_GROUP + lane;
+    const bool valid = f < F;  // padded lanes of the last group only take part in the barriers
+    const WLane Wm = {Wg + (size_t)gi * M * M * OIVA_GROUP + lane};  // this bin's W_hat (padded lanes: zeros, unused)
+    const cplx* Vgrp = Vg + (size_t)gi * K * NE * OIVA_GROUP;
+    // STAGED: covariances read from the warp's shared-memory copies; otherwise straight from global memory
+    const cplx* sC = STAGED ? reinterpret_cast<const cplx*>(wsm + 128) + lane : Cg + (size_t)gi * NE * OIVA_GROUP + lane;
+    const cplx* sV = reinterpret_cast<const cplx*>(wsm + 128 + MAT_BYTES) + lane;
+
+    if (STAGED && lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+        mbar_arrive_expect_tx(&bars[0], MAT_BYTES);
+        tma_load_1d(wsm + 128, Cg + (size_t)gi * NE * OIVA_GROUP, MAT_BYTES, &bars[0]);
+        mbar_arrive_expect_tx(&bars[1], MAT_BYTES);
+        tma_load_1d(wsm + 128 + MAT_BYTES, Vgrp, MAT_BYTES, &bars[1]);
+    }
+    __syncwarp();
     bool singular = false;
 
-    if (wscale) {  // W /= gamma (laplace) or sqrt(gamma) (gauss)                       overiva.py:161-167
+    if (valid && wscale) {  // W /= gamma (laplace) or sqrt(gamma) (gauss)              overiva.py:161-167
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const double sc = wscale[b * K + k];
@@ -144,63 +331,36 @@ __global__ void __launch_bounds__(128) k_ip_update_tpb(cplx* __restrict__ What, 
 
 #pragma unroll 1
     for (int s = 0; s < K; ++s) {
-        const cplx* Vs = Vb + (size_t)s * NE * OIVA_GROUP;
-        // A = W_hat^H V_s, rhs = e_s
-        cplx A[M][M], rhs[M][1];
-#pragma unroll
-        for (int i = 0; i < M; ++i) {
-#pragma unroll
-            for (int c = 0; c < M; ++c) A[i][c] = cmake(0.0, 0.0);
-            rhs[i][0] = cmake(i == s ? 1.0 : 0.0, 0.0);
-        }
-#pragma unroll
-        for (int j = 0; j < M; ++j) {
-            cplx vrow[M];
-#pragma unroll
-            for (int c = 0; c < M; ++c) vrow[c] = herm_load(Vs, j, c);
-            if (j < K) {
-                // rows i < K: conj(W[j][i]);  rows i >= K: conj(J[j][i-K]) -- both are W_hat[j][i]
-#pragma unroll
-                for (int i = 0; i < M; ++i) {
-                    const cplx a = Wm[j * M + i];
-#pragma unroll
-                    for (int c = 0; c < M; ++c) cfmac(A[i][c], a, vrow[c]);
-                }
+        if (STAGED) mbar_wait(&bars[1], s & 1);
+        else sV = Vgrp + (size_t)s * NE * OIVA_GROUP + lane;
+        if (valid) {
+            if constexpr (K < M) {
+                ip_source_reduced<M, K, STAGED>(Wm, sV, s, singular);
             } else {
-                // W_hat[j][i] for j >= K: W[j][i] for i < K, -delta(i, j) otherwise
-#pragma unroll
-                for (int i = 0; i < K; ++i) {
-                    const cplx a = Wm[j * M + i];
-#pragma unroll
-                    for (int c = 0; c < M; ++c) cfmac(A[i][c], a, vrow[c]);
-                }
-#pragma unroll
-                for (int c = 0; c < M; ++c) A[j][c] = csub(A[j][c], vrow[c]);
+                ip_source_full<M, STAGED>(Wm, sV, s, singular);
             }
         }
-        lu_solve<M, 1>(A, rhs, singular);
-        // normalise: w /= sqrt(w^H V_s w)                                               overiva.py:185-186
-        cplx d = cmake(0.0, 0.0);
-#pragma unroll
-        for (int i = 0; i < M; ++i) {
-            cplx u = cmake(0.0, 0.0);
-#pragma unroll
-            for (int j = 0; j < M; ++j) cfma(u, herm_load(Vs, i, j), rhs[j][0]);
-            cfmac(d, rhs[i][0], u);
+        __syncwarp();  // every lane is done reading V_s: its buffer may be refilled
+        if (STAGED && lane == 0 && s + 1 < K) {
+            mbar_arrive_expect_tx(&bars[1], MAT_BYTES);
+            tma_load_1d(wsm + 128 + MAT_BYTES, Vgrp + (size_t)(s + 1) * NE * OIVA_GROUP, MAT_BYTES, &bars[1]);
         }
-        const cplx inv = crecip(csqrt_(d));
-#pragma unroll
-        for (int i = 0; i < M; ++i) Wm[i * M + s] = cmul(rhs[i][0], inv);
-        background_tpb<M, K>(Wm, Cb, singular);
+        if (K < M) {
+            if (STAGED && s == 0) mbar_wait(&bars[0], 0);
+            if (valid) background_tpb<M, K, STAGED>(Wm, sC, singular);
+        }
     }
 
-    bool bad = false;
+    if (valid) {
+        bool bad = false;
 #pragma unroll
-    for (int i = 0; i < M * M; ++i) {
-        const cplx v = Wm[i];
-        if (!isfinite(v.x) || !isfinite(v.y)) bad = true;
+        for (int i = 0; i < M * M; ++i) {
+            const cplx v = Wm[i];
+            if (!isfinite(v.x) || !isfinite(v.y)) bad = true;
+        }
+        if (singular || bad)
+            atomicOr(status, (singular ? OIVA_STATUS_SINGULAR : 0) | (bad ? OIVA_STATUS_NONFINITE : 0));
     }
-    if (singular || bad) atomicOr(status, (singular ? OIVA_STATUS_SINGULAR : 0) | (bad ? OIVA_STATUS_NONFINITE : 0));
 }
 
 }  // namespace oiva

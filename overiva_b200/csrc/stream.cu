@@ -94,26 +94,28 @@ static int check_dims(const char* who, int B, int T, int F, int M, int K) {
     return OIVA_OK;
 }
 
-static StreamParams make_params(const void* Xg, const void* W, int w_cols, int T, int F, int M, int K) {
+static StreamParams make_params(const void* Xg, const void* W, int w_cols, int T, int F, int M, int K,
+                                int w_grouped = 0) {
     StreamParams p = {};
     p.Xg = Xg;
     p.W = (const cplx*)W;
     p.w_row = (long long)M * w_cols;
     p.w_c = w_cols;
+    p.w_grouped = w_grouped;
     p.L = oiva_make_layout(T, F, M);
     p.K = K;
     p.nsplit = 1;
     return p;
 }
 
-extern "C" int oiva_demix_power(const void* Xg, const void* W, int w_cols, double* r2part, int n_batch, int n_frames,
-                                int n_freq, int n_chan, int n_src, int dtype, void* stream) {
+extern "C" int oiva_demix_power(const void* Xg, const void* W, int w_cols, int w_grouped, double* r2part, int n_batch,
+                                int n_frames, int n_freq, int n_chan, int n_src, int dtype, void* stream) {
     OIVA_REQUIRE(Xg && W && r2part, "oiva_demix_power: null pointer");
     OIVA_REQUIRE(w_cols >= n_src, "oiva_demix_power: w_cols %d < n_src %d", w_cols, n_src);
     int rc = check_dims("oiva_demix_power", n_batch, n_frames, n_freq, n_chan, n_src);
     if (rc) return rc;
     OIVA_REQUIRE(n_src <= n_chan, "oiva_demix_power: n_src > n_chan");
-    StreamParams p = make_params(Xg, W, w_cols, n_frames, n_freq, n_chan, n_src);
+    StreamParams p = make_params(Xg, W, w_cols, n_frames, n_freq, n_chan, n_src, w_grouped);
     p.r2part = r2part;
     return stream_launch(n_chan, KIND_POWER, dtype, p, (long long)n_batch * p.L.NG, (cudaStream_t)stream);
 }

@@ -17,9 +17,10 @@ constexpr int POWER_FB = 8;  // frames reduced together in the power kernel
 
 struct StreamParams {
     const void* Xg;
-    const cplx* W;   // filters: element (row, c, k) at W[row*w_row + c*w_c + k], row = b*F + f
-    long long w_row;
+    const cplx* W;   // filters: element (c, k) of bin (b, f): row-major W[(b*F+f)*w_row + c*w_c + k], or, when
+    long long w_row; //          w_grouped, W[((gi*w_row) + c*w_c + k)*32 + lane]  (w_row = M * w_c in both cases)
     int w_c;
+    int w_grouped;
     GroupLayout L;
     int K;
     int nsplit;       // frame splits per group (grid.y)
@@ -30,14 +31,16 @@ struct StreamParams {
 
 // this lane's demixing vectors: w[c][k] for KC sources starting at k0 (zero beyond K / beyond F)
 template <int M, int KC>
-__device__ __forceinline__ void load_filters(cplx (&w)[M][KC], const StreamParams& p, long long row, bool bin_ok,
-                                             int k0) {
+__device__ __forceinline__ void load_filters(cplx (&w)[M][KC], const StreamParams& p, long long row, long long gi,
+                                             int lane, bool bin_ok, int k0) {
+    const cplx* base = p.w_grouped ? p.W + (size_t)gi * p.w_row * OIVA_GROUP + lane : p.W + row * p.w_row;
+    const int es = p.w_grouped ? OIVA_GROUP : 1;
 #pragma unroll
     for (int c = 0; c < M; ++c)
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
             w[c][k] = cmake(0.0, 0.0);
-            if (bin_ok && k0 + k < p.K) w[c][k] = ld_nc_c(p.W + row * p.w_row + (size_t)c * p.w_c + k0 + k);
+            if (bin_ok && k0 + k < p.K) w[c][k] = ld_nc_c(base + ((size_t)c * p.w_c + k0 + k) * es);
         }
 }
 
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(512) k_demix_power(const StreamParams p) {
     const int k0 = warp * KC;
     const int Tp = L.frame_pitch();
     cplx w[M][KC];
-    load_filters<M, KC>(w, p, b * L.F + (bin_ok ? f : 0), bin_ok, k0);
+    load_filters<M, KC>(w, p, b * L.F + (bin_ok ? f : 0), gi, lane, bin_ok, k0);
     const XC* xg = reinterpret_cast<const XC*>(p.Xg) + (size_t)gi * L.group_elems();
     const int nblk = Tp / POWER_FB;  // blocks over the padded frame range: the padding is written as zeros
     const int blk0 = (int)((long long)nblk * blockIdx.y / p.nsplit);
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(512) k_demix_output(const StreamParams p) {
     const bool bin_ok = f < L.F;
     const int k0 = warp * KC;
     cplx w[M][KC];
-    load_filters<M, KC>(w, p, b * L.F + (bin_ok ? f : 0), bin_ok, k0);
+    load_filters<M, KC>(w, p, b * L.F + (bin_ok ? f : 0), gi, lane, bin_ok, k0);
     const XC* xg = reinterpret_cast<const XC*>(p.Xg) + (size_t)gi * L.group_elems();
     XC* Y = reinterpret_cast<XC*>(p.Y);
     const int t_begin = (int)((long long)L.T * blockIdx.y / p.nsplit);
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(512) k_project_rows(const StreamParams p) {
     const bool bin_ok = f < L.F;
     const int k0 = warp * KC;
     cplx w[M][KC];
-    load_filters<M, KC>(w, p, b * L.F + (bin_ok ? f : 0), bin_ok, k0);
+    load_filters<M, KC>(w, p, b * L.F + (bin_ok ? f : 0), gi, lane, bin_ok, k0);
     const XC* xg = reinterpret_cast<const XC*>(p.Xg) + (size_t)gi * L.group_elems();
     XC* xr = reinterpret_cast<XC*>(p.Xr) + (size_t)gi * L.T * p.K * OIVA_GROUP;
     const int t_begin = (int)((long long)L.T * blockIdx.y / p.nsplit);

@@ -118,3 +118,43 @@ extern "C" int oiva_unpack_cov(const void* Vg, void* V, int n_batch, int n_freq,
     OIVA_LAUNCH_CHECK();
     return OIVA_OK;
 }
+
+// ---- per-bin matrices: row-major (R, n) <-> grouped [gi][n][32] -------------------------------------
+// The loop keeps the demixing matrices in the grouped form (lane <-> bin: a warp access to one matrix element of
+// 32 consecutive bins is one 512-byte segment instead of 32 scattered 16-byte words).
+__global__ void k_regroup_rows(const cplx* __restrict__ src, cplx* __restrict__ dst, int F, int NG, int n, long long G,
+                               int to_grouped) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over (gi, e, l)
+    if (idx >= G * n * OIVA_GROUP) return;
+    const int l = (int)(idx % OIVA_GROUP);
+    const int e = (int)((idx / OIVA_GROUP) % n);
+    const long long gi = idx / ((long long)OIVA_GROUP * n);
+    const long long b = gi / NG;
+    const int f = (int)(gi - b * NG) * OIVA_GROUP + l;
+    if (to_grouped) {
+        cplx v = make_double2(0.0, 0.0);
+        if (f < F) v = src[((size_t)b * F + f) * n + e];
+        dst[idx] = v;
+    } else if (f < F) {
+        dst[((size_t)b * F + f) * n + e] = src[idx];
+    }
+}
+
+static int regroup(const void* src, void* dst, int n_batch, int n_freq, int n, int to_grouped, void* stream) {
+    OIVA_REQUIRE(src && dst, "oiva_(un)group_rows: null pointer");
+    OIVA_REQUIRE(n_batch > 0 && n_freq > 0 && n > 0, "oiva_(un)group_rows: bad shape");
+    const int NG = oiva_bin_groups(n_freq);
+    const long long G = (long long)n_batch * NG;
+    const long long total = G * n * OIVA_GROUP;
+    k_regroup_rows<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const cplx*)src, (cplx*)dst, n_freq,
+                                                                                       NG, n, G, to_grouped);
+    OIVA_LAUNCH_CHECK();
+    return OIVA_OK;
+}
+
+extern "C" int oiva_group_rows(const void* rows, void* grouped, int n_batch, int n_freq, int n_elems, void* stream) {
+    return regroup(rows, grouped, n_batch, n_freq, n_elems, 1, stream);
+}
+extern "C" int oiva_ungroup_rows(const void* grouped, void* rows, int n_batch, int n_freq, int n_elems, void* stream) {
+    return regroup(grouped, rows, n_batch, n_freq, n_elems, 0, stream);
+}

@@ -91,7 +91,7 @@ def demix_power(Xg, W, B, T, F, M, K, code):
     nch = lib.oiva_bin_groups(F)
     Wd = to_dev(W.astype(np.complex128))
     part = torch.full((B, nch, K, Tp), np.nan, dtype=torch.float64, device=dev())
-    L.check(lib.oiva_demix_power(P(Xg), P(Wd), W.shape[-1], P(part), B, T, F, M, K, code, stream()),
+    L.check(lib.oiva_demix_power(P(Xg), P(Wd), W.shape[-1], 0, P(part), B, T, F, M, K, code, stream()),
             "oiva_demix_power")
     r2 = torch.empty((B, K, Tp), dtype=torch.float64, device=dev())
     L.check(lib.oiva_sum_partials(P(part), nch, P(r2), B, T, K, stream()), "oiva_sum_partials")
@@ -124,7 +124,12 @@ def ip_update(What, V, Cx, wscale, K, grouped_c=True):
     Cgd = pack_cov(Cx[:, :, None]) if grouped_c else None
     wsd = to_dev(wscale) if wscale is not None else None
     st = torch.zeros(4, dtype=torch.int32, device=dev())
-    L.check(lib.oiva_ip_update(P(Wd), P(Vgd), P(Cd), P(Cgd), P(wsd), P(st), B, F, M, K, stream()), "oiva_ip_update")
+    NG = lib.oiva_bin_groups(F)
+    Wg = torch.empty((B * NG, M * M, 32), dtype=torch.complex128, device=dev())
+    L.check(lib.oiva_group_rows(P(Wd), P(Wg), B, F, M * M, stream()), "oiva_group_rows")
+    L.check(lib.oiva_ip_update(P(Wg), P(Vgd), P(Cd), P(Cgd), P(wsd), P(st), B, F, M, K, stream()), "oiva_ip_update")
+    Wd.fill_(float("nan"))
+    L.check(lib.oiva_ungroup_rows(P(Wg), P(Wd), B, F, M * M, stream()), "oiva_ungroup_rows")
     torch.cuda.synchronize()
     return Wd.cpu().numpy(), int(st[0].item())
 
