@@ -124,6 +124,16 @@ int oiva_source_model(const double* r2part, int n_chunks, double* phi, double* w
 int oiva_ip_update(void* Wg, const void* Vg, const void* C, const void* Cg, const double* wscale, int* status,
                    int n_batch, int n_freq, int n_chan, int n_src, void* stream);
 
+/* Fused variant for M <= 6, K <= 4 (oiva_ip_update_power_supported): the same sweep (thread per bin), and then, with
+ * the fresh filters still in registers, the statistic of the NEXT epoch r2part (B,NG,K,Tp) from Xg -- per bin group
+ * the sweep of epoch i and the demix-power pass of epoch i+1 only depend on each other, so one warp does both and
+ * the sweep's latency hides behind the streaming of the other warps.
+ * replaces: overiva.py:161-167,176-190 followed by overiva.py:140,152-155 of the following epoch. */
+int oiva_ip_update_power(void* Wg, const void* Vg, const void* Cg, const double* wscale, int* status,
+                         const void* Xg, double* r2part, int n_batch, int n_frames, int n_freq, int n_chan,
+                         int n_src, int dtype, void* stream);
+int oiva_ip_update_power_supported(int n_chan, int n_src);
+
 /* Build What (R,M,M): W from eye / eigenvectors / W0, then J and the -I block.
  * evecs: (R,M,M) from oiva_eigh (ascending; used when mode == OIVA_INIT_EIG: w_k = conj(v_{M-K+k})).
  * W0: (R,M,K) c128 (mode == OIVA_INIT_W0).                    replaces: overiva.py:89-123 */

@@ -51,6 +51,8 @@ SIGNATURES = {
     "oiva_sum_partials": (_i, [_p, _i, _p, _i, _i, _i, _p]),
     "oiva_source_model": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
     "oiva_ip_update": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "oiva_ip_update_power": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "oiva_ip_update_power_supported": (_i, [_i, _i]),
     "oiva_init_demix": (_i, [_p, _p, _p, _p, _i, _p, _i, _i, _i, _p]),
     "oiva_eigh": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "oiva_projback_filters": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _p]),

@@ -28,6 +28,7 @@ struct oiva_plan {
     unsigned char* ws;
     long long launches;
     bool loaded, inited;
+    bool r2_valid;  // r2part holds the statistic of the CURRENT demixing matrices (left by the fused kernel)
     bool timing;
     std::vector<TimedSpan>* spans;
     std::vector<cudaEvent_t>* pool;
@@ -242,6 +243,7 @@ extern "C" int oiva_plan_init(oiva_plan_t* p, int mode, const void* W0, void* st
     if (rc) return rc;
     p->launches += 2;
     p->inited = true;
+    p->r2_valid = false;
     return OIVA_OK;
 }
 
@@ -264,7 +266,20 @@ static int plan_power_partials(oiva_plan_t* p, void* stream) {
     return OIVA_OK;
 }
 
-static int plan_update_from(oiva_plan_t* p, const double* r2src, int nch, void* stream) {
+// The fused IP sweep + next-epoch statistic kernel (fused.cuh) is OPT-IN (OIVA_FUSE=1): measured on B200 at the
+// bench shape it is ~7 % slower than the two separate kernels (2.60 ms vs 1.88 + 0.53 ms per epoch: with one warp
+// per bin group and ~140 registers the streaming phase has less memory parallelism than the dedicated power
+// kernel, and the sweep's latency is already cheap).  Kept because it removes a launch and a W_hat round trip,
+// which matters for latency-bound shapes; needs enough bin groups to fill the GPU with one warp per group.
+static bool plan_can_fuse(const oiva_plan_t* p) {
+    static const bool enabled = [] {
+        const char* v = getenv("OIVA_FUSE");
+        return v && *v && *v != '0';
+    }();
+    return enabled && oiva_ip_update_power_supported(p->d.n_chan, p->d.n_src) && p->G >= 1184;
+}
+
+static int plan_update_from(oiva_plan_t* p, const double* r2src, int nch, void* stream, bool fuse_next_power = false) {
     const oiva_plan_desc& d = p->d;
     double* phi = (double*)(p->ws + p->off_phi);
     double* wscale = (double*)(p->ws + p->off_wscale);
@@ -279,10 +294,17 @@ static int plan_update_from(oiva_plan_t* p, const double* r2src, int nch, void* 
     if (rc) return rc;
     {
         SpanGuard g(p, TK_SOLVE, stream);
-        rc = oiva_ip_update(p->ws + p->off_wg, p->ws + p->off_vg, p->ws + p->off_c, p->ws + p->off_cg, wscale,
-                            (int*)(p->ws + p->off_status), d.n_batch, d.n_freq, d.n_chan, d.n_src, stream);
+        if (fuse_next_power)
+            rc = oiva_ip_update_power(p->ws + p->off_wg, p->ws + p->off_vg, p->ws + p->off_cg, wscale,
+                                      (int*)(p->ws + p->off_status), p->ws + p->off_xg,
+                                      (double*)(p->ws + p->off_r2part), d.n_batch, d.n_frames, d.n_freq, d.n_chan,
+                                      d.n_src, d.dtype, stream);
+        else
+            rc = oiva_ip_update(p->ws + p->off_wg, p->ws + p->off_vg, p->ws + p->off_c, p->ws + p->off_cg, wscale,
+                                (int*)(p->ws + p->off_status), d.n_batch, d.n_freq, d.n_chan, d.n_src, stream);
     }
     if (rc) return rc;
+    p->r2_valid = fuse_next_power;
     p->launches += 3;
     return OIVA_OK;
 }
@@ -296,10 +318,15 @@ static int plan_update_from(oiva_plan_t* p, const double* r2src, int nch, void* 
 
 extern "C" int oiva_plan_iterate(oiva_plan_t* p, int n_iter, void* stream) {
     PLAN_INITED(p, "oiva_plan_iterate");
+    const bool fuse = plan_can_fuse(p);
     for (int it = 0; it < n_iter; ++it) {
-        int rc = plan_power_partials(p, stream);
-        if (rc) return rc;
-        rc = plan_update_from(p, (const double*)(p->ws + p->off_r2part), p->NG, stream);
+        int rc = OIVA_OK;
+        if (!p->r2_valid) {
+            rc = plan_power_partials(p, stream);
+            if (rc) return rc;
+        }
+        // all but the last epoch of this call leave the next epoch's statistic behind (solve + power fused)
+        rc = plan_update_from(p, (const double*)(p->ws + p->off_r2part), p->NG, stream, fuse && it + 1 < n_iter);
         if (rc) return rc;
     }
     return OIVA_OK;
@@ -307,6 +334,7 @@ extern "C" int oiva_plan_iterate(oiva_plan_t* p, int n_iter, void* stream) {
 
 extern "C" int oiva_plan_power(oiva_plan_t* p, void* stream) {
     PLAN_INITED(p, "oiva_plan_power");
+    p->r2_valid = false;
     int rc = plan_power_partials(p, stream);
     if (rc) return rc;
     rc = oiva_sum_partials((const double*)(p->ws + p->off_r2part), p->NG, (double*)(p->ws + p->off_r2), p->d.n_batch,

@@ -178,3 +178,25 @@ def demix_output(Xg, Weff, B, T, F, M, K, code):
     L.check(lib.oiva_demix_output(P(Xg), P(Wd), P(Y), B, T, F, M, K, code, stream()), "oiva_demix_output")
     torch.cuda.synchronize()
     return Y.cpu().numpy()
+
+
+def ip_update_power(What, V, Cx, wscale, K, Xg, T, code):
+    """fused sweep + next-epoch statistic: returns (What', r2 (B,K,T), status)"""
+    lib = L.load()
+    B, F, M, _ = What.shape
+    Wd, Vgd = to_dev(What), pack_cov(V)
+    Cgd = pack_cov(Cx[:, :, None])
+    wsd = to_dev(wscale) if wscale is not None else None
+    st = torch.zeros(4, dtype=torch.int32, device=dev())
+    NG = lib.oiva_bin_groups(F)
+    Tp = lib.oiva_frame_pitch(T)
+    Wg = torch.empty((B * NG, M * M, 32), dtype=torch.complex128, device=dev())
+    L.check(lib.oiva_group_rows(P(Wd), P(Wg), B, F, M * M, stream()), "oiva_group_rows")
+    part = torch.full((B, NG, K, Tp), np.nan, dtype=torch.float64, device=dev())
+    L.check(lib.oiva_ip_update_power(P(Wg), P(Vgd), P(Cgd), P(wsd), P(st), P(Xg), P(part), B, T, F, M, K, code,
+                                     stream()), "oiva_ip_update_power")
+    L.check(lib.oiva_ungroup_rows(P(Wg), P(Wd), B, F, M * M, stream()), "oiva_ungroup_rows")
+    r2 = torch.empty((B, K, Tp), dtype=torch.float64, device=dev())
+    L.check(lib.oiva_sum_partials(P(part), NG, P(r2), B, T, K, stream()), "oiva_sum_partials")
+    torch.cuda.synchronize()
+    return Wd.cpu().numpy(), r2.cpu().numpy()[:, :, :T], int(st[0].item())

@@ -164,3 +164,16 @@ def test_host_batch_pipeline_equals_device_batch():
     bad[4, :, :, 3] = bad[4, :, :, 0]  # one rank-deficient mixture in the middle chunk
     with pytest.raises(np.linalg.LinAlgError):
         ob.overiva_batch(bad, n_src=2, n_iter=3, chunk=3)
+
+
+def test_large_batch(monkeypatch):
+    """>= 1184 bin groups (no frame splitting anywhere; with OIVA_FUSE=1 the plan would run the fused sweep +
+    next-epoch-statistic kernel, which tests/test_kernels_gpu.py covers directly); results vs the oracle"""
+    B = 37
+    Xs = np.stack([small_test_mixture(600 + b, 4, 2, n_samples=20000, frame=2048, hop=1024) for b in range(B)])
+    assert Xs.shape[2] == 1025 and B * 33 >= 1184
+    Y, W = ob.overiva_batch(torch.from_numpy(Xs).cuda(), n_src=2, n_iter=7, return_filters=True)
+    Y, W = Y.cpu().numpy(), W.cpu().numpy()
+    for b in (0, 17, 36):
+        Yo, Wo = orc.overiva(Xs[b], n_src=2, n_iter=7, return_filters=True)
+        assert rel_err(Y[b], Yo) <= FP64_TOL and rel_err(W[b], Wo) <= FP64_TOL

@@ -219,3 +219,39 @@ def test_final_demix_and_projection_back(M, K, n_samples, dtype, proj_back):
             z = orc.projection_back(want, X128[b][:, :, 0])
             want = want * np.conj(z[None])
         assert rel_err(Y[b], want) < (1e-12 if dtype == np.complex128 else 1e-6)
+
+
+@pytest.mark.parametrize("M,K,dtype", [(4, 2, np.complex128), (6, 2, np.complex128), (6, 4, np.complex128),
+                                        (3, 3, np.complex128), (5, 1, np.complex64), (2, 2, np.complex128)])
+def test_fused_sweep_and_next_statistic(M, K, dtype):
+    """oiva_ip_update_power == oiva_ip_update followed by oiva_demix_power with the updated filters"""
+    B = 2
+    X = _mix(21, M, 1500, 64, dtype, B=B)
+    _, T, F, _ = X.shape
+    X128 = X.astype(np.complex128)
+    rng = np.random.default_rng(22)
+    Whats, Vs, Cs = [], [], []
+    for b in range(B):
+        Cx = orc.input_covariance(X128[b])
+        What = orc.init_demixing(Cx, K)
+        What[:, :, :K] += 0.2 * (rng.standard_normal((F, M, K)) + 1j * rng.standard_normal((F, M, K)))
+        if K < M:
+            orc.background_update(What, Cx, K)
+        Xf = np.ascontiguousarray(X128[b].swapaxes(0, 1))
+        r_inv = rng.gamma(1.0, 1.0, size=(T, K)) + 0.05
+        Vs.append(np.stack([orc.weighted_covariance(Xf, r_inv[:, s]) for s in range(K)], axis=1))
+        Whats.append(What)
+        Cs.append(Cx)
+    What, V, Cx = np.stack(Whats), np.stack(Vs), np.stack(Cs)
+    wscale = rng.uniform(0.5, 2.0, size=(B, K))
+    Xg = G.grouped(X)
+    got_W, got_r2, status = G.ip_update_power(What, V, Cx, wscale, K, Xg, T, G.code_of(dtype))
+    assert status == 0
+    for b in range(B):
+        want = What[b].copy()
+        want[:, :, :K] *= wscale[b][None, None, :]
+        for s in range(K):
+            orc.ip_update_source(want, V[b][:, s], Cx[b], s, K)
+        assert rel_err(got_W[b], want) < 1e-11
+        Xf = np.ascontiguousarray(X128[b].swapaxes(0, 1))
+        assert rel_err(got_r2[b].T, orc.demix_power(Xf, want[:, :, :K])) < 1e-11
