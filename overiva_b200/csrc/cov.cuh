@@ -49,9 +49,10 @@ __host__ __device__ constexpr int cov_nep_max(int M, int KC) {
 __host__ __device__ constexpr int cov_parts(int M, int KC) {
     return (oiva_tri(M) + cov_nep_max(M, KC) - 1) / cov_nep_max(M, KC);
 }
-// frames per stage: ~16 KB of fp64 samples, even
+// frames per stage (even): ~16 KB of fp64 samples for M <= 8 (many single-warp teams per SM), ~32 KB for the
+// blocked many-channel kernel (one big team per SM: fewer, larger hand-offs)
 __host__ __device__ constexpr int cov_chunk_frames(int M) {
-    int tc = 32 / M;
+    int tc = (M <= 8 ? 32 : 64) / M;
     tc &= ~1;
     return tc < 2 ? 2 : (tc > 16 ? 16 : tc);
 }
@@ -76,11 +77,12 @@ struct CovPart {
     typedef typename StoreC<ST>::type XC;
     static constexpr int NE = oiva_tri(M);
     static constexpr int NEP = (NE + P - 1) / P;
+    static constexpr int NACC = NEP;
     static constexpr int TC = cov_chunk_frames(M);
 
     // accumulate `nfr` (<= TC) frames of a staged chunk: xs = [TC][M][32] complex, ph = [KC][TC]
     __device__ static __forceinline__ void accumulate(cplx (&acc)[NEP][KC], const XC* __restrict__ xs,
-                                                      const double* __restrict__ ph, int nfr, int lane) {
+                                                      const double* __restrict__ ph, int nfr, int lane, int) {
 #pragma unroll
         for (int fr = 0; fr < TC; ++fr) {
             if (fr < nfr) {
@@ -116,7 +118,7 @@ struct CovPart {
 
     // write this lane's entries of the group
     __device__ static __forceinline__ void finish(const cplx (&acc)[NEP][KC], cplx* __restrict__ Vgrp /* (K,NE,32) */,
-                                                  int k0, int K, double invT, bool atomic, int lane) {
+                                                  int k0, int K, double invT, bool atomic, int lane, int) {
         static_for<NEP>([&](auto nc) {
             constexpr int n = decltype(nc)::value;
             constexpr int e = PART + n * P;
@@ -143,10 +145,9 @@ struct CovPart {
 // The body run by one warp of a team for its compile-time part.
 // Units of work: (group, frame split); a team owns the contiguous unit range [u_begin, u_end).  All
 // producer / consumer cursors are advanced incrementally (no divisions in the per-chunk path).
-template <typename ST, int M, int KC, int P, int PART, bool USE_TMA>
+template <typename CP, typename ST, int M, int KC, bool USE_TMA>
 __device__ __forceinline__ void cov_team_body(const CovParams& p, unsigned char* team_smem, long long team_global,
-                                              long long n_teams_total, int lane, bool is_leader_warp) {
-    using CP = CovPart<ST, M, KC, P, PART>;
+                                              long long n_teams_total, int lane, bool is_leader_warp, int part) {
     typedef typename CP::XC XC;
     constexpr int TC = CP::TC;
     const GroupLayout& L = p.L;
@@ -220,9 +221,9 @@ __device__ __forceinline__ void cov_team_body(const CovParams& p, unsigned char*
         const int c0 = nsplit == 1 ? 0 : (int)((long long)nchunks * sp / nsplit);
         const int c1 = nsplit == 1 ? nchunks : (int)((long long)nchunks * (sp + 1) / nsplit);
         if (c0 >= c1) continue;
-        cplx acc[CP::NEP][KC];
+        cplx acc[CP::NACC][KC];
 #pragma unroll
-        for (int n = 0; n < CP::NEP; ++n)
+        for (int n = 0; n < CP::NACC; ++n)
 #pragma unroll
             for (int k = 0; k < KC; ++k) acc[n][k] = cmake(0.0, 0.0);
         for (int c = c0; c < c1; ++c) {
@@ -232,7 +233,7 @@ __device__ __forceinline__ void cov_team_body(const CovParams& p, unsigned char*
                 mbar_wait(&full[cstage], cphase);
                 const unsigned char* src = stage0 + (size_t)cstage * stage_bytes;
                 CP::accumulate(acc, reinterpret_cast<const XC*>(src), reinterpret_cast<const double*>(src + x_stage), nfr,
-                               lane);
+                               lane, part);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[cstage]);
                 if (++cstage == S) {
@@ -250,10 +251,10 @@ __device__ __forceinline__ void cov_team_body(const CovParams& p, unsigned char*
                     for (int fr = 0; fr < TC; ++fr)
                         phl[k * TC + fr] =
                             fr < nfr ? p.phi[((size_t)b * p.K + min(p.k0 + k, p.K - 1)) * Tp + t0 + fr] : 0.0;
-                CP::accumulate(acc, Xg + (size_t)gi * group_elems + (size_t)t0 * frame_elems, phl, nfr, lane);
+                CP::accumulate(acc, Xg + (size_t)gi * group_elems + (size_t)t0 * frame_elems, phl, nfr, lane, part);
             }
         }
-        CP::finish(acc, p.Vg + (size_t)gi * p.K * CP::NE * OIVA_GROUP, p.k0, p.K, p.invT, nsplit > 1, lane);
+        CP::finish(acc, p.Vg + (size_t)gi * p.K * CP::NE * OIVA_GROUP, p.k0, p.K, p.invT, nsplit > 1, lane, part);
     }
 }
 
@@ -262,7 +263,8 @@ struct CovDispatch {
     __device__ static __forceinline__ void run(int part, const CovParams& p, unsigned char* team_smem,
                                                long long team_global, long long n_teams_total, int lane) {
         if (part == PART)
-            cov_team_body<ST, M, KC, P, PART, USE_TMA>(p, team_smem, team_global, n_teams_total, lane, PART == 0);
+            cov_team_body<CovPart<ST, M, KC, P, PART>, ST, M, KC, USE_TMA>(p, team_smem, team_global, n_teams_total, lane,
+                                                                          PART == 0, PART);
         else if constexpr (PART + 1 < P)
             CovDispatch<ST, M, KC, P, USE_TMA, PART + 1>::run(part, p, team_smem, team_global, n_teams_total, lane);
     }
@@ -289,6 +291,117 @@ __global__ void __launch_bounds__(cov_threads(P)) k_cov(const CovParams p, int t
     }
     CovDispatch<ST, M, KC, P, USE_TMA>::run(part, p, team_smem, (long long)blockIdx.x * teams_per_cta + team,
                                             (long long)gridDim.x * teams_per_cta, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Block-partitioned variant for many channels (M >= 9).  With the 1-D "entry e -> part e % P" split above every
+// part is its own unrolled code path; at M = 16 that is 13 paths and the kernel starves on instruction fetch
+// (ncu: stall_no_instruction 30 cycles per issue, 8 % fp64 utilisation).  Here the lower triangle is cut into
+// BT x BT blocks, a warp's block coordinates (bi, bj) are RUNTIME values (only shared-memory addresses depend on
+// them) while the indexing inside a block stays compile-time, so all warps of a team run ONE code path; a block
+// needs 2*BT channel loads for BT*BT entries (classic register tiling).  Diagonal blocks compute the full block
+// and store only i >= j.  KC <= 2 keeps BT*BT*KC complex accumulators in registers; more sources = more passes.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int COV_BT = 4;
+__host__ __device__ constexpr int cov_blocks_per_dim(int M) { return (M + COV_BT - 1) / COV_BT; }
+__host__ __device__ constexpr int cov_block_parts(int M) { return cov_blocks_per_dim(M) * (cov_blocks_per_dim(M) + 1) / 2; }
+
+template <typename ST, int M, int KC>
+struct CovBlock {
+    typedef typename StoreC<ST>::type XC;
+    static constexpr int NE = oiva_tri(M);
+    static constexpr int NACC = COV_BT * COV_BT;
+    static constexpr int TC = cov_chunk_frames(M);
+
+    __device__ static __forceinline__ void coords(int part, int& bi, int& bj) {
+        bi = 0;
+        while ((bi + 1) * (bi + 2) / 2 <= part) ++bi;
+        bj = part - bi * (bi + 1) / 2;
+    }
+
+    __device__ static __forceinline__ void accumulate(cplx (&acc)[NACC][KC], const XC* __restrict__ xs,
+                                                      const double* __restrict__ ph, int nfr, int lane, int part) {
+        int bi, bj;
+        coords(part, bi, bj);
+        const XC* xi0 = xs + (size_t)(bi * COV_BT) * OIVA_GROUP + lane;
+        const XC* xj0 = xs + (size_t)(bj * COV_BT) * OIVA_GROUP + lane;
+#pragma unroll
+        for (int fr = 0; fr < TC; ++fr) {
+            if (fr < nfr) {
+                cplx xi[COV_BT], xj[COV_BT];
+                double w[KC];
+#pragma unroll
+                for (int a = 0; a < COV_BT; ++a) {
+                    // channels beyond M (M not a multiple of BT) contribute zeros
+                    xi[a] = (bi * COV_BT + a < M) ? widen(xi0[(fr * M + a) * OIVA_GROUP]) : cmake(0.0, 0.0);
+                    xj[a] = (bj * COV_BT + a < M) ? widen(xj0[(fr * M + a) * OIVA_GROUP]) : cmake(0.0, 0.0);
+                }
+#pragma unroll
+                for (int k = 0; k < KC; ++k) w[k] = ph[k * TC + fr];
+#pragma unroll
+                for (int a = 0; a < COV_BT; ++a)
+#pragma unroll
+                    for (int b = 0; b < COV_BT; ++b) {
+                        const double pr = fma(xi[a].x, xj[b].x, xi[a].y * xj[b].y);
+                        const double pi = fma(xi[a].y, xj[b].x, -(xi[a].x * xj[b].y));
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) {
+                            acc[a * COV_BT + b][k].x = fma(w[k], pr, acc[a * COV_BT + b][k].x);
+                            acc[a * COV_BT + b][k].y = fma(w[k], pi, acc[a * COV_BT + b][k].y);
+                        }
+                    }
+            }
+        }
+    }
+
+    __device__ static __forceinline__ void finish(const cplx (&acc)[NACC][KC], cplx* __restrict__ Vgrp, int k0, int K,
+                                                  double invT, bool atomic, int lane, int part) {
+        int bi, bj;
+        coords(part, bi, bj);
+#pragma unroll
+        for (int a = 0; a < COV_BT; ++a)
+#pragma unroll
+            for (int b = 0; b < COV_BT; ++b) {
+                const int i = bi * COV_BT + a, j = bj * COV_BT + b;
+                if (i < M && j <= i) {
+                    const int e = i * (i + 1) / 2 + j;
+#pragma unroll
+                    for (int k = 0; k < KC; ++k) {
+                        if (k0 + k < K) {
+                            const cplx v = cmake(acc[a * COV_BT + b][k].x * invT, i == j ? 0.0 : acc[a * COV_BT + b][k].y * invT);
+                            cplx* dst = Vgrp + ((size_t)(k0 + k) * NE + e) * OIVA_GROUP + lane;
+                            if (atomic) {
+                                atomicAdd(&dst->x, v.x);
+                                if (i != j) atomicAdd(&dst->y, v.y);
+                            } else {
+                                *dst = v;
+                            }
+                        }
+                    }
+                }
+            }
+    }
+};
+
+// one team of cov_block_parts(M) warps per CTA
+template <typename ST, int M, int KC, bool USE_TMA>
+__global__ void __launch_bounds__(cov_block_parts(M) * 32) k_cov_blocked(const CovParams p, int team_smem_bytes) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int P = cov_block_parts(M);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (USE_TMA) {
+        if (warp == 0 && lane == 0) {
+            uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+            uint64_t* empty = full + p.stages;
+            for (int s = 0; s < p.stages; ++s) {
+                mbar_init(&full[s], 1);
+                mbar_init(&empty[s], P);
+            }
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
+    cov_team_body<CovBlock<ST, M, KC>, ST, M, KC, USE_TMA>(p, smem_raw, blockIdx.x, gridDim.x, lane, warp == 0, warp);
 }
 
 }  // namespace oiva

@@ -1,5 +1,7 @@
 // Instantiates the covariance kernels for ONE channel count (compiled once per M with -DOIVA_COV_M=<M>,
-// so the 16 channel counts build in parallel).  See cov.cuh for the kernel, cov.cu for the C entry point.
+// so the 16 channel counts build in parallel).  See cov.cuh for the kernels, cov.cu for the C entry point.
+//   M <= 8 : k_cov          -- 1-D split of the lower triangle over P compile-time parts (P = 1 for the bench shape)
+//   M >= 9 : k_cov_blocked  -- BT x BT blocks with runtime block coordinates (one code path), source chunks <= 2
 #include <stdlib.h>
 
 #include "cov.cuh"
@@ -16,76 +18,99 @@ static int env_int(const char* name, int dflt) {
 }
 
 constexpr int COV_MAX_PARTS = 16;
+constexpr bool COV_USE_BLOCKS = OIVA_COV_M >= 9;
+
+// shared launch logic: ring sizing, persistent grid, frame splitting for few groups
+template <typename Kern, typename Launch>
+static int launch_common(Kern kern, CovParams p, cudaStream_t st, int P, int teams_max, size_t stage_bytes, int TC,
+                         int M, int KC, bool tma, bool& attr_done, Launch do_launch) {
+    int dev = 0, sms = 148;
+    OIVA_CUDA_CHECK(cudaGetDevice(&dev));
+    OIVA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int teams = env_int("OIVA_COV_TEAMS", teams_max);
+    if (teams > teams_max) teams = teams_max;
+    if (teams < 1) teams = 1;
+    // measured on B200 (cfg4 shape): 2 stages x 8 single-warp teams per SM reaches 0.92 of the copy bandwidth,
+    // 3-4 stages x 5 teams 0.70: more resident warps beat a deeper ring (profiles/r01_notes.md)
+    int S = env_int("OIVA_COV_STAGES", teams_max == 1 ? 4 : 2);
+    if (S < 2) S = 2;
+    size_t team_smem = 0, smem = 0;
+    const size_t budget = 200 * 1024;
+    if (tma) {
+        for (;;) {
+            team_smem = 128 * ((2 * S * sizeof(uint64_t) + 127) / 128) + (size_t)S * stage_bytes;
+            if (teams * team_smem <= budget) break;
+            if (S > 3) { --S; continue; }
+            if (teams > 1) { --teams; continue; }
+            if (S > 2) { --S; continue; }
+            oiva_set_error("oiva_weighted_cov: stage of %zu bytes does not fit shared memory", stage_bytes);
+            return OIVA_ERR_INVALID;
+        }
+        smem = teams * team_smem;
+    }
+    p.stages = S;
+    const int threads = teams * P * 32;
+    if (!attr_done) {
+        OIVA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        attr_done = true;
+    }
+    int occ = 1;
+    OIVA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    if (occ < 1) occ = 1;
+    const long long max_ctas = (long long)sms * occ;
+    // few groups: split the frames of a group over several teams (atomic accumulation into zeroed Vg)
+    const int nchunks = (p.L.T + TC - 1) / TC;
+    p.nsplit = 1;
+    if (p.G < 2 * max_ctas * teams && nchunks > 1) {
+        long long want = (2 * max_ctas * teams + p.G - 1) / p.G;
+        p.nsplit = (int)(want < nchunks ? want : nchunks);
+    }
+    if (p.nsplit > 1 && p.k0 == 0)
+        OIVA_CUDA_CHECK(cudaMemsetAsync(p.Vg, 0, (size_t)p.G * p.K * oiva_tri(M) * OIVA_GROUP * sizeof(cplx), st));
+    const long long U = p.G * p.nsplit;
+    long long grid = (U + teams - 1) / teams;
+    if (grid > max_ctas) grid = max_ctas;
+    if (grid < 1) grid = 1;
+    do_launch(p, (unsigned)grid, threads, smem, teams, (int)team_smem);
+    OIVA_LAUNCH_CHECK();
+    (void)KC;
+    return OIVA_OK;
+}
 
 template <typename ST, int KC, bool TMA>
 static int launch(CovParams p, cudaStream_t st) {
     constexpr int M = OIVA_COV_M;
-    constexpr int P = cov_parts(M, KC);
-    // K <= M, so chunks larger than the smallest instantiated value >= M are never requested
-    constexpr int kc_cap = M <= 4 ? M : (M <= 6 ? 6 : 8);
-    if constexpr (P > COV_MAX_PARTS || KC > kc_cap) {
-        oiva_set_error("cov_launch: (M=%d, KC=%d) is not instantiated (%d parts)", M, KC, P);
-        return OIVA_ERR_INVALID;
+    typedef typename StoreC<ST>::type XC;
+    constexpr int TC = cov_chunk_frames(M);
+    constexpr size_t x_stage = (size_t)TC * M * OIVA_GROUP * sizeof(XC);
+    constexpr size_t stage_bytes = ((x_stage + (size_t)KC * TC * sizeof(double) + 127) / 128) * 128;
+    if constexpr (COV_USE_BLOCKS) {
+        if constexpr (KC > 2) {
+            oiva_set_error("cov_launch: blocked kernel (M=%d) takes source chunks of 1 or 2, not %d", M, KC);
+            return OIVA_ERR_INVALID;
+        } else {
+            constexpr int P = cov_block_parts(M);
+            auto kern = k_cov_blocked<ST, M, KC, TMA>;
+            static bool attr_done = false;
+            return launch_common(kern, p, st, P, 1, stage_bytes, TC, M, KC, TMA, attr_done,
+                                 [&](const CovParams& q, unsigned grid, int threads, size_t smem, int, int team_smem) {
+                                     kern<<<grid, threads, smem, st>>>(q, team_smem);
+                                 });
+        }
     } else {
-        typedef typename StoreC<ST>::type XC;
-        constexpr int TC = cov_chunk_frames(M);
-        auto kern = k_cov<ST, M, KC, P, TMA>;
-
-        int dev = 0, sms = 148;
-        OIVA_CUDA_CHECK(cudaGetDevice(&dev));
-        OIVA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-
-        constexpr size_t x_stage = (size_t)TC * M * OIVA_GROUP * sizeof(XC);
-        constexpr size_t stage_bytes = ((x_stage + (size_t)KC * TC * sizeof(double) + 127) / 128) * 128;
-        int teams = env_int("OIVA_COV_TEAMS", cov_teams_per_cta(P));
-        if (teams > cov_teams_per_cta(P)) teams = cov_teams_per_cta(P);
-        if (teams < 1) teams = 1;
-        // measured on B200 (cfg4 shape): 2 stages x 8 single-warp teams per SM reaches 0.90 of the copy bandwidth,
-        // 3-4 stages x 5 teams 0.70: more resident warps beat a deeper ring (profiles/r01_notes.md)
-        int S = env_int("OIVA_COV_STAGES", 2);
-        if (S < 2) S = 2;
-        size_t team_smem = 0, smem = 0;
-        const size_t budget = 200 * 1024;
-        if (TMA) {
-            for (;;) {
-                team_smem = 128 * ((2 * S * sizeof(uint64_t) + 127) / 128) + (size_t)S * stage_bytes;
-                if (teams * team_smem <= budget) break;
-                if (S > 3) { --S; continue; }
-                if (teams > 1) { --teams; continue; }
-                if (S > 2) { --S; continue; }
-                oiva_set_error("oiva_weighted_cov: stage of %zu bytes does not fit shared memory", stage_bytes);
-                return OIVA_ERR_INVALID;
-            }
-            smem = teams * team_smem;
+        constexpr int P = cov_parts(M, KC);
+        // K <= M, so chunks larger than the smallest instantiated value >= M are never requested
+        constexpr int kc_cap = M <= 4 ? M : (M <= 6 ? 6 : 8);
+        if constexpr (P > COV_MAX_PARTS || KC > kc_cap) {
+            oiva_set_error("cov_launch: (M=%d, KC=%d) is not instantiated (%d parts)", M, KC, P);
+            return OIVA_ERR_INVALID;
+        } else {
+            auto kern = k_cov<ST, M, KC, P, TMA>;
+            static bool attr_done = false;
+            return launch_common(kern, p, st, P, cov_teams_per_cta(P), stage_bytes, TC, M, KC, TMA, attr_done,
+                                 [&](const CovParams& q, unsigned grid, int threads, size_t smem, int teams,
+                                     int team_smem) { kern<<<grid, threads, smem, st>>>(q, teams, team_smem); });
         }
-        p.stages = S;
-        const int threads = teams * P * 32;
-
-        static bool attr_done = false;  // per instantiation
-        if (!attr_done) {
-            OIVA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-            attr_done = true;
-        }
-        int occ = 1;
-        OIVA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
-        if (occ < 1) occ = 1;
-        const long long max_ctas = (long long)sms * occ;
-        // few groups: split the frames of a group over several teams (atomic accumulation into zeroed Vg)
-        const int nchunks = (p.L.T + TC - 1) / TC;
-        p.nsplit = 1;
-        if (p.G < 2 * max_ctas * teams && nchunks > 1) {
-            long long want = (2 * max_ctas * teams + p.G - 1) / p.G;
-            p.nsplit = (int)(want < nchunks ? want : nchunks);
-        }
-        if (p.nsplit > 1 && p.k0 == 0)
-            OIVA_CUDA_CHECK(cudaMemsetAsync(p.Vg, 0, (size_t)p.G * p.K * oiva_tri(M) * OIVA_GROUP * sizeof(cplx), st));
-        const long long U = p.G * p.nsplit;
-        long long grid = (U + teams - 1) / teams;
-        if (grid > max_ctas) grid = max_ctas;
-        if (grid < 1) grid = 1;
-        kern<<<(unsigned)grid, threads, smem, st>>>(p, teams, (int)team_smem);
-        OIVA_LAUNCH_CHECK();
-        return OIVA_OK;
     }
 }
 
@@ -95,6 +120,7 @@ static int launch(CovParams p, cudaStream_t st) {
 // largest usable source chunk for this M (register budget => number of parts)
 int OIVA_CAT(cov_max_kc_m, OIVA_COV_M)() {
     constexpr int M = OIVA_COV_M;
+    if (COV_USE_BLOCKS) return 2;
     int best = 1;
     if (cov_parts(M, 2) <= COV_MAX_PARTS) best = 2;
     if (cov_parts(M, 3) <= COV_MAX_PARTS) best = 3;
@@ -105,7 +131,7 @@ int OIVA_CAT(cov_max_kc_m, OIVA_COV_M)() {
 }
 
 int OIVA_CAT(cov_launch_m, OIVA_COV_M)(int dtype, int KC, int use_tma, const CovParams& p, cudaStream_t st) {
-#define OIVA_COV_CASE(ST_, KC_)                                  \
+#define OIVA_COV_CASE(ST_, KC_) \
     if (KC == KC_) return launch<ST_, KC_, true>(p, st);
     if (!use_tma) {  // debug path, fp64 storage, chunks of 1 or 2 sources only
         if (dtype == OIVA_C128 && KC == 1) return launch<double, 1, false>(p, st);
@@ -116,17 +142,21 @@ int OIVA_CAT(cov_launch_m, OIVA_COV_M)(int dtype, int KC, int use_tma, const Cov
     if (dtype == OIVA_C64) {
         OIVA_COV_CASE(float, 1)
         OIVA_COV_CASE(float, 2)
-        OIVA_COV_CASE(float, 3)
-        OIVA_COV_CASE(float, 4)
-        OIVA_COV_CASE(float, 6)
-        OIVA_COV_CASE(float, 8)
+        if (!COV_USE_BLOCKS) {
+            OIVA_COV_CASE(float, 3)
+            OIVA_COV_CASE(float, 4)
+            OIVA_COV_CASE(float, 6)
+            OIVA_COV_CASE(float, 8)
+        }
     } else {
         OIVA_COV_CASE(double, 1)
         OIVA_COV_CASE(double, 2)
-        OIVA_COV_CASE(double, 3)
-        OIVA_COV_CASE(double, 4)
-        OIVA_COV_CASE(double, 6)
-        OIVA_COV_CASE(double, 8)
+        if (!COV_USE_BLOCKS) {
+            OIVA_COV_CASE(double, 3)
+            OIVA_COV_CASE(double, 4)
+            OIVA_COV_CASE(double, 6)
+            OIVA_COV_CASE(double, 8)
+        }
     }
     oiva_set_error("cov_launch: unsupported source chunk %d", KC);
     return OIVA_ERR_INVALID;
