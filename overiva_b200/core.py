@@ -93,9 +93,13 @@ class DemixPlan:
         with torch.cuda.device(self.device):
             self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         L.check(self.lib.oiva_plan_bind(h, _ptr(self.ws), nbytes), "oiva_plan_bind")
-        off = self.lib.oiva_plan_status_ptr(h) - self.ws.data_ptr()
-        self.ws[off : off + 16].zero_()  # the status word accumulates from here on (see raise_on_failure)
+        self.in_use = False
+        self._status_off = self.lib.oiva_plan_status_ptr(h) - self.ws.data_ptr()
+        self.reset_status()  # the status word accumulates from here on (see raise_on_failure)
         self.Tp = self.lib.oiva_frame_pitch(n_frames)
+
+    def reset_status(self):
+        self.ws[self._status_off : self._status_off + 16].zero_()
 
     def __del__(self):
         h, self.h = getattr(self, "h", None), None
@@ -193,6 +197,51 @@ class DemixPlan:
         return int(self.lib.oiva_plan_launch_count(self.h))
 
 
+# ---- plan cache -------------------------------------------------------------------------------------
+# A plan (workspace + captured CUDA graph of the epoch loop) is reused by later calls of the same shape: for a
+# single short mixture the allocation and the graph capture would otherwise cost more than the separation.
+# Only small plans are kept (default budget 1 GiB, OVERIVA_B200_PLAN_CACHE_MB); a plan in use is never shared.
+_PLAN_CACHE = {}
+_PLAN_CACHE_ORDER = []
+
+
+def _plan_cache_budget():
+    import os
+
+    return int(float(os.environ.get("OVERIVA_B200_PLAN_CACHE_MB", "1024")) * (1 << 20))
+
+
+def _acquire_plan(B, T, F, M, K, model_code, dtype, device, n_freq_total=0):
+    key = (B, T, F, M, K, model_code, dtype, torch.device(device).index, n_freq_total)
+    plan = _PLAN_CACHE.get(key)
+    if plan is not None and not plan.in_use:
+        plan.in_use = True
+        plan.reset_status()
+        _PLAN_CACHE_ORDER.remove(key)
+        _PLAN_CACHE_ORDER.append(key)
+        return plan
+    plan = DemixPlan(B, T, F, M, K, model_code, dtype, device, n_freq_total)
+    plan.in_use = True
+    budget = _plan_cache_budget()
+    if key not in _PLAN_CACHE and plan.ws.numel() <= budget // 2:
+        _PLAN_CACHE[key] = plan
+        _PLAN_CACHE_ORDER.append(key)
+        while sum(_PLAN_CACHE[k].ws.numel() for k in _PLAN_CACHE_ORDER) > budget and len(_PLAN_CACHE_ORDER) > 1:
+            old = _PLAN_CACHE_ORDER.pop(0)
+            del _PLAN_CACHE[old]
+    return plan
+
+
+def _release_plan(plan):
+    plan.in_use = False
+
+
+def clear_plan_cache():
+    """Drop every cached plan (frees their device workspaces)."""
+    _PLAN_CACHE.clear()
+    del _PLAN_CACHE_ORDER[:]
+
+
 def _model_code(model, table=_MODELS):
     try:
         return table[model]
@@ -222,7 +271,15 @@ def _run_overiva(Xd, n_src, n_iter, proj_back, W0, model, init_eig, return_filte
         raise ValueError("n_src=%d must be in 1..n_chan=%d" % (n_src, M))
     if M > 16:
         raise ValueError("at most 16 channels are supported, got %d" % M)
-    plan = DemixPlan(B, T, F, M, n_src, _model_code(model), Xd.dtype, Xd.device, n_freq_total)
+    plan = _acquire_plan(B, T, F, M, n_src, _model_code(model), Xd.dtype, Xd.device, n_freq_total)
+    try:
+        return _run_overiva_on(plan, Xd, n_src, n_iter, proj_back, W0, init_eig, return_filters, callback, cb_wrap)
+    finally:
+        _release_plan(plan)
+
+
+def _run_overiva_on(plan, Xd, n_src, n_iter, proj_back, W0, init_eig, return_filters, callback, cb_wrap):
+    B, T, F, M = Xd.shape
     plan.load(Xd)
     if W0 is not None:
         plan.init(L.INIT_W0, _prepare_W0(W0, B, F, M, n_src, Xd.device))

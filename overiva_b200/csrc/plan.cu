@@ -32,6 +32,10 @@ struct oiva_plan {
     bool timing;
     std::vector<TimedSpan>* spans;
     std::vector<cudaEvent_t>* pool;
+    // the n_iter epochs of oiva_plan_iterate captured once as a CUDA graph (launch-bound shapes: 4 launches/epoch)
+    cudaGraphExec_t graph_exec;
+    int graph_n_iter;
+    long long graph_launches;  // kernel launches one replay stands for
 };
 
 static cudaEvent_t plan_event(oiva_plan* p) {
@@ -129,6 +133,7 @@ extern "C" void oiva_plan_destroy(oiva_plan_t* plan) {
         for (auto e : *plan->pool) cudaEventDestroy(e);
         delete plan->pool;
     }
+    if (plan->graph_exec) cudaGraphExecDestroy(plan->graph_exec);
     free(plan);
 }
 
@@ -162,6 +167,10 @@ extern "C" int oiva_plan_bind(oiva_plan_t* plan, void* workspace, size_t bytes) 
     OIVA_REQUIRE(plan && workspace, "oiva_plan_bind: null pointer");
     OIVA_REQUIRE(bytes >= plan->ws_bytes, "oiva_plan_bind: workspace %zu < %zu bytes", bytes, plan->ws_bytes);
     OIVA_REQUIRE(((uintptr_t)workspace & 255) == 0, "oiva_plan_bind: workspace must be 256-byte aligned");
+    if (plan->graph_exec && plan->ws != (unsigned char*)workspace) {  // captured pointers are stale
+        cudaGraphExecDestroy(plan->graph_exec);
+        plan->graph_exec = nullptr;
+    }
     plan->ws = (unsigned char*)workspace;
     plan->loaded = plan->inited = false;
     return OIVA_OK;
@@ -316,8 +325,7 @@ static int plan_update_from(oiva_plan_t* p, const double* r2src, int nch, void* 
         return OIVA_ERR_STATE;                                                \
     }
 
-extern "C" int oiva_plan_iterate(oiva_plan_t* p, int n_iter, void* stream) {
-    PLAN_INITED(p, "oiva_plan_iterate");
+static int plan_iterate_eager(oiva_plan_t* p, int n_iter, void* stream) {
     const bool fuse = plan_can_fuse(p);
     for (int it = 0; it < n_iter; ++it) {
         int rc = OIVA_OK;
@@ -329,6 +337,59 @@ extern "C" int oiva_plan_iterate(oiva_plan_t* p, int n_iter, void* stream) {
         rc = plan_update_from(p, (const double*)(p->ws + p->off_r2part), p->NG, stream, fuse && it + 1 < n_iter);
         if (rc) return rc;
     }
+    return OIVA_OK;
+}
+
+// Small problems are launch-bound (config 1: ~15 us kernels, 4 per epoch): the whole n_iter loop is captured once
+// per (plan, n_iter) as a CUDA graph and replayed with a single launch.  Large batches (>= 4096 bin groups) run
+// eagerly: their kernels are milliseconds long and the per-kernel event timing of bench.py needs real launches.
+static bool plan_use_graph(const oiva_plan_t* p, int n_iter) {
+    static const bool disabled = [] {
+        const char* v = getenv("OIVA_NO_GRAPH");
+        return v && *v && *v != '0';
+    }();
+    return !disabled && !p->timing && n_iter >= 2 && p->G < 4096 && !p->r2_valid;
+}
+
+extern "C" int oiva_plan_iterate(oiva_plan_t* p, int n_iter, void* stream) {
+    PLAN_INITED(p, "oiva_plan_iterate");
+    if (n_iter <= 0) return OIVA_OK;
+    if (!plan_use_graph(p, n_iter)) return plan_iterate_eager(p, n_iter, stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!p->graph_exec || p->graph_n_iter != n_iter) {
+        if (p->graph_exec) {
+            cudaGraphExecDestroy(p->graph_exec);
+            p->graph_exec = nullptr;
+        }
+        const long long l0 = p->launches;
+        cudaGraph_t graph = nullptr;
+        cudaStream_t cap = nullptr;
+        OIVA_CUDA_CHECK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+        // capture on a private stream: nothing executes, the launchers' one-time attribute / occupancy calls are legal
+        // during capture, and the caller's stream is left untouched if capture fails
+        cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+        int rc = OIVA_OK;
+        if (e == cudaSuccess) {
+            const bool rv = p->r2_valid;
+            rc = plan_iterate_eager(p, n_iter, cap);
+            p->r2_valid = rv;
+            e = cudaStreamEndCapture(cap, &graph);
+        }
+        p->graph_launches = p->launches - l0;
+        p->launches = l0;
+        if (rc == OIVA_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&p->graph_exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        cudaStreamDestroy(cap);
+        if (rc != OIVA_OK || e != cudaSuccess || !p->graph_exec) {
+            cudaGetLastError();  // clear; fall back to eager launches
+            p->graph_exec = nullptr;
+            return plan_iterate_eager(p, n_iter, stream);
+        }
+        p->graph_n_iter = n_iter;
+    }
+    OIVA_CUDA_CHECK(cudaGraphLaunch(p->graph_exec, st));
+    p->launches += p->graph_launches;
+    p->r2_valid = false;
     return OIVA_OK;
 }
 
