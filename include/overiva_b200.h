@@ -182,6 +182,31 @@ int oiva_ogive_switching(const void* a, const void* C, const double* cnorm, uint
                          int n_chan, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * STFT analysis / synthesis on the device (the step either side of the loop in the reference's drivers).
+ * replaces: pra.transform.analysis(mix.T, 4096, 2048, win=win_a)   overiva_oneshot.py:293-295, overiva_sim.py:206-207
+ *           pra.transform.synthesis(Y, 4096, 2048, win=win_s)      overiva_oneshot.py:371-379, overiva_sim.py:213-218
+ * (pyroomacoustics is third-party and absent from the reference tree: X[t] = rfft(win * frame_t), no scaling;
+ * synthesis = overlap-add of win * irfft(Y[t]).)  frame_len: a power of two in 8..8192; F = frame_len/2 + 1.
+ * ---------------------------------------------------------------------------------------------- */
+/* tw (frame_len/2 c128) <- exp(-2 pi i q / frame_len): the table both transforms need */
+int oiva_stft_twiddles(void* tw, int frame_len, void* stream);
+/* frames of length frame_len every hop samples over pad_front zeros + the signal + pad_back zeros */
+int oiva_stft_num_frames(long long n_samples, int frame_len, int hop, long long pad_front, long long pad_back);
+/* x: real audio, sample (b, n, c) at x[b*stride_b + n*stride_n + c*stride_c] (elements; fp64, or fp32 if x_f32);
+ * frame t covers samples t*hop - pad_front + [0, frame_len), samples outside [0, n_samples) read as zero.
+ * win: (frame_len) fp64 or NULL.  out: grouped != 0 -> grouped samples Xg (what oiva_plan_samples() holds, then
+ * oiva_plan_adopt_samples); grouped == 0 -> X (B,T,F,M) interleaved complex.  dtype: storage of out. */
+int oiva_stft_analysis(const void* x, int x_f32, long long stride_b, long long stride_n, long long stride_c,
+                       long long n_samples, long long pad_front, const double* win, const void* tw, void* out,
+                       int grouped, int n_batch, int n_frames, int n_chan, int frame_len, int hop, int dtype,
+                       void* stream);
+/* Y (B,T,F,K) complex -> y (B, (T-1)*hop + frame_len, K) real (fp64, or fp32 if y_f32): overlap-add of
+ * win * irfft(Y[b,t,:,k]) in ascending frame order (deterministic).  scratch: oiva_stft_scratch_bytes() bytes. */
+size_t oiva_stft_scratch_bytes(int n_batch, int n_frames, int n_src, int frame_len);
+int oiva_stft_synthesis(const void* Y, const double* win, const void* tw, void* scratch, void* y, int y_f32,
+                        int n_batch, int n_frames, int n_src, int frame_len, int hop, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Plan: the whole overiva() call on device pointers (what the Python entry points use).
  * The plan owns no device memory: the caller provides one workspace block.
  * ---------------------------------------------------------------------------------------------- */

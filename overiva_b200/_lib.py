@@ -32,7 +32,7 @@ class PlanDesc(C.Structure):
     ]
 
 
-_i, _p, _d, _sz = C.c_int, C.c_void_p, C.c_double, C.c_size_t
+_i, _p, _d, _sz, _ll = C.c_int, C.c_void_p, C.c_double, C.c_size_t, C.c_longlong
 
 # name -> (restype, argtypes); every symbol declared in include/overiva_b200.h
 SIGNATURES = {
@@ -63,6 +63,11 @@ SIGNATURES = {
     "oiva_ogive_setup": (_i, [_p, _p, _p, _p, _i, _i, _p]),
     "oiva_ogive_a_from_w": (_i, [_p, _p, _p, _i, _i, _p]),
     "oiva_ogive_switching": (_i, [_p, _p, _p, _p, _i, _i, _p]),
+    "oiva_stft_twiddles": (_i, [_p, _i, _p]),
+    "oiva_stft_num_frames": (_i, [_ll, _i, _i, _ll, _ll]),
+    "oiva_stft_analysis": (_i, [_p, _i, _ll, _ll, _ll, _ll, _ll, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "oiva_stft_scratch_bytes": (_sz, [_i, _i, _i, _i]),
+    "oiva_stft_synthesis": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "oiva_plan_create": (_i, [C.POINTER(_p), C.POINTER(PlanDesc)]),
     "oiva_plan_destroy": (None, [_p]),
     "oiva_plan_workspace_bytes": (_sz, [_p]),

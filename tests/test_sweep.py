@@ -1,0 +1,123 @@
+"""Batched sweep driver (reference: overiva_sim.py + rrtools).
+
+CPU: argument enumeration / seeds, algorithm selection rules, record schema and result files, with a numpy stand-in
+engine built on the oracle.  GPU: the device engine produces the same records as the stand-in."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import overiva_oracle as orc
+from oracle import stft_oracle as so
+from overiva_b200 import sweep
+
+PARAMS = {
+    "name": "test", "n_repeat": 2, "seed": 7, "n_targets_list": [1, 2, 3], "n_mics_list": [2, 3],
+    "rt60_list": {"0.02": {}}, "sinr_list": [10], "snr": 60, "fs": 8000, "duration": 0.4, "n_interferers": 3,
+    "ref_mic": 0, "monitor_convergence": False, "stft_params": {"framesize": 64},
+    "algorithm_kwargs": {
+        "auxiva_laplace": {"algo": "auxiva", "kwargs": {"n_iter": 5, "proj_back": True, "model": "laplace"}},
+        "overiva_gauss": {"algo": "overiva", "kwargs": {"n_iter": 5, "proj_back": True, "init_eig": False, "model": "gauss"}},
+        "auxiva_pca_laplace": {"algo": "auxiva_pca", "kwargs": {"n_iter": 5, "proj_back": True, "model": "laplace"}},
+        "ogive_laplace": {"algo": "ogive", "kwargs": {"n_iter": 20, "step_size": 0.1, "tol": 1e-3, "update": "demix",
+                                                      "proj_back": True, "model": "laplace", "init_eig": False}},
+        "ilrma": {"algo": "ilrma", "kwargs": {"n_iter": 5}},
+    },
+    "overdet_algos": ["overiva_gauss", "auxiva_pca_laplace", "ogive_laplace"],
+}
+
+
+class OracleEngine:
+    """numpy stand-in for sweep.GpuEngine (same interface), built on the oracle."""
+
+    def __init__(self, framesize):
+        self.L, self.hop = framesize, framesize // 2
+        self.win_a = so.hann(self.L)
+        self.win_s = so.compute_synthesis_window(self.win_a, self.hop)
+
+    def analysis(self, mixes):
+        return np.stack([so.analysis(m, self.L, self.hop, win=self.win_a, pad_front=self.L - self.hop) for m in mixes])
+
+    def synthesis(self, Y):
+        return np.stack([so.synthesis(y, self.L, self.hop, win=self.win_s) for y in Y])
+
+    def run(self, algo, X, n_targets, kwargs):
+        fn = {"auxiva": lambda x: orc.overiva(x, **kwargs), "overiva": lambda x: orc.overiva(x, n_src=n_targets, **kwargs),
+              "auxiva_pca": lambda x: orc.auxiva_pca(x, n_src=n_targets, **kwargs), "ogive": lambda x: orc.ogive(x, **kwargs)}[algo]
+        return np.stack([fn(x) for x in X]), 0.5
+
+
+def test_generate_arguments_follows_the_reference_enumeration():
+    args = sweep.generate_arguments(PARAMS)
+    # targets-major, then mics; underdetermined (3 targets, 2 mics) skipped; n_repeat entries each
+    assert [(a[0], a[1]) for a in args] == [(1, 2)] * 2 + [(1, 3)] * 2 + [(2, 2)] * 2 + [(2, 3)] * 2 + [(3, 3)] * 2
+    assert all(a[2] == "0.02" and a[3] == 10 for a in args)
+    seeds = [a[4] for a in args]
+    assert len(set(seeds)) == len(seeds) and seeds == [a[4] for a in sweep.generate_arguments(PARAMS)]
+    # same draws as the reference's loop: np.random.seed(seed); one draw for the file sampling; then one per case
+    np.random.seed(7)
+    np.random.randint(2**32, dtype=np.uint32)
+    assert seeds[0] == int(np.random.randint(2**32, dtype=np.uint32))
+    state_before = np.random.get_state()[1][:5].tolist()
+    sweep.generate_arguments(PARAMS)
+    assert np.random.get_state()[1][:5].tolist() == state_before  # caller's RNG state restored (overiva_sim.py:390)
+
+
+def test_algorithm_selection_rules():
+    names = lambda n: [a[0] for a in sweep.algorithms_for(PARAMS, n)]
+    assert names(1) == ["auxiva_laplace", "overiva_gauss", "ogive_laplace"]  # no PCA for a single target
+    assert names(2) == ["auxiva_laplace", "overiva_gauss", "auxiva_pca_laplace"]  # OGIVE only for one target
+
+
+def test_sweep_records_and_files(tmp_path):
+    p = dict(PARAMS, n_targets_list=[1, 2], n_repeat=2)
+    seen = []
+    segs = sweep.run(p, str(tmp_path), batch=3, engine=OracleEngine(64), progress=lambda *a: seen.append(a))
+    args = sweep.generate_arguments(p)
+    assert len(segs) == len(args) == 8
+    for seg, a in zip(segs, args):
+        assert [r["algorithm"] for r in seg] == [x[0] for x in sweep.algorithms_for(p, a[0])]
+        for r in seg:
+            assert set(r) == {"algorithm", "n_targets", "n_mics", "rt60", "sinr", "seed", "sdr", "sir", "runtime",
+                              "n_samples"}
+            assert (r["n_targets"], r["n_mics"], r["rt60"], r["sinr"], r["seed"]) == tuple(a)
+            assert len(r["sdr"]) == 2 and len(r["sdr"][0]) == len(r["sdr"][1]) == a[0]
+            assert r["n_samples"] == 3200 and r["runtime"] == 0.5
+            assert np.all(np.isfinite(r["sdr"])) and np.all(np.isfinite(r["sir"]))
+    # initial values are shared by every algorithm of a mixture (overiva_sim.py:285-287)
+    assert segs[0][0]["sdr"][0] == segs[0][1]["sdr"][0]
+    # files in the layout overiva_sim_plot.py:161-190 reads
+    data = json.load(open(os.path.join(tmp_path, "data.json")))
+    records = []
+    for seg in data:
+        records += seg
+    assert len(records) == sum(len(s) for s in segs) and records[0] == segs[0][0]
+    assert json.load(open(os.path.join(tmp_path, "parameters.json")))["fs"] == 8000
+    assert json.load(open(os.path.join(tmp_path, "arguments.json"))) == args
+    rows = sweep.summarise(segs, p["fs"])
+    assert {r["algorithm"] for r in rows} == {"auxiva_laplace", "overiva_gauss", "auxiva_pca_laplace", "ogive_laplace"}
+    assert all(r["runtime_per_s"] == pytest.approx(0.5 / 3200 * 8000) for r in rows)
+    assert seen and seen[0][0] == "auxiva_laplace"
+
+
+def test_separation_improves_sir():
+    p = dict(PARAMS, n_targets_list=[2], n_mics_list=[3], n_repeat=3, duration=1.0,
+             algorithm_kwargs={"overiva_laplace": {"algo": "overiva", "kwargs": {"n_iter": 30, "proj_back": True,
+                                                                                "model": "laplace"}}},
+             overdet_algos=["overiva_laplace"])
+    rows = sweep.summarise(sweep.run(p, engine=OracleEngine(64)), p["fs"])
+    assert rows[0]["sir_improvement"] > 3.0
+
+
+@pytest.mark.gpu
+def test_gpu_engine_matches_the_oracle_engine():
+    p = dict(PARAMS, n_targets_list=[1, 2], n_mics_list=[3], n_repeat=2)
+    ref = sweep.run(p, engine=OracleEngine(64))
+    got = sweep.run(p, batch=2)
+    assert len(got) == len(ref)
+    for sg, sr in zip(got, ref):
+        for rg, rr in zip(sg, sr):
+            assert rg["algorithm"] == rr["algorithm"] and rg["seed"] == rr["seed"]
+            assert np.allclose(rg["sdr"], rr["sdr"], atol=1e-6) and np.allclose(rg["sir"], rr["sir"], atol=1e-6)
+            assert rg["runtime"] > 0
