@@ -206,6 +206,17 @@ size_t oiva_stft_scratch_bytes(int n_batch, int n_frames, int n_src, int frame_l
 int oiva_stft_synthesis(const void* Y, const double* win, const void* tw, void* scratch, void* y, int y_f32,
                         int n_batch, int n_frames, int n_src, int frame_len, int hop, int dtype, void* stream);
 
+/* out (R,R) fp64, R = a_rows + b_rows <= 64: Gram matrix of the real signals a[r*a_row_stride + n*a_sample_stride]
+ * (rows 0..a_rows-1) and b[...] (the following b_rows rows; b may be NULL with b_rows = 0) over n_samples samples
+ * -- the one pass over the audio an SDR / SIR evaluation needs.  Deterministic (two fixed-order passes).
+ * scratch: oiva_gram_scratch_bytes(R, n_samples) bytes.
+ * replaces: the inner products inside mir_eval.separation.bss_eval_sources as called by the drivers'
+ * convergence_callback (overiva_oneshot.py:263-284, overiva_sim.py:210-232). */
+size_t oiva_gram_scratch_bytes(int n_rows, long long n_samples);
+int oiva_gram(const double* a, long long a_row_stride, long long a_sample_stride, int a_rows, const double* b,
+              long long b_row_stride, long long b_sample_stride, int b_rows, long long n_samples, void* scratch,
+              double* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Plan: the whole overiva() call on device pointers (what the Python entry points use).
  * The plan owns no device memory: the caller provides one workspace block.

@@ -299,3 +299,114 @@ extern "C" int oiva_stft_synthesis(const void* Y, const double* win, const void*
     OIVA_LAUNCH_CHECK();
     return OIVA_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Gram matrix of a few long real signals: the only pass over the audio that an SDR / SIR evaluation needs
+// (convergence monitoring without copying the separated audio to the host every 10
+// epochs; reference: mir_eval.separation.bss_eval_sources inside convergence_callback,
+// overiva_oneshot.py:263-284, overiva_sim.py:210-232).  Rows 0..Ra-1 come from `a`, rows Ra..Ra+Rb-1 from `b`
+// (arbitrary row / sample strides, so slices of (N, K) channel-last audio are read in place).
+// Two passes, fixed summation order (deterministic): per-chunk partial dot products, then their sum.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int GRAM_THREADS = 256;
+constexpr int GRAM_CHUNK = 8192;  // samples per CTA
+
+struct GramParams {
+    const double* a;
+    long long a_rs, a_ss;
+    int Ra;
+    const double* b;
+    long long b_rs, b_ss;
+    int Rb;
+    long long n;
+    int n_chunks;
+    double* partials;  // (R(R+1)/2, n_chunks)
+    double* out;       // (R, R)
+};
+
+__device__ __forceinline__ const double* gram_row(const GramParams& p, int r, long long& ss) {
+    if (r < p.Ra) {
+        ss = p.a_ss;
+        return p.a + (size_t)r * p.a_rs;
+    }
+    ss = p.b_ss;
+    return p.b + (size_t)(r - p.Ra) * p.b_rs;
+}
+
+// grid (n_chunks, n_pairs): pair e = i(i+1)/2 + j, i >= j
+__global__ void __launch_bounds__(GRAM_THREADS) k_gram_partial(const GramParams p) {
+    __shared__ double red[GRAM_THREADS / 32];
+    int i = 0;
+    const int e = blockIdx.y;
+    while ((i + 1) * (i + 2) / 2 <= e) ++i;
+    const int j = e - i * (i + 1) / 2;
+    long long si, sj;
+    const double* ri = gram_row(p, i, si);
+    const double* rj = gram_row(p, j, sj);
+    const long long n0 = (long long)blockIdx.x * GRAM_CHUNK;
+    const long long n1 = min(p.n, n0 + GRAM_CHUNK);
+    double acc = 0.0;
+    for (long long n = n0 + threadIdx.x; n < n1; n += GRAM_THREADS) acc = fma(ri[n * si], rj[n * sj], acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < GRAM_THREADS / 32; ++w) s += red[w];
+        p.partials[(size_t)e * p.n_chunks + blockIdx.x] = s;
+    }
+}
+
+// one warp per pair: fixed-order strided sum of the chunk partials, butterfly, symmetric write
+__global__ void k_gram_final(const GramParams p) {
+    const int e = blockIdx.x;
+    int i = 0;
+    while ((i + 1) * (i + 2) / 2 <= e) ++i;
+    const int j = e - i * (i + 1) / 2;
+    double acc = 0.0;
+    for (int c = threadIdx.x; c < p.n_chunks; c += 32) acc += p.partials[(size_t)e * p.n_chunks + c];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (threadIdx.x == 0) {
+        const int R = p.Ra + p.Rb;
+        p.out[i * R + j] = acc;
+        p.out[j * R + i] = acc;
+    }
+}
+}  // namespace
+
+extern "C" size_t oiva_gram_scratch_bytes(int n_rows, long long n_samples) {
+    if (n_rows <= 0 || n_samples <= 0) return 0;
+    return (size_t)(n_rows * (n_rows + 1) / 2) * (size_t)((n_samples + GRAM_CHUNK - 1) / GRAM_CHUNK) * sizeof(double);
+}
+
+extern "C" int oiva_gram(const double* a, long long a_row_stride, long long a_sample_stride, int a_rows, const double* b,
+                         long long b_row_stride, long long b_sample_stride, int b_rows, long long n_samples,
+                         void* scratch, double* out, void* stream) {
+    OIVA_REQUIRE(a && scratch && out && (b || b_rows == 0), "oiva_gram: null pointer");
+    OIVA_REQUIRE(a_rows >= 1 && b_rows >= 0 && a_rows + b_rows <= 64, "oiva_gram: %d + %d rows not in 1..64", a_rows, b_rows);
+    OIVA_REQUIRE(n_samples >= 1 && n_samples < (1ll << 40), "oiva_gram: bad n_samples");
+    GramParams p;
+    p.a = a;
+    p.a_rs = a_row_stride;
+    p.a_ss = a_sample_stride;
+    p.Ra = a_rows;
+    p.b = b;
+    p.b_rs = b_row_stride;
+    p.b_ss = b_sample_stride;
+    p.Rb = b_rows;
+    p.n = n_samples;
+    p.n_chunks = (int)((n_samples + GRAM_CHUNK - 1) / GRAM_CHUNK);
+    p.partials = (double*)scratch;
+    p.out = out;
+    const int R = a_rows + b_rows, pairs = R * (R + 1) / 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_gram_partial<<<dim3(p.n_chunks, pairs), GRAM_THREADS, 0, st>>>(p);
+    OIVA_LAUNCH_CHECK();
+    k_gram_final<<<pairs, 32, 0, st>>>(p);
+    OIVA_LAUNCH_CHECK();
+    return OIVA_OK;
+}

@@ -113,8 +113,11 @@ def _analysis_launch(a, frame_len, hop, win, pad_front, n_frames, out, grouped, 
     d = a.dev
     B, N, M = d.shape
     sb, sn, sc = d.stride()
+    # keep the window / twiddle tensors referenced until the launch has been queued: a temporary freed before
+    # the launch could be handed to the next allocation on this stream
+    wd, tw = _window(win, frame_len, a.device), _twiddles(frame_len, a.device)
     L.check(lib.oiva_stft_analysis(core._ptr(d), int(d.dtype == torch.float32), sb, sn, sc, N, int(pad_front),
-                                   core._ptr(_window(win, frame_len, a.device)), core._ptr(_twiddles(frame_len, a.device)),
+                                   core._ptr(wd), core._ptr(tw),
                                    out if isinstance(out, C.c_void_p) else core._ptr(out), int(grouped), B, n_frames, M,
                                    int(frame_len), int(hop), L.C64 if cdtype == torch.complex64 else L.C128,
                                    core._stream_ptr(a.device)), "oiva_stft_analysis")
@@ -154,8 +157,8 @@ def _synthesis_dev(Yd, frame_len, hop, win, out_dtype=torch.float64):
     dev = Yd.device
     scratch = torch.empty(lib.oiva_stft_scratch_bytes(B, T, K, frame_len), dtype=torch.uint8, device=dev)
     y = torch.empty((B, (T - 1) * hop + frame_len, K), dtype=out_dtype, device=dev)
-    L.check(lib.oiva_stft_synthesis(core._ptr(Yd), core._ptr(_window(win, frame_len, dev)),
-                                    core._ptr(_twiddles(frame_len, dev)), core._ptr(scratch), core._ptr(y),
+    wd, tw = _window(win, frame_len, dev), _twiddles(frame_len, dev)  # referenced until the launch is queued
+    L.check(lib.oiva_stft_synthesis(core._ptr(Yd), core._ptr(wd), core._ptr(tw), core._ptr(scratch), core._ptr(y),
                                     int(out_dtype == torch.float32), B, T, K, int(frame_len), int(hop),
                                     L.C64 if Yd.dtype == torch.complex64 else L.C128, core._stream_ptr(dev)),
             "oiva_stft_synthesis")

@@ -58,7 +58,7 @@ def main():
     S = torch.randn((B, N, K + 3), generator=g, device=dev, dtype=torch.float64)
     env = torch.rand((B, N // 4000 + 1, K + 3), generator=g, device=dev, dtype=torch.float64).repeat_interleave(4000, 1)[:, :N]
     A = torch.randn((B, K + 3, M), generator=g, device=dev, dtype=torch.float64)
-    x = torch.bmm(S * S.abs() * env, A)
+    x = torch.bmm(S * S.abs() * env, A) + 1e-3 * torch.randn((B, N, M), generator=g, device=dev, dtype=torch.float64)
     del S, env
     xh = torch.empty((B, N, M), dtype=torch.float64).pin_memory()
     xh.copy_(x)

@@ -218,9 +218,10 @@ def test_separate_batch_filters_and_errors():
     assert y.shape[0] == 3 and y.shape[2] == 2 and W.shape == (3, 33, 3, 2)
     for b in range(3):
         yb, Wb = gst.separate(mixes[b], n_src=2, framesize=64, return_filters=True)
-        assert np.array_equal(yb, y[b]) and np.array_equal(Wb, W[b])  # batching never changes a mixture's result
+        # same arithmetic per mixture; only the frame split of the covariance sums depends on the batch size
+        assert rel_err(yb, y[b]) < 1e-11 and rel_err(Wb, W[b]) < 1e-11
     yt = gst.separate(torch.from_numpy(mixes[0]).cuda(), n_src=2, framesize=64)
-    assert yt.is_cuda and np.array_equal(yt.cpu().numpy(), y[0])
+    assert yt.is_cuda and rel_err(yt.cpu().numpy(), y[0]) < 1e-11
     with pytest.raises(ValueError, match="No such algorithm"):
         gst.separate(mixes[0], algo="ilrma")
     with pytest.raises(ValueError, match="one mixture at a time"):
@@ -236,10 +237,10 @@ def test_separate_batch_host_pipeline_equals_per_mixture_calls():
     y = gst.separate_batch(mixes, n_src=2, framesize=64, chunk=2)  # 3 chunks, the last one partial
     assert y.shape == (5, (mixes.shape[1] - 64) // 32 * 32 + 64, 2) and y.dtype == np.float64
     for b in range(5):
-        assert np.array_equal(y[b], gst.separate(mixes[b], n_src=2, framesize=64))
+        assert rel_err(y[b], gst.separate(mixes[b], n_src=2, framesize=64)) < 1e-11
     pinned = torch.from_numpy(mixes).pin_memory()
     out = torch.empty(y.shape, dtype=torch.float64).pin_memory()
     yt = gst.separate_batch(pinned, n_src=2, framesize=64, chunk=4, out=out)
-    assert yt is out and np.array_equal(out.numpy(), y)
+    assert yt is out and rel_err(out.numpy(), y) < 1e-11
     y32 = gst.separate_batch(mixes.astype(np.float32), n_src=2, framesize=64, dtype=torch.complex64)
     assert y32.dtype == np.float32 and rel_err(y32, y) < 1e-3
