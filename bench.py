@@ -11,7 +11,8 @@ complex128), one shard per rank, no collective in the data path (weak scaling).
 
 Printed JSON (one line, rank 0): ``value`` = device-resident throughput (X already in HBM), ``e2e`` = the
 same metric through the public ``overiva_batch`` call with pinned HOST buffers (H2D of X and D2H of Y inside
-the timed region), ``roofline`` for the dominant kernel (weighted covariance) from CUDA events recorded
+the timed region), ``e2e_audio`` = the same workload entered as time-domain AUDIO through
+``overiva_b200.stft.separate_batch`` (STFT / iSTFT on the device: half the PCIe bytes), ``roofline`` for the dominant kernel (weighted covariance) from CUDA events recorded
 around its launches inside the timed region, ``cpu_baseline`` = the numpy oracle (a port of the reference's
 algorithm) on this box's host cores over a bounded sample of the same workload.
 
@@ -329,6 +330,43 @@ def run_gpu(args):
     except RuntimeError as exc:  # e.g. not enough pinnable host memory
         e2e = {"value": None, "unit": UNIT, "error": str(exc)[:200]}
 
+    # ---- end-to-end from AUDIO: STFT and iSTFT on the device, only audio crosses PCIe ---
+    e2e_audio = None
+    try:
+        from overiva_b200 import stft as gstft
+        from overiva_b200.synth import audio_batch_torch
+
+        del Xh, Yh
+        torch.cuda.empty_cache()
+        n_samples = int(DURATION_S * FS)
+        xa = audio_batch_torch(B, n_samples, M, K, seed=99 + rank, device=dev)
+        assert gstft.num_frames(n_samples, 4096, 2048) == T
+        xh = torch.empty((B, n_samples, M), dtype=torch.float64, pin_memory=True)
+        xh.copy_(xa)
+        del xa
+        torch.cuda.empty_cache()
+        yh = torch.empty((B, (T - 1) * 2048 + 4096, K), dtype=torch.float64, pin_memory=True)
+        for _ in range(2):
+            gstft.separate_batch(xh, n_src=K, n_iter=N_ITER, framesize=4096, model=MODEL, out=yh)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            gstft.separate_batch(xh, n_src=K, n_iter=N_ITER, framesize=4096, model=MODEL, out=yh)
+        barrier()
+        t_a = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_a, op=dist.ReduceOp.MAX)
+        e2e_audio = {
+            "value": world * B * DURATION_S / (float(t_a.item()) / e2e_steps), "unit": UNIT,
+            "h2d_bytes_per_step": xh.numel() * 8, "d2h_bytes_per_step": yh.numel() * 8, "steps": e2e_steps,
+            "api": "overiva_b200.stft.separate_batch(pinned host audio (B,N,M) float64, out=pinned): STFT 4096/2048 "
+                   "-> loop -> iSTFT on the device, chunks of 64 mixtures on three streams",
+        }
+        assert bool(torch.isfinite(yh).all())
+        del xh, yh
+    except (RuntimeError, NameError) as exc:
+        e2e_audio = {"value": None, "unit": UNIT, "error": str(exc)[:200]}
+
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -346,7 +384,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(B, world), "clocks": clocks,
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "e2e_audio": e2e_audio, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

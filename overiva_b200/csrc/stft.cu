@@ -1,4 +1,4 @@
-// STFT analysis / synthesis feeding and consuming the demixing loop on the device (SURVEY.md §8(f) rank 1).
+// STFT analysis / synthesis feeding and consuming the demixing loop on the device (SURVEY.md 8(f) rank 1).
 //
 // The reference's drivers call pyroomacoustics for this (third-party, not in the reference tree):
 //   X = pra.transform.analysis(mix.T, framesize, framesize // 2, win=win_a)      overiva_oneshot.py:293-295,
@@ -6,17 +6,27 @@
 //   y = pra.transform.synthesis(Y, framesize, framesize // 2, win=win_s)          overiva_oneshot.py:371-379,
 //                                                                                 overiva_sim.py:213-218
 // with framesize 4096, hop 2048, a Hann analysis window and the matched synthesis window
-// (overiva_oneshot.py:156-158).  Here one CTA transforms one frame of one channel entirely in shared memory
-// (real FFT of length L as a complex FFT of length L/2 on the even/odd samples, fp64, radix-2 with table
-// twiddles) and writes the L/2+1 bins EITHER in the caller's (B,T,F,M) order OR directly in the grouped layout
-// Xg[gi][t][c][lane] the loop streams -- so "audio in" needs neither a (T,F,M) array in HBM nor the relayout pass.
-// Synthesis is the inverse: one CTA per (mixture, frame, source) -> windowed time frame, then a gather
-// overlap-add (fixed summation order: deterministic).
+// (overiva_oneshot.py:156-158).
+//
+// One CTA transforms one frame of TWO channels at once: z = x_c + i x_{c+1} goes through ONE complex FFT of length L
+// held in shared memory and the two real spectra are separated afterwards (X_c = (Z[k] + conj Z[L-k]) / 2,
+// X_{c+1} = -i (Z[k] - conj Z[L-k]) / 2).  The FFT is a Stockham autosort transform in fp64: radix-8 passes (plus one
+// radix-2 / radix-4 pass when log2 L is not a multiple of 3), each thread holding its butterflies in registers
+// between the read and the write of a pass so a single buffer suffices; indices are padded by i/8 so that every
+// quarter-warp of a 16-byte access hits 32 distinct banks in all passes; the three twiddles w, w^2, w^4 of a
+// butterfly come from a table, the others are their products.  Bins are written EITHER in the caller's (B,T,F,M)
+// order OR directly in the grouped layout Xg[gi][t][c][lane] the loop streams -- "audio in" then needs neither a
+// (T,F,M) array in HBM nor the relayout pass.  Synthesis is the inverse (two sources per complex FFT, inverse by
+// conjugation), followed by a gather overlap-add in ascending frame order (deterministic).
 #include "common.cuh"
 
 namespace {
 
-constexpr int STFT_THREADS = 256;
+constexpr int FFT_PTS = 16;  // points per thread: blockDim = L / 16 (at least one warp)
+
+__host__ __device__ inline int stft_threads(int L) { return L / FFT_PTS < 32 ? 32 : L / FFT_PTS; }
+__host__ __device__ inline size_t stft_smem_bytes(int L) { return (size_t)(L + L / 8 + 1) * sizeof(cplx); }
+__device__ __forceinline__ int pidx(int i) { return i + (i >> 3); }
 
 // tw[q] = exp(-2 pi i q / L), q < L/2
 __global__ void k_twiddles(cplx* __restrict__ tw, int L) {
@@ -28,27 +38,101 @@ __global__ void k_twiddles(cplx* __restrict__ tw, int L) {
     }
 }
 
-// In-place radix-2 decimation-in-time FFT of n2 = 2^lg points held in shared memory in BIT-REVERSED order.
-// tw[2 q] = exp(-2 pi i q / n2); INVERSE conjugates the twiddles (no scaling).
-template <bool INVERSE>
-__device__ __forceinline__ void fft_smem(cplx* z, int lg, const cplx* __restrict__ tw) {
-    const int n2 = 1 << lg;
-    for (int s = 0; s < lg; ++s) {
-        __syncthreads();
-        const int half = 1 << s;
-        for (int j = threadIdx.x; j < n2 / 2; j += STFT_THREADS) {
-            const int pos = j & (half - 1);
-            const int i0 = ((j >> s) << (s + 1)) + pos;
-            const int i1 = i0 + half;
-            cplx w = __ldg(&tw[(size_t)(pos << (lg - 1 - s)) * 2]);
-            if (INVERSE) w.y = -w.y;
-            const cplx a = z[i0];
-            const cplx b = cmul(z[i1], w);
-            z[i0] = cadd(a, b);
-            z[i1] = csub(a, b);
+// natural-order forward DFTs of 2 / 4 / 8 points in registers
+__device__ __forceinline__ cplx mul_mi(cplx a) { return cmake(a.y, -a.x); }  // -i a
+__device__ __forceinline__ void dft4(cplx& a0, cplx& a1, cplx& a2, cplx& a3) {
+    const cplx s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = mul_mi(csub(a1, a3));
+    a0 = cadd(s02, s13);
+    a1 = cadd(d02, d13);
+    a2 = csub(s02, s13);
+    a3 = csub(d02, d13);
+}
+template <int R>
+__device__ __forceinline__ void dft_r(cplx (&v)[R]) {
+    if constexpr (R == 2) {
+        const cplx a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    } else if constexpr (R == 4) {
+        dft4(v[0], v[1], v[2], v[3]);
+    } else {
+        cplx e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+        dft4(e0, e1, e2, e3);
+        dft4(o0, o1, o2, o3);
+        const double h = 0.70710678118654752440;
+        o1 = cmake(h * (o1.x + o1.y), h * (o1.y - o1.x));    // * (1 - i)/sqrt2
+        o2 = mul_mi(o2);                                     // * -i
+        o3 = cmake(h * (o3.y - o3.x), -h * (o3.x + o3.y));   // * (-1 - i)/sqrt2
+        v[0] = cadd(e0, o0);
+        v[4] = csub(e0, o0);
+        v[1] = cadd(e1, o1);
+        v[5] = csub(e1, o1);
+        v[2] = cadd(e2, o2);
+        v[6] = csub(e2, o2);
+        v[3] = cadd(e3, o3);
+        v[7] = csub(e3, o3);
+    }
+}
+
+// One Stockham pass of radix R over the N points in z (padded indexing); Ns = product of the radices done so far.
+// tw: exp(-2 pi i q / N) for q < N/2.  Every thread reads all its butterflies, then (barrier) writes them.
+template <int R>
+__device__ __forceinline__ void stockham_pass(cplx* z, int N, int Ns, const cplx* __restrict__ tw) {
+    constexpr int NB = FFT_PTS / R;
+    cplx v[NB][R];
+    const int nbf = N / R;
+    const int step = N / (Ns * R);
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        const int j = threadIdx.x + i * blockDim.x;
+        if (j < nbf) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[i][r] = z[pidx(j + r * nbf)];
+            const int k = j & (Ns - 1);
+            if (k != 0) {
+                const cplx w1 = __ldg(&tw[k * step]);
+                v[i][1] = cmul(v[i][1], w1);
+                if constexpr (R >= 4) {
+                    const cplx w2 = __ldg(&tw[2 * k * step]);
+                    const cplx w3 = cmul(w1, w2);
+                    v[i][2] = cmul(v[i][2], w2);
+                    v[i][3] = cmul(v[i][3], w3);
+                    if constexpr (R == 8) {
+                        const cplx w4 = __ldg(&tw[4 * k * step]);
+                        v[i][4] = cmul(v[i][4], w4);
+                        v[i][5] = cmul(v[i][5], cmul(w4, w1));
+                        v[i][6] = cmul(v[i][6], cmul(w4, w2));
+                        v[i][7] = cmul(v[i][7], cmul(w4, w3));
+                    }
+                }
+            }
+            dft_r<R>(v[i]);
         }
     }
     __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        const int j = threadIdx.x + i * blockDim.x;
+        if (j < nbf) {
+            const int k = j & (Ns - 1);
+            const int j0 = (j - k) * R + k;
+#pragma unroll
+            for (int r = 0; r < R; ++r) z[pidx(j0 + r * Ns)] = v[i][r];
+        }
+    }
+    __syncthreads();
+}
+
+// forward complex FFT of N = 2^lg points in z (natural order in and out); the caller has synchronised after filling z
+__device__ __forceinline__ void fft_forward(cplx* z, int lg, const cplx* __restrict__ tw) {
+    const int N = 1 << lg;
+    int Ns = 1;
+    for (int p = 0; p < lg / 3; ++p) {
+        stockham_pass<8>(z, N, Ns, tw);
+        Ns *= 8;
+    }
+    if (lg % 3 == 1) stockham_pass<2>(z, N, Ns, tw);
+    if (lg % 3 == 2) stockham_pass<4>(z, N, Ns, tw);
 }
 
 struct AnalysisParams {
@@ -63,50 +147,58 @@ struct AnalysisParams {
     int grouped;          // 1: Xg[gi][t][c][lane];  0: X (B,T,F,M)
 };
 
+// grid (T * ceil(M/2), B)
 template <typename AT, typename ST>
-__global__ void __launch_bounds__(STFT_THREADS) k_stft_analysis(const AnalysisParams p) {
+__global__ void __launch_bounds__(512) k_stft_analysis(const AnalysisParams p) {
     typedef typename StoreC<ST>::type XC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* z = reinterpret_cast<cplx*>(smem_raw);
-    const int c = blockIdx.x % p.M;
-    const int t = blockIdx.x / p.M;
+    const int MP = (p.M + 1) / 2;
+    const int c0 = 2 * (blockIdx.x % MP);
+    const int t = blockIdx.x / MP;
     const int b = blockIdx.y;
-    const int n2 = p.L / 2, lg = p.lg;
-    const AT* x = reinterpret_cast<const AT*>(p.x) + (size_t)b * p.sb + (size_t)c * p.sc;
+    const bool two = c0 + 1 < p.M;
+    const AT* xa = reinterpret_cast<const AT*>(p.x) + (size_t)b * p.sb + (size_t)c0 * p.sc;
+    const AT* xb = xa + (two ? p.sc : 0);
     const long long n0 = p.first + (long long)t * p.hop;
-    for (int n = threadIdx.x; n < n2; n += STFT_THREADS) {
-        const long long s0 = n0 + 2 * n, s1 = s0 + 1;
-        double v0 = (s0 >= 0 && s0 < p.N) ? (double)x[s0 * p.sn] : 0.0;
-        double v1 = (s1 >= 0 && s1 < p.N) ? (double)x[s1 * p.sn] : 0.0;
-        if (p.win) {
-            v0 *= __ldg(&p.win[2 * n]);
-            v1 *= __ldg(&p.win[2 * n + 1]);
+    for (int n = threadIdx.x; n < p.L; n += blockDim.x) {
+        const long long s = n0 + n;
+        double va = 0.0, vb = 0.0;
+        if (s >= 0 && s < p.N) {
+            va = (double)xa[s * p.sn];
+            if (two) vb = (double)xb[s * p.sn];
         }
-        z[__brev((unsigned)n) >> (32 - lg)] = cmake(v0, v1);
+        if (p.win) {
+            const double w = __ldg(&p.win[n]);
+            va *= w;
+            vb *= w;
+        }
+        z[pidx(n)] = cmake(va, vb);
     }
-    fft_smem<false>(z, lg, p.tw);
-    // X[k] = E[k] + exp(-2 pi i k / L) O[k],  E = (Z[k] + conj Z[n2-k]) / 2,  O = -i (Z[k] - conj Z[n2-k]) / 2
+    __syncthreads();
+    fft_forward(z, p.lg, p.tw);
     XC* out = reinterpret_cast<XC*>(p.out);
     const int kmax = p.grouped ? p.NG * OIVA_GROUP : p.F;
-    for (int k = threadIdx.x; k < kmax; k += STFT_THREADS) {
-        cplx X = cmake(0.0, 0.0);
+    for (int k = threadIdx.x; k < kmax; k += blockDim.x) {
+        cplx Xa = cmake(0.0, 0.0), Xb = cmake(0.0, 0.0);
         if (k < p.F) {
-            const cplx zk = z[k & (n2 - 1)];
-            const cplx zm = cconj(z[(n2 - k) & (n2 - 1)]);
-            const cplx e = cscale(cadd(zk, zm), 0.5);
-            const cplx d = cscale(csub(zk, zm), 0.5);
-            const cplx o = cmake(d.y, -d.x);  // -i d
-            const cplx w = k < n2 ? __ldg(&p.tw[k]) : cmake(-1.0, 0.0);
-            X = cadd(e, cmul(w, o));
-            if (k == 0 || k == n2) X.y = 0.0;  // exactly real for real input
+            const cplx zk = z[pidx(k)];
+            const cplx zm = cconj(z[pidx((p.L - k) & (p.L - 1))]);
+            Xa = cscale(cadd(zk, zm), 0.5);
+            Xb = mul_mi(cscale(csub(zk, zm), 0.5));
         }
-        XC v;
-        narrow(v, X);
+        XC va, vb;
+        narrow(va, Xa);
+        narrow(vb, Xb);
         if (p.grouped) {
             const size_t gi = (size_t)b * p.NG + (k >> 5);
-            out[((gi * p.T + t) * p.M + c) * OIVA_GROUP + (k & 31)] = v;
+            XC* dst = out + ((gi * p.T + t) * p.M + c0) * OIVA_GROUP + (k & 31);
+            dst[0] = va;
+            if (two) dst[OIVA_GROUP] = vb;
         } else {
-            out[(((size_t)b * p.T + t) * p.F + k) * p.M + c] = v;
+            XC* dst = out + (((size_t)b * p.T + t) * p.F + k) * p.M + c0;
+            dst[0] = va;
+            if (two) dst[1] = vb;
         }
     }
 }
@@ -119,43 +211,40 @@ struct SynthesisParams {
     int B, T, K, L, lg, F;
 };
 
+// grid (T * ceil(K/2), B): irfft of two sources through one complex FFT (inverse = conj o forward o conj)
 template <typename ST>
-__global__ void __launch_bounds__(STFT_THREADS) k_stft_frames(const SynthesisParams p) {
+__global__ void __launch_bounds__(512) k_stft_frames(const SynthesisParams p) {
     typedef typename StoreC<ST>::type XC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* z = reinterpret_cast<cplx*>(smem_raw);
-    const int k = blockIdx.x % p.K;
-    const int t = blockIdx.x / p.K;
+    const int KP = (p.K + 1) / 2;
+    const int k0 = 2 * (blockIdx.x % KP);
+    const int t = blockIdx.x / KP;
     const int b = blockIdx.y;
-    const int n2 = p.L / 2, lg = p.lg;
-    const XC* Y = reinterpret_cast<const XC*>(p.Y) + ((size_t)b * p.T + t) * p.F * p.K + k;
-    // Z[q] = E[q] + i O[q],  E = (X[q] + conj X[n2-q]) / 2,  O = exp(+2 pi i q / L) (X[q] - conj X[n2-q]) / 2
-    for (int q = threadIdx.x; q < n2; q += STFT_THREADS) {
-        cplx xq = widen(Y[(size_t)q * p.K]);
-        cplx xm = widen(Y[(size_t)(n2 - q) * p.K]);
-        if (q == 0) {  // numpy.fft.irfft ignores the imaginary parts of the DC and Nyquist bins
-            xq.y = 0.0;
-            xm.y = 0.0;
+    const bool two = k0 + 1 < p.K;
+    const int half = p.L / 2;
+    const XC* Y = reinterpret_cast<const XC*>(p.Y) + ((size_t)b * p.T + t) * p.F * p.K + k0;
+    // Z[q] = Xa[q] + i Xb[q] (q <= L/2),  Z[L-q] = conj Xa[q] + i conj Xb[q];  the buffer receives conj Z
+    for (int q = threadIdx.x; q <= half; q += blockDim.x) {
+        cplx xa = widen(Y[(size_t)q * p.K]);
+        cplx xb = two ? widen(Y[(size_t)q * p.K + 1]) : cmake(0.0, 0.0);
+        if (q == 0 || q == half) {  // numpy.fft.irfft ignores the imaginary parts of the DC and Nyquist bins
+            xa.y = 0.0;
+            xb.y = 0.0;
         }
-        xm.y = -xm.y;
-        const cplx e = cscale(cadd(xq, xm), 0.5);
-        const cplx d = cscale(csub(xq, xm), 0.5);
-        cplx w = __ldg(&p.tw[q]);
-        w.y = -w.y;
-        const cplx o = cmul(w, d);
-        z[__brev((unsigned)q) >> (32 - lg)] = cmake(e.x - o.y, e.y + o.x);  // e + i o
+        z[pidx(q)] = cmake(xa.x - xb.y, -(xa.y + xb.x));
+        if (q != 0 && q != half) z[pidx(p.L - q)] = cmake(xa.x + xb.y, -(xb.x - xa.y));
     }
-    fft_smem<true>(z, lg, p.tw);
-    const double scale = 1.0 / (double)n2;
-    double* fr = p.frames + (((size_t)b * p.T + t) * p.K + k) * p.L;
-    for (int n = threadIdx.x; n < n2; n += STFT_THREADS) {
-        const cplx v = z[n];
-        double a = v.x * scale, c = v.y * scale;
-        if (p.win) {
-            a *= __ldg(&p.win[2 * n]);
-            c *= __ldg(&p.win[2 * n + 1]);
-        }
-        reinterpret_cast<double2*>(fr)[n] = make_double2(a, c);
+    __syncthreads();
+    fft_forward(z, p.lg, p.tw);
+    const double scale = 1.0 / (double)p.L;
+    double* fa = p.frames + (((size_t)b * p.T + t) * p.K + k0) * p.L;
+    double* fb = fa + p.L;
+    for (int n = threadIdx.x; n < p.L; n += blockDim.x) {
+        const cplx v = z[pidx(n)];
+        const double w = p.win ? scale * __ldg(&p.win[n]) : scale;
+        fa[n] = v.x * w;
+        if (two) fb[n] = -v.y * w;
     }
 }
 
@@ -229,19 +318,19 @@ extern "C" int oiva_stft_analysis(const void* x, int x_f32, long long stride_b, 
     p.T = n_frames;
     p.M = n_chan;
     p.L = frame_len;
-    p.lg = lg - 1;
+    p.lg = lg;
     p.hop = hop;
     p.F = frame_len / 2 + 1;
     p.NG = oiva_bin_groups(p.F);
     p.grouped = grouped;
-    const size_t smem = (size_t)(frame_len / 2) * sizeof(cplx);
-    dim3 grid((unsigned)((long long)n_frames * n_chan), n_batch);
+    const size_t smem = stft_smem_bytes(frame_len);
+    dim3 grid((unsigned)((long long)n_frames * ((n_chan + 1) / 2)), n_batch);
     cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_A(AT, ST)                                                                                           \
     do {                                                                                                           \
         OIVA_CUDA_CHECK(cudaFuncSetAttribute(k_stft_analysis<AT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             64 * 1024));                                                          \
-        k_stft_analysis<AT, ST><<<grid, STFT_THREADS, smem, st>>>(p);                                              \
+                                             (int)stft_smem_bytes(8192)));                                         \
+        k_stft_analysis<AT, ST><<<grid, stft_threads(frame_len), smem, st>>>(p);                                   \
     } while (0)
     if (x_f32) {
         if (dtype == OIVA_C64) LAUNCH_A(float, float); else LAUNCH_A(float, double);
@@ -277,17 +366,19 @@ extern "C" int oiva_stft_synthesis(const void* Y, const double* win, const void*
     p.T = n_frames;
     p.K = n_src;
     p.L = frame_len;
-    p.lg = lg - 1;
+    p.lg = lg;
     p.F = frame_len / 2 + 1;
-    const size_t smem = (size_t)(frame_len / 2) * sizeof(cplx);
-    dim3 grid((unsigned)((long long)n_frames * n_src), n_batch);
+    const size_t smem = stft_smem_bytes(frame_len);
+    dim3 grid((unsigned)((long long)n_frames * ((n_src + 1) / 2)), n_batch);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == OIVA_C64) {
-        OIVA_CUDA_CHECK(cudaFuncSetAttribute(k_stft_frames<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        k_stft_frames<float><<<grid, STFT_THREADS, smem, st>>>(p);
+        OIVA_CUDA_CHECK(cudaFuncSetAttribute(k_stft_frames<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)stft_smem_bytes(8192)));
+        k_stft_frames<float><<<grid, stft_threads(frame_len), smem, st>>>(p);
     } else {
-        OIVA_CUDA_CHECK(cudaFuncSetAttribute(k_stft_frames<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        k_stft_frames<double><<<grid, STFT_THREADS, smem, st>>>(p);
+        OIVA_CUDA_CHECK(cudaFuncSetAttribute(k_stft_frames<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)stft_smem_bytes(8192)));
+        k_stft_frames<double><<<grid, stft_threads(frame_len), smem, st>>>(p);
     }
     OIVA_LAUNCH_CHECK();
     const long long n_out = (long long)(n_frames - 1) * hop + frame_len;

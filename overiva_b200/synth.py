@@ -179,3 +179,39 @@ def stft_domain_batch_torch(n_batch, n_frames, n_freq, n_mics, n_src, seed, devi
         X += sig * torch.complex(rnd(nb, T, F, M), rnd(nb, T, F, M))
         out[b0 : b0 + nb] = X
     return out
+
+
+def audio_batch_torch(n_batch, n_samples, n_mics, n_src, seed, device, n_interferers=10, sinr_db=10.0, snr_db=60.0,
+                      fs=16000, chunk=64):
+    """Device-side generator of time-domain inputs for throughput runs of the audio-in / audio-out path:
+    (B, N, M) float64 -- per mixture ``n_src`` targets and ``n_interferers`` weaker sources (super-Gaussian samples
+    with a 250 ms block envelope), each reaching the microphones through a short random decaying filter (32 taps,
+    applied as a sum of delayed copies), plus sensor noise; SINR / SNR as in ``convolutive_mixture``.  Cheap on
+    purpose: the cost of the separation does not depend on the signal content."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    B, N, M, Q = n_batch, n_samples, n_mics, n_src + n_interferers
+    out = torch.empty((B, N, M), dtype=torch.float64, device=device)
+    blk = max(1, int(0.25 * fs))
+    gain = torch.ones(Q, dtype=torch.float64, device=device)
+    sig_n = (10 ** (-snr_db / 10) * n_src) ** 0.5
+    if n_interferers:
+        gain[n_src:] = (max(0.0, 10 ** (-sinr_db / 10) * n_src - sig_n**2) / n_interferers) ** 0.5
+    taps = 32
+    decay = torch.exp(-0.25 * torch.arange(taps, dtype=torch.float64, device=device))
+    for b0 in range(0, B, chunk):
+        nb = min(chunk, B - b0)
+        rnd = lambda *s: torch.randn(*s, generator=g, device=device, dtype=torch.float64)
+        S = rnd(nb, N, Q)
+        S = S * S.abs()  # heavier tails than a Gaussian
+        env = (0.5 * rnd(nb, N // blk + 1, Q) ** 2 + 0.05).repeat_interleave(blk, dim=1)[:, :N]
+        S = S * env * gain
+        H = rnd(nb, taps, Q, M) * decay[None, :, None, None] * 0.3
+        H[:, 0] += 1.0
+        x = sig_n * rnd(nb, N, M)
+        for d in range(taps):
+            x[:, d:] += torch.bmm(S[:, : N - d], H[:, d])
+        out[b0 : b0 + nb] = x
+    return out

@@ -52,14 +52,11 @@ def main():
     T = stft.num_frames(N, Lf, hop)
     F = Lf // 2 + 1
     lib = L.load()
+    from overiva_b200.synth import audio_batch_torch
+
     g = torch.Generator(device=dev)
     g.manual_seed(1)
-    # synthetic audio: a per-channel random mix of K + 3 Laplacian-ish sources with block envelopes
-    S = torch.randn((B, N, K + 3), generator=g, device=dev, dtype=torch.float64)
-    env = torch.rand((B, N // 4000 + 1, K + 3), generator=g, device=dev, dtype=torch.float64).repeat_interleave(4000, 1)[:, :N]
-    A = torch.randn((B, K + 3, M), generator=g, device=dev, dtype=torch.float64)
-    x = torch.bmm(S * S.abs() * env, A) + 1e-3 * torch.randn((B, N, M), generator=g, device=dev, dtype=torch.float64)
-    del S, env
+    x = audio_batch_torch(B, N, M, K, seed=4321, device=dev)
     xh = torch.empty((B, N, M), dtype=torch.float64).pin_memory()
     xh.copy_(x)
     res = {"workload": "%d mixtures x %.0f s @ 16 kHz, M=%d K=%d, framesize 4096 hop 2048 -> (T=%d, F=%d), 20 iterations"

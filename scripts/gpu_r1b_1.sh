@@ -8,6 +8,5 @@ run() {
   echo "rc=$?" | tee -a gpurun_out/summary.txt
   tail -n 12 gpurun_out/$name.log | cut -c1-3000 | tee -a gpurun_out/summary.txt
 }
-run pytest_new 600 python -m pytest tests/test_stft.py tests/test_sweep.py -q -m gpu
+run pytest_new 600 python -m pytest tests/test_stft.py tests/test_sweep.py tests/test_monitor.py -q -m gpu
 run audio 600 python scripts/bench_audio.py
-run pytest_all 900 python -m pytest tests -x -q -m gpu
