@@ -323,7 +323,7 @@ def run_gpu(args):
             "value": world * B * DURATION_S / (float(t_e.item()) / e2e_steps), "unit": UNIT,
             "h2d_bytes_per_step": Xh.numel() * 16, "d2h_bytes_per_step": Yh.numel() * 16,
             "steps": e2e_steps,
-            "api": "overiva_b200.overiva_batch(pinned CPU tensor, out=pinned CPU tensor): chunks of 64 mixtures, "
+            "api": "overiva_b200.overiva_batch(pinned CPU tensor, out=pinned CPU tensor): chunks of 32 mixtures, "
                    "H2D / loop / D2H overlapped on three streams",
         }
         assert bool(torch.isfinite(Yh.real).all())
@@ -360,7 +360,7 @@ def run_gpu(args):
             "value": world * B * DURATION_S / (float(t_a.item()) / e2e_steps), "unit": UNIT,
             "h2d_bytes_per_step": xh.numel() * 8, "d2h_bytes_per_step": yh.numel() * 8, "steps": e2e_steps,
             "api": "overiva_b200.stft.separate_batch(pinned host audio (B,N,M) float64, out=pinned): STFT 4096/2048 "
-                   "-> loop -> iSTFT on the device, chunks of 64 mixtures on three streams",
+                   "-> loop -> iSTFT on the device, chunks of 32 mixtures on three streams",
         }
         assert bool(torch.isfinite(yh).all())
         del xh, yh

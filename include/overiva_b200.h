@@ -188,7 +188,9 @@ int oiva_ogive_switching(const void* a, const void* C, const double* cnorm, uint
  * (pyroomacoustics is third-party and absent from the reference tree: X[t] = rfft(win * frame_t), no scaling;
  * synthesis = overlap-add of win * irfft(Y[t]).)  frame_len: a power of two in 8..8192; F = frame_len/2 + 1.
  * ---------------------------------------------------------------------------------------------- */
-/* tw (frame_len/2 c128) <- exp(-2 pi i q / frame_len): the table both transforms need */
+/* tw (oiva_stft_twiddle_bytes(frame_len) bytes) <- the twiddle factors both transforms need, one compact block
+ * per FFT pass (csrc/stft.cu) */
+size_t oiva_stft_twiddle_bytes(int frame_len);
 int oiva_stft_twiddles(void* tw, int frame_len, void* stream);
 /* frames of length frame_len every hop samples over pad_front zeros + the signal + pad_back zeros */
 int oiva_stft_num_frames(long long n_samples, int frame_len, int hop, long long pad_front, long long pad_back);

@@ -63,6 +63,7 @@ SIGNATURES = {
     "oiva_ogive_setup": (_i, [_p, _p, _p, _p, _i, _i, _p]),
     "oiva_ogive_a_from_w": (_i, [_p, _p, _p, _i, _i, _p]),
     "oiva_ogive_switching": (_i, [_p, _p, _p, _p, _i, _i, _p]),
+    "oiva_stft_twiddle_bytes": (_sz, [_i]),
     "oiva_stft_twiddles": (_i, [_p, _i, _p]),
     "oiva_stft_num_frames": (_i, [_ll, _i, _i, _ll, _ll]),
     "oiva_stft_analysis": (_i, [_p, _i, _ll, _ll, _ll, _ll, _ll, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),

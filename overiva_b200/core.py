@@ -402,7 +402,7 @@ def _host_pipeline(Xh, n_src, n_iter, proj_back, W0, model, init_eig, return_fil
 
 
 def overiva_batch(X, n_src=None, n_iter=20, proj_back=True, W0=None, model="laplace", init_eig=False,
-                  return_filters=False, chunk=64, out=None):
+                  return_filters=False, chunk=32, out=None):
     """Many independent mixtures at once: X (B, n_frames, n_freq, n_chan) -> Y (B, n_frames, n_freq, n_src)
     [, W (B, n_freq, n_chan, n_src)].  The role of the reference's task farm (``overiva_sim.py`` +
     ``rrtools``) for mixtures of one shape; every mixture is processed exactly as ``overiva`` would.

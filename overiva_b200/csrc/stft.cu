@@ -18,6 +18,8 @@
 // order OR directly in the grouped layout Xg[gi][t][c][lane] the loop streams -- "audio in" then needs neither a
 // (T,F,M) array in HBM nor the relayout pass.  Synthesis is the inverse (two sources per complex FFT, inverse by
 // conjugation), followed by a gather overlap-add in ascending frame order (deterministic).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -28,13 +30,36 @@ __host__ __device__ inline int stft_threads(int L) { return L / FFT_PTS < 32 ? 3
 __host__ __device__ inline size_t stft_smem_bytes(int L) { return (size_t)(L + L / 8 + 1) * sizeof(cplx); }
 __device__ __forceinline__ int pidx(int i) { return i + (i >> 3); }
 
-// tw[q] = exp(-2 pi i q / L), q < L/2
-__global__ void k_twiddles(cplx* __restrict__ tw, int L) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < L / 2) {
-        double s, c;
-        sincospi(-2.0 * (double)q / (double)L, &s, &c);
-        tw[q] = cmake(c, s);
+// Twiddle table of the complex FFT of N = 2^lg points, one compact block per Stockham pass after the first:
+// the pass with Ns = 8^p (p >= 1) and radix R reads, for butterfly phase k < Ns, the record
+//     tw[3 * ((Ns - 8) / 7 + k) + {0, 1, 2}] = w, w^2, w^4,   w = exp(-2 pi i k / (Ns R)),
+// so that consecutive lanes read consecutive 48-byte records (coalesced / conflict-free) instead of gathering
+// from one long table with a stride that changes per pass.
+__host__ __device__ inline int twiddle_records(int lg) {  // sum of Ns over the passes after the first
+    int n = 0, Ns = 8;
+    const int passes = lg / 3 + (lg % 3 ? 1 : 0);
+    for (int p = 1; p < passes; ++p) {
+        n += Ns;
+        Ns *= 8;
+    }
+    return n;
+}
+__global__ void k_twiddles(cplx* __restrict__ tw, int lg, int n_records) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_records) return;
+    int Ns = 8, base = 0, p = 1;
+    while (i >= base + Ns) {
+        base += Ns;
+        Ns *= 8;
+        ++p;
+    }
+    const int k = i - base;
+    const int R = p < lg / 3 ? 8 : (lg % 3 == 0 ? 8 : (lg % 3 == 1 ? 2 : 4));
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        double sn, cs;
+        sincospi(-2.0 * (double)(k << e) / (double)(Ns * R), &sn, &cs);
+        tw[3 * i + e] = cmake(cs, sn);
     }
 }
 
@@ -75,13 +100,12 @@ __device__ __forceinline__ void dft_r(cplx (&v)[R]) {
 }
 
 // One Stockham pass of radix R over the N points in z (padded indexing); Ns = product of the radices done so far.
-// tw: exp(-2 pi i q / N) for q < N/2.  Every thread reads all its butterflies, then (barrier) writes them.
+// tw: the per-pass twiddle records (k_twiddles).  Every thread reads all its butterflies, then (barrier) writes them.
 template <int R>
 __device__ __forceinline__ void stockham_pass(cplx* z, int N, int Ns, const cplx* __restrict__ tw) {
     constexpr int NB = FFT_PTS / R;
     cplx v[NB][R];
     const int nbf = N / R;
-    const int step = N / (Ns * R);
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
         const int j = threadIdx.x + i * blockDim.x;
@@ -90,15 +114,16 @@ __device__ __forceinline__ void stockham_pass(cplx* z, int N, int Ns, const cplx
             for (int r = 0; r < R; ++r) v[i][r] = z[pidx(j + r * nbf)];
             const int k = j & (Ns - 1);
             if (k != 0) {
-                const cplx w1 = __ldg(&tw[k * step]);
+                const cplx* rec = tw + 3 * ((Ns - 8) / 7 + k);
+                const cplx w1 = __ldg(rec);
                 v[i][1] = cmul(v[i][1], w1);
                 if constexpr (R >= 4) {
-                    const cplx w2 = __ldg(&tw[2 * k * step]);
+                    const cplx w2 = __ldg(rec + 1);
                     const cplx w3 = cmul(w1, w2);
                     v[i][2] = cmul(v[i][2], w2);
                     v[i][3] = cmul(v[i][3], w3);
                     if constexpr (R == 8) {
-                        const cplx w4 = __ldg(&tw[4 * k * step]);
+                        const cplx w4 = __ldg(rec + 2);
                         v[i][4] = cmul(v[i][4], w4);
                         v[i][5] = cmul(v[i][5], cmul(w4, w1));
                         v[i][6] = cmul(v[i][6], cmul(w4, w2));
@@ -147,9 +172,23 @@ struct AnalysisParams {
     int grouped;          // 1: Xg[gi][t][c][lane];  0: X (B,T,F,M)
 };
 
-// grid (T * ceil(M/2), B)
-template <typename AT, typename ST>
-__global__ void __launch_bounds__(512) k_stft_analysis(const AnalysisParams p) {
+// pair (x_c0[s], x_c0+1[s]) of interleaved channel-last audio as one aligned 16-byte (fp64) / 8-byte (fp32) load:
+// half the sectors of two scalar loads at a stride of M elements
+__device__ __forceinline__ void load_pair(const double* p, double& a, double& b) {
+    const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+    a = v.x;
+    b = v.y;
+}
+__device__ __forceinline__ void load_pair(const float* p, double& a, double& b) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    a = (double)v.x;
+    b = (double)v.y;
+}
+
+// grid (T * ceil(M/2), B).  MAXT: 256 (frame lengths <= 4096, three CTAs per SM) or 512 (8192).
+// VEC: channel-last audio (stride_c == 1) with an even channel count and an aligned base.
+template <typename AT, typename ST, int MAXT, bool VEC, int MINB>
+__global__ void __launch_bounds__(MAXT, MAXT == 256 ? MINB : 1) k_stft_analysis(const AnalysisParams p) {
     typedef typename StoreC<ST>::type XC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* z = reinterpret_cast<cplx*>(smem_raw);
@@ -161,19 +200,30 @@ __global__ void __launch_bounds__(512) k_stft_analysis(const AnalysisParams p) {
     const AT* xa = reinterpret_cast<const AT*>(p.x) + (size_t)b * p.sb + (size_t)c0 * p.sc;
     const AT* xb = xa + (two ? p.sc : 0);
     const long long n0 = p.first + (long long)t * p.hop;
-    for (int n = threadIdx.x; n < p.L; n += blockDim.x) {
+    // all FFT_PTS samples of a thread are requested before the first one is used (blockDim >= L / FFT_PTS)
+    double va[FFT_PTS], vb[FFT_PTS];
+#pragma unroll
+    for (int i = 0; i < FFT_PTS; ++i) {
+        const int n = threadIdx.x + i * blockDim.x;
         const long long s = n0 + n;
-        double va = 0.0, vb = 0.0;
-        if (s >= 0 && s < p.N) {
-            va = (double)xa[s * p.sn];
-            if (two) vb = (double)xb[s * p.sn];
+        va[i] = 0.0;
+        vb[i] = 0.0;
+        if (n < p.L && s >= 0 && s < p.N) {
+            if constexpr (VEC) {
+                load_pair(xa + s * p.sn, va[i], vb[i]);
+            } else {
+                va[i] = (double)xa[s * p.sn];
+                if (two) vb[i] = (double)xb[s * p.sn];
+            }
         }
-        if (p.win) {
-            const double w = __ldg(&p.win[n]);
-            va *= w;
-            vb *= w;
+    }
+#pragma unroll
+    for (int i = 0; i < FFT_PTS; ++i) {
+        const int n = threadIdx.x + i * blockDim.x;
+        if (n < p.L) {
+            const double w = p.win ? __ldg(&p.win[n]) : 1.0;
+            z[pidx(n)] = cmake(va[i] * w, vb[i] * w);
         }
-        z[pidx(n)] = cmake(va, vb);
     }
     __syncthreads();
     fft_forward(z, p.lg, p.tw);
@@ -212,8 +262,8 @@ struct SynthesisParams {
 };
 
 // grid (T * ceil(K/2), B): irfft of two sources through one complex FFT (inverse = conj o forward o conj)
-template <typename ST>
-__global__ void __launch_bounds__(512) k_stft_frames(const SynthesisParams p) {
+template <typename ST, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MAXT == 256 ? MINB : 1) k_stft_frames(const SynthesisParams p) {
     typedef typename StoreC<ST>::type XC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* z = reinterpret_cast<cplx*>(smem_raw);
@@ -225,15 +275,30 @@ __global__ void __launch_bounds__(512) k_stft_frames(const SynthesisParams p) {
     const int half = p.L / 2;
     const XC* Y = reinterpret_cast<const XC*>(p.Y) + ((size_t)b * p.T + t) * p.F * p.K + k0;
     // Z[q] = Xa[q] + i Xb[q] (q <= L/2),  Z[L-q] = conj Xa[q] + i conj Xb[q];  the buffer receives conj Z
-    for (int q = threadIdx.x; q <= half; q += blockDim.x) {
-        cplx xa = widen(Y[(size_t)q * p.K]);
-        cplx xb = two ? widen(Y[(size_t)q * p.K + 1]) : cmake(0.0, 0.0);
-        if (q == 0 || q == half) {  // numpy.fft.irfft ignores the imaginary parts of the DC and Nyquist bins
-            xa.y = 0.0;
-            xb.y = 0.0;
+    constexpr int NQ = FFT_PTS / 2 + 1;  // ceil((L/2 + 1) / blockDim) for blockDim >= L / FFT_PTS
+    cplx ya[NQ], yb[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+        const int q = threadIdx.x + i * blockDim.x;
+        ya[i] = cmake(0.0, 0.0);
+        yb[i] = cmake(0.0, 0.0);
+        if (q <= half) {
+            ya[i] = widen(Y[(size_t)q * p.K]);
+            if (two) yb[i] = widen(Y[(size_t)q * p.K + 1]);
         }
-        z[pidx(q)] = cmake(xa.x - xb.y, -(xa.y + xb.x));
-        if (q != 0 && q != half) z[pidx(p.L - q)] = cmake(xa.x + xb.y, -(xb.x - xa.y));
+    }
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+        const int q = threadIdx.x + i * blockDim.x;
+        if (q <= half) {
+            cplx xa = ya[i], xb = yb[i];
+            if (q == 0 || q == half) {  // numpy.fft.irfft ignores the imaginary parts of the DC and Nyquist bins
+                xa.y = 0.0;
+                xb.y = 0.0;
+            }
+            z[pidx(q)] = cmake(xa.x - xb.y, -(xa.y + xb.x));
+            if (q != 0 && q != half) z[pidx(p.L - q)] = cmake(xa.x + xb.y, -(xb.x - xa.y));
+        }
     }
     __syncthreads();
     fft_forward(z, p.lg, p.tw);
@@ -276,12 +341,23 @@ int log2_exact(int v) {
 
 }  // namespace
 
+extern "C" size_t oiva_stft_twiddle_bytes(int frame_len) {
+    const int lg = log2_exact(frame_len);
+    if (lg < 3 || frame_len > 8192) return 0;
+    const size_t n = 3 * (size_t)twiddle_records(lg) * sizeof(cplx);
+    return n ? n : sizeof(cplx);
+}
+
 extern "C" int oiva_stft_twiddles(void* tw, int frame_len, void* stream) {
     OIVA_REQUIRE(tw, "oiva_stft_twiddles: null pointer");
-    OIVA_REQUIRE(log2_exact(frame_len) >= 3 && frame_len <= 8192, "oiva_stft_twiddles: frame_len=%d must be a power of two in 8..8192",
+    const int lg = log2_exact(frame_len);
+    OIVA_REQUIRE(lg >= 3 && frame_len <= 8192, "oiva_stft_twiddles: frame_len=%d must be a power of two in 8..8192",
                  frame_len);
-    k_twiddles<<<oiva_div_up(frame_len / 2, 256), 256, 0, (cudaStream_t)stream>>>((cplx*)tw, frame_len);
-    OIVA_LAUNCH_CHECK();
+    const int n = twiddle_records(lg);
+    if (n > 0) {
+        k_twiddles<<<oiva_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>((cplx*)tw, lg, n);
+        OIVA_LAUNCH_CHECK();
+    }
     return OIVA_OK;
 }
 
@@ -326,11 +402,31 @@ extern "C" int oiva_stft_analysis(const void* x, int x_f32, long long stride_b, 
     const size_t smem = stft_smem_bytes(frame_len);
     dim3 grid((unsigned)((long long)n_frames * ((n_chan + 1) / 2)), n_batch);
     cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH_A(AT, ST)                                                                                           \
-    do {                                                                                                           \
-        OIVA_CUDA_CHECK(cudaFuncSetAttribute(k_stft_analysis<AT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             (int)stft_smem_bytes(8192)));                                         \
-        k_stft_analysis<AT, ST><<<grid, stft_threads(frame_len), smem, st>>>(p);                                   \
+    const bool vec = stride_c == 1 && (n_chan % 2) == 0 && (stride_n % 2) == 0 && (stride_b % 2) == 0 &&
+                     ((uintptr_t)x % (x_f32 ? 8 : 16)) == 0;
+    // resident CTAs per SM for frame lengths <= 4096: 2 leaves ~90 KB of L1 for the twiddle / window tables,
+    // 3 hides more barrier latency but shrinks L1 to its minimum (OIVA_STFT_CTAS=2|3)
+    static const int ctas = [] {
+        const char* v = getenv("OIVA_STFT_CTAS");
+        return (v && *v == '3') ? 3 : 2;
+    }();
+#define LAUNCH_A3(AT, ST, MAXT, VEC, MINB)                                                                           \
+    do {                                                                                                             \
+        auto kern = k_stft_analysis<AT, ST, MAXT, VEC, MINB>;                                                        \
+        OIVA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                      \
+                                             (int)stft_smem_bytes(MAXT * FFT_PTS)));                                 \
+        if (MINB == 3)                                                                                               \
+            OIVA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));        \
+        kern<<<grid, stft_threads(frame_len), smem, st>>>(p);                                                        \
+    } while (0)
+#define LAUNCH_A2(AT, ST, MAXT, VEC)                                                                                 \
+    do {                                                                                                             \
+        if (MAXT == 256 && ctas == 3) LAUNCH_A3(AT, ST, MAXT, VEC, 3); else LAUNCH_A3(AT, ST, MAXT, VEC, 2);         \
+    } while (0)
+#define LAUNCH_A(AT, ST)                                                                                             \
+    do {                                                                                                             \
+        if (frame_len > 4096) { if (vec) LAUNCH_A2(AT, ST, 512, true); else LAUNCH_A2(AT, ST, 512, false); }         \
+        else { if (vec) LAUNCH_A2(AT, ST, 256, true); else LAUNCH_A2(AT, ST, 256, false); }                          \
     } while (0)
     if (x_f32) {
         if (dtype == OIVA_C64) LAUNCH_A(float, float); else LAUNCH_A(float, double);
@@ -338,6 +434,8 @@ extern "C" int oiva_stft_analysis(const void* x, int x_f32, long long stride_b, 
         if (dtype == OIVA_C64) LAUNCH_A(double, float); else LAUNCH_A(double, double);
     }
 #undef LAUNCH_A
+#undef LAUNCH_A2
+#undef LAUNCH_A3
     OIVA_LAUNCH_CHECK();
     return OIVA_OK;
 }
@@ -371,15 +469,30 @@ extern "C" int oiva_stft_synthesis(const void* Y, const double* win, const void*
     const size_t smem = stft_smem_bytes(frame_len);
     dim3 grid((unsigned)((long long)n_frames * ((n_src + 1) / 2)), n_batch);
     cudaStream_t st = (cudaStream_t)stream;
+    static const int ctas = [] {
+        const char* v = getenv("OIVA_STFT_CTAS");
+        return (v && *v == '3') ? 3 : 2;
+    }();
+#define LAUNCH_S2(ST, MAXT, MINB)                                                                            \
+    do {                                                                                                     \
+        auto kern = k_stft_frames<ST, MAXT, MINB>;                                                           \
+        OIVA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                             (int)stft_smem_bytes(MAXT * FFT_PTS)));                         \
+        if (MINB == 3)                                                                                       \
+            OIVA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
+        kern<<<grid, stft_threads(frame_len), smem, st>>>(p);                                                \
+    } while (0)
+#define LAUNCH_S(ST, MAXT)                                                                                   \
+    do {                                                                                                     \
+        if (MAXT == 256 && ctas == 3) LAUNCH_S2(ST, MAXT, 3); else LAUNCH_S2(ST, MAXT, 2);                   \
+    } while (0)
     if (dtype == OIVA_C64) {
-        OIVA_CUDA_CHECK(cudaFuncSetAttribute(k_stft_frames<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)stft_smem_bytes(8192)));
-        k_stft_frames<float><<<grid, stft_threads(frame_len), smem, st>>>(p);
+        if (frame_len > 4096) LAUNCH_S(float, 512); else LAUNCH_S(float, 256);
     } else {
-        OIVA_CUDA_CHECK(cudaFuncSetAttribute(k_stft_frames<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)stft_smem_bytes(8192)));
-        k_stft_frames<double><<<grid, stft_threads(frame_len), smem, st>>>(p);
+        if (frame_len > 4096) LAUNCH_S(double, 512); else LAUNCH_S(double, 256);
     }
+#undef LAUNCH_S
+#undef LAUNCH_S2
     OIVA_LAUNCH_CHECK();
     const long long n_out = (long long)(n_frames - 1) * hop + frame_len;
     dim3 g2((unsigned)oiva_div_up(n_out * n_src, 256), n_batch);

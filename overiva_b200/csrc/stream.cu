@@ -36,35 +36,54 @@ __global__ void k_sum_partials(const double* __restrict__ part, double* __restri
 }
 
 // one CTA per (mixture, source): statistic -> r -> gamma -> phi, wscale        (overiva.py:152-173)
+// 256 threads = 32 frame lanes x 8 slices of the partial sums: a thread adds every 8th partial of its frames (8
+// independent loads in flight per thread instead of a serial chain over all NCH partials -- this kernel sits on
+// the critical path of every epoch and is pure latency), the slices are combined through shared memory in a fixed
+// order (deterministic).
 __global__ void __launch_bounds__(256) k_source_model(const double* __restrict__ part, int NCH, double* __restrict__ phi,
                                                       double* __restrict__ wscale, int T, int Tp, int K, int F_total,
                                                       int model) {
-    __shared__ double red[256];
+    __shared__ double slice[8][32];
+    __shared__ double red[8];
     const int b = blockIdx.x / K, k = blockIdx.x - b * K;
+    const int tl = threadIdx.x & 31, cs = threadIdx.x >> 5;
     double* ph = phi + ((size_t)b * K + k) * Tp;
+    const double* pb = part + ((size_t)b * NCH * K + k) * Tp;
     double lsum = 0.0;
-    for (int t = threadIdx.x; t < Tp; t += 256) {
-        double r = 0.0;
+    for (int t0 = 0; t0 < Tp; t0 += 32) {
+        const int t = t0 + tl;  // Tp is a multiple of 32
+        double s = 0.0;
         if (t < T) {
-            double s = 0.0;
-            for (int ch = 0; ch < NCH; ++ch) s += part[(((size_t)b * NCH + ch) * K + k) * Tp + t];
-            switch (model) {
-                case OIVA_MODEL_LAPLACE: r = 2.0 * sqrt(s); break;
-                case OIVA_MODEL_GAUSS: r = s / (double)F_total; break;
-                case OIVA_MODEL_OGIVE_LAPLACE: r = sqrt(s) / sqrt((double)F_total); break;
-                case OIVA_MODEL_OGIVE_GAUSS: r = s / (double)F_total; break;
-                default: r = 0.0; break;
-            }
-            lsum += r;
+#pragma unroll 4
+            for (int ch = cs; ch < NCH; ch += 8) s += pb[(size_t)ch * K * Tp + t];
         }
-        ph[t] = r;
-    }
-    red[threadIdx.x] = lsum;
-    __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) {
-        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        slice[cs][tl] = s;
+        __syncthreads();
+        if (cs == 0) {
+            double r = 0.0;
+            if (t < T) {
+                s = ((slice[0][tl] + slice[1][tl]) + (slice[2][tl] + slice[3][tl])) +
+                    ((slice[4][tl] + slice[5][tl]) + (slice[6][tl] + slice[7][tl]));
+                switch (model) {
+                    case OIVA_MODEL_LAPLACE: r = 2.0 * sqrt(s); break;
+                    case OIVA_MODEL_GAUSS: r = s / (double)F_total; break;
+                    case OIVA_MODEL_OGIVE_LAPLACE: r = sqrt(s) / sqrt((double)F_total); break;
+                    case OIVA_MODEL_OGIVE_GAUSS: r = s / (double)F_total; break;
+                    default: r = 0.0; break;
+                }
+                lsum += r;
+            }
+            ph[t] = r;
+        }
         __syncthreads();
     }
+    // gamma = mean_t r: warp 0 holds the per-lane sums
+    if (cs == 0) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+        if (tl == 0) red[0] = lsum;
+    }
+    __syncthreads();
     const bool rescale = (model == OIVA_MODEL_LAPLACE || model == OIVA_MODEL_GAUSS || model == OIVA_MODEL_NONE);
     const double gamma = rescale ? red[0] / (double)T : 1.0;
     for (int t = threadIdx.x; t < Tp; t += 256) {

@@ -56,7 +56,10 @@ def _twiddles(frame_len, device):
     key = (int(frame_len), torch.device(device).index)
     tw = _TW_CACHE.get(key)
     if tw is None:
-        tw = torch.empty(frame_len // 2, dtype=torch.complex128, device=device)
+        nbytes = L.load().oiva_stft_twiddle_bytes(int(frame_len))
+        if nbytes == 0:
+            raise ValueError("frame length %d must be a power of two in 8..8192" % frame_len)
+        tw = torch.empty(nbytes // 16, dtype=torch.complex128, device=device)
         L.check(L.load().oiva_stft_twiddles(core._ptr(tw), int(frame_len), core._stream_ptr(device)),
                 "oiva_stft_twiddles")
         _TW_CACHE[key] = tw
@@ -193,7 +196,7 @@ _ALGOS = ("overiva", "auxiva", "auxiva_pca", "ogive")
 
 
 def separate_batch(mix, n_src=None, n_iter=20, framesize=4096, hop=None, win_a=None, win_s=None, model="laplace",
-                   init_eig=False, proj_back=True, pad_front=0, pad_back=0, chunk=64, out=None,
+                   init_eig=False, proj_back=True, pad_front=0, pad_back=0, chunk=32, out=None,
                    dtype=torch.complex128):
     """Host-resident batch of mixtures, audio in -> audio out: mix (B, N, M) real numpy / CPU tensor (pin it for
     full PCIe speed) -> y (B, N', K).  Chunks of ``chunk`` mixtures stream through the GPU with the H2D copy of

@@ -109,7 +109,7 @@ def main():
         best = min(best, time.perf_counter() - t0)
     res["e2e_audio"] = {"value": B * args.seconds / best, "unit": "mixture-s/s", "ms": best * 1e3,
                         "h2d_bytes_per_step": xh.numel() * 8, "d2h_bytes_per_step": yh.numel() * 8,
-                        "api": "overiva_b200.stft.separate_batch(pinned host audio, out=pinned): chunks of 64"}
+                        "api": "overiva_b200.stft.separate_batch(pinned host audio, out=pinned): chunks of 32"}
     print(json.dumps(res))
 
 

@@ -76,6 +76,9 @@ def test_num_frames_and_argument_checks():
     assert lib.oiva_stft_analysis(one, 0, 0, 1, 1, 100, 0, None, one, one, 0, 1, 1, 1, 64, 0, 0, None) == -1  # hop 0
     assert lib.oiva_stft_synthesis(one, None, one, one, one, 0, 1, 1, 1, 16384, 64, 0, None) == -1  # frame too long
     assert lib.oiva_stft_scratch_bytes(2, 3, 4, 64) == 2 * 3 * 4 * 64 * 8
+    # one 48-byte record (w, w^2, w^4) per butterfly phase of every FFT pass after the first: 8 + 64 + 512 at 4096
+    assert lib.oiva_stft_twiddle_bytes(4096) == 3 * (8 + 64 + 512) * 16
+    assert lib.oiva_stft_twiddle_bytes(64) == 3 * 8 * 16 and lib.oiva_stft_twiddle_bytes(100) == 0
 
 
 def test_no_cpu_fallback():
@@ -147,7 +150,7 @@ def test_grouped_output_equals_relayout_of_plain_output(cdt):
     code = L.C64 if cdt == np.complex64 else L.C128
     got = torch.full((lib.oiva_grouped_bytes(B, T, F, M, code),), 0xFF, dtype=torch.uint8, device=dev())
     win = torch.from_numpy(so.hann(L_)).to(dev())
-    tw = torch.empty(L_ // 2, dtype=torch.complex128, device=dev())
+    tw = torch.empty(lib.oiva_stft_twiddle_bytes(L_) // 16, dtype=torch.complex128, device=dev())
     L.check(lib.oiva_stft_twiddles(P(tw), L_, stream()), "tw")
     L.check(lib.oiva_stft_analysis(P(xd), 0, N * M, M, 1, N, 0, P(win), P(tw), P(got), 1, B, T, M, L_, hop, code,
                                    stream()), "analysis")
