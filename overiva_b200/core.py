@@ -55,7 +55,10 @@ class _Input:
                 raise TypeError("X must be a complex STFT array, got dtype %s" % X.dtype)
             if X.dtype not in (np.complex128, np.complex64):
                 X = X.astype(np.complex128)
-            t = torch.from_numpy(np.ascontiguousarray(X))
+            X = np.ascontiguousarray(X)
+            if not X.flags.writeable:  # torch refuses read-only buffers; the input is never written to anyway
+                X = X.copy()
+            t = torch.from_numpy(X)
         if t.dtype not in (torch.complex128, torch.complex64):
             raise TypeError("X must be complex64 or complex128, got %s" % t.dtype)
         self.device = _require_cuda(t.device if t.is_cuda else device)

@@ -325,7 +325,7 @@ extern "C" int oiva_ip_update(void* What, const void* V, const void* C, const vo
     cudaStream_t st = (cudaStream_t)stream;
     const char* env = getenv("OIVA_SOLVER_ROWOWNER");
     const bool force_rowowner = env && *env && *env != '0';
-    if (Cg && n_chan <= 6 && !force_rowowner) {  // thread-per-bin sweep (solve_tpb.cuh)
+    if (Cg && n_chan <= 8 && !force_rowowner) {  // thread-per-bin sweep (solve_tpb.cuh) where instantiated
         const int NG = oiva_bin_groups(n_freq);
         int rc = ip_update_tpb(n_chan, n_src, (cplx*)What, (const cplx*)V, (const cplx*)Cg, wscale, status, n_freq, NG,
                                (long long)n_batch * NG, st);

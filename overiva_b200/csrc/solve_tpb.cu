@@ -1,4 +1,4 @@
-// Instantiations + launcher of the thread-per-bin IP sweep (solve_tpb.cuh) for M <= 6, K <= M.
+// Instantiations + launcher of the thread-per-bin IP sweep (solve_tpb.cuh) for M <= 6, K <= M and M = 7, 8 with K <= 4.
 #include <stdlib.h>
 
 #include "solve_tpb.cuh"
@@ -42,6 +42,10 @@ int ip_update_tpb(int M, int K, cplx* What, const cplx* Vg, const cplx* Cg, cons
     OIVA_TPB(4, 1) OIVA_TPB(4, 2) OIVA_TPB(4, 3) OIVA_TPB(4, 4)
     OIVA_TPB(5, 1) OIVA_TPB(5, 2) OIVA_TPB(5, 3) OIVA_TPB(5, 4) OIVA_TPB(5, 5)
     OIVA_TPB(6, 1) OIVA_TPB(6, 2) OIVA_TPB(6, 3) OIVA_TPB(6, 4) OIVA_TPB(6, 5) OIVA_TPB(6, 6)
+    // 7 and 8 channels: the overdetermined sweep only (Cholesky of V in registers + a K x K solve, K <= 4); the
+    // determined LU of an 8 x 8 complex system does not fit one thread's registers and stays with the row-owner kernel
+    OIVA_TPB(7, 1) OIVA_TPB(7, 2) OIVA_TPB(7, 3) OIVA_TPB(7, 4)
+    OIVA_TPB(8, 1) OIVA_TPB(8, 2) OIVA_TPB(8, 3) OIVA_TPB(8, 4)
 #undef OIVA_TPB
     return OIVA_ERR_INVALID;
 }
