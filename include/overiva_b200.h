@@ -82,6 +82,13 @@ int oiva_relayout(const void* X, void* Xg, int n_batch, int n_frames, int n_freq
  * auxiva_pca.py:71 (phi == NULL). */
 int oiva_weighted_cov(const void* Xg, const double* phi, void* Vg, int n_batch, int n_frames, int n_freq,
                       int n_chan, int n_src, int dtype, void* stream);
+/* Same, with caller-provided scratch (oiva_weighted_cov_scratch_bytes(); may be 0 = not needed).  Inputs with few bin
+ * groups (a single mixture) split the frames of a group over several thread teams to fill the GPU: with scratch every
+ * split writes its partial sum to its own slot and the slots are added in a fixed order (bit-reproducible results);
+ * without it (oiva_weighted_cov) the partial sums are combined with fp64 atomics, whose order is not fixed. */
+size_t oiva_weighted_cov_scratch_bytes(int n_batch, int n_frames, int n_freq, int n_chan, int n_src);
+int oiva_weighted_cov_ws(const void* Xg, const double* phi, void* Vg, void* scratch, size_t scratch_bytes,
+                         int n_batch, int n_frames, int n_freq, int n_chan, int n_src, int dtype, void* stream);
 
 /* per-bin arrays of n_elems c128 each: row-major (R, n_elems) <-> grouped [gi][n_elems][32] (padded bins: 0).
  * Inside the loop the demixing matrices live in the grouped form (coalesced for lane <-> bin kernels). */

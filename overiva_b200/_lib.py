@@ -44,6 +44,8 @@ SIGNATURES = {
     "oiva_grouped_cov_bytes": (_sz, [_i, _i, _i, _i]),
     "oiva_relayout": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "oiva_weighted_cov": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "oiva_weighted_cov_scratch_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "oiva_weighted_cov_ws": (_i, [_p, _p, _p, _p, _sz, _i, _i, _i, _i, _i, _i, _p]),
     "oiva_unpack_cov": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "oiva_demix_power": (_i, [_p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
     "oiva_group_rows": (_i, [_p, _p, _i, _i, _i, _p]),

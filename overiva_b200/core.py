@@ -569,6 +569,8 @@ def ogive(X, n_iter=4000, step_size=0.1, tol=1e-3, update="demix", proj_back=Tru
         r2part = torch.empty((nch, Tp), dtype=torch.float64, device=dev)
         phi = torch.empty((Tp,), dtype=torch.float64, device=dev)
         Vg = torch.empty(lib.oiva_grouped_cov_bytes(1, F, M, 1), dtype=torch.uint8, device=dev)
+        cov_ws_bytes = lib.oiva_weighted_cov_scratch_bytes(1, T, F, M, 1)
+        cov_ws = torch.empty(max(cov_ws_bytes, 16), dtype=torch.uint8, device=dev)
         V = torch.empty((F, M, M), **c128)
         dmax = torch.zeros((1,), dtype=torch.float64, device=dev)
 
@@ -591,8 +593,8 @@ def ogive(X, n_iter=4000, step_size=0.1, tol=1e-3, update="demix", proj_back=Tru
                     "oiva_demix_power")
             L.check(lib.oiva_source_model(_ptr(r2part), nch, _ptr(phi), None, 1, T, 1, F, mcode, st),
                     "oiva_source_model")
-            L.check(lib.oiva_weighted_cov(plan.samples_ptr, _ptr(phi), _ptr(Vg), 1, T, F, M, 1, code, st),
-                    "oiva_weighted_cov")
+            L.check(lib.oiva_weighted_cov_ws(plan.samples_ptr, _ptr(phi), _ptr(Vg), _ptr(cov_ws), cov_ws_bytes, 1, T, F,
+                                             M, 1, code, st), "oiva_weighted_cov_ws")
             L.check(lib.oiva_unpack_cov(_ptr(Vg), _ptr(V), 1, F, M, 1, st), "oiva_unpack_cov")
             dmax.zero_()
             L.check(lib.oiva_ogive_update(_ptr(w), _ptr(a), _ptr(lam), _ptr(V), _ptr(Cx), _ptr(Cinv), _ptr(do_a),

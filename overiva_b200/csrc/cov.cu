@@ -5,7 +5,7 @@
 
 namespace oiva {
 #define OIVA_DECL(M)                                                                                 \
-    int cov_launch_m##M(int dtype, int KC, int use_tma, const CovParams& p, cudaStream_t st);        \
+    int cov_launch_m##M(int dtype, int KC, int use_tma, const CovParams& p, cudaStream_t st, int* nsplit_out); \
     int cov_max_kc_m##M();
 OIVA_DECL(1) OIVA_DECL(2) OIVA_DECL(3) OIVA_DECL(4) OIVA_DECL(5) OIVA_DECL(6) OIVA_DECL(7) OIVA_DECL(8)
 OIVA_DECL(9) OIVA_DECL(10) OIVA_DECL(11) OIVA_DECL(12) OIVA_DECL(13) OIVA_DECL(14) OIVA_DECL(15) OIVA_DECL(16)
@@ -35,6 +35,19 @@ static int get_ones(size_t n, cudaStream_t st, const double** out) {
     return OIVA_OK;
 }
 
+// Vg[i] = sum_sp Vpart[sp][i], sp ascending: the deterministic combination of the frame-split partial sums
+__global__ void k_cov_sum_partials(const cplx* __restrict__ part, cplx* __restrict__ Vg, int nsplit, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cplx s = part[i];
+    for (int sp = 1; sp < nsplit; ++sp) {
+        const cplx v = part[(size_t)sp * n + i];
+        s.x += v.x;
+        s.y += v.y;
+    }
+    Vg[i] = s;
+}
+
 static int pick_chunk(int rem, int max_kc) {
     static const int sizes[] = {1, 2, 3, 4, 6, 8};
     int best = 1;
@@ -47,8 +60,22 @@ static int pick_chunk(int rem, int max_kc) {
 }
 }  // namespace oiva
 
-extern "C" int oiva_weighted_cov(const void* Xg, const double* phi, void* Vg, int n_batch, int n_frames, int n_freq,
-                                 int n_chan, int n_src, int dtype, void* stream) {
+extern "C" size_t oiva_weighted_cov_scratch_bytes(int n_batch, int n_frames, int n_freq, int n_chan, int n_src) {
+    // frame splitting only happens when there are few bin groups; 64 slots or 128 MiB, whichever is smaller, keeps
+    // every SM busy for the shapes that need it (the split count is clamped to the slots available)
+    const size_t vg = oiva_grouped_cov_bytes(n_batch, n_freq, n_chan, n_src);
+    if (vg == 0 || n_frames <= 0) return 0;
+    const long long G = (long long)n_batch * oiva_bin_groups(n_freq);
+    if (G >= 4096) return 0;  // enough groups for every team of every SM: never split
+    size_t slots = 64;
+    const size_t cap = (size_t)128 << 20;
+    if (slots * vg > cap) slots = cap / vg;
+    return slots < 2 ? 0 : slots * vg;
+}
+
+extern "C" int oiva_weighted_cov_ws(const void* Xg, const double* phi, void* Vg, void* scratch, size_t scratch_bytes,
+                                    int n_batch, int n_frames, int n_freq, int n_chan, int n_src, int dtype,
+                                    void* stream) {
     using namespace oiva;
     OIVA_REQUIRE(Xg && Vg, "oiva_weighted_cov: null pointer");
     OIVA_REQUIRE(n_batch > 0 && n_frames > 0 && n_freq > 0 && n_chan >= 1 && n_chan <= OIVA_MAX_M && n_src >= 1,
@@ -63,8 +90,16 @@ extern "C" int oiva_weighted_cov(const void* Xg, const double* phi, void* Vg, in
     p.NGphi = p.L.NG;
     p.K = n_src;
     p.invT = 1.0 / (double)n_frames;
-    p.nsplit = 1;
+    p.nsplit = 0;  // chosen by the first pass
     p.stages = 4;
+    const size_t vg_bytes = oiva_grouped_cov_bytes(n_batch, n_freq, n_chan, n_src);
+    p.Vpart = nullptr;
+    p.max_split = 1;
+    if (scratch && scratch_bytes >= 2 * vg_bytes) {
+        p.Vpart = (cplx*)scratch;
+        const size_t slots = scratch_bytes / vg_bytes;
+        p.max_split = slots > 4096 ? 4096 : (int)slots;
+    }
     if (phi) {
         p.phi = phi;
     } else {
@@ -91,15 +126,27 @@ extern "C" int oiva_weighted_cov(const void* Xg, const double* phi, void* Vg, in
         if (!use_tma && KC > n_src - k0) KC = n_src - k0 >= 2 ? 2 : 1;
         p.k0 = k0;
         int rc = OIVA_ERR_INVALID;
+        int nsplit_used = 0;
         switch (n_chan) {
-#define OIVA_CASE(M) case M: rc = cov_launch_m##M(dtype, KC, use_tma, p, st); break;
+#define OIVA_CASE(M) case M: rc = cov_launch_m##M(dtype, KC, use_tma, p, st, &nsplit_used); break;
             OIVA_CASE(1) OIVA_CASE(2) OIVA_CASE(3) OIVA_CASE(4) OIVA_CASE(5) OIVA_CASE(6) OIVA_CASE(7) OIVA_CASE(8)
             OIVA_CASE(9) OIVA_CASE(10) OIVA_CASE(11) OIVA_CASE(12) OIVA_CASE(13) OIVA_CASE(14) OIVA_CASE(15)
             OIVA_CASE(16)
 #undef OIVA_CASE
         }
         if (rc) return rc;
+        p.nsplit = nsplit_used;  // later passes keep the first pass's split
         k0 += KC;
     }
+    if (p.Vpart && p.nsplit > 1) {
+        const size_t n = vg_bytes / sizeof(cplx);
+        k_cov_sum_partials<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.Vpart, p.Vg, p.nsplit, n);
+        OIVA_LAUNCH_CHECK();
+    }
     return OIVA_OK;
+}
+
+extern "C" int oiva_weighted_cov(const void* Xg, const double* phi, void* Vg, int n_batch, int n_frames, int n_freq,
+                                 int n_chan, int n_src, int dtype, void* stream) {
+    return oiva_weighted_cov_ws(Xg, phi, Vg, nullptr, 0, n_batch, n_frames, n_freq, n_chan, n_src, dtype, stream);
 }

@@ -15,7 +15,9 @@
 //    (entry e belongs to part e % P; a warp's part is compile-time, so register indexing is static).
 //  * at the end of the group the lane writes its entries, scaled by 1/T, to the grouped lower-triangle
 //    layout Vg[gi][k][e][lane] (512-byte coalesced stores).  Few-groups / long-mixture inputs split the
-//    frames of a group over several teams and add the partial sums atomically.
+//    frames of a group over several teams; each split writes its partial sum to its own slot of a scratch buffer
+//    and a second tiny kernel adds the slots in a fixed order (bit-reproducible), or, without scratch, the partial
+//    sums are added atomically into a zeroed Vg.
 #pragma once
 #include <type_traits>
 
@@ -63,11 +65,13 @@ struct CovParams {
     const void* Xg;      // grouped samples
     const double* phi;   // (B, K, Tp)
     cplx* Vg;            // (G, K, NE, 32)
+    cplx* Vpart;         // (nsplit, G, K, NE, 32) per-split partial sums (deterministic mode), or nullptr: atomics into Vg
     GroupLayout L;
     long long G;         // groups in total = B * NG
     int NGphi;           // groups per phi block (NG, or G when one block of ones serves every group)
     int K, k0;
-    int nsplit;          // >1: the frames of a group are split over several teams (atomic accumulation)
+    int nsplit;          // >1: the frames of a group are split over several teams; <= 0 on entry of the launcher: choose
+    int max_split;       // largest split count the scratch buffer has slots for
     int stages;          // ring depth S
     double invT;
 };
@@ -220,7 +224,7 @@ __device__ __forceinline__ void cov_team_body(const CovParams& p, unsigned char*
         const int sp = u - gi * nsplit;
         const int c0 = nsplit == 1 ? 0 : (int)((long long)nchunks * sp / nsplit);
         const int c1 = nsplit == 1 ? nchunks : (int)((long long)nchunks * (sp + 1) / nsplit);
-        if (c0 >= c1) continue;
+        if (c0 >= c1 && !(nsplit > 1 && p.Vpart)) continue;  // (a partial buffer slot must always be written)
         cplx acc[CP::NACC][KC];
 #pragma unroll
         for (int n = 0; n < CP::NACC; ++n)
@@ -254,7 +258,11 @@ __device__ __forceinline__ void cov_team_body(const CovParams& p, unsigned char*
                 CP::accumulate(acc, Xg + (size_t)gi * group_elems + (size_t)t0 * frame_elems, phl, nfr, lane, part);
             }
         }
-        CP::finish(acc, p.Vg + (size_t)gi * p.K * CP::NE * OIVA_GROUP, p.k0, p.K, p.invT, nsplit > 1, lane, part);
+        const size_t grp_elems = (size_t)p.K * CP::NE * OIVA_GROUP;
+        if (nsplit > 1 && p.Vpart)  // this split's own slot, summed in a fixed order by k_cov_sum_partials
+            CP::finish(acc, p.Vpart + ((size_t)sp * p.G + gi) * grp_elems, p.k0, p.K, p.invT, false, lane, part);
+        else
+            CP::finish(acc, p.Vg + (size_t)gi * grp_elems, p.k0, p.K, p.invT, nsplit > 1, lane, part);
     }
 }
 

@@ -23,7 +23,7 @@ constexpr bool COV_USE_BLOCKS = OIVA_COV_M >= 9;
 // shared launch logic: ring sizing, persistent grid, frame splitting for few groups
 template <typename Kern, typename Launch>
 static int launch_common(Kern kern, CovParams p, cudaStream_t st, int P, int teams_max, size_t stage_bytes, int TC,
-                         int M, int KC, bool tma, bool& attr_done, Launch do_launch) {
+                         int M, int KC, bool tma, bool& attr_done, int* nsplit_out, Launch do_launch) {
     int dev = 0, sms = 148;
     OIVA_CUDA_CHECK(cudaGetDevice(&dev));
     OIVA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -58,15 +58,21 @@ static int launch_common(Kern kern, CovParams p, cudaStream_t st, int P, int tea
     OIVA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     if (occ < 1) occ = 1;
     const long long max_ctas = (long long)sms * occ;
-    // few groups: split the frames of a group over several teams (atomic accumulation into zeroed Vg)
+    // few groups: split the frames of a group over several teams; the partial sums go to per-split slots of the
+    // caller's scratch (summed in a fixed order afterwards) or, without scratch, atomically into a zeroed Vg.
+    // All source-chunk passes of one call use the split count chosen by the first pass (p.nsplit preset > 0).
     const int nchunks = (p.L.T + TC - 1) / TC;
-    p.nsplit = 1;
-    if (p.G < 2 * max_ctas * teams && nchunks > 1) {
-        long long want = (2 * max_ctas * teams + p.G - 1) / p.G;
-        p.nsplit = (int)(want < nchunks ? want : nchunks);
+    if (p.nsplit <= 0) {
+        p.nsplit = 1;
+        if (p.G < 2 * max_ctas * teams && nchunks > 1) {
+            long long want = (2 * max_ctas * teams + p.G - 1) / p.G;
+            p.nsplit = (int)(want < nchunks ? want : nchunks);
+        }
+        if (p.Vpart && p.nsplit > p.max_split) p.nsplit = p.max_split < 1 ? 1 : p.max_split;
+        if (p.nsplit > 1 && !p.Vpart)
+            OIVA_CUDA_CHECK(cudaMemsetAsync(p.Vg, 0, (size_t)p.G * p.K * oiva_tri(M) * OIVA_GROUP * sizeof(cplx), st));
     }
-    if (p.nsplit > 1 && p.k0 == 0)
-        OIVA_CUDA_CHECK(cudaMemsetAsync(p.Vg, 0, (size_t)p.G * p.K * oiva_tri(M) * OIVA_GROUP * sizeof(cplx), st));
+    if (nsplit_out) *nsplit_out = p.nsplit;
     const long long U = p.G * p.nsplit;
     long long grid = (U + teams - 1) / teams;
     if (grid > max_ctas) grid = max_ctas;
@@ -78,7 +84,7 @@ static int launch_common(Kern kern, CovParams p, cudaStream_t st, int P, int tea
 }
 
 template <typename ST, int KC, bool TMA>
-static int launch(CovParams p, cudaStream_t st) {
+static int launch(CovParams p, cudaStream_t st, int* nsplit_out) {
     constexpr int M = OIVA_COV_M;
     typedef typename StoreC<ST>::type XC;
     constexpr int TC = cov_chunk_frames(M);
@@ -92,7 +98,7 @@ static int launch(CovParams p, cudaStream_t st) {
             constexpr int P = cov_block_parts(M);
             auto kern = k_cov_blocked<ST, M, KC, TMA>;
             static bool attr_done = false;
-            return launch_common(kern, p, st, P, 1, stage_bytes, TC, M, KC, TMA, attr_done,
+            return launch_common(kern, p, st, P, 1, stage_bytes, TC, M, KC, TMA, attr_done, nsplit_out,
                                  [&](const CovParams& q, unsigned grid, int threads, size_t smem, int, int team_smem) {
                                      kern<<<grid, threads, smem, st>>>(q, team_smem);
                                  });
@@ -107,7 +113,7 @@ static int launch(CovParams p, cudaStream_t st) {
         } else {
             auto kern = k_cov<ST, M, KC, P, TMA>;
             static bool attr_done = false;
-            return launch_common(kern, p, st, P, cov_teams_per_cta(P), stage_bytes, TC, M, KC, TMA, attr_done,
+            return launch_common(kern, p, st, P, cov_teams_per_cta(P), stage_bytes, TC, M, KC, TMA, attr_done, nsplit_out,
                                  [&](const CovParams& q, unsigned grid, int threads, size_t smem, int teams,
                                      int team_smem) { kern<<<grid, threads, smem, st>>>(q, teams, team_smem); });
         }
@@ -130,12 +136,13 @@ int OIVA_CAT(cov_max_kc_m, OIVA_COV_M)() {
     return best;
 }
 
-int OIVA_CAT(cov_launch_m, OIVA_COV_M)(int dtype, int KC, int use_tma, const CovParams& p, cudaStream_t st) {
+int OIVA_CAT(cov_launch_m, OIVA_COV_M)(int dtype, int KC, int use_tma, const CovParams& p, cudaStream_t st,
+                                       int* nsplit_out) {
 #define OIVA_COV_CASE(ST_, KC_) \
-    if (KC == KC_) return launch<ST_, KC_, true>(p, st);
+    if (KC == KC_) return launch<ST_, KC_, true>(p, st, nsplit_out);
     if (!use_tma) {  // debug path, fp64 storage, chunks of 1 or 2 sources only
-        if (dtype == OIVA_C128 && KC == 1) return launch<double, 1, false>(p, st);
-        if (dtype == OIVA_C128 && KC == 2) return launch<double, 2, false>(p, st);
+        if (dtype == OIVA_C128 && KC == 1) return launch<double, 1, false>(p, st, nsplit_out);
+        if (dtype == OIVA_C128 && KC == 2) return launch<double, 2, false>(p, st, nsplit_out);
         oiva_set_error("cov_launch: the non-TMA debug path supports complex128 with source chunks of 1 or 2");
         return OIVA_ERR_INVALID;
     }

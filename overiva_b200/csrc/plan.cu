@@ -23,7 +23,8 @@ struct oiva_plan {
     int Tp, NG;
     int es;  // bytes per real element of X / Y
     // workspace offsets
-    size_t off_xg, off_c, off_cg, off_what, off_wg, off_vg, off_weff, off_r2part, off_r2, off_phi, off_wscale, off_evals, off_status;
+    size_t off_xg, off_c, off_cg, off_what, off_wg, off_vg, off_weff, off_r2part, off_r2, off_phi, off_wscale, off_evals, off_status, off_covws;
+    size_t covws_bytes;
     size_t ws_bytes;
     unsigned char* ws;
     long long launches;
@@ -113,6 +114,9 @@ extern "C" int oiva_plan_create(oiva_plan_t** out, const oiva_plan_desc* desc) {
     p->off_wscale = o;  o += align_up(B * K * 8);
     p->off_evals = o;   o += align_up(R * M * 8);
     p->off_status = o;  o += align_up(16);
+    // per-split partial covariances of inputs with few bin groups (deterministic frame-split accumulation)
+    p->covws_bytes = oiva_weighted_cov_scratch_bytes(d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.n_src);
+    p->off_covws = o;   o += align_up(p->covws_bytes);
     p->ws_bytes = o;
     p->spans = new std::vector<TimedSpan>();
     p->pool = new std::vector<cudaEvent_t>();
@@ -196,8 +200,8 @@ extern "C" long long oiva_plan_launch_count(const oiva_plan_t* p) { return p ? p
 // input covariance C = (1/T) sum_t x x^H (overiva.py:87): grouped accumulation, then full row-major matrices
 static int plan_input_cov(oiva_plan_t* p, void* stream) {
     const oiva_plan_desc& d = p->d;
-    int rc = oiva_weighted_cov(p->ws + p->off_xg, nullptr, p->ws + p->off_cg, d.n_batch, d.n_frames, d.n_freq, d.n_chan,
-                               1, d.dtype, stream);
+    int rc = oiva_weighted_cov_ws(p->ws + p->off_xg, nullptr, p->ws + p->off_cg, p->covws_bytes ? p->ws + p->off_covws : nullptr,
+                                  p->covws_bytes, d.n_batch, d.n_frames, d.n_freq, d.n_chan, 1, d.dtype, stream);
     if (rc) return rc;
     rc = oiva_unpack_cov(p->ws + p->off_cg, p->ws + p->off_c, d.n_batch, d.n_freq, d.n_chan, 1, stream);
     if (rc) return rc;
@@ -297,8 +301,8 @@ static int plan_update_from(oiva_plan_t* p, const double* r2src, int nch, void* 
     if (rc) return rc;
     {
         SpanGuard g(p, TK_COV, stream);
-        rc = oiva_weighted_cov(p->ws + p->off_xg, phi, p->ws + p->off_vg, d.n_batch, d.n_frames, d.n_freq, d.n_chan,
-                               d.n_src, d.dtype, stream);
+        rc = oiva_weighted_cov_ws(p->ws + p->off_xg, phi, p->ws + p->off_vg, p->covws_bytes ? p->ws + p->off_covws : nullptr,
+                                  p->covws_bytes, d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.n_src, d.dtype, stream);
     }
     if (rc) return rc;
     {

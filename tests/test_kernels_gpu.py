@@ -84,6 +84,41 @@ def test_weighted_covariance_split_rows():
         assert rel_err(V[0, :, k], orc.weighted_covariance(Xf, phi[0, k])) < 1e-12
 
 
+def test_weighted_covariance_deterministic_split():
+    """With scratch, frame-split partial sums are combined in a fixed order: bit-identical from run to run and equal
+    (to rounding) to the atomic combination."""
+    lib = L.load()
+    X = _mix(21, 5, 30000, 64)
+    B, T, F, M = X.shape
+    K = 2
+    code = G.code_of(X.dtype)
+    Xg = G.grouped(X)
+    Tp = lib.oiva_frame_pitch(T)
+    rng = np.random.default_rng(1)
+    ph = np.zeros((B, K, Tp))
+    ph[:, :, :T] = rng.gamma(1.0, 1.0, size=(B, K, T)) + 0.05
+    phid = G.to_dev(ph)
+    nbytes = lib.oiva_grouped_cov_bytes(B, F, M, K)
+    ws_bytes = lib.oiva_weighted_cov_scratch_bytes(B, T, F, M, K)
+    assert ws_bytes >= 2 * nbytes
+    outs = []
+    for _ in range(3):
+        ws = torch.full((ws_bytes,), 0xFF, dtype=torch.uint8, device=G.dev())
+        Vg = torch.full((nbytes,), 0xFF, dtype=torch.uint8, device=G.dev())
+        L.check(lib.oiva_weighted_cov_ws(G.P(Xg), G.P(phid), G.P(Vg), G.P(ws), ws_bytes, B, T, F, M, K, code, G.stream()),
+                "oiva_weighted_cov_ws")
+        torch.cuda.synchronize()
+        outs.append(Vg.clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    Va = torch.empty((nbytes,), dtype=torch.uint8, device=G.dev())
+    L.check(lib.oiva_weighted_cov(G.P(Xg), G.P(phid), G.P(Va), B, T, F, M, K, code, G.stream()), "oiva_weighted_cov")
+    torch.cuda.synchronize()
+    a, b = outs[0].view(torch.float64).cpu().numpy(), Va.view(torch.float64).cpu().numpy()
+    assert rel_err(a, b) < 1e-14
+    # a scratch too small for two slots falls back to the atomic path; no scratch needed for large batches
+    assert lib.oiva_weighted_cov_scratch_bytes(512, 116, 2049, 6, 2) == 0
+
+
 @pytest.mark.parametrize("M,K,n_samples,dtype", [(4, 2, 1500, np.complex128), (6, 6, 1200, np.complex128),
                                                   (8, 3, 5000, np.complex128), (16, 4, 2300, np.complex128),
                                                   (5, 1, 1500, np.complex64), (10, 10, 900, np.complex128)])
