@@ -302,6 +302,8 @@ def run_gpu(args):
     torch.cuda.empty_cache()
     e2e = None
     try:
+        if args.no_e2e:
+            raise RuntimeError("skipped (--no-e2e)")
         Xh = torch.empty((B, T, F, M), dtype=torch.complex128, pin_memory=True)
         Xh.copy_(X)
         del X, Y
@@ -333,6 +335,8 @@ def run_gpu(args):
     # ---- end-to-end from AUDIO: STFT and iSTFT on the device, only audio crosses PCIe ---
     e2e_audio = None
     try:
+        if args.no_e2e:
+            raise RuntimeError("skipped (--no-e2e)")
         from overiva_b200 import stft as gstft
         from overiva_b200.synth import audio_batch_torch
 
@@ -400,6 +404,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=None, help="mixtures per GPU (default 512 = BASELINE cfg4 / 8)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the two end-to-end legs (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
