@@ -61,14 +61,14 @@ static int pick_chunk(int rem, int max_kc) {
 }  // namespace oiva
 
 extern "C" size_t oiva_weighted_cov_scratch_bytes(int n_batch, int n_frames, int n_freq, int n_chan, int n_src) {
-    // frame splitting only happens when there are few bin groups; 64 slots or 128 MiB, whichever is smaller, keeps
+    // frame splitting only happens when there are few bin groups; 64 slots or 512 MiB, whichever is smaller, keeps
     // every SM busy for the shapes that need it (the split count is clamped to the slots available)
     const size_t vg = oiva_grouped_cov_bytes(n_batch, n_freq, n_chan, n_src);
     if (vg == 0 || n_frames <= 0) return 0;
     const long long G = (long long)n_batch * oiva_bin_groups(n_freq);
     if (G >= 4096) return 0;  // enough groups for every team of every SM: never split
     size_t slots = 64;
-    const size_t cap = (size_t)128 << 20;
+    const size_t cap = (size_t)512 << 20;
     if (slots * vg > cap) slots = cap / vg;
     return slots < 2 ? 0 : slots * vg;
 }

@@ -65,10 +65,22 @@ static int launch_common(Kern kern, CovParams p, cudaStream_t st, int P, int tea
     if (p.nsplit <= 0) {
         p.nsplit = 1;
         if (p.G < 2 * max_ctas * teams && nchunks > 1) {
-            long long want = (2 * max_ctas * teams + p.G - 1) / p.G;
-            p.nsplit = (int)(want < nchunks ? want : nchunks);
+            // pick the split that minimises the busiest team's work: ceil(units / teams) units of
+            // ceil(nchunks / split) chunks each, plus ~2 chunk-times of ring fill and write-out per unit
+            const long long n_teams = max_ctas * teams;
+            long long hi = (4 * n_teams + p.G - 1) / p.G;
+            if (hi > nchunks) hi = nchunks;
+            if (p.Vpart && hi > p.max_split) hi = p.max_split < 1 ? 1 : p.max_split;
+            long long best_cost = -1;
+            for (long long ns = 1; ns <= hi; ++ns) {
+                const long long per_team = (p.G * ns + n_teams - 1) / n_teams;
+                const long long cost = per_team * ((nchunks + ns - 1) / ns + 2);
+                if (best_cost < 0 || cost < best_cost) {
+                    best_cost = cost;
+                    p.nsplit = (int)ns;
+                }
+            }
         }
-        if (p.Vpart && p.nsplit > p.max_split) p.nsplit = p.max_split < 1 ? 1 : p.max_split;
         if (p.nsplit > 1 && !p.Vpart)
             OIVA_CUDA_CHECK(cudaMemsetAsync(p.Vg, 0, (size_t)p.G * p.K * oiva_tri(M) * OIVA_GROUP * sizeof(cplx), st));
     }
