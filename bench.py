@@ -342,6 +342,8 @@ def run_gpu(args):
 
         del Xh, Yh
         torch.cuda.empty_cache()
+        if hasattr(torch._C, "_host_emptyCache"):  # give the 15.6 GB of pinned spectra buffers back to the OS
+            torch._C._host_emptyCache()
         n_samples = int(DURATION_S * FS)
         xa = audio_batch_torch(B, n_samples, M, K, seed=99 + rank, device=dev)
         assert gstft.num_frames(n_samples, 4096, 2048) == T
