@@ -181,6 +181,14 @@ int oiva_compose_filters(const void* E, const void* Wr, void* Wout, int n_rows, 
 int oiva_ogive_update(void* w, void* a, double* lambda_a, const void* V, const void* C, const void* Cinv,
                       const uint8_t* do_a, double step_size, double* delta_max, int n_rows, int n_chan,
                       void* stream);
+/* The same update for epoch `epoch` with the stopping rule of ive.py:238-241 evaluated on the device: delta_hist is a
+ * zero-initialised array of at least epoch + 1 doubles; delta_hist[epoch] receives max_f ||delta_f||, and once
+ * delta_hist[epoch - 1] < tol (the epoch at which the reference leaves its loop) the update is a no-op that carries
+ * the value forward.  The host may therefore look at delta_hist every few epochs instead of after each one and still
+ * ends in the state the reference stops in. */
+int oiva_ogive_update_gated(void* w, void* a, double* lambda_a, const void* V, const void* C, const void* Cinv,
+                            const uint8_t* do_a, double step_size, double* delta_hist, int epoch, double tol,
+                            int n_rows, int n_chan, void* stream);
 /* OGIVE set-up: Cinv = C^-1 (ive.py:98), cnorm (R,) = ||C||_F (ive.py:99); a from w (ive.py:132-135,168);
  * switching criterion masks (ive.py:142-161). */
 int oiva_ogive_setup(const void* C, void* Cinv, double* cnorm, int* status, int n_rows, int n_chan, void* stream);

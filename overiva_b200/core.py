@@ -529,8 +529,9 @@ def ogive(X, n_iter=4000, step_size=0.1, tol=1e-3, update="demix", proj_back=Tru
 
     Returns Y (n_frames, n_freq, 1) and, if ``return_filters``, w (n_freq, n_chan, 1).  The per-iteration
     statistic is obtained from the shared weighted-covariance kernel (x_psi = V w / (w^H V w)); the stopping
-    rule ``max_f ||delta_f|| < tol`` (ive.py:238-241) is evaluated every iteration, so the loop ends at the
-    same epoch as the reference.
+    rule ``max_f ||delta_f|| < tol`` (ive.py:238-241) is evaluated every iteration ON THE DEVICE -- once it holds,
+    the per-bin update becomes a no-op -- and read by the host every 20 epochs, so the result is the state of the
+    epoch at which the reference stops, without a device-to-host round trip per epoch.
     """
     if getattr(X, "ndim", 0) != 3:
         raise ValueError("X must have shape (n_frames, n_freq, n_chan)")
@@ -572,7 +573,9 @@ def ogive(X, n_iter=4000, step_size=0.1, tol=1e-3, update="demix", proj_back=Tru
         cov_ws_bytes = lib.oiva_weighted_cov_scratch_bytes(1, T, F, M, 1)
         cov_ws = torch.empty(max(cov_ws_bytes, 16), dtype=torch.uint8, device=dev)
         V = torch.empty((F, M, M), **c128)
-        dmax = torch.zeros((1,), dtype=torch.float64, device=dev)
+        n_iter = int(n_iter)
+        dhist = torch.zeros((max(n_iter, 1),), dtype=torch.float64, device=dev)  # max_f ||delta_f|| per epoch
+        SYNC_EVERY = 20  # divides the callback period (100): convergence is known before every callback
 
         def project(wcur):
             Weff = torch.empty((F, M, 1), **c128)
@@ -583,7 +586,14 @@ def ogive(X, n_iter=4000, step_size=0.1, tol=1e-3, update="demix", proj_back=Tru
                     "oiva_demix_output")
             return Y[0]
 
-        for epoch in range(int(n_iter)):
+        def converged(upto):  # ive.py:238-241 for the epochs run so far (one small D2H copy)
+            return upto > 0 and float(dhist[upto - 1].item()) < tol
+
+        for epoch in range(n_iter):
+            # the stopping rule is evaluated on the device every epoch (oiva_ogive_update_gated freezes the state at
+            # the epoch the reference breaks at); the host only looks every SYNC_EVERY epochs
+            if epoch % SYNC_EVERY == 0 and converged(epoch):
+                break
             if update == "switching" and epoch % 10 == 0:  # ive.py:187-188
                 L.check(lib.oiva_ogive_switching(_ptr(a), _ptr(Cx), _ptr(cnorm), _ptr(do_a), F, M, st),
                         "oiva_ogive_switching")
@@ -596,11 +606,9 @@ def ogive(X, n_iter=4000, step_size=0.1, tol=1e-3, update="demix", proj_back=Tru
             L.check(lib.oiva_weighted_cov_ws(plan.samples_ptr, _ptr(phi), _ptr(Vg), _ptr(cov_ws), cov_ws_bytes, 1, T, F,
                                              M, 1, code, st), "oiva_weighted_cov_ws")
             L.check(lib.oiva_unpack_cov(_ptr(Vg), _ptr(V), 1, F, M, 1, st), "oiva_unpack_cov")
-            dmax.zero_()
-            L.check(lib.oiva_ogive_update(_ptr(w), _ptr(a), _ptr(lam), _ptr(V), _ptr(Cx), _ptr(Cinv), _ptr(do_a),
-                                          float(step_size), _ptr(dmax), F, M, st), "oiva_ogive_update")
-            if float(dmax.item()) < tol:  # ive.py:238-241 (one scalar D2H per epoch)
-                break
+            L.check(lib.oiva_ogive_update_gated(_ptr(w), _ptr(a), _ptr(lam), _ptr(V), _ptr(Cx), _ptr(Cinv), _ptr(do_a),
+                                                float(step_size), _ptr(dhist), epoch, float(tol), F, M, st),
+                    "oiva_ogive_update_gated")
         Y = project(w)
         plan.raise_on_failure()
         Yo = inp.give_back(Y)

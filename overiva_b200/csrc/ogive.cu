@@ -122,10 +122,19 @@ __global__ void k_ogive_switching(const cplx* __restrict__ a, const cplx* __rest
 }
 
 // one OGIVE iteration for a bin (ive.py:216-241), V = weighted covariance of the current extraction
+// gate (may be NULL): max_f ||delta_f|| of the PREVIOUS epoch.  Once it is below tol the reference has left its loop
+// (ive.py:238-241), so the update becomes a no-op that only carries the value forward: the host can then check for
+// convergence every few epochs instead of synchronising after each one, and still ends in the state of the epoch at
+// which the reference stops.
 __global__ void k_ogive_update(cplx* __restrict__ w, cplx* __restrict__ a, double* __restrict__ lambda_a,
                                const cplx* __restrict__ V, const cplx* __restrict__ C, const cplx* __restrict__ Cinv,
-                               const uint8_t* __restrict__ do_a, double step, double* delta_max, long long R, int M) {
+                               const uint8_t* __restrict__ do_a, double step, double* delta_max, const double* gate,
+                               double tol, long long R, int M) {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gate != nullptr && *gate < tol) {
+        if (row == 0) *delta_max = *gate;
+        return;
+    }
     if (row >= R) return;
     cplx wv[OIVA_MAX_M], av[OIVA_MAX_M], xpsi[OIVA_MAX_M], tmp[OIVA_MAX_M];
     for (int i = 0; i < M; ++i) {
@@ -208,7 +217,20 @@ extern "C" int oiva_ogive_update(void* w, void* a, double* lambda_a, const void*
                  "oiva_ogive_update: bad arguments");
     k_ogive_update<<<(n_rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         (cplx*)w, (cplx*)a, lambda_a, (const cplx*)V, (const cplx*)C, (const cplx*)Cinv, do_a, step_size, delta_max,
-        n_rows, n_chan);
+        nullptr, 0.0, n_rows, n_chan);
+    OIVA_LAUNCH_CHECK();
+    return OIVA_OK;
+}
+
+extern "C" int oiva_ogive_update_gated(void* w, void* a, double* lambda_a, const void* V, const void* C,
+                                       const void* Cinv, const uint8_t* do_a, double step_size, double* delta_hist,
+                                       int epoch, double tol, int n_rows, int n_chan, void* stream) {
+    OIVA_REQUIRE(w && a && lambda_a && V && C && Cinv && do_a && delta_hist && epoch >= 0 && n_rows > 0 &&
+                     n_chan >= 1 && n_chan <= OIVA_MAX_M,
+                 "oiva_ogive_update_gated: bad arguments");
+    k_ogive_update<<<(n_rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        (cplx*)w, (cplx*)a, lambda_a, (const cplx*)V, (const cplx*)C, (const cplx*)Cinv, do_a, step_size,
+        delta_hist + epoch, epoch > 0 ? delta_hist + epoch - 1 : nullptr, tol, n_rows, n_chan);
     OIVA_LAUNCH_CHECK();
     return OIVA_OK;
 }
