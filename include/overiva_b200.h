@@ -90,6 +90,15 @@ size_t oiva_weighted_cov_scratch_bytes(int n_batch, int n_frames, int n_freq, in
 int oiva_weighted_cov_ws(const void* Xg, const double* phi, void* Vg, void* scratch, size_t scratch_bytes,
                          int n_batch, int n_frames, int n_freq, int n_chan, int n_src, int dtype, void* stream);
 
+/* oiva_relayout + the unweighted oiva_weighted_cov in ONE pass over X (read X once, write Xg and Cg): M <= 8, and for
+ * complex64 an even F*M (16-byte aligned rows); oiva_relayout_cov_supported() tells.  Cg: grouped lower-triangle
+ * covariance (oiva_unpack_cov gives the full matrices), bit-identical to the two-kernel path.  scratch as for
+ * oiva_weighted_cov_ws with n_src = 1 (may be NULL: no frame splitting).
+ * replaces: overiva.py:131-132 and overiva.py:87 together. */
+int oiva_relayout_cov_supported(int n_freq, int n_chan, int dtype);
+int oiva_relayout_cov(const void* X, void* Xg, void* Cg, void* scratch, size_t scratch_bytes, int n_batch,
+                      int n_frames, int n_freq, int n_chan, int dtype, void* stream);
+
 /* per-bin arrays of n_elems c128 each: row-major (R, n_elems) <-> grouped [gi][n_elems][32] (padded bins: 0).
  * Inside the loop the demixing matrices live in the grouped form (coalesced for lane <-> bin kernels). */
 int oiva_group_rows(const void* rows, void* grouped, int n_batch, int n_freq, int n_elems, void* stream);

@@ -43,6 +43,8 @@ SIGNATURES = {
     "oiva_grouped_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "oiva_grouped_cov_bytes": (_sz, [_i, _i, _i, _i]),
     "oiva_relayout": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "oiva_relayout_cov_supported": (_i, [_i, _i, _i]),
+    "oiva_relayout_cov": (_i, [_p, _p, _p, _p, _sz, _i, _i, _i, _i, _i, _p]),
     "oiva_weighted_cov": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "oiva_weighted_cov_scratch_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "oiva_weighted_cov_ws": (_i, [_p, _p, _p, _p, _sz, _i, _i, _i, _i, _i, _i, _p]),

@@ -2,11 +2,13 @@
 #include <stdlib.h>
 
 #include "cov.cuh"
+#include "relayout_cov.cuh"
 
 namespace oiva {
 #define OIVA_DECL(M)                                                                                 \
     int cov_launch_m##M(int dtype, int KC, int use_tma, const CovParams& p, cudaStream_t st, int* nsplit_out); \
-    int cov_max_kc_m##M();
+    int cov_max_kc_m##M();                                                                                     \
+    int relayout_cov_launch_m##M(int dtype, RelayoutCovParams p, int max_split, cudaStream_t st, int* nsplit_out);
 OIVA_DECL(1) OIVA_DECL(2) OIVA_DECL(3) OIVA_DECL(4) OIVA_DECL(5) OIVA_DECL(6) OIVA_DECL(7) OIVA_DECL(8)
 OIVA_DECL(9) OIVA_DECL(10) OIVA_DECL(11) OIVA_DECL(12) OIVA_DECL(13) OIVA_DECL(14) OIVA_DECL(15) OIVA_DECL(16)
 #undef OIVA_DECL
@@ -149,4 +151,54 @@ extern "C" int oiva_weighted_cov_ws(const void* Xg, const double* phi, void* Vg,
 extern "C" int oiva_weighted_cov(const void* Xg, const double* phi, void* Vg, int n_batch, int n_frames, int n_freq,
                                  int n_chan, int n_src, int dtype, void* stream) {
     return oiva_weighted_cov_ws(Xg, phi, Vg, nullptr, 0, n_batch, n_frames, n_freq, n_chan, n_src, dtype, stream);
+}
+
+extern "C" int oiva_relayout_cov_supported(int n_freq, int n_chan, int dtype) {
+    if (n_chan < 1 || n_chan > 8 || n_freq < 1) return 0;
+    // the per-frame bulk copies need 16-byte aligned rows: always true for complex128; for complex64 (8-byte
+    // elements) only when F * M is even
+    if (dtype == OIVA_C64 && (((long long)n_freq * n_chan) & 1)) return 0;
+    return dtype == OIVA_C64 || dtype == OIVA_C128;
+}
+
+extern "C" int oiva_relayout_cov(const void* X, void* Xg, void* Cg, void* scratch, size_t scratch_bytes, int n_batch,
+                                 int n_frames, int n_freq, int n_chan, int dtype, void* stream) {
+    using namespace oiva;
+    OIVA_REQUIRE(X && Xg && Cg, "oiva_relayout_cov: null pointer");
+    OIVA_REQUIRE(n_batch > 0 && n_frames > 0 && n_freq > 0, "oiva_relayout_cov: bad shape B=%d T=%d F=%d", n_batch,
+                 n_frames, n_freq);
+    OIVA_REQUIRE(oiva_relayout_cov_supported(n_freq, n_chan, dtype), "oiva_relayout_cov: unsupported (M=%d, F=%d, dtype=%d)",
+                 n_chan, n_freq, dtype);
+    OIVA_REQUIRE(((uintptr_t)X & 15) == 0, "oiva_relayout_cov: X must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    RelayoutCovParams p;
+    p.X = X;
+    p.Xg = Xg;
+    p.Cg = (cplx*)Cg;
+    p.L = oiva_make_layout(n_frames, n_freq, n_chan);
+    p.G = (long long)n_batch * p.L.NG;
+    p.invT = 1.0 / (double)n_frames;
+    p.nsplit = 1;
+    p.stages = 2;
+    const size_t cg_bytes = oiva_grouped_cov_bytes(n_batch, n_freq, n_chan, 1);
+    int max_split = 1;
+    p.Cpart = nullptr;
+    if (scratch && scratch_bytes >= 2 * cg_bytes) {
+        p.Cpart = (cplx*)scratch;
+        const size_t slots = scratch_bytes / cg_bytes;
+        max_split = slots > 4096 ? 4096 : (int)slots;
+    }
+    int rc = OIVA_ERR_INVALID, nsplit = 1;
+    switch (n_chan) {
+#define OIVA_CASE(M) case M: rc = relayout_cov_launch_m##M(dtype, p, max_split, st, &nsplit); break;
+        OIVA_CASE(1) OIVA_CASE(2) OIVA_CASE(3) OIVA_CASE(4) OIVA_CASE(5) OIVA_CASE(6) OIVA_CASE(7) OIVA_CASE(8)
+#undef OIVA_CASE
+    }
+    if (rc) return rc;
+    if (nsplit > 1) {
+        const size_t n = cg_bytes / sizeof(cplx);
+        k_cov_sum_partials<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.Cpart, p.Cg, nsplit, n);
+        OIVA_LAUNCH_CHECK();
+    }
+    return OIVA_OK;
 }

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 
 #include "cov.cuh"
+#include "relayout_cov.cuh"
 
 #ifndef OIVA_COV_M
 #error "compile with -DOIVA_COV_M=<1..16>"
@@ -15,6 +16,25 @@ namespace oiva {
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
+}
+
+// frame splits per group that minimise the busiest team's work: ceil(units / teams) units of
+// ceil(nchunks / split) chunks each, plus ~2 chunk-times of ring fill and write-out per unit
+static int choose_split(long long G, int nchunks, long long n_teams, long long max_split) {
+    long long hi = (4 * n_teams + G - 1) / G;
+    if (hi > nchunks) hi = nchunks;
+    if (hi > max_split) hi = max_split < 1 ? 1 : max_split;
+    long long best_cost = -1;
+    int best = 1;
+    for (long long ns = 1; ns <= hi; ++ns) {
+        const long long per_team = (G * ns + n_teams - 1) / n_teams;
+        const long long cost = per_team * ((nchunks + ns - 1) / ns + 2);
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best = (int)ns;
+        }
+    }
+    return best;
 }
 
 constexpr int COV_MAX_PARTS = 16;
@@ -65,21 +85,7 @@ static int launch_common(Kern kern, CovParams p, cudaStream_t st, int P, int tea
     if (p.nsplit <= 0) {
         p.nsplit = 1;
         if (p.G < 2 * max_ctas * teams && nchunks > 1) {
-            // pick the split that minimises the busiest team's work: ceil(units / teams) units of
-            // ceil(nchunks / split) chunks each, plus ~2 chunk-times of ring fill and write-out per unit
-            const long long n_teams = max_ctas * teams;
-            long long hi = (4 * n_teams + p.G - 1) / p.G;
-            if (hi > nchunks) hi = nchunks;
-            if (p.Vpart && hi > p.max_split) hi = p.max_split < 1 ? 1 : p.max_split;
-            long long best_cost = -1;
-            for (long long ns = 1; ns <= hi; ++ns) {
-                const long long per_team = (p.G * ns + n_teams - 1) / n_teams;
-                const long long cost = per_team * ((nchunks + ns - 1) / ns + 2);
-                if (best_cost < 0 || cost < best_cost) {
-                    best_cost = cost;
-                    p.nsplit = (int)ns;
-                }
-            }
+            p.nsplit = choose_split(p.G, nchunks, max_ctas * teams, p.Vpart ? p.max_split : nchunks);
         }
         if (p.nsplit > 1 && !p.Vpart)
             OIVA_CUDA_CHECK(cudaMemsetAsync(p.Vg, 0, (size_t)p.G * p.K * oiva_tri(M) * OIVA_GROUP * sizeof(cplx), st));
@@ -179,6 +185,69 @@ int OIVA_CAT(cov_launch_m, OIVA_COV_M)(int dtype, int KC, int use_tma, const Cov
     }
     oiva_set_error("cov_launch: unsupported source chunk %d", KC);
     return OIVA_ERR_INVALID;
+}
+
+// relayout + input covariance in one pass (relayout_cov.cuh); M <= 8 only.  max_split: slots in p.Cpart (<= 1: none)
+template <int M>
+static int relayout_cov_launch_t(int dtype, RelayoutCovParams p, int max_split, cudaStream_t st, int* nsplit_out) {
+    if constexpr (M > 8) {
+        return OIVA_ERR_INVALID;
+    } else {
+        int dev = 0, sms = 148;
+        OIVA_CUDA_CHECK(cudaGetDevice(&dev));
+        OIVA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        constexpr int TC = cov_chunk_frames(M);
+        const size_t es = dtype == OIVA_C64 ? sizeof(float2) : sizeof(double2);
+        const size_t stage_bytes = ((TC * OIVA_GROUP * M * es + 127) / 128) * 128;
+        const int S = 2;
+        int teams = 8;
+        const size_t team_smem = 128 * ((2 * S * sizeof(uint64_t) + 127) / 128) + (size_t)S * stage_bytes;
+        const size_t budget = 200 * 1024;
+        while (teams > 1 && teams * team_smem > budget) --teams;
+        const size_t smem = teams * team_smem;
+        p.stages = S;
+        const int threads = teams * 32;
+        int occ = 1;
+        if (dtype == OIVA_C64) {
+            auto kern = k_relayout_cov<float, M>;
+            static bool attr_done = false;
+            if (!attr_done) {
+                OIVA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+                attr_done = true;
+            }
+            OIVA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+        } else {
+            auto kern = k_relayout_cov<double, M>;
+            static bool attr_done = false;
+            if (!attr_done) {
+                OIVA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+                attr_done = true;
+            }
+            OIVA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+        }
+        if (occ < 1) occ = 1;
+        const long long max_ctas = (long long)sms * occ;
+        const int nchunks = (p.L.T + TC - 1) / TC;
+        p.nsplit = 1;
+        if (p.G < 2 * max_ctas * teams && nchunks > 1 && p.Cpart && max_split > 1)
+            p.nsplit = choose_split(p.G, nchunks, max_ctas * teams, max_split);
+        if (nsplit_out) *nsplit_out = p.nsplit;
+        const long long U = p.G * p.nsplit;
+        long long grid = (U + teams - 1) / teams;
+        if (grid > max_ctas) grid = max_ctas;
+        if (grid < 1) grid = 1;
+        if (dtype == OIVA_C64)
+            k_relayout_cov<float, M><<<(unsigned)grid, threads, smem, st>>>(p, teams, (int)team_smem);
+        else
+            k_relayout_cov<double, M><<<(unsigned)grid, threads, smem, st>>>(p, teams, (int)team_smem);
+        OIVA_LAUNCH_CHECK();
+        return OIVA_OK;
+    }
+}
+
+int OIVA_CAT(relayout_cov_launch_m, OIVA_COV_M)(int dtype, RelayoutCovParams p, int max_split, cudaStream_t st,
+                                                int* nsplit_out) {
+    return relayout_cov_launch_t<OIVA_COV_M>(dtype, p, max_split, st, nsplit_out);
 }
 
 }  // namespace oiva

@@ -213,11 +213,26 @@ extern "C" int oiva_plan_load(oiva_plan_t* p, const void* X, void* stream) {
     PLAN_READY(p, "oiva_plan_load");
     OIVA_REQUIRE(X, "oiva_plan_load: null X");
     const oiva_plan_desc& d = p->d;
-    int rc = oiva_relayout(X, p->ws + p->off_xg, d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.dtype, stream);
-    if (rc) return rc;
-    p->launches += 1;
-    rc = plan_input_cov(p, stream);
-    if (rc) return rc;
+    int rc;
+    static const bool no_fuse = [] {
+        const char* v = getenv("OIVA_NO_RELAYOUT_COV");
+        return v && *v && *v != '0';
+    }();
+    if (!no_fuse && oiva_relayout_cov_supported(d.n_freq, d.n_chan, d.dtype) && (((uintptr_t)X) & 15) == 0) {
+        // one pass: grouped samples + grouped covariance, then the full row-major matrices        overiva.py:87,131-132
+        rc = oiva_relayout_cov(X, p->ws + p->off_xg, p->ws + p->off_cg, p->covws_bytes ? p->ws + p->off_covws : nullptr,
+                               p->covws_bytes, d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.dtype, stream);
+        if (rc) return rc;
+        rc = oiva_unpack_cov(p->ws + p->off_cg, p->ws + p->off_c, d.n_batch, d.n_freq, d.n_chan, 1, stream);
+        if (rc) return rc;
+        p->launches += 2;
+    } else {
+        rc = oiva_relayout(X, p->ws + p->off_xg, d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.dtype, stream);
+        if (rc) return rc;
+        p->launches += 1;
+        rc = plan_input_cov(p, stream);
+        if (rc) return rc;
+    }
     p->loaded = true;
     p->inited = false;
     return OIVA_OK;

@@ -84,6 +84,51 @@ def test_weighted_covariance_split_rows():
         assert rel_err(V[0, :, k], orc.weighted_covariance(Xf, phi[0, k])) < 1e-12
 
 
+@pytest.mark.parametrize("M,n_samples,frame,dtype,B", [(6, 4200, 64, np.complex128, 2), (4, 1500, 64, np.complex128, 1),
+                                                       (3, 1000, 32, np.complex128, 2), (1, 700, 64, np.complex128, 1),
+                                                       (8, 30000, 64, np.complex128, 1), (6, 2500, 64, np.complex64, 2),
+                                                       (5, 2500, 62, np.complex64, 1), (7, 900, 16, np.complex128, 3)])
+def test_relayout_cov_fused_equals_two_kernels(M, n_samples, frame, dtype, B):
+    """One pass (relayout + input covariance) == oiva_relayout followed by the unweighted oiva_weighted_cov_ws:
+    identical grouped samples, identical covariance (same arithmetic in the same order)."""
+    lib = L.load()
+    X = _mix(31, M, n_samples, frame, dtype, B=B)
+    B, T, F, M = X.shape
+    code = G.code_of(X.dtype)
+    if not lib.oiva_relayout_cov_supported(F, M, code):
+        assert code == L.C64 and (F * M) % 2 == 1
+        pytest.skip("complex64 rows of odd length are not 16-byte aligned: the plan keeps the two-kernel path")
+    Xd = G.to_dev(X)
+    nx = lib.oiva_grouped_bytes(B, T, F, M, code)
+    nc = lib.oiva_grouped_cov_bytes(B, F, M, 1)
+    ws_bytes = lib.oiva_weighted_cov_scratch_bytes(B, T, F, M, 1)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=G.dev())
+    Xg1 = torch.full((nx,), 0xFF, dtype=torch.uint8, device=G.dev())
+    Cg1 = torch.full((nc,), 0xFF, dtype=torch.uint8, device=G.dev())
+    L.check(lib.oiva_relayout_cov(G.P(Xd), G.P(Xg1), G.P(Cg1), G.P(ws), ws_bytes, B, T, F, M, code, G.stream()),
+            "oiva_relayout_cov")
+    torch.cuda.synchronize()
+    Xg0 = G.grouped(X)
+    Cg0 = torch.full((nc,), 0xFF, dtype=torch.uint8, device=G.dev())
+    L.check(lib.oiva_weighted_cov_ws(G.P(Xg0), None, G.P(Cg0), G.P(ws), ws_bytes, B, T, F, M, 1, code, G.stream()),
+            "oiva_weighted_cov_ws")
+    torch.cuda.synchronize()
+    assert torch.equal(Xg1, Xg0)
+    a, b = Cg1.view(torch.float64).cpu().numpy(), Cg0.view(torch.float64).cpu().numpy()
+    assert np.all(np.isfinite(a)) and rel_err(a, b) < 1e-14
+    # and against numpy
+    C = torch.empty((B, F, 1, M, M), dtype=torch.complex128, device=G.dev())
+    L.check(lib.oiva_unpack_cov(G.P(Cg1), G.P(C), B, F, M, 1, G.stream()), "oiva_unpack_cov")
+    torch.cuda.synchronize()
+    want = np.stack([orc.input_covariance(X[b].astype(np.complex128)) for b in range(B)])
+    assert rel_err(C.cpu().numpy()[:, :, 0], want) < (1e-6 if dtype == np.complex64 else 1e-13)
+    # no scratch: no frame splitting, same result to rounding
+    Cg2 = torch.full((nc,), 0xFF, dtype=torch.uint8, device=G.dev())
+    L.check(lib.oiva_relayout_cov(G.P(Xd), G.P(Xg1), G.P(Cg2), None, 0, B, T, F, M, code, G.stream()), "oiva_relayout_cov")
+    torch.cuda.synchronize()
+    assert rel_err(Cg2.view(torch.float64).cpu().numpy(), b) < 1e-13
+
+
 def test_weighted_covariance_deterministic_split():
     """With scratch, frame-split partial sums are combined in a fixed order: bit-identical from run to run and equal
     (to rounding) to the atomic combination."""

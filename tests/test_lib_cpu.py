@@ -68,6 +68,13 @@ def test_argument_validation_without_gpu(lib):
     assert lib.oiva_plan_iterate(h, 1, None) == -3  # no workspace bound: state error, not a crash
     lib.oiva_plan_destroy(h)
     assert lib.oiva_relayout(None, None, 1, 1, 1, 1, 0, None) == -1
+    # the one-pass relayout + covariance: up to 8 channels; complex64 needs 16-byte aligned rows (even F * M)
+    assert lib.oiva_relayout_cov_supported(2049, 6, L.C128) == 1 and lib.oiva_relayout_cov_supported(2049, 9, L.C128) == 0
+    assert lib.oiva_relayout_cov_supported(2049, 6, L.C64) == 1 and lib.oiva_relayout_cov_supported(2049, 5, L.C64) == 0
+    assert lib.oiva_relayout_cov(None, None, None, None, 0, 1, 1, 1, 1, 0, None) == -1
+    # scratch for the deterministic frame-split sums: none for big batches, a few slots of |Vg| for single mixtures
+    assert lib.oiva_weighted_cov_scratch_bytes(512, 116, 2049, 6, 2) == 0
+    assert lib.oiva_weighted_cov_scratch_bytes(1, 116, 2049, 6, 2) == 64 * lib.oiva_grouped_cov_bytes(1, 2049, 6, 2)
 
 
 def test_no_cpu_fallback():
