@@ -352,12 +352,17 @@ __global__ void __launch_bounds__(TPB_WARPS * 32) k_ip_update_tpb(cplx* __restri
     }
 
     if (valid) {
+        // only the entries the sweep writes can go bad: the K filter columns and the K x (M-K) block J (the rest of
+        // W_hat is the constant [0; -I]) -- 20 of 36 entries at M = 6, K = 2, i.e. 0.27 GB less DRAM read per sweep
         bool bad = false;
 #pragma unroll
-        for (int i = 0; i < M * M; ++i) {
-            const cplx v = Wm[i];
-            if (!isfinite(v.x) || !isfinite(v.y)) bad = true;
-        }
+        for (int j = 0; j < M; ++j)
+#pragma unroll
+            for (int c = 0; c < M; ++c)
+                if (c < K || j < K) {
+                    const cplx v = Wm[j * M + c];
+                    if (!isfinite(v.x) || !isfinite(v.y)) bad = true;
+                }
         if (singular || bad)
             atomicOr(status, (singular ? OIVA_STATUS_SINGULAR : 0) | (bad ? OIVA_STATUS_NONFINITE : 0));
     }
