@@ -17,5 +17,5 @@ run refarm 600 python bench.py --impl reference --steps 2 --warmup 1
 run configs 600 python scripts/bench_configs.py --configs cfg1,cfg2,cfg3,cfg5 --cpu
 run audio 600 python scripts/bench_audio.py
 run nextrows 900 python scripts/bench_next_rows.py
-run ncu_list 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 261 -c 174 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 2 --no-cpu --no-e2e
+run ncu_list 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -s 261 -c 174 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 2 --no-cpu --no-e2e
 run ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:"k_cov|k_ip_update_tpb|k_demix_power" -s 190 -c 3 -o gpurun_out/prof_r1b python bench.py --steps 1 --no-cpu --no-e2e
