@@ -14,6 +14,7 @@ library every function raises.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 
 import numpy as np
 import torch
@@ -243,6 +244,36 @@ def clear_plan_cache():
     """Drop every cached plan (frees their device workspaces)."""
     _PLAN_CACHE.clear()
     del _PLAN_CACHE_ORDER[:]
+    _PIPE_STATE.clear()
+
+
+# Host pipelines (overiva_batch / stft.separate_batch on host inputs) keep their three streams for the life of the
+# process (the caching allocator keys free blocks by stream: fresh streams per call would mean fresh cudaMallocs per
+# call) and the device slots + plans of the MOST RECENT pipeline shape, so that repeated calls of one shape -- a sweep,
+# a benchmark -- allocate nothing.  ``clear_plan_cache()`` releases them.
+_PIPE_STREAMS = {}
+_PIPE_STATE = {}
+_PIPE_LOCK = threading.Lock()
+
+
+def _pipe_streams(dev):
+    key = torch.device(dev).index
+    st = _PIPE_STREAMS.get(key)
+    if st is None:
+        st = (torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        _PIPE_STREAMS[key] = st
+    return st
+
+
+def _pipe_state(name, key, build):
+    """The cached state of pipeline ``name`` if it was built for ``key``, else ``build()`` (replacing the old one)."""
+    cur = _PIPE_STATE.get(name)
+    if cur is not None and cur[0] == key:
+        return cur[1]
+    _PIPE_STATE.pop(name, None)
+    state = build()
+    _PIPE_STATE[name] = (key, state)
+    return state
 
 
 def _model_code(model, table=_MODELS):
@@ -346,15 +377,38 @@ def _host_pipeline(Xh, n_src, n_iter, proj_back, W0, model, init_eig, return_fil
     Wh = torch.empty((B, F, M, K), dtype=torch.complex128, pin_memory=True) if return_filters else None
     W0d = _prepare_W0(W0, B, F, M, K, dev) if W0 is not None else None
     main = torch.cuda.current_stream(dev)
-    s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    owned = _PIPE_LOCK.acquire(blocking=False)  # a concurrent caller (another thread) gets private, uncached state
+    try:
+        return _host_pipeline_locked(Xh, K, n_iter, proj_back, W0d, code, init_eig, return_filters, chunk, Yh, Wh, dev,
+                                     main, owned)
+    finally:
+        if owned:
+            _PIPE_LOCK.release()
+
+
+def _host_pipeline_locked(Xh, K, n_iter, proj_back, W0d, code, init_eig, return_filters, chunk, Yh, Wh, dev, main, owned):
+    B, T, F, M = Xh.shape
+    cdt = Xh.dtype
+    s_in, s_cmp, s_out = _pipe_streams(dev) if owned else (torch.cuda.Stream(dev), torch.cuda.Stream(dev),
+                                                            torch.cuda.Stream(dev))
+    n_slots = 2
+
+    def build():
+        return {
+            "Xd": [torch.empty((chunk, T, F, M), dtype=cdt, device=dev) for _ in range(n_slots)],
+            "Yd": [torch.empty((chunk, T, F, K), dtype=cdt, device=dev) for _ in range(n_slots)],
+            "Wd": [torch.empty((chunk, F, M, K), dtype=torch.complex128, device=dev) if return_filters else None
+                   for _ in range(n_slots)],
+            "plans": {},
+        }
+
+    key = (chunk, T, F, M, K, code, cdt, torch.device(dev).index, bool(return_filters))
+    state = _pipe_state("spectra", key, build) if owned else build()
+    Xd, Yd, Wd, plans = state["Xd"], state["Yd"], state["Wd"], state["plans"]
+    for plan in plans.values():
+        plan.reset_status()  # (on the caller's stream, which the pipeline streams wait for next)
     for st in (s_in, s_cmp, s_out):
         st.wait_stream(main)
-    n_slots = 2
-    Xd = [torch.empty((chunk, T, F, M), dtype=cdt, device=dev) for _ in range(n_slots)]
-    Yd = [torch.empty((chunk, T, F, K), dtype=cdt, device=dev) for _ in range(n_slots)]
-    Wd = [torch.empty((chunk, F, M, K), dtype=torch.complex128, device=dev) if return_filters else None
-          for _ in range(n_slots)]
-    plans = {}
 
     def plan_for(nb, slot):
         key = (nb, slot)

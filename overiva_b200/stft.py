@@ -226,57 +226,80 @@ def separate_batch(mix, n_src=None, n_iter=20, framesize=4096, hop=None, win_a=N
     with torch.cuda.device(dev):
         yh = out if out is not None else torch.empty((B, n_out, K), dtype=out_dtype, pin_memory=True)
         main = torch.cuda.current_stream(dev)
-        s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        owned = core._PIPE_LOCK.acquire(blocking=False)  # a concurrent caller gets private, uncached state
+        s_in, s_cmp, s_out = core._pipe_streams(dev) if owned else (torch.cuda.Stream(dev), torch.cuda.Stream(dev),
+                                                                     torch.cuda.Stream(dev))
+        chunk = min(int(chunk), B)
+        lib = L.load()
+
+        def build():  # device slots, scratch and plans of this pipeline shape: kept until another shape comes along
+            with torch.cuda.stream(s_cmp):
+                return {
+                    "xd": [torch.empty((chunk, N, M), dtype=xh.dtype, device=dev) for _ in range(2)],
+                    "yd": [torch.empty((chunk, n_out, K), dtype=out_dtype, device=dev) for _ in range(2)],
+                    "Yd": torch.empty((chunk, T, F, K), dtype=dtype, device=dev),
+                    "scratch": torch.empty(lib.oiva_stft_scratch_bytes(chunk, T, K, framesize), dtype=torch.uint8,
+                                           device=dev),
+                    "plans": {},
+                }
+
+        key = (chunk, N, M, K, T, int(framesize), hop, code, dtype, xh.dtype, torch.device(dev).index)
+        try:
+            state = core._pipe_state("audio", key, build) if owned else build()
+        except BaseException:
+            if owned:
+                core._PIPE_LOCK.release()
+            raise
+        xd, yd, Yd, scratch, plans = state["xd"], state["yd"], state["Yd"], state["scratch"], state["plans"]
+        for plan in plans.values():
+            plan.reset_status()  # (on the caller's stream, which the pipeline streams wait for next)
         for st in (s_in, s_cmp, s_out):
             st.wait_stream(main)
-        chunk = min(int(chunk), B)
-        xd = [torch.empty((chunk, N, M), dtype=xh.dtype, device=dev) for _ in range(2)]
-        yd = [torch.empty((chunk, n_out, K), dtype=out_dtype, device=dev) for _ in range(2)]
-        with torch.cuda.stream(s_cmp):
-            wa, ws, tw = _window(win_a, framesize, dev), _window(win_s, framesize, dev), _twiddles(framesize, dev)
-            Yd = torch.empty((chunk, T, F, K), dtype=dtype, device=dev)
-            scratch = torch.empty(L.load().oiva_stft_scratch_bytes(chunk, T, K, framesize), dtype=torch.uint8, device=dev)
-        lib = L.load()
-        plans = {}
-        ev_in, ev_cmp, ev_out = [None] * 2, [None] * 2, [None] * 2
-        for i, b0 in enumerate(range(0, B, chunk)):
-            nb = min(chunk, B - b0)
-            slot = i % 2
-            with torch.cuda.stream(s_in):
-                if ev_cmp[slot] is not None:
-                    s_in.wait_event(ev_cmp[slot])
-                xd[slot][:nb].copy_(xh[b0 : b0 + nb], non_blocking=True)
-                ev_in[slot] = s_in.record_event()
+        try:
             with torch.cuda.stream(s_cmp):
-                s_cmp.wait_event(ev_in[slot])
-                if ev_out[slot] is not None:
-                    s_cmp.wait_event(ev_out[slot])
-                if nb not in plans:
-                    plans[nb] = core.DemixPlan(nb, T, F, M, K, code, dtype, dev)
-                plan = plans[nb]
-                st = core._stream_ptr(dev)
-                L.check(lib.oiva_stft_analysis(core._ptr(xd[slot]), int(xh.dtype == torch.float32), N * M, M, 1, N,
-                                               int(pad_front), core._ptr(wa), core._ptr(tw),
-                                               C.c_void_p(plan.samples_ptr), 1, nb, T, M, int(framesize), hop,
-                                               plan.code, st), "oiva_stft_analysis")
-                plan.adopt_samples()
-                plan.init(L.INIT_EIG if init_eig else L.INIT_EYE)
-                plan.iterate(int(n_iter))
-                plan.output(proj_back, out=Yd[:nb])
-                L.check(lib.oiva_stft_synthesis(core._ptr(Yd), core._ptr(ws), core._ptr(tw), core._ptr(scratch),
-                                                core._ptr(yd[slot]), int(out_dtype == torch.float32), nb, T, K,
-                                                int(framesize), hop, plan.code, st), "oiva_stft_synthesis")
-                ev_cmp[slot] = s_cmp.record_event()
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_cmp[slot])
-                yh[b0 : b0 + nb].copy_(yd[slot][:nb], non_blocking=True)
-                ev_out[slot] = s_out.record_event()
-        for st in (s_in, s_cmp, s_out):
-            main.wait_stream(st)
-        with torch.cuda.stream(s_cmp):
-            for plan in plans.values():
-                plan.raise_on_failure()
-        main.synchronize()
+                wa, ws, tw = _window(win_a, framesize, dev), _window(win_s, framesize, dev), _twiddles(framesize, dev)
+            ev_in, ev_cmp, ev_out = [None] * 2, [None] * 2, [None] * 2
+            for i, b0 in enumerate(range(0, B, chunk)):
+                nb = min(chunk, B - b0)
+                slot = i % 2
+                with torch.cuda.stream(s_in):
+                    if ev_cmp[slot] is not None:
+                        s_in.wait_event(ev_cmp[slot])
+                    xd[slot][:nb].copy_(xh[b0 : b0 + nb], non_blocking=True)
+                    ev_in[slot] = s_in.record_event()
+                with torch.cuda.stream(s_cmp):
+                    s_cmp.wait_event(ev_in[slot])
+                    if ev_out[slot] is not None:
+                        s_cmp.wait_event(ev_out[slot])
+                    if nb not in plans:
+                        plans[nb] = core.DemixPlan(nb, T, F, M, K, code, dtype, dev)
+                    plan = plans[nb]
+                    st = core._stream_ptr(dev)
+                    L.check(lib.oiva_stft_analysis(core._ptr(xd[slot]), int(xh.dtype == torch.float32), N * M, M, 1, N,
+                                                   int(pad_front), core._ptr(wa), core._ptr(tw),
+                                                   C.c_void_p(plan.samples_ptr), 1, nb, T, M, int(framesize), hop,
+                                                   plan.code, st), "oiva_stft_analysis")
+                    plan.adopt_samples()
+                    plan.init(L.INIT_EIG if init_eig else L.INIT_EYE)
+                    plan.iterate(int(n_iter))
+                    plan.output(proj_back, out=Yd[:nb])
+                    L.check(lib.oiva_stft_synthesis(core._ptr(Yd), core._ptr(ws), core._ptr(tw), core._ptr(scratch),
+                                                    core._ptr(yd[slot]), int(out_dtype == torch.float32), nb, T, K,
+                                                    int(framesize), hop, plan.code, st), "oiva_stft_synthesis")
+                    ev_cmp[slot] = s_cmp.record_event()
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_cmp[slot])
+                    yh[b0 : b0 + nb].copy_(yd[slot][:nb], non_blocking=True)
+                    ev_out[slot] = s_out.record_event()
+            for st in (s_in, s_cmp, s_out):
+                main.wait_stream(st)
+            with torch.cuda.stream(s_cmp):
+                for plan in plans.values():
+                    plan.raise_on_failure()
+            main.synchronize()
+        finally:
+            if owned:
+                core._PIPE_LOCK.release()
     return yh.numpy() if kind == "numpy" else yh
 
 
