@@ -119,6 +119,104 @@ __global__ void __launch_bounds__(512) k_demix_power(const StreamParams p) {
     }
 }
 
+// Same statistic for K > KC (several source-chunk warps per group): instead of every warp re-reading X from global
+// memory, the CTA stages each block of POWER_FB frames ONCE in shared memory -- a contiguous piece of the grouped
+// layout, i.e. one 1-D bulk-TMA copy into a 2-stage ring (full / empty mbarriers as in cov.cuh) -- and all warps
+// read it from there (conflict-free LDS.128).  Measured at M = K = 6, 256 mixtures: see DESIGN.md.
+// grid (G, nsplit), block = 32 * ceil(K/KC); dynamic smem = 128 + 2 * POWER_FB * M * 32 * sizeof(XC)
+template <typename ST, int M, int KC>
+__global__ void __launch_bounds__(512) k_demix_power_staged(const StreamParams p) {
+    typedef typename StoreC<ST>::type XC;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr size_t stage_bytes = (size_t)POWER_FB * M * OIVA_GROUP * sizeof(XC);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* empty = full + 2;
+    unsigned char* stage0 = smem_raw + 128;
+    const GroupLayout& L = p.L;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_init(&empty[0], nwarps);
+        mbar_init(&empty[1], nwarps);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const long long gi = blockIdx.x;
+    const long long b = gi / L.NG;
+    const int g = (int)(gi - b * L.NG);
+    const int f = g * OIVA_GROUP + lane;
+    const bool bin_ok = f < L.F;
+    const int k0 = warp * KC;
+    const int Tp = L.frame_pitch();
+    cplx w[M][KC];
+    load_filters<M, KC>(w, p, b * L.F + (bin_ok ? f : 0), gi, lane, bin_ok, k0);
+    const XC* xg = reinterpret_cast<const XC*>(p.Xg) + (size_t)gi * L.group_elems();
+    const int nblk = Tp / POWER_FB;
+    const int blk0 = (int)((long long)nblk * blockIdx.y / p.nsplit);
+    const int blk1 = (int)((long long)nblk * (blockIdx.y + 1) / p.nsplit);
+    // producer: thread 0 keeps one block in flight ahead of the consumers
+    auto issue = [&](int blk, int stage, int use) {
+        const int t0 = blk * POWER_FB;
+        const int nfr = min(POWER_FB, L.T - t0);
+        if (use > 0) mbar_wait(&empty[stage], (use - 1) & 1);
+        if (nfr > 0) {
+            const uint32_t bytes = (uint32_t)((size_t)nfr * M * OIVA_GROUP * sizeof(XC));
+            mbar_arrive_expect_tx(&full[stage], bytes);
+            tma_load_1d(stage0 + (size_t)stage * stage_bytes, xg + (size_t)t0 * M * OIVA_GROUP, bytes, &full[stage]);
+        } else {
+            mbar_arrive(&full[stage]);  // a block made of padding frames only: nothing to copy
+        }
+    };
+    if (threadIdx.x == 0 && blk0 < blk1) issue(blk0, 0, 0);
+    int it = 0;
+    for (int blk = blk0; blk < blk1; ++blk, ++it) {
+        const int stage = it & 1, use = it >> 1;
+        if (threadIdx.x == 0 && blk + 1 < blk1) issue(blk + 1, (it + 1) & 1, (it + 1) >> 1);
+        mbar_wait(&full[stage], use & 1);
+        const XC* xs = reinterpret_cast<const XC*>(stage0 + (size_t)stage * stage_bytes);
+        const int t0 = blk * POWER_FB;
+        double v[KC][POWER_FB];
+#pragma unroll
+        for (int j = 0; j < POWER_FB; ++j) {
+            cplx x[M], y[KC];
+            if (t0 + j < L.T) {
+#pragma unroll
+                for (int c = 0; c < M; ++c) x[c] = widen(xs[((size_t)j * M + c) * OIVA_GROUP + lane]);
+                demix_frame<M, KC>(y, x, w);
+#pragma unroll
+                for (int k = 0; k < KC; ++k) v[k][j] = fma(y[k].x, y[k].x, y[k].y * y[k].y);
+            } else {
+#pragma unroll
+                for (int k = 0; k < KC; ++k) v[k][j] = 0.0;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+#pragma unroll
+            for (int lvl = 0; lvl < 3; ++lvl) {
+                const int H = POWER_FB >> (lvl + 1);
+                const int off = 16 >> lvl;
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int n = 0; n < H; ++n) {
+                    const double lo = v[k][n], hi = v[k][n + H];
+                    const double send = up ? lo : hi;
+                    const double keep = up ? hi : lo;
+                    v[k][n] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            double sres = v[k][0];
+            sres += __shfl_xor_sync(0xffffffffu, sres, 2);
+            sres += __shfl_xor_sync(0xffffffffu, sres, 1);
+            if ((lane & 3) == 0 && k0 + k < p.K) p.r2part[((size_t)gi * p.K + k0 + k) * Tp + t0 + (lane >> 2)] = sres;
+        }
+    }
+}
+
 // grid (G, nsplit), block = 32 * ceil(K/KC)
 template <typename ST, int M, int KC>
 __global__ void __launch_bounds__(512) k_demix_output(const StreamParams p) {

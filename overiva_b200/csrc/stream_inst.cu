@@ -1,4 +1,6 @@
 // Instantiates the streaming demix kernels for ONE channel count (-DOIVA_M=<M>); see stream.cuh.
+#include <stdlib.h>
+
 #include "stream.cuh"
 
 #ifndef OIVA_M
@@ -39,7 +41,22 @@ static int launch(int kind, StreamParams p, long long G, cudaStream_t st) {
         const int units = kind == KIND_POWER ? p.L.frame_pitch() / POWER_FB : p.L.T;
         p.nsplit = frame_splits(G, units);
         dim3 grid((unsigned)G, p.nsplit, 1);
-        if (kind == KIND_POWER)
+        static const bool no_staged = [] {
+            const char* v = getenv("OIVA_POWER_NO_STAGE");
+            return v && *v && *v != '0';
+        }();
+        if (kind == KIND_POWER && warps > 1 && !no_staged) {
+            // several source-chunk warps per group: stage X once per CTA instead of once per warp
+            typedef typename StoreC<ST>::type XC;
+            const size_t smem = 128 + 2 * (size_t)POWER_FB * M * OIVA_GROUP * sizeof(XC);
+            auto kern = k_demix_power_staged<ST, M, KC>;
+            static bool attr_done = false;
+            if (!attr_done) {
+                OIVA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_done = true;
+            }
+            kern<<<grid, 32 * warps, smem, st>>>(p);
+        } else if (kind == KIND_POWER)
             k_demix_power<ST, M, KC><<<grid, 32 * warps, 0, st>>>(p);
         else if (kind == KIND_OUTPUT)
             k_demix_output<ST, M, KC><<<grid, 32 * warps, 0, st>>>(p);

@@ -166,7 +166,8 @@ def test_weighted_covariance_deterministic_split():
 
 @pytest.mark.parametrize("M,K,n_samples,dtype", [(4, 2, 1500, np.complex128), (6, 6, 1200, np.complex128),
                                                   (8, 3, 5000, np.complex128), (16, 4, 2300, np.complex128),
-                                                  (5, 1, 1500, np.complex64), (10, 10, 900, np.complex128)])
+                                                  (5, 1, 1500, np.complex64), (10, 10, 900, np.complex128),
+                                                  (7, 7, 2000, np.complex64), (3, 3, 700, np.complex128)])
 def test_demix_power(M, K, n_samples, dtype):
     B = 2
     X = _mix(4, M, n_samples, 64 if M % 2 == 0 else 32, dtype, B=B)
