@@ -391,7 +391,10 @@ struct CovBlock {
     }
 };
 
-// one team of cov_block_parts(M) warps per CTA
+// one team of cov_block_parts(M) warps per CTA.  Register budget: the 10 warps of M = 13..16 put 3 warps on one SM
+// sub-partition, 3 x 32 x R <= 16384 caps R at 168 (what ptxas picks from the launch bounds; a larger __maxnreg__ makes
+// the launch fail), and 128 of those hold the 4 x 4 x KC=2 complex accumulators -- staging the products of a block row
+// before accumulating them (more ILP against the "wait" stalls ncu shows) spills.  The kernel is register-file-bound.
 template <typename ST, int M, int KC, bool USE_TMA>
 __global__ void __launch_bounds__(cov_block_parts(M) * 32) k_cov_blocked(const CovParams p, int team_smem_bytes) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
