@@ -20,6 +20,9 @@ Different by necessity (no pyroomacoustics / CMU ARCTIC / mir_eval offline): mix
 ``overiva_b200.synth.convolutive_mixture`` (seeded Laplacian sources, random RIRs, same SINR / SNR mixing rules,
 ``overiva_sim.py:163-192``) and SDR / SIR from ``overiva_b200.metrics.bss_eval``.  ``runtime`` is the wall time of the
 batched algorithm call divided by the batch size (seconds per mixture, STFT excluded like ``overiva_sim.py:293-320``).
+With ``monitor_convergence`` (``overiva_sim.py:272-284``) every mixture runs on its own with the convergence callback
+-- scored on the device by ``overiva_b200.monitor`` -- and ``sdr`` / ``sir`` hold one entry per callback plus the final
+evaluation; otherwise ``[initial, final]``.
 """
 from __future__ import annotations
 
@@ -103,6 +106,10 @@ def make_mixture(parameters, arg):
     return mix, ref
 
 
+def _noise_channel(m, noise_seed):
+    return np.random.default_rng(noise_seed).standard_normal(m)  # "fill this to compare to background"
+
+
 def evaluate(y, ref, n_targets, framesize, reorder, noise_seed=0):
     """``convergence_callback`` (``overiva_sim.py:210-232``): y (N', J) time-domain outputs -> (sdr, sir) lists of
     length n_targets, scored at the reference microphone 0."""
@@ -113,7 +120,7 @@ def evaluate(y, ref, n_targets, framesize, reorder, noise_seed=0):
     m = int(min(y.shape[0] - half, ref.shape[1]))
     est = np.zeros((n_targets + 1, m))
     est[:n_targets] = y[half : m + half, :n_targets].T
-    est[n_targets] = np.random.default_rng(noise_seed).standard_normal(m)  # "fill this to compare to background"
+    est[n_targets] = _noise_channel(m, noise_seed)
     sdr, sir, _ = metrics.bss_eval(ref[: n_targets + 1, :m, 0], est)
     return sdr[:n_targets].tolist(), sir[:n_targets].tolist()
 
@@ -141,6 +148,46 @@ class GpuEngine:
 
     def synthesis(self, Y):
         return self.stft.synthesis(Y, self.L, self.hop, win=self.win_s).cpu().numpy()
+
+    def run_monitored(self, algo, Xb, n_targets, kwargs, ref, reorder, noise_seed):
+        """One mixture with the reference's convergence callback (``overiva_sim.py:272-284``) kept on the device:
+        every 10 epochs (100 for ogive) the estimate is synthesised and scored without leaving the GPU (one Gram
+        kernel; ``overiva_b200.monitor``).  -> (Y device (T, F, K), seconds, sdr list, sir list)."""
+        torch, core = self.torch, self.core
+        from . import monitor
+
+        half = self.L // 2
+        refd = torch.from_numpy(np.ascontiguousarray(ref[: n_targets + 1, :, 0])).to(self.device)
+        sdrs, sirs = [], []
+
+        def cb(Y):
+            y = self.stft.synthesis(Y, self.L, self.hop, win=self.win_s)  # (N', K) on the device
+            if reorder:
+                y = y[:, torch.argsort(y.std(dim=0), descending=True)]
+            m = int(min(y.shape[0] - half, refd.shape[1]))
+            est = torch.empty((n_targets + 1, m), dtype=torch.float64, device=self.device)
+            est[:n_targets] = y[half : m + half, :n_targets].T
+            est[n_targets] = torch.from_numpy(_noise_channel(m, noise_seed)).to(self.device)
+            sdr, sir, _ = monitor.bss_eval_device(refd[:, :m], est)
+            sdrs.append(sdr[:n_targets].tolist())
+            sirs.append(sir[:n_targets].tolist())
+
+        torch.cuda.synchronize(self.device)
+        t0 = time.perf_counter()
+        if algo == "auxiva":
+            Y = core.overiva(Xb, None, callback=cb, **kwargs)
+        elif algo == "overiva":
+            Y = core.overiva(Xb, n_targets, callback=cb, **kwargs)
+        elif algo == "auxiva_pca":
+            Y = core.auxiva_pca(Xb, n_src=n_targets, callback=cb, **kwargs)
+        elif algo == "ogive":
+            Y = core.ogive(Xb, callback=cb, **kwargs)
+        else:
+            raise ValueError(algo)
+        torch.cuda.synchronize(self.device)
+        dt = time.perf_counter() - t0
+        cb(Y)  # "the last evaluation" (overiva_sim.py:320-330)
+        return Y, dt, sdrs, sirs
 
     def run(self, algo, X, n_targets, kwargs):
         """-> (Y device (B, T, F, K), seconds per mixture)."""
@@ -189,7 +236,25 @@ def run(parameters=None, results_dir=None, batch=64, engine=None, progress=None)
             y0 = engine.synthesis(X[..., :n_targets])
             init = [evaluate(y0[b], refs[b], n_targets, framesize, True, args[i][4]) for b, i in enumerate(chunk)]
             recs = [[] for _ in chunk]
+            monitored = bool(parameters.get("monitor_convergence", False))
             for full_name, algo, kwargs in algos:
+                if monitored:
+                    # overiva_sim.py:272-284: the callback scores the estimate every 10 epochs; one mixture at a time
+                    # (the batched entry point has no callback), the scoring itself stays on the device
+                    for b, i in enumerate(chunk):
+                        n_t, n_m, rt60, sinr, seed = args[i]
+                        try:
+                            _, dt, sdrs, sirs = engine.run_monitored(algo, X[b], n_targets, kwargs, refs[b],
+                                                                     full_name not in overdet, seed)
+                        except np.linalg.LinAlgError:
+                            dt, sdrs, sirs = float("nan"), [[float("nan")]], [[float("nan")]]
+                        recs[b].append({
+                            "algorithm": full_name, "n_targets": n_t, "n_mics": n_m, "rt60": rt60, "sinr": sinr,
+                            "seed": seed, "sdr": sdrs, "sir": sirs, "runtime": dt, "n_samples": int(n_samples),
+                        })
+                    if progress:
+                        progress(full_name, n_targets, n_mics, len(chunk), recs[-1][-1]["runtime"])
+                    continue
                 try:
                     Y, per_mix = engine.run(algo, X, n_targets, kwargs)
                     y = engine.synthesis(Y)

@@ -42,6 +42,23 @@ class OracleEngine:
     def synthesis(self, Y):
         return np.stack([so.synthesis(y, self.L, self.hop, win=self.win_s) for y in Y])
 
+    def run_monitored(self, algo, Xb, n_targets, kwargs, ref, reorder, noise_seed):
+        sdrs, sirs = [], []
+
+        def cb(Y):
+            sdr, sir = sweep.evaluate(so.synthesis(Y, self.L, self.hop, win=self.win_s), ref, n_targets, self.L, reorder,
+                                      noise_seed)
+            sdrs.append(sdr)
+            sirs.append(sir)
+
+        fn = {"auxiva": lambda x: orc.overiva(x, callback=cb, **kwargs),
+              "overiva": lambda x: orc.overiva(x, n_src=n_targets, callback=cb, **kwargs),
+              "auxiva_pca": lambda x: orc.auxiva_pca(x, n_src=n_targets, callback=cb, **kwargs),
+              "ogive": lambda x: orc.ogive(x, callback=cb, **kwargs)}[algo]
+        Y = fn(Xb)
+        cb(Y)
+        return Y, 0.25, sdrs, sirs
+
     def run(self, algo, X, n_targets, kwargs):
         fn = {"auxiva": lambda x: orc.overiva(x, **kwargs), "overiva": lambda x: orc.overiva(x, n_src=n_targets, **kwargs),
               "auxiva_pca": lambda x: orc.auxiva_pca(x, n_src=n_targets, **kwargs), "ogive": lambda x: orc.ogive(x, **kwargs)}[algo]
@@ -108,6 +125,39 @@ def test_separation_improves_sir():
              overdet_algos=["overiva_laplace"])
     rows = sweep.summarise(sweep.run(p, engine=OracleEngine(64)), p["fs"])
     assert rows[0]["sir_improvement"] > 3.0
+
+
+def test_monitor_convergence_mode():
+    """overiva_sim.py:272-284: with monitor_convergence the sdr / sir lists hold one entry per callback (epochs 0, 10,
+    ...) plus the final evaluation, instead of [initial, final]."""
+    algs = {"overiva_laplace": {"algo": "overiva", "kwargs": {"n_iter": 25, "proj_back": True, "model": "laplace"}},
+            "auxiva_laplace": {"algo": "auxiva", "kwargs": {"n_iter": 12, "proj_back": True, "model": "laplace"}}}
+    p = dict(PARAMS, n_targets_list=[2], n_mics_list=[3], n_repeat=2, monitor_convergence=True, algorithm_kwargs=algs,
+             overdet_algos=["overiva_laplace"], duration=1.0)
+    segs = sweep.run(p, engine=OracleEngine(64))
+    assert len(segs) == 2
+    for seg in segs:
+        by = {r["algorithm"]: r for r in seg}
+        assert len(by["overiva_laplace"]["sdr"]) == 3 + 1 and len(by["auxiva_laplace"]["sdr"]) == 2 + 1
+        assert all(len(v) == 2 for v in by["overiva_laplace"]["sir"])
+        assert by["overiva_laplace"]["runtime"] == 0.25
+    # over the sweep the separation improves between the first callback (before any update) and the final evaluation
+    assert np.mean([np.mean(s[0]["sir"][-1]) - np.mean(s[0]["sir"][0]) for s in segs]) > 0
+    rows = sweep.summarise(segs, p["fs"])  # first entry = before the first update, last = final: improvements defined
+    assert all(np.isfinite(r["sir_improvement"]) for r in rows)
+
+
+@pytest.mark.gpu
+def test_gpu_monitored_sweep_matches_the_oracle_engine():
+    algs = {"overiva_laplace": {"algo": "overiva", "kwargs": {"n_iter": 12, "proj_back": True, "model": "laplace"}}}
+    p = dict(PARAMS, n_targets_list=[2], n_mics_list=[3], n_repeat=2, monitor_convergence=True, algorithm_kwargs=algs,
+             overdet_algos=["overiva_laplace"])
+    ref = sweep.run(p, engine=OracleEngine(64))
+    got = sweep.run(p)
+    for sg, sr in zip(got, ref):
+        for rg, rr in zip(sg, sr):
+            assert len(rg["sdr"]) == len(rr["sdr"]) == 3
+            assert np.allclose(rg["sdr"], rr["sdr"], atol=1e-6) and np.allclose(rg["sir"], rr["sir"], atol=1e-6)
 
 
 @pytest.mark.gpu
