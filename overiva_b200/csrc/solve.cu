@@ -314,6 +314,8 @@ static int bins_per_cta() {
 namespace oiva {
 int ip_update_tpb(int M, int K, cplx* What, const cplx* Vg, const cplx* Cg, const double* wscale, int* status, int F,
                   int NG, long long G, cudaStream_t st);
+int ip_update_smem(int M, int K, cplx* Wg, const cplx* Vg, const cplx* Cg, const double* wscale, int* status, int F,
+                   int NG, long long G, cudaStream_t st);
 }
 
 extern "C" int oiva_ip_update(void* What, const void* V, const void* C, const void* Cg, const double* wscale,
@@ -329,6 +331,12 @@ extern "C" int oiva_ip_update(void* What, const void* V, const void* C, const vo
         const int NG = oiva_bin_groups(n_freq);
         int rc = ip_update_tpb(n_chan, n_src, (cplx*)What, (const cplx*)V, (const cplx*)Cg, wscale, status, n_freq, NG,
                                (long long)n_batch * NG, st);
+        if (rc != OIVA_ERR_INVALID) return rc;
+    }
+    if (Cg && n_chan >= 7 && !force_rowowner) {  // thread-per-bin with the matrices in shared memory (solve_smem.cu)
+        const int NG = oiva_bin_groups(n_freq);
+        int rc = ip_update_smem(n_chan, n_src, (cplx*)What, (const cplx*)V, (const cplx*)Cg, wscale, status, n_freq, NG,
+                                (long long)n_batch * NG, st);
         if (rc != OIVA_ERR_INVALID) return rc;
     }
     OIVA_DISPATCH_M(n_chan, {

@@ -198,10 +198,10 @@ def test_source_model(model):
         assert rel_err(ws[b], 1.0 / w_scale) < 1e-14
 
 
-@pytest.mark.parametrize("grouped_c", [True, False])  # thread-per-bin sweep (M <= 6; M = 7, 8 with K <= 4) / lane-group-per-bin sweep
+@pytest.mark.parametrize("grouped_c", [True, False])  # thread-per-bin sweep (registers: M <= 6, M = 7, 8 with K <= 4; shared memory: other M >= 7) / lane-group-per-bin sweep
 @pytest.mark.parametrize("M,K", [(4, 2), (6, 2), (6, 6), (3, 3), (2, 1), (8, 2), (5, 4), (16, 4), (16, 16), (1, 1), (9, 3),
                                  (6, 1), (6, 4), (5, 5), (4, 3), (7, 1), (7, 3), (7, 4), (8, 1), (8, 4), (8, 5), (7, 7),
-                                 (8, 8)])
+                                 (8, 8), (12, 12), (13, 2), (16, 15), (10, 1)])
 def test_ip_update_sweep(M, K, grouped_c):
     X = _mix(9, M, 1500, 64 if M % 2 == 0 else 32)[0]
     T, F, _ = X.shape
@@ -223,6 +223,13 @@ def test_ip_update_sweep(M, K, grouped_c):
         orc.ip_update_source(want, V[:, s], Cx, s, K)
     assert status == 0
     assert rel_err(got[0], want) < 1e-11
+
+
+@pytest.mark.parametrize("M,K", [(8, 8), (7, 5), (9, 3), (16, 16), (12, 1)])
+def test_ip_update_sweep_shared_memory_variant(M, K, monkeypatch):
+    """The opt-in thread-per-bin sweep with per-lane matrices in shared memory (solve_smem.cu)."""
+    monkeypatch.setenv("OIVA_SOLVER_SMEM", "1")
+    test_ip_update_sweep(M, K, True)
 
 
 def test_ip_update_flags_singular():
