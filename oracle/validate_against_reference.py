@@ -47,6 +47,23 @@ def cases():
     yield "ogive early stop", "ogive", (3, 32), dict(n_iter=400, tol=5e-2)
 
 
+# edge shapes of tests/test_edge_gpu.py (T, F, M, K, model): the GPU tests compare with the oracle on exactly these
+# inputs, so the oracle is pinned against the reference on them too
+EDGE_TOL = 1e-11
+EDGE_SHAPES = [(40, 1, 3, 2, "laplace"), (7, 33, 2, 2, "gauss"), (3, 5, 2, 1, "laplace"), (50, 17, 1, 1, "laplace"),
+               (64, 9, 16, 16, "laplace"), (300, 9, 16, 4, "gauss"), (90, 40, 9, 3, "laplace"), (60, 64, 7, 7, "gauss")]
+
+
+def run_edge(T, F, M, K, model):
+    from overiva_b200.synth import stft_domain_mixture
+
+    X = stft_domain_mixture(T * 1000 + F * 10 + M, T, F, M, K, n_interferers=min(3, max(0, M - K)), noise_db=-30.0)
+    kw = dict(n_src=K, n_iter=5, model=model)
+    Yr, Wr = ref.ref_overiva(X, return_filters=True, **kw)
+    Yo, Wo = orc.overiva(X, return_filters=True, **kw)
+    return {"Y": rel(Yo, Yr), "W": rel(Wo, Wr)}
+
+
 def run_case(kind, shape, kwargs, seed):
     M, frame = shape
     X = small_test_mixture(seed, M, 2, frame=frame, hop=frame // 2)
@@ -89,6 +106,13 @@ def main():
         ok = all(e <= tol for e in errs.values())
         worst = max(worst, *(e / tol for e in errs.values()))
         print("%-32s %s %s" % (name, " ".join("%s=%.2e" % kv for kv in errs.items()), "ok" if ok else "FAIL"))
+    for T, F, M, K, model in EDGE_SHAPES:
+        errs = run_edge(T, F, M, K, model)
+        # the 16- and 9-channel cases amplify a 1e-15 perturbation of X to ~1e-12 on W in the reference itself
+        ok = all(e <= EDGE_TOL for e in errs.values())
+        worst = max(worst, *(e / EDGE_TOL for e in errs.values()))
+        print("%-32s %s %s" % ("edge T%d F%d M%d K%d %s" % (T, F, M, K, model),
+                               " ".join("%s=%.2e" % kv for kv in errs.items()), "ok" if ok else "FAIL"))
     # callback cadence (overiva.py:142: epochs 0, 10, 20, ... before that epoch's update)
     X = small_test_mixture(7, 3, 2, n_samples=1000, frame=16, hop=8)
     got_r, got_o = [], []

@@ -21,6 +21,7 @@ if torch.cuda.is_available():
 TOL = 1e-10
 
 
+# (the same list is pinned against the unmodified reference by oracle/validate_against_reference.py::EDGE_SHAPES)
 @pytest.mark.parametrize("T,F,M,K,model", [
     (40, 1, 3, 2, "laplace"),      # a single frequency bin (31 padded lanes)
     (7, 33, 2, 2, "gauss"),        # fewer frames than one staging chunk; 33 bins = one full group + one bin
