@@ -37,7 +37,10 @@ static int choose_split(long long G, int nchunks, long long n_teams, long long m
     return best;
 }
 
-constexpr int COV_MAX_PARTS = 16;
+// Every part of the 1-D entry split is its own unrolled code path: beyond 4 parts the kernel starves on instruction
+// fetch (measured at M = K = 8, 256 mixtures: 8 sources per pass = 8 parts 17.6 ms; two passes of 4 sources = 4 parts
+// each are 3x faster although X is read twice).  Larger splits are not instantiated.
+constexpr int COV_MAX_PARTS = 4;
 constexpr bool COV_USE_BLOCKS = OIVA_COV_M >= 9;
 
 // shared launch logic: ring sizing, persistent grid, frame splitting for few groups
@@ -145,16 +148,12 @@ static int launch(CovParams p, cudaStream_t st, int* nsplit_out) {
 int OIVA_CAT(cov_max_kc_m, OIVA_COV_M)() {
     constexpr int M = OIVA_COV_M;
     if (COV_USE_BLOCKS) return 2;
-    // Every part of the 1-D entry split is its own unrolled code path: beyond 4 parts the kernel starves on
-    // instruction fetch (measured at M = K = 8, 256 mixtures: 8 sources per pass = 8 parts 17.6 ms; two passes of
-    // 4 sources = 4 parts each are 3x faster although X is read twice).
-    constexpr int MAX_PARTS_FAST = 4;
     int best = 1;
-    if (cov_parts(M, 2) <= MAX_PARTS_FAST) best = 2;
-    if (cov_parts(M, 3) <= MAX_PARTS_FAST) best = 3;
-    if (cov_parts(M, 4) <= MAX_PARTS_FAST) best = 4;
-    if (cov_parts(M, 6) <= MAX_PARTS_FAST) best = 6;
-    if (cov_parts(M, 8) <= MAX_PARTS_FAST) best = 8;
+    if (cov_parts(M, 2) <= COV_MAX_PARTS) best = 2;
+    if (cov_parts(M, 3) <= COV_MAX_PARTS) best = 3;
+    if (cov_parts(M, 4) <= COV_MAX_PARTS) best = 4;
+    if (cov_parts(M, 6) <= COV_MAX_PARTS) best = 6;
+    if (cov_parts(M, 8) <= COV_MAX_PARTS) best = 8;
     return best;
 }
 
