@@ -51,3 +51,92 @@ def bss_eval(refs, ests):
     perm = np.array(best_perm)
     ks = np.arange(K)
     return sdr[perm, ks], sir[perm, ks], perm
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BSS Eval v3 with time-invariant distortion FILTERS -- what ``mir_eval.separation.bss_eval_sources`` computes (the
+# metric of the reference's drivers and of its published ``data.json``; mir_eval is third-party and absent offline,
+# so this restates the published algorithm of Vincent, Gribonval and Fevotte, "Performance measurement in blind audio
+# source separation", IEEE TASLP 2006: PARITY UNPINNED against mir_eval itself).  ``bss_eval`` above is its
+# ``flen = 1`` special case and is what the device-side monitor evaluates; this one is for final scoring on the host.
+# ---------------------------------------------------------------------------------------------------------------
+def _delayed_gram(refs, flen):
+    """G[(k, a), (l, b)] = sum_n refs[k][n - a] refs[l][n - b] for 0 <= a, b < flen (block Toeplitz), via FFT."""
+    K, N = refs.shape
+    nfft = 1 << int(np.ceil(np.log2(N + flen)))
+    Rf = np.fft.rfft(refs, nfft, axis=1)
+    G = np.empty((K * flen, K * flen))
+    idx = np.arange(flen)
+    lag = idx[:, None] - idx[None, :]  # a - b
+    for k in range(K):
+        for l in range(k, K):
+            # c[m] = sum_n refs[k][n] refs[l][n + m]  =>  entry (a, b) = c[a - b]
+            c = np.fft.irfft(np.conj(Rf[k]) * Rf[l], nfft)
+            blk = c[lag % nfft]
+            G[k * flen : (k + 1) * flen, l * flen : (l + 1) * flen] = blk
+            if l != k:
+                G[l * flen : (l + 1) * flen, k * flen : (k + 1) * flen] = blk.T
+    return G
+
+
+def _project(refs, est, flen, G=None):
+    """Least-squares projection of ``est`` on the span of the references delayed by 0..flen-1 samples; signals of
+    length N are treated as zero-padded to N + flen - 1 (as mir_eval does).  Returns the projection (N + flen - 1,)."""
+    K, N = refs.shape
+    nfft = 1 << int(np.ceil(np.log2(N + flen)))
+    if G is None:
+        G = _delayed_gram(refs, flen)
+    Rf = np.fft.rfft(refs, nfft, axis=1)
+    Ef = np.fft.rfft(est, nfft)
+    D = np.empty(K * flen)
+    for k in range(K):
+        c = np.fft.irfft(np.conj(Rf[k]) * Ef, nfft)  # c[a] = sum_n refs[k][n] est[n + a]
+        D[k * flen : (k + 1) * flen] = c[:flen]
+    try:
+        C = np.linalg.solve(G, D)
+    except np.linalg.LinAlgError:
+        C = np.linalg.lstsq(G, D, rcond=None)[0]
+    C = C.reshape(K, flen)
+    out = np.zeros(N + flen - 1)
+    for k in range(K):
+        out += np.convolve(refs[k], C[k])[: N + flen - 1]
+    return out
+
+
+def bss_eval_sources(refs, ests, flen=512, compute_permutation=True):
+    """``mir_eval.separation.bss_eval_sources(reference_sources, estimated_sources)`` restated: refs (K, N), ests
+    (K, N) -> ``(sdr, sir, sar, perm)`` with ``ests[perm[k]]`` the estimate of source k (the permutation maximising
+    the mean SIR, as mir_eval does).  Distortion filters of ``flen`` taps (mir_eval's default: 512)."""
+    refs = np.atleast_2d(np.asarray(refs, dtype=np.float64))
+    ests = np.atleast_2d(np.asarray(ests, dtype=np.float64))
+    if refs.shape != ests.shape:
+        raise ValueError("refs and ests must have the same shape, got %s and %s" % (refs.shape, ests.shape))
+    K, N = refs.shape
+    tiny = np.finfo(float).tiny
+    G = _delayed_gram(refs, flen)
+    sdr = np.empty((K, K))
+    sir = np.empty((K, K))
+    sar = np.empty((K, K))
+    pad = np.zeros(flen - 1)
+    for j in range(K):  # estimate
+        e = np.concatenate([ests[j], pad])
+        p_all = _project(refs, ests[j], flen, G)
+        for k in range(K):  # scored as source k
+            s_t = _project(refs[k : k + 1], ests[j], flen, G[k * flen : (k + 1) * flen, k * flen : (k + 1) * flen])
+            e_i = p_all - s_t
+            e_a = e - p_all
+            pt = float(s_t @ s_t)
+            sdr[j, k] = 10 * np.log10(max(pt, tiny) / max(float((e_i + e_a) @ (e_i + e_a)), tiny))
+            sir[j, k] = 10 * np.log10(max(pt, tiny) / max(float(e_i @ e_i), tiny))
+            sar[j, k] = 10 * np.log10(max(float((s_t + e_i) @ (s_t + e_i)), tiny) / max(float(e_a @ e_a), tiny))
+    if compute_permutation:
+        best, perm = -np.inf, None
+        for cand in itertools.permutations(range(K)):
+            score = np.mean([sir[cand[k], k] for k in range(K)])
+            if score > best:
+                best, perm = score, cand
+        perm = np.array(perm)
+    else:
+        perm = np.arange(K)
+    ks = np.arange(K)
+    return sdr[perm, ks], sir[perm, ks], sar[perm, ks], perm

@@ -18,7 +18,9 @@ Kept from the reference:
 
 Different by necessity (no pyroomacoustics / CMU ARCTIC / mir_eval offline): mixtures come from
 ``overiva_b200.synth.convolutive_mixture`` (seeded Laplacian sources, random RIRs, same SINR / SNR mixing rules,
-``overiva_sim.py:163-192``) and SDR / SIR from ``overiva_b200.metrics.bss_eval``.  ``runtime`` is the wall time of the
+``overiva_sim.py:163-192``) and SDR / SIR from ``overiva_b200.metrics`` (``bss_eval``, one-tap distortion, by default;
+``"bss_eval_filter_length": 512`` in the parameters selects ``bss_eval_sources``, the restatement of mir_eval's
+512-tap metric, for the initial / final scores).  ``runtime`` is the wall time of the
 batched algorithm call divided by the batch size (seconds per mixture, STFT excluded like ``overiva_sim.py:293-320``).
 With ``monitor_convergence`` (``overiva_sim.py:272-284``) every mixture runs on its own with the convergence callback
 -- scored on the device by ``overiva_b200.monitor`` -- and ``sdr`` / ``sir`` hold one entry per callback plus the final
@@ -110,9 +112,10 @@ def _noise_channel(m, noise_seed):
     return np.random.default_rng(noise_seed).standard_normal(m)  # "fill this to compare to background"
 
 
-def evaluate(y, ref, n_targets, framesize, reorder, noise_seed=0):
+def evaluate(y, ref, n_targets, framesize, reorder, noise_seed=0, flen=1):
     """``convergence_callback`` (``overiva_sim.py:210-232``): y (N', J) time-domain outputs -> (sdr, sir) lists of
-    length n_targets, scored at the reference microphone 0."""
+    length n_targets, scored at the reference microphone 0.  ``flen``: taps of the allowed distortion filter -- 1 is
+    the fast one-tap metric, 512 is what ``mir_eval.separation.bss_eval_sources`` uses (``metrics.bss_eval_sources``)."""
     y = np.asarray(y, dtype=np.float64)
     if reorder:
         y = y[:, np.argsort(np.std(y, axis=0))[::-1]]
@@ -121,7 +124,10 @@ def evaluate(y, ref, n_targets, framesize, reorder, noise_seed=0):
     est = np.zeros((n_targets + 1, m))
     est[:n_targets] = y[half : m + half, :n_targets].T
     est[n_targets] = _noise_channel(m, noise_seed)
-    sdr, sir, _ = metrics.bss_eval(ref[: n_targets + 1, :m, 0], est)
+    if flen > 1:
+        sdr, sir, _, _ = metrics.bss_eval_sources(ref[: n_targets + 1, :m, 0], est, flen=flen)
+    else:
+        sdr, sir, _ = metrics.bss_eval(ref[: n_targets + 1, :m, 0], est)
     return sdr[:n_targets].tolist(), sir[:n_targets].tolist()
 
 
@@ -223,6 +229,7 @@ def run(parameters=None, results_dir=None, batch=64, engine=None, progress=None)
     for i, a in enumerate(args):
         groups.setdefault((a[0], a[1]), []).append(i)
     overdet = set(parameters.get("overdet_algos", []))
+    flen = int(parameters.get("bss_eval_filter_length", 1))  # 512 = mir_eval's bss_eval_sources (host, slower)
     for (n_targets, n_mics), idx in groups.items():
         algos = algorithms_for(parameters, n_targets)
         for c0 in range(0, len(idx), batch):
@@ -234,7 +241,7 @@ def run(parameters=None, results_dir=None, batch=64, engine=None, progress=None)
             X = engine.analysis(mixes)
             # initial SDR / SIR: the microphone signals themselves as the estimate (overiva_sim.py:236-242)
             y0 = engine.synthesis(X[..., :n_targets])
-            init = [evaluate(y0[b], refs[b], n_targets, framesize, True, args[i][4]) for b, i in enumerate(chunk)]
+            init = [evaluate(y0[b], refs[b], n_targets, framesize, True, args[i][4], flen) for b, i in enumerate(chunk)]
             recs = [[] for _ in chunk]
             monitored = bool(parameters.get("monitor_convergence", False))
             for full_name, algo, kwargs in algos:
@@ -258,7 +265,7 @@ def run(parameters=None, results_dir=None, batch=64, engine=None, progress=None)
                 try:
                     Y, per_mix = engine.run(algo, X, n_targets, kwargs)
                     y = engine.synthesis(Y)
-                    final = [evaluate(y[b], refs[b], n_targets, framesize, full_name not in overdet, args[i][4])
+                    final = [evaluate(y[b], refs[b], n_targets, framesize, full_name not in overdet, args[i][4], flen)
                              for b, i in enumerate(chunk)]
                 except np.linalg.LinAlgError:  # the reference logs the failure and records NaN (:333-349)
                     per_mix = float("nan")

@@ -127,6 +127,18 @@ def test_separation_improves_sir():
     assert rows[0]["sir_improvement"] > 3.0
 
 
+def test_filter_based_metric_option():
+    """bss_eval_filter_length > 1 scores with the mir_eval-style filter metric: never lower SDR than the one-tap metric
+    (the allowed distortion is a superset), same record layout."""
+    algs = {"overiva_laplace": {"algo": "overiva", "kwargs": {"n_iter": 10, "proj_back": True, "model": "laplace"}}}
+    p1 = dict(PARAMS, n_targets_list=[2], n_mics_list=[3], n_repeat=1, algorithm_kwargs=algs, overdet_algos=["overiva_laplace"])
+    p2 = dict(p1, bss_eval_filter_length=16)
+    r1 = sweep.run(p1, engine=OracleEngine(64))[0][0]
+    r2 = sweep.run(p2, engine=OracleEngine(64))[0][0]
+    assert len(r2["sdr"]) == 2 and len(r2["sdr"][1]) == 2
+    assert np.all(np.array(r2["sdr"][1]) >= np.array(r1["sdr"][1]) - 1e-9)
+
+
 def test_monitor_convergence_mode():
     """overiva_sim.py:272-284: with monitor_convergence the sdr / sir lists hold one entry per callback (epochs 0, 10,
     ...) plus the final evaluation, instead of [initial, final]."""
