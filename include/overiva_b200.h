@@ -11,8 +11,10 @@
  * Conventions
  *  - plain C: pointers + sizes, no C++/torch types.  All data pointers are DEVICE pointers unless the
  *    name says host.  `stream` is a cudaStream_t passed as void* (NULL = default stream).  All calls
- *    are asynchronous on that stream and return 0 (OIVA_OK) or a negative OIVA_ERR_* / positive
- *    cudaError_t; oiva_last_error() gives a thread-local message.
+ *    are asynchronous on that stream and return 0 (OIVA_OK) or a negative OIVA_ERR_* code (a failing
+ *    CUDA runtime call is OIVA_ERR_CUDA); oiva_last_error() gives a thread-local message with the
+ *    details (for OIVA_ERR_CUDA: the call, the cudaError_t value and its string).  Return values are
+ *    never positive except where a declaration says it returns a status word.
  *  - complex numbers are interleaved (re, im).  "c128" = two doubles, "c64" = two floats.  `dtype`
  *    (OIVA_C128 / OIVA_C64) is the storage type of X and Y only; covariances, demixing matrices and all
  *    on-chip arithmetic are fp64 in both modes.
@@ -25,6 +27,9 @@
  *  - numerical failure (singular pivot / non-finite value; the reference raises
  *    numpy.linalg.LinAlgError from overiva.py:98,182) is reported through a device status word that the
  *    caller reads back when convenient: bit 0 = singular pivot, bit 1 = non-finite result.
+ *    Status words are PER MIXTURE: every `int* status` argument points to n_batch ints (word b belongs to
+ *    mixture b), so that one failing mixture of a batch can be told from the others -- the reference's
+ *    sweep records NaN for the failing mixture only and carries on (overiva_sim.py:334-350).
  */
 #ifndef OVERIVA_B200_H
 #define OVERIVA_B200_H
@@ -40,6 +45,7 @@ extern "C" {
 #define OIVA_ERR_INVALID (-1)
 #define OIVA_ERR_NOMEM (-2)
 #define OIVA_ERR_STATE (-3)
+#define OIVA_ERR_CUDA (-4) /* a CUDA runtime call failed; oiva_last_error() names it */
 
 #define OIVA_C128 0
 #define OIVA_C64 1
@@ -140,28 +146,19 @@ int oiva_source_model(const double* r2part, int n_chunks, double* phi, double* w
 int oiva_ip_update(void* Wg, const void* Vg, const void* C, const void* Cg, const double* wscale, int* status,
                    int n_batch, int n_freq, int n_chan, int n_src, void* stream);
 
-/* Fused variant for M <= 6, K <= 4 (oiva_ip_update_power_supported): the same sweep (thread per bin), and then, with
- * the fresh filters still in registers, the statistic of the NEXT epoch r2part (B,NG,K,Tp) from Xg -- per bin group
- * the sweep of epoch i and the demix-power pass of epoch i+1 only depend on each other, so one warp does both and
- * the sweep's latency hides behind the streaming of the other warps.
- * replaces: overiva.py:161-167,176-190 followed by overiva.py:140,152-155 of the following epoch. */
-int oiva_ip_update_power(void* Wg, const void* Vg, const void* Cg, const double* wscale, int* status,
-                         const void* Xg, double* r2part, int n_batch, int n_frames, int n_freq, int n_chan,
-                         int n_src, int dtype, void* stream);
-int oiva_ip_update_power_supported(int n_chan, int n_src);
-
 /* Build What (R,M,M): W from eye / eigenvectors / W0, then J and the -I block.
  * evecs: (R,M,M) from oiva_eigh (ascending; used when mode == OIVA_INIT_EIG: w_k = conj(v_{M-K+k})).
- * W0: (R,M,K) c128 (mode == OIVA_INIT_W0).                    replaces: overiva.py:89-123 */
+ * W0: (R,M,K) c128 (mode == OIVA_INIT_W0).  status: n_rows / rows_per_mixture words (row r reports to word
+ * r / rows_per_mixture).                                      replaces: overiva.py:89-123 */
 int oiva_init_demix(void* What, const void* C, const void* W0, const void* evecs, int mode, int* status,
-                    int n_rows, int n_chan, int n_src, void* stream);
+                    int n_rows, int rows_per_mixture, int n_chan, int n_src, void* stream);
 
 /* Hermitian eigendecomposition per row (cyclic Jacobi, fp64): evals (R,M) ascending, evecs (R,M,M) with
  * eigenvectors in columns.  lapack_phase != 0 rotates each eigenvector so that its largest-magnitude
- * component is real positive (what zgeev, i.e. np.linalg.eig, returns).
+ * component is real positive (what zgeev, i.e. np.linalg.eig, returns).  status as for oiva_init_demix.
  * replaces: overiva.py:106 / ive.py:110 (np.linalg.eig) and auxiva_pca.py:75 (np.linalg.eigh). */
-int oiva_eigh(const void* C, double* evals, void* evecs, int* status, int n_rows, int n_chan,
-              int lapack_phase, void* stream);
+int oiva_eigh(const void* C, double* evals, void* evecs, int* status, int n_rows, int rows_per_mixture,
+              int n_chan, int lapack_phase, void* stream);
 
 /* W: (R,M,w_cols) c128.  Weff (R,M,K) c128 = W[:, :, k] * z_k with z_k = (w_k^H C e_0)/(w_k^H C w_k)
  * (1 if the denominator is 0) when proj_back != 0, else a plain copy of the W columns.
@@ -291,11 +288,15 @@ void* oiva_plan_what(oiva_plan_t* plan);    /* (R,M,M) c128 row-major; refreshed
                                                oiva_plan_init / oiva_plan_output / oiva_plan_filters */
 void* oiva_plan_cov(oiva_plan_t* plan);     /* (R,M,M) c128, full */
 void* oiva_plan_samples(oiva_plan_t* plan); /* Xg */
-/* the status word (4 ints).  The CALLER zeroes it after oiva_plan_bind (the workspace is uninitialised memory);
- * it then accumulates (atomic OR) over everything the plan runs, across loads, until the caller zeroes it again */
+/* the status words: n_batch ints, one per mixture.  The CALLER zeroes them after oiva_plan_bind (the workspace is
+ * uninitialised memory; oiva_plan_reset_status does it); they then accumulate (atomic OR) over everything the plan
+ * runs, across loads, until the caller zeroes them again */
 int* oiva_plan_status_ptr(oiva_plan_t* plan);
-/* synchronises the stream and returns the status word (0 = fine) */
+int oiva_plan_reset_status(oiva_plan_t* plan, void* stream);
+/* synchronises the stream and returns the OR of all mixtures' status words (0 = fine, > 0 = OIVA_STATUS_* bits,
+ * < 0 = OIVA_ERR_*); status_host (may be NULL) receives the n_batch per-mixture words */
 int oiva_plan_status(oiva_plan_t* plan, void* stream);
+int oiva_plan_status_vector(oiva_plan_t* plan, int* status_host, void* stream);
 /* number of kernels launched by this plan since creation (bench.py's gpu_launches) */
 long long oiva_plan_launch_count(const oiva_plan_t* plan);
 
@@ -308,9 +309,10 @@ int oiva_plan_read_timing(oiva_plan_t* plan, double* ms3, long long* counts3);
 
 /* Convenience: the complete call with HOST buffers (pinned or pageable): H2D of X (B,T,F,M), the loop,
  * D2H of Y (B,T,F,K) [and W (B,F,M,K) c128 if W_host != NULL].  Allocates and frees its own device memory.
- * Returns the status word (>0) on numerical failure. */
+ * Returns 0, a negative OIVA_ERR_* code, or (> 0) the OR of the mixtures' status words on numerical failure;
+ * status_host (may be NULL) receives the n_batch per-mixture words. */
 int oiva_overiva_host(const void* X_host, void* Y_host, void* W_host, const void* W0_host,
-                      const oiva_plan_desc* desc, int n_iter, int proj_back, int init_mode);
+                      const oiva_plan_desc* desc, int n_iter, int proj_back, int init_mode, int* status_host);
 
 #ifdef __cplusplus
 }

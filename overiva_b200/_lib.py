@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "liboveriva_b200.so")
 
 OK = 0
+ERR_INVALID, ERR_NOMEM, ERR_STATE, ERR_CUDA = -1, -2, -3, -4
 C128, C64 = 0, 1
 MODEL_LAPLACE, MODEL_GAUSS, MODEL_NONE, MODEL_OGIVE_LAPLACE, MODEL_OGIVE_GAUSS = 0, 1, 2, 3, 4
 INIT_EYE, INIT_EIG, INIT_W0 = 0, 1, 2
@@ -55,10 +56,8 @@ SIGNATURES = {
     "oiva_sum_partials": (_i, [_p, _i, _p, _i, _i, _i, _p]),
     "oiva_source_model": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
     "oiva_ip_update": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
-    "oiva_ip_update_power": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
-    "oiva_ip_update_power_supported": (_i, [_i, _i]),
-    "oiva_init_demix": (_i, [_p, _p, _p, _p, _i, _p, _i, _i, _i, _p]),
-    "oiva_eigh": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "oiva_init_demix": (_i, [_p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _p]),
+    "oiva_eigh": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "oiva_projback_filters": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _p]),
     "oiva_demix_output": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "oiva_project_rows": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
@@ -95,10 +94,12 @@ SIGNATURES = {
     "oiva_plan_samples": (_p, [_p]),
     "oiva_plan_status_ptr": (_p, [_p]),
     "oiva_plan_status": (_i, [_p, _p]),
+    "oiva_plan_status_vector": (_i, [_p, C.POINTER(C.c_int), _p]),
+    "oiva_plan_reset_status": (_i, [_p, _p]),
     "oiva_plan_launch_count": (C.c_longlong, [_p]),
     "oiva_plan_enable_timing": (_i, [_p, _i]),
     "oiva_plan_read_timing": (_i, [_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
-    "oiva_overiva_host": (_i, [_p, _p, _p, _p, C.POINTER(PlanDesc), _i, _i, _i]),
+    "oiva_overiva_host": (_i, [_p, _p, _p, _p, C.POINTER(PlanDesc), _i, _i, _i, C.POINTER(C.c_int)]),
 }
 
 _lib = None

@@ -1,8 +1,10 @@
 """Python host layer: the reference's entry points on top of the CUDA library.
 
-``overiva``, ``auxiva_pca`` and ``ogive`` keep the exact signatures, argument meaning, return shapes
-and error behaviour of ``overiva.py:28-38``, ``auxiva_pca.py:30`` and ``ive.py:33-45`` of
-onolab-tmu/overiva; ``auxiva`` is ``overiva`` with ``n_src`` omitted (``overiva_oneshot.py:301-309``).
+``overiva``, ``auxiva_pca`` and ``ogive`` keep the exact signatures, argument meaning and return shapes of
+``overiva.py:28-38``, ``auxiva_pca.py:30`` and ``ive.py:33-45`` of onolab-tmu/overiva, and its error behaviour with
+the deviations listed in INTEGRATION.md ("Error behaviour": ``LinAlgError`` for singular bins like the reference,
+also raised when a weighted covariance is not positive definite; NaN results with a ``RuntimeWarning`` where the
+reference returns NaNs silently; ``ValueError`` for more than 16 channels or an unknown ``model`` string); ``auxiva`` is ``overiva`` with ``n_src`` omitted (``overiva_oneshot.py:301-309``).
 Inputs may be numpy arrays (result: numpy), CPU torch tensors (result: CPU torch tensors, pinned when
 the input is pinned) or CUDA torch tensors (result: CUDA tensors, nothing leaves the device).
 
@@ -15,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
+import warnings
 
 import numpy as np
 import torch
@@ -37,6 +40,29 @@ def _stream_ptr(device):
 
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+# Pageable host inputs (numpy arrays) are staged through a cached PINNED buffer: a multi-threaded host copy into
+# it, then one DMA transfer, instead of the driver's own bounce-buffer copy of pageable memory (config 1, numpy in ->
+# numpy out: 4.9 ms -> see DESIGN.md).  Results go to pinned memory from torch's caching host allocator (a freed
+# result's block is reused by the next call, so steady-state calls allocate nothing).
+_STAGING = {}
+_STAGING_LOCK = threading.Lock()
+_STAGING_MAX_BYTES = 256 << 20
+
+
+def _staging_buffer(shape, dtype):
+    nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+    if nbytes == 0 or nbytes > _STAGING_MAX_BYTES:
+        return None
+    key = (tuple(shape), dtype)
+    buf = _STAGING.get(key)
+    if buf is None:
+        while _STAGING and sum(b.numel() * b.element_size() for b in _STAGING.values()) + nbytes > _STAGING_MAX_BYTES:
+            _STAGING.pop(next(iter(_STAGING)))
+        buf = torch.empty(shape, dtype=dtype, pin_memory=True)
+        _STAGING[key] = buf
+    return buf
 
 
 class _Input:
@@ -63,20 +89,32 @@ class _Input:
         if t.dtype not in (torch.complex128, torch.complex64):
             raise TypeError("X must be complex64 or complex128, got %s" % t.dtype)
         self.device = _require_cuda(t.device if t.is_cuda else device)
-        self.dev = t.to(self.device, non_blocking=True).contiguous()
         self.dtype = t.dtype
+        if t.is_cuda or self.pinned:
+            self.dev = t.to(self.device, non_blocking=True).contiguous()
+            return
+        # pageable host memory: stage through the cached pinned buffer (one caller at a time; a concurrent caller
+        # falls back to the plain pageable copy)
+        if _STAGING_LOCK.acquire(blocking=False):
+            try:
+                buf = _staging_buffer(t.shape, t.dtype)
+                if buf is not None:
+                    buf.copy_(t)
+                    self.dev = buf.to(self.device, non_blocking=True)
+                    torch.cuda.current_stream(self.device).synchronize()  # the buffer is reusable from here on
+                    return
+            finally:
+                _STAGING_LOCK.release()
+        self.dev = t.to(self.device).contiguous()
 
     def give_back(self, t, dtype=None):
         if dtype is not None and t.dtype != dtype:
             t = t.to(dtype)
         if self.kind == "cuda":
             return t
-        if self.pinned:
-            out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            out.copy_(t, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-        else:
-            out = t.cpu()
+        out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # torch's caching host allocator
+        out.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
         return out.numpy() if self.kind == "numpy" else out
 
 
@@ -99,11 +137,16 @@ class DemixPlan:
         L.check(self.lib.oiva_plan_bind(h, _ptr(self.ws), nbytes), "oiva_plan_bind")
         self.in_use = False
         self._status_off = self.lib.oiva_plan_status_ptr(h) - self.ws.data_ptr()
-        self.reset_status()  # the status word accumulates from here on (see raise_on_failure)
+        self.reset_status()  # the status words accumulate from here on (see raise_on_failure)
         self.Tp = self.lib.oiva_frame_pitch(n_frames)
 
     def reset_status(self):
-        self.ws[self._status_off : self._status_off + 16].zero_()
+        L.check(self.lib.oiva_plan_reset_status(self.h, _stream_ptr(self.device)), "oiva_plan_reset_status")
+
+    @property
+    def status_words(self):
+        """(B,) int32 view of the per-mixture status words inside the workspace (device tensor)."""
+        return self.ws[self._status_off : self._status_off + 4 * self.B].view(torch.int32)
 
     def __del__(self):
         h, self.h = getattr(self, "h", None), None
@@ -174,17 +217,25 @@ class DemixPlan:
         return W
 
     def status(self):
+        """OR of the mixtures' status words (synchronises the stream); negative = library error."""
         return self.lib.oiva_plan_status(self.h, _stream_ptr(self.device))
 
+    def status_vector(self):
+        """(B,) numpy int32: one status word per mixture (synchronises the stream)."""
+        out = (C.c_int * self.B)()
+        st = self.lib.oiva_plan_status_vector(self.h, out, _stream_ptr(self.device))
+        if st < 0:
+            L.check(st, "oiva_plan_status_vector")
+        return np.frombuffer(out, dtype=np.int32).copy()
+
     def raise_on_failure(self):
-        """The reference raises ``numpy.linalg.LinAlgError('Singular matrix')`` out of overiva.py:98,182."""
+        """See :func:`raise_for_status`."""
         st = self.status()
         if st < 0:
             L.check(st, "oiva_plan_status")
-        if st & L.STATUS_SINGULAR:
-            raise np.linalg.LinAlgError("Singular matrix")
-        if st & L.STATUS_NONFINITE:
-            raise np.linalg.LinAlgError("non-finite value in the demixing matrices")
+        if st == 0:
+            return
+        raise_for_status(self.status_vector() if self.B > 1 else np.array([st], dtype=np.int32))
 
     def enable_timing(self, on=True):
         L.check(self.lib.oiva_plan_enable_timing(self.h, int(on)), "oiva_plan_enable_timing")
@@ -201,12 +252,38 @@ class DemixPlan:
         return int(self.lib.oiva_plan_launch_count(self.h))
 
 
+def raise_for_status(status):
+    """Turn per-mixture status words into the reference's error behaviour.
+
+    * ``STATUS_SINGULAR`` (an exactly zero / NaN pivot in an LU factorisation, or a covariance that is not positive
+      definite in the Cholesky-based update): ``numpy.linalg.LinAlgError("Singular matrix")`` -- what
+      ``np.linalg.solve`` raises out of ``overiva.py:98,182`` on rank-deficient input.
+    * ``STATUS_NONFINITE`` alone (NaN / Inf in the demixing matrices without a singular pivot, e.g. an all-zero
+      input where gamma = 0): the reference silently returns NaN arrays (numpy emits RuntimeWarnings); so does this
+      implementation, with one ``RuntimeWarning``.
+    Any other value is a corrupted status word and raises ``RuntimeError``."""
+    status = np.atleast_1d(np.asarray(status))
+    if np.any((status < 0) | (status > (L.STATUS_SINGULAR | L.STATUS_NONFINITE))):
+        raise RuntimeError("corrupt status words %r" % (status[(status < 0) | (status > 3)][:8],))
+    sing = np.nonzero(status & L.STATUS_SINGULAR)[0]
+    if sing.size:
+        if status.size == 1:
+            raise np.linalg.LinAlgError("Singular matrix")
+        raise np.linalg.LinAlgError("Singular matrix (mixture%s %s of %d)" % (
+            "s" if sing.size > 1 else "", ", ".join(str(i) for i in sing[:16]) + (" ..." if sing.size > 16 else ""),
+            status.size))
+    if np.any(status & L.STATUS_NONFINITE):
+        warnings.warn("non-finite values in the demixing matrices (the reference returns NaN arrays here as well)",
+                      RuntimeWarning, stacklevel=3)
+
+
 # ---- plan cache -------------------------------------------------------------------------------------
 # A plan (workspace + captured CUDA graph of the epoch loop) is reused by later calls of the same shape: for a
 # single short mixture the allocation and the graph capture would otherwise cost more than the separation.
 # Only small plans are kept (default budget 1 GiB, OVERIVA_B200_PLAN_CACHE_MB); a plan in use is never shared.
 _PLAN_CACHE = {}
 _PLAN_CACHE_ORDER = []
+_PLAN_CACHE_LOCK = threading.Lock()  # the cache bookkeeping is shared by every thread that calls the entry points
 
 
 def _plan_cache_budget():
@@ -217,34 +294,42 @@ def _plan_cache_budget():
 
 def _acquire_plan(B, T, F, M, K, model_code, dtype, device, n_freq_total=0):
     key = (B, T, F, M, K, model_code, dtype, torch.device(device).index, n_freq_total)
-    plan = _PLAN_CACHE.get(key)
-    if plan is not None and not plan.in_use:
-        plan.in_use = True
+    with _PLAN_CACHE_LOCK:
+        plan = _PLAN_CACHE.get(key)
+        if plan is not None and not plan.in_use:
+            plan.in_use = True
+            _PLAN_CACHE_ORDER.remove(key)
+            _PLAN_CACHE_ORDER.append(key)
+        else:
+            plan = None
+    if plan is not None:
         plan.reset_status()
-        _PLAN_CACHE_ORDER.remove(key)
-        _PLAN_CACHE_ORDER.append(key)
         return plan
-    plan = DemixPlan(B, T, F, M, K, model_code, dtype, device, n_freq_total)
+    plan = DemixPlan(B, T, F, M, K, model_code, dtype, device, n_freq_total)  # (a concurrent caller gets its own)
     plan.in_use = True
     budget = _plan_cache_budget()
-    if key not in _PLAN_CACHE and plan.ws.numel() <= budget // 2:
-        _PLAN_CACHE[key] = plan
-        _PLAN_CACHE_ORDER.append(key)
-        while sum(_PLAN_CACHE[k].ws.numel() for k in _PLAN_CACHE_ORDER) > budget and len(_PLAN_CACHE_ORDER) > 1:
-            old = _PLAN_CACHE_ORDER.pop(0)
-            del _PLAN_CACHE[old]
+    with _PLAN_CACHE_LOCK:
+        if key not in _PLAN_CACHE and plan.ws.numel() <= budget // 2:
+            _PLAN_CACHE[key] = plan
+            _PLAN_CACHE_ORDER.append(key)
+            while sum(_PLAN_CACHE[k].ws.numel() for k in _PLAN_CACHE_ORDER) > budget and len(_PLAN_CACHE_ORDER) > 1:
+                old = _PLAN_CACHE_ORDER.pop(0)
+                del _PLAN_CACHE[old]
     return plan
 
 
 def _release_plan(plan):
-    plan.in_use = False
+    with _PLAN_CACHE_LOCK:
+        plan.in_use = False
 
 
 def clear_plan_cache():
     """Drop every cached plan (frees their device workspaces)."""
-    _PLAN_CACHE.clear()
-    del _PLAN_CACHE_ORDER[:]
+    with _PLAN_CACHE_LOCK:
+        _PLAN_CACHE.clear()
+        del _PLAN_CACHE_ORDER[:]
     _PIPE_STATE.clear()
+    _STAGING.clear()
 
 
 # Host pipelines (overiva_batch / stft.separate_batch on host inputs) keep their three streams for the life of the
@@ -295,8 +380,9 @@ def _prepare_W0(W0, B, F, M, K, device):
 
 
 def _run_overiva(Xd, n_src, n_iter, proj_back, W0, model, init_eig, return_filters, callback, cb_wrap,
-                 n_freq_total=0):
-    """Xd: (B, T, F, M) CUDA tensor.  Returns (Y (B,T,F,K), W (B,F,M,K) or None, plan)."""
+                 n_freq_total=0, status_out=None):
+    """Xd: (B, T, F, M) CUDA tensor.  Returns (Y (B,T,F,K), W (B,F,M,K) or None, plan).  With ``status_out`` (a list)
+    numerical failures do not raise: the per-mixture status words are appended to it instead."""
     B, T, F, M = Xd.shape
     if n_src is None:
         n_src = M  # overiva.py:83-84
@@ -307,12 +393,14 @@ def _run_overiva(Xd, n_src, n_iter, proj_back, W0, model, init_eig, return_filte
         raise ValueError("at most 16 channels are supported, got %d" % M)
     plan = _acquire_plan(B, T, F, M, n_src, _model_code(model), Xd.dtype, Xd.device, n_freq_total)
     try:
-        return _run_overiva_on(plan, Xd, n_src, n_iter, proj_back, W0, init_eig, return_filters, callback, cb_wrap)
+        return _run_overiva_on(plan, Xd, n_src, n_iter, proj_back, W0, init_eig, return_filters, callback, cb_wrap,
+                               status_out)
     finally:
         _release_plan(plan)
 
 
-def _run_overiva_on(plan, Xd, n_src, n_iter, proj_back, W0, init_eig, return_filters, callback, cb_wrap):
+def _run_overiva_on(plan, Xd, n_src, n_iter, proj_back, W0, init_eig, return_filters, callback, cb_wrap,
+                    status_out=None):
     B, T, F, M = Xd.shape
     plan.load(Xd)
     if W0 is not None:
@@ -333,7 +421,10 @@ def _run_overiva_on(plan, Xd, n_src, n_iter, proj_back, W0, init_eig, return_fil
             epoch += step
     Y = plan.output(proj_back)
     W = plan.filters() if return_filters else None
-    plan.raise_on_failure()
+    if status_out is not None:
+        status_out.append(plan.status_vector())
+    else:
+        plan.raise_on_failure()
     return Y, W, plan
 
 
@@ -362,7 +453,8 @@ def auxiva(X, n_iter=20, proj_back=True, W0=None, model="laplace", init_eig=Fals
     return overiva(X, None, n_iter, proj_back, W0, model, init_eig, return_filters, callback)
 
 
-def _host_pipeline(Xh, n_src, n_iter, proj_back, W0, model, init_eig, return_filters, chunk, out, device):
+def _host_pipeline(Xh, n_src, n_iter, proj_back, W0, model, init_eig, return_filters, chunk, out, device,
+                   return_status=False):
     """Host-resident batch through the GPU in chunks: H2D of chunk i+1, the loop on chunk i and D2H of chunk
     i-1 run concurrently on three streams (PCIe is full duplex), with two device slots per direction.  The
     whole call then costs about max(PCIe time, compute time) instead of their sum."""
@@ -380,13 +472,14 @@ def _host_pipeline(Xh, n_src, n_iter, proj_back, W0, model, init_eig, return_fil
     owned = _PIPE_LOCK.acquire(blocking=False)  # a concurrent caller (another thread) gets private, uncached state
     try:
         return _host_pipeline_locked(Xh, K, n_iter, proj_back, W0d, code, init_eig, return_filters, chunk, Yh, Wh, dev,
-                                     main, owned)
+                                     main, owned, return_status)
     finally:
         if owned:
             _PIPE_LOCK.release()
 
 
-def _host_pipeline_locked(Xh, K, n_iter, proj_back, W0d, code, init_eig, return_filters, chunk, Yh, Wh, dev, main, owned):
+def _host_pipeline_locked(Xh, K, n_iter, proj_back, W0d, code, init_eig, return_filters, chunk, Yh, Wh, dev, main, owned,
+                          return_status=False):
     B, T, F, M = Xh.shape
     cdt = Xh.dtype
     s_in, s_cmp, s_out = _pipe_streams(dev) if owned else (torch.cuda.Stream(dev), torch.cuda.Stream(dev),
@@ -405,8 +498,7 @@ def _host_pipeline_locked(Xh, K, n_iter, proj_back, W0d, code, init_eig, return_
     key = (chunk, T, F, M, K, code, cdt, torch.device(dev).index, bool(return_filters))
     state = _pipe_state("spectra", key, build) if owned else build()
     Xd, Yd, Wd, plans = state["Xd"], state["Yd"], state["Wd"], state["plans"]
-    for plan in plans.values():
-        plan.reset_status()  # (on the caller's stream, which the pipeline streams wait for next)
+    status_dev = torch.zeros((B,), dtype=torch.int32, device=dev)  # one status word per mixture of the whole batch
     for st in (s_in, s_cmp, s_out):
         st.wait_stream(main)
 
@@ -433,6 +525,7 @@ def _host_pipeline_locked(Xh, K, n_iter, proj_back, W0d, code, init_eig, return_
             if ev_out[slot] is not None:
                 s_cmp.wait_event(ev_out[slot])
             plan = plan_for(nb, slot)
+            plan.reset_status()
             plan.load(Xd[slot][:nb])
             if W0d is not None:
                 plan.init(L.INIT_W0, W0d[b0 : b0 + nb].contiguous())
@@ -442,6 +535,7 @@ def _host_pipeline_locked(Xh, K, n_iter, proj_back, W0d, code, init_eig, return_
             plan.output(proj_back, out=Yd[slot][:nb])
             if return_filters:
                 L.check(plan.lib.oiva_plan_filters(plan.h, _ptr(Wd[slot]), _stream_ptr(dev)), "oiva_plan_filters")
+            status_dev[b0 : b0 + nb].copy_(plan.status_words, non_blocking=True)
             ev_cmp[slot] = s_cmp.record_event()
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_cmp[slot])
@@ -451,22 +545,29 @@ def _host_pipeline_locked(Xh, K, n_iter, proj_back, W0d, code, init_eig, return_
             ev_out[slot] = s_out.record_event()
     for st in (s_in, s_cmp, s_out):
         main.wait_stream(st)
-    with torch.cuda.stream(s_cmp):
-        for plan in plans.values():
-            plan.raise_on_failure()  # the status word accumulates over all chunks a plan has processed
+    status = status_dev.cpu().numpy()  # (synchronises the caller's stream, which has waited for the three others)
     main.synchronize()
-    return Yh, Wh
+    if return_status:
+        return Yh, Wh, status
+    raise_for_status(status)
+    return Yh, Wh, None
 
 
 def overiva_batch(X, n_src=None, n_iter=20, proj_back=True, W0=None, model="laplace", init_eig=False,
-                  return_filters=False, chunk=32, out=None):
+                  return_filters=False, chunk=32, out=None, return_status=False):
     """Many independent mixtures at once: X (B, n_frames, n_freq, n_chan) -> Y (B, n_frames, n_freq, n_src)
     [, W (B, n_freq, n_chan, n_src)].  The role of the reference's task farm (``overiva_sim.py`` +
     ``rrtools``) for mixtures of one shape; every mixture is processed exactly as ``overiva`` would.
 
     Host inputs (numpy / CPU tensors) with more than ``chunk`` mixtures are streamed through the GPU in chunks
     with copies and compute overlapped (pin the input for full PCIe speed; ``out`` may be a preallocated pinned
-    (B, T, F, K) tensor to receive Y).  Device inputs are processed in one piece."""
+    (B, T, F, K) tensor to receive Y).  Device inputs are processed in one piece.
+
+    Failures are tracked PER MIXTURE.  By default a singular mixture raises ``LinAlgError`` naming the offending
+    mixtures (what a plain loop over ``overiva`` would do at the first of them).  With ``return_status=True`` nothing
+    is raised: a last return value ``status`` (B,) int32 holds each mixture's status word (0 = fine, bit 0 = singular,
+    bit 1 = non-finite) and the caller decides -- the reference's sweep records NaN for the failing mixture only and
+    carries on (``overiva_sim.py:334-350``)."""
     if getattr(X, "ndim", 0) != 4:
         raise ValueError("X must have shape (n_batch, n_frames, n_freq, n_chan)")
     is_host = not (isinstance(X, torch.Tensor) and X.is_cuda)
@@ -477,24 +578,29 @@ def overiva_batch(X, n_src=None, n_iter=20, proj_back=True, W0=None, model="lapl
             raise TypeError("X must be complex64 or complex128, got %s" % Xh.dtype)
         dev = _require_cuda()
         with torch.cuda.device(dev):
-            Yh, Wh = _host_pipeline(Xh.contiguous(), n_src, n_iter, proj_back, W0, model, init_eig, return_filters,
-                                    int(chunk), out, dev)
+            Yh, Wh, status = _host_pipeline(Xh.contiguous(), n_src, n_iter, proj_back, W0, model, init_eig,
+                                            return_filters, int(chunk), out, dev, return_status)
         if kind == "numpy":
             Yh = Yh.numpy()
             Wh = Wh.numpy().astype(X.dtype) if Wh is not None else None
         elif Wh is not None:
             Wh = Wh.to(Xh.dtype)
-        return (Yh, Wh) if return_filters else Yh
-    inp = _Input(X)
-    with torch.cuda.device(inp.device):
-        Y, W, _ = _run_overiva(inp.dev, n_src, n_iter, proj_back, W0, model, init_eig, return_filters, None, None)
-        Yo = inp.give_back(Y)
-        if out is not None:
-            out.copy_(Yo if isinstance(Yo, torch.Tensor) else torch.from_numpy(Yo))
-            Yo = out
-        if return_filters:
-            return Yo, inp.give_back(W, inp.dtype)
-        return Yo
+        res = (Yh, Wh) if return_filters else (Yh,)
+    else:
+        inp = _Input(X)
+        st = [] if return_status else None
+        with torch.cuda.device(inp.device):
+            Y, W, _ = _run_overiva(inp.dev, n_src, n_iter, proj_back, W0, model, init_eig, return_filters, None, None,
+                                   status_out=st)
+            Yo = inp.give_back(Y)
+            if out is not None:
+                out.copy_(Yo if isinstance(Yo, torch.Tensor) else torch.from_numpy(Yo))
+                Yo = out
+            res = (Yo, inp.give_back(W, inp.dtype)) if return_filters else (Yo,)
+        status = st[0] if return_status else None
+    if return_status:
+        res = res + (status,)
+    return res if len(res) > 1 else res[0]
 
 
 def auxiva_pca(X, n_src=None, **kwargs):
@@ -534,7 +640,7 @@ def auxiva_pca(X, n_src=None, **kwargs):
             # eigh of the input covariance, keep the K principal eigenvectors      auxiva_pca.py:71-81
             evals = torch.empty((F, M), dtype=torch.float64, device=dev)
             evecs = torch.empty((F, M, M), dtype=torch.complex128, device=dev)
-            L.check(lib.oiva_eigh(_ptr(full.cov), _ptr(evals), _ptr(evecs), lib.oiva_plan_status_ptr(full.h), F, M, 0,
+            L.check(lib.oiva_eigh(_ptr(full.cov), _ptr(evals), _ptr(evecs), lib.oiva_plan_status_ptr(full.h), F, F, M, 0,
                                   st), "oiva_eigh")
             E = evecs[:, :, M - K :].contiguous()
             red = DemixPlan(1, T, F, K, K, _model_code(model), inp.dtype, dev)
@@ -613,7 +719,7 @@ def ogive(X, n_iter=4000, step_size=0.1, tol=1e-3, update="demix", proj_back=Tru
         elif init_eig:  # ive.py:110-123: the un-conjugated leading eigenvector of np.linalg.eig
             evals = torch.empty((F, M), dtype=torch.float64, device=dev)
             evecs = torch.empty((F, M, M), **c128)
-            L.check(lib.oiva_eigh(_ptr(Cx), _ptr(evals), _ptr(evecs), status, F, M, 1, st), "oiva_eigh")
+            L.check(lib.oiva_eigh(_ptr(Cx), _ptr(evals), _ptr(evecs), status, F, F, M, 1, st), "oiva_eigh")
             w.copy_(evecs[:, :, M - 1])
         else:
             w[:, 0] = 1.0  # ive.py:125-127

@@ -178,8 +178,9 @@ void oiva_set_error(const char* fmt, ...);
     do {                                                                                        \
         cudaError_t _e = (expr);                                                                \
         if (_e != cudaSuccess) {                                                                \
-            oiva_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
-            return (int)_e;                                                                     \
+            oiva_set_error("%s:%d: %s -> CUDA error %d (%s)", __FILE__, __LINE__, #expr, (int)_e,  \
+                           cudaGetErrorString(_e));                                             \
+            return OIVA_ERR_CUDA;                                                               \
         }                                                                                       \
     } while (0)
 
@@ -192,6 +193,23 @@ void oiva_set_error(const char* fmt, ...);
     } while (0)
 
 #define OIVA_LAUNCH_CHECK() OIVA_CUDA_CHECK(cudaGetLastError())
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE property of a kernel: launchers remember it per
+// (kernel instantiation, device), not per process (one static instance per instantiation).
+struct OivaPerDeviceOnce {
+    bool done[64] = {};
+    bool& operator[](int dev) { return done[(unsigned)dev & 63u]; }
+};
+#define OIVA_SET_MAX_SMEM_ONCE(kern, bytes)                                                                        \
+    do {                                                                                                           \
+        static OivaPerDeviceOnce once_;                                                                            \
+        int dev_ = 0;                                                                                              \
+        OIVA_CUDA_CHECK(cudaGetDevice(&dev_));                                                                     \
+        if (!once_[dev_]) {                                                                                        \
+            OIVA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            once_[dev_] = true;                                                                                    \
+        }                                                                                                          \
+    } while (0)
 
 static inline int oiva_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -1,37 +1,42 @@
 // C entry point of the weighted-covariance kernel (include/overiva_b200.h: oiva_weighted_cov).
 #include <stdlib.h>
 
+#include <mutex>
+#include <vector>
+
 #include "cov.cuh"
 #include "relayout_cov.cuh"
 
 namespace oiva {
 #define OIVA_DECL(M)                                                                                 \
-    int cov_launch_m##M(int dtype, int KC, int use_tma, const CovParams& p, cudaStream_t st, int* nsplit_out); \
+    int cov_launch_m##M(int dtype, int KC, const CovParams& p, cudaStream_t st, int* nsplit_out); \
     int cov_max_kc_m##M();                                                                                     \
     int relayout_cov_launch_m##M(int dtype, RelayoutCovParams p, int max_split, cudaStream_t st, int* nsplit_out);
 OIVA_DECL(1) OIVA_DECL(2) OIVA_DECL(3) OIVA_DECL(4) OIVA_DECL(5) OIVA_DECL(6) OIVA_DECL(7) OIVA_DECL(8)
 OIVA_DECL(9) OIVA_DECL(10) OIVA_DECL(11) OIVA_DECL(12) OIVA_DECL(13) OIVA_DECL(14) OIVA_DECL(15) OIVA_DECL(16)
 #undef OIVA_DECL
 
-// phi == NULL: a device buffer of ones (grown on demand, per device) stands in for the weights
+// phi == NULL: a device buffer of ones (grown on demand, per device) stands in for the weights.  The buffer is
+// created under a mutex and filled SYNCHRONOUSLY (blocking cudaMemcpy from a host vector) before its pointer is
+// published, so any stream / thread that sees it sees ones; growing it must not happen under stream capture
+// (plans size it once at creation through oiva_reserve_ones).
+static std::mutex g_ones_mu;
 static double* g_ones[64] = {nullptr};
 static size_t g_ones_n[64] = {0};
-__global__ void k_fill(double* p, size_t n, double v) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
-static int get_ones(size_t n, cudaStream_t st, const double** out) {
+static int get_ones(size_t n, const double** out) {
     int dev = 0;
     OIVA_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) dev = 0;
+    std::lock_guard<std::mutex> lock(g_ones_mu);
     if (g_ones_n[dev] < n) {
         // a previous, smaller buffer may still be in use by queued kernels: keep it alive (tiny leak by design)
+        size_t cap = n < 4096 ? 4096 : n;
         double* q = nullptr;
-        OIVA_CUDA_CHECK(cudaMalloc(&q, n * sizeof(double)));
-        k_fill<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q, n, 1.0);
-        OIVA_LAUNCH_CHECK();
+        OIVA_CUDA_CHECK(cudaMalloc(&q, cap * sizeof(double)));
+        std::vector<double> host(cap, 1.0);
+        OIVA_CUDA_CHECK(cudaMemcpy(q, host.data(), cap * sizeof(double), cudaMemcpyHostToDevice));
         g_ones[dev] = q;
-        g_ones_n[dev] = n;
+        g_ones_n[dev] = cap;
     }
     *out = g_ones[dev];
     return OIVA_OK;
@@ -61,6 +66,12 @@ static int pick_chunk(int rem, int max_kc) {
     return best;  // largest usable chunk; more passes follow
 }
 }  // namespace oiva
+
+// make sure the ones buffer of the current device covers n_frames (called at plan creation, outside any capture)
+int oiva_reserve_ones(int n_frames) {
+    const double* ones = nullptr;
+    return oiva::get_ones((size_t)oiva_frame_pitch(n_frames), &ones);
+}
 
 extern "C" size_t oiva_weighted_cov_scratch_bytes(int n_batch, int n_frames, int n_freq, int n_chan, int n_src) {
     // frame splitting only happens when there are few bin groups; 64 slots or 512 MiB, whichever is smaller, keeps
@@ -106,14 +117,12 @@ extern "C" int oiva_weighted_cov_ws(const void* Xg, const double* phi, void* Vg,
         p.phi = phi;
     } else {
         const double* ones = nullptr;
-        int rc = get_ones((size_t)p.L.frame_pitch(), st, &ones);
+        int rc = get_ones((size_t)p.L.frame_pitch(), &ones);
         if (rc) return rc;
         p.phi = ones;
         OIVA_REQUIRE(p.G < (1ll << 31), "oiva_weighted_cov: too many groups");
         p.NGphi = (int)p.G;  // every group maps to "mixture 0": the ones buffer holds one (K=1, Tp) block
     }
-    const char* env = getenv("OIVA_COV_NO_TMA");
-    const int use_tma = !(env && *env && *env != '0');
     int max_kc = 1;
     switch (n_chan) {
 #define OIVA_CASE(M) case M: max_kc = cov_max_kc_m##M(); break;
@@ -121,16 +130,14 @@ extern "C" int oiva_weighted_cov_ws(const void* Xg, const double* phi, void* Vg,
         OIVA_CASE(9) OIVA_CASE(10) OIVA_CASE(11) OIVA_CASE(12) OIVA_CASE(13) OIVA_CASE(14) OIVA_CASE(15) OIVA_CASE(16)
 #undef OIVA_CASE
     }
-    if (!use_tma && max_kc > 2) max_kc = 2;
     int k0 = 0;
     while (k0 < n_src) {
         int KC = pick_chunk(n_src - k0, max_kc);
-        if (!use_tma && KC > n_src - k0) KC = n_src - k0 >= 2 ? 2 : 1;
         p.k0 = k0;
         int rc = OIVA_ERR_INVALID;
         int nsplit_used = 0;
         switch (n_chan) {
-#define OIVA_CASE(M) case M: rc = cov_launch_m##M(dtype, KC, use_tma, p, st, &nsplit_used); break;
+#define OIVA_CASE(M) case M: rc = cov_launch_m##M(dtype, KC, p, st, &nsplit_used); break;
             OIVA_CASE(1) OIVA_CASE(2) OIVA_CASE(3) OIVA_CASE(4) OIVA_CASE(5) OIVA_CASE(6) OIVA_CASE(7) OIVA_CASE(8)
             OIVA_CASE(9) OIVA_CASE(10) OIVA_CASE(11) OIVA_CASE(12) OIVA_CASE(13) OIVA_CASE(14) OIVA_CASE(15)
             OIVA_CASE(16)

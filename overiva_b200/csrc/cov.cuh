@@ -149,7 +149,7 @@ struct CovPart {
 // The body run by one warp of a team for its compile-time part.
 // Units of work: (group, frame split); a team owns the contiguous unit range [u_begin, u_end).  All
 // producer / consumer cursors are advanced incrementally (no divisions in the per-chunk path).
-template <typename CP, typename ST, int M, int KC, bool USE_TMA>
+template <typename CP, typename ST, int M, int KC>
 __device__ __forceinline__ void cov_team_body(const CovParams& p, unsigned char* team_smem, long long team_global,
                                               long long n_teams_total, int lane, bool is_leader_warp, int part) {
     typedef typename CP::XC XC;
@@ -210,7 +210,7 @@ __device__ __forceinline__ void cov_team_body(const CovParams& p, unsigned char*
             ++puse;
         }
     };
-    if (USE_TMA && leader && pu < u_end) {
+    if (leader && pu < u_end) {
         producer_unit();
         for (int i = 0; i < S - 1; ++i) issue();
     } else {
@@ -232,30 +232,16 @@ __device__ __forceinline__ void cov_team_body(const CovParams& p, unsigned char*
             for (int k = 0; k < KC; ++k) acc[n][k] = cmake(0.0, 0.0);
         for (int c = c0; c < c1; ++c) {
             const int nfr = min(TC, L.T - c * TC);
-            if (USE_TMA) {
-                if (leader && pu < u_end) issue();
-                mbar_wait(&full[cstage], cphase);
-                const unsigned char* src = stage0 + (size_t)cstage * stage_bytes;
-                CP::accumulate(acc, reinterpret_cast<const XC*>(src), reinterpret_cast<const double*>(src + x_stage), nfr,
-                               lane, part);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[cstage]);
-                if (++cstage == S) {
-                    cstage = 0;
-                    cphase ^= 1;
-                }
-            } else {
-                // debug path without TMA: read the chunk straight from global memory
-                const int b = gi / p.NGphi;
-                const int t0 = c * TC;
-                double phl[KC * TC];
-#pragma unroll
-                for (int k = 0; k < KC; ++k)
-#pragma unroll
-                    for (int fr = 0; fr < TC; ++fr)
-                        phl[k * TC + fr] =
-                            fr < nfr ? p.phi[((size_t)b * p.K + min(p.k0 + k, p.K - 1)) * Tp + t0 + fr] : 0.0;
-                CP::accumulate(acc, Xg + (size_t)gi * group_elems + (size_t)t0 * frame_elems, phl, nfr, lane, part);
+            if (leader && pu < u_end) issue();
+            mbar_wait(&full[cstage], cphase);
+            const unsigned char* src = stage0 + (size_t)cstage * stage_bytes;
+            CP::accumulate(acc, reinterpret_cast<const XC*>(src), reinterpret_cast<const double*>(src + x_stage), nfr, lane,
+                           part);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[cstage]);
+            if (++cstage == S) {
+                cstage = 0;
+                cphase ^= 1;
             }
         }
         const size_t grp_elems = (size_t)p.K * CP::NE * OIVA_GROUP;
@@ -266,38 +252,36 @@ __device__ __forceinline__ void cov_team_body(const CovParams& p, unsigned char*
     }
 }
 
-template <typename ST, int M, int KC, int P, bool USE_TMA, int PART = 0>
+template <typename ST, int M, int KC, int P, int PART = 0>
 struct CovDispatch {
     __device__ static __forceinline__ void run(int part, const CovParams& p, unsigned char* team_smem,
                                                long long team_global, long long n_teams_total, int lane) {
         if (part == PART)
-            cov_team_body<CovPart<ST, M, KC, P, PART>, ST, M, KC, USE_TMA>(p, team_smem, team_global, n_teams_total, lane,
-                                                                          PART == 0, PART);
+            cov_team_body<CovPart<ST, M, KC, P, PART>, ST, M, KC>(p, team_smem, team_global, n_teams_total, lane, PART == 0,
+                                                                 PART);
         else if constexpr (PART + 1 < P)
-            CovDispatch<ST, M, KC, P, USE_TMA, PART + 1>::run(part, p, team_smem, team_global, n_teams_total, lane);
+            CovDispatch<ST, M, KC, P, PART + 1>::run(part, p, team_smem, team_global, n_teams_total, lane);
     }
 };
 
 // blockDim.x = teams_per_cta * P * 32; dynamic smem = teams_per_cta * team_smem_bytes
-template <typename ST, int M, int KC, int P, bool USE_TMA>
+template <typename ST, int M, int KC, int P>
 __global__ void __launch_bounds__(cov_threads(P)) k_cov(const CovParams p, int teams_per_cta, int team_smem_bytes) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int team = warp / P, part = warp - team * P;
     unsigned char* team_smem = smem_raw + (size_t)team * team_smem_bytes;
-    if (USE_TMA) {
-        if (part == 0 && lane == 0) {
-            uint64_t* full = reinterpret_cast<uint64_t*>(team_smem);
-            uint64_t* empty = full + p.stages;
-            for (int s = 0; s < p.stages; ++s) {
-                mbar_init(&full[s], 1);
-                mbar_init(&empty[s], P);
-            }
-            mbar_fence_init();
+    if (part == 0 && lane == 0) {
+        uint64_t* full = reinterpret_cast<uint64_t*>(team_smem);
+        uint64_t* empty = full + p.stages;
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], P);
         }
-        __syncthreads();
+        mbar_fence_init();
     }
-    CovDispatch<ST, M, KC, P, USE_TMA>::run(part, p, team_smem, (long long)blockIdx.x * teams_per_cta + team,
+    __syncthreads();
+    CovDispatch<ST, M, KC, P>::run(part, p, team_smem, (long long)blockIdx.x * teams_per_cta + team,
                                             (long long)gridDim.x * teams_per_cta, lane);
 }
 
@@ -395,24 +379,22 @@ struct CovBlock {
 // sub-partition, 3 x 32 x R <= 16384 caps R at 168 (what ptxas picks from the launch bounds; a larger __maxnreg__ makes
 // the launch fail), and 128 of those hold the 4 x 4 x KC=2 complex accumulators -- staging the products of a block row
 // before accumulating them (more ILP against the "wait" stalls ncu shows) spills.  The kernel is register-file-bound.
-template <typename ST, int M, int KC, bool USE_TMA>
+template <typename ST, int M, int KC>
 __global__ void __launch_bounds__(cov_block_parts(M) * 32) k_cov_blocked(const CovParams p, int team_smem_bytes) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int P = cov_block_parts(M);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (USE_TMA) {
-        if (warp == 0 && lane == 0) {
-            uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-            uint64_t* empty = full + p.stages;
-            for (int s = 0; s < p.stages; ++s) {
-                mbar_init(&full[s], 1);
-                mbar_init(&empty[s], P);
-            }
-            mbar_fence_init();
+    if (warp == 0 && lane == 0) {
+        uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+        uint64_t* empty = full + p.stages;
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], P);
         }
-        __syncthreads();
+        mbar_fence_init();
     }
-    cov_team_body<CovBlock<ST, M, KC>, ST, M, KC, USE_TMA>(p, smem_raw, blockIdx.x, gridDim.x, lane, warp == 0, warp);
+    __syncthreads();
+    cov_team_body<CovBlock<ST, M, KC>, ST, M, KC>(p, smem_raw, blockIdx.x, gridDim.x, lane, warp == 0, warp);
 }
 
 }  // namespace oiva

@@ -46,7 +46,7 @@ constexpr bool COV_USE_BLOCKS = OIVA_COV_M >= 9;
 // shared launch logic: ring sizing, persistent grid, frame splitting for few groups
 template <typename Kern, typename Launch>
 static int launch_common(Kern kern, CovParams p, cudaStream_t st, int P, int teams_max, size_t stage_bytes, int TC,
-                         int M, int KC, bool tma, bool& attr_done, int* nsplit_out, Launch do_launch) {
+                         int M, int KC, OivaPerDeviceOnce& attr_done, int* nsplit_out, Launch do_launch) {
     int dev = 0, sms = 148;
     OIVA_CUDA_CHECK(cudaGetDevice(&dev));
     OIVA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -59,23 +59,21 @@ static int launch_common(Kern kern, CovParams p, cudaStream_t st, int P, int tea
     if (S < 2) S = 2;
     size_t team_smem = 0, smem = 0;
     const size_t budget = 200 * 1024;
-    if (tma) {
-        for (;;) {
-            team_smem = 128 * ((2 * S * sizeof(uint64_t) + 127) / 128) + (size_t)S * stage_bytes;
-            if (teams * team_smem <= budget) break;
-            if (S > 3) { --S; continue; }
-            if (teams > 1) { --teams; continue; }
-            if (S > 2) { --S; continue; }
-            oiva_set_error("oiva_weighted_cov: stage of %zu bytes does not fit shared memory", stage_bytes);
-            return OIVA_ERR_INVALID;
-        }
-        smem = teams * team_smem;
+    for (;;) {
+        team_smem = 128 * ((2 * S * sizeof(uint64_t) + 127) / 128) + (size_t)S * stage_bytes;
+        if (teams * team_smem <= budget) break;
+        if (S > 3) { --S; continue; }
+        if (teams > 1) { --teams; continue; }
+        if (S > 2) { --S; continue; }
+        oiva_set_error("oiva_weighted_cov: stage of %zu bytes does not fit shared memory", stage_bytes);
+        return OIVA_ERR_INVALID;
     }
+    smem = teams * team_smem;
     p.stages = S;
     const int threads = teams * P * 32;
-    if (!attr_done) {
+    if (!attr_done[dev]) {
         OIVA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-        attr_done = true;
+        attr_done[dev] = true;
     }
     int occ = 1;
     OIVA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
@@ -104,7 +102,7 @@ static int launch_common(Kern kern, CovParams p, cudaStream_t st, int P, int tea
     return OIVA_OK;
 }
 
-template <typename ST, int KC, bool TMA>
+template <typename ST, int KC>
 static int launch(CovParams p, cudaStream_t st, int* nsplit_out) {
     constexpr int M = OIVA_COV_M;
     typedef typename StoreC<ST>::type XC;
@@ -117,9 +115,9 @@ static int launch(CovParams p, cudaStream_t st, int* nsplit_out) {
             return OIVA_ERR_INVALID;
         } else {
             constexpr int P = cov_block_parts(M);
-            auto kern = k_cov_blocked<ST, M, KC, TMA>;
-            static bool attr_done = false;
-            return launch_common(kern, p, st, P, 1, stage_bytes, TC, M, KC, TMA, attr_done, nsplit_out,
+            auto kern = k_cov_blocked<ST, M, KC>;
+            static OivaPerDeviceOnce attr_done;
+            return launch_common(kern, p, st, P, 1, stage_bytes, TC, M, KC, attr_done, nsplit_out,
                                  [&](const CovParams& q, unsigned grid, int threads, size_t smem, int, int team_smem) {
                                      kern<<<grid, threads, smem, st>>>(q, team_smem);
                                  });
@@ -132,9 +130,9 @@ static int launch(CovParams p, cudaStream_t st, int* nsplit_out) {
             oiva_set_error("cov_launch: (M=%d, KC=%d) is not instantiated (%d parts)", M, KC, P);
             return OIVA_ERR_INVALID;
         } else {
-            auto kern = k_cov<ST, M, KC, P, TMA>;
-            static bool attr_done = false;
-            return launch_common(kern, p, st, P, cov_teams_per_cta(P), stage_bytes, TC, M, KC, TMA, attr_done, nsplit_out,
+            auto kern = k_cov<ST, M, KC, P>;
+            static OivaPerDeviceOnce attr_done;
+            return launch_common(kern, p, st, P, cov_teams_per_cta(P), stage_bytes, TC, M, KC, attr_done, nsplit_out,
                                  [&](const CovParams& q, unsigned grid, int threads, size_t smem, int teams,
                                      int team_smem) { kern<<<grid, threads, smem, st>>>(q, teams, team_smem); });
         }
@@ -157,16 +155,9 @@ int OIVA_CAT(cov_max_kc_m, OIVA_COV_M)() {
     return best;
 }
 
-int OIVA_CAT(cov_launch_m, OIVA_COV_M)(int dtype, int KC, int use_tma, const CovParams& p, cudaStream_t st,
-                                       int* nsplit_out) {
+int OIVA_CAT(cov_launch_m, OIVA_COV_M)(int dtype, int KC, const CovParams& p, cudaStream_t st, int* nsplit_out) {
 #define OIVA_COV_CASE(ST_, KC_) \
-    if (KC == KC_) return launch<ST_, KC_, true>(p, st, nsplit_out);
-    if (!use_tma) {  // debug path, fp64 storage, chunks of 1 or 2 sources only
-        if (dtype == OIVA_C128 && KC == 1) return launch<double, 1, false>(p, st, nsplit_out);
-        if (dtype == OIVA_C128 && KC == 2) return launch<double, 2, false>(p, st, nsplit_out);
-        oiva_set_error("cov_launch: the non-TMA debug path supports complex128 with source chunks of 1 or 2");
-        return OIVA_ERR_INVALID;
-    }
+    if (KC == KC_) return launch<ST_, KC_>(p, st, nsplit_out);
     if (dtype == OIVA_C64) {
         OIVA_COV_CASE(float, 1)
         OIVA_COV_CASE(float, 2)
@@ -213,19 +204,11 @@ static int relayout_cov_launch_t(int dtype, RelayoutCovParams p, int max_split, 
         int occ = 1;
         if (dtype == OIVA_C64) {
             auto kern = k_relayout_cov<float, M>;
-            static bool attr_done = false;
-            if (!attr_done) {
-                OIVA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-                attr_done = true;
-            }
+            OIVA_SET_MAX_SMEM_ONCE(kern, budget);
             OIVA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
         } else {
             auto kern = k_relayout_cov<double, M>;
-            static bool attr_done = false;
-            if (!attr_done) {
-                OIVA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-                attr_done = true;
-            }
+            OIVA_SET_MAX_SMEM_ONCE(kern, budget);
             OIVA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
         }
         if (occ < 1) occ = 1;

@@ -7,6 +7,8 @@
 
 #include "common.cuh"
 
+int oiva_reserve_ones(int n_frames);  // cov.cu
+
 // optional per-kernel timing (bench.py's roofline leg): CUDA events recorded on the launching stream
 // around the launches of the three loop kernels; read back after the caller has synchronised
 enum { TK_COV = 0, TK_POWER = 1, TK_SOLVE = 2, TK_N = 3 };
@@ -29,7 +31,6 @@ struct oiva_plan {
     unsigned char* ws;
     long long launches;
     bool loaded, inited;
-    bool r2_valid;  // r2part holds the statistic of the CURRENT demixing matrices (left by the fused kernel)
     bool timing;
     std::vector<TimedSpan>* spans;
     std::vector<cudaEvent_t>* pool;
@@ -44,8 +45,9 @@ static cudaEvent_t plan_event(oiva_plan* p) {
     if (!p->pool->empty()) {
         e = p->pool->back();
         p->pool->pop_back();
-    } else {
-        cudaEventCreate(&e);
+    } else if (cudaEventCreate(&e) != cudaSuccess) {
+        cudaGetLastError();
+        e = nullptr;
     }
     return e;
 }
@@ -59,6 +61,12 @@ struct SpanGuard {  // records an event pair around a launch sequence when timin
             sp.kind = kind;
             sp.a = plan_event(p);
             sp.b = plan_event(p);
+            if (!sp.a || !sp.b) {  // no event to be had: this span simply goes untimed
+                if (sp.a) p->pool->push_back(sp.a);
+                if (sp.b) p->pool->push_back(sp.b);
+                on = false;
+                return;
+            }
             cudaEventRecord(sp.a, st);
         }
     }
@@ -113,7 +121,7 @@ extern "C" int oiva_plan_create(oiva_plan_t** out, const oiva_plan_desc* desc) {
     p->off_phi = o;     o += align_up(B * K * p->Tp * 8);
     p->off_wscale = o;  o += align_up(B * K * 8);
     p->off_evals = o;   o += align_up(R * M * 8);
-    p->off_status = o;  o += align_up(16);
+    p->off_status = o;  o += align_up(sizeof(int) * (B + 4));  // one status word per mixture
     // per-split partial covariances of inputs with few bin groups (deterministic frame-split accumulation)
     p->covws_bytes = oiva_weighted_cov_scratch_bytes(d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.n_src);
     p->off_covws = o;   o += align_up(p->covws_bytes);
@@ -121,6 +129,18 @@ extern "C" int oiva_plan_create(oiva_plan_t** out, const oiva_plan_desc* desc) {
     p->spans = new std::vector<TimedSpan>();
     p->pool = new std::vector<cudaEvent_t>();
     *out = p;
+    // the "ones" weights of the unweighted input covariance: sized here so that no allocation happens mid-stream
+    int dev_count = 0;
+    if (cudaGetDeviceCount(&dev_count) == cudaSuccess && dev_count > 0) {
+        int rc = oiva_reserve_ones(d.n_frames);
+        if (rc) {
+            oiva_plan_destroy(p);
+            *out = nullptr;
+            return rc;
+        }
+    } else {
+        cudaGetLastError();
+    }
     return OIVA_OK;
 }
 
@@ -259,19 +279,18 @@ extern "C" int oiva_plan_init(oiva_plan_t* p, int mode, const void* W0, void* st
     if (mode == OIVA_INIT_EIG) {
         // principal eigenvectors of C with np.linalg.eig's phase convention            overiva.py:103-109
         int rc = oiva_eigh(p->ws + p->off_c, (double*)(p->ws + p->off_evals), p->ws + p->off_vg, status, (int)p->R,
-                           d.n_chan, 1, stream);
+                           d.n_freq, d.n_chan, 1, stream);
         if (rc) return rc;
         evecs = p->ws + p->off_vg;
         p->launches += 1;
     }
-    int rc = oiva_init_demix(p->ws + p->off_what, p->ws + p->off_c, W0, evecs, mode, status, (int)p->R, d.n_chan,
-                             d.n_src, stream);
+    int rc = oiva_init_demix(p->ws + p->off_what, p->ws + p->off_c, W0, evecs, mode, status, (int)p->R, d.n_freq,
+                             d.n_chan, d.n_src, stream);
     if (rc) return rc;
     rc = oiva_group_rows(p->ws + p->off_what, p->ws + p->off_wg, d.n_batch, d.n_freq, d.n_chan * d.n_chan, stream);
     if (rc) return rc;
     p->launches += 2;
     p->inited = true;
-    p->r2_valid = false;
     return OIVA_OK;
 }
 
@@ -294,20 +313,7 @@ static int plan_power_partials(oiva_plan_t* p, void* stream) {
     return OIVA_OK;
 }
 
-// The fused IP sweep + next-epoch statistic kernel (fused.cuh) is OPT-IN (OIVA_FUSE=1): measured on B200 at the
-// bench shape it is ~7 % slower than the two separate kernels (2.60 ms vs 1.88 + 0.53 ms per epoch: with one warp
-// per bin group and ~140 registers the streaming phase has less memory parallelism than the dedicated power
-// kernel, and the sweep's latency is already cheap).  Kept because it removes a launch and a W_hat round trip,
-// which matters for latency-bound shapes; needs enough bin groups to fill the GPU with one warp per group.
-static bool plan_can_fuse(const oiva_plan_t* p) {
-    static const bool enabled = [] {
-        const char* v = getenv("OIVA_FUSE");
-        return v && *v && *v != '0';
-    }();
-    return enabled && oiva_ip_update_power_supported(p->d.n_chan, p->d.n_src) && p->G >= 1184;
-}
-
-static int plan_update_from(oiva_plan_t* p, const double* r2src, int nch, void* stream, bool fuse_next_power = false) {
+static int plan_update_from(oiva_plan_t* p, const double* r2src, int nch, void* stream) {
     const oiva_plan_desc& d = p->d;
     double* phi = (double*)(p->ws + p->off_phi);
     double* wscale = (double*)(p->ws + p->off_wscale);
@@ -322,17 +328,10 @@ static int plan_update_from(oiva_plan_t* p, const double* r2src, int nch, void* 
     if (rc) return rc;
     {
         SpanGuard g(p, TK_SOLVE, stream);
-        if (fuse_next_power)
-            rc = oiva_ip_update_power(p->ws + p->off_wg, p->ws + p->off_vg, p->ws + p->off_cg, wscale,
-                                      (int*)(p->ws + p->off_status), p->ws + p->off_xg,
-                                      (double*)(p->ws + p->off_r2part), d.n_batch, d.n_frames, d.n_freq, d.n_chan,
-                                      d.n_src, d.dtype, stream);
-        else
-            rc = oiva_ip_update(p->ws + p->off_wg, p->ws + p->off_vg, p->ws + p->off_c, p->ws + p->off_cg, wscale,
-                                (int*)(p->ws + p->off_status), d.n_batch, d.n_freq, d.n_chan, d.n_src, stream);
+        rc = oiva_ip_update(p->ws + p->off_wg, p->ws + p->off_vg, p->ws + p->off_c, p->ws + p->off_cg, wscale,
+                            (int*)(p->ws + p->off_status), d.n_batch, d.n_freq, d.n_chan, d.n_src, stream);
     }
     if (rc) return rc;
-    p->r2_valid = fuse_next_power;
     p->launches += 3;
     return OIVA_OK;
 }
@@ -345,15 +344,10 @@ static int plan_update_from(oiva_plan_t* p, const double* r2src, int nch, void* 
     }
 
 static int plan_iterate_eager(oiva_plan_t* p, int n_iter, void* stream) {
-    const bool fuse = plan_can_fuse(p);
     for (int it = 0; it < n_iter; ++it) {
-        int rc = OIVA_OK;
-        if (!p->r2_valid) {
-            rc = plan_power_partials(p, stream);
-            if (rc) return rc;
-        }
-        // all but the last epoch of this call leave the next epoch's statistic behind (solve + power fused)
-        rc = plan_update_from(p, (const double*)(p->ws + p->off_r2part), p->NG, stream, fuse && it + 1 < n_iter);
+        int rc = plan_power_partials(p, stream);
+        if (rc) return rc;
+        rc = plan_update_from(p, (const double*)(p->ws + p->off_r2part), p->NG, stream);
         if (rc) return rc;
     }
     return OIVA_OK;
@@ -367,7 +361,7 @@ static bool plan_use_graph(const oiva_plan_t* p, int n_iter) {
         const char* v = getenv("OIVA_NO_GRAPH");
         return v && *v && *v != '0';
     }();
-    return !disabled && !p->timing && n_iter >= 2 && p->G < 4096 && !p->r2_valid;
+    return !disabled && !p->timing && n_iter >= 2 && p->G < 4096;
 }
 
 extern "C" int oiva_plan_iterate(oiva_plan_t* p, int n_iter, void* stream) {
@@ -389,9 +383,7 @@ extern "C" int oiva_plan_iterate(oiva_plan_t* p, int n_iter, void* stream) {
         cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
         int rc = OIVA_OK;
         if (e == cudaSuccess) {
-            const bool rv = p->r2_valid;
             rc = plan_iterate_eager(p, n_iter, cap);
-            p->r2_valid = rv;
             e = cudaStreamEndCapture(cap, &graph);
         }
         p->graph_launches = p->launches - l0;
@@ -408,13 +400,11 @@ extern "C" int oiva_plan_iterate(oiva_plan_t* p, int n_iter, void* stream) {
     }
     OIVA_CUDA_CHECK(cudaGraphLaunch(p->graph_exec, st));
     p->launches += p->graph_launches;
-    p->r2_valid = false;
     return OIVA_OK;
 }
 
 extern "C" int oiva_plan_power(oiva_plan_t* p, void* stream) {
     PLAN_INITED(p, "oiva_plan_power");
-    p->r2_valid = false;
     int rc = plan_power_partials(p, stream);
     if (rc) return rc;
     rc = oiva_sum_partials((const double*)(p->ws + p->off_r2part), p->NG, (double*)(p->ws + p->off_r2), p->d.n_batch,
@@ -459,17 +449,35 @@ extern "C" int oiva_plan_filters(oiva_plan_t* p, void* W, void* stream) {
     return OIVA_OK;
 }
 
-extern "C" int oiva_plan_status(oiva_plan_t* p, void* stream) {
-    PLAN_READY(p, "oiva_plan_status");
-    int h = 0;
-    OIVA_CUDA_CHECK(cudaMemcpyAsync(&h, p->ws + p->off_status, sizeof(int), cudaMemcpyDeviceToHost,
+extern "C" int oiva_plan_reset_status(oiva_plan_t* p, void* stream) {
+    PLAN_READY(p, "oiva_plan_reset_status");
+    OIVA_CUDA_CHECK(cudaMemsetAsync(p->ws + p->off_status, 0, sizeof(int) * ((size_t)p->d.n_batch + 4),
                                     (cudaStream_t)stream));
-    OIVA_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
-    return h;
+    return OIVA_OK;
 }
 
+extern "C" int oiva_plan_status_vector(oiva_plan_t* p, int* status_host, void* stream) {
+    PLAN_READY(p, "oiva_plan_status");
+    const int B = p->d.n_batch;
+    std::vector<int> tmp;
+    int* h = status_host;
+    if (!h) {
+        tmp.resize(B);
+        h = tmp.data();
+    }
+    OIVA_CUDA_CHECK(cudaMemcpyAsync(h, p->ws + p->off_status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost,
+                                    (cudaStream_t)stream));
+    OIVA_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    int all = 0;
+    for (int b = 0; b < B; ++b) all |= h[b];
+    return all & (OIVA_STATUS_SINGULAR | OIVA_STATUS_NONFINITE);
+}
+
+extern "C" int oiva_plan_status(oiva_plan_t* p, void* stream) { return oiva_plan_status_vector(p, nullptr, stream); }
+
 extern "C" int oiva_overiva_host(const void* X_host, void* Y_host, void* W_host, const void* W0_host,
-                                 const oiva_plan_desc* desc, int n_iter, int proj_back, int init_mode) {
+                                 const oiva_plan_desc* desc, int n_iter, int proj_back, int init_mode,
+                                 int* status_host) {
     OIVA_REQUIRE(X_host && Y_host && desc, "oiva_overiva_host: null pointer");
     OIVA_REQUIRE(init_mode != OIVA_INIT_W0 || W0_host, "oiva_overiva_host: W0 missing");
     oiva_plan_t* p = nullptr;
@@ -487,8 +495,9 @@ extern "C" int oiva_overiva_host(const void* X_host, void* Y_host, void* W_host,
     do {                                                                                            \
         cudaError_t _e = (expr);                                                                    \
         if (_e != cudaSuccess) {                                                                    \
-            oiva_set_error("oiva_overiva_host: %s -> %s", #expr, cudaGetErrorString(_e));           \
-            status = (int)_e;                                                                       \
+            oiva_set_error("oiva_overiva_host: %s -> CUDA error %d (%s)", #expr, (int)_e,           \
+                           cudaGetErrorString(_e));                                                 \
+            status = OIVA_ERR_CUDA;                                                                 \
             goto done;                                                                              \
         }                                                                                           \
     } while (0)
@@ -503,7 +512,7 @@ extern "C" int oiva_overiva_host(const void* X_host, void* Y_host, void* W_host,
     HOST_TRY(cudaMalloc(&dW, wbytes));
     HOST_TRY(cudaMalloc(&ws, p->ws_bytes));
     HOST_RC(oiva_plan_bind(p, ws, p->ws_bytes));
-    HOST_TRY(cudaMemsetAsync(oiva_plan_status_ptr(p), 0, 16, st));
+    HOST_RC(oiva_plan_reset_status(p, st));
     HOST_TRY(cudaMemcpyAsync(dX, X_host, xbytes, cudaMemcpyHostToDevice, st));
     if (init_mode == OIVA_INIT_W0) HOST_TRY(cudaMemcpyAsync(dW, W0_host, wbytes, cudaMemcpyHostToDevice, st));
     HOST_RC(oiva_plan_load(p, dX, st));
@@ -515,7 +524,7 @@ extern "C" int oiva_overiva_host(const void* X_host, void* Y_host, void* W_host,
         HOST_RC(oiva_plan_filters(p, dW, st));
         HOST_TRY(cudaMemcpyAsync(W_host, dW, wbytes, cudaMemcpyDeviceToHost, st));
     }
-    status = oiva_plan_status(p, st);  // synchronises
+    status = oiva_plan_status_vector(p, status_host, st);  // synchronises
 done:
     if (st) cudaStreamSynchronize(st);
     cudaFree(dX);

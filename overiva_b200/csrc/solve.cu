@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(ip_warps<M>() * 32) k_ip_update(cplx* __restri
         }
     }
     if (row_ok && (singular || bad))
-        atomicOr(status, (singular ? OIVA_STATUS_SINGULAR : 0) | (bad ? OIVA_STATUS_NONFINITE : 0));
+        atomicOr(status + bmix, (singular ? OIVA_STATUS_SINGULAR : 0) | (bad ? OIVA_STATUS_NONFINITE : 0));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -110,7 +110,7 @@ template <int M>
 __global__ void __launch_bounds__(SOLVE_WARPS * 32) k_init_demix(cplx* __restrict__ What, const cplx* __restrict__ C,
                                                                  const cplx* __restrict__ W0,
                                                                  const cplx* __restrict__ evecs, int mode, int* status,
-                                                                 long long R, int K) {
+                                                                 long long R, int rows_per_mixture, int K) {
     constexpr int G = Grp<M>::G, BINS = Grp<M>::BINS;
     __shared__ cplx sWall[SOLVE_WARPS * BINS * M * M];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) k_init_demix(cplx* __restric
 #pragma unroll
         for (int c = 0; c < M; ++c) What[row * M * M + gl * M + c] = sW[gl * M + c];
     }
-    if (row_ok && singular) atomicOr(status, OIVA_STATUS_SINGULAR);
+    if (row_ok && singular) atomicOr(status + row / rows_per_mixture, OIVA_STATUS_SINGULAR);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -196,7 +196,7 @@ __global__ void k_compose_filters(const cplx* __restrict__ E, const cplx* __rest
 template <int M>
 __global__ void __launch_bounds__(SOLVE_WARPS * 32) k_eigh(const cplx* __restrict__ C, double* __restrict__ evals,
                                                            cplx* __restrict__ evecs, int* status, long long R,
-                                                           int lapack_phase) {
+                                                           int rows_per_mixture, int lapack_phase) {
     __shared__ cplx sA[SOLVE_WARPS][M * M];
     __shared__ cplx sQ[SOLVE_WARPS][M * M];
     __shared__ int sPerm[SOLVE_WARPS][M];
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) k_eigh(const cplx* __restric
             if (lj < li || (lj == li && j < lane)) ++rank;
         }
         sPerm[warp][rank] = lane;
-        if (!isfinite(li)) atomicOr(status, OIVA_STATUS_NONFINITE);
+        if (!isfinite(li)) atomicOr(status + row / rows_per_mixture, OIVA_STATUS_NONFINITE);
     }
     __syncwarp();
     if (lane < M) {
@@ -314,8 +314,6 @@ static int bins_per_cta() {
 namespace oiva {
 int ip_update_tpb(int M, int K, cplx* What, const cplx* Vg, const cplx* Cg, const double* wscale, int* status, int F,
                   int NG, long long G, cudaStream_t st);
-int ip_update_smem(int M, int K, cplx* Wg, const cplx* Vg, const cplx* Cg, const double* wscale, int* status, int F,
-                   int NG, long long G, cudaStream_t st);
 }
 
 extern "C" int oiva_ip_update(void* What, const void* V, const void* C, const void* Cg, const double* wscale,
@@ -333,12 +331,6 @@ extern "C" int oiva_ip_update(void* What, const void* V, const void* C, const vo
                                (long long)n_batch * NG, st);
         if (rc != OIVA_ERR_INVALID) return rc;
     }
-    if (Cg && n_chan >= 7 && !force_rowowner) {  // thread-per-bin with the matrices in shared memory (solve_smem.cu)
-        const int NG = oiva_bin_groups(n_freq);
-        int rc = ip_update_smem(n_chan, n_src, (cplx*)What, (const cplx*)V, (const cplx*)Cg, wscale, status, n_freq, NG,
-                                (long long)n_batch * NG, st);
-        if (rc != OIVA_ERR_INVALID) return rc;
-    }
     OIVA_DISPATCH_M(n_chan, {
         const int per = ip_warps<M_>() * Grp<M_>::BINS;
         k_ip_update<M_><<<(unsigned)((R + per - 1) / per), ip_warps<M_>() * 32, 0, st>>>(
@@ -349,9 +341,9 @@ extern "C" int oiva_ip_update(void* What, const void* V, const void* C, const vo
 }
 
 extern "C" int oiva_init_demix(void* What, const void* C, const void* W0, const void* evecs, int mode, int* status,
-                               int n_rows, int n_chan, int n_src, void* stream) {
+                               int n_rows, int rows_per_mixture, int n_chan, int n_src, void* stream) {
     OIVA_REQUIRE(What && C && status, "oiva_init_demix: null pointer");
-    OIVA_REQUIRE(n_rows > 0 && n_src >= 1 && n_src <= n_chan, "oiva_init_demix: bad shape");
+    OIVA_REQUIRE(n_rows > 0 && rows_per_mixture > 0 && n_src >= 1 && n_src <= n_chan, "oiva_init_demix: bad shape");
     OIVA_REQUIRE(mode != OIVA_INIT_W0 || W0, "oiva_init_demix: W0 missing");
     OIVA_REQUIRE(mode != OIVA_INIT_EIG || evecs, "oiva_init_demix: eigenvectors missing");
     const long long R = n_rows;
@@ -359,7 +351,7 @@ extern "C" int oiva_init_demix(void* What, const void* C, const void* W0, const 
     OIVA_DISPATCH_M(n_chan, {
         const int per = bins_per_cta<M_>();
         k_init_demix<M_><<<(unsigned)((R + per - 1) / per), SOLVE_WARPS * 32, 0, st>>>(
-            (cplx*)What, (const cplx*)C, (const cplx*)W0, (const cplx*)evecs, mode, status, R, n_src);
+            (cplx*)What, (const cplx*)C, (const cplx*)W0, (const cplx*)evecs, mode, status, R, rows_per_mixture, n_src);
     });
     OIVA_LAUNCH_CHECK();
     return OIVA_OK;
@@ -390,15 +382,15 @@ extern "C" int oiva_compose_filters(const void* E, const void* Wr, void* Wout, i
     return OIVA_OK;
 }
 
-extern "C" int oiva_eigh(const void* C, double* evals, void* evecs, int* status, int n_rows, int n_chan,
-                         int lapack_phase, void* stream) {
+extern "C" int oiva_eigh(const void* C, double* evals, void* evecs, int* status, int n_rows, int rows_per_mixture,
+                         int n_chan, int lapack_phase, void* stream) {
     OIVA_REQUIRE(C && evals && evecs && status, "oiva_eigh: null pointer");
-    OIVA_REQUIRE(n_rows > 0, "oiva_eigh: bad shape");
+    OIVA_REQUIRE(n_rows > 0 && rows_per_mixture > 0, "oiva_eigh: bad shape");
     const long long R = n_rows;
     cudaStream_t st = (cudaStream_t)stream;
     OIVA_DISPATCH_M(n_chan, {
         k_eigh<M_><<<(unsigned)((R + SOLVE_WARPS - 1) / SOLVE_WARPS), SOLVE_WARPS * 32, 0, st>>>(
-            (const cplx*)C, evals, (cplx*)evecs, status, R, lapack_phase);
+            (const cplx*)C, evals, (cplx*)evecs, status, R, rows_per_mixture, lapack_phase);
     });
     OIVA_LAUNCH_CHECK();
     return OIVA_OK;

@@ -8,25 +8,8 @@ namespace oiva {
 template <int M, int K>
 static int launch_tpb(cplx* What, const cplx* Vg, const cplx* Cg, const double* wscale, int* status, int F, int NG,
                       long long G, cudaStream_t st) {
-    static const bool staged = [] {
-        const char* v = getenv("OIVA_TPB_STAGED");
-        return v && *v && *v != '0';
-    }();
     const unsigned grid = (unsigned)((G + TPB_WARPS - 1) / TPB_WARPS);
-    if (!staged) {  // default: covariances read straight from global memory (measured faster on B200)
-        k_ip_update_tpb<M, K, false><<<grid, TPB_WARPS * 32, 0, st>>>(What, Vg, Cg, wscale, status, F, NG, G);
-        OIVA_LAUNCH_CHECK();
-        return OIVA_OK;
-    }
-    auto kern = k_ip_update_tpb<M, K, true>;
-    const size_t smem = TPB_WARPS * tpb_warp_smem<M>();
-    static bool attr_done = false;  // per instantiation
-    if (!attr_done) {
-        OIVA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
-    kern<<<grid, TPB_WARPS * 32, smem, st>>>(What, Vg, Cg, wscale, status, F, NG,
-                                                                                     G);
+    k_ip_update_tpb<M, K><<<grid, TPB_WARPS * 32, 0, st>>>(What, Vg, Cg, wscale, status, F, NG, G);
     OIVA_LAUNCH_CHECK();
     return OIVA_OK;
 }

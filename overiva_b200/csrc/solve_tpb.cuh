@@ -96,22 +96,9 @@ __device__ __forceinline__ void lu_solve(cplx (&A)[N][N], cplx (&rhs)[N][NR], bo
     });
 }
 
-// element (i, j) of a Hermitian matrix staged in shared memory as [e][32 lanes] lower-triangle entries
-__device__ __forceinline__ cplx herm_lds(const cplx* sbase, int i, int j) {
-    const int hi = i >= j ? i : j, lo = i >= j ? j : i;
-    cplx v = sbase[(hi * (hi + 1) / 2 + lo) * OIVA_GROUP];
-    if (i < j) v.y = -v.y;
-    return v;
-}
-
-template <bool STAGED>
-__device__ __forceinline__ cplx herm_get(const cplx* base, int i, int j) {
-    if constexpr (STAGED) return herm_lds(base, i, j);
-    else return herm_load(base, i, j);
-}
 
 // OverIVA background refresh for one bin held by one thread: J = (W^H C E1)^-1 (W^H C E2)      overiva.py:96-98
-template <int M, int K, bool STAGED>
+template <int M, int K>
 __device__ __forceinline__ void background_tpb(WLane Wm, const cplx* sC, bool& singular) {
     if constexpr (K < M) {
         cplx T1[K][K], T2[K][M - K];
@@ -126,7 +113,7 @@ __device__ __forceinline__ void background_tpb(WLane Wm, const cplx* sC, bool& s
         for (int j = 0; j < M; ++j) {
             cplx crow[M];
 #pragma unroll
-            for (int c = 0; c < M; ++c) crow[c] = herm_get<STAGED>(sC, j, c);
+            for (int c = 0; c < M; ++c) crow[c] = herm_load(sC, j, c);
 #pragma unroll
             for (int i = 0; i < K; ++i) {
                 const cplx a = Wm[j * M + i];
@@ -145,7 +132,7 @@ __device__ __forceinline__ void background_tpb(WLane Wm, const cplx* sC, bool& s
 }
 
 // ---- one IP update, determined case (K == M): w_s = (W^H V_s)^-1 e_s by LU with partial pivoting ----------
-template <int M, bool STAGED>
+template <int M>
 __device__ __forceinline__ void ip_source_full(WLane Wm, const cplx* sV, int s, bool& singular) {
     cplx A[M][M], rhs[M][1];
 #pragma unroll
@@ -158,7 +145,7 @@ __device__ __forceinline__ void ip_source_full(WLane Wm, const cplx* sV, int s, 
     for (int j = 0; j < M; ++j) {
         cplx vrow[M];
 #pragma unroll
-        for (int c = 0; c < M; ++c) vrow[c] = herm_get<STAGED>(sV, j, c);
+        for (int c = 0; c < M; ++c) vrow[c] = herm_load(sV, j, c);
 #pragma unroll
         for (int i = 0; i < M; ++i) {
             const cplx a = Wm[j * M + i];
@@ -173,7 +160,7 @@ __device__ __forceinline__ void ip_source_full(WLane Wm, const cplx* sV, int s, 
     for (int i = 0; i < M; ++i) {
         cplx u = cmake(0.0, 0.0);
 #pragma unroll
-        for (int j = 0; j < M; ++j) cfma(u, herm_get<STAGED>(sV, i, j), rhs[j][0]);
+        for (int j = 0; j < M; ++j) cfma(u, herm_load(sV, i, j), rhs[j][0]);
         cfmac(d, rhs[i][0], u);
     }
     const cplx inv = crecip(csqrt_(d));
@@ -186,7 +173,7 @@ __device__ __forceinline__ void ip_source_full(WLane Wm, const cplx* sV, int s, 
 // system:  q1 = (W1^H + W2^H J^H)^-1 e_s,  q2 = J^H q1   (W1 / W2: top K / bottom M-K rows of W);  then V w = q is
 // solved by Cholesky (V is Hermitian positive definite: no pivoting, no row swaps), and the normalisation needs
 // only w^H V w = w^H q.  ~3x fewer operations than forming W_hat^H V and factorising it, same result.
-template <int M, int K, bool STAGED>
+template <int M, int K>
 __device__ __forceinline__ void ip_source_reduced(WLane Wm, const cplx* sV, int s, bool& singular) {
     constexpr int R = M - K;
     cplx q[M];
@@ -225,8 +212,7 @@ __device__ __forceinline__ void ip_source_reduced(WLane Wm, const cplx* sV, int 
     cplx Lm[oiva_tri(M)];
 #pragma unroll
     for (int e = 0; e < oiva_tri(M); ++e) {
-        if constexpr (STAGED) Lm[e] = sV[e * OIVA_GROUP];
-        else Lm[e] = ld_nc_c(sV + (size_t)e * OIVA_GROUP);
+        Lm[e] = ld_nc_c(sV + (size_t)e * OIVA_GROUP);
     }
     double dinv[M];
 #pragma unroll
@@ -280,92 +266,65 @@ __device__ __forceinline__ void ip_source_reduced(WLane Wm, const cplx* sV, int 
 }
 
 constexpr int TPB_WARPS = 4;
-template <int M>
-__host__ __device__ constexpr size_t tpb_warp_smem() { return 2 * (size_t)oiva_tri(M) * OIVA_GROUP * sizeof(cplx) + 128; }
 
-// grid: ceil(G / 4) CTAs of 4 warps; warp <-> group gi, lane <-> bin.  Per warp, the group's covariances
-// Cg[gi] and Vg[gi][s] (each ONE contiguous block of NE*32 complex) are staged in shared memory by 1-D bulk
-// TMA: C and V_0 up front, V_{s+1} as soon as the warp is done with V_s (it lands during the J refresh).
-template <int M, int K, bool STAGED>
+// The whole sweep of one bin by its thread: W rescale, K x (IP update + J refresh).  Cl / Vl point at this lane's
+// element 0 of the grouped lower triangles (Cg[gi][e][lane], Vg[gi][s][e][lane]).  Shared by the batched sweep kernel
+// below and by the persistent single-mixture loop (resident.cuh).
+template <int M, int K>
+__device__ __forceinline__ void ip_sweep_bin(WLane Wm, const cplx* Vl, const cplx* Cl, const double* wscale_b,
+                                             bool& singular, bool& bad) {
+    constexpr int NE = oiva_tri(M);
+    if (wscale_b) {  // W /= gamma (laplace) or sqrt(gamma) (gauss)              overiva.py:161-167
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double sc = wscale_b[k];
+#pragma unroll
+            for (int j = 0; j < M; ++j) Wm[j * M + k] = cscale(Wm[j * M + k], sc);
+        }
+    }
+#pragma unroll 1
+    for (int s = 0; s < K; ++s) {
+        const cplx* sV = Vl + (size_t)s * NE * OIVA_GROUP;
+        if constexpr (K < M) {
+            ip_source_reduced<M, K>(Wm, sV, s, singular);
+            background_tpb<M, K>(Wm, Cl, singular);
+        } else {
+            ip_source_full<M>(Wm, sV, s, singular);
+        }
+    }
+    // only the entries the sweep writes can go bad: the K filter columns and the K x (M-K) block J (the rest of
+    // W_hat is the constant [0; -I]) -- 20 of 36 entries at M = 6, K = 2, i.e. 0.27 GB less DRAM read per sweep
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int c = 0; c < M; ++c)
+            if (c < K || j < K) {
+                const cplx v = Wm[j * M + c];
+                if (!isfinite(v.x) || !isfinite(v.y)) bad = true;
+            }
+}
+
+// grid: ceil(G / 4) CTAs of 4 warps; warp <-> group gi, lane <-> bin; the grouped covariances Cg[gi] and Vg[gi][s]
+// are read straight from global memory as 512-byte warp segments (staging them in shared memory by bulk TMA was
+// measured slower: profiles/r01_notes).  status: one word per mixture.
+template <int M, int K>
 __global__ void __launch_bounds__(TPB_WARPS * 32) k_ip_update_tpb(cplx* __restrict__ Wg, const cplx* __restrict__ Vg,
                                                                   const cplx* __restrict__ Cg,
                                                                   const double* __restrict__ wscale, int* status,
                                                                   int F, int NG, long long G) {
     constexpr int NE = oiva_tri(M);
-    constexpr uint32_t MAT_BYTES = NE * OIVA_GROUP * sizeof(cplx);
-    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long gi = (long long)blockIdx.x * TPB_WARPS + warp;
     if (gi >= G) return;  // whole warp
-    unsigned char* wsm = smem_raw + (size_t)warp * tpb_warp_smem<M>();
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm);  // [0]: C landed, [1]: V_s landed
     const long long b = gi / NG;
     const int f = (int)(gi - b * NG) * OIVA_GROUP + lane;
-    const bool valid = f < F;  // padded lanes of the last group only take part in the barriers
-    const WLane Wm = {Wg + (size_t)gi * M * M * OIVA_GROUP + lane};  // this bin's W_hat (padded lanes: zeros, unused)
-    const cplx* Vgrp = Vg + (size_t)gi * K * NE * OIVA_GROUP;
-    // STAGED: covariances read from the warp's shared-memory copies; otherwise straight from global memory
-    const cplx* sC = STAGED ? reinterpret_cast<const cplx*>(wsm + 128) + lane : Cg + (size_t)gi * NE * OIVA_GROUP + lane;
-    const cplx* sV = reinterpret_cast<const cplx*>(wsm + 128 + MAT_BYTES) + lane;
-
-    if (STAGED && lane == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        mbar_fence_init();
-        mbar_arrive_expect_tx(&bars[0], MAT_BYTES);
-        tma_load_1d(wsm + 128, Cg + (size_t)gi * NE * OIVA_GROUP, MAT_BYTES, &bars[0]);
-        mbar_arrive_expect_tx(&bars[1], MAT_BYTES);
-        tma_load_1d(wsm + 128 + MAT_BYTES, Vgrp, MAT_BYTES, &bars[1]);
-    }
-    __syncwarp();
-    bool singular = false;
-
-    if (valid && wscale) {  // W /= gamma (laplace) or sqrt(gamma) (gauss)              overiva.py:161-167
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const double sc = wscale[b * K + k];
-#pragma unroll
-            for (int j = 0; j < M; ++j) Wm[j * M + k] = cscale(Wm[j * M + k], sc);
-        }
-    }
-
-#pragma unroll 1
-    for (int s = 0; s < K; ++s) {
-        if (STAGED) mbar_wait(&bars[1], s & 1);
-        else sV = Vgrp + (size_t)s * NE * OIVA_GROUP + lane;
-        if (valid) {
-            if constexpr (K < M) {
-                ip_source_reduced<M, K, STAGED>(Wm, sV, s, singular);
-            } else {
-                ip_source_full<M, STAGED>(Wm, sV, s, singular);
-            }
-        }
-        __syncwarp();  // every lane is done reading V_s: its buffer may be refilled
-        if (STAGED && lane == 0 && s + 1 < K) {
-            mbar_arrive_expect_tx(&bars[1], MAT_BYTES);
-            tma_load_1d(wsm + 128 + MAT_BYTES, Vgrp + (size_t)(s + 1) * NE * OIVA_GROUP, MAT_BYTES, &bars[1]);
-        }
-        if (K < M) {
-            if (STAGED && s == 0) mbar_wait(&bars[0], 0);
-            if (valid) background_tpb<M, K, STAGED>(Wm, sC, singular);
-        }
-    }
-
-    if (valid) {
-        // only the entries the sweep writes can go bad: the K filter columns and the K x (M-K) block J (the rest of
-        // W_hat is the constant [0; -I]) -- 20 of 36 entries at M = 6, K = 2, i.e. 0.27 GB less DRAM read per sweep
-        bool bad = false;
-#pragma unroll
-        for (int j = 0; j < M; ++j)
-#pragma unroll
-            for (int c = 0; c < M; ++c)
-                if (c < K || j < K) {
-                    const cplx v = Wm[j * M + c];
-                    if (!isfinite(v.x) || !isfinite(v.y)) bad = true;
-                }
-        if (singular || bad)
-            atomicOr(status, (singular ? OIVA_STATUS_SINGULAR : 0) | (bad ? OIVA_STATUS_NONFINITE : 0));
-    }
+    if (f >= F) return;  // padded lanes of the last group
+    const WLane Wm = {Wg + (size_t)gi * M * M * OIVA_GROUP + lane};  // this bin's W_hat
+    bool singular = false, bad = false;
+    ip_sweep_bin<M, K>(Wm, Vg + (size_t)gi * K * NE * OIVA_GROUP + lane, Cg + (size_t)gi * NE * OIVA_GROUP + lane,
+                       wscale ? wscale + b * K : nullptr, singular, bad);
+    if (singular || bad)
+        atomicOr(status + b, (singular ? OIVA_STATUS_SINGULAR : 0) | (bad ? OIVA_STATUS_NONFINITE : 0));
 }
 
 }  // namespace oiva

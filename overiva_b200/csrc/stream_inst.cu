@@ -50,11 +50,7 @@ static int launch(int kind, StreamParams p, long long G, cudaStream_t st) {
             typedef typename StoreC<ST>::type XC;
             const size_t smem = 128 + 2 * (size_t)POWER_FB * M * OIVA_GROUP * sizeof(XC);
             auto kern = k_demix_power_staged<ST, M, KC>;
-            static bool attr_done = false;
-            if (!attr_done) {
-                OIVA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_done = true;
-            }
+            OIVA_SET_MAX_SMEM_ONCE(kern, smem);
             kern<<<grid, 32 * warps, smem, st>>>(p);
         } else if (kind == KIND_POWER)
             k_demix_power<ST, M, KC><<<grid, 32 * warps, 0, st>>>(p);

@@ -251,8 +251,7 @@ def separate_batch(mix, n_src=None, n_iter=20, framesize=4096, hop=None, win_a=N
                 core._PIPE_LOCK.release()
             raise
         xd, yd, Yd, scratch, plans = state["xd"], state["yd"], state["Yd"], state["scratch"], state["plans"]
-        for plan in plans.values():
-            plan.reset_status()  # (on the caller's stream, which the pipeline streams wait for next)
+        status_dev = torch.zeros((B,), dtype=torch.int32, device=dev)  # one status word per mixture
         for st in (s_in, s_cmp, s_out):
             st.wait_stream(main)
         try:
@@ -274,6 +273,7 @@ def separate_batch(mix, n_src=None, n_iter=20, framesize=4096, hop=None, win_a=N
                     if nb not in plans:
                         plans[nb] = core.DemixPlan(nb, T, F, M, K, code, dtype, dev)
                     plan = plans[nb]
+                    plan.reset_status()
                     st = core._stream_ptr(dev)
                     L.check(lib.oiva_stft_analysis(core._ptr(xd[slot]), int(xh.dtype == torch.float32), N * M, M, 1, N,
                                                    int(pad_front), core._ptr(wa), core._ptr(tw),
@@ -286,6 +286,7 @@ def separate_batch(mix, n_src=None, n_iter=20, framesize=4096, hop=None, win_a=N
                     L.check(lib.oiva_stft_synthesis(core._ptr(Yd), core._ptr(ws), core._ptr(tw), core._ptr(scratch),
                                                     core._ptr(yd[slot]), int(out_dtype == torch.float32), nb, T, K,
                                                     int(framesize), hop, plan.code, st), "oiva_stft_synthesis")
+                    status_dev[b0 : b0 + nb].copy_(plan.status_words, non_blocking=True)
                     ev_cmp[slot] = s_cmp.record_event()
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(ev_cmp[slot])
@@ -293,10 +294,9 @@ def separate_batch(mix, n_src=None, n_iter=20, framesize=4096, hop=None, win_a=N
                     ev_out[slot] = s_out.record_event()
             for st in (s_in, s_cmp, s_out):
                 main.wait_stream(st)
-            with torch.cuda.stream(s_cmp):
-                for plan in plans.values():
-                    plan.raise_on_failure()
+            status = status_dev.cpu().numpy()  # (synchronises the caller's stream)
             main.synchronize()
+            core.raise_for_status(status)
         finally:
             if owned:
                 core._PIPE_LOCK.release()

@@ -11,7 +11,7 @@ Kept from the reference:
   * which algorithm runs for which case (``overiva_sim.py:250-256``: no ``auxiva_pca`` for one target, ``ogive`` only
     for one target; unknown algorithms are skipped, ``:316-317``),
   * the evaluation rule of ``convergence_callback`` (``overiva_sim.py:210-232``): synthesis, reorder by decreasing
-    power unless the algorithm is in ``overdet_algos``, drop the ``framesize // 2`` delay of the STFT state buffer,
+    power unless the algorithm's base name is in ``overdet_algos`` (the reference tests ``name``, not ``full_name``), drop the ``framesize // 2`` delay of the STFT state buffer,
     score the first ``n_targets`` outputs plus a noise channel against targets + background,
   * the record schema (``overiva_sim.py:258-271``) and the ``data.json`` / ``parameters.json`` / ``arguments.json``
     files ``overiva_sim_plot.py:161-190`` reads (``data.json`` = list of segments, each a list of records).
@@ -196,23 +196,36 @@ class GpuEngine:
         return Y, dt, sdrs, sirs
 
     def run(self, algo, X, n_targets, kwargs):
-        """-> (Y device (B, T, F, K), seconds per mixture)."""
+        """-> (Y device (B, T, F, K), seconds per mixture, failed (B,) bool).  A mixture whose separation fails
+        numerically (singular matrix) is flagged, its estimate is NaN, and the others are unaffected -- the reference
+        records NaN for the failing task only (``overiva_sim.py:334-350``)."""
         torch, core = self.torch, self.core
         B = X.shape[0]
+        failed = np.zeros(B, dtype=bool)
         torch.cuda.synchronize(self.device)
         t0 = time.perf_counter()
-        if algo == "auxiva":
-            Y = core.overiva_batch(X, None, **kwargs)
-        elif algo == "overiva":
-            Y = core.overiva_batch(X, n_targets, **kwargs)
-        elif algo == "auxiva_pca":
-            Y = torch.stack([core.auxiva_pca(X[b], n_src=n_targets, **kwargs) for b in range(B)])
-        elif algo == "ogive":
-            Y = torch.stack([core.ogive(X[b], **kwargs) for b in range(B)])
+        if algo in ("auxiva", "overiva"):
+            Y, status = core.overiva_batch(X, None if algo == "auxiva" else n_targets, return_status=True, **kwargs)
+            failed = (status & 1) != 0
+            if failed.any():
+                Y[torch.from_numpy(failed).to(Y.device)] = float("nan")
+        elif algo in ("auxiva_pca", "ogive"):
+            outs = []
+            for b in range(B):
+                try:
+                    outs.append(core.auxiva_pca(X[b], n_src=n_targets, **kwargs) if algo == "auxiva_pca"
+                                else core.ogive(X[b], **kwargs))
+                except np.linalg.LinAlgError:
+                    failed[b] = True
+                    outs.append(None)
+            good = next((o for o in outs if o is not None), None)
+            if good is None:
+                raise np.linalg.LinAlgError("Singular matrix")
+            Y = torch.stack([o if o is not None else torch.full_like(good, float("nan")) for o in outs])
         else:
             raise ValueError(algo)
         torch.cuda.synchronize(self.device)
-        return Y, (time.perf_counter() - t0) / B
+        return Y, (time.perf_counter() - t0) / B, failed
 
 
 def run(parameters=None, results_dir=None, batch=64, engine=None, progress=None):
@@ -229,6 +242,13 @@ def run(parameters=None, results_dir=None, batch=64, engine=None, progress=None)
     for i, a in enumerate(args):
         groups.setdefault((a[0], a[1]), []).append(i)
     overdet = set(parameters.get("overdet_algos", []))
+
+    def reorder(algo_name):
+        # overiva_sim.py:220 tests the algorithm's BASE name (`name`, passed at :282 and :329) against overdet_algos,
+        # which in the shipped configuration lists FULL names ("overiva_laplace", ...): the outputs are therefore
+        # always re-ordered by power.  Kept as is -- records must be comparable with the reference's.
+        return algo_name not in overdet
+
     flen = int(parameters.get("bss_eval_filter_length", 1))  # 512 = mir_eval's bss_eval_sources (host, slower)
     for (n_targets, n_mics), idx in groups.items():
         algos = algorithms_for(parameters, n_targets)
@@ -252,7 +272,7 @@ def run(parameters=None, results_dir=None, batch=64, engine=None, progress=None)
                         n_t, n_m, rt60, sinr, seed = args[i]
                         try:
                             _, dt, sdrs, sirs = engine.run_monitored(algo, X[b], n_targets, kwargs, refs[b],
-                                                                     full_name not in overdet, seed)
+                                                                     reorder(algo), seed)
                         except np.linalg.LinAlgError:
                             dt, sdrs, sirs = float("nan"), [[float("nan")]], [[float("nan")]]
                         recs[b].append({
@@ -262,20 +282,23 @@ def run(parameters=None, results_dir=None, batch=64, engine=None, progress=None)
                     if progress:
                         progress(full_name, n_targets, n_mics, len(chunk), recs[-1][-1]["runtime"])
                     continue
+                nan_score = ([float("nan")], [float("nan")])
                 try:
-                    Y, per_mix = engine.run(algo, X, n_targets, kwargs)
+                    Y, per_mix, failed = engine.run(algo, X, n_targets, kwargs)
                     y = engine.synthesis(Y)
-                    final = [evaluate(y[b], refs[b], n_targets, framesize, full_name not in overdet, args[i][4], flen)
+                    # the reference logs a failure and records NaN for THAT task only (:333-349)
+                    final = [nan_score if failed[b] else
+                             evaluate(y[b], refs[b], n_targets, framesize, reorder(algo), args[i][4], flen)
                              for b, i in enumerate(chunk)]
-                except np.linalg.LinAlgError:  # the reference logs the failure and records NaN (:333-349)
-                    per_mix = float("nan")
-                    final = [([float("nan")], [float("nan")])] * len(chunk)
+                except np.linalg.LinAlgError:  # every mixture of the chunk failed
+                    per_mix, failed = float("nan"), np.ones(len(chunk), dtype=bool)
+                    final = [nan_score] * len(chunk)
                 for b, i in enumerate(chunk):
                     n_t, n_m, rt60, sinr, seed = args[i]
                     recs[b].append({
                         "algorithm": full_name, "n_targets": n_t, "n_mics": n_m, "rt60": rt60, "sinr": sinr,
                         "seed": seed, "sdr": [init[b][0], final[b][0]], "sir": [init[b][1], final[b][1]],
-                        "runtime": per_mix, "n_samples": int(n_samples),
+                        "runtime": float("nan") if failed[b] else per_mix, "n_samples": int(n_samples),
                     })
                 if progress:
                     progress(full_name, n_targets, n_mics, len(chunk), per_mix)

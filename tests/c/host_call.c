@@ -25,13 +25,15 @@ int main(int argc, char** argv) {
     }
     fclose(f);
     oiva_plan_desc d = {B, T, F, 0, M, K, model, OIVA_C128, 0};
-    const int status = oiva_overiva_host(X, Y, W, NULL, &d, n_iter, proj_back, init);
+    int* per_mixture = (int*)calloc((size_t)B, sizeof(int));
+    const int status = oiva_overiva_host(X, Y, W, NULL, &d, n_iter, proj_back, init, per_mixture);
     if (status < 0) {
         fprintf(stderr, "oiva_overiva_host failed (%d): %s\n", status, oiva_last_error());
         return 5;
     }
     if (status & OIVA_STATUS_SINGULAR) {
-        fprintf(stderr, "singular\n");
+        for (int b = 0; b < B; ++b)
+            if (per_mixture[b] & OIVA_STATUS_SINGULAR) fprintf(stderr, "mixture %d: singular\n", b);
         return 6;
     }
     f = fopen(argv[2], "wb");
@@ -41,5 +43,6 @@ int main(int argc, char** argv) {
     free(X);
     free(Y);
     free(W);
+    free(per_mixture);
     return 0;
 }

@@ -123,7 +123,7 @@ def ip_update(What, V, Cx, wscale, K, grouped_c=True):
     Wd, Vgd, Cd = to_dev(What), pack_cov(V), to_dev(Cx)
     Cgd = pack_cov(Cx[:, :, None]) if grouped_c else None
     wsd = to_dev(wscale) if wscale is not None else None
-    st = torch.zeros(4, dtype=torch.int32, device=dev())
+    st = torch.zeros(B, dtype=torch.int32, device=dev())  # one status word per mixture
     NG = lib.oiva_bin_groups(F)
     Wg = torch.empty((B * NG, M * M, 32), dtype=torch.complex128, device=dev())
     L.check(lib.oiva_group_rows(P(Wd), P(Wg), B, F, M * M, stream()), "oiva_group_rows")
@@ -131,7 +131,8 @@ def ip_update(What, V, Cx, wscale, K, grouped_c=True):
     Wd.fill_(float("nan"))
     L.check(lib.oiva_ungroup_rows(P(Wg), P(Wd), B, F, M * M, stream()), "oiva_ungroup_rows")
     torch.cuda.synchronize()
-    return Wd.cpu().numpy(), int(st[0].item())
+    per = st.cpu().numpy()
+    return Wd.cpu().numpy(), (int(per[0]) if B == 1 else per)
 
 
 def init_demix(Cx, K, mode, W0=None, evecs=None):
@@ -142,7 +143,7 @@ def init_demix(Cx, K, mode, W0=None, evecs=None):
     Ed = to_dev(evecs) if evecs is not None else None
     What = torch.empty((R, M, M), dtype=torch.complex128, device=dev())
     st = torch.zeros(4, dtype=torch.int32, device=dev())
-    L.check(lib.oiva_init_demix(P(What), P(Cd), P(W0d), P(Ed), mode, P(st), R, M, K, stream()), "oiva_init_demix")
+    L.check(lib.oiva_init_demix(P(What), P(Cd), P(W0d), P(Ed), mode, P(st), R, R, M, K, stream()), "oiva_init_demix")
     torch.cuda.synchronize()
     return What.cpu().numpy(), int(st[0].item())
 
@@ -154,7 +155,7 @@ def eigh(Cx, lapack_phase):
     ev = torch.empty((R, M), dtype=torch.float64, device=dev())
     vec = torch.empty((R, M, M), dtype=torch.complex128, device=dev())
     st = torch.zeros(4, dtype=torch.int32, device=dev())
-    L.check(lib.oiva_eigh(P(Cd), P(ev), P(vec), P(st), R, M, int(lapack_phase), stream()), "oiva_eigh")
+    L.check(lib.oiva_eigh(P(Cd), P(ev), P(vec), P(st), R, R, M, int(lapack_phase), stream()), "oiva_eigh")
     torch.cuda.synchronize()
     return ev.cpu().numpy(), vec.cpu().numpy(), int(st[0].item())
 
@@ -178,25 +179,3 @@ def demix_output(Xg, Weff, B, T, F, M, K, code):
     L.check(lib.oiva_demix_output(P(Xg), P(Wd), P(Y), B, T, F, M, K, code, stream()), "oiva_demix_output")
     torch.cuda.synchronize()
     return Y.cpu().numpy()
-
-
-def ip_update_power(What, V, Cx, wscale, K, Xg, T, code):
-    """fused sweep + next-epoch statistic: returns (What', r2 (B,K,T), status)"""
-    lib = L.load()
-    B, F, M, _ = What.shape
-    Wd, Vgd = to_dev(What), pack_cov(V)
-    Cgd = pack_cov(Cx[:, :, None])
-    wsd = to_dev(wscale) if wscale is not None else None
-    st = torch.zeros(4, dtype=torch.int32, device=dev())
-    NG = lib.oiva_bin_groups(F)
-    Tp = lib.oiva_frame_pitch(T)
-    Wg = torch.empty((B * NG, M * M, 32), dtype=torch.complex128, device=dev())
-    L.check(lib.oiva_group_rows(P(Wd), P(Wg), B, F, M * M, stream()), "oiva_group_rows")
-    part = torch.full((B, NG, K, Tp), np.nan, dtype=torch.float64, device=dev())
-    L.check(lib.oiva_ip_update_power(P(Wg), P(Vgd), P(Cgd), P(wsd), P(st), P(Xg), P(part), B, T, F, M, K, code,
-                                     stream()), "oiva_ip_update_power")
-    L.check(lib.oiva_ungroup_rows(P(Wg), P(Wd), B, F, M * M, stream()), "oiva_ungroup_rows")
-    r2 = torch.empty((B, K, Tp), dtype=torch.float64, device=dev())
-    L.check(lib.oiva_sum_partials(P(part), NG, P(r2), B, T, K, stream()), "oiva_sum_partials")
-    torch.cuda.synchronize()
-    return Wd.cpu().numpy(), r2.cpu().numpy()[:, :, :T], int(st[0].item())

@@ -166,9 +166,8 @@ def test_host_batch_pipeline_equals_device_batch():
         ob.overiva_batch(bad, n_src=2, n_iter=3, chunk=3)
 
 
-def test_large_batch(monkeypatch):
-    """>= 1184 bin groups (no frame splitting anywhere; with OIVA_FUSE=1 the plan would run the fused sweep +
-    next-epoch-statistic kernel, which tests/test_kernels_gpu.py covers directly); results vs the oracle"""
+def test_large_batch():
+    """>= 1184 bin groups (no frame splitting anywhere); results vs the oracle"""
     B = 37
     Xs = np.stack([small_test_mixture(600 + b, 4, 2, n_samples=20000, frame=2048, hop=1024) for b in range(B)])
     assert Xs.shape[2] == 1025 and B * 33 >= 1184

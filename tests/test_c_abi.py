@@ -70,7 +70,8 @@ def test_host_entry_point_through_ctypes():
     W = np.empty((1, F, M, K), dtype=np.complex128)
     desc = L.PlanDesc(1, T, F, 0, M, K, L.MODEL_LAPLACE, L.C128, 0)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    st = lib.oiva_overiva_host(p(Xc), p(Y), p(W), p(np.ascontiguousarray(W0[None])), C.byref(desc), 6, 1, L.INIT_W0)
+    st = lib.oiva_overiva_host(p(Xc), p(Y), p(W), p(np.ascontiguousarray(W0[None])), C.byref(desc), 6, 1, L.INIT_W0,
+                               None)
     assert st == 0, L.last_error()
     Yo, Wo = orc.overiva(X, n_src=K, n_iter=6, W0=W0, return_filters=True)
     assert rel_err(Y[0], Yo) <= 1e-10 and rel_err(W[0], Wo) <= 1e-10
@@ -78,10 +79,12 @@ def test_host_entry_point_through_ctypes():
     X32 = Xc.astype(np.complex64)
     Y32 = np.empty((1, T, F, K), dtype=np.complex64)
     desc32 = L.PlanDesc(1, T, F, 0, M, K, L.MODEL_LAPLACE, L.C64, 0)
-    assert lib.oiva_overiva_host(p(X32), p(Y32), None, None, C.byref(desc32), 6, 1, L.INIT_EYE) == 0
+    assert lib.oiva_overiva_host(p(X32), p(Y32), None, None, C.byref(desc32), 6, 1, L.INIT_EYE, None) == 0
     assert rel_err(Y32[0].astype(np.complex128), orc.overiva(X, n_src=K, n_iter=6)) <= 1e-3
     # numerical failure is reported through the returned status word, argument errors through a negative code
     bad = Xc.copy()
     bad[..., 2] = bad[..., 0]
-    assert lib.oiva_overiva_host(p(bad), p(Y), None, None, C.byref(desc), 3, 1, L.INIT_EYE) & L.STATUS_SINGULAR
-    assert lib.oiva_overiva_host(p(Xc), p(Y), None, None, C.byref(desc), 3, 1, L.INIT_W0) == -1  # W0 missing
+    per = (C.c_int * 1)()
+    assert lib.oiva_overiva_host(p(bad), p(Y), None, None, C.byref(desc), 3, 1, L.INIT_EYE, per) & L.STATUS_SINGULAR
+    assert per[0] & L.STATUS_SINGULAR
+    assert lib.oiva_overiva_host(p(Xc), p(Y), None, None, C.byref(desc), 3, 1, L.INIT_W0, None) == L.ERR_INVALID  # W0 missing
