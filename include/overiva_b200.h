@@ -240,6 +240,11 @@ int oiva_gram(const double* a, long long a_row_stride, long long a_sample_stride
               long long b_row_stride, long long b_sample_stride, int b_rows, long long n_samples, void* scratch,
               double* out, void* stream);
 
+/* fp64 throughput of this GPU in TFLOP/s, measured: kind 0 = plain DFMA, kind 1 = the fp64 tensor-core instruction
+ * (DMMA, mma.sync.m8n8k4).  Synchronous (best of `reps` timed launches on `stream`).  The denominator of the
+ * FMA-bound covariance shapes (M = 16, K = 4) and the DMMA-vs-DFMA evaluation of SURVEY.md 7.1(12). */
+int oiva_fp64_peak(int kind, int iters, int reps, double* tflops, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Plan: the whole overiva() call on device pointers (what the Python entry points use).
  * The plan owns no device memory: the caller provides one workspace block.

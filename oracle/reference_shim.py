@@ -10,13 +10,16 @@ as-is in this image:
    vectors" semantics, which numpy >= 2 rejects -> ``numpy.linalg.solve`` is wrapped for the
    duration of each reference call.
 
-The reference tree stays read-only and nothing is copied from it.  ``/root/reference`` does
-not exist on the GPU box, so everything here is optional: ``available()`` says whether the
-real files can be used.
+The reference tree stays read-only and no source is copied from it.  ``/root/reference`` does
+not exist on the GPU box; ``oracle/build_ref.py`` byte-compiles the three modules into the
+git-ignored ``oracle/_ref/*.pyc`` (a build output, like a compiled C reference), which travels
+with the snapshot and is imported here when the source tree is absent.  ``available()`` says
+whether the real implementation can be used (``source()`` tells which form).
 """
 from __future__ import annotations
 
 import contextlib
+import importlib.machinery
 import importlib.util
 import os
 import sys
@@ -25,12 +28,22 @@ import types
 import numpy as np
 
 REFERENCE_DIR = os.environ.get("OVERIVA_REFERENCE_DIR", "/root/reference")
+COMPILED_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 _modules = {}
 
 
+def source():
+    """'tree' (the .py files under REFERENCE_DIR), 'compiled' (oracle/_ref/*.pyc built from them) or None."""
+    if os.path.isfile(os.path.join(REFERENCE_DIR, "overiva.py")):
+        return "tree"
+    if all(os.path.isfile(os.path.join(COMPILED_DIR, m + ".pyc")) for m in ("overiva", "auxiva_pca", "ive")):
+        return "compiled"
+    return None
+
+
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_DIR, "overiva.py"))
+    return source() is not None
 
 
 def _install_pra_stub():
@@ -76,11 +89,17 @@ def _load(name):
     drop-in ``overiva.py`` etc., so the plain import name must not be used)."""
     if name in _modules:
         return _modules[name]
-    if not available():
-        raise RuntimeError("reference tree not present at %s" % REFERENCE_DIR)
+    src = source()
+    if src is None:
+        raise RuntimeError("reference not present (neither %s nor %s)" % (REFERENCE_DIR, COMPILED_DIR))
     _install_pra_stub()
-    path = os.path.join(REFERENCE_DIR, name + ".py")
-    spec = importlib.util.spec_from_file_location("_reference_" + name, path)
+    if src == "tree":
+        path = os.path.join(REFERENCE_DIR, name + ".py")
+        spec = importlib.util.spec_from_file_location("_reference_" + name, path)
+    else:
+        path = os.path.join(COMPILED_DIR, name + ".pyc")
+        loader = importlib.machinery.SourcelessFileLoader("_reference_" + name, path)
+        spec = importlib.util.spec_from_loader("_reference_" + name, loader, origin=path)
     mod = importlib.util.module_from_spec(spec)
     if name == "auxiva_pca":
         # auxiva_pca.py:28 does ``from overiva import overiva``: point it at the real one

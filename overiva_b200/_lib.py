@@ -75,6 +75,7 @@ SIGNATURES = {
     "oiva_stft_synthesis": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "oiva_gram_scratch_bytes": (_sz, [_i, _ll]),
     "oiva_gram": (_i, [_p, _ll, _ll, _i, _p, _ll, _ll, _i, _ll, _p, _p, _p]),
+    "oiva_fp64_peak": (_i, [_i, _i, _i, C.POINTER(C.c_double), _p]),
     "oiva_plan_create": (_i, [C.POINTER(_p), C.POINTER(PlanDesc)]),
     "oiva_plan_destroy": (None, [_p]),
     "oiva_plan_workspace_bytes": (_sz, [_p]),

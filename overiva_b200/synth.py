@@ -181,6 +181,49 @@ def stft_domain_batch_torch(n_batch, n_frames, n_freq, n_mics, n_src, seed, devi
     return out
 
 
+def stft_domain_bins_torch(n_frames, n_freq_total, f_begin, f_end, n_mics, n_src, seed, device, dtype=None,
+                           n_interferers=10, sinr_db=10.0, noise_db=-60.0):
+    """Bins ``[f_begin, f_end)`` of ONE long synthetic mixture ``(T, f_end - f_begin, M)``, reproducible for ANY split
+    of the frequency axis on multiples of 32 bins: the per-frame source activities depend on ``seed`` only and every
+    group of 32 bins draws from its own generator ``(seed, group)``, so concatenating the ranges drawn by different
+    ranks (or drawing the full range in one piece) gives bit-identical data -- what the frequency-sharded benchmark
+    needs to compare its shards with a single-GPU run.  Same source model as :func:`stft_domain_batch_torch`."""
+    import torch
+
+    assert f_begin % 32 == 0 and 0 <= f_begin <= f_end <= n_freq_total
+    dtype = dtype or torch.complex128
+    rdt = torch.float64 if dtype == torch.complex128 else torch.float32
+    T, M, K = n_frames, n_mics, n_src
+    Q = K + n_interferers
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    act = 0.5 * torch.randn(T, 1, Q, generator=g, device=device, dtype=rdt) ** 2 + 0.05
+    gain = torch.ones(Q, dtype=rdt, device=device)
+    if n_interferers:
+        gain[K:] = (10 ** (-sinr_db / 10) * K / n_interferers) ** 0.5
+    amp = (act * gain).to(dtype)
+    out = torch.empty((T, f_end - f_begin, M), dtype=dtype, device=device)
+    sig = 10 ** (noise_db / 20) * K**0.5
+    for f0 in range(f_begin, f_end, 32):
+        nb = min(32, f_end - f0, n_freq_total - f0)
+        g.manual_seed(int(seed) * 1000003 + 7919 * (f0 // 32) + 1)
+
+        def rnd(*shape):
+            return torch.randn(*shape, generator=g, device=device, dtype=rdt)
+
+        def lap(*shape):
+            u = torch.rand(2, *shape, generator=g, device=device, dtype=rdt).clamp_min(1e-12).log()
+            return u[0] - u[1]
+
+        # always draw a full group of 32 bins (so a ragged last group sees the same numbers however it is reached)
+        S = torch.complex(lap(T, 32, Q), lap(T, 32, Q)) * amp
+        A = torch.complex(rnd(32, M, Q), rnd(32, M, Q))
+        X = torch.einsum("fmq,tfq->tfm", A, S)
+        X += sig * torch.complex(rnd(T, 32, M), rnd(T, 32, M))
+        out[:, f0 - f_begin : f0 - f_begin + nb] = X[:, :nb]
+    return out
+
+
 def audio_batch_torch(n_batch, n_samples, n_mics, n_src, seed, device, n_interferers=10, sinr_db=10.0, snr_db=60.0,
                       fs=16000, chunk=64):
     """Device-side generator of time-domain inputs for throughput runs of the audio-in / audio-out path:
