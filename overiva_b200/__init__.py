@@ -7,7 +7,9 @@ Drop-in entry points (same signatures as onolab-tmu/overiva):
 plus ``overiva_batch`` for many independent mixtures and ``overiva_b200.distributed`` for the
 multi-GPU drivers.  See DESIGN.md / INTEGRATION.md.
 """
-from .core import DemixPlan, auxiva, auxiva_pca, ogive, overiva, overiva_batch  # noqa: F401
+from .core import (DemixPlan, auxiva, auxiva_pca, clear_plan_cache, ogive, overiva, overiva_batch,  # noqa: F401
+                   raise_for_status)
 
-__all__ = ["overiva", "auxiva", "auxiva_pca", "ogive", "overiva_batch", "DemixPlan"]
+__all__ = ["overiva", "auxiva", "auxiva_pca", "ogive", "overiva_batch", "DemixPlan", "clear_plan_cache",
+           "raise_for_status"]
 __version__ = "0.1.0"

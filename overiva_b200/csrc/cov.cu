@@ -11,6 +11,7 @@ namespace oiva {
 #define OIVA_DECL(M)                                                                                 \
     int cov_launch_m##M(int dtype, int KC, const CovParams& p, cudaStream_t st, int* nsplit_out); \
     int cov_max_kc_m##M();                                                                                     \
+    int cov_launch_tiled_m##M(int dtype, const CovParams& p, cudaStream_t st, int* nsplit_out);                \
     int relayout_cov_launch_m##M(int dtype, RelayoutCovParams p, int max_split, cudaStream_t st, int* nsplit_out);
 OIVA_DECL(1) OIVA_DECL(2) OIVA_DECL(3) OIVA_DECL(4) OIVA_DECL(5) OIVA_DECL(6) OIVA_DECL(7) OIVA_DECL(8)
 OIVA_DECL(9) OIVA_DECL(10) OIVA_DECL(11) OIVA_DECL(12) OIVA_DECL(13) OIVA_DECL(14) OIVA_DECL(15) OIVA_DECL(16)
@@ -130,18 +131,36 @@ extern "C" int oiva_weighted_cov_ws(const void* Xg, const double* phi, void* Vg,
         OIVA_CASE(9) OIVA_CASE(10) OIVA_CASE(11) OIVA_CASE(12) OIVA_CASE(13) OIVA_CASE(14) OIVA_CASE(15) OIVA_CASE(16)
 #undef OIVA_CASE
     }
+    // many channels and >= 3 sources left: the tiled kernel takes 4 sources per pass (one pass over X for config 5's
+    // K = 4; cov.cuh).  It combines frame splits through scratch slots only.
+    static const bool no_tiled = [] {
+        const char* v = getenv("OIVA_COV_NO_TILED");
+        return v && *v && *v != '0';
+    }();
     int k0 = 0;
     while (k0 < n_src) {
-        int KC = pick_chunk(n_src - k0, max_kc);
+        const bool tiled = !no_tiled && n_chan >= 9 && n_src - k0 >= 3 && (p.Vpart || p.nsplit == 1 || p.nsplit <= 0);
+        int KC = tiled ? 4 : pick_chunk(n_src - k0, max_kc);
         p.k0 = k0;
         int rc = OIVA_ERR_INVALID;
         int nsplit_used = 0;
-        switch (n_chan) {
-#define OIVA_CASE(M) case M: rc = cov_launch_m##M(dtype, KC, p, st, &nsplit_used); break;
-            OIVA_CASE(1) OIVA_CASE(2) OIVA_CASE(3) OIVA_CASE(4) OIVA_CASE(5) OIVA_CASE(6) OIVA_CASE(7) OIVA_CASE(8)
-            OIVA_CASE(9) OIVA_CASE(10) OIVA_CASE(11) OIVA_CASE(12) OIVA_CASE(13) OIVA_CASE(14) OIVA_CASE(15)
-            OIVA_CASE(16)
+        if (tiled) {
+            CovParams q = p;
+            if (!q.Vpart) q.nsplit = 1;  // no scratch: no frame splits
+            switch (n_chan) {
+#define OIVA_CASE(M) case M: rc = cov_launch_tiled_m##M(dtype, q, st, &nsplit_used); break;
+                OIVA_CASE(9) OIVA_CASE(10) OIVA_CASE(11) OIVA_CASE(12) OIVA_CASE(13) OIVA_CASE(14) OIVA_CASE(15)
+                OIVA_CASE(16)
 #undef OIVA_CASE
+            }
+        } else {
+            switch (n_chan) {
+#define OIVA_CASE(M) case M: rc = cov_launch_m##M(dtype, KC, p, st, &nsplit_used); break;
+                OIVA_CASE(1) OIVA_CASE(2) OIVA_CASE(3) OIVA_CASE(4) OIVA_CASE(5) OIVA_CASE(6) OIVA_CASE(7) OIVA_CASE(8)
+                OIVA_CASE(9) OIVA_CASE(10) OIVA_CASE(11) OIVA_CASE(12) OIVA_CASE(13) OIVA_CASE(14) OIVA_CASE(15)
+                OIVA_CASE(16)
+#undef OIVA_CASE
+            }
         }
         if (rc) return rc;
         p.nsplit = nsplit_used;  // later passes keep the first pass's split

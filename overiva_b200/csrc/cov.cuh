@@ -397,4 +397,334 @@ __global__ void __launch_bounds__(cov_block_parts(M) * 32) k_cov_blocked(const C
     cov_team_body<CovBlock<ST, M, KC>, ST, M, KC>(p, smem_raw, blockIdx.x, gridDim.x, lane, warp == 0, warp);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Tiled variant for many channels AND several sources (M >= 9, K >= 3; config 5: M = 16, K = 4).
+//
+// The blocked kernel above keeps 4 x 4 entries x 2 sources per warp, so four sources cost two passes over X and
+// every pass re-forms the products x_i conj(x_j): 2 x (4 + 2*2) = 16 fp64-pipe operations per entry and frame.
+// Here a warp keeps a 2 x 4 tile for FOUR sources (the same 64 complex accumulators): the product is formed once,
+// 4 + 2*4 = 12 operations per entry and frame, and X is streamed ONCE per epoch.  The 4 x 4 diagonal blocks get
+// their own tile type -- the 10 entries i >= j, real-only diagonal accumulators -- which costs exactly as much as a
+// 2 x 4 tile (6 x 12 + 4 x 6 = 96 operations per frame), so nothing is computed that is not stored (the blocked kernel
+// computes 160 entries for the 136 of M = 16).  NB^2 tiles per bin group (NB = ceil(M/4)): NB(NB-1) full + NB diagonal.
+// They do not fit the registers of one SM (a tile takes ~200 registers per thread), so the tiles of a group are
+// split over the TWO CTAs of a thread-block CLUSTER ("halves", CovTiling<M>::WARPS warps each).  Both halves need the
+// same frames: every chunk of frames is fetched from L2 / HBM ONCE -- each CTA issues half of it as a bulk-TMA copy
+// with .multicast::cluster, which lands in the shared memory of both CTAs and signals both CTAs' "full" barriers; a stage
+// is re-filled when the consumers of BOTH CTAs have released it (they arrive on the local and on the peer's "empty"
+// barrier).  8 warps per SM = 2 per scheduler with up to 255 registers each; the per-frame work of every warp is
+// identical (96 DFMA-pipe operations), so the four schedulers stay balanced.
+// ---------------------------------------------------------------------------------------------------------
+template <int M>
+struct CovTiling {
+    static constexpr int NB = (M + 3) / 4;
+    static constexpr int NFULL = NB * (NB - 1);  // 2 x 4 tiles of the strictly-lower 4 x 4 blocks
+    static constexpr int NDIAG = NB;             // 10-entry tiles of the diagonal blocks
+    static constexpr int FULL_H = NFULL / 2;     // full tiles per half
+    static constexpr int DIAG_H0 = (NDIAG + 1) / 2;
+    static constexpr int WARPS = FULL_H + DIAG_H0;  // NB = 4: 6 + 2 = 8 warps per CTA; NB = 3: 3 + 2 = 5
+    static constexpr int KC = 4;
+    static constexpr int TC = 8;                 // frames per stage (M = 16, complex128: 64 KB; 3 stages)
+};
+
+// one 2 x 4 tile (rows r0, r0+1; columns c0..c0+3; all below the diagonal blocks) for KC = 4 sources
+template <typename ST, int M>
+struct CovTileFull {
+    typedef typename StoreC<ST>::type XC;
+    static constexpr int KC = 4, TC = CovTiling<M>::TC, NE = oiva_tri(M);
+    cplx acc[2][4][KC];
+    int r0, c0;
+    __device__ __forceinline__ void init(int ft) {  // ft: index among the full tiles of the group
+        const int blk = ft >> 1;
+        int bi = 1;
+        while (bi * (bi + 1) / 2 <= blk) ++bi;  // off-diagonal blocks (1,0) (2,0) (2,1) (3,0) ...
+        const int bj = blk - bi * (bi - 1) / 2;
+        r0 = bi * 4 + (ft & 1) * 2;
+        c0 = bj * 4;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int k = 0; k < KC; ++k) acc[a][b][k] = cmake(0.0, 0.0);
+    }
+    // WHOLE: a complete chunk of TC frames (no per-frame test: the loads of a frame can be hoisted over the arithmetic
+    // of the previous one)
+    template <bool WHOLE>
+    __device__ __forceinline__ void accumulate(const XC* __restrict__ xs, const double* __restrict__ ph, int nfr, int lane) {
+        const XC* xr = xs + (size_t)r0 * OIVA_GROUP + lane;
+        const XC* xc = xs + (size_t)c0 * OIVA_GROUP + lane;
+        const bool r_ok0 = r0 < M, r_ok1 = r0 + 1 < M;  // channels beyond M (M not a multiple of 4) contribute zeros
+#pragma unroll
+        for (int fr = 0; fr < TC; ++fr) {
+            if (WHOLE || fr < nfr) {
+                cplx xi[2], xj[4];
+                double w[KC];
+                xi[0] = r_ok0 ? widen(xr[(fr * M + 0) * OIVA_GROUP]) : cmake(0.0, 0.0);
+                xi[1] = r_ok1 ? widen(xr[(fr * M + 1) * OIVA_GROUP]) : cmake(0.0, 0.0);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) xj[b] = widen(xc[(fr * M + b) * OIVA_GROUP]);  // c0 + 3 < 4*(NB-1) <= M
+#pragma unroll
+                for (int k = 0; k < KC; ++k) w[k] = ph[k * TC + fr];
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const double pr = fma(xi[a].x, xj[b].x, xi[a].y * xj[b].y);
+                        const double pi = fma(xi[a].y, xj[b].x, -(xi[a].x * xj[b].y));
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) {
+                            acc[a][b][k].x = fma(w[k], pr, acc[a][b][k].x);
+                            acc[a][b][k].y = fma(w[k], pi, acc[a][b][k].y);
+                        }
+                    }
+            }
+        }
+    }
+    __device__ __forceinline__ void finish(cplx* __restrict__ Vgrp, int k0, int K, double invT, int lane) const {
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int i = r0 + a, j = c0 + b;
+                if (i < M) {
+                    const int e = i * (i + 1) / 2 + j;
+#pragma unroll
+                    for (int k = 0; k < KC; ++k)
+                        if (k0 + k < K)
+                            Vgrp[((size_t)(k0 + k) * NE + e) * OIVA_GROUP + lane] =
+                                cmake(acc[a][b][k].x * invT, acc[a][b][k].y * invT);
+                }
+            }
+    }
+};
+
+// the lower triangle (incl. diagonal) of one diagonal 4 x 4 block, KC = 4 sources: 6 complex + 4 real accumulators
+template <typename ST, int M>
+struct CovTileDiag {
+    typedef typename StoreC<ST>::type XC;
+    static constexpr int KC = 4, TC = CovTiling<M>::TC, NE = oiva_tri(M);
+    cplx off[6][KC];   // (1,0) (2,0) (2,1) (3,0) (3,1) (3,2)
+    double dg[4][KC];  // (0,0) (1,1) (2,2) (3,3)
+    int d0;
+    __device__ __forceinline__ void init(int d) {
+        d0 = d * 4;
+#pragma unroll
+        for (int n = 0; n < 6; ++n)
+#pragma unroll
+            for (int k = 0; k < KC; ++k) off[n][k] = cmake(0.0, 0.0);
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int k = 0; k < KC; ++k) dg[n][k] = 0.0;
+    }
+    template <bool WHOLE>
+    __device__ __forceinline__ void accumulate(const XC* __restrict__ xs, const double* __restrict__ ph, int nfr, int lane) {
+        const XC* xd = xs + (size_t)d0 * OIVA_GROUP + lane;
+#pragma unroll
+        for (int fr = 0; fr < TC; ++fr) {
+            if (WHOLE || fr < nfr) {
+                cplx x[4];
+                double w[KC];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) x[a] = (d0 + a < M) ? widen(xd[(fr * M + a) * OIVA_GROUP]) : cmake(0.0, 0.0);
+#pragma unroll
+                for (int k = 0; k < KC; ++k) w[k] = ph[k * TC + fr];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const double pr = fma(x[a].x, x[a].x, x[a].y * x[a].y);
+#pragma unroll
+                    for (int k = 0; k < KC; ++k) dg[a][k] = fma(w[k], pr, dg[a][k]);
+#pragma unroll
+                    for (int b = 0; b < a; ++b) {
+                        const int n = a * (a - 1) / 2 + b;
+                        const double qr = fma(x[a].x, x[b].x, x[a].y * x[b].y);
+                        const double qi = fma(x[a].y, x[b].x, -(x[a].x * x[b].y));
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) {
+                            off[n][k].x = fma(w[k], qr, off[n][k].x);
+                            off[n][k].y = fma(w[k], qi, off[n][k].y);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void finish(cplx* __restrict__ Vgrp, int k0, int K, double invT, int lane) const {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = d0 + a;
+            if (i < M) {
+#pragma unroll
+                for (int k = 0; k < KC; ++k)
+                    if (k0 + k < K)
+                        Vgrp[((size_t)(k0 + k) * NE + i * (i + 1) / 2 + i) * OIVA_GROUP + lane] = cmake(dg[a][k] * invT, 0.0);
+#pragma unroll
+                for (int b = 0; b < a; ++b) {
+                    const int n = a * (a - 1) / 2 + b;
+                    const int e = i * (i + 1) / 2 + d0 + b;
+#pragma unroll
+                    for (int k = 0; k < KC; ++k)
+                        if (k0 + k < K)
+                            Vgrp[((size_t)(k0 + k) * NE + e) * OIVA_GROUP + lane] =
+                                cmake(off[n][k].x * invT, off[n][k].y * invT);
+                }
+            }
+        }
+    }
+};
+
+// Consumer loop of one warp over the units (group, frame split) of its cluster; TILE = CovTileFull / CovTileDiag.
+// `active` = false: an idle warp (NB = 3: the second half has one tile fewer) that only keeps the barriers moving.
+// Lane 0 of warp 0 of EACH CTA is that CTA's producer: it issues its half of every chunk (multicast to both CTAs) and
+// the CTA's own phi rows, never blocks (a stage that is still in use is retried later) and keeps polling while its
+// warp waits for data, so the ring refills as fast as stages are released.
+template <typename TILE, typename ST, int M>
+__device__ __forceinline__ void cov_tiled_consume(const CovParams& p, unsigned char* smem, int tile_index, bool active,
+                                                  int lane, bool is_producer_warp, long long pair, long long n_pairs,
+                                                  uint32_t rank) {
+    typedef typename StoreC<ST>::type XC;
+    constexpr int TC = CovTiling<M>::TC, KC = CovTiling<M>::KC, NE = oiva_tri(M);
+    const GroupLayout& L = p.L;
+    const int S = p.stages;
+    const int Tp = L.frame_pitch();
+    constexpr size_t x_stage = (size_t)TC * M * OIVA_GROUP * sizeof(XC);
+    constexpr size_t stage_bytes = ((x_stage + (size_t)KC * TC * sizeof(double) + 127) / 128) * 128;
+    constexpr uint32_t frame_bytes = (uint32_t)(M * OIVA_GROUP * sizeof(XC));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + S;
+    unsigned char* stage0 = smem + 128 * ((2 * S * sizeof(uint64_t) + 127) / 128);
+    const int nchunks = (L.T + TC - 1) / TC;
+    const int nsplit = p.nsplit;
+    const long long U = p.G * nsplit;
+    const XC* Xg = reinterpret_cast<const XC*>(p.Xg);
+    const size_t frame_elems = L.frame_elems(), group_elems = L.group_elems();
+    const bool leader = is_producer_warp && lane == 0;
+    const uint32_t peer_empty0 = cluster_map(smem_u32(empty), rank ^ 1u);
+
+    // ---- producer state (leader lane) ----------------------------------------------------------------------------
+    long long pu = pair;
+    int pc = 0, pce = 0, pstage = 0, puse = 0;
+    const XC* psrc = nullptr;
+    const double* pphi = nullptr;
+    auto producer_unit = [&]() {
+        const long long gi = pu / nsplit;
+        const int sp = (int)(pu - gi * nsplit);
+        pc = (int)((long long)nchunks * sp / nsplit);
+        pce = (int)((long long)nchunks * (sp + 1) / nsplit);
+        const long long b = gi / p.NGphi;
+        psrc = Xg + (size_t)gi * group_elems + (size_t)pc * TC * frame_elems;
+        pphi = p.phi + (size_t)b * p.K * Tp + (size_t)pc * TC;
+    };
+    auto try_issue = [&]() {  // issue every chunk whose stage is free (in both CTAs), without blocking
+        while (pu < U) {
+            if (pc >= pce) {
+                pu += n_pairs;
+                if (pu < U) producer_unit();
+                continue;
+            }
+            if (puse > 0 && !mbar_test_cluster(&empty[pstage], (puse - 1) & 1)) return;
+            const int nfr = min(TC, L.T - pc * TC);
+            unsigned char* dst = stage0 + (size_t)pstage * stage_bytes;
+            const uint32_t pb = (uint32_t)(((nfr + 1) & ~1) * sizeof(double));
+            mbar_arrive_expect_tx(&full[pstage], (uint32_t)nfr * frame_bytes + KC * pb);
+            // this CTA's half of the frames of the chunk, delivered to both CTAs
+            const int h0 = min(nfr, TC / 2);
+            const int f0 = rank ? h0 : 0, fn = rank ? nfr - h0 : h0;
+            if (fn > 0)
+                tma_load_1d_multicast(dst + (size_t)f0 * frame_bytes, psrc + (size_t)f0 * frame_elems,
+                                      (uint32_t)fn * frame_bytes, &full[pstage], (uint16_t)3);
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const int ks = min(p.k0 + k, p.K - 1);  // padded source slots re-read the last row (never written back)
+                tma_load_1d(dst + x_stage + (size_t)k * TC * sizeof(double), pphi + (size_t)ks * Tp, pb, &full[pstage]);
+            }
+            psrc += (size_t)TC * frame_elems;
+            pphi += TC;
+            ++pc;
+            if (++pstage == S) {
+                pstage = 0;
+                ++puse;
+            }
+        }
+    };
+    if (leader && pu < U) {
+        producer_unit();
+        try_issue();
+    } else if (!leader) {
+        pu = U;
+    }
+
+    int cstage = 0, cphase = 0;
+    for (long long u = pair; u < U; u += n_pairs) {
+        const long long gi = u / nsplit;
+        const int sp = (int)(u - gi * nsplit);
+        const int c0 = (int)((long long)nchunks * sp / nsplit);
+        const int c1 = (int)((long long)nchunks * (sp + 1) / nsplit);
+        TILE tile;
+        tile.init(tile_index);
+        for (int c = c0; c < c1; ++c) {
+            const int nfr = min(TC, L.T - c * TC);
+            if (leader) {
+                while (!mbar_test(&full[cstage], cphase)) try_issue();
+                try_issue();
+            }
+            __syncwarp();
+            mbar_wait(&full[cstage], cphase);
+            const unsigned char* src = stage0 + (size_t)cstage * stage_bytes;
+            if (active) {
+                if (nfr == TC)
+                    tile.template accumulate<true>(reinterpret_cast<const XC*>(src),
+                                                   reinterpret_cast<const double*>(src + x_stage), nfr, lane);
+                else
+                    tile.template accumulate<false>(reinterpret_cast<const XC*>(src),
+                                                    reinterpret_cast<const double*>(src + x_stage), nfr, lane);
+            }
+            __syncwarp();
+            if (lane == 0) {  // release the stage in both CTAs (each producer writes into both)
+                mbar_arrive(&empty[cstage]);
+                mbar_arrive_cluster(peer_empty0 + (uint32_t)cstage * 8u);
+            }
+            if (++cstage == S) {
+                cstage = 0;
+                cphase ^= 1;
+            }
+        }
+        if (active) {
+            const size_t grp_elems = (size_t)p.K * NE * OIVA_GROUP;
+            cplx* dst = (nsplit > 1) ? p.Vpart + ((size_t)sp * p.G + gi) * grp_elems : p.Vg + (size_t)gi * grp_elems;
+            tile.finish(dst, p.k0, p.K, p.invT, lane);
+        }
+    }
+}
+
+// grid = 2 x pairs, cluster dimension 2: cluster j runs the units j, j + pairs, ...; CTA rank h owns half h of the
+// tiles.  nsplit > 1 REQUIRES p.Vpart (per-split slots, summed afterwards in a fixed order): no atomics here.
+template <typename ST, int M>
+__global__ void __launch_bounds__(CovTiling<M>::WARPS * 32, 1) k_cov_tiled(const CovParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    typedef CovTiling<M> TL;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+        uint64_t* empty = full + p.stages;
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full[s], 1);               // the CTA's own producer (expect_tx); bytes come from both CTAs
+            mbar_init(&empty[s], 2 * TL::WARPS);  // the consumer warps of BOTH CTAs
+        }
+        mbar_fence_init();
+    }
+    cluster_sync_all();  // both CTAs' barriers exist before anyone copies into / arrives on the peer's
+    const uint32_t rank = cluster_ctarank();
+    const long long pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    if (warp < TL::FULL_H) {
+        cov_tiled_consume<CovTileFull<ST, M>, ST, M>(p, smem_raw, (int)rank * TL::FULL_H + warp, true, lane, warp == 0, pair,
+                                                    n_pairs, rank);
+    } else {
+        const int d = (rank ? TL::DIAG_H0 : 0) + (warp - TL::FULL_H);
+        cov_tiled_consume<CovTileDiag<ST, M>, ST, M>(p, smem_raw, d, d < TL::NDIAG, lane, false, pair, n_pairs, rank);
+    }
+    cluster_sync_all();  // nobody leaves while the peer may still signal this CTA's barriers
+}
+
 }  // namespace oiva

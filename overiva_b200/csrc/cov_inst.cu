@@ -21,7 +21,7 @@ static int env_int(const char* name, int dflt) {
 // frame splits per group that minimise the busiest team's work: ceil(units / teams) units of
 // ceil(nchunks / split) chunks each, plus ~2 chunk-times of ring fill and write-out per unit
 static int choose_split(long long G, int nchunks, long long n_teams, long long max_split) {
-    long long hi = (4 * n_teams + G - 1) / G;
+    long long hi = (16 * n_teams + G - 1) / G;  // (up to ~16 units per team: finer splits balance better)
     if (hi > nchunks) hi = nchunks;
     if (hi > max_split) hi = max_split < 1 ? 1 : max_split;
     long long best_cost = -1;
@@ -179,6 +179,65 @@ int OIVA_CAT(cov_launch_m, OIVA_COV_M)(int dtype, int KC, const CovParams& p, cu
     }
     oiva_set_error("cov_launch: unsupported source chunk %d", KC);
     return OIVA_ERR_INVALID;
+}
+
+// tiled kernel (cov.cuh: k_cov_tiled): M >= 9, chunks of 4 sources, clusters of two CTAs (the two halves of the tiles)
+template <typename ST>
+static int launch_tiled(CovParams p, cudaStream_t st, int* nsplit_out) {
+    constexpr int M = OIVA_COV_M;
+    if constexpr (M < 9) {
+        oiva_set_error("cov_launch: the tiled kernel needs M >= 9");
+        return OIVA_ERR_INVALID;
+    } else {
+        typedef typename StoreC<ST>::type XC;
+        typedef CovTiling<M> TL;
+        constexpr int TC = TL::TC, KC = TL::KC;
+        constexpr size_t x_stage = (size_t)TC * M * OIVA_GROUP * sizeof(XC);
+        constexpr size_t stage_bytes = ((x_stage + (size_t)KC * TC * sizeof(double) + 127) / 128) * 128;
+        auto kern = k_cov_tiled<ST, M>;
+        int S = env_int("OIVA_COV_TILED_STAGES", 3);
+        if (S < 2) S = 2;
+        const size_t budget = 200 * 1024;
+        while (S > 2 && 128 * ((2 * S * sizeof(uint64_t) + 127) / 128) + (size_t)S * stage_bytes > budget) --S;
+        const size_t smem = 128 * ((2 * S * sizeof(uint64_t) + 127) / 128) + (size_t)S * stage_bytes;
+        p.stages = S;
+        OIVA_SET_MAX_SMEM_ONCE(kern, budget);
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.blockDim = dim3(TL::WARPS * 32, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cfg.gridDim = dim3(2, 1, 1);
+        int max_pairs = 0;
+        OIVA_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&max_pairs, kern, &cfg));
+        if (max_pairs < 1) max_pairs = 1;
+        const int nchunks = (p.L.T + TC - 1) / TC;
+        if (p.nsplit <= 0) {
+            p.nsplit = 1;
+            if (p.G < 2ll * max_pairs && nchunks > 1 && p.Vpart && p.max_split > 1)
+                p.nsplit = choose_split(p.G, nchunks, max_pairs, p.max_split);
+        }
+        if (p.nsplit > 1 && !p.Vpart) {
+            oiva_set_error("cov_launch: the tiled kernel needs scratch for frame splits");
+            return OIVA_ERR_INVALID;
+        }
+        if (nsplit_out) *nsplit_out = p.nsplit;
+        long long pairs = p.G * p.nsplit;
+        if (pairs > max_pairs) pairs = max_pairs;
+        cfg.gridDim = dim3((unsigned)(2 * pairs), 1, 1);
+        OIVA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
+        return OIVA_OK;
+    }
+}
+
+int OIVA_CAT(cov_launch_tiled_m, OIVA_COV_M)(int dtype, const CovParams& p, cudaStream_t st, int* nsplit_out) {
+    return dtype == OIVA_C64 ? launch_tiled<float>(p, st, nsplit_out) : launch_tiled<double>(p, st, nsplit_out);
 }
 
 // relayout + input covariance in one pass (relayout_cov.cuh); M <= 8 only.  max_split: slots in p.Cpart (<= 1: none)

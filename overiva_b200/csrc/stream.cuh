@@ -119,13 +119,14 @@ __global__ void __launch_bounds__(512) k_demix_power(const StreamParams p) {
     }
 }
 
-// Same statistic for K > KC (several source-chunk warps per group): instead of every warp re-reading X from global
+// Same kernels for K > KC (several source-chunk warps per group): instead of every warp re-reading X from global
 // memory, the CTA stages each block of POWER_FB frames ONCE in shared memory -- a contiguous piece of the grouped
 // layout, i.e. one 1-D bulk-TMA copy into a 2-stage ring (full / empty mbarriers as in cov.cuh) -- and all warps
-// read it from there (conflict-free LDS.128).  Measured at M = K = 6, 256 mixtures: see DESIGN.md.
+// read it from there (conflict-free LDS.128).  OUTPUT = false: the statistic (k_demix_power's result, same
+// arithmetic); OUTPUT = true: the demixed samples Y (k_demix_output's result).  Measured: DESIGN.md.
 // grid (G, nsplit), block = 32 * ceil(K/KC); dynamic smem = 128 + 2 * POWER_FB * M * 32 * sizeof(XC)
-template <typename ST, int M, int KC>
-__global__ void __launch_bounds__(512) k_demix_power_staged(const StreamParams p) {
+template <typename ST, int M, int KC, bool OUTPUT>
+__global__ void __launch_bounds__(512) k_demix_staged(const StreamParams p) {
     typedef typename StoreC<ST>::type XC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr size_t stage_bytes = (size_t)POWER_FB * M * OIVA_GROUP * sizeof(XC);
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(512) k_demix_power_staged(const StreamParams p
     cplx w[M][KC];
     load_filters<M, KC>(w, p, b * L.F + (bin_ok ? f : 0), gi, lane, bin_ok, k0);
     const XC* xg = reinterpret_cast<const XC*>(p.Xg) + (size_t)gi * L.group_elems();
+    XC* Y = reinterpret_cast<XC*>(p.Y);
     const int nblk = Tp / POWER_FB;
     const int blk0 = (int)((long long)nblk * blockIdx.y / p.nsplit);
     const int blk1 = (int)((long long)nblk * (blockIdx.y + 1) / p.nsplit);
@@ -185,34 +187,45 @@ __global__ void __launch_bounds__(512) k_demix_power_staged(const StreamParams p
 #pragma unroll
                 for (int c = 0; c < M; ++c) x[c] = widen(xs[((size_t)j * M + c) * OIVA_GROUP + lane]);
                 demix_frame<M, KC>(y, x, w);
+                if constexpr (OUTPUT) {
+                    if (bin_ok) {
+                        XC* dst = Y + (((size_t)b * L.T + t0 + j) * L.F + f) * p.K + k0;
 #pragma unroll
-                for (int k = 0; k < KC; ++k) v[k][j] = fma(y[k].x, y[k].x, y[k].y * y[k].y);
-            } else {
+                        for (int k = 0; k < KC; ++k)
+                            if (k0 + k < p.K) narrow(dst[k], y[k]);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < KC; ++k) v[k][j] = fma(y[k].x, y[k].x, y[k].y * y[k].y);
+                }
+            } else if constexpr (!OUTPUT) {
 #pragma unroll
                 for (int k = 0; k < KC; ++k) v[k][j] = 0.0;
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
+        if constexpr (!OUTPUT) {
 #pragma unroll
-        for (int k = 0; k < KC; ++k) {
+            for (int k = 0; k < KC; ++k) {
 #pragma unroll
-            for (int lvl = 0; lvl < 3; ++lvl) {
-                const int H = POWER_FB >> (lvl + 1);
-                const int off = 16 >> lvl;
-                const bool up = (lane & off) != 0;
+                for (int lvl = 0; lvl < 3; ++lvl) {
+                    const int H = POWER_FB >> (lvl + 1);
+                    const int off = 16 >> lvl;
+                    const bool up = (lane & off) != 0;
 #pragma unroll
-                for (int n = 0; n < H; ++n) {
-                    const double lo = v[k][n], hi = v[k][n + H];
-                    const double send = up ? lo : hi;
-                    const double keep = up ? hi : lo;
-                    v[k][n] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    for (int n = 0; n < H; ++n) {
+                        const double lo = v[k][n], hi = v[k][n + H];
+                        const double send = up ? lo : hi;
+                        const double keep = up ? hi : lo;
+                        v[k][n] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
                 }
+                double sres = v[k][0];
+                sres += __shfl_xor_sync(0xffffffffu, sres, 2);
+                sres += __shfl_xor_sync(0xffffffffu, sres, 1);
+                if ((lane & 3) == 0 && k0 + k < p.K) p.r2part[((size_t)gi * p.K + k0 + k) * Tp + t0 + (lane >> 2)] = sres;
             }
-            double sres = v[k][0];
-            sres += __shfl_xor_sync(0xffffffffu, sres, 2);
-            sres += __shfl_xor_sync(0xffffffffu, sres, 1);
-            if ((lane & 3) == 0 && k0 + k < p.K) p.r2part[((size_t)gi * p.K + k0 + k) * Tp + t0 + (lane >> 2)] = sres;
         }
     }
 }

@@ -45,13 +45,21 @@ static int launch(int kind, StreamParams p, long long G, cudaStream_t st) {
             const char* v = getenv("OIVA_POWER_NO_STAGE");
             return v && *v && *v != '0';
         }();
-        if (kind == KIND_POWER && warps > 1 && !no_staged) {
+        if ((kind == KIND_POWER || kind == KIND_OUTPUT) && warps > 1 && !no_staged) {
             // several source-chunk warps per group: stage X once per CTA instead of once per warp
             typedef typename StoreC<ST>::type XC;
             const size_t smem = 128 + 2 * (size_t)POWER_FB * M * OIVA_GROUP * sizeof(XC);
-            auto kern = k_demix_power_staged<ST, M, KC>;
-            OIVA_SET_MAX_SMEM_ONCE(kern, smem);
-            kern<<<grid, 32 * warps, smem, st>>>(p);
+            p.nsplit = frame_splits(G, p.L.frame_pitch() / POWER_FB);
+            grid = dim3((unsigned)G, p.nsplit, 1);
+            if (kind == KIND_POWER) {
+                auto kern = k_demix_staged<ST, M, KC, false>;
+                OIVA_SET_MAX_SMEM_ONCE(kern, smem);
+                kern<<<grid, 32 * warps, smem, st>>>(p);
+            } else {
+                auto kern = k_demix_staged<ST, M, KC, true>;
+                OIVA_SET_MAX_SMEM_ONCE(kern, smem);
+                kern<<<grid, 32 * warps, smem, st>>>(p);
+            }
         } else if (kind == KIND_POWER)
             k_demix_power<ST, M, KC><<<grid, 32 * warps, 0, st>>>(p);
         else if (kind == KIND_OUTPUT)
