@@ -635,10 +635,12 @@ def run_gpu(args):
                 torch.cuda.synchronize()
                 times.append(a.elapsed_time(b))
             ms_c = statistics.median(times)
-            t0 = time.perf_counter()
-            for _ in range(3):
+            for _ in range(3):  # steady state of the drop-in call: staging buffers exist from the second call on
                 Yn = ob.overiva(Xn, **kw)
-            ms_np = (time.perf_counter() - t0) / 3 * 1e3
+            t0 = time.perf_counter()
+            for _ in range(5):
+                Yn = ob.overiva(Xn, **kw)
+            ms_np = (time.perf_counter() - t0) / 5 * 1e3
             tt, ff, mm = Xn.shape
             kk = kw.get("n_src") or mm
             alg = (2 * kw["n_iter"] + 2) * ff * tt * mm * 16 + ff * tt * kk * 16

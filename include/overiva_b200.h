@@ -46,6 +46,7 @@ extern "C" {
 #define OIVA_ERR_NOMEM (-2)
 #define OIVA_ERR_STATE (-3)
 #define OIVA_ERR_CUDA (-4) /* a CUDA runtime call failed; oiva_last_error() names it */
+#define OIVA_ERR_UNSUPPORTED (-5) /* the shape is outside what this entry point covers (callers fall back) */
 
 #define OIVA_C128 0
 #define OIVA_C64 1
@@ -239,6 +240,20 @@ size_t oiva_gram_scratch_bytes(int n_rows, long long n_samples);
 int oiva_gram(const double* a, long long a_row_stride, long long a_sample_stride, int a_rows, const double* b,
               long long b_row_stride, long long b_sample_stride, int b_rows, long long n_samples, void* scratch,
               double* out, void* stream);
+
+/* n_iter epochs of the loop (overiva.py:138-190) in ONE persistent cooperative launch, for inputs short enough that
+ * every bin group's samples fit the shared memory of the SMs (one short mixture: BASELINE configs 1-2; M <= 8): the grid
+ * stays resident, the samples are read from HBM once and kept in shared memory for all epochs, the epochs are separated
+ * by grid barriers instead of kernel boundaries (csrc/resident.cuh).  Same arguments as the separate kernels: Xg grouped
+ * samples, Wg grouped W_hat (in/out), Cg grouped input covariance, r2part (B,NG,K,Tp) and rbuf (B,K,Tp) scratch,
+ * scratch = oiva_weighted_cov_scratch_bytes() bytes of partial-covariance slots, sync = oiva_loop_resident_sync_bytes()
+ * bytes (zeroed by the call), status = n_batch words.  Returns OIVA_ERR_UNSUPPORTED (nothing launched) when the shape
+ * does not fit; callers then run the kernel-per-step loop.
+ * replaces: overiva.py:138-190 (the whole epoch loop). */
+size_t oiva_loop_resident_sync_bytes(int n_batch, int n_freq);
+int oiva_loop_resident(const void* Xg, void* Wg, const void* Cg, double* r2part, double* rbuf, void* scratch,
+                       size_t scratch_bytes, void* sync, int* status, int n_batch, int n_frames, int n_freq,
+                       int n_freq_total, int n_chan, int n_src, int model, int dtype, int n_iter, void* stream);
 
 /* fp64 throughput of this GPU in TFLOP/s, measured: kind 0 = plain DFMA, kind 1 = the fp64 tensor-core instruction
  * (DMMA, mma.sync.m8n8k4).  Synchronous (best of `reps` timed launches on `stream`).  The denominator of the

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "liboveriva_b200.so")
 
 OK = 0
-ERR_INVALID, ERR_NOMEM, ERR_STATE, ERR_CUDA = -1, -2, -3, -4
+ERR_INVALID, ERR_NOMEM, ERR_STATE, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 C128, C64 = 0, 1
 MODEL_LAPLACE, MODEL_GAUSS, MODEL_NONE, MODEL_OGIVE_LAPLACE, MODEL_OGIVE_GAUSS = 0, 1, 2, 3, 4
 INIT_EYE, INIT_EIG, INIT_W0 = 0, 1, 2
@@ -75,6 +75,8 @@ SIGNATURES = {
     "oiva_stft_synthesis": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "oiva_gram_scratch_bytes": (_sz, [_i, _ll]),
     "oiva_gram": (_i, [_p, _ll, _ll, _i, _p, _ll, _ll, _i, _ll, _p, _p, _p]),
+    "oiva_loop_resident_sync_bytes": (_sz, [_i, _i]),
+    "oiva_loop_resident": (_i, [_p, _p, _p, _p, _p, _p, _sz, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "oiva_fp64_peak": (_i, [_i, _i, _i, C.POINTER(C.c_double), _p]),
     "oiva_plan_create": (_i, [C.POINTER(_p), C.POINTER(PlanDesc)]),
     "oiva_plan_destroy": (None, [_p]),

@@ -47,7 +47,8 @@ def _ptr(t):
 # numpy out: 4.9 ms -> see DESIGN.md).  Results go to pinned memory from torch's caching host allocator (a freed
 # result's block is reused by the next call, so steady-state calls allocate nothing).
 _STAGING = {}
-_STAGING_LOCK = threading.Lock()
+_STAGING_SEEN = {}  # (shape, dtype) of pageable inputs seen once: pinned staging starts with the SECOND call of a shape
+_STAGING_LOCK = threading.Lock()  # (allocating pinned memory costs more than one pageable copy saves)
 _STAGING_MAX_BYTES = 256 << 20
 
 
@@ -58,6 +59,11 @@ def _staging_buffer(shape, dtype):
     key = (tuple(shape), dtype)
     buf = _STAGING.get(key)
     if buf is None:
+        if key not in _STAGING_SEEN:
+            if len(_STAGING_SEEN) > 64:
+                _STAGING_SEEN.clear()
+            _STAGING_SEEN[key] = True
+            return None
         while _STAGING and sum(b.numel() * b.element_size() for b in _STAGING.values()) + nbytes > _STAGING_MAX_BYTES:
             _STAGING.pop(next(iter(_STAGING)))
         buf = torch.empty(shape, dtype=dtype, pin_memory=True)
@@ -90,6 +96,7 @@ class _Input:
             raise TypeError("X must be complex64 or complex128, got %s" % t.dtype)
         self.device = _require_cuda(t.device if t.is_cuda else device)
         self.dtype = t.dtype
+        self.staged = False
         if t.is_cuda or self.pinned:
             self.dev = t.to(self.device, non_blocking=True).contiguous()
             return
@@ -102,6 +109,7 @@ class _Input:
                     buf.copy_(t)
                     self.dev = buf.to(self.device, non_blocking=True)
                     torch.cuda.current_stream(self.device).synchronize()  # the buffer is reusable from here on
+                    self.staged = True
                     return
             finally:
                 _STAGING_LOCK.release()
@@ -112,9 +120,12 @@ class _Input:
             t = t.to(dtype)
         if self.kind == "cuda":
             return t
-        out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # torch's caching host allocator
-        out.copy_(t, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        if self.pinned or self.staged:
+            out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # torch's caching host allocator
+            out.copy_(t, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        else:
+            out = t.cpu()
         return out.numpy() if self.kind == "numpy" else out
 
 
@@ -330,6 +341,7 @@ def clear_plan_cache():
         del _PLAN_CACHE_ORDER[:]
     _PIPE_STATE.clear()
     _STAGING.clear()
+    _STAGING_SEEN.clear()
 
 
 # Host pipelines (overiva_batch / stft.separate_batch on host inputs) keep their three streams for the life of the

@@ -25,7 +25,8 @@ struct oiva_plan {
     int Tp, NG;
     int es;  // bytes per real element of X / Y
     // workspace offsets
-    size_t off_xg, off_c, off_cg, off_what, off_wg, off_vg, off_weff, off_r2part, off_r2, off_phi, off_wscale, off_evals, off_status, off_covws;
+    size_t off_xg, off_c, off_cg, off_what, off_wg, off_vg, off_weff, off_r2part, off_r2, off_phi, off_wscale, off_evals, off_status, off_covws, off_sync;
+    int resident;  // the persistent single-launch loop: 0 = not tried yet, 1 = in use, -1 = shape does not fit
     size_t covws_bytes;
     size_t ws_bytes;
     unsigned char* ws;
@@ -125,6 +126,7 @@ extern "C" int oiva_plan_create(oiva_plan_t** out, const oiva_plan_desc* desc) {
     // per-split partial covariances of inputs with few bin groups (deterministic frame-split accumulation)
     p->covws_bytes = oiva_weighted_cov_scratch_bytes(d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.n_src);
     p->off_covws = o;   o += align_up(p->covws_bytes);
+    p->off_sync = o;    o += align_up(oiva_loop_resident_sync_bytes(d.n_batch, d.n_freq));
     p->ws_bytes = o;
     p->spans = new std::vector<TimedSpan>();
     p->pool = new std::vector<cudaEvent_t>();
@@ -361,12 +363,43 @@ static bool plan_use_graph(const oiva_plan_t* p, int n_iter) {
         const char* v = getenv("OIVA_NO_GRAPH");
         return v && *v && *v != '0';
     }();
-    return !disabled && !p->timing && n_iter >= 2 && p->G < 4096;
+    // (inputs of hundreds of MB run kernels of milliseconds: nothing to gain, and their plans are too large for the
+    // Python-side plan cache, so the capture would be paid on every call)
+    const size_t xg_bytes = oiva_grouped_bytes(p->d.n_batch, p->d.n_frames, p->d.n_freq, p->d.n_chan, p->d.dtype);
+    return !disabled && !p->timing && n_iter >= 2 && p->G < 4096 && xg_bytes < ((size_t)256 << 20);
+}
+
+// One short mixture (few bin groups, samples that fit the shared memory of the SMs): the whole loop in ONE persistent
+// cooperative launch (resident.cuh) instead of 5 kernels per epoch.  Returns OIVA_ERR_UNSUPPORTED when the shape does not
+// fit (remembered: later calls go straight to the kernel-per-step loop).
+static int plan_iterate_resident(oiva_plan_t* p, int n_iter, void* stream) {
+    const char* off = getenv("OIVA_NO_RESIDENT");  // (read per call: the tests run both loops in one process)
+    const bool disabled = off && *off && *off != '0';
+    const oiva_plan_desc& d = p->d;
+    if (disabled || p->timing || p->resident < 0 || !p->covws_bytes || d.n_chan > 8 ||
+        !(d.model == OIVA_MODEL_LAPLACE || d.model == OIVA_MODEL_GAUSS || d.model == OIVA_MODEL_NONE))
+        return OIVA_ERR_UNSUPPORTED;
+    int rc = oiva_loop_resident(p->ws + p->off_xg, p->ws + p->off_wg, p->ws + p->off_cg, (double*)(p->ws + p->off_r2part),
+                                (double*)(p->ws + p->off_r2), p->ws + p->off_covws, p->covws_bytes, p->ws + p->off_sync,
+                                (int*)(p->ws + p->off_status), d.n_batch, d.n_frames, d.n_freq, p->n_freq_total, d.n_chan,
+                                d.n_src, d.model, d.dtype, n_iter, stream);
+    if (rc == OIVA_ERR_UNSUPPORTED) {
+        p->resident = -1;
+        return rc;
+    }
+    if (rc) return rc;
+    p->resident = 1;
+    p->launches += 1;
+    return OIVA_OK;
 }
 
 extern "C" int oiva_plan_iterate(oiva_plan_t* p, int n_iter, void* stream) {
     PLAN_INITED(p, "oiva_plan_iterate");
     if (n_iter <= 0) return OIVA_OK;
+    {
+        const int rc = plan_iterate_resident(p, n_iter, stream);
+        if (rc != OIVA_ERR_UNSUPPORTED) return rc;
+    }
     if (!plan_use_graph(p, n_iter)) return plan_iterate_eager(p, n_iter, stream);
     cudaStream_t st = (cudaStream_t)stream;
     if (!p->graph_exec || p->graph_n_iter != n_iter) {

@@ -1,0 +1,403 @@
+// The whole epoch loop of a SHORT input in ONE persistent cooperative launch (configs 1-2 of BASELINE.json: a single
+// 15 s mixture; the call the reference times at overiva_oneshot.py:298-368).
+//
+// For one short mixture the streaming kernels are latency-bound: 65 bin groups cannot fill 148 SMs, and every epoch is
+// a chain of 5 dependent kernels (demix-power -> source model -> covariance -> partial sums -> IP sweep) whose launch
+// gaps cost more than their work (29 us per epoch at config 1, of which the HBM floor is 4 us).  Here the grid stays
+// resident for all n_iter epochs (overiva.py:138-190):
+//   * every CTA owns one SLICE (bin group gi, frame range) and keeps its samples in SHARED MEMORY for the whole loop
+//     (one bulk-TMA copy at start; config 1: 15 MB over 130 SMs) -- X is never read from L2 / HBM again;
+//   * epoch = statistic of the slice (lane <-> bin, the same butterfly as k_demix_power) -> grid barrier -> the
+//     (k, t) pairs are reduced over the bin groups by whichever CTA they fall to (k_source_model's summation order)
+//     -> grid barrier -> every CTA forms gamma, phi and the W scale for its own frames -> weighted covariance of the
+//     slice from shared memory (per-warp partial sums to an L2-resident scratch) -> the LAST CTA of a bin group to
+//     arrive adds the partial sums in a fixed order and runs the group's IP sweep (thread per bin, exactly the
+//     arithmetic of k_ip_update_tpb, with C, V_s and W_hat staged in shared memory so that the dependent chain never
+//     waits for L2), then releases the group's epoch flag; the other CTAs of the group spin on it.
+//   All cross-CTA traffic (statistic partials, covariance partials, W_hat) is a few hundred KB per epoch and stays in L2.
+// Results are deterministic (fixed summation orders everywhere) and agree with the multi-kernel path to rounding
+// (the statistic and the sweep are bit-identical; the covariance sums frames in different sub-ranges).
+#pragma once
+#include "cov.cuh"
+#include "solve_tpb.cuh"
+#include "stream.cuh"
+
+namespace oiva {
+
+constexpr int RES_WARPS = 8;
+constexpr int RES_THREADS = RES_WARPS * 32;
+constexpr int RES_SYNC_HEADER = 8;  // sync[0]: grid-barrier counter; [8 + gi]: arrivals of group gi; [8 + G + gi]: its flag
+
+struct ResidentParams {
+    const void* Xg;   // grouped samples
+    cplx* Wg;         // grouped W_hat [gi][M*M][32], updated in place
+    const cplx* Cg;   // grouped input covariance [gi][NE][32]
+    double* r2part;   // (G, K, Tp) per-group statistic
+    double* rbuf;     // (B, K, Tp) r = model(sum over groups)
+    cplx* Vpart;      // (NSLOT, G, K, NE, 32) partial covariances, NSLOT = SG * FW
+    unsigned* sync;   // RES_SYNC_HEADER + 2 G words, zeroed before the launch
+    int* status;      // one word per mixture
+    GroupLayout L;
+    long long G;
+    int B, SG, n_iter, model, F_total;
+    int slice_cap;    // frames a slice can hold (= max over slices)
+    int v_bufs;       // 1 or 2 shared-memory buffers for the reduced V_s
+    double invT;
+};
+
+// how the covariance accumulators of a slice are spread over the 8 warps: P entry parts x FW frame ranges
+template <int M, int K>
+struct ResCfg {
+    static constexpr int NE = oiva_tri(M);
+    static constexpr int P = (NE * K <= 72) ? 1 : (NE * K <= 144) ? 2 : (NE * K <= 288) ? 4 : 8;
+    static constexpr int FW = RES_WARPS / P;
+    static constexpr int NEP = (NE + P - 1) / P;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// all CTAs of the (cooperative, co-resident) grid; `target` = gridDim.x * (number of barriers so far)
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (ld_acquire_u32(counter) < target) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// weighted covariance of frames [f0, f1) of the slice for the entries of one part, all K sources; same products and
+// accumulation as CovPart::accumulate / finish (cov.cuh)
+template <typename ST, int M, int K, int P, int PART>
+struct ResCovPart {
+    typedef typename StoreC<ST>::type XC;
+    static constexpr int NE = oiva_tri(M), NEP = (NE + P - 1) / P;
+    __device__ static __forceinline__ void run(const XC* __restrict__ sX, const double* __restrict__ sPhi, int pitch, int f0,
+                                               int f1, cplx* __restrict__ dst, double invT, int lane) {
+        cplx acc[NEP][K];
+#pragma unroll
+        for (int n = 0; n < NEP; ++n)
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[n][k] = cmake(0.0, 0.0);
+#pragma unroll 2
+        for (int fr = f0; fr < f1; ++fr) {
+            cplx x[M];
+            double w[K];
+#pragma unroll
+            for (int c = 0; c < M; ++c) x[c] = widen(sX[((size_t)fr * M + c) * OIVA_GROUP + lane]);
+#pragma unroll
+            for (int k = 0; k < K; ++k) w[k] = sPhi[k * pitch + fr];
+            static_for<NEP>([&](auto nc) {
+                constexpr int n = decltype(nc)::value;
+                constexpr int e = PART + n * P;
+                if constexpr (e < NE) {
+                    constexpr int i = ent_row(e), j = ent_col(e);
+                    if constexpr (i == j) {
+                        const double pr = fma(x[i].x, x[i].x, x[i].y * x[i].y);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) acc[n][k].x = fma(w[k], pr, acc[n][k].x);
+                    } else {
+                        const double pr = fma(x[i].x, x[j].x, x[i].y * x[j].y);
+                        const double pi = fma(x[i].y, x[j].x, -(x[i].x * x[j].y));
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            acc[n][k].x = fma(w[k], pr, acc[n][k].x);
+                            acc[n][k].y = fma(w[k], pi, acc[n][k].y);
+                        }
+                    }
+                }
+            });
+        }
+        static_for<NEP>([&](auto nc) {
+            constexpr int n = decltype(nc)::value;
+            constexpr int e = PART + n * P;
+            if constexpr (e < NE) {
+                constexpr bool diag = ent_row(e) == ent_col(e);
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    __stcg(dst + ((size_t)k * NE + e) * OIVA_GROUP + lane,
+                           cmake(acc[n][k].x * invT, diag ? 0.0 : acc[n][k].y * invT));
+            }
+        });
+    }
+};
+template <typename ST, int M, int K, int P, int PART = 0>
+struct ResCovDispatch {
+    typedef typename StoreC<ST>::type XC;
+    __device__ static __forceinline__ void run(int part, const XC* sX, const double* sPhi, int pitch, int f0, int f1, cplx* dst,
+                                               double invT, int lane) {
+        if (part == PART) ResCovPart<ST, M, K, P, PART>::run(sX, sPhi, pitch, f0, f1, dst, invT, lane);
+        else if constexpr (PART + 1 < P) ResCovDispatch<ST, M, K, P, PART + 1>::run(part, sX, sPhi, pitch, f0, f1, dst, invT, lane);
+    }
+};
+
+// shared-memory carve-up (host and device agree through this one function); offsets in bytes from the dynamic base
+struct ResSmem {
+    size_t x, phi, misc, c, v, w, total;
+};
+__host__ __device__ inline ResSmem res_smem_layout(int M, int K, int slice_cap, int v_bufs, int elem_bytes) {
+    ResSmem s;
+    const size_t mat = (size_t)oiva_tri(M) * OIVA_GROUP * sizeof(cplx);
+    size_t o = 128;  // [0]: mbarrier of the slice load
+    s.x = o;    o += (((size_t)slice_cap * M * OIVA_GROUP * elem_bytes) + 127) / 128 * 128;
+    s.phi = o;  o += (((size_t)K * slice_cap * sizeof(double)) + 127) / 128 * 128;
+    s.misc = o; o += 256;  // gamma[8], wscale[8], flags
+    s.c = o;    o += mat;
+    s.v = o;    o += (size_t)v_bufs * mat;
+    s.w = o;    o += (size_t)M * M * OIVA_GROUP * sizeof(cplx);
+    s.total = o;
+    return s;
+}
+
+// grid = G * SG CTAs of 256 threads (cooperative launch); CTA c owns slice s = c % SG of bin group gi = c / SG
+template <typename ST, int M, int K>
+__global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const ResidentParams p) {
+    typedef typename StoreC<ST>::type XC;
+    typedef ResCfg<M, K> RC;
+    constexpr int NE = RC::NE;
+    constexpr uint32_t MAT_ELEMS = NE * OIVA_GROUP;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const ResSmem lay = res_smem_layout(M, K, p.slice_cap, p.v_bufs, (int)sizeof(XC));
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    XC* sX = reinterpret_cast<XC*>(smem_raw + lay.x);
+    double* sPhi = reinterpret_cast<double*>(smem_raw + lay.phi);
+    double* sGamma = reinterpret_cast<double*>(smem_raw + lay.misc);
+    double* sWs = sGamma + 8;
+    int* sFlag = reinterpret_cast<int*>(sWs + 8);
+    cplx* sC = reinterpret_cast<cplx*>(smem_raw + lay.c);
+    cplx* sV = reinterpret_cast<cplx*>(smem_raw + lay.v);
+    cplx* sW = reinterpret_cast<cplx*>(smem_raw + lay.w);
+
+    const GroupLayout& L = p.L;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long gi = blockIdx.x / p.SG;
+    const int sl = (int)(blockIdx.x - gi * p.SG);
+    const long long b = gi / L.NG;
+    const int g = (int)(gi - b * L.NG);
+    const int T = L.T, Tp = L.frame_pitch();
+    const int t0 = (int)((long long)T * sl / p.SG), t1 = (int)((long long)T * (sl + 1) / p.SG);
+    const int nfr = t1 - t0;
+    const int pitch = p.slice_cap;
+    const bool bin_ok = g * OIVA_GROUP + lane < L.F;
+    unsigned* bar_counter = p.sync;
+    unsigned* arrive = p.sync + RES_SYNC_HEADER + gi;
+    unsigned* flag = p.sync + RES_SYNC_HEADER + p.G + gi;
+    cplx* Wgrp = p.Wg + (size_t)gi * M * M * OIVA_GROUP;
+    const size_t grp_cov = (size_t)K * NE * OIVA_GROUP;
+
+    // ---- one-time: the slice's samples (bulk TMA) and the group's input covariance into shared memory ---------------
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        const XC* src = reinterpret_cast<const XC*>(p.Xg) + (size_t)gi * L.group_elems() + (size_t)t0 * L.frame_elems();
+        const size_t bytes = (size_t)nfr * L.frame_elems() * sizeof(XC);
+        mbar_arrive_expect_tx(bar, (uint32_t)bytes);
+        const size_t piece = 32768;
+        for (size_t o = 0; o < bytes; o += piece)
+            tma_load_1d(reinterpret_cast<unsigned char*>(sX) + o, reinterpret_cast<const unsigned char*>(src) + o,
+                        (uint32_t)(bytes - o < piece ? bytes - o : piece), bar);
+    }
+    for (uint32_t i = tid; i < MAT_ELEMS; i += RES_THREADS) sC[i] = p.Cg[(size_t)gi * MAT_ELEMS + i];
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    unsigned n_bar = 0;
+#pragma unroll 1
+    for (int epoch = 0; epoch < p.n_iter; ++epoch) {
+        // ---- (1) statistic of the slice: r2part[gi][k][t] = sum over the 32 bins |w_k^H x|^2      overiva.py:140,152-155
+        {
+            cplx w[M][K];
+#pragma unroll
+            for (int c = 0; c < M; ++c)
+#pragma unroll
+                for (int k = 0; k < K; ++k) w[c][k] = __ldcg(Wgrp + (size_t)(c * M + k) * OIVA_GROUP + lane);
+            double* r2g = p.r2part + (size_t)gi * K * Tp;
+            for (int blk = warp; blk * POWER_FB < nfr; blk += RES_WARPS) {
+                const int fb = blk * POWER_FB;
+                double v[K][POWER_FB];
+#pragma unroll
+                for (int j = 0; j < POWER_FB; ++j) {
+                    if (fb + j < nfr) {
+                        cplx x[M], y[K];
+#pragma unroll
+                        for (int c = 0; c < M; ++c) x[c] = widen(sX[((size_t)(fb + j) * M + c) * OIVA_GROUP + lane]);
+                        demix_frame<M, K>(y, x, w);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) v[k][j] = fma(y[k].x, y[k].x, y[k].y * y[k].y);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) v[k][j] = 0.0;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) {  // the transposing butterfly of k_demix_power (stream.cuh)
+#pragma unroll
+                    for (int lvl = 0; lvl < 3; ++lvl) {
+                        const int H = POWER_FB >> (lvl + 1);
+                        const int off = 16 >> lvl;
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int n = 0; n < H; ++n) {
+                            const double lo = v[k][n], hi = v[k][n + H];
+                            const double send = up ? lo : hi;
+                            const double keep = up ? hi : lo;
+                            v[k][n] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    double s = v[k][0];
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    const int j = lane >> 2;
+                    if ((lane & 3) == 0 && fb + j < nfr) __stcg(r2g + (size_t)k * Tp + t0 + fb + j, s);
+                }
+            }
+        }
+        grid_barrier(bar_counter, (++n_bar) * gridDim.x);
+
+        // ---- (2) r[b][k][t] = model(sum over the bin groups), pairs dealt round-robin to the CTAs; the summation
+        //      order is k_source_model's (8 interleaved slices, then a fixed tree)                 overiva.py:152-155
+        {
+            const long long n_pairs = (long long)p.B * K * T;
+            const int sub = lane >> 3, cs = lane & 7;
+            for (long long q0 = ((long long)blockIdx.x * RES_WARPS + warp) * 4; q0 < n_pairs;
+                 q0 += (long long)gridDim.x * RES_WARPS * 4) {
+                const long long q = q0 + sub;
+                const bool ok = q < n_pairs;
+                const long long qq = ok ? q : 0;
+                const long long pb = qq / ((long long)K * T);
+                const int rem = (int)(qq - pb * K * T);
+                const int k = rem / T, t = rem - k * T;
+                double s = 0.0;
+                if (ok) {
+                    const double* src = p.r2part + ((size_t)pb * L.NG * K + k) * Tp + t;
+#pragma unroll 4
+                    for (int ch = cs; ch < L.NG; ch += 8) s += __ldcg(src + (size_t)ch * K * Tp);
+                }
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                if (ok && cs == 0) {
+                    double r;
+                    switch (p.model) {
+                        case OIVA_MODEL_LAPLACE: r = 2.0 * sqrt(s); break;
+                        case OIVA_MODEL_GAUSS: r = s / (double)p.F_total; break;
+                        default: r = 0.0; break;
+                    }
+                    __stcg(p.rbuf + ((size_t)pb * K + k) * Tp + t, r);
+                }
+            }
+        }
+        grid_barrier(bar_counter, (++n_bar) * gridDim.x);
+
+        // ---- (3) gamma = mean_t r, phi = 1 / max(r / gamma, 1e-15) for the slice's frames, W scale   overiva.py:158-173
+        if (warp < K) {
+            const double* rk = p.rbuf + ((size_t)b * K + warp) * Tp;
+            double lsum = 0.0;
+            for (int tt = 0; tt < Tp; tt += 32) {
+                const int t = tt + lane;
+                if (t < T) lsum += __ldcg(rk + t);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+            if (lane == 0) {
+                const double gamma = lsum / (double)T;
+                sGamma[warp] = gamma;
+                sWs[warp] = p.model == OIVA_MODEL_LAPLACE ? 1.0 / gamma : (p.model == OIVA_MODEL_GAUSS ? 1.0 / sqrt(gamma) : 1.0);
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < K * nfr; i += RES_THREADS) {
+            const int k = i / nfr, fr = i - k * nfr;
+            double r = __ldcg(p.rbuf + ((size_t)b * K + k) * Tp + t0 + fr) / sGamma[k];  // 0/0 -> NaN as in numpy
+            if (r < 1e-15) r = 1e-15;                                                    // NaN stays NaN
+            sPhi[k * pitch + fr] = 1.0 / r;
+        }
+        __syncthreads();
+
+        // ---- (4) weighted covariance of the slice, per-warp partial sums to the L2 scratch            overiva.py:179
+        {
+            const int part = warp % RC::P, fw = warp / RC::P;
+            const int f0 = (int)((long long)nfr * fw / RC::FW), f1 = (int)((long long)nfr * (fw + 1) / RC::FW);
+            const int slot = sl * RC::FW + fw;
+            cplx* dst = p.Vpart + ((size_t)slot * p.G + gi) * grp_cov;
+            ResCovDispatch<ST, M, K, RC::P>::run(part, sX, sPhi, pitch, f0, f1, dst, p.invT, lane);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            const unsigned old = atomicAdd(arrive, 1u);
+            sFlag[0] = (old == (unsigned)(p.SG * (epoch + 1) - 1)) ? 1 : 0;
+        }
+        __syncthreads();
+
+        if (sFlag[0]) {
+            // ---- (5) last CTA of the group: fixed-order sum of the partial covariances + the IP sweep   overiva.py:176-190
+            __threadfence();
+            const int n_slots = p.SG * RC::FW;
+            auto reduce_source = [&](int s, cplx* out, int first_thread, int n_threads) {
+                for (uint32_t i = tid - first_thread; i < MAT_ELEMS; i += n_threads) {
+                    const cplx* src = p.Vpart + (size_t)gi * grp_cov + (size_t)s * MAT_ELEMS + i;
+                    cplx acc = __ldcg(src);
+                    for (int sp = 1; sp < n_slots; ++sp) {
+                        const cplx v = __ldcg(src + (size_t)sp * p.G * grp_cov);
+                        acc.x += v.x;
+                        acc.y += v.y;
+                    }
+                    out[i] = acc;
+                }
+            };
+            for (uint32_t i = tid; i < (uint32_t)(M * M * OIVA_GROUP); i += RES_THREADS) sW[i] = __ldcg(Wgrp + i);
+            reduce_source(0, sV, 0, RES_THREADS);
+            __syncthreads();
+            bool singular = false;
+            const WLane Wm = {sW + lane};
+#pragma unroll 1
+            for (int s = 0; s < K; ++s) {
+                cplx* cur = sV + (size_t)(p.v_bufs == 2 ? (s & 1) : 0) * MAT_ELEMS;
+                if (warp == 0) {
+                    if (bin_ok) {
+                        if (s == 0) ip_sweep_rescale<M, K>(Wm, sWs);
+                        ip_sweep_source<M, K, false>(Wm, cur + lane, sC + lane, s, singular);
+                    }
+                } else if (p.v_bufs == 2 && s + 1 < K) {
+                    reduce_source(s + 1, sV + (size_t)((s + 1) & 1) * MAT_ELEMS, 32, RES_THREADS - 32);
+                }
+                __syncthreads();
+                if (p.v_bufs == 1 && s + 1 < K) {
+                    reduce_source(s + 1, sV, 0, RES_THREADS);
+                    __syncthreads();
+                }
+            }
+            if (warp == 0 && bin_ok) {
+                const bool bad = ip_sweep_nonfinite<M, K>(Wm);
+                if (singular || bad)
+                    atomicOr(p.status + b, (singular ? OIVA_STATUS_SINGULAR : 0) | (bad ? OIVA_STATUS_NONFINITE : 0));
+            }
+            __syncthreads();
+            for (uint32_t i = tid; i < (uint32_t)(M * M * OIVA_GROUP); i += RES_THREADS) __stcg(Wgrp + i, sW[i]);
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                st_release_u32(flag, (unsigned)(epoch + 1));
+            }
+        } else {
+            if (tid == 0) {
+                while (ld_acquire_u32(flag) < (unsigned)(epoch + 1)) {
+                }
+                __threadfence();
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace oiva

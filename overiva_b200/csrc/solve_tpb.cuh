@@ -13,10 +13,18 @@
 
 namespace oiva {
 
+// covariance loads: NC = true reads global memory through the read-only path (the batched sweep kernel); NC = false is
+// a plain load that also works on shared memory (the persistent single-mixture loop keeps C and V there)
+template <bool NC>
+__device__ __forceinline__ cplx cov_ld(const cplx* p) {
+    if constexpr (NC) return ld_nc_c(p);
+    else return *p;
+}
 // Hermitian matrix stored as its lower triangle in the grouped layout: element (i, j)
+template <bool NC = true>
 __device__ __forceinline__ cplx herm_load(const cplx* __restrict__ base, int i, int j) {
     const int hi = i >= j ? i : j, lo = i >= j ? j : i;
-    cplx v = ld_nc_c(base + (size_t)(hi * (hi + 1) / 2 + lo) * OIVA_GROUP);
+    cplx v = cov_ld<NC>(base + (size_t)(hi * (hi + 1) / 2 + lo) * OIVA_GROUP);
     if (i < j) v.y = -v.y;
     return v;
 }
@@ -98,7 +106,7 @@ __device__ __forceinline__ void lu_solve(cplx (&A)[N][N], cplx (&rhs)[N][NR], bo
 
 
 // OverIVA background refresh for one bin held by one thread: J = (W^H C E1)^-1 (W^H C E2)      overiva.py:96-98
-template <int M, int K>
+template <int M, int K, bool NC = true>
 __device__ __forceinline__ void background_tpb(WLane Wm, const cplx* sC, bool& singular) {
     if constexpr (K < M) {
         cplx T1[K][K], T2[K][M - K];
@@ -113,7 +121,7 @@ __device__ __forceinline__ void background_tpb(WLane Wm, const cplx* sC, bool& s
         for (int j = 0; j < M; ++j) {
             cplx crow[M];
 #pragma unroll
-            for (int c = 0; c < M; ++c) crow[c] = herm_load(sC, j, c);
+            for (int c = 0; c < M; ++c) crow[c] = herm_load<NC>(sC, j, c);
 #pragma unroll
             for (int i = 0; i < K; ++i) {
                 const cplx a = Wm[j * M + i];
@@ -132,7 +140,7 @@ __device__ __forceinline__ void background_tpb(WLane Wm, const cplx* sC, bool& s
 }
 
 // ---- one IP update, determined case (K == M): w_s = (W^H V_s)^-1 e_s by LU with partial pivoting ----------
-template <int M>
+template <int M, bool NC = true>
 __device__ __forceinline__ void ip_source_full(WLane Wm, const cplx* sV, int s, bool& singular) {
     cplx A[M][M], rhs[M][1];
 #pragma unroll
@@ -145,7 +153,7 @@ __device__ __forceinline__ void ip_source_full(WLane Wm, const cplx* sV, int s, 
     for (int j = 0; j < M; ++j) {
         cplx vrow[M];
 #pragma unroll
-        for (int c = 0; c < M; ++c) vrow[c] = herm_load(sV, j, c);
+        for (int c = 0; c < M; ++c) vrow[c] = herm_load<NC>(sV, j, c);
 #pragma unroll
         for (int i = 0; i < M; ++i) {
             const cplx a = Wm[j * M + i];
@@ -160,7 +168,7 @@ __device__ __forceinline__ void ip_source_full(WLane Wm, const cplx* sV, int s, 
     for (int i = 0; i < M; ++i) {
         cplx u = cmake(0.0, 0.0);
 #pragma unroll
-        for (int j = 0; j < M; ++j) cfma(u, herm_load(sV, i, j), rhs[j][0]);
+        for (int j = 0; j < M; ++j) cfma(u, herm_load<NC>(sV, i, j), rhs[j][0]);
         cfmac(d, rhs[i][0], u);
     }
     const cplx inv = crecip(csqrt_(d));
@@ -173,7 +181,7 @@ __device__ __forceinline__ void ip_source_full(WLane Wm, const cplx* sV, int s, 
 // system:  q1 = (W1^H + W2^H J^H)^-1 e_s,  q2 = J^H q1   (W1 / W2: top K / bottom M-K rows of W);  then V w = q is
 // solved by Cholesky (V is Hermitian positive definite: no pivoting, no row swaps), and the normalisation needs
 // only w^H V w = w^H q.  ~3x fewer operations than forming W_hat^H V and factorising it, same result.
-template <int M, int K>
+template <int M, int K, bool NC = true>
 __device__ __forceinline__ void ip_source_reduced(WLane Wm, const cplx* sV, int s, bool& singular) {
     constexpr int R = M - K;
     cplx q[M];
@@ -212,7 +220,7 @@ __device__ __forceinline__ void ip_source_reduced(WLane Wm, const cplx* sV, int 
     cplx Lm[oiva_tri(M)];
 #pragma unroll
     for (int e = 0; e < oiva_tri(M); ++e) {
-        Lm[e] = ld_nc_c(sV + (size_t)e * OIVA_GROUP);
+        Lm[e] = cov_ld<NC>(sV + (size_t)e * OIVA_GROUP);
     }
     double dinv[M];
 #pragma unroll
@@ -267,33 +275,34 @@ __device__ __forceinline__ void ip_source_reduced(WLane Wm, const cplx* sV, int 
 
 constexpr int TPB_WARPS = 4;
 
-// The whole sweep of one bin by its thread: W rescale, K x (IP update + J refresh).  Cl / Vl point at this lane's
-// element 0 of the grouped lower triangles (Cg[gi][e][lane], Vg[gi][s][e][lane]).  Shared by the batched sweep kernel
-// below and by the persistent single-mixture loop (resident.cuh).
+// The sweep of one bin by its thread, in steps: W rescale, then per source the IP update + J refresh, then the
+// finiteness check.  Cl / Vs point at this lane's element 0 of the grouped lower triangles (Cg[gi][e][lane],
+// Vg[gi][s][e][lane]); NC as for cov_ld.  Shared by the batched sweep kernel below and by the persistent
+// single-mixture loop (resident.cuh), which runs exactly the same arithmetic.
 template <int M, int K>
-__device__ __forceinline__ void ip_sweep_bin(WLane Wm, const cplx* Vl, const cplx* Cl, const double* wscale_b,
-                                             bool& singular, bool& bad) {
-    constexpr int NE = oiva_tri(M);
-    if (wscale_b) {  // W /= gamma (laplace) or sqrt(gamma) (gauss)              overiva.py:161-167
+__device__ __forceinline__ void ip_sweep_rescale(WLane Wm, const double* wscale_b) {
+    // W /= gamma (laplace) or sqrt(gamma) (gauss)                                   overiva.py:161-167
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const double sc = wscale_b[k];
+    for (int k = 0; k < K; ++k) {
+        const double sc = wscale_b[k];
 #pragma unroll
-            for (int j = 0; j < M; ++j) Wm[j * M + k] = cscale(Wm[j * M + k], sc);
-        }
+        for (int j = 0; j < M; ++j) Wm[j * M + k] = cscale(Wm[j * M + k], sc);
     }
-#pragma unroll 1
-    for (int s = 0; s < K; ++s) {
-        const cplx* sV = Vl + (size_t)s * NE * OIVA_GROUP;
-        if constexpr (K < M) {
-            ip_source_reduced<M, K>(Wm, sV, s, singular);
-            background_tpb<M, K>(Wm, Cl, singular);
-        } else {
-            ip_source_full<M>(Wm, sV, s, singular);
-        }
+}
+template <int M, int K, bool NC>
+__device__ __forceinline__ void ip_sweep_source(WLane Wm, const cplx* Vs, const cplx* Cl, int s, bool& singular) {
+    if constexpr (K < M) {
+        ip_source_reduced<M, K, NC>(Wm, Vs, s, singular);
+        background_tpb<M, K, NC>(Wm, Cl, singular);
+    } else {
+        ip_source_full<M, NC>(Wm, Vs, s, singular);
     }
+}
+template <int M, int K>
+__device__ __forceinline__ bool ip_sweep_nonfinite(WLane Wm) {
     // only the entries the sweep writes can go bad: the K filter columns and the K x (M-K) block J (the rest of
     // W_hat is the constant [0; -I]) -- 20 of 36 entries at M = 6, K = 2, i.e. 0.27 GB less DRAM read per sweep
+    bool bad = false;
 #pragma unroll
     for (int j = 0; j < M; ++j)
 #pragma unroll
@@ -302,6 +311,16 @@ __device__ __forceinline__ void ip_sweep_bin(WLane Wm, const cplx* Vl, const cpl
                 const cplx v = Wm[j * M + c];
                 if (!isfinite(v.x) || !isfinite(v.y)) bad = true;
             }
+    return bad;
+}
+template <int M, int K>
+__device__ __forceinline__ void ip_sweep_bin(WLane Wm, const cplx* Vl, const cplx* Cl, const double* wscale_b,
+                                             bool& singular, bool& bad) {
+    constexpr int NE = oiva_tri(M);
+    if (wscale_b) ip_sweep_rescale<M, K>(Wm, wscale_b);
+#pragma unroll 1
+    for (int s = 0; s < K; ++s) ip_sweep_source<M, K, true>(Wm, Vl + (size_t)s * NE * OIVA_GROUP, Cl, s, singular);
+    bad = ip_sweep_nonfinite<M, K>(Wm);
 }
 
 // grid: ceil(G / 4) CTAs of 4 warps; warp <-> group gi, lane <-> bin; the grouped covariances Cg[gi] and Vg[gi][s]

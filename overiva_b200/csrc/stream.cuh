@@ -15,6 +15,30 @@ namespace oiva {
 
 constexpr int POWER_FB = 8;  // frames reduced together in the power kernel
 
+// Sum over the 32 lanes (bins) of NF per-lane values (NF = 8, 4 or 2 frames): log2(NF) transposing exchanges (each halves
+// the live values), then plain xor sums.  Whatever NF, a frame's 32 values are added in the same order (partners at lane
+// distance 16, 8, 4, 2, 1), so the result does not depend on how the frames are blocked.  Returns the sum for frame
+// lane / (32 / NF), valid on the lanes with lane % (32 / NF) == 0.
+template <int NF>
+__device__ __forceinline__ double lane_sum_frames(double (&v)[NF], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int H = NF / 2; H >= 1; H >>= 1, off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int n = 0; n < H; ++n) {
+            const double lo = v[n], hi = v[n + H];
+            const double send = up ? lo : hi;
+            const double keep = up ? hi : lo;
+            v[n] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    double s = v[0];
+#pragma unroll
+    for (int o = 16 / NF; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+
 struct StreamParams {
     const void* Xg;
     const cplx* W;   // filters: element (c, k) of bin (b, f): row-major W[(b*F+f)*w_row + c*w_c + k], or, when
@@ -97,37 +121,26 @@ __global__ void __launch_bounds__(512) k_demix_power(const StreamParams p) {
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
             // 8 -> 4 -> 2 -> 1 values across lane bits 4, 3, 2; then plain sums across bits 1, 0
-#pragma unroll
-            for (int lvl = 0; lvl < 3; ++lvl) {
-                const int H = POWER_FB >> (lvl + 1);
-                const int off = 16 >> lvl;
-                const bool up = (lane & off) != 0;
-#pragma unroll
-                for (int n = 0; n < H; ++n) {
-                    const double lo = v[k][n], hi = v[k][n + H];
-                    const double send = up ? lo : hi;
-                    const double keep = up ? hi : lo;
-                    v[k][n] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                }
-            }
-            double s = v[k][0];
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            const double s = lane_sum_frames<POWER_FB>(v[k], lane);
             // lanes with (lane & 3) == 0 hold the sum over the 32 bins for frame t0 + (lane >> 2)
             if ((lane & 3) == 0 && k0 + k < p.K) p.r2part[((size_t)gi * p.K + k0 + k) * Tp + t0 + (lane >> 2)] = s;
         }
     }
 }
 
-// Same kernels for K > KC (several source-chunk warps per group): instead of every warp re-reading X from global
-// memory, the CTA stages each block of POWER_FB frames ONCE in shared memory -- a contiguous piece of the grouped
-// layout, i.e. one 1-D bulk-TMA copy into a 2-stage ring (full / empty mbarriers as in cov.cuh) -- and all warps
-// read it from there (conflict-free LDS.128).  OUTPUT = false: the statistic (k_demix_power's result, same
-// arithmetic); OUTPUT = true: the demixed samples Y (k_demix_output's result).  Measured: DESIGN.md.
-// grid (G, nsplit), block = 32 * ceil(K/KC); dynamic smem = 128 + 2 * POWER_FB * M * 32 * sizeof(XC)
-template <typename ST, int M, int KC, bool OUTPUT>
-__global__ void __launch_bounds__(512) k_demix_staged(const StreamParams p) {
+// Same kernels for several warps per group: instead of every warp re-reading X from global memory, the CTA stages
+// each block of POWER_FB frames ONCE in shared memory -- a contiguous piece of the grouped layout, i.e. one 1-D
+// bulk-TMA copy into a 2-stage ring (full / empty mbarriers as in cov.cuh) -- and all warps read it from there
+// (conflict-free LDS.128).  Warp = (source chunk of KC, sub-block of FBW frames): blockDim = 32 * ceil(K/KC) * (8/FBW),
+// so that few source chunks still give 8 warps per CTA (config 5: M = 16, K = 4 -> 2 chunks x 4 sub-blocks).
+// OUTPUT = false: the statistic (k_demix_power's result, same arithmetic); OUTPUT = true: the demixed samples Y
+// (k_demix_output's result).  Measured: DESIGN.md.
+// grid (G, nsplit); dynamic smem = 128 + 2 * POWER_FB * M * 32 * sizeof(XC)
+// (M >= 13 runs at most 12 warps -- <= 8 source chunks of 2, or <= 3 chunks x 4 sub-blocks -- and needs ~170 registers)
+template <typename ST, int M, int KC, int FBW, bool OUTPUT>
+__global__ void __launch_bounds__(M >= 13 ? 384 : 512) k_demix_staged(const StreamParams p) {
     typedef typename StoreC<ST>::type XC;
+    constexpr int NSUB = POWER_FB / FBW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr size_t stage_bytes = (size_t)POWER_FB * M * OIVA_GROUP * sizeof(XC);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
@@ -149,7 +162,8 @@ __global__ void __launch_bounds__(512) k_demix_staged(const StreamParams p) {
     const int g = (int)(gi - b * L.NG);
     const int f = g * OIVA_GROUP + lane;
     const bool bin_ok = f < L.F;
-    const int k0 = warp * KC;
+    const int k0 = (warp / NSUB) * KC;
+    const int j0 = (warp % NSUB) * FBW;  // this warp's frames inside every block
     const int Tp = L.frame_pitch();
     cplx w[M][KC];
     load_filters<M, KC>(w, p, b * L.F + (bin_ok ? f : 0), gi, lane, bin_ok, k0);
@@ -178,14 +192,14 @@ __global__ void __launch_bounds__(512) k_demix_staged(const StreamParams p) {
         if (threadIdx.x == 0 && blk + 1 < blk1) issue(blk + 1, (it + 1) & 1, (it + 1) >> 1);
         mbar_wait(&full[stage], use & 1);
         const XC* xs = reinterpret_cast<const XC*>(stage0 + (size_t)stage * stage_bytes);
-        const int t0 = blk * POWER_FB;
-        double v[KC][POWER_FB];
+        const int t0 = blk * POWER_FB + j0;
+        double v[KC][FBW];
 #pragma unroll
-        for (int j = 0; j < POWER_FB; ++j) {
+        for (int j = 0; j < FBW; ++j) {
             cplx x[M], y[KC];
             if (t0 + j < L.T) {
 #pragma unroll
-                for (int c = 0; c < M; ++c) x[c] = widen(xs[((size_t)j * M + c) * OIVA_GROUP + lane]);
+                for (int c = 0; c < M; ++c) x[c] = widen(xs[((size_t)(j0 + j) * M + c) * OIVA_GROUP + lane]);
                 demix_frame<M, KC>(y, x, w);
                 if constexpr (OUTPUT) {
                     if (bin_ok) {
@@ -208,23 +222,9 @@ __global__ void __launch_bounds__(512) k_demix_staged(const StreamParams p) {
         if constexpr (!OUTPUT) {
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
-#pragma unroll
-                for (int lvl = 0; lvl < 3; ++lvl) {
-                    const int H = POWER_FB >> (lvl + 1);
-                    const int off = 16 >> lvl;
-                    const bool up = (lane & off) != 0;
-#pragma unroll
-                    for (int n = 0; n < H; ++n) {
-                        const double lo = v[k][n], hi = v[k][n + H];
-                        const double send = up ? lo : hi;
-                        const double keep = up ? hi : lo;
-                        v[k][n] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                    }
-                }
-                double sres = v[k][0];
-                sres += __shfl_xor_sync(0xffffffffu, sres, 2);
-                sres += __shfl_xor_sync(0xffffffffu, sres, 1);
-                if ((lane & 3) == 0 && k0 + k < p.K) p.r2part[((size_t)gi * p.K + k0 + k) * Tp + t0 + (lane >> 2)] = sres;
+                const double sres = lane_sum_frames<FBW>(v[k], lane);
+                constexpr int LPF = OIVA_GROUP / FBW;  // lanes per frame after the exchanges
+                if ((lane % LPF) == 0 && k0 + k < p.K) p.r2part[((size_t)gi * p.K + k0 + k) * Tp + t0 + lane / LPF] = sres;
             }
         }
     }

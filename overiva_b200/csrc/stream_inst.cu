@@ -13,7 +13,8 @@ namespace oiva {
 #define OIVA_CAT(a, b) OIVA_CAT2(a, b)
 
 // sources per warp: the lane keeps 2*M*KC doubles of filters in registers
-constexpr int kc_cap() { return (24 / OIVA_M) < 1 ? 1 : ((24 / OIVA_M) > 4 ? 4 : (24 / OIVA_M)); }
+// (M >= 13: two sources per warp -- 64 filter values -- halve the shared-memory reads of the staged kernels)
+constexpr int kc_cap() { return OIVA_M >= 13 ? 2 : ((24 / OIVA_M) > 4 ? 4 : (24 / OIVA_M)); }
 static int pick_kc(int K) {
     int kc = K < 4 ? K : 4;
     return kc < kc_cap() ? kc : kc_cap();
@@ -38,6 +39,9 @@ static int launch(int kind, StreamParams p, long long G, cudaStream_t st) {
         return OIVA_ERR_INVALID;
     } else {
         const int warps = (p.K + KC - 1) / KC;
+        // many channels: one warp per group cannot hide the latency of its own loads (M = 16: 16 x LDG.128 per frame
+        // and a 64-deep dependent chain) -- the staged kernels with 4 sub-block warps do better even for one source chunk
+        const bool staged_single = M >= 9;
         const int units = kind == KIND_POWER ? p.L.frame_pitch() / POWER_FB : p.L.T;
         p.nsplit = frame_splits(G, units);
         dim3 grid((unsigned)G, p.nsplit, 1);
@@ -45,21 +49,26 @@ static int launch(int kind, StreamParams p, long long G, cudaStream_t st) {
             const char* v = getenv("OIVA_POWER_NO_STAGE");
             return v && *v && *v != '0';
         }();
-        if ((kind == KIND_POWER || kind == KIND_OUTPUT) && warps > 1 && !no_staged) {
-            // several source-chunk warps per group: stage X once per CTA instead of once per warp
+        if ((kind == KIND_POWER || kind == KIND_OUTPUT) && (warps > 1 || staged_single) && !no_staged) {
+            // several warps per group: stage X once per CTA instead of once per warp; few source chunks are given
+            // sub-blocks of the 8 frames so that a CTA still has up to 8 warps
             typedef typename StoreC<ST>::type XC;
             const size_t smem = 128 + 2 * (size_t)POWER_FB * M * OIVA_GROUP * sizeof(XC);
             p.nsplit = frame_splits(G, p.L.frame_pitch() / POWER_FB);
             grid = dim3((unsigned)G, p.nsplit, 1);
+            const int nsub = warps >= 8 ? 1 : (warps >= 4 ? 2 : 4);
+#define OIVA_STAGED(FBW_, OUT_)                                      \
+    {                                                                \
+        auto kern = k_demix_staged<ST, M, KC, FBW_, OUT_>;           \
+        OIVA_SET_MAX_SMEM_ONCE(kern, smem);                          \
+        kern<<<grid, 32 * warps * (POWER_FB / FBW_), smem, st>>>(p); \
+    }
             if (kind == KIND_POWER) {
-                auto kern = k_demix_staged<ST, M, KC, false>;
-                OIVA_SET_MAX_SMEM_ONCE(kern, smem);
-                kern<<<grid, 32 * warps, smem, st>>>(p);
+                if (nsub == 1) OIVA_STAGED(8, false) else if (nsub == 2) OIVA_STAGED(4, false) else OIVA_STAGED(2, false)
             } else {
-                auto kern = k_demix_staged<ST, M, KC, true>;
-                OIVA_SET_MAX_SMEM_ONCE(kern, smem);
-                kern<<<grid, 32 * warps, smem, st>>>(p);
+                if (nsub == 1) OIVA_STAGED(8, true) else if (nsub == 2) OIVA_STAGED(4, true) else OIVA_STAGED(2, true)
             }
+#undef OIVA_STAGED
         } else if (kind == KIND_POWER)
             k_demix_power<ST, M, KC><<<grid, 32 * warps, 0, st>>>(p);
         else if (kind == KIND_OUTPUT)

@@ -34,8 +34,21 @@ def _run(case):
     raise ValueError(fn)
 
 
+@pytest.fixture(params=["resident", "kernel_loop"])
+def loop_path(request, monkeypatch):
+    """Short inputs run the persistent single-launch loop (csrc/resident.cuh); OIVA_NO_RESIDENT=1 forces the
+    kernel-per-step loop (CUDA graph / eager) for the same shapes, so both paths see every case."""
+    if request.param == "kernel_loop":
+        monkeypatch.setenv("OIVA_NO_RESIDENT", "1")
+    else:
+        monkeypatch.delenv("OIVA_NO_RESIDENT", raising=False)
+    if torch.cuda.is_available():
+        ob.clear_plan_cache()
+    return request.param
+
+
 @pytest.mark.parametrize("name", golden_names())
-def test_against_reference_golden(name):
+def test_against_reference_golden(name, loop_path):
     case = load_golden(name)
     Y, W = _run(case)
     c64 = case["X"].dtype == np.complex64
@@ -59,23 +72,64 @@ def test_fp32_storage_mode_vs_fp64_reference():
 
 
 # BASELINE.json configs at their real STFT shape (F = 2049), on convolutive mixtures, against the oracle
-@pytest.mark.parametrize("cfg", ["cfg1", "cfg2", "cfg3_short"])
-def test_baseline_configs_full_bins(cfg):
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2", "cfg3"])
+def test_baseline_configs_full_bins(cfg, loop_path):
     if cfg == "cfg1":  # overiva -m 4 -s 2 -n 20, 15 s @ 16 kHz
         mix, _ = convolutive_mixture(101, 4, 2, duration=15.0)
         kw = dict(n_src=2, n_iter=20, model="laplace")
     elif cfg == "cfg2":  # auxiva determined M = K = 6
         mix, _ = convolutive_mixture(102, 6, 2, duration=15.0)
         kw = dict(n_iter=20, model="laplace")
-    else:  # overiva M=8 K=2 gauss init_eig (20 s instead of 60 s to keep the oracle quick)
-        mix, _ = convolutive_mixture(103, 8, 2, duration=20.0)
+    else:  # overiva M=8 K=2 gauss init_eig, the full 60 s mixture of BASELINE config 3 (T = 467)
+        if loop_path == "resident":
+            pytest.skip("config 3 does not fit the resident loop: one path only")
+        mix, _ = convolutive_mixture(103, 8, 2, duration=60.0)
         kw = dict(n_src=2, n_iter=20, model="gauss", init_eig=True)
     X = stft(mix)
-    assert X.shape[1] == 2049
+    assert X.shape[1] == 2049 and (cfg != "cfg3" or X.shape[0] == 467)
     Yo, Wo = orc.overiva(X, return_filters=True, **kw)
     Y, W = ob.overiva(X, return_filters=True, **kw)
     assert rel_err(Y, Yo) <= FP64_TOL
     assert rel_err(W, Wo) <= FP64_TOL
+
+
+@pytest.mark.parametrize("M,K,model,dtype,n_samples,frame", [
+    (4, 2, "laplace", np.complex128, 30000, 512), (6, 6, "laplace", np.complex128, 20000, 512),
+    (3, 1, "gauss", np.complex128, 9000, 128), (8, 4, "laplace", np.complex128, 16000, 256),
+    (5, 5, "gauss", np.complex64, 12000, 256), (2, 2, "laplace", np.complex128, 700, 64),
+    (6, 2, "laplace", np.complex64, 40000, 1024), (7, 3, "gauss", np.complex128, 8000, 64)])
+def test_resident_loop_equals_kernel_loop(M, K, model, dtype, n_samples, frame, monkeypatch):
+    """The persistent single-launch loop against the kernel-per-step loop on the same input: same statistic and sweep
+    arithmetic, covariance frames summed in different sub-ranges -> agreement to rounding (<= 1e-11 after 12 epochs),
+    for one mixture and for a small batch, both storage types; and the resident loop is deterministic."""
+    from overiva_b200 import _lib as L
+    from overiva_b200.core import DemixPlan
+
+    Xs = np.stack([small_test_mixture(40 + b, M, min(K, 2), n_samples=n_samples, frame=frame, hop=frame // 2)
+                   for b in range(2)]).astype(dtype)
+    for X in (Xs[:1], Xs):
+        Xd = torch.from_numpy(X).cuda()
+        B, T, F, _ = X.shape
+        out = {}
+        for path in ("resident", "kernel_loop", "resident_again"):
+            if path == "kernel_loop":
+                monkeypatch.setenv("OIVA_NO_RESIDENT", "1")
+            else:
+                monkeypatch.delenv("OIVA_NO_RESIDENT", raising=False)
+            plan = DemixPlan(B, T, F, M, K, L.MODEL_LAPLACE if model == "laplace" else L.MODEL_GAUSS, Xd.dtype, Xd.device)
+            plan.load(Xd)
+            plan.init(L.INIT_EYE)
+            l0 = plan.launches
+            plan.iterate(12)
+            n_launch = plan.launches - l0
+            assert (n_launch == 1) == (path != "kernel_loop"), (path, n_launch)  # the resident loop really ran
+            out[path] = (plan.output(True).cpu().numpy(), plan.filters().cpu().numpy())
+            plan.raise_on_failure()
+        tol = 1e-11 if dtype == np.complex128 else 1e-6
+        assert rel_err(out["resident"][0], out["kernel_loop"][0]) <= tol
+        assert rel_err(out["resident"][1], out["kernel_loop"][1]) <= tol
+        assert np.array_equal(out["resident"][0], out["resident_again"][0])
+        assert np.array_equal(out["resident"][1], out["resident_again"][1])
 
 
 def test_batch_equals_single_and_is_deterministic():
