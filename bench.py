@@ -60,6 +60,7 @@ UNIT = "mixture-s/s"
 
 # BASELINE.json config 5: one 10-minute 48 kHz mixture, M=16, K=4
 C5_T, C5_F, C5_M, C5_K, C5_SECS = 14061, 2049, 16, 4, 600.0
+C5_Q = 16  # interfering sources of the synthetic cfg5 mixture: 4 + 16 sources >= 16 channels (well-conditioned bins)
 
 
 def workload_config(batch, n_gpus):
@@ -718,7 +719,7 @@ def cfg5_leg(args, R, torch, dist, ob, L, hbm_peak, fp64):
         free, _ = torch.cuda.mem_get_info(dev)
         if need > free:
             raise MemoryError("cfg5 shard needs %.1f GB of device memory, %.1f GB free" % (need / 1e9, free / 1e9))
-        state["X"] = stft_domain_bins_torch(Tn, C5_F, f0, f1, C5_M, C5_K, seed=4242, device=dev)
+        state["X"] = stft_domain_bins_torch(Tn, C5_F, f0, f1, C5_M, C5_K, seed=4242, device=dev, n_interferers=C5_Q)
 
     _, err = guarded(prepare)
     ok, rk, msg = R.agree(err)
@@ -759,7 +760,8 @@ def cfg5_leg(args, R, torch, dist, ob, L, hbm_peak, fp64):
     def check():
         if rank != 0 or args.no_cfg5_check:
             return
-        Xfull = stft_domain_bins_torch(Tn, C5_F, 0, C5_F, C5_M, C5_K, seed=4242, device=dev) if world > 1 else Xl
+        Xfull = (stft_domain_bins_torch(Tn, C5_F, 0, C5_F, C5_M, C5_K, seed=4242, device=dev, n_interferers=C5_Q)
+                 if world > 1 else Xl)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ob.overiva(Xfull, **kw)

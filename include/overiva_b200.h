@@ -303,6 +303,10 @@ size_t oiva_plan_r2_elems(const oiva_plan_t* plan);
 int oiva_plan_output(oiva_plan_t* plan, int proj_back, void* Y, void* stream);
 /* copy the filters W (B,F,M,K) c128 (contiguous) out of What       overiva.py:201-202 */
 int oiva_plan_filters(oiva_plan_t* plan, void* W, void* stream);
+/* oiva_plan_load + _init + _iterate + _output (+ _filters if W != NULL) in one call (one foreign-function round trip
+ * instead of five: for one short mixture the host language's call overhead is comparable to the GPU work) */
+int oiva_plan_run(oiva_plan_t* plan, const void* X, int init_mode, const void* W0, int n_iter, int proj_back, void* Y,
+                  void* W, void* stream);
 /* device pointers into the workspace (for tests and wrappers) */
 void* oiva_plan_what(oiva_plan_t* plan);    /* (R,M,M) c128 row-major; refreshed from the grouped state by
                                                oiva_plan_init / oiva_plan_output / oiva_plan_filters */

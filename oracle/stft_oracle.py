@@ -8,10 +8,14 @@ tree and not installed here):
 * ``X = pra.transform.analysis(mix.T, framesize, framesize//2, win=win_a)``  overiva_oneshot.py:293-295
 * ``y = pra.transform.synthesis(Y, framesize, framesize//2, win=win_s)``     overiva_oneshot.py:371-379
 
-PARITY UNPINNED for this file: the package's sources are not available offline, so the functions below restate
-its published behaviour (DFT analysis ``X[t] = rfft(win_a * frame_t)`` without scaling, synthesis = overlap-add of
-``win_s * irfft(Y[t])``, synthesis window = analysis window divided by the sum of its squared hop-shifted copies)
-and they DEFINE what the CUDA kernels in ``overiva_b200/csrc/stft.cu`` are checked against.  Framing follows
+The package's sources are not available offline, so the functions below restate its published behaviour (DFT
+analysis ``X[t] = rfft(win_a * frame_t)`` without scaling, synthesis = overlap-add of ``win_s * irfft(Y[t])``,
+synthesis window = analysis window divided by the sum of its squared hop-shifted copies) and they define what the
+CUDA kernels in ``overiva_b200/csrc/stft.cu`` are checked against.  PINNING: against pyroomacoustics itself the
+parity is unpinned (absent); the transform pair is pinned against an independent implementation instead --
+``scipy.signal.ShortTimeFFT`` (scipy 1.18) with the same window / hop / no scaling gives the same spectra, the same
+dual (synthesis) window and the same reconstruction to 1e-13 (``tests/test_stft.py::
+test_oracle_against_scipy_short_time_fft``).  Framing follows
 SURVEY.md section 8(d): no padding, ``T = (N - L)//hop + 1``; ``pad_front`` zeros may be prepended (the
 ``L - hop`` state buffer of a streaming STFT, which is what makes the reference compare ``y[framesize//2:]``
 with the clean signals, overiva_oneshot.py:393-401).

@@ -92,6 +92,7 @@ SIGNATURES = {
     "oiva_plan_r2_elems": (_sz, [_p]),
     "oiva_plan_output": (_i, [_p, _i, _p, _p]),
     "oiva_plan_filters": (_i, [_p, _p, _p]),
+    "oiva_plan_run": (_i, [_p, _p, _i, _p, _i, _i, _p, _p, _p]),
     "oiva_plan_what": (_p, [_p]),
     "oiva_plan_cov": (_p, [_p]),
     "oiva_plan_samples": (_p, [_p]),

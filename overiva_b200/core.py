@@ -227,6 +227,20 @@ class DemixPlan:
         L.check(self.lib.oiva_plan_filters(self.h, _ptr(W), _stream_ptr(self.device)), "oiva_plan_filters")
         return W
 
+    def run(self, X, init_mode, W0, n_iter, proj_back, return_filters=False, out=None):
+        """load + init + iterate + output [+ filters] in ONE library call.  -> (Y, W or None)"""
+        assert X.is_cuda and X.is_contiguous() and X.dtype == self.cdtype
+        assert tuple(X.shape) == (self.B, self.T, self.F, self.M), (tuple(X.shape), (self.B, self.T, self.F, self.M))
+        if W0 is not None:
+            assert W0.is_cuda and W0.is_contiguous() and W0.dtype == torch.complex128
+            assert tuple(W0.shape) == (self.B, self.F, self.M, self.K)
+        Y = out if out is not None else torch.empty((self.B, self.T, self.F, self.K), dtype=self.cdtype, device=self.device)
+        W = (torch.empty((self.B, self.F, self.M, self.K), dtype=torch.complex128, device=self.device)
+             if return_filters else None)
+        L.check(self.lib.oiva_plan_run(self.h, _ptr(X), int(init_mode), _ptr(W0), int(n_iter), int(bool(proj_back)),
+                                       _ptr(Y), _ptr(W), _stream_ptr(self.device)), "oiva_plan_run")
+        return Y, W
+
     def status(self):
         """OR of the mixtures' status words (synchronises the stream); negative = library error."""
         return self.lib.oiva_plan_status(self.h, _stream_ptr(self.device))
@@ -414,6 +428,15 @@ def _run_overiva(Xd, n_src, n_iter, proj_back, W0, model, init_eig, return_filte
 def _run_overiva_on(plan, Xd, n_src, n_iter, proj_back, W0, init_eig, return_filters, callback, cb_wrap,
                     status_out=None):
     B, T, F, M = Xd.shape
+    if callback is None:  # the whole call in one library round trip
+        W0d = _prepare_W0(W0, B, F, M, n_src, Xd.device) if W0 is not None else None
+        mode = L.INIT_W0 if W0 is not None else (L.INIT_EIG if init_eig else L.INIT_EYE)
+        Y, W = plan.run(Xd, mode, W0d, n_iter, proj_back, return_filters)
+        if status_out is not None:
+            status_out.append(plan.status_vector())
+        else:
+            plan.raise_on_failure()
+        return Y, W, plan
     plan.load(Xd)
     if W0 is not None:
         plan.init(L.INIT_W0, _prepare_W0(W0, B, F, M, n_src, Xd.device))

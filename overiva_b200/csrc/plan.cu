@@ -452,6 +452,8 @@ extern "C" int oiva_plan_update(oiva_plan_t* p, void* stream) {
     return plan_update_from(p, (const double*)(p->ws + p->off_r2), 1, stream);
 }
 
+extern "C" int oiva_plan_filters(oiva_plan_t* p, void* W, void* stream);
+
 extern "C" int oiva_plan_output(oiva_plan_t* p, int proj_back, void* Y, void* stream) {
     PLAN_INITED(p, "oiva_plan_output");
     OIVA_REQUIRE(Y, "oiva_plan_output: null Y");
@@ -466,6 +468,21 @@ extern "C" int oiva_plan_output(oiva_plan_t* p, int proj_back, void* Y, void* st
     if (rc) return rc;
     p->launches += 2;
     return OIVA_OK;
+}
+
+// load + init + iterate + output (+ filters) in one call: for one short mixture the per-call overhead of the host
+// language (five ctypes round trips from Python) is of the order of the GPU work itself
+extern "C" int oiva_plan_run(oiva_plan_t* p, const void* X, int init_mode, const void* W0, int n_iter, int proj_back,
+                             void* Y, void* W, void* stream) {
+    int rc = oiva_plan_load(p, X, stream);
+    if (rc) return rc;
+    rc = oiva_plan_init(p, init_mode, W0, stream);
+    if (rc) return rc;
+    rc = oiva_plan_iterate(p, n_iter, stream);
+    if (rc) return rc;
+    rc = oiva_plan_output(p, proj_back, Y, stream);
+    if (rc) return rc;
+    return W ? oiva_plan_filters(p, W, stream) : OIVA_OK;
 }
 
 extern "C" int oiva_plan_filters(oiva_plan_t* p, void* W, void* stream) {

@@ -7,18 +7,20 @@
 // resident for all n_iter epochs (overiva.py:138-190):
 //   * every CTA owns one SLICE (bin group gi, frame range) and keeps its samples in SHARED MEMORY for the whole loop
 //     (one bulk-TMA copy at start; config 1: 15 MB over 130 SMs) -- X is never read from L2 / HBM again;
-//   * epoch = statistic of the slice (lane <-> bin, the same butterfly as k_demix_power) -> grid barrier -> the
-//     (k, t) pairs are reduced over the bin groups by whichever CTA they fall to (k_source_model's summation order)
-//     -> grid barrier -> every CTA forms gamma, phi and the W scale for its own frames -> weighted covariance of the
-//     slice from shared memory (per-warp partial sums to an L2-resident scratch) -> the LAST CTA of a bin group to
-//     arrive adds the partial sums in a fixed order and runs the group's IP sweep (thread per bin, exactly the
-//     arithmetic of k_ip_update_tpb, with C, V_s and W_hat staged in shared memory so that the dependent chain never
-//     waits for L2), then releases the group's epoch flag; the other CTAs of the group spin on it.
+//   * epoch = statistic of the slice (lane <-> bin, the same butterfly as k_demix_power) -> grid barrier -> the sum
+//     over the bin groups in k_source_model's order (few frames: by every CTA for its own mixture; many frames: pairs
+//     dealt to the CTAs, r exchanged through L2 and a second barrier) -> gamma, phi and the W scale for the slice's
+//     frames -> weighted covariance of the slice from shared memory (per-warp partial sums to an L2-resident scratch)
+//     -> the LAST CTA of a bin group to arrive adds the partial sums in a fixed order and runs the group's IP sweep
+//     with C, V_s and W_hat staged in shared memory so that the dependent chain never waits for L2 (K < M: thread per
+//     bin, exactly the arithmetic of k_ip_update_tpb; K = M: a lane group per bin over all 8 warps, the arithmetic of
+//     k_ip_update), then releases the group's epoch flag; the other CTAs of the group spin on it.
 //   All cross-CTA traffic (statistic partials, covariance partials, W_hat) is a few hundred KB per epoch and stays in L2.
 // Results are deterministic (fixed summation orders everywhere) and agree with the multi-kernel path to rounding
-// (the statistic and the sweep are bit-identical; the covariance sums frames in different sub-ranges).
+// (same statistic arithmetic; the covariance sums frames in different sub-ranges).
 #pragma once
 #include "cov.cuh"
+#include "solve.cuh"
 #include "solve_tpb.cuh"
 #include "stream.cuh"
 
@@ -42,6 +44,8 @@ struct ResidentParams {
     int B, SG, n_iter, model, F_total;
     int slice_cap;    // frames a slice can hold (= max over slices)
     int v_bufs;       // 1 or 2 shared-memory buffers for the reduced V_s
+    int stat_local;   // 1: every CTA sums the statistic partials of its mixture itself (one grid barrier per epoch instead of
+                      //    two); 0: the (k, t) pairs are dealt to the CTAs and exchanged through rbuf (many frames)
     double invT;
 };
 
@@ -142,9 +146,10 @@ struct ResCovDispatch {
 
 // shared-memory carve-up (host and device agree through this one function); offsets in bytes from the dynamic base
 struct ResSmem {
-    size_t x, phi, misc, c, v, w, total;
+    size_t x, phi, misc, c, v, w, r, total;
 };
-__host__ __device__ inline ResSmem res_smem_layout(int M, int K, int slice_cap, int v_bufs, int elem_bytes) {
+// r_doubles: K * Tp when the statistic is reduced locally (stat_local), else 0
+__host__ __device__ inline ResSmem res_smem_layout(int M, int K, int slice_cap, int v_bufs, int elem_bytes, int r_doubles) {
     ResSmem s;
     const size_t mat = (size_t)oiva_tri(M) * OIVA_GROUP * sizeof(cplx);
     size_t o = 128;  // [0]: mbarrier of the slice load
@@ -154,6 +159,7 @@ __host__ __device__ inline ResSmem res_smem_layout(int M, int K, int slice_cap, 
     s.c = o;    o += mat;
     s.v = o;    o += (size_t)v_bufs * mat;
     s.w = o;    o += (size_t)M * M * OIVA_GROUP * sizeof(cplx);
+    s.r = o;    o += (((size_t)r_doubles * sizeof(double)) + 127) / 128 * 128;
     s.total = o;
     return s;
 }
@@ -166,7 +172,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
     constexpr int NE = RC::NE;
     constexpr uint32_t MAT_ELEMS = NE * OIVA_GROUP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const ResSmem lay = res_smem_layout(M, K, p.slice_cap, p.v_bufs, (int)sizeof(XC));
+    const ResSmem lay = res_smem_layout(M, K, p.slice_cap, p.v_bufs, (int)sizeof(XC), p.stat_local ? K * p.L.frame_pitch() : 0);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     XC* sX = reinterpret_cast<XC*>(smem_raw + lay.x);
     double* sPhi = reinterpret_cast<double*>(smem_raw + lay.phi);
@@ -176,6 +182,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
     cplx* sC = reinterpret_cast<cplx*>(smem_raw + lay.c);
     cplx* sV = reinterpret_cast<cplx*>(smem_raw + lay.v);
     cplx* sW = reinterpret_cast<cplx*>(smem_raw + lay.w);
+    double* sR = reinterpret_cast<double*>(smem_raw + lay.r);
 
     const GroupLayout& L = p.L;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -263,9 +270,53 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
         }
         grid_barrier(bar_counter, (++n_bar) * gridDim.x);
 
-        // ---- (2) r[b][k][t] = model(sum over the bin groups), pairs dealt round-robin to the CTAs; the summation
-        //      order is k_source_model's (8 interleaved slices, then a fixed tree)                 overiva.py:152-155
-        {
+        // ---- (2) r[b][k][t] = model(sum over the bin groups); the summation order is k_source_model's (8 interleaved
+        //      slices, then a fixed tree)                                                           overiva.py:152-155
+        auto model_fn = [&](double s) {
+            switch (p.model) {
+                case OIVA_MODEL_LAPLACE: return 2.0 * sqrt(s);
+                case OIVA_MODEL_GAUSS: return s / (double)p.F_total;
+                default: return 0.0;
+            }
+        };
+        if (p.stat_local) {
+            // few frames: every CTA adds up the partials of its own mixture (L2 reads, 4 items x NG/8 loads in flight
+            // per thread) -- no second grid barrier, no exchange of r
+            const int n_items = K * T * 8;  // item = (k * T + t) * 8 + slice
+            const double* base = p.r2part + (size_t)b * L.NG * K * Tp;
+            for (int i0 = 0; i0 < n_items; i0 += RES_THREADS * 4) {
+                double acc[4];
+                const double* src[4];
+                bool ok[4];
+                int kk[4], tt[4];
+                const int cs = tid & 7;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int item = i0 + u * RES_THREADS + tid;
+                    ok[u] = item < n_items;
+                    const int pair = (ok[u] ? item : 0) >> 3;
+                    kk[u] = pair / T;
+                    tt[u] = pair - kk[u] * T;
+                    src[u] = base + (size_t)kk[u] * Tp + tt[u];
+                    acc[u] = 0.0;
+                }
+                for (int ch = cs; ch < L.NG; ch += 8) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (ok[u]) acc[u] += __ldcg(src[u] + (size_t)ch * K * Tp);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    double v = acc[u];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    if (ok[u] && cs == 0) sR[kk[u] * Tp + tt[u]] = model_fn(v);
+                }
+            }
+            __syncthreads();
+        } else {
+            // many frames: the (k, t) pairs are dealt round-robin to the CTAs, r goes through rbuf and a second barrier
             const long long n_pairs = (long long)p.B * K * T;
             const int sub = lane >> 3, cs = lane & 7;
             for (long long q0 = ((long long)blockIdx.x * RES_WARPS + warp) * 4; q0 < n_pairs;
@@ -276,35 +327,28 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                 const long long pb = qq / ((long long)K * T);
                 const int rem = (int)(qq - pb * K * T);
                 const int k = rem / T, t = rem - k * T;
-                double s = 0.0;
+                double sum = 0.0;
                 if (ok) {
                     const double* src = p.r2part + ((size_t)pb * L.NG * K + k) * Tp + t;
 #pragma unroll 4
-                    for (int ch = cs; ch < L.NG; ch += 8) s += __ldcg(src + (size_t)ch * K * Tp);
+                    for (int ch = cs; ch < L.NG; ch += 8) sum += __ldcg(src + (size_t)ch * K * Tp);
                 }
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                s += __shfl_xor_sync(0xffffffffu, s, 4);
-                if (ok && cs == 0) {
-                    double r;
-                    switch (p.model) {
-                        case OIVA_MODEL_LAPLACE: r = 2.0 * sqrt(s); break;
-                        case OIVA_MODEL_GAUSS: r = s / (double)p.F_total; break;
-                        default: r = 0.0; break;
-                    }
-                    __stcg(p.rbuf + ((size_t)pb * K + k) * Tp + t, r);
-                }
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+                if (ok && cs == 0) __stcg(p.rbuf + ((size_t)pb * K + k) * Tp + t, model_fn(sum));
             }
+            grid_barrier(bar_counter, (++n_bar) * gridDim.x);
         }
-        grid_barrier(bar_counter, (++n_bar) * gridDim.x);
 
         // ---- (3) gamma = mean_t r, phi = 1 / max(r / gamma, 1e-15) for the slice's frames, W scale   overiva.py:158-173
+        const double* rglob = p.rbuf + (size_t)b * K * Tp;
+        auto r_at = [&](int k, int t) { return p.stat_local ? sR[k * Tp + t] : __ldcg(rglob + (size_t)k * Tp + t); };
         if (warp < K) {
-            const double* rk = p.rbuf + ((size_t)b * K + warp) * Tp;
             double lsum = 0.0;
             for (int tt = 0; tt < Tp; tt += 32) {
                 const int t = tt + lane;
-                if (t < T) lsum += __ldcg(rk + t);
+                if (t < T) lsum += r_at(warp, t);
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
@@ -317,8 +361,8 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
         __syncthreads();
         for (int i = tid; i < K * nfr; i += RES_THREADS) {
             const int k = i / nfr, fr = i - k * nfr;
-            double r = __ldcg(p.rbuf + ((size_t)b * K + k) * Tp + t0 + fr) / sGamma[k];  // 0/0 -> NaN as in numpy
-            if (r < 1e-15) r = 1e-15;                                                    // NaN stays NaN
+            double r = r_at(k, t0 + fr) / sGamma[k];  // 0/0 -> NaN as in numpy
+            if (r < 1e-15) r = 1e-15;                // NaN stays NaN
             sPhi[k * pitch + fr] = 1.0 / r;
         }
         __syncthreads();
@@ -358,29 +402,88 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
             for (uint32_t i = tid; i < (uint32_t)(M * M * OIVA_GROUP); i += RES_THREADS) sW[i] = __ldcg(Wgrp + i);
             reduce_source(0, sV, 0, RES_THREADS);
             __syncthreads();
-            bool singular = false;
-            const WLane Wm = {sW + lane};
-#pragma unroll 1
-            for (int s = 0; s < K; ++s) {
-                cplx* cur = sV + (size_t)(p.v_bufs == 2 ? (s & 1) : 0) * MAT_ELEMS;
-                if (warp == 0) {
-                    if (bin_ok) {
-                        if (s == 0) ip_sweep_rescale<M, K>(Wm, sWs);
-                        ip_sweep_source<M, K, false>(Wm, cur + lane, sC + lane, s, singular);
-                    }
-                } else if (p.v_bufs == 2 && s + 1 < K) {
-                    reduce_source(s + 1, sV + (size_t)((s + 1) & 1) * MAT_ELEMS, 32, RES_THREADS - 32);
-                }
+            if constexpr (K == M && M >= 3) {
+                // determined case: the in-thread LU of the thread-per-bin sweep is one long dependent chain per source
+                // (config 2: ~6 us x 6 sources with 31 warps of the GPU idle).  Here all 8 warps take part: a group
+                // of G = next_pow2(M) lanes owns a bin, one row of [W_hat^H V_s | e_s] per lane, Gauss-Jordan with
+                // shuffle pivoting (solve.cuh, the arithmetic of k_ip_update) -- ~M times shorter chains.
+                constexpr int GL = Grp<M>::G, BPW = Grp<M>::BINS;
+                int singular = 0;
+                for (uint32_t i = tid; i < (uint32_t)(M * M * OIVA_GROUP); i += RES_THREADS)  // W *= wscale   overiva.py:161-167
+                    sW[i] = cscale(sW[i], sWs[(i / OIVA_GROUP) % M]);
                 __syncthreads();
-                if (p.v_bufs == 1 && s + 1 < K) {
-                    reduce_source(s + 1, sV, 0, RES_THREADS);
+#pragma unroll 1
+                for (int s = 0; s < K; ++s) {
+                    for (int bin0 = warp * BPW; bin0 < OIVA_GROUP; bin0 += RES_WARPS * BPW) {
+                        const int l = bin0 + lane / GL, gl = lane % GL;
+                        const bool rv = gl < M;
+                        const bool lv = g * OIVA_GROUP + l < L.F;  // padded bins keep their zero W_hat (nothing is written)
+                        auto Wat = [&](int r, int c) -> cplx& { return sW[(size_t)(r * M + c) * OIVA_GROUP + l]; };
+                        auto Vat = [&](int r, int c) { return herm_load<false>(sV + l, r, c); };
+                        cplx A[M + 1];
+#pragma unroll
+                        for (int c = 0; c <= M; ++c) A[c] = cmake(0.0, 0.0);
+                        if (rv) {
+                            for (int j = 0; j < M; ++j) {
+                                const cplx a = Wat(j, gl);
+#pragma unroll
+                                for (int c = 0; c < M; ++c) cfmac(A[c], a, Vat(j, c));
+                            }
+                            if (gl == s) A[M] = cmake(1.0, 0.0);
+                        }
+                        const int col = gauss_jordan<M, GL>(A, M, gl, lane, rv, singular);
+                        __syncwarp();
+                        if (col >= 0 && lv) Wat(col, s) = A[M];
+                        __syncwarp();
+                        cplx wi = cmake(0.0, 0.0), u = cmake(0.0, 0.0);  // w_s /= sqrt(w_s^H V_s w_s)    overiva.py:185-186
+                        if (rv) {
+                            wi = Wat(gl, s);
+#pragma unroll
+                            for (int j = 0; j < M; ++j) cfma(u, Vat(gl, j), Wat(j, s));
+                        }
+                        const cplx d = group_sum<GL>(cmulc(wi, u));
+                        const cplx inv = crecip(csqrt_(d));
+                        __syncwarp();
+                        if (rv && lv) Wat(gl, s) = cmul(wi, inv);
+                        __syncwarp();
+                        if (singular && lv) atomicOr(p.status + b, OIVA_STATUS_SINGULAR);
+                        singular = 0;
+                    }
                     __syncthreads();
+                    if (s + 1 < K) {
+                        reduce_source(s + 1, sV, 0, RES_THREADS);
+                        __syncthreads();
+                    }
                 }
-            }
-            if (warp == 0 && bin_ok) {
-                const bool bad = ip_sweep_nonfinite<M, K>(Wm);
-                if (singular || bad)
-                    atomicOr(p.status + b, (singular ? OIVA_STATUS_SINGULAR : 0) | (bad ? OIVA_STATUS_NONFINITE : 0));
+                bool bad = false;
+                for (uint32_t i = tid; i < (uint32_t)(M * M * OIVA_GROUP); i += RES_THREADS)
+                    if (g * OIVA_GROUP + (int)(i % OIVA_GROUP) < L.F && (!isfinite(sW[i].x) || !isfinite(sW[i].y))) bad = true;
+                if (bad) atomicOr(p.status + b, OIVA_STATUS_NONFINITE);
+            } else {
+                bool singular = false;
+                const WLane Wm = {sW + lane};
+#pragma unroll 1
+                for (int s = 0; s < K; ++s) {
+                    cplx* cur = sV + (size_t)(p.v_bufs == 2 ? (s & 1) : 0) * MAT_ELEMS;
+                    if (warp == 0) {
+                        if (bin_ok) {
+                            if (s == 0) ip_sweep_rescale<M, K>(Wm, sWs);
+                            ip_sweep_source<M, K, false>(Wm, cur + lane, sC + lane, s, singular);
+                        }
+                    } else if (p.v_bufs == 2 && s + 1 < K) {
+                        reduce_source(s + 1, sV + (size_t)((s + 1) & 1) * MAT_ELEMS, 32, RES_THREADS - 32);
+                    }
+                    __syncthreads();
+                    if (p.v_bufs == 1 && s + 1 < K) {
+                        reduce_source(s + 1, sV, 0, RES_THREADS);
+                        __syncthreads();
+                    }
+                }
+                if (warp == 0 && bin_ok) {
+                    const bool bad = ip_sweep_nonfinite<M, K>(Wm);
+                    if (singular || bad)
+                        atomicOr(p.status + b, (singular ? OIVA_STATUS_SINGULAR : 0) | (bad ? OIVA_STATUS_NONFINITE : 0));
+                }
             }
             __syncthreads();
             for (uint32_t i = tid; i < (uint32_t)(M * M * OIVA_GROUP); i += RES_THREADS) __stcg(Wgrp + i, sW[i]);

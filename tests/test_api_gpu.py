@@ -198,6 +198,17 @@ def test_sdr_sir_within_0p1_db_of_oracle():
     assert out["oracle"][1].mean() > 3.0  # the algorithm does separate on this synthetic mixture
 
 
+def test_config5_full_length_reduced_bins():
+    """BASELINE config 5 at its full LENGTH (T = 14061 frames, M = 16, K = 4) on 64 bins, 3 iterations, against the
+    oracle: the frame-split x tiled-covariance x many-group-statistic combination at the real frame count."""
+    from overiva_b200.synth import stft_domain_mixture
+
+    X = stft_domain_mixture(77, 14061, 64, 16, 4, n_interferers=16)  # >= M sources: well conditioned (sens. 6e-14)
+    Yo, Wo = orc.overiva(X, n_src=4, n_iter=3, return_filters=True)
+    Y, W = ob.overiva(X, n_src=4, n_iter=3, return_filters=True)
+    assert rel_err(Y, Yo) <= FP64_TOL and rel_err(W, Wo) <= FP64_TOL
+
+
 def test_host_batch_pipeline_equals_device_batch():
     """Host batches larger than `chunk` are streamed through the GPU in overlapped chunks: same results as the
     one-piece device path, including a ragged last chunk, W0 slicing and the accumulated failure status."""
@@ -216,8 +227,15 @@ def test_host_batch_pipeline_equals_device_batch():
     assert Yp is out and rel_err(out.numpy(), Yh) <= 1e-12
     bad = Xs.copy()
     bad[4, :, :, 3] = bad[4, :, :, 0]  # one rank-deficient mixture in the middle chunk
-    with pytest.raises(np.linalg.LinAlgError):
+    with pytest.raises(np.linalg.LinAlgError, match="mixture 4 of 7"):
         ob.overiva_batch(bad, n_src=2, n_iter=3, chunk=3)
+    # per-mixture status: only the offending mixture is flagged, the others are separated as usual
+    # (the reference's sweep records NaN for the failing task only, overiva_sim.py:334-350)
+    for kw in (dict(chunk=3), dict(chunk=64)):  # host pipeline / one-piece path
+        Yb, status = ob.overiva_batch(bad, n_src=2, n_iter=6, W0=W0, return_status=True, **kw)
+        assert status.shape == (B,) and status[4] & 1 and not np.any(np.delete(status, 4))
+        good = np.delete(np.arange(B), 4)
+        assert rel_err(Yb[good], Yh[good]) <= 1e-12
 
 
 def test_large_batch():

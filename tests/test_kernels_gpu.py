@@ -177,10 +177,11 @@ def test_demix_power(M, K, n_samples, dtype):
         assert rel_err(r2[b].T, want) < 1e-12
 
 
+@pytest.mark.parametrize("T", [173, 2049, 5000])  # > 2048 frames: the two-kernel path for long mixtures
 @pytest.mark.parametrize("model", ["laplace", "gauss"])
-def test_source_model(model):
+def test_source_model(model, T):
     rng = np.random.default_rng(8)
-    B, K, T, M, F = 3, 2, 173, 4, 65
+    B, K, M, F = 3, 2, 4, 65
     r2 = rng.gamma(1.0, 1.0, size=(B, K, T))
     r2[0, 0, 5] = 0.0  # exercises the 1e-15 clamp
     code = {"laplace": L.MODEL_LAPLACE, "gauss": L.MODEL_GAUSS}[model]

@@ -40,6 +40,33 @@ def test_oracle_perfect_reconstruction(L_, hop):
     assert rel_err(y[lo:hi], x[lo:hi]) < 1e-13
 
 
+@pytest.mark.parametrize("L_,hop", [(64, 32), (64, 16), (32, 8), (4096, 2048)])
+def test_oracle_against_scipy_short_time_fft(L_, hop):
+    """An INDEPENDENT implementation pins the restated transform pair (pyroomacoustics itself is absent):
+    scipy.signal.ShortTimeFFT with the same window, hop, no scaling and no phase shift computes
+    rfft(win * x[p*hop - L/2 : p*hop + L/2]) for slice p, i.e. our frame t = p - (L/2)/hop; its canonical dual window is
+    win / sum_p win_p^2 (our ``compute_synthesis_window``) and its inverse is the overlap-add of dual * irfft (our
+    ``synthesis``)."""
+    from scipy.signal import ShortTimeFFT
+
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(L_ * 7 + 11)
+    wa = so.hann(L_)
+    sft = ShortTimeFFT(wa, hop, fs=1.0, fft_mode="onesided", scale_to=None, phase_shift=None)
+    Z = sft.stft(x)  # (F, slices), slices p_min .. p_max-1
+    X = so.analysis(x, L_, hop, win=wa)
+    p0 = (L_ // 2) // hop - sft.p_min
+    assert rel_err(X, Z[:, p0 : p0 + X.shape[0]].T) < 1e-13
+    ws = so.compute_synthesis_window(wa, hop)
+    assert rel_err(ws, sft.dual_win) < 1e-13
+    # scipy's inverse of ITS transform and our overlap-add of OUR transform agree where every shift is present
+    y_scipy = sft.istft(Z, k1=len(x))
+    y_ours = so.synthesis(X, L_, hop, win=ws)
+    lo, hi = L_ - hop, (X.shape[0] - 1) * hop
+    assert rel_err(y_ours[lo:hi], y_scipy[lo:hi]) < 1e-12
+    assert rel_err(y_scipy[lo:hi], x[lo:hi]) < 1e-12
+
+
 def test_oracle_matches_the_generator_stft():
     # overiva_b200.synth.stft (what the golden fixtures were made with) is the same transform
     x = np.random.default_rng(1).standard_normal((700, 2))
