@@ -300,10 +300,23 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                     src[u] = base + (size_t)kk[u] * Tp + tt[u];
                     acc[u] = 0.0;
                 }
-                for (int ch = cs; ch < L.NG; ch += 8) {
+                // all loads of a pass are issued before the first add (9 x 4 independent L2 loads per thread in flight:
+                // one L2 latency per 72 bin groups instead of one per load); the adds keep k_source_model's order, and
+                // adding +0.0 for a slot beyond NG changes nothing
+                constexpr int NJ = 9;
+                for (int ch0 = cs; ch0 < L.NG; ch0 += 8 * NJ) {
+                    double v[4][NJ];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (ok[u]) acc[u] += __ldcg(src[u] + (size_t)ch * K * Tp);
+                    for (int j = 0; j < NJ; ++j) {
+                        const int ch = ch0 + 8 * j;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            v[u][j] = (ok[u] && ch < L.NG) ? __ldcg(src[u] + (size_t)ch * K * Tp) : 0.0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) acc[u] += v[u][j];
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {

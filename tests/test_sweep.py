@@ -191,3 +191,35 @@ def test_gpu_engine_matches_the_oracle_engine():
             assert rg["algorithm"] == rr["algorithm"] and rg["seed"] == rr["seed"]
             assert np.allclose(rg["sdr"], rr["sdr"], atol=1e-6) and np.allclose(rg["sir"], rr["sir"], atol=1e-6)
             assert rg["runtime"] > 0
+
+
+@pytest.mark.gpu
+def test_one_failing_mixture_gets_nan_and_the_rest_of_the_chunk_is_scored(monkeypatch):
+    """overiva_sim.py:334-350: a task that raises is recorded with NaN and the farm carries on.  One rank-deficient
+    mixture (a duplicated microphone) inside a GPU chunk must not take the other mixtures of the chunk with it."""
+    algs = {"overiva_laplace": {"algo": "overiva", "kwargs": {"n_iter": 8, "proj_back": True, "model": "laplace"}},
+            "auxiva_laplace": {"algo": "auxiva", "kwargs": {"n_iter": 8, "proj_back": True, "model": "laplace"}}}
+    p = dict(PARAMS, n_targets_list=[2], n_mics_list=[3], n_repeat=4, algorithm_kwargs=algs, overdet_algos=[])
+    real = sweep.make_mixture
+    calls = []
+
+    def broken(parameters, arg):
+        mix, ref = real(parameters, arg)
+        calls.append(arg)
+        if len(calls) % 4 == 2:  # the second mixture of every run of four
+            mix = mix.copy()
+            mix[:, 2] = mix[:, 0]
+        return mix, ref
+
+    monkeypatch.setattr(sweep, "make_mixture", broken)
+    got = sweep.run(p, batch=4)
+    calls.clear()
+    ref = sweep.run(p, engine=OracleEngine(64))
+    assert len(got) == len(ref) == 4
+    for i, (sg, sr) in enumerate(zip(got, ref)):
+        for rg, rr in zip(sg, sr):
+            failed = i == 1
+            assert np.isnan(rg["runtime"]) == failed
+            assert bool(np.all(np.isnan(rg["sdr"][1]))) == failed and bool(np.all(np.isnan(rr["sdr"][1]))) == failed
+            if not failed:
+                assert np.allclose(rg["sdr"], rr["sdr"], atol=1e-6) and np.allclose(rg["sir"], rr["sir"], atol=1e-6)
