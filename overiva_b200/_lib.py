@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liboveriva_b200.so")
+# (OVERIVA_B200_LIB: an alternative build of the same library, used by tuning scripts to compare kernel variants)
+LIB_PATH = os.environ.get("OVERIVA_B200_LIB") or os.path.join(_HERE, "lib", "liboveriva_b200.so")
 
 OK = 0
 ERR_INVALID, ERR_NOMEM, ERR_STATE, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3, -4, -5

@@ -448,15 +448,15 @@ struct CovTileFull {
 #pragma unroll
                 for (int k = 0; k < KC; ++k) acc[a][b][k] = cmake(0.0, 0.0);
     }
-    // frames [F0, F1) of the staged chunk.  WHOLE: all of them exist (no per-frame test: the loads of a frame can be
-    // hoisted over the arithmetic of the previous one)
-    template <bool WHOLE, int F0, int F1>
+    // WHOLE: a complete chunk of TC frames (no per-frame test: the loads of a frame can be hoisted over the arithmetic
+    // of the previous one)
+    template <bool WHOLE>
     __device__ __forceinline__ void accumulate(const XC* __restrict__ xs, const double* __restrict__ ph, int nfr, int lane) {
         const XC* xr = xs + (size_t)r0 * OIVA_GROUP + lane;
         const XC* xc = xs + (size_t)c0 * OIVA_GROUP + lane;
         const bool r_ok0 = r0 < M, r_ok1 = r0 + 1 < M;  // channels beyond M (M not a multiple of 4) contribute zeros
 #pragma unroll
-        for (int fr = F0; fr < F1; ++fr) {
+        for (int fr = 0; fr < TC; ++fr) {
             if (WHOLE || fr < nfr) {
                 cplx xi[2], xj[4];
                 double w[KC];
@@ -518,11 +518,11 @@ struct CovTileDiag {
 #pragma unroll
             for (int k = 0; k < KC; ++k) dg[n][k] = 0.0;
     }
-    template <bool WHOLE, int F0, int F1>
+    template <bool WHOLE>
     __device__ __forceinline__ void accumulate(const XC* __restrict__ xs, const double* __restrict__ ph, int nfr, int lane) {
         const XC* xd = xs + (size_t)d0 * OIVA_GROUP + lane;
 #pragma unroll
-        for (int fr = F0; fr < F1; ++fr) {
+        for (int fr = 0; fr < TC; ++fr) {
             if (WHOLE || fr < nfr) {
                 cplx x[4];
                 double w[KC];
@@ -574,88 +574,15 @@ struct CovTileDiag {
     }
 };
 
-// Producer of one CTA (lane 0 of warp 0): issues this CTA's half of every chunk (multicast to both CTAs) and the CTA's
-// own phi rows; never blocks -- a stage that is still in use in either CTA is retried at the next call.  Its cursor
-// lives in SHARED memory (one lane uses it; in registers it would cost every consumer warp ~14 registers of a kernel
-// that is at the 255 limit) and the function is kept out of line for the same reason.
-template <typename XC>
-struct CovTiledProducer {
-    long long pu;
-    const XC* psrc;
-    const double* pphi;
-    int pc, pce, pstage, puse;
-};
-template <typename ST, int M>
-__device__ __noinline__ void cov_tiled_try_issue(const CovParams& p, unsigned char* smem, long long n_pairs, uint32_t rank) {
-    typedef typename StoreC<ST>::type XC;
-    constexpr int TC = CovTiling<M>::TC, KC = CovTiling<M>::KC;
-    const GroupLayout& L = p.L;
-    const int S = p.stages;
-    const int Tp = L.frame_pitch();
-    constexpr size_t x_stage = (size_t)TC * M * OIVA_GROUP * sizeof(XC);
-    constexpr size_t stage_bytes = ((x_stage + (size_t)KC * TC * sizeof(double) + 127) / 128) * 128;
-    constexpr uint32_t frame_bytes = (uint32_t)(M * OIVA_GROUP * sizeof(XC));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-    uint64_t* empty = full + S;
-    CovTiledProducer<XC>& ps = *reinterpret_cast<CovTiledProducer<XC>*>(smem + 128);
-    unsigned char* stage0 = smem + 256;
-    const int nchunks = (L.T + TC - 1) / TC;
-    const int nsplit = p.nsplit;
-    const long long U = p.G * nsplit;
-    const size_t frame_elems = L.frame_elems(), group_elems = L.group_elems();
-    long long pu = ps.pu;
-    int pc = ps.pc, pce = ps.pce, pstage = ps.pstage, puse = ps.puse;
-    const XC* psrc = ps.psrc;
-    const double* pphi = ps.pphi;
-    while (pu < U) {
-        if (pc >= pce) {  // position the cursor on the next unit of this cluster
-            if (pce >= 0) pu += n_pairs;  // (pce < 0: first call, the cursor sits before the cluster's first unit)
-            if (pu >= U) break;
-            const long long gi = pu / nsplit;
-            const int sp = (int)(pu - gi * nsplit);
-            pc = (int)((long long)nchunks * sp / nsplit);
-            pce = (int)((long long)nchunks * (sp + 1) / nsplit);
-            const long long b = gi / p.NGphi;
-            psrc = reinterpret_cast<const XC*>(p.Xg) + (size_t)gi * group_elems + (size_t)pc * TC * frame_elems;
-            pphi = p.phi + (size_t)b * p.K * Tp + (size_t)pc * TC;
-            continue;
-        }
-        if (puse > 0 && !mbar_test_cluster(&empty[pstage], (puse - 1) & 1)) break;
-        const int nfr = min(TC, L.T - pc * TC);
-        unsigned char* dst = stage0 + (size_t)pstage * stage_bytes;
-        const uint32_t pb = (uint32_t)(((nfr + 1) & ~1) * sizeof(double));
-        mbar_arrive_expect_tx(&full[pstage], (uint32_t)nfr * frame_bytes + KC * pb);
-        const int h0 = min(nfr, TC / 2);  // this CTA's half of the frames of the chunk, delivered to both CTAs
-        const int f0 = rank ? h0 : 0, fn = rank ? nfr - h0 : h0;
-        if (fn > 0)
-            tma_load_1d_multicast(dst + (size_t)f0 * frame_bytes, psrc + (size_t)f0 * frame_elems, (uint32_t)fn * frame_bytes,
-                                  &full[pstage], (uint16_t)3);
-#pragma unroll
-        for (int k = 0; k < KC; ++k) {
-            const int ks = min(p.k0 + k, p.K - 1);  // padded source slots re-read the last row (never written back)
-            tma_load_1d(dst + x_stage + (size_t)k * TC * sizeof(double), pphi + (size_t)ks * Tp, pb, &full[pstage]);
-        }
-        psrc += (size_t)TC * frame_elems;
-        pphi += TC;
-        ++pc;
-        if (++pstage == S) {
-            pstage = 0;
-            ++puse;
-        }
-    }
-    ps.pu = pu;
-    ps.pc = pc;
-    ps.pce = pce;
-    ps.pstage = pstage;
-    ps.puse = puse;
-    ps.psrc = psrc;
-    ps.pphi = pphi;
-}
-
 // Consumer loop of one warp over the units (group, frame split) of its cluster; TILE = CovTileFull / CovTileDiag.
 // `active` = false: an idle warp (NB = 3: the second half has one tile fewer) that only keeps the barriers moving.
-// The producer lane polls cov_tiled_try_issue while its warp waits for data and between the two halves of a chunk, so
-// the ring refills as soon as stages are released.
+// Lane 0 of warp 0 of EACH CTA is that CTA's producer: it issues its half of every chunk (multicast to both CTAs) and
+// the CTA's own phi rows, never blocks (a stage that is still in use is retried later) and keeps polling while its
+// warp waits for data, so the ring refills as fast as stages are released.
+// Measured alternatives (config 5, one B200, ms per covariance pass; profiles/r02_cov_tiled_variants.md): this version
+// 3.89; the producer also polling between the two halves of a chunk through an out-of-line function 4.86 (its warp
+// becomes the straggler every stage release waits for); every warp's lane 0 polling behind a shared-memory try-lock
+// 4.28-4.43; 4 frames per stage with 4 / 6 / 8 stages 5.4 / 4.8 / 4.5.
 template <typename TILE, typename ST, int M>
 __device__ __forceinline__ void cov_tiled_consume(const CovParams& p, unsigned char* smem, int tile_index, bool active,
                                                   int lane, bool is_producer_warp, long long pair, long long n_pairs,
@@ -664,17 +591,73 @@ __device__ __forceinline__ void cov_tiled_consume(const CovParams& p, unsigned c
     constexpr int TC = CovTiling<M>::TC, KC = CovTiling<M>::KC, NE = oiva_tri(M);
     const GroupLayout& L = p.L;
     const int S = p.stages;
+    const int Tp = L.frame_pitch();
     constexpr size_t x_stage = (size_t)TC * M * OIVA_GROUP * sizeof(XC);
     constexpr size_t stage_bytes = ((x_stage + (size_t)KC * TC * sizeof(double) + 127) / 128) * 128;
+    constexpr uint32_t frame_bytes = (uint32_t)(M * OIVA_GROUP * sizeof(XC));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + S;
-    unsigned char* stage0 = smem + 256;
+    unsigned char* stage0 = smem + 128 * ((2 * S * sizeof(uint64_t) + 127) / 128);
     const int nchunks = (L.T + TC - 1) / TC;
     const int nsplit = p.nsplit;
     const long long U = p.G * nsplit;
+    const XC* Xg = reinterpret_cast<const XC*>(p.Xg);
+    const size_t frame_elems = L.frame_elems(), group_elems = L.group_elems();
     const bool leader = is_producer_warp && lane == 0;
     const uint32_t peer_empty0 = cluster_map(smem_u32(empty), rank ^ 1u);
-    if (leader) cov_tiled_try_issue<ST, M>(p, smem, n_pairs, rank);
+
+    // ---- producer state (leader lane) ----------------------------------------------------------------------------
+    long long pu = pair;
+    int pc = 0, pce = 0, pstage = 0, puse = 0;
+    const XC* psrc = nullptr;
+    const double* pphi = nullptr;
+    auto producer_unit = [&]() {
+        const long long gi = pu / nsplit;
+        const int sp = (int)(pu - gi * nsplit);
+        pc = (int)((long long)nchunks * sp / nsplit);
+        pce = (int)((long long)nchunks * (sp + 1) / nsplit);
+        const long long b = gi / p.NGphi;
+        psrc = Xg + (size_t)gi * group_elems + (size_t)pc * TC * frame_elems;
+        pphi = p.phi + (size_t)b * p.K * Tp + (size_t)pc * TC;
+    };
+    auto try_issue = [&]() {  // issue every chunk whose stage is free (in both CTAs), without blocking
+        while (pu < U) {
+            if (pc >= pce) {
+                pu += n_pairs;
+                if (pu < U) producer_unit();
+                continue;
+            }
+            if (puse > 0 && !mbar_test_cluster(&empty[pstage], (puse - 1) & 1)) return;
+            const int nfr = min(TC, L.T - pc * TC);
+            unsigned char* dst = stage0 + (size_t)pstage * stage_bytes;
+            const uint32_t pb = (uint32_t)(((nfr + 1) & ~1) * sizeof(double));
+            mbar_arrive_expect_tx(&full[pstage], (uint32_t)nfr * frame_bytes + KC * pb);
+            // this CTA's half of the frames of the chunk, delivered to both CTAs
+            const int h0 = min(nfr, TC / 2);
+            const int f0 = rank ? h0 : 0, fn = rank ? nfr - h0 : h0;
+            if (fn > 0)
+                tma_load_1d_multicast(dst + (size_t)f0 * frame_bytes, psrc + (size_t)f0 * frame_elems,
+                                      (uint32_t)fn * frame_bytes, &full[pstage], (uint16_t)3);
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const int ks = min(p.k0 + k, p.K - 1);  // padded source slots re-read the last row (never written back)
+                tma_load_1d(dst + x_stage + (size_t)k * TC * sizeof(double), pphi + (size_t)ks * Tp, pb, &full[pstage]);
+            }
+            psrc += (size_t)TC * frame_elems;
+            pphi += TC;
+            ++pc;
+            if (++pstage == S) {
+                pstage = 0;
+                ++puse;
+            }
+        }
+    };
+    if (leader && pu < U) {
+        producer_unit();
+        try_issue();
+    } else if (!leader) {
+        pu = U;
+    }
 
     int cstage = 0, cphase = 0;
     for (long long u = pair; u < U; u += n_pairs) {
@@ -687,22 +670,19 @@ __device__ __forceinline__ void cov_tiled_consume(const CovParams& p, unsigned c
         for (int c = c0; c < c1; ++c) {
             const int nfr = min(TC, L.T - c * TC);
             if (leader) {
-                while (!mbar_test(&full[cstage], cphase)) cov_tiled_try_issue<ST, M>(p, smem, n_pairs, rank);
-                cov_tiled_try_issue<ST, M>(p, smem, n_pairs, rank);
+                while (!mbar_test(&full[cstage], cphase)) try_issue();
+                try_issue();
             }
             __syncwarp();
             mbar_wait(&full[cstage], cphase);
             const unsigned char* src = stage0 + (size_t)cstage * stage_bytes;
-            const XC* xs = reinterpret_cast<const XC*>(src);
-            const double* ph = reinterpret_cast<const double*>(src + x_stage);
-            if (nfr == TC) {
-                // in two halves: between them the producer lane looks for released stages again -- a stage released
-                // while its warp is busy would otherwise wait a whole chunk (~1.6 us) for its refill to be issued
-                if (active) tile.template accumulate<true, 0, TC / 2>(xs, ph, nfr, lane);
-                if (leader) cov_tiled_try_issue<ST, M>(p, smem, n_pairs, rank);
-                if (active) tile.template accumulate<true, TC / 2, TC>(xs, ph, nfr, lane);
-            } else if (active) {
-                tile.template accumulate<false, 0, TC>(xs, ph, nfr, lane);
+            if (active) {
+                if (nfr == TC)
+                    tile.template accumulate<true>(reinterpret_cast<const XC*>(src),
+                                                   reinterpret_cast<const double*>(src + x_stage), nfr, lane);
+                else
+                    tile.template accumulate<false>(reinterpret_cast<const XC*>(src),
+                                                    reinterpret_cast<const double*>(src + x_stage), nfr, lane);
             }
             __syncwarp();
             if (lane == 0) {  // release the stage in both CTAs (each producer writes into both)
@@ -737,15 +717,6 @@ __global__ void __launch_bounds__(CovTiling<M>::WARPS * 32, 1) k_cov_tiled(const
             mbar_init(&empty[s], 2 * TL::WARPS);  // the consumer warps of BOTH CTAs
         }
         mbar_fence_init();
-        typedef CovTiledProducer<typename StoreC<ST>::type> PS;
-        PS& ps = *reinterpret_cast<PS*>(smem_raw + 128);
-        ps.pu = blockIdx.x >> 1;  // the cursor sits before the cluster's first unit
-        ps.pc = 0;
-        ps.pce = -1;
-        ps.pstage = 0;
-        ps.puse = 0;
-        ps.psrc = nullptr;
-        ps.pphi = nullptr;
     }
     cluster_sync_all();  // both CTAs' barriers exist before anyone copies into / arrives on the peer's
     const uint32_t rank = cluster_ctarank();

@@ -198,9 +198,8 @@ static int launch_tiled(CovParams p, cudaStream_t st, int* nsplit_out) {
         int S = env_int("OIVA_COV_TILED_STAGES", 3);
         if (S < 2) S = 2;
         const size_t budget = 200 * 1024;
-        if (S > 8) S = 8;  // (barriers: 128 bytes; producer cursor: 128 bytes)
-        while (S > 2 && 256 + (size_t)S * stage_bytes > budget) --S;
-        const size_t smem = 256 + (size_t)S * stage_bytes;
+        while (S > 2 && 128 * ((2 * S * sizeof(uint64_t) + 127) / 128) + (size_t)S * stage_bytes > budget) --S;
+        const size_t smem = 128 * ((2 * S * sizeof(uint64_t) + 127) / 128) + (size_t)S * stage_bytes;
         p.stages = S;
         OIVA_SET_MAX_SMEM_ONCE(kern, budget);
         cudaLaunchConfig_t cfg = {};

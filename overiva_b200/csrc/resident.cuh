@@ -359,9 +359,15 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
         auto r_at = [&](int k, int t) { return p.stat_local ? sR[k * Tp + t] : __ldcg(rglob + (size_t)k * Tp + t); };
         if (warp < K) {
             double lsum = 0.0;
-            for (int tt = 0; tt < Tp; tt += 32) {
-                const int t = tt + lane;
-                if (t < T) lsum += r_at(warp, t);
+            for (int tt = 0; tt < Tp; tt += 128) {  // 4 loads in flight, added in ascending order (+0.0 beyond T)
+                double v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int t = tt + 32 * j + lane;
+                    v[j] = t < T ? r_at(warp, t) : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) lsum += v[j];
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
@@ -400,14 +406,35 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
             // ---- (5) last CTA of the group: fixed-order sum of the partial covariances + the IP sweep   overiva.py:176-190
             __threadfence();
             const int n_slots = p.SG * RC::FW;
+            // (the slots are added in ascending order, as k_cov_sum_partials does; the loads of 8 slots are issued
+            // before the first add -- one L2 latency per 8 slots instead of one per slot: ncu showed the other CTAs of
+            // the group waiting 30 % of the epoch for this loop when it was a plain load-add chain)
             auto reduce_source = [&](int s, cplx* out, int first_thread, int n_threads) {
                 for (uint32_t i = tid - first_thread; i < MAT_ELEMS; i += n_threads) {
                     const cplx* src = p.Vpart + (size_t)gi * grp_cov + (size_t)s * MAT_ELEMS + i;
-                    cplx acc = __ldcg(src);
-                    for (int sp = 1; sp < n_slots; ++sp) {
-                        const cplx v = __ldcg(src + (size_t)sp * p.G * grp_cov);
-                        acc.x += v.x;
-                        acc.y += v.y;
+                    const size_t slot_stride = (size_t)p.G * grp_cov;
+                    cplx acc = cmake(0.0, 0.0);
+                    for (int sp0 = 0; sp0 < n_slots; sp0 += 8) {
+                        cplx v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            v[j] = sp0 + j < n_slots ? __ldcg(src + (size_t)(sp0 + j) * slot_stride) : cmake(0.0, 0.0);
+                        if (sp0 == 0) {
+                            acc = v[0];
+#pragma unroll
+                            for (int j = 1; j < 8; ++j)
+                                if (j < n_slots) {
+                                    acc.x += v[j].x;
+                                    acc.y += v[j].y;
+                                }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (sp0 + j < n_slots) {
+                                    acc.x += v[j].x;
+                                    acc.y += v[j].y;
+                                }
+                        }
                     }
                     out[i] = acc;
                 }
