@@ -5,8 +5,7 @@
 
 namespace oiva {
 #define OIVA_DECL(M)                                                                                              \
-    int resident_launch_m##M(int dtype, int K, int stream_mode, const ResidentParams& p, unsigned grid, size_t smem, \
-                             cudaStream_t st);                                                                    \
+    int resident_launch_m##M(int dtype, int K, const ResidentParams& p, unsigned grid, size_t smem, cudaStream_t st); \
     int resident_fw_m##M(int K);
 OIVA_DECL(1) OIVA_DECL(2) OIVA_DECL(3) OIVA_DECL(4) OIVA_DECL(5) OIVA_DECL(6) OIVA_DECL(7) OIVA_DECL(8)
 #undef OIVA_DECL
@@ -24,7 +23,7 @@ constexpr size_t RES_MAX_SMEM = 232448;  // 227 KB: the per-CTA maximum of sm_10
 constexpr int RES_MAX_SG = 8;            // slices per bin group (keeps the partial-sum slots <= 64)
 
 struct ResidentChoice {
-    int SG, slice_cap, v_bufs, fw, n_stages;  // n_stages > 0: the STREAM kernels (samples through a ring)
+    int SG, slice_cap, v_bufs, fw, stat_local;
     size_t smem;
 };
 
@@ -44,35 +43,25 @@ static bool resident_choose(int B, int T, int F, int M, int K, int dtype, int ma
     for (; SG >= 1; --SG) {
         if ((size_t)SG * fw * vg > scratch_bytes) continue;
         const int cap = (T + SG - 1) / SG;
-        for (int vb = (K == M && M >= 3) ? 1 : 2; vb >= 1; --vb) {  // (the determined sweep uses all warps: one V buffer)
-            const ResSmem lay = res_smem_layout(M, K, cap, vb, esz);
+        const int Tp = oiva_frame_pitch(T), NG = oiva_bin_groups(F);
+        // few frames: every CTA reduces the statistic of its mixture itself (K * Tp doubles of shared memory, K * T * NG
+        // L2 loads per CTA) and the epoch needs one grid barrier instead of two
+        const bool want_local = (size_t)K * Tp * 8 <= 16384 && (long long)K * T * NG <= 40000;
+        for (int mode = want_local ? 0 : 2; mode < 4; ++mode) {  // (local, 2 V buffers) (local, 1) (exchange, 2) (exchange, 1)
+            const int local = mode < 2, vb = (mode & 1) ? 1 : 2;
+            if (K == M && M >= 3 && vb == 2) continue;  // the determined sweep uses all warps: a single V buffer
+            const ResSmem lay = res_smem_layout(M, K, cap, vb, esz, local ? K * Tp : 0);
             if (lay.total <= RES_MAX_SMEM) {
                 out->SG = SG;
                 out->slice_cap = cap;
                 out->v_bufs = vb;
                 out->fw = fw;
-                out->n_stages = 0;
+                out->stat_local = local;
                 out->smem = lay.total;
                 return true;
             }
         }
-        // The slice does not fit shared memory (a finer slicing would need more CTAs than the GPU has): stream it through a
-        // ring of 16-frame stages instead, as many stages as fit (>= 2).
-        for (int ns = 4; ns >= 2; --ns) {
-            const int vb = (K == M && M >= 3) ? 1 : 2;
-            for (int v = vb; v >= 1; --v) {
-                const ResSmem lay = res_smem_layout(M, K, cap, v, esz, ns);
-                if (lay.total <= RES_MAX_SMEM) {
-                    out->SG = SG;
-                    out->slice_cap = cap;
-                    out->v_bufs = v;
-                    out->fw = fw;
-                    out->n_stages = ns;
-                    out->smem = lay.total;
-                    return true;
-                }
-            }
-        }
+        // a finer slicing needs more CTAs than the GPU has: only coarser ones remain, which need even more shared memory
         return false;
     }
     return false;
@@ -122,12 +111,12 @@ extern "C" int oiva_loop_resident(const void* Xg, void* Wg, const void* Cg, doub
     p.F_total = n_freq_total > 0 ? n_freq_total : n_freq;
     p.slice_cap = ch.slice_cap;
     p.v_bufs = ch.v_bufs;
-    p.n_stages = ch.n_stages;
+    p.stat_local = ch.stat_local;
     p.invT = 1.0 / (double)n_frames;
     OIVA_CUDA_CHECK(cudaMemsetAsync(sync, 0, oiva_loop_resident_sync_bytes(n_batch, n_freq), st));
     const unsigned grid = (unsigned)(p.G * ch.SG);
     switch (n_chan) {
-#define OIVA_CASE(M_) case M_: return resident_launch_m##M_(dtype, n_src, ch.n_stages > 0, p, grid, ch.smem, st);
+#define OIVA_CASE(M_) case M_: return resident_launch_m##M_(dtype, n_src, p, grid, ch.smem, st);
         OIVA_CASE(1) OIVA_CASE(2) OIVA_CASE(3) OIVA_CASE(4) OIVA_CASE(5) OIVA_CASE(6) OIVA_CASE(7) OIVA_CASE(8)
 #undef OIVA_CASE
     }

@@ -18,12 +18,6 @@
 //   All cross-CTA traffic (statistic partials, covariance partials, W_hat) is a few hundred KB per epoch and stays in L2.
 // Results are deterministic (fixed summation orders everywhere) and agree with the multi-kernel path to rounding
 // (same statistic arithmetic; the covariance sums frames in different sub-ranges).
-//
-// STREAM variant (a mixture too long for shared memory, still few bin groups -- config 3: 60 s, M = 8, 122 MB): the same
-// loop, but a slice is streamed through a ring of 16-frame stages by bulk TMA in both passes of every epoch.  The
-// chunk sequence of a slice is known in advance (chunks 0..NC-1, twice per epoch), so the ring runs CONTINUOUSLY across
-// the phases and epochs: while the CTAs sit in a grid barrier or wait for a sweep, the first stages of the next pass
-// are already landing.
 #pragma once
 #include "cov.cuh"
 #include "solve.cuh"
@@ -50,7 +44,8 @@ struct ResidentParams {
     int B, SG, n_iter, model, F_total;
     int slice_cap;    // frames a slice can hold (= max over slices)
     int v_bufs;       // 1 or 2 shared-memory buffers for the reduced V_s
-    int n_stages;     // STREAM kernels: stages of the sample ring (RES_CH frames each); resident kernels: 0
+    int stat_local;   // 1: every CTA sums the statistic partials of its mixture itself (one grid barrier per epoch instead of
+                      //    two); 0: the (k, t) pairs are dealt to the CTAs and exchanged through rbuf (many frames)
     double invT;
 };
 
@@ -84,30 +79,27 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
     __syncthreads();
 }
 
-// weighted covariance accumulators of one warp: the entries of one part, all K sources; same products and accumulation
-// as CovPart::accumulate / finish (cov.cuh).  add(): frames [f0, f1) of a block of samples xs ([frame][M][32]) with the
-// weights ph[k * pitch + frame].
+// weighted covariance of frames [f0, f1) of the slice for the entries of one part, all K sources; same products and
+// accumulation as CovPart::accumulate / finish (cov.cuh)
 template <typename ST, int M, int K, int P, int PART>
-struct ResCovAcc {
+struct ResCovPart {
     typedef typename StoreC<ST>::type XC;
     static constexpr int NE = oiva_tri(M), NEP = (NE + P - 1) / P;
-    cplx acc[NEP][K];
-    __device__ __forceinline__ void zero() {
+    __device__ static __forceinline__ void run(const XC* __restrict__ sX, const double* __restrict__ sPhi, int pitch, int f0,
+                                               int f1, cplx* __restrict__ dst, double invT, int lane) {
+        cplx acc[NEP][K];
 #pragma unroll
         for (int n = 0; n < NEP; ++n)
 #pragma unroll
             for (int k = 0; k < K; ++k) acc[n][k] = cmake(0.0, 0.0);
-    }
-    __device__ __forceinline__ void add(const XC* __restrict__ xs, const double* __restrict__ ph, int pitch, int f0, int f1,
-                                        int lane) {
 #pragma unroll 2
         for (int fr = f0; fr < f1; ++fr) {
             cplx x[M];
             double w[K];
 #pragma unroll
-            for (int c = 0; c < M; ++c) x[c] = widen(xs[((size_t)fr * M + c) * OIVA_GROUP + lane]);
+            for (int c = 0; c < M; ++c) x[c] = widen(sX[((size_t)fr * M + c) * OIVA_GROUP + lane]);
 #pragma unroll
-            for (int k = 0; k < K; ++k) w[k] = ph[k * pitch + fr];
+            for (int k = 0; k < K; ++k) w[k] = sPhi[k * pitch + fr];
             static_for<NEP>([&](auto nc) {
                 constexpr int n = decltype(nc)::value;
                 constexpr int e = PART + n * P;
@@ -129,8 +121,6 @@ struct ResCovAcc {
                 }
             });
         }
-    }
-    __device__ __forceinline__ void store(cplx* __restrict__ dst, double invT, int lane) const {
         static_for<NEP>([&](auto nc) {
             constexpr int n = decltype(nc)::value;
             constexpr int e = PART + n * P;
@@ -144,83 +134,45 @@ struct ResCovAcc {
         });
     }
 };
-
-// STREAM kernels: the CTA's ring of sample stages.  One producer (thread 0) that never blocks and is polled whenever
-// its warp waits for data or releases a stage; every warp consumes every chunk (wait -> use -> release).
-constexpr int RES_CH = 16;  // frames per stage: 2 per warp in the statistic pass
-template <typename XC>
-struct ResRing {
-    uint64_t* full;
-    uint64_t* empty;
-    unsigned char* stage0;
-    const unsigned char* src;  // the slice in global memory
-    size_t stage_bytes, frame_bytes;
-    int n_stages, n_chunks, nfr;
-    int cstage, cphase;                // consumer cursor (all threads, in step)
-    long long pq, ptotal;              // producer cursor (thread 0)
-    int pstage, puse, pc;
-    __device__ __forceinline__ void try_issue() {
-        while (pq < ptotal) {
-            if (puse > 0 && !mbar_test(&empty[pstage], (puse - 1) & 1)) return;
-            const int n = min(RES_CH, nfr - pc * RES_CH);
-            const uint32_t bytes = (uint32_t)((size_t)n * frame_bytes);
-            mbar_arrive_expect_tx(&full[pstage], bytes);
-            tma_load_1d(stage0 + (size_t)pstage * stage_bytes, src + (size_t)pc * RES_CH * frame_bytes, bytes, &full[pstage]);
-            ++pq;
-            if (++pc == n_chunks) pc = 0;
-            if (++pstage == n_stages) {
-                pstage = 0;
-                ++puse;
-            }
-        }
-    }
-    __device__ __forceinline__ const XC* wait() {
-        if (threadIdx.x == 0) {
-            while (!mbar_test(&full[cstage], cphase)) try_issue();
-        }
-        __syncwarp();
-        mbar_wait(&full[cstage], cphase);
-        return reinterpret_cast<const XC*>(stage0 + (size_t)cstage * stage_bytes);
-    }
-    __device__ __forceinline__ void release() {
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[cstage]);
-        if (++cstage == n_stages) {
-            cstage = 0;
-            cphase ^= 1;
-        }
-        if (threadIdx.x == 0) try_issue();
+template <typename ST, int M, int K, int P, int PART = 0>
+struct ResCovDispatch {
+    typedef typename StoreC<ST>::type XC;
+    __device__ static __forceinline__ void run(int part, const XC* sX, const double* sPhi, int pitch, int f0, int f1, cplx* dst,
+                                               double invT, int lane) {
+        if (part == PART) ResCovPart<ST, M, K, P, PART>::run(sX, sPhi, pitch, f0, f1, dst, invT, lane);
+        else if constexpr (PART + 1 < P) ResCovDispatch<ST, M, K, P, PART + 1>::run(part, sX, sPhi, pitch, f0, f1, dst, invT, lane);
     }
 };
 
 // shared-memory carve-up (host and device agree through this one function); offsets in bytes from the dynamic base
 struct ResSmem {
-    size_t x, phi, misc, c, v, w, total;
+    size_t x, phi, misc, c, v, w, r, total;
 };
-// n_stages > 0 (STREAM kernels): the sample region holds n_stages stages of RES_CH frames instead of the whole slice
-__host__ __device__ inline ResSmem res_smem_layout(int M, int K, int slice_cap, int v_bufs, int elem_bytes, int n_stages = 0) {
+// r_doubles: K * Tp when the statistic is reduced locally (stat_local), else 0
+__host__ __device__ inline ResSmem res_smem_layout(int M, int K, int slice_cap, int v_bufs, int elem_bytes, int r_doubles) {
     ResSmem s;
     const size_t mat = (size_t)oiva_tri(M) * OIVA_GROUP * sizeof(cplx);
     size_t o = 128;  // [0]: mbarrier of the slice load
-    s.x = o;    o += (((size_t)(n_stages > 0 ? n_stages * 16 : slice_cap) * M * OIVA_GROUP * elem_bytes) + 127) / 128 * 128;
+    s.x = o;    o += (((size_t)slice_cap * M * OIVA_GROUP * elem_bytes) + 127) / 128 * 128;
     s.phi = o;  o += (((size_t)K * slice_cap * sizeof(double)) + 127) / 128 * 128;
     s.misc = o; o += 256;  // gamma[8], wscale[8], flags
     s.c = o;    o += mat;
     s.v = o;    o += (size_t)v_bufs * mat;
     s.w = o;    o += (size_t)M * M * OIVA_GROUP * sizeof(cplx);
+    s.r = o;    o += (((size_t)r_doubles * sizeof(double)) + 127) / 128 * 128;
     s.total = o;
     return s;
 }
 
 // grid = G * SG CTAs of 256 threads (cooperative launch); CTA c owns slice s = c % SG of bin group gi = c / SG
-template <typename ST, int M, int K, bool STREAM>
+template <typename ST, int M, int K>
 __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const ResidentParams p) {
     typedef typename StoreC<ST>::type XC;
     typedef ResCfg<M, K> RC;
     constexpr int NE = RC::NE;
     constexpr uint32_t MAT_ELEMS = NE * OIVA_GROUP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const ResSmem lay = res_smem_layout(M, K, p.slice_cap, p.v_bufs, (int)sizeof(XC), STREAM ? p.n_stages : 0);
+    const ResSmem lay = res_smem_layout(M, K, p.slice_cap, p.v_bufs, (int)sizeof(XC), p.stat_local ? K * p.L.frame_pitch() : 0);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     XC* sX = reinterpret_cast<XC*>(smem_raw + lay.x);
     double* sPhi = reinterpret_cast<double*>(smem_raw + lay.phi);
@@ -230,6 +182,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
     cplx* sC = reinterpret_cast<cplx*>(smem_raw + lay.c);
     cplx* sV = reinterpret_cast<cplx*>(smem_raw + lay.v);
     cplx* sW = reinterpret_cast<cplx*>(smem_raw + lay.w);
+    double* sR = reinterpret_cast<double*>(smem_raw + lay.r);
 
     const GroupLayout& L = p.L;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -248,50 +201,21 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
     cplx* Wgrp = p.Wg + (size_t)gi * M * M * OIVA_GROUP;
     const size_t grp_cov = (size_t)K * NE * OIVA_GROUP;
 
-    // ---- one-time: the slice's samples (bulk TMA; STREAM: the ring and its first stages) and the group's input covariance
-    const XC* slice_src = reinterpret_cast<const XC*>(p.Xg) + (size_t)gi * L.group_elems() + (size_t)t0 * L.frame_elems();
-    ResRing<XC> ring;
-    if constexpr (STREAM) {
-        ring.full = bar + 1;
-        ring.empty = bar + 1 + p.n_stages;
-        ring.stage0 = reinterpret_cast<unsigned char*>(sX);
-        ring.src = reinterpret_cast<const unsigned char*>(slice_src);
-        ring.frame_bytes = L.frame_elems() * sizeof(XC);
-        ring.stage_bytes = (size_t)RES_CH * ring.frame_bytes;
-        ring.n_stages = p.n_stages;
-        ring.n_chunks = (nfr + RES_CH - 1) / RES_CH;
-        ring.nfr = nfr;
-        ring.cstage = 0;
-        ring.cphase = 0;
-        ring.pq = 0;
-        ring.ptotal = 2ll * p.n_iter * ring.n_chunks;  // every epoch walks the slice twice (statistic, covariance)
-        ring.pstage = 0;
-        ring.puse = 0;
-        ring.pc = 0;
-        if (tid == 0) {
-            for (int s2 = 0; s2 < p.n_stages; ++s2) {
-                mbar_init(&ring.full[s2], 1);
-                mbar_init(&ring.empty[s2], RES_WARPS);
-            }
-            mbar_fence_init();
-        }
-    } else if (tid == 0) {
+    // ---- one-time: the slice's samples (bulk TMA) and the group's input covariance into shared memory ---------------
+    if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
+        const XC* src = reinterpret_cast<const XC*>(p.Xg) + (size_t)gi * L.group_elems() + (size_t)t0 * L.frame_elems();
         const size_t bytes = (size_t)nfr * L.frame_elems() * sizeof(XC);
         mbar_arrive_expect_tx(bar, (uint32_t)bytes);
         const size_t piece = 32768;
         for (size_t o = 0; o < bytes; o += piece)
-            tma_load_1d(reinterpret_cast<unsigned char*>(sX) + o, reinterpret_cast<const unsigned char*>(slice_src) + o,
+            tma_load_1d(reinterpret_cast<unsigned char*>(sX) + o, reinterpret_cast<const unsigned char*>(src) + o,
                         (uint32_t)(bytes - o < piece ? bytes - o : piece), bar);
     }
     for (uint32_t i = tid; i < MAT_ELEMS; i += RES_THREADS) sC[i] = p.Cg[(size_t)gi * MAT_ELEMS + i];
     __syncthreads();
-    if constexpr (STREAM) {
-        if (tid == 0) ring.try_issue();
-    } else {
-        mbar_wait(bar, 0);
-    }
+    mbar_wait(bar, 0);
 
     unsigned n_bar = 0;
 #pragma unroll 1
@@ -304,60 +228,43 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
 #pragma unroll
                 for (int k = 0; k < K; ++k) w[c][k] = __ldcg(Wgrp + (size_t)(c * M + k) * OIVA_GROUP + lane);
             double* r2g = p.r2part + (size_t)gi * K * Tp;
-            if constexpr (STREAM) {
-                constexpr int FBW = RES_CH / RES_WARPS;  // frames per warp and chunk
-                constexpr int LPF = OIVA_GROUP / FBW;
-                for (int c = 0; c < ring.n_chunks; ++c) {
-                    const XC* xs = ring.wait();
-                    const int nfc = min(RES_CH, nfr - c * RES_CH);
-                    const int j0 = warp * FBW;
-                    double v[K][FBW];
+            for (int blk = warp; blk * POWER_FB < nfr; blk += RES_WARPS) {
+                const int fb = blk * POWER_FB;
+                double v[K][POWER_FB];
 #pragma unroll
-                    for (int j = 0; j < FBW; ++j) {
-                        if (j0 + j < nfc) {
-                            cplx x[M], y[K];
+                for (int j = 0; j < POWER_FB; ++j) {
+                    if (fb + j < nfr) {
+                        cplx x[M], y[K];
 #pragma unroll
-                            for (int ch = 0; ch < M; ++ch) x[ch] = widen(xs[((size_t)(j0 + j) * M + ch) * OIVA_GROUP + lane]);
-                            demix_frame<M, K>(y, x, w);
+                        for (int c = 0; c < M; ++c) x[c] = widen(sX[((size_t)(fb + j) * M + c) * OIVA_GROUP + lane]);
+                        demix_frame<M, K>(y, x, w);
 #pragma unroll
-                            for (int k = 0; k < K; ++k) v[k][j] = fma(y[k].x, y[k].x, y[k].y * y[k].y);
-                        } else {
+                        for (int k = 0; k < K; ++k) v[k][j] = fma(y[k].x, y[k].x, y[k].y * y[k].y);
+                    } else {
 #pragma unroll
-                            for (int k = 0; k < K; ++k) v[k][j] = 0.0;
-                        }
-                    }
-                    ring.release();
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const double sres = lane_sum_frames<FBW>(v[k], lane);
-                        const int j = j0 + lane / LPF;
-                        if ((lane % LPF) == 0 && j < nfc) __stcg(r2g + (size_t)k * Tp + t0 + c * RES_CH + j, sres);
+                        for (int k = 0; k < K; ++k) v[k][j] = 0.0;
                     }
                 }
-            } else {
-                for (int blk = warp; blk * POWER_FB < nfr; blk += RES_WARPS) {
-                    const int fb = blk * POWER_FB;
-                    double v[K][POWER_FB];
 #pragma unroll
-                    for (int j = 0; j < POWER_FB; ++j) {
-                        if (fb + j < nfr) {
-                            cplx x[M], y[K];
+                for (int k = 0; k < K; ++k) {  // the transposing butterfly of k_demix_power (stream.cuh)
 #pragma unroll
-                            for (int c = 0; c < M; ++c) x[c] = widen(sX[((size_t)(fb + j) * M + c) * OIVA_GROUP + lane]);
-                            demix_frame<M, K>(y, x, w);
+                    for (int lvl = 0; lvl < 3; ++lvl) {
+                        const int H = POWER_FB >> (lvl + 1);
+                        const int off = 16 >> lvl;
+                        const bool up = (lane & off) != 0;
 #pragma unroll
-                            for (int k = 0; k < K; ++k) v[k][j] = fma(y[k].x, y[k].x, y[k].y * y[k].y);
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < K; ++k) v[k][j] = 0.0;
+                        for (int n = 0; n < H; ++n) {
+                            const double lo = v[k][n], hi = v[k][n + H];
+                            const double send = up ? lo : hi;
+                            const double keep = up ? hi : lo;
+                            v[k][n] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                         }
                     }
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {  // the lane sum of k_demix_power (stream.cuh)
-                        const double sres = lane_sum_frames<POWER_FB>(v[k], lane);
-                        const int j = lane >> 2;
-                        if ((lane & 3) == 0 && fb + j < nfr) __stcg(r2g + (size_t)k * Tp + t0 + fb + j, sres);
-                    }
+                    double s = v[k][0];
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    const int j = lane >> 2;
+                    if ((lane & 3) == 0 && fb + j < nfr) __stcg(r2g + (size_t)k * Tp + t0 + fb + j, s);
                 }
             }
         }
@@ -372,10 +279,57 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                 default: return 0.0;
             }
         };
-        {
-            // the (k, t) pairs are dealt round-robin to the CTAs, r goes through rbuf (L2) and a second grid barrier.
-            // (Every CTA summing all partials of its mixture itself -- one barrier less -- measured slower at config 1:
-            // 0.47 vs 0.41 ms per 20 epochs; the 130 CTAs re-read K * T * NG partials each, 8 of every 32-byte sector.)
+        if (p.stat_local) {
+            // few frames: every CTA adds up the partials of its own mixture (L2 reads, 4 items x NG/8 loads in flight
+            // per thread) -- no second grid barrier, no exchange of r
+            const int n_items = K * T * 8;  // item = (k * T + t) * 8 + slice
+            const double* base = p.r2part + (size_t)b * L.NG * K * Tp;
+            for (int i0 = 0; i0 < n_items; i0 += RES_THREADS * 4) {
+                double acc[4];
+                const double* src[4];
+                bool ok[4];
+                int kk[4], tt[4];
+                const int cs = tid & 7;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int item = i0 + u * RES_THREADS + tid;
+                    ok[u] = item < n_items;
+                    const int pair = (ok[u] ? item : 0) >> 3;
+                    kk[u] = pair / T;
+                    tt[u] = pair - kk[u] * T;
+                    src[u] = base + (size_t)kk[u] * Tp + tt[u];
+                    acc[u] = 0.0;
+                }
+                // all loads of a pass are issued before the first add (9 x 4 independent L2 loads per thread in flight:
+                // one L2 latency per 72 bin groups instead of one per load); the adds keep k_source_model's order, and
+                // adding +0.0 for a slot beyond NG changes nothing
+                constexpr int NJ = 9;
+                for (int ch0 = cs; ch0 < L.NG; ch0 += 8 * NJ) {
+                    double v[4][NJ];
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        const int ch = ch0 + 8 * j;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            v[u][j] = (ok[u] && ch < L.NG) ? __ldcg(src[u] + (size_t)ch * K * Tp) : 0.0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) acc[u] += v[u][j];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    double v = acc[u];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    if (ok[u] && cs == 0) sR[kk[u] * Tp + tt[u]] = model_fn(v);
+                }
+            }
+            __syncthreads();
+        } else {
+            // many frames: the (k, t) pairs are dealt round-robin to the CTAs, r goes through rbuf and a second barrier
             const long long n_pairs = (long long)p.B * K * T;
             const int sub = lane >> 3, cs = lane & 7;
             for (long long q0 = ((long long)blockIdx.x * RES_WARPS + warp) * 4; q0 < n_pairs;
@@ -402,7 +356,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
 
         // ---- (3) gamma = mean_t r, phi = 1 / max(r / gamma, 1e-15) for the slice's frames, W scale   overiva.py:158-173
         const double* rglob = p.rbuf + (size_t)b * K * Tp;
-        auto r_at = [&](int k, int t) { return __ldcg(rglob + (size_t)k * Tp + t); };
+        auto r_at = [&](int k, int t) { return p.stat_local ? sR[k * Tp + t] : __ldcg(rglob + (size_t)k * Tp + t); };
         if (warp < K) {
             double lsum = 0.0;
             for (int tt = 0; tt < Tp; tt += 128) {  // 4 loads in flight, added in ascending order (+0.0 beyond T)
@@ -435,28 +389,10 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
         // ---- (4) weighted covariance of the slice, per-warp partial sums to the L2 scratch            overiva.py:179
         {
             const int part = warp % RC::P, fw = warp / RC::P;
+            const int f0 = (int)((long long)nfr * fw / RC::FW), f1 = (int)((long long)nfr * (fw + 1) / RC::FW);
             const int slot = sl * RC::FW + fw;
             cplx* dst = p.Vpart + ((size_t)slot * p.G + gi) * grp_cov;
-            static_for<RC::P>([&](auto pc_) {
-                constexpr int PART = decltype(pc_)::value;
-                if (part == PART) {
-                    ResCovAcc<ST, M, K, RC::P, PART> acc;
-                    acc.zero();
-                    if constexpr (STREAM) {
-                        for (int c = 0; c < ring.n_chunks; ++c) {
-                            const XC* xs = ring.wait();
-                            const int nfc = min(RES_CH, nfr - c * RES_CH);
-                            const int f0 = min(nfc, RES_CH * fw / RC::FW), f1 = min(nfc, RES_CH * (fw + 1) / RC::FW);
-                            acc.add(xs, sPhi + c * RES_CH, pitch, f0, f1, lane);
-                            ring.release();
-                        }
-                    } else {
-                        const int f0 = (int)((long long)nfr * fw / RC::FW), f1 = (int)((long long)nfr * (fw + 1) / RC::FW);
-                        acc.add(sX, sPhi, pitch, f0, f1, lane);
-                    }
-                    acc.store(dst, p.invT, lane);
-                }
-            });
+            ResCovDispatch<ST, M, K, RC::P>::run(part, sX, sPhi, pitch, f0, f1, dst, p.invT, lane);
         }
         __syncthreads();
         if (tid == 0) {

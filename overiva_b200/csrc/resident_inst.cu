@@ -10,7 +10,7 @@ namespace oiva {
 #define OIVA_CAT2(a, b) a##b
 #define OIVA_CAT(a, b) OIVA_CAT2(a, b)
 
-template <typename ST, int K, bool STREAM>
+template <typename ST, int K>
 static int launch_res(const ResidentParams& p, unsigned grid, size_t smem, cudaStream_t st) {
     constexpr int M = OIVA_M;
     // the sweep runs one thread per bin: the shapes k_ip_update_tpb is instantiated for (solve_tpb.cu) -- the determined
@@ -18,7 +18,7 @@ static int launch_res(const ResidentParams& p, unsigned grid, size_t smem, cudaS
     if constexpr (K > M || (M >= 7 && K > 4)) {
         return OIVA_ERR_UNSUPPORTED;
     } else {
-        auto kern = k_loop_resident<ST, M, K, STREAM>;
+        auto kern = k_loop_resident<ST, M, K>;
         OIVA_SET_MAX_SMEM_ONCE(kern, 232448);
         int dev = 0, sms = 0, occ = 0;
         OIVA_CUDA_CHECK(cudaGetDevice(&dev));
@@ -35,15 +35,11 @@ static int launch_res(const ResidentParams& p, unsigned grid, size_t smem, cudaS
     }
 }
 
-int OIVA_CAT(resident_launch_m, OIVA_M)(int dtype, int K, int stream_mode, const ResidentParams& p, unsigned grid,
-                                        size_t smem, cudaStream_t st) {
-#define OIVA_RES_CASE(K_)                                                                                        \
-    case K_:                                                                                                     \
-        if (stream_mode)                                                                                         \
-            return dtype == OIVA_C64 ? launch_res<float, K_, true>(p, grid, smem, st)                            \
-                                     : launch_res<double, K_, true>(p, grid, smem, st);                          \
-        return dtype == OIVA_C64 ? launch_res<float, K_, false>(p, grid, smem, st)                               \
-                                 : launch_res<double, K_, false>(p, grid, smem, st);
+int OIVA_CAT(resident_launch_m, OIVA_M)(int dtype, int K, const ResidentParams& p, unsigned grid, size_t smem,
+                                        cudaStream_t st) {
+#define OIVA_RES_CASE(K_)                                                                        \
+    case K_:                                                                                     \
+        return dtype == OIVA_C64 ? launch_res<float, K_>(p, grid, smem, st) : launch_res<double, K_>(p, grid, smem, st);
     switch (K) {
         OIVA_RES_CASE(1) OIVA_RES_CASE(2) OIVA_RES_CASE(3) OIVA_RES_CASE(4)
         OIVA_RES_CASE(5) OIVA_RES_CASE(6) OIVA_RES_CASE(7) OIVA_RES_CASE(8)

@@ -42,9 +42,7 @@ def run_plan(Xd, K, model, n_iter, resident):
 
 worst = 0.0
 for M, K, n_samples, frame in [(4, 2, 3000, 64), (2, 1, 900, 32), (6, 6, 20000, 512), (3, 3, 5000, 128), (8, 4, 16000, 256),
-                               (5, 2, 60000, 2048), (7, 3, 4000, 64), (6, 2, 9000, 256),
-                               # long inputs with few bins: the STREAM kernels (slices through a ring of stages)
-                               (8, 2, 32000, 64), (4, 2, 80000, 64), (6, 6, 40000, 64), (3, 1, 150000, 32)]:
+                               (5, 2, 60000, 2048), (7, 3, 4000, 64), (6, 2, 9000, 256)]:
     for B in (1, 2):
         X = np.stack([small_test_mixture(70 + b, M, min(K, 2), n_samples=n_samples, frame=frame, hop=frame // 2)
                       for b in range(B)])
@@ -58,8 +56,7 @@ for M, K, n_samples, frame in [(4, 2, 3000, 64), (2, 1, 900, 32), (6, 6, 20000, 
         assert nl == 1 and st == 0 and e < 1e-11, (nl, st, e)
 os.environ.pop("OIVA_NO_RESIDENT", None)
 for name, m, secs, kw in [("cfg1", 4, 15.0, dict(n_src=2, n_iter=20, model="laplace")),
-                          ("cfg2", 6, 15.0, dict(n_iter=20, model="laplace")),
-                          ("cfg3", 8, 60.0, dict(n_src=2, n_iter=20, model="gauss", init_eig=True))]:
+                          ("cfg2", 6, 15.0, dict(n_iter=20, model="laplace"))]:
     mix, _ = convolutive_mixture(900 + m, m, 2, duration=secs)
     Xn = stft(mix)
     Xd = torch.from_numpy(Xn).cuda()
@@ -84,7 +81,7 @@ for name, m, secs, kw in [("cfg1", 4, 15.0, dict(n_src=2, n_iter=20, model="lapl
         # the epoch loop alone
         T_, F_, M_ = Xn.shape
         K_ = kw.get("n_src") or M_
-        plan = DemixPlan(1, T_, F_, M_, K_, L.MODEL_GAUSS if kw["model"] == "gauss" else L.MODEL_LAPLACE, Xd.dtype, Xd.device)
+        plan = DemixPlan(1, T_, F_, M_, K_, L.MODEL_LAPLACE, Xd.dtype, Xd.device)
         plan.load(Xd[None])
         plan.init(L.INIT_EYE)
         plan.iterate(20)
