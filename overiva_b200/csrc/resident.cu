@@ -23,7 +23,7 @@ constexpr size_t RES_MAX_SMEM = 232448;  // 227 KB: the per-CTA maximum of sm_10
 constexpr int RES_MAX_SG = 8;            // slices per bin group (keeps the partial-sum slots <= 64)
 
 struct ResidentChoice {
-    int SG, slice_cap, v_bufs, fw, stat_local;
+    int SG, slice_cap, v_bufs, fw;
     size_t smem;
 };
 
@@ -43,20 +43,13 @@ static bool resident_choose(int B, int T, int F, int M, int K, int dtype, int ma
     for (; SG >= 1; --SG) {
         if ((size_t)SG * fw * vg > scratch_bytes) continue;
         const int cap = (T + SG - 1) / SG;
-        const int Tp = oiva_frame_pitch(T), NG = oiva_bin_groups(F);
-        // few frames: every CTA reduces the statistic of its mixture itself (K * Tp doubles of shared memory, K * T * NG
-        // L2 loads per CTA) and the epoch needs one grid barrier instead of two
-        const bool want_local = (size_t)K * Tp * 8 <= 16384 && (long long)K * T * NG <= 40000;
-        for (int mode = want_local ? 0 : 2; mode < 4; ++mode) {  // (local, 2 V buffers) (local, 1) (exchange, 2) (exchange, 1)
-            const int local = mode < 2, vb = (mode & 1) ? 1 : 2;
-            if (K == M && M >= 3 && vb == 2) continue;  // the determined sweep uses all warps: a single V buffer
-            const ResSmem lay = res_smem_layout(M, K, cap, vb, esz, local ? K * Tp : 0);
+        for (int vb = (K == M && M >= 3) ? 1 : 2; vb >= 1; --vb) {  // (the determined sweep uses all warps: one V buffer)
+            const ResSmem lay = res_smem_layout(M, K, cap, vb, esz);
             if (lay.total <= RES_MAX_SMEM) {
                 out->SG = SG;
                 out->slice_cap = cap;
                 out->v_bufs = vb;
                 out->fw = fw;
-                out->stat_local = local;
                 out->smem = lay.total;
                 return true;
             }
@@ -111,7 +104,6 @@ extern "C" int oiva_loop_resident(const void* Xg, void* Wg, const void* Cg, doub
     p.F_total = n_freq_total > 0 ? n_freq_total : n_freq;
     p.slice_cap = ch.slice_cap;
     p.v_bufs = ch.v_bufs;
-    p.stat_local = ch.stat_local;
     p.invT = 1.0 / (double)n_frames;
     OIVA_CUDA_CHECK(cudaMemsetAsync(sync, 0, oiva_loop_resident_sync_bytes(n_batch, n_freq), st));
     const unsigned grid = (unsigned)(p.G * ch.SG);

@@ -8,9 +8,8 @@
 //   * every CTA owns one SLICE (bin group gi, frame range) and keeps its samples in SHARED MEMORY for the whole loop
 //     (one bulk-TMA copy at start; config 1: 15 MB over 130 SMs) -- X is never read from L2 / HBM again;
 //   * epoch = statistic of the slice (lane <-> bin, the same butterfly as k_demix_power) -> grid barrier -> the sum
-//     over the bin groups in k_source_model's order (few frames: by every CTA for its own mixture; many frames: pairs
-//     dealt to the CTAs, r exchanged through L2 and a second barrier) -> gamma, phi and the W scale for the slice's
-//     frames -> weighted covariance of the slice from shared memory (per-warp partial sums to an L2-resident scratch)
+//     over the bin groups in k_source_model's order ((k, t) pairs dealt to the CTAs, r exchanged through L2 and a
+//     second barrier) -> gamma, phi and the W scale for the slice's frames -> weighted covariance of the slice from shared memory (per-warp partial sums to an L2-resident scratch)
 //     -> the LAST CTA of a bin group to arrive adds the partial sums in a fixed order and runs the group's IP sweep
 //     with C, V_s and W_hat staged in shared memory so that the dependent chain never waits for L2 (K < M: thread per
 //     bin, exactly the arithmetic of k_ip_update_tpb; K = M: a lane group per bin over all 8 warps, the arithmetic of
@@ -44,8 +43,6 @@ struct ResidentParams {
     int B, SG, n_iter, model, F_total;
     int slice_cap;    // frames a slice can hold (= max over slices)
     int v_bufs;       // 1 or 2 shared-memory buffers for the reduced V_s
-    int stat_local;   // 1: every CTA sums the statistic partials of its mixture itself (one grid barrier per epoch instead of
-                      //    two); 0: the (k, t) pairs are dealt to the CTAs and exchanged through rbuf (many frames)
     double invT;
 };
 
@@ -146,10 +143,9 @@ struct ResCovDispatch {
 
 // shared-memory carve-up (host and device agree through this one function); offsets in bytes from the dynamic base
 struct ResSmem {
-    size_t x, phi, misc, c, v, w, r, total;
+    size_t x, phi, misc, c, v, w, total;
 };
-// r_doubles: K * Tp when the statistic is reduced locally (stat_local), else 0
-__host__ __device__ inline ResSmem res_smem_layout(int M, int K, int slice_cap, int v_bufs, int elem_bytes, int r_doubles) {
+__host__ __device__ inline ResSmem res_smem_layout(int M, int K, int slice_cap, int v_bufs, int elem_bytes) {
     ResSmem s;
     const size_t mat = (size_t)oiva_tri(M) * OIVA_GROUP * sizeof(cplx);
     size_t o = 128;  // [0]: mbarrier of the slice load
@@ -159,7 +155,6 @@ __host__ __device__ inline ResSmem res_smem_layout(int M, int K, int slice_cap, 
     s.c = o;    o += mat;
     s.v = o;    o += (size_t)v_bufs * mat;
     s.w = o;    o += (size_t)M * M * OIVA_GROUP * sizeof(cplx);
-    s.r = o;    o += (((size_t)r_doubles * sizeof(double)) + 127) / 128 * 128;
     s.total = o;
     return s;
 }
@@ -172,7 +167,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
     constexpr int NE = RC::NE;
     constexpr uint32_t MAT_ELEMS = NE * OIVA_GROUP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const ResSmem lay = res_smem_layout(M, K, p.slice_cap, p.v_bufs, (int)sizeof(XC), p.stat_local ? K * p.L.frame_pitch() : 0);
+    const ResSmem lay = res_smem_layout(M, K, p.slice_cap, p.v_bufs, (int)sizeof(XC));
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     XC* sX = reinterpret_cast<XC*>(smem_raw + lay.x);
     double* sPhi = reinterpret_cast<double*>(smem_raw + lay.phi);
@@ -182,7 +177,6 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
     cplx* sC = reinterpret_cast<cplx*>(smem_raw + lay.c);
     cplx* sV = reinterpret_cast<cplx*>(smem_raw + lay.v);
     cplx* sW = reinterpret_cast<cplx*>(smem_raw + lay.w);
-    double* sR = reinterpret_cast<double*>(smem_raw + lay.r);
 
     const GroupLayout& L = p.L;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -279,57 +273,10 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                 default: return 0.0;
             }
         };
-        if (p.stat_local) {
-            // few frames: every CTA adds up the partials of its own mixture (L2 reads, 4 items x NG/8 loads in flight
-            // per thread) -- no second grid barrier, no exchange of r
-            const int n_items = K * T * 8;  // item = (k * T + t) * 8 + slice
-            const double* base = p.r2part + (size_t)b * L.NG * K * Tp;
-            for (int i0 = 0; i0 < n_items; i0 += RES_THREADS * 4) {
-                double acc[4];
-                const double* src[4];
-                bool ok[4];
-                int kk[4], tt[4];
-                const int cs = tid & 7;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int item = i0 + u * RES_THREADS + tid;
-                    ok[u] = item < n_items;
-                    const int pair = (ok[u] ? item : 0) >> 3;
-                    kk[u] = pair / T;
-                    tt[u] = pair - kk[u] * T;
-                    src[u] = base + (size_t)kk[u] * Tp + tt[u];
-                    acc[u] = 0.0;
-                }
-                // all loads of a pass are issued before the first add (9 x 4 independent L2 loads per thread in flight:
-                // one L2 latency per 72 bin groups instead of one per load); the adds keep k_source_model's order, and
-                // adding +0.0 for a slot beyond NG changes nothing
-                constexpr int NJ = 9;
-                for (int ch0 = cs; ch0 < L.NG; ch0 += 8 * NJ) {
-                    double v[4][NJ];
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) {
-                        const int ch = ch0 + 8 * j;
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            v[u][j] = (ok[u] && ch < L.NG) ? __ldcg(src[u] + (size_t)ch * K * Tp) : 0.0;
-                    }
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j)
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) acc[u] += v[u][j];
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    double v = acc[u];
-                    v += __shfl_xor_sync(0xffffffffu, v, 1);
-                    v += __shfl_xor_sync(0xffffffffu, v, 2);
-                    v += __shfl_xor_sync(0xffffffffu, v, 4);
-                    if (ok[u] && cs == 0) sR[kk[u] * Tp + tt[u]] = model_fn(v);
-                }
-            }
-            __syncthreads();
-        } else {
-            // many frames: the (k, t) pairs are dealt round-robin to the CTAs, r goes through rbuf and a second barrier
+        {
+            // the (k, t) pairs are dealt round-robin to the CTAs, r goes through rbuf (L2) and a second grid barrier.
+            // (Every CTA summing all partials of its mixture itself -- one barrier less -- measured slower at config 1:
+            // 0.47 vs 0.41 ms per 20 epochs; the 130 CTAs re-read K * T * NG partials each, 8 of every 32-byte sector.)
             const long long n_pairs = (long long)p.B * K * T;
             const int sub = lane >> 3, cs = lane & 7;
             for (long long q0 = ((long long)blockIdx.x * RES_WARPS + warp) * 4; q0 < n_pairs;
@@ -356,7 +303,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
 
         // ---- (3) gamma = mean_t r, phi = 1 / max(r / gamma, 1e-15) for the slice's frames, W scale   overiva.py:158-173
         const double* rglob = p.rbuf + (size_t)b * K * Tp;
-        auto r_at = [&](int k, int t) { return p.stat_local ? sR[k * Tp + t] : __ldcg(rglob + (size_t)k * Tp + t); };
+        auto r_at = [&](int k, int t) { return __ldcg(rglob + (size_t)k * Tp + t); };
         if (warp < K) {
             double lsum = 0.0;
             for (int tt = 0; tt < Tp; tt += 128) {  // 4 loads in flight, added in ascending order (+0.0 beyond T)

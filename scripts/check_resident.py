@@ -56,7 +56,8 @@ for M, K, n_samples, frame in [(4, 2, 3000, 64), (2, 1, 900, 32), (6, 6, 20000, 
         assert nl == 1 and st == 0 and e < 1e-11, (nl, st, e)
 os.environ.pop("OIVA_NO_RESIDENT", None)
 for name, m, secs, kw in [("cfg1", 4, 15.0, dict(n_src=2, n_iter=20, model="laplace")),
-                          ("cfg2", 6, 15.0, dict(n_iter=20, model="laplace"))]:
+                          ("cfg2", 6, 15.0, dict(n_iter=20, model="laplace")),
+                          ("cfg3", 8, 60.0, dict(n_src=2, n_iter=20, model="gauss", init_eig=True))]:
     mix, _ = convolutive_mixture(900 + m, m, 2, duration=secs)
     Xn = stft(mix)
     Xd = torch.from_numpy(Xn).cuda()
@@ -81,7 +82,7 @@ for name, m, secs, kw in [("cfg1", 4, 15.0, dict(n_src=2, n_iter=20, model="lapl
         # the epoch loop alone
         T_, F_, M_ = Xn.shape
         K_ = kw.get("n_src") or M_
-        plan = DemixPlan(1, T_, F_, M_, K_, L.MODEL_LAPLACE, Xd.dtype, Xd.device)
+        plan = DemixPlan(1, T_, F_, M_, K_, L.MODEL_GAUSS if kw["model"] == "gauss" else L.MODEL_LAPLACE, Xd.dtype, Xd.device)
         plan.load(Xd[None])
         plan.init(L.INIT_EYE)
         plan.iterate(20)

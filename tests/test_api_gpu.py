@@ -82,7 +82,7 @@ def test_baseline_configs_full_bins(cfg, loop_path):
         kw = dict(n_iter=20, model="laplace")
     else:  # overiva M=8 K=2 gauss init_eig, the full 60 s mixture of BASELINE config 3 (T = 467)
         if loop_path == "resident":
-            pytest.skip("config 3 does not fit the resident loop: one path only")
+            pytest.skip("config 3 does not fit the resident loop (122 MB of samples): one path only")
         mix, _ = convolutive_mixture(103, 8, 2, duration=60.0)
         kw = dict(n_src=2, n_iter=20, model="gauss", init_eig=True)
     X = stft(mix)
