@@ -3,8 +3,9 @@
 TEST / BENCH INFRASTRUCTURE ONLY.  The reference (onolab-tmu/overiva) is three pure-Python files; ``/root/reference``
 exists in the build container but not on the GPU box, and reference SOURCES must never be copied into this repository.
 So, exactly like a C reference would be compiled into ``oracle/_ref/*.so``, the Python reference is compiled -- from
-the sources where they lie, nothing is copied -- into CPython bytecode files ``oracle/_ref/<module>.pyc`` (build outputs:
-git-ignored, they travel to the GPU box with the snapshot like the built ``.so``).  ``oracle/reference_shim.py`` imports
+the sources where they lie, nothing is copied -- into CPython bytecode files ``oracle/_ref/<module>.refbc`` (a ``.pyc`` image under
+another extension: snapshot tools commonly drop ``*.pyc``; build outputs: git-ignored, they travel to the GPU box with
+the snapshot like the built ``.so``).  ``oracle/reference_shim.py`` imports
 the bytecode when the source tree is absent, so that ``bench.py --impl reference`` and ``cpu_baseline`` time the REAL
 reference implementation (``kind: "reference"``) on the box's host cores.
 
@@ -24,10 +25,10 @@ MODULES = ("overiva", "auxiva_pca", "ive")  # the three files on the hot path (S
 def build(reference_dir="/root/reference") -> bool:
     """Returns True when oracle/_ref/ holds bytecode of all three modules for this interpreter."""
     if not os.path.isfile(os.path.join(reference_dir, "overiva.py")):
-        return all(os.path.isfile(os.path.join(REF_OUT, m + ".pyc")) for m in MODULES)
+        return all(os.path.isfile(os.path.join(REF_OUT, m + ".refbc")) for m in MODULES)
     os.makedirs(REF_OUT, exist_ok=True)
     for m in MODULES:
-        py_compile.compile(os.path.join(reference_dir, m + ".py"), cfile=os.path.join(REF_OUT, m + ".pyc"),
+        py_compile.compile(os.path.join(reference_dir, m + ".py"), cfile=os.path.join(REF_OUT, m + ".refbc"),
                            dfile="<reference>/%s.py" % m, doraise=True, optimize=0,
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
     with open(os.path.join(REF_OUT, "BUILT_WITH"), "w") as f:

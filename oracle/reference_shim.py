@@ -12,7 +12,7 @@ as-is in this image:
 
 The reference tree stays read-only and no source is copied from it.  ``/root/reference`` does
 not exist on the GPU box; ``oracle/build_ref.py`` byte-compiles the three modules into the
-git-ignored ``oracle/_ref/*.pyc`` (a build output, like a compiled C reference), which travels
+git-ignored ``oracle/_ref/*.refbc`` (a build output, like a compiled C reference), which travels
 with the snapshot and is imported here when the source tree is absent.  ``available()`` says
 whether the real implementation can be used (``source()`` tells which form).
 """
@@ -34,16 +34,28 @@ _modules = {}
 
 
 def source():
-    """'tree' (the .py files under REFERENCE_DIR), 'compiled' (oracle/_ref/*.pyc built from them) or None."""
+    """'tree' (the .py files under REFERENCE_DIR), 'compiled' (oracle/_ref/*.refbc built from them) or None."""
     if os.path.isfile(os.path.join(REFERENCE_DIR, "overiva.py")):
         return "tree"
-    if all(os.path.isfile(os.path.join(COMPILED_DIR, m + ".pyc")) for m in ("overiva", "auxiva_pca", "ive")):
+    if all(os.path.isfile(os.path.join(COMPILED_DIR, m + ".refbc")) for m in ("overiva", "auxiva_pca", "ive")):
         return "compiled"
     return None
 
 
 def available() -> bool:
     return source() is not None
+
+
+class _BytecodeLoader(importlib.machinery.SourcelessFileLoader):
+    """SourcelessFileLoader for a .pyc image stored under another extension."""
+
+    def get_code(self, fullname):
+        import marshal
+
+        data = self.get_data(self.get_filename(fullname))
+        if data[:4] != importlib.util.MAGIC_NUMBER:
+            raise ImportError("%s was compiled by another Python version; rebuild oracle/_ref" % self.path)
+        return marshal.loads(data[16:])
 
 
 def _install_pra_stub():
@@ -97,8 +109,8 @@ def _load(name):
         path = os.path.join(REFERENCE_DIR, name + ".py")
         spec = importlib.util.spec_from_file_location("_reference_" + name, path)
     else:
-        path = os.path.join(COMPILED_DIR, name + ".pyc")
-        loader = importlib.machinery.SourcelessFileLoader("_reference_" + name, path)
+        path = os.path.join(COMPILED_DIR, name + ".refbc")  # a .pyc image (oracle/build_ref.py)
+        loader = _BytecodeLoader("_reference_" + name, path)
         spec = importlib.util.spec_from_loader("_reference_" + name, loader, origin=path)
     mod = importlib.util.module_from_spec(spec)
     if name == "auxiva_pca":
