@@ -147,12 +147,29 @@ int oiva_source_model(const double* r2part, int n_chunks, double* phi, double* w
 int oiva_ip_update(void* Wg, const void* Vg, const void* C, const void* Cg, const double* wscale, int* status,
                    int n_batch, int n_freq, int n_chan, int n_src, void* stream);
 
+/* oiva_weighted_cov + oiva_ip_update in ONE kernel: the pass over X that accumulates V_1..V_K of a bin ends, per bin
+ * group, in the thread-per-bin sweep of that group with the covariances still in registers (Vg is never written or
+ * re-read).  Wg is bit-identical to the two-call sequence.  Covered: M <= 8 with all K lower triangles in one lane's
+ * registers and K <= 3 ((M <= 5, K <= min(M, 3)), (6, K <= 2), (7 | 8, 1)) and n_batch * ceil(F/32) >= 4096 bin groups (no
+ * frame splitting); otherwise OIVA_ERR_UNSUPPORTED is returned, nothing is launched and no error text is set -- run the
+ * two calls instead.  Arguments as for those two calls.
+ * replaces: overiva.py:161-167 and :176-190 (the whole source loop of an epoch). */
+int oiva_cov_ip_update(const void* Xg, const double* phi, void* Wg, const void* Cg, const double* wscale, int* status,
+                       int n_batch, int n_frames, int n_freq, int n_chan, int n_src, int dtype, void* stream);
+
 /* Build What (R,M,M): W from eye / eigenvectors / W0, then J and the -I block.
  * evecs: (R,M,M) from oiva_eigh (ascending; used when mode == OIVA_INIT_EIG: w_k = conj(v_{M-K+k})).
  * W0: (R,M,K) c128 (mode == OIVA_INIT_W0).  status: n_rows / rows_per_mixture words (row r reports to word
  * r / rows_per_mixture).                                      replaces: overiva.py:89-123 */
 int oiva_init_demix(void* What, const void* C, const void* W0, const void* evecs, int mode, int* status,
                     int n_rows, int rows_per_mixture, int n_chan, int n_src, void* stream);
+
+/* The same for the identity / W0 initialisations, written straight into the GROUPED layout Wg[gi][M*M][32] by one
+ * thread per bin from the grouped covariance Cg (W0: (R,M,K) c128 or NULL = identity; status: n_batch words).
+ * OIVA_ERR_UNSUPPORTED (nothing launched, no error text) outside the thread-per-bin shapes (M <= 6, and M = 7, 8 with
+ * K <= 4): use oiva_init_demix + oiva_group_rows there. */
+int oiva_init_demix_grouped(void* Wg, const void* Cg, const void* W0, int* status, int n_batch, int n_freq, int n_chan,
+                            int n_src, void* stream);
 
 /* Hermitian eigendecomposition per row (cyclic Jacobi, fp64): evals (R,M) ascending, evecs (R,M,M) with
  * eigenvectors in columns.  lapack_phase != 0 rotates each eigenvector so that its largest-magnitude
@@ -171,6 +188,14 @@ int oiva_projback_filters(const void* W, int w_cols, const void* C, void* Weff, 
 /* Y (B,T,F,K) interleaved complex (dtype) = Weff^H x, Weff (R,M,K) c128.   replaces: overiva.py:192-199 */
 int oiva_demix_output(const void* Xg, const void* Weff, void* Y, int n_batch, int n_frames, int n_freq,
                       int n_chan, int n_src, int dtype, void* stream);
+
+/* The same straight from the loop's grouped state: Wg = the grouped W_hat [gi][M*M][32] (columns :K are the filters).
+ * With Cg (grouped lower-triangle input covariance) the projection-back scale z_k of oiva_projback_filters is computed
+ * per bin and folded into the filters (same arithmetic and order); Cg == NULL: no projection back.  M <= 8: inside the
+ * output kernel, one launch for overiva.py:192-199.  M >= 9: a small kernel writes the scales to zscratch
+ * (n_batch * ceil(F/32) * n_src * 32 c128, device memory, required then) first. */
+int oiva_demix_output_grouped(const void* Xg, const void* Wg, const void* Cg, void* zscratch, void* Y, int n_batch,
+                              int n_frames, int n_freq, int n_chan, int n_src, int dtype, void* stream);
 
 /* Xr = grouped samples (K channels) of E_K^H x with E_K (R,M,K) c128 -- the PCA projection of
  * auxiva_pca.py:79-81 written directly in the layout the loop streams. */

@@ -57,10 +57,13 @@ SIGNATURES = {
     "oiva_sum_partials": (_i, [_p, _i, _p, _i, _i, _i, _p]),
     "oiva_source_model": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
     "oiva_ip_update": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "oiva_cov_ip_update": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "oiva_init_demix": (_i, [_p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _p]),
+    "oiva_init_demix_grouped": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "oiva_eigh": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "oiva_projback_filters": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _p]),
     "oiva_demix_output": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "oiva_demix_output_grouped": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "oiva_project_rows": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "oiva_compose_filters": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "oiva_ogive_update": (_i, [_p, _p, _p, _p, _p, _p, _p, _d, _p, _i, _i, _p]),

@@ -12,6 +12,7 @@ namespace oiva {
     int cov_launch_m##M(int dtype, int KC, const CovParams& p, cudaStream_t st, int* nsplit_out); \
     int cov_max_kc_m##M();                                                                                     \
     int cov_launch_tiled_m##M(int dtype, const CovParams& p, cudaStream_t st, int* nsplit_out);                \
+    int cov_sweep_launch_m##M(int dtype, int K, const CovParams& p, cudaStream_t st);                          \
     int relayout_cov_launch_m##M(int dtype, RelayoutCovParams p, int max_split, cudaStream_t st, int* nsplit_out);
 OIVA_DECL(1) OIVA_DECL(2) OIVA_DECL(3) OIVA_DECL(4) OIVA_DECL(5) OIVA_DECL(6) OIVA_DECL(7) OIVA_DECL(8)
 OIVA_DECL(9) OIVA_DECL(10) OIVA_DECL(11) OIVA_DECL(12) OIVA_DECL(13) OIVA_DECL(14) OIVA_DECL(15) OIVA_DECL(16)
@@ -109,6 +110,10 @@ extern "C" int oiva_weighted_cov_ws(const void* Xg, const double* phi, void* Vg,
     const size_t vg_bytes = oiva_grouped_cov_bytes(n_batch, n_freq, n_chan, n_src);
     p.Vpart = nullptr;
     p.max_split = 1;
+    p.Wg = nullptr;
+    p.Cg = nullptr;
+    p.wscale = nullptr;
+    p.status = nullptr;
     if (scratch && scratch_bytes >= 2 * vg_bytes) {
         p.Vpart = (cplx*)scratch;
         const size_t slots = scratch_bytes / vg_bytes;
@@ -172,6 +177,46 @@ extern "C" int oiva_weighted_cov_ws(const void* Xg, const double* phi, void* Vg,
         OIVA_LAUNCH_CHECK();
     }
     return OIVA_OK;
+}
+
+// One pass over X that ends, per bin group, in the IP sweep of that group (cov_sweep.cuh).  Covers the shapes whose K
+// lower triangles fit one lane's registers and inputs with enough bin groups that no group is split over teams;
+// everything else returns OIVA_ERR_UNSUPPORTED (no error text) and the caller runs oiva_weighted_cov + oiva_ip_update.
+extern "C" int oiva_cov_ip_update(const void* Xg, const double* phi, void* Wg, const void* Cg, const double* wscale,
+                                  int* status, int n_batch, int n_frames, int n_freq, int n_chan, int n_src, int dtype,
+                                  void* stream) {
+    using namespace oiva;
+    OIVA_REQUIRE(Xg && phi && Wg && Cg && status, "oiva_cov_ip_update: null pointer");
+    OIVA_REQUIRE(n_batch > 0 && n_frames > 0 && n_freq > 0 && n_chan >= 1 && n_chan <= OIVA_MAX_M && n_src >= 1 &&
+                     n_src <= n_chan,
+                 "oiva_cov_ip_update: bad shape B=%d T=%d F=%d M=%d K=%d", n_batch, n_frames, n_freq, n_chan, n_src);
+    OIVA_REQUIRE(dtype == OIVA_C64 || dtype == OIVA_C128, "oiva_cov_ip_update: bad dtype %d", dtype);
+    CovParams p;
+    p.Xg = Xg;
+    p.phi = phi;
+    p.Vg = nullptr;
+    p.Vpart = nullptr;
+    p.L = oiva_make_layout(n_frames, n_freq, n_chan);
+    p.G = (long long)n_batch * p.L.NG;
+    p.NGphi = p.L.NG;
+    p.K = n_src;
+    p.k0 = 0;
+    p.nsplit = 1;
+    p.max_split = 1;
+    p.stages = 2;
+    p.invT = 1.0 / (double)n_frames;
+    p.Wg = (cplx*)Wg;
+    p.Cg = (const cplx*)Cg;
+    p.wscale = wscale;
+    p.status = status;
+    if (n_chan > 8 || p.G < 4096) return OIVA_ERR_UNSUPPORTED;  // (few groups: the frames of a group are split)
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (n_chan) {
+#define OIVA_CASE(M) case M: return cov_sweep_launch_m##M(dtype, n_src, p, st);
+        OIVA_CASE(1) OIVA_CASE(2) OIVA_CASE(3) OIVA_CASE(4) OIVA_CASE(5) OIVA_CASE(6) OIVA_CASE(7) OIVA_CASE(8)
+#undef OIVA_CASE
+    }
+    return OIVA_ERR_UNSUPPORTED;
 }
 
 extern "C" int oiva_weighted_cov(const void* Xg, const double* phi, void* Vg, int n_batch, int n_frames, int n_freq,

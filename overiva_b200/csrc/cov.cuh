@@ -74,7 +74,16 @@ struct CovParams {
     int max_split;       // largest split count the scratch buffer has slots for
     int stages;          // ring depth S
     double invT;
+    // fused covariance + IP sweep (cov_sweep.cuh): the loop state the epilogue of a group updates.  Unused otherwise.
+    cplx* Wg;              // (G, M*M, 32) grouped W_hat
+    const cplx* Cg;        // (G, NE, 32) grouped input covariance
+    const double* wscale;  // (B, K) or nullptr
+    int* status;           // (B) per-mixture status words
 };
+
+// epilogue of a group in cov_team_body: by default the lane's entries go to Vg (CovPart::finish); the fused kernel
+// passes a policy whose run() consumes the accumulators in registers instead
+struct CovStoreEpilogue {};
 
 template <typename ST, int M, int KC, int P, int PART>
 struct CovPart {
@@ -82,7 +91,7 @@ struct CovPart {
     static constexpr int NE = oiva_tri(M);
     static constexpr int NEP = (NE + P - 1) / P;
     static constexpr int NACC = NEP;
-    static constexpr int TC = cov_chunk_frames(M);
+    static constexpr int TC = cov_chunk_frames(M);  // frames per ring stage
 
     // accumulate `nfr` (<= TC) frames of a staged chunk: xs = [TC][M][32] complex, ph = [KC][TC]
     __device__ static __forceinline__ void accumulate(cplx (&acc)[NEP][KC], const XC* __restrict__ xs,
@@ -149,7 +158,7 @@ struct CovPart {
 // The body run by one warp of a team for its compile-time part.
 // Units of work: (group, frame split); a team owns the contiguous unit range [u_begin, u_end).  All
 // producer / consumer cursors are advanced incrementally (no divisions in the per-chunk path).
-template <typename CP, typename ST, int M, int KC>
+template <typename CP, typename ST, int M, int KC, typename EP = CovStoreEpilogue>
 __device__ __forceinline__ void cov_team_body(const CovParams& p, unsigned char* team_smem, long long team_global,
                                               long long n_teams_total, int lane, bool is_leader_warp, int part) {
     typedef typename CP::XC XC;
@@ -243,6 +252,10 @@ __device__ __forceinline__ void cov_team_body(const CovParams& p, unsigned char*
                 cstage = 0;
                 cphase ^= 1;
             }
+        }
+        if constexpr (!std::is_same<EP, CovStoreEpilogue>::value) {
+            EP::run(acc, p, gi, lane);  // (launched with nsplit == 1 only)
+            continue;
         }
         const size_t grp_elems = (size_t)p.K * CP::NE * OIVA_GROUP;
         if (nsplit > 1 && p.Vpart)  // this split's own slot, summed in a fixed order by k_cov_sum_partials

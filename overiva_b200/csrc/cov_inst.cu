@@ -5,6 +5,7 @@
 #include <stdlib.h>
 
 #include "cov.cuh"
+#include "cov_sweep.cuh"
 #include "relayout_cov.cuh"
 
 #ifndef OIVA_COV_M
@@ -179,6 +180,39 @@ int OIVA_CAT(cov_launch_m, OIVA_COV_M)(int dtype, int KC, const CovParams& p, cu
     }
     oiva_set_error("cov_launch: unsupported source chunk %d", KC);
     return OIVA_ERR_INVALID;
+}
+
+// fused covariance + IP sweep (cov_sweep.cuh): single-warp teams, all K sources, no frame splits (many groups)
+// (ring shape: measured at the bench shape with 2-frame stages x 4 and x 3, and 4-frame stages x 3 with fewer teams:
+// 93.8 / 92.4 / 102.5 ms per step against 89.2 ms for the 4 frames x 2 stages x 8 teams of k_cov -- kept)
+template <typename ST, int K>
+static int launch_sweep(CovParams p, cudaStream_t st) {
+    constexpr int M = OIVA_COV_M;
+    if constexpr (!cov_sweep_supported(M, K)) {
+        return OIVA_ERR_UNSUPPORTED;
+    } else {
+        typedef typename StoreC<ST>::type XC;
+        constexpr int TC = cov_chunk_frames(M);
+        constexpr size_t x_stage = (size_t)TC * M * OIVA_GROUP * sizeof(XC);
+        constexpr size_t stage_bytes = ((x_stage + (size_t)K * TC * sizeof(double) + 127) / 128) * 128;
+        auto kern = k_cov_sweep<ST, M, K>;
+        static OivaPerDeviceOnce attr_done;
+        p.nsplit = 1;
+        return launch_common(kern, p, st, 1, cov_teams_per_cta(1), stage_bytes, TC, M, K, attr_done, nullptr,
+                             [&](const CovParams& q, unsigned grid, int threads, size_t smem, int teams,
+                                 int team_smem) { kern<<<grid, threads, smem, st>>>(q, teams, team_smem); });
+    }
+}
+
+// OIVA_ERR_UNSUPPORTED (no error text) when (M, K) is not covered
+int OIVA_CAT(cov_sweep_launch_m, OIVA_COV_M)(int dtype, int K, const CovParams& p, cudaStream_t st) {
+#define OIVA_SWEEP_CASE(K_) \
+    if (K == K_) return dtype == OIVA_C64 ? launch_sweep<float, K_>(p, st) : launch_sweep<double, K_>(p, st);
+    OIVA_SWEEP_CASE(1)
+    OIVA_SWEEP_CASE(2)
+    OIVA_SWEEP_CASE(3)
+#undef OIVA_SWEEP_CASE
+    return OIVA_ERR_UNSUPPORTED;
 }
 
 // tiled kernel (cov.cuh: k_cov_tiled): M >= 9, chunks of 4 sources, clusters of two CTAs (the two halves of the tiles)

@@ -32,6 +32,8 @@ struct oiva_plan {
     unsigned char* ws;
     long long launches;
     bool loaded, inited;
+    bool c_full;  // the row-major copy C (R,M,M) of the input covariance is up to date (oiva_plan_run skips it when
+                  // nothing on its path reads it: the thread-per-bin kernels work on the grouped Cg)
     bool timing;
     std::vector<TimedSpan>* spans;
     std::vector<cudaEvent_t>* pool;
@@ -69,6 +71,13 @@ struct SpanGuard {  // records an event pair around a launch sequence when timin
                 return;
             }
             cudaEventRecord(sp.a, st);
+        }
+    }
+    void cancel() {  // nothing was launched: hand the events back
+        if (on) {
+            p->pool->push_back(sp.a);
+            p->pool->push_back(sp.b);
+            on = false;
         }
     }
     ~SpanGuard() {
@@ -116,7 +125,7 @@ extern "C" int oiva_plan_create(oiva_plan_t** out, const oiva_plan_desc* desc) {
     p->off_wg = o;      o += align_up(G * M * M * OIVA_GROUP * 16);  // the loop's W_hat, grouped
     // grouped covariances of the K sources; also scratch for the eigenvectors at init time
     p->off_vg = o;      o += align_up(max_sz(G * K * oiva_tri((int)M) * OIVA_GROUP * 16, R * M * M * 16));
-    p->off_weff = o;    o += align_up(R * M * K * 16);
+    p->off_weff = o;    o += align_up(max_sz(R * M * K, G * K * OIVA_GROUP) * 16);  // (also the z scratch of the output)
     p->off_r2part = o;  o += align_up(B * p->NG * K * p->Tp * 8);
     p->off_r2 = o;      o += align_up(B * K * p->Tp * 8);
     p->off_phi = o;     o += align_up(B * K * p->Tp * 8);
@@ -220,18 +229,45 @@ extern "C" size_t oiva_plan_r2_elems(const oiva_plan_t* p) {
 extern "C" long long oiva_plan_launch_count(const oiva_plan_t* p) { return p ? p->launches : 0; }
 
 // input covariance C = (1/T) sum_t x x^H (overiva.py:87): grouped accumulation, then full row-major matrices
+static bool plan_force_rowowner() {  // (read per call: the tests run both solver families in one process)
+    const char* env = getenv("OIVA_SOLVER_ROWOWNER");
+    return env && *env && *env != '0';
+}
+// the shapes whose init / sweep / output run thread-per-bin on the grouped arrays only (solve_tpb.cu's instantiations)
+static bool plan_tpb_shape(const oiva_plan_t* p) {
+    const int M = p->d.n_chan, K = p->d.n_src;
+    return !plan_force_rowowner() && (M <= 6 || (M <= 8 && K <= 4));
+}
+
+// full row-major matrices C (R,M,M) from the grouped lower triangles (needed by the eigendecomposition, the row-owner
+// kernels and callers of oiva_plan_cov)
+static int plan_full_cov(oiva_plan_t* p, void* stream) {
+    if (p->c_full) return OIVA_OK;
+    const oiva_plan_desc& d = p->d;
+    int rc = oiva_unpack_cov(p->ws + p->off_cg, p->ws + p->off_c, d.n_batch, d.n_freq, d.n_chan, 1, stream);
+    if (rc) return rc;
+    p->launches += 1;
+    p->c_full = true;
+    return OIVA_OK;
+}
+
 static int plan_input_cov(oiva_plan_t* p, void* stream) {
     const oiva_plan_desc& d = p->d;
     int rc = oiva_weighted_cov_ws(p->ws + p->off_xg, nullptr, p->ws + p->off_cg, p->covws_bytes ? p->ws + p->off_covws : nullptr,
                                   p->covws_bytes, d.n_batch, d.n_frames, d.n_freq, d.n_chan, 1, d.dtype, stream);
     if (rc) return rc;
-    rc = oiva_unpack_cov(p->ws + p->off_cg, p->ws + p->off_c, d.n_batch, d.n_freq, d.n_chan, 1, stream);
-    if (rc) return rc;
-    p->launches += 2;
-    return OIVA_OK;
+    p->launches += 1;
+    p->c_full = false;
+    return plan_full_cov(p, stream);
 }
 
+static int plan_load_impl(oiva_plan_t* p, const void* X, void* stream, bool full_c);
+
 extern "C" int oiva_plan_load(oiva_plan_t* p, const void* X, void* stream) {
+    return plan_load_impl(p, X, stream, true);
+}
+
+static int plan_load_impl(oiva_plan_t* p, const void* X, void* stream, bool full_c) {
     PLAN_READY(p, "oiva_plan_load");
     OIVA_REQUIRE(X, "oiva_plan_load: null X");
     const oiva_plan_desc& d = p->d;
@@ -245,9 +281,12 @@ extern "C" int oiva_plan_load(oiva_plan_t* p, const void* X, void* stream) {
         rc = oiva_relayout_cov(X, p->ws + p->off_xg, p->ws + p->off_cg, p->covws_bytes ? p->ws + p->off_covws : nullptr,
                                p->covws_bytes, d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.dtype, stream);
         if (rc) return rc;
-        rc = oiva_unpack_cov(p->ws + p->off_cg, p->ws + p->off_c, d.n_batch, d.n_freq, d.n_chan, 1, stream);
-        if (rc) return rc;
-        p->launches += 2;
+        p->launches += 1;
+        p->c_full = false;
+        if (full_c) {
+            rc = plan_full_cov(p, stream);
+            if (rc) return rc;
+        }
     } else {
         rc = oiva_relayout(X, p->ws + p->off_xg, d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.dtype, stream);
         if (rc) return rc;
@@ -278,6 +317,22 @@ extern "C" int oiva_plan_init(oiva_plan_t* p, int mode, const void* W0, void* st
     const oiva_plan_desc& d = p->d;
     int* status = (int*)(p->ws + p->off_status);
     const void* evecs = nullptr;
+    if (mode != OIVA_INIT_EIG && !plan_force_rowowner()) {
+        // identity / W0: one thread-per-bin kernel writes the grouped W_hat directly (solve_tpb.cuh)
+        OIVA_REQUIRE(mode != OIVA_INIT_W0 || W0, "oiva_plan_init: W0 missing");
+        const int rc = oiva_init_demix_grouped(p->ws + p->off_wg, p->ws + p->off_cg, mode == OIVA_INIT_W0 ? W0 : nullptr,
+                                               status, d.n_batch, d.n_freq, d.n_chan, d.n_src, stream);
+        if (rc == OIVA_OK) {
+            p->launches += 1;
+            p->inited = true;
+            return OIVA_OK;
+        }
+        if (rc != OIVA_ERR_UNSUPPORTED) return rc;
+    }
+    {
+        const int rc = plan_full_cov(p, stream);  // (everything below reads the row-major C)
+        if (rc) return rc;
+    }
     if (mode == OIVA_INIT_EIG) {
         // principal eigenvectors of C with np.linalg.eig's phase convention            overiva.py:103-109
         int rc = oiva_eigh(p->ws + p->off_c, (double*)(p->ws + p->off_evals), p->ws + p->off_vg, status, (int)p->R,
@@ -323,11 +378,31 @@ static int plan_update_from(oiva_plan_t* p, const double* r2src, int nch, void* 
                                stream);
     if (rc) return rc;
     {
+        // one kernel for covariance + sweep where the covariances of a bin fit its lane's registers (cov_sweep.cuh)
+        const char* off = getenv("OIVA_NO_COV_SWEEP");  // (read per call: the tests compare both paths in one process)
+        if (!(off && *off && *off != '0')) {
+            SpanGuard g(p, TK_COV, stream);
+            rc = oiva_cov_ip_update(p->ws + p->off_xg, phi, p->ws + p->off_wg, p->ws + p->off_cg, wscale,
+                                    (int*)(p->ws + p->off_status), d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.n_src,
+                                    d.dtype, stream);
+            if (rc == OIVA_OK) {
+                p->launches += 2;  // source model + the fused kernel
+                return rc;
+            }
+            g.cancel();
+            if (rc != OIVA_ERR_UNSUPPORTED) return rc;
+        }
+    }
+    {
         SpanGuard g(p, TK_COV, stream);
         rc = oiva_weighted_cov_ws(p->ws + p->off_xg, phi, p->ws + p->off_vg, p->covws_bytes ? p->ws + p->off_covws : nullptr,
                                   p->covws_bytes, d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.n_src, d.dtype, stream);
     }
     if (rc) return rc;
+    if (!plan_tpb_shape(p)) {
+        rc = plan_full_cov(p, stream);  // the row-owner sweep reads the row-major C
+        if (rc) return rc;
+    }
     {
         SpanGuard g(p, TK_SOLVE, stream);
         rc = oiva_ip_update(p->ws + p->off_wg, p->ws + p->off_vg, p->ws + p->off_c, p->ws + p->off_cg, wscale,
@@ -396,6 +471,10 @@ static int plan_iterate_resident(oiva_plan_t* p, int n_iter, void* stream) {
 extern "C" int oiva_plan_iterate(oiva_plan_t* p, int n_iter, void* stream) {
     PLAN_INITED(p, "oiva_plan_iterate");
     if (n_iter <= 0) return OIVA_OK;
+    if (!plan_tpb_shape(p)) {  // (before any graph capture: the row-owner sweep reads the row-major C)
+        const int rc = plan_full_cov(p, stream);
+        if (rc) return rc;
+    }
     {
         const int rc = plan_iterate_resident(p, n_iter, stream);
         if (rc != OIVA_ERR_UNSUPPORTED) return rc;
@@ -458,15 +537,12 @@ extern "C" int oiva_plan_output(oiva_plan_t* p, int proj_back, void* Y, void* st
     PLAN_INITED(p, "oiva_plan_output");
     OIVA_REQUIRE(Y, "oiva_plan_output: null Y");
     const oiva_plan_desc& d = p->d;
-    int rc = plan_sync_what(p, stream);
+    // one launch: the filters come from the grouped W_hat, the projection-back scale from the grouped C, per lane
+    // (off_weff doubles as the scratch of the projection-back scales for M >= 9)
+    int rc = oiva_demix_output_grouped(p->ws + p->off_xg, p->ws + p->off_wg, proj_back ? p->ws + p->off_cg : nullptr,
+                                       p->ws + p->off_weff, Y, d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.n_src, d.dtype, stream);
     if (rc) return rc;
-    rc = oiva_projback_filters(p->ws + p->off_what, d.n_chan, p->ws + p->off_c, p->ws + p->off_weff, (int)p->R,
-                                   d.n_chan, d.n_src, proj_back, stream);
-    if (rc) return rc;
-    rc = oiva_demix_output(p->ws + p->off_xg, p->ws + p->off_weff, Y, d.n_batch, d.n_frames, d.n_freq, d.n_chan,
-                           d.n_src, d.dtype, stream);
-    if (rc) return rc;
-    p->launches += 2;
+    p->launches += 1;
     return OIVA_OK;
 }
 
@@ -474,7 +550,8 @@ extern "C" int oiva_plan_output(oiva_plan_t* p, int proj_back, void* Y, void* st
 // language (five ctypes round trips from Python) is of the order of the GPU work itself
 extern "C" int oiva_plan_run(oiva_plan_t* p, const void* X, int init_mode, const void* W0, int n_iter, int proj_back,
                              void* Y, void* W, void* stream) {
-    int rc = oiva_plan_load(p, X, stream);
+    // (the row-major copy of C is only produced when something on the path reads it)
+    int rc = plan_load_impl(p, X, stream, false);
     if (rc) return rc;
     rc = oiva_plan_init(p, init_mode, W0, stream);
     if (rc) return rc;

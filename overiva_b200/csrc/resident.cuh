@@ -63,15 +63,24 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// all CTAs of the (cooperative, co-resident) grid; `target` = gridDim.x * (number of barriers so far)
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned atom_acq_rel_add_u32(unsigned* p, unsigned v) {
+    unsigned old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+// all CTAs of the (cooperative, co-resident) grid; `target` = gridDim.x * (number of barriers so far).
+// One release-add and an acquire spin by thread 0 between two CTA barriers: the CTA barrier orders the other threads'
+// writes before thread 0's release and thread 0's acquire before their later reads (causality order is cumulative), so
+// no separate __threadfence() is needed (the first version had two per barrier: MEMBAR.SC.GPU at 3.3 us per barrier).
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
+        red_release_add_u32(counter, 1u);
         while (ld_acquire_u32(counter) < target) {
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -342,16 +351,14 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
             ResCovDispatch<ST, M, K, RC::P>::run(part, sX, sPhi, pitch, f0, f1, dst, p.invT, lane);
         }
         __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            const unsigned old = atomicAdd(arrive, 1u);
+        if (tid == 0) {  // (acq_rel: publishes this CTA's partial sums, and the last arriver sees everybody else's)
+            const unsigned old = atom_acq_rel_add_u32(arrive, 1u);
             sFlag[0] = (old == (unsigned)(p.SG * (epoch + 1) - 1)) ? 1 : 0;
         }
         __syncthreads();
 
         if (sFlag[0]) {
             // ---- (5) last CTA of the group: fixed-order sum of the partial covariances + the IP sweep   overiva.py:176-190
-            __threadfence();
             const int n_slots = p.SG * RC::FW;
             // (the slots are added in ascending order, as k_cov_sum_partials does; the loads of 8 slots are issued
             // before the first add -- one L2 latency per 8 slots instead of one per slot: ncu showed the other CTAs of
@@ -475,15 +482,11 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
             __syncthreads();
             for (uint32_t i = tid; i < (uint32_t)(M * M * OIVA_GROUP); i += RES_THREADS) __stcg(Wgrp + i, sW[i]);
             __syncthreads();
-            if (tid == 0) {
-                __threadfence();
-                st_release_u32(flag, (unsigned)(epoch + 1));
-            }
+            if (tid == 0) st_release_u32(flag, (unsigned)(epoch + 1));
         } else {
             if (tid == 0) {
                 while (ld_acquire_u32(flag) < (unsigned)(epoch + 1)) {
                 }
-                __threadfence();
             }
             __syncthreads();
         }

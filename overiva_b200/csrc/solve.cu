@@ -340,6 +340,23 @@ extern "C" int oiva_ip_update(void* What, const void* V, const void* C, const vo
     return OIVA_OK;
 }
 
+namespace oiva {
+int init_demix_tpb(int M, int K, cplx* Wg, const cplx* Cg, const cplx* W0, int* status, int F, int NG, long long G,
+                   cudaStream_t st);
+}
+
+// initial W_hat (identity or W0) written straight into the grouped layout by one thread per bin; OIVA_ERR_UNSUPPORTED
+// (nothing launched, no error text) for the shapes the thread-per-bin kernels do not cover
+extern "C" int oiva_init_demix_grouped(void* Wg, const void* Cg, const void* W0, int* status, int n_batch, int n_freq,
+                                       int n_chan, int n_src, void* stream) {
+    OIVA_REQUIRE(Wg && Cg && status, "oiva_init_demix_grouped: null pointer");
+    OIVA_REQUIRE(n_batch > 0 && n_freq > 0 && n_src >= 1 && n_src <= n_chan, "oiva_init_demix_grouped: bad shape");
+    if (n_chan > 8) return OIVA_ERR_UNSUPPORTED;
+    const int NG = oiva_bin_groups(n_freq);
+    return init_demix_tpb(n_chan, n_src, (cplx*)Wg, (const cplx*)Cg, (const cplx*)W0, status, n_freq, NG,
+                          (long long)n_batch * NG, (cudaStream_t)stream);
+}
+
 extern "C" int oiva_init_demix(void* What, const void* C, const void* W0, const void* evecs, int mode, int* status,
                                int n_rows, int rows_per_mixture, int n_chan, int n_src, void* stream) {
     OIVA_REQUIRE(What && C && status, "oiva_init_demix: null pointer");

@@ -33,4 +33,29 @@ int ip_update_tpb(int M, int K, cplx* What, const cplx* Vg, const cplx* Cg, cons
     return OIVA_ERR_INVALID;
 }
 
+template <int M, int K>
+static int launch_init(cplx* Wg, const cplx* Cg, const cplx* W0, int* status, int F, int NG, long long G, cudaStream_t st) {
+    const unsigned grid = (unsigned)((G + TPB_WARPS - 1) / TPB_WARPS);
+    k_init_grouped<M, K><<<grid, TPB_WARPS * 32, 0, st>>>(Wg, Cg, W0, status, F, NG, G);
+    OIVA_LAUNCH_CHECK();
+    return OIVA_OK;
+}
+
+// the grouped initialisation for the same (M, K) set; OIVA_ERR_UNSUPPORTED (no error text) when not covered
+int init_demix_tpb(int M, int K, cplx* Wg, const cplx* Cg, const cplx* W0, int* status, int F, int NG, long long G,
+                   cudaStream_t st) {
+#define OIVA_TPB(M_, K_) \
+    if (M == M_ && K == K_) return launch_init<M_, K_>(Wg, Cg, W0, status, F, NG, G, st);
+    OIVA_TPB(1, 1)
+    OIVA_TPB(2, 1) OIVA_TPB(2, 2)
+    OIVA_TPB(3, 1) OIVA_TPB(3, 2) OIVA_TPB(3, 3)
+    OIVA_TPB(4, 1) OIVA_TPB(4, 2) OIVA_TPB(4, 3) OIVA_TPB(4, 4)
+    OIVA_TPB(5, 1) OIVA_TPB(5, 2) OIVA_TPB(5, 3) OIVA_TPB(5, 4) OIVA_TPB(5, 5)
+    OIVA_TPB(6, 1) OIVA_TPB(6, 2) OIVA_TPB(6, 3) OIVA_TPB(6, 4) OIVA_TPB(6, 5) OIVA_TPB(6, 6)
+    OIVA_TPB(7, 1) OIVA_TPB(7, 2) OIVA_TPB(7, 3) OIVA_TPB(7, 4)
+    OIVA_TPB(8, 1) OIVA_TPB(8, 2) OIVA_TPB(8, 3) OIVA_TPB(8, 4)
+#undef OIVA_TPB
+    return OIVA_ERR_UNSUPPORTED;
+}
+
 }  // namespace oiva

@@ -140,8 +140,25 @@ __device__ __forceinline__ void background_tpb(WLane Wm, const cplx* sC, bool& s
 }
 
 // ---- one IP update, determined case (K == M): w_s = (W^H V_s)^-1 e_s by LU with partial pivoting ----------
-template <int M, bool NC = true>
-__device__ __forceinline__ void ip_source_full(WLane Wm, const cplx* sV, int s, bool& singular) {
+// V_s is read through a getter vget(i, j) (full Hermitian element): the grouped array in global / shared memory, or a
+// register copy of the lower triangle (the fused covariance + sweep kernel, cov_sweep.cuh).
+template <bool NC>
+struct HermFromMemory {
+    const cplx* base;
+    __device__ __forceinline__ cplx operator()(int i, int j) const { return herm_load<NC>(base, i, j); }
+};
+template <int M>
+struct HermFromRegs {
+    const cplx (&tri)[oiva_tri(M)];
+    __device__ __forceinline__ cplx operator()(int i, int j) const {
+        const int hi = i >= j ? i : j, lo = i >= j ? j : i;
+        cplx v = tri[hi * (hi + 1) / 2 + lo];
+        if (i < j) v.y = -v.y;
+        return v;
+    }
+};
+template <int M, typename VGet>
+__device__ __forceinline__ void ip_source_full_v(WLane Wm, const VGet& vget, int s, bool& singular) {
     cplx A[M][M], rhs[M][1];
 #pragma unroll
     for (int i = 0; i < M; ++i) {
@@ -153,7 +170,7 @@ __device__ __forceinline__ void ip_source_full(WLane Wm, const cplx* sV, int s, 
     for (int j = 0; j < M; ++j) {
         cplx vrow[M];
 #pragma unroll
-        for (int c = 0; c < M; ++c) vrow[c] = herm_load<NC>(sV, j, c);
+        for (int c = 0; c < M; ++c) vrow[c] = vget(j, c);
 #pragma unroll
         for (int i = 0; i < M; ++i) {
             const cplx a = Wm[j * M + i];
@@ -168,12 +185,16 @@ __device__ __forceinline__ void ip_source_full(WLane Wm, const cplx* sV, int s, 
     for (int i = 0; i < M; ++i) {
         cplx u = cmake(0.0, 0.0);
 #pragma unroll
-        for (int j = 0; j < M; ++j) cfma(u, herm_load<NC>(sV, i, j), rhs[j][0]);
+        for (int j = 0; j < M; ++j) cfma(u, vget(i, j), rhs[j][0]);
         cfmac(d, rhs[i][0], u);
     }
     const cplx inv = crecip(csqrt_(d));
 #pragma unroll
     for (int i = 0; i < M; ++i) Wm[i * M + s] = cmul(rhs[i][0], inv);
+}
+template <int M, bool NC = true>
+__device__ __forceinline__ void ip_source_full(WLane Wm, const cplx* sV, int s, bool& singular) {
+    ip_source_full_v<M>(Wm, HermFromMemory<NC>{sV}, s, singular);
 }
 
 // ---- one IP update, overdetermined case (K < M) ------------------------------------------------------------
@@ -181,8 +202,9 @@ __device__ __forceinline__ void ip_source_full(WLane Wm, const cplx* sV, int s, 
 // system:  q1 = (W1^H + W2^H J^H)^-1 e_s,  q2 = J^H q1   (W1 / W2: top K / bottom M-K rows of W);  then V w = q is
 // solved by Cholesky (V is Hermitian positive definite: no pivoting, no row swaps), and the normalisation needs
 // only w^H V w = w^H q.  ~3x fewer operations than forming W_hat^H V and factorising it, same result.
-template <int M, int K, bool NC = true>
-__device__ __forceinline__ void ip_source_reduced(WLane Wm, const cplx* sV, int s, bool& singular) {
+// (Lm: the lower triangle of V_s, row-major packed, e = i(i+1)/2 + j; overwritten by its Cholesky factor)
+template <int M, int K>
+__device__ __forceinline__ void ip_source_reduced_tri(WLane Wm, cplx (&Lm)[oiva_tri(M)], int s, bool& singular) {
     constexpr int R = M - K;
     cplx q[M];
     {
@@ -216,61 +238,68 @@ __device__ __forceinline__ void ip_source_reduced(WLane Wm, const cplx* sV, int 
             q[K + r] = acc;
         }
     }
-    // Cholesky V = L L^H in place on the lower triangle (row-major packed: e = i(i+1)/2 + j)
-    cplx Lm[oiva_tri(M)];
-#pragma unroll
-    for (int e = 0; e < oiva_tri(M); ++e) {
-        Lm[e] = cov_ld<NC>(sV + (size_t)e * OIVA_GROUP);
-    }
+    // Cholesky V = L L^H in place on the lower triangle.  (static_for: the triple loop must be unrolled completely so
+    // that Lm is indexed with constants and stays in registers -- with "#pragma unroll" alone ptxas kept a 336-byte
+    // local-memory copy of it at M = 6)
     double dinv[M];
-#pragma unroll
-    for (int j = 0; j < M; ++j) {
+    static_for<M>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
         double djj = Lm[j * (j + 1) / 2 + j].x;
-#pragma unroll
-        for (int k = 0; k < j; ++k) {
+        static_for<j>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
             const cplx l = Lm[j * (j + 1) / 2 + k];
             djj = fma(-l.x, l.x, fma(-l.y, l.y, djj));
-        }
+        });
         if (!(djj > 0.0)) singular = true;  // not positive definite (or NaN)
         const double ljj = sqrt(djj);
         dinv[j] = 1.0 / ljj;
-#pragma unroll
-        for (int i = j + 1; i < M; ++i) {
+        static_for<M - 1 - j>([&](auto ic) {
+            constexpr int i = j + 1 + decltype(ic)::value;
             cplx v = Lm[i * (i + 1) / 2 + j];
-#pragma unroll
-            for (int k = 0; k < j; ++k) {
+            static_for<j>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
                 // v -= L[i][k] conj(L[j][k])
                 const cplx a = Lm[i * (i + 1) / 2 + k], bb = Lm[j * (j + 1) / 2 + k];
                 v.x = fma(-a.x, bb.x, fma(-a.y, bb.y, v.x));
                 v.y = fma(-a.y, bb.x, fma(a.x, bb.y, v.y));
-            }
+            });
             Lm[i * (i + 1) / 2 + j] = cscale(v, dinv[j]);
-        }
-    }
+        });
+    });
     // forward: L y = q
-#pragma unroll
-    for (int i = 0; i < M; ++i) {
+    static_for<M>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
         cplx v = q[i];
-#pragma unroll
-        for (int k = 0; k < i; ++k) cfms(v, Lm[i * (i + 1) / 2 + k], q[k]);
+        static_for<i>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            cfms(v, Lm[i * (i + 1) / 2 + k], q[k]);
+        });
         q[i] = cscale(v, dinv[i]);
-    }
+    });
     // normalisation: w^H V w = w^H L L^H w = |L^H w|^2 = |y|^2 -- available before the back substitution
     double den = 0.0;
 #pragma unroll
     for (int i = 0; i < M; ++i) den = fma(q[i].x, q[i].x, fma(q[i].y, q[i].y, den));
     // backward: L^H w = y
-#pragma unroll
-    for (int ii = 0; ii < M; ++ii) {
-        const int i = M - 1 - ii;
+    static_for<M>([&](auto iic) {
+        constexpr int i = M - 1 - decltype(iic)::value;
         cplx v = q[i];
-#pragma unroll
-        for (int k = i + 1; k < M; ++k) cfms_conj(v, Lm[k * (k + 1) / 2 + i], q[k]);  // L^H[i][k] = conj(L[k][i])
+        static_for<M - 1 - i>([&](auto kc) {
+            constexpr int k = i + 1 + decltype(kc)::value;
+            cfms_conj(v, Lm[k * (k + 1) / 2 + i], q[k]);  // L^H[i][k] = conj(L[k][i])
+        });
         q[i] = cscale(v, dinv[i]);
-    }
+    });
     const double inv = 1.0 / sqrt(den);  // w^H V_s w = |y|^2 is real positive                 overiva.py:185-186
 #pragma unroll
     for (int i = 0; i < M; ++i) Wm[i * M + s] = cscale(q[i], inv);
+}
+template <int M, int K, bool NC = true>
+__device__ __forceinline__ void ip_source_reduced(WLane Wm, const cplx* sV, int s, bool& singular) {
+    cplx Lm[oiva_tri(M)];
+#pragma unroll
+    for (int e = 0; e < oiva_tri(M); ++e) Lm[e] = cov_ld<NC>(sV + (size_t)e * OIVA_GROUP);
+    ip_source_reduced_tri<M, K>(Wm, Lm, s, singular);
 }
 
 constexpr int TPB_WARPS = 4;
@@ -344,6 +373,40 @@ __global__ void __launch_bounds__(TPB_WARPS * 32) k_ip_update_tpb(cplx* __restri
                        wscale ? wscale + b * K : nullptr, singular, bad);
     if (singular || bad)
         atomicOr(status + b, (singular ? OIVA_STATUS_SINGULAR : 0) | (bad ? OIVA_STATUS_NONFINITE : 0));
+}
+
+// Initial W_hat written straight into the grouped layout, one thread per bin (overiva.py:89-123): the K filter columns
+// from the identity (W0 == nullptr) or from W0 (R, M, K) row-major, J from the K x K solve of background_tpb, the -I
+// block, zeros on the padded bins of a mixture's last group.  One launch instead of k_init_demix + the regrouping of
+// its row-major result.  (init_eig keeps the row-major path: its eigenvectors come from k_eigh.)
+template <int M, int K>
+__global__ void __launch_bounds__(TPB_WARPS * 32) k_init_grouped(cplx* __restrict__ Wg, const cplx* __restrict__ Cg,
+                                                                 const cplx* __restrict__ W0, int* status, int F, int NG,
+                                                                 long long G) {
+    constexpr int NE = oiva_tri(M);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long gi = (long long)blockIdx.x * TPB_WARPS + warp;
+    if (gi >= G) return;  // whole warp
+    const long long b = gi / NG;
+    const int f = (int)(gi - b * NG) * OIVA_GROUP + lane;
+    const bool ok = f < F;
+    const WLane Wm = {Wg + (size_t)gi * M * M * OIVA_GROUP + lane};
+    const cplx* w0 = W0 ? W0 + ((size_t)b * F + (ok ? f : 0)) * M * K : nullptr;
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+            cplx v = cmake(0.0, 0.0);
+            if (ok) {
+                if (c < K) v = w0 ? w0[j * K + c] : cmake(j == c ? 1.0 : 0.0, 0.0);
+                else if (j == c) v = cmake(-1.0, 0.0);  // (c >= K implies K < M: the [K:, K:] = -I block)
+            }
+            Wm[j * M + c] = v;
+        }
+    if (!ok) return;
+    bool singular = false;
+    background_tpb<M, K, true>(Wm, Cg + (size_t)gi * NE * OIVA_GROUP + lane, singular);
+    if (singular) atomicOr(status + b, OIVA_STATUS_SINGULAR);
 }
 
 }  // namespace oiva

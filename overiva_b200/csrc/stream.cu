@@ -108,16 +108,16 @@ __global__ void __launch_bounds__(256) k_source_model(const double* __restrict__
 // arithmetic and summation orders: (1) the sum over the partials and the model function for chunks of frames in
 // parallel (r is parked in phi), (2) per (mixture, source) gamma -- lane tl adds r[tl], r[tl+32], ... in ascending
 // order, then the xor tree, exactly as above -- followed by phi = 1 / max(r / gamma, 1e-15) in place.
-constexpr int SM_CHUNK = 256;  // frames per CTA of the first kernel
+// (sm_chunk: frames per CTA of the first kernel, a multiple of 32)
 __global__ void __launch_bounds__(256) k_source_r(const double* __restrict__ part, int NCH, double* __restrict__ phi, int T,
-                                                  int Tp, int K, int F_total, int model) {
+                                                  int Tp, int K, int F_total, int model, int sm_chunk) {
     __shared__ double slice[8][32];
     const int b = blockIdx.x / K, k = blockIdx.x - b * K;
     const int tl = threadIdx.x & 31, cs = threadIdx.x >> 5;
     double* ph = phi + ((size_t)b * K + k) * Tp;
     const double* pb = part + ((size_t)b * NCH * K + k) * Tp;
-    const int t_end = min(Tp, (int)(blockIdx.y + 1) * SM_CHUNK);
-    for (int t0 = blockIdx.y * SM_CHUNK; t0 < t_end; t0 += 32) {
+    const int t_end = min(Tp, (int)(blockIdx.y + 1) * sm_chunk);
+    for (int t0 = blockIdx.y * sm_chunk; t0 < t_end; t0 += 32) {
         const int t = t0 + tl;
         double s = 0.0;
         if (t < T) {
@@ -177,6 +177,37 @@ __global__ void __launch_bounds__(256) k_source_finish(double* __restrict__ phi,
     }
 }
 
+// projection-back scales from the grouped state, any M (runtime loops; thread per bin): z[gi][k][lane] with exactly the
+// arithmetic of k_projback_filters / projback_scale
+__global__ void __launch_bounds__(128) k_projback_z(const cplx* __restrict__ Wg, const cplx* __restrict__ Cg,
+                                                    cplx* __restrict__ Zg, long long G, int M, int K) {
+    const int lane = threadIdx.x & 31;
+    const long long gi = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (gi >= G) return;
+    const cplx* Wl = Wg + (size_t)gi * M * M * OIVA_GROUP + lane;
+    const cplx* Cl = Cg + (size_t)gi * (M * (M + 1) / 2) * OIVA_GROUP + lane;
+    auto Cat = [&](int a, int b) {
+        const int hi = a >= b ? a : b, lo = a >= b ? b : a;
+        cplx v = ld_nc_c(Cl + (size_t)(hi * (hi + 1) / 2 + lo) * OIVA_GROUP);
+        if (a < b) v.y = -v.y;
+        return v;
+    };
+    for (int k = 0; k < K; ++k) {
+        cplx num = cmake(0.0, 0.0);
+        double den = 0.0;
+        for (int a = 0; a < M; ++a) {
+            const cplx wa = Wl[(size_t)(a * M + k) * OIVA_GROUP];
+            cfmac(num, wa, Cat(a, 0));
+            cplx cw = cmake(0.0, 0.0);
+            for (int b = 0; b < M; ++b) cfma(cw, Cat(a, b), Wl[(size_t)(b * M + k) * OIVA_GROUP]);
+            den += wa.x * cw.x + wa.y * cw.y;
+        }
+        cplx z = cmake(1.0, 0.0);
+        if (den > 0.0) z = cmake(num.x / den, num.y / den);
+        Zg[((size_t)gi * K + k) * OIVA_GROUP + lane] = z;
+    }
+}
+
 }  // namespace oiva
 
 using namespace oiva;
@@ -229,11 +260,16 @@ extern "C" int oiva_source_model(const double* r2part, int n_chunks, double* phi
     OIVA_REQUIRE(n_batch > 0 && n_frames > 0 && n_src >= 1 && n_freq_total > 0, "oiva_source_model: bad shape");
     const int Tp = oiva_frame_pitch(n_frames);
     cudaStream_t st = (cudaStream_t)stream;
-    if (n_frames > 2048) {  // long mixtures: the frames in parallel, then one small finishing kernel
-        const int chunks = (Tp + SM_CHUNK - 1) / SM_CHUNK;
+    // Long mixtures, and few (mixture, source) pairs with more than a couple of 32-frame blocks (one short mixture: 2-6
+    // CTAs walking their frames block after block, each block a dependent round of loads over the partials -- ~20 us per
+    // epoch at config 3): the frames in parallel, then one small finishing kernel.  Same sums in the same order.
+    const bool few_pairs = (long long)n_batch * n_src < 64 && n_frames > 64;
+    if (n_frames > 2048 || few_pairs) {
+        const int sm_chunk = n_frames > 2048 ? 256 : 32;
+        const int chunks = (Tp + sm_chunk - 1) / sm_chunk;
         OIVA_REQUIRE(chunks <= 65535, "oiva_source_model: too many frames");
         k_source_r<<<dim3((unsigned)(n_batch * n_src), (unsigned)chunks), 256, 0, st>>>(r2part, n_chunks, phi, n_frames, Tp,
-                                                                                         n_src, n_freq_total, model);
+                                                                                         n_src, n_freq_total, model, sm_chunk);
         OIVA_LAUNCH_CHECK();
         k_source_finish<<<(unsigned)(n_batch * n_src), 256, 0, st>>>(phi, wscale, n_frames, Tp, n_src, model);
         OIVA_LAUNCH_CHECK();
@@ -252,6 +288,30 @@ extern "C" int oiva_demix_output(const void* Xg, const void* Weff, void* Y, int 
     if (rc) return rc;
     StreamParams p = make_params(Xg, Weff, n_src, n_frames, n_freq, n_chan, n_src);
     p.Y = Y;
+    return stream_launch(n_chan, KIND_OUTPUT, dtype, p, (long long)n_batch * p.L.NG, (cudaStream_t)stream);
+}
+
+// the final demix straight from the loop's grouped state: Y = (w_k z_k)^H x with the projection-back scale computed per
+// lane from the grouped covariance (Cg != NULL) -- one launch instead of ungroup + projback_filters + demix_output
+extern "C" int oiva_demix_output_grouped(const void* Xg, const void* Wg, const void* Cg, void* zscratch, void* Y,
+                                         int n_batch, int n_frames, int n_freq, int n_chan, int n_src, int dtype,
+                                         void* stream) {
+    OIVA_REQUIRE(Xg && Wg && Y, "oiva_demix_output_grouped: null pointer");
+    int rc = check_dims("oiva_demix_output_grouped", n_batch, n_frames, n_freq, n_chan, n_src);
+    if (rc) return rc;
+    OIVA_REQUIRE(n_src <= n_chan, "oiva_demix_output_grouped: n_src > n_chan");
+    StreamParams p = make_params(Xg, Wg, n_chan, n_frames, n_freq, n_chan, n_src, 1);
+    p.Y = Y;
+    if (Cg && n_chan <= PROJBACK_INLINE_MAX_M) {
+        p.Cg = (const cplx*)Cg;
+    } else if (Cg) {  // many channels: the scales in a small kernel of their own
+        OIVA_REQUIRE(zscratch, "oiva_demix_output_grouped: n_chan > %d needs zscratch", PROJBACK_INLINE_MAX_M);
+        const long long G = (long long)n_batch * p.L.NG;
+        k_projback_z<<<(unsigned)((G + 3) / 4), 128, 0, (cudaStream_t)stream>>>((const cplx*)Wg, (const cplx*)Cg,
+                                                                                  (cplx*)zscratch, G, n_chan, n_src);
+        OIVA_LAUNCH_CHECK();
+        p.Zg = (const cplx*)zscratch;
+    }
     return stream_launch(n_chan, KIND_OUTPUT, dtype, p, (long long)n_batch * p.L.NG, (cudaStream_t)stream);
 }
 

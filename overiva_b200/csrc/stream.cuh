@@ -51,7 +51,67 @@ struct StreamParams {
     double* r2part;   // (B, NG, K, Tp)
     void* Y;          // (B, T, F, K) interleaved complex ST
     void* Xr;         // grouped samples with K channels
+    const cplx* Cg;   // output kernels, M <= 8: grouped input covariance [gi][NE][32] -> projection back folded into the
+                      // filters inside the kernel (projback_scale)
+    const cplx* Zg;   // output kernels, M >= 9: the projection-back scales z [gi][K][32] from k_projback_z (the unrolled
+                      // in-kernel version is ~2 MB of code per channel count there, for kernels that run milliseconds)
 };
+constexpr int PROJBACK_INLINE_MAX_M = 8;
+
+// w_k <- w_k z_k with z from the grouped array of k_projback_z
+template <int M, int KC>
+__device__ __forceinline__ void projback_apply(cplx (&w)[M][KC], const cplx* __restrict__ Zl, int k0, int K) {
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        if (k0 + k < K) {
+            const cplx z = ld_nc_c(Zl + (size_t)(k0 + k) * OIVA_GROUP);
+#pragma unroll
+            for (int a = 0; a < M; ++a) w[a][k] = cmul(w[a][k], z);
+        }
+    }
+}
+
+// Projection back folded into this lane's filters: w_k <- w_k z_k, z_k = (w_k^H C e_0) / (w_k^H C w_k), 1 where the
+// denominator is not positive (pyroomacoustics.bss.projection_back as called at overiva.py:197-199; no pass over Y:
+// sum_t conj(x_0) y_k = T w_k^H C e_0, sum_t |y_k|^2 = T w_k^H C w_k).  The arithmetic and its order are those of
+// k_projback_filters (solve.cu), which does the same on row-major arrays.  Cl: this lane's element 0 of Cg[gi].
+template <int M, int KC>
+__device__ __forceinline__ void projback_scale(cplx (&w)[M][KC], const cplx* __restrict__ Cl) {
+    cplx num[KC];
+    double den[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        num[k] = cmake(0.0, 0.0);
+        den[k] = 0.0;
+    }
+#pragma unroll
+    for (int a = 0; a < M; ++a) {
+        cplx crow[M];  // row a of the Hermitian C from its stored lower triangle
+#pragma unroll
+        for (int b = 0; b < M; ++b) {
+            const int hi = a >= b ? a : b, lo = a >= b ? b : a;
+            cplx v = ld_nc_c(Cl + (size_t)(hi * (hi + 1) / 2 + lo) * OIVA_GROUP);
+            if (a < b) v.y = -v.y;
+            crow[b] = v;
+        }
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            const cplx wa = w[a][k];
+            cfmac(num[k], wa, crow[0]);
+            cplx cw = cmake(0.0, 0.0);
+#pragma unroll
+            for (int b = 0; b < M; ++b) cfma(cw, crow[b], w[b][k]);
+            den[k] += wa.x * cw.x + wa.y * cw.y;  // Re(conj(w_a) (C w)_a)
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        cplx z = cmake(1.0, 0.0);
+        if (den[k] > 0.0) z = cmake(num[k].x / den[k], num[k].y / den[k]);
+#pragma unroll
+        for (int a = 0; a < M; ++a) w[a][k] = cmul(w[a][k], z);
+    }
+}
 
 // this lane's demixing vectors: w[c][k] for KC sources starting at k0 (zero beyond K / beyond F)
 template <int M, int KC>
@@ -167,6 +227,13 @@ __global__ void __launch_bounds__(M >= 13 ? 384 : 512) k_demix_staged(const Stre
     const int Tp = L.frame_pitch();
     cplx w[M][KC];
     load_filters<M, KC>(w, p, b * L.F + (bin_ok ? f : 0), gi, lane, bin_ok, k0);
+    if constexpr (OUTPUT) {
+        if constexpr (M <= PROJBACK_INLINE_MAX_M) {
+            if (p.Cg) projback_scale<M, KC>(w, p.Cg + (size_t)gi * oiva_tri(M) * OIVA_GROUP + lane);
+        } else {
+            if (p.Zg) projback_apply<M, KC>(w, p.Zg + (size_t)gi * p.K * OIVA_GROUP + lane, k0, p.K);
+        }
+    }
     const XC* xg = reinterpret_cast<const XC*>(p.Xg) + (size_t)gi * L.group_elems();
     XC* Y = reinterpret_cast<XC*>(p.Y);
     const int nblk = Tp / POWER_FB;
@@ -244,6 +311,11 @@ __global__ void __launch_bounds__(512) k_demix_output(const StreamParams p) {
     const int k0 = warp * KC;
     cplx w[M][KC];
     load_filters<M, KC>(w, p, b * L.F + (bin_ok ? f : 0), gi, lane, bin_ok, k0);
+    if constexpr (M <= PROJBACK_INLINE_MAX_M) {
+        if (p.Cg) projback_scale<M, KC>(w, p.Cg + (size_t)gi * oiva_tri(M) * OIVA_GROUP + lane);
+    } else {
+        if (p.Zg) projback_apply<M, KC>(w, p.Zg + (size_t)gi * p.K * OIVA_GROUP + lane, k0, p.K);
+    }
     const XC* xg = reinterpret_cast<const XC*>(p.Xg) + (size_t)gi * L.group_elems();
     XC* Y = reinterpret_cast<XC*>(p.Y);
     const int t_begin = (int)((long long)L.T * blockIdx.y / p.nsplit);

@@ -258,8 +258,10 @@ def separate_batch(mix, n_src=None, n_iter=20, framesize=4096, hop=None, win_a=N
             with torch.cuda.stream(s_cmp):
                 wa, ws, tw = _window(win_a, framesize, dev), _window(win_s, framesize, dev), _twiddles(framesize, dev)
             ev_in, ev_cmp, ev_out = [None] * 2, [None] * 2, [None] * 2
-            for i, b0 in enumerate(range(0, B, chunk)):
-                nb = min(chunk, B - b0)
+            b0 = prev_nb = 0
+            for i, nb in enumerate(core._chunk_schedule(B, chunk)):  # (small chunks at both ends: less fill / drain)
+                b0 += prev_nb
+                prev_nb = nb
                 slot = i % 2
                 with torch.cuda.stream(s_in):
                     if ev_cmp[slot] is not None:

@@ -179,3 +179,55 @@ def demix_output(Xg, Weff, B, T, F, M, K, code):
     L.check(lib.oiva_demix_output(P(Xg), P(Wd), P(Y), B, T, F, M, K, code, stream()), "oiva_demix_output")
     torch.cuda.synchronize()
     return Y.cpu().numpy()
+
+
+def group_rows(rows, B, F, n_elems):
+    """rows (B*F, n_elems) numpy complex128 -> device grouped [B*NG][n_elems][32]."""
+    lib = L.load()
+    NG = lib.oiva_bin_groups(F)
+    Rd = to_dev(rows.astype(np.complex128))
+    Gd = torch.empty((B * NG, n_elems, 32), dtype=torch.complex128, device=dev())
+    L.check(lib.oiva_group_rows(P(Rd), P(Gd), B, F, n_elems, stream()), "oiva_group_rows")
+    return Gd
+
+
+def ungroup_rows(Gd, B, F, n_elems):
+    lib = L.load()
+    Rd = torch.full((B * F, n_elems), float("nan"), dtype=torch.complex128, device=dev())
+    L.check(lib.oiva_ungroup_rows(P(Gd), P(Rd), B, F, n_elems, stream()), "oiva_ungroup_rows")
+    torch.cuda.synchronize()
+    return Rd.cpu().numpy()
+
+
+def init_demix_grouped(Cx, K, W0=None):
+    """Cx (B, F, M, M), W0 (B, F, M, K) or None -> (What (B, F, M, M) ungrouped, status (B,), rc)."""
+    lib = L.load()
+    B, F, M, _ = Cx.shape
+    NG = lib.oiva_bin_groups(F)
+    Cgd = pack_cov(Cx[:, :, None])
+    W0d = to_dev(W0.astype(np.complex128)) if W0 is not None else None
+    Wg = torch.full((B * NG, M * M, 32), float("nan"), dtype=torch.complex128, device=dev())
+    st = torch.zeros(B, dtype=torch.int32, device=dev())
+    rc = lib.oiva_init_demix_grouped(P(Wg), P(Cgd), P(W0d), P(st), B, F, M, K, stream())
+    if rc != 0:
+        return None, None, rc
+    torch.cuda.synchronize()
+    # padded bins of a ragged last group must hold zeros
+    if F % 32:
+        pad = Wg.view(B, NG, M * M, 32)[:, -1, :, F % 32:]
+        assert bool((pad == 0).all())
+    return ungroup_rows(Wg, B, F, M * M).reshape(B, F, M, M), st.cpu().numpy(), 0
+
+
+def demix_output_grouped(Xg, What, Cx, B, T, F, M, K, code, proj_back):
+    """What (B, F, M, M), Cx (B, F, M, M) numpy -> Y (B, T, F, K) through the single-launch grouped output kernel."""
+    lib = L.load()
+    Wg = group_rows(What.reshape(B * F, M * M), B, F, M * M)
+    Cgd = pack_cov(Cx[:, :, None]) if proj_back else None
+    dt = torch.complex64 if code == L.C64 else torch.complex128
+    Y = torch.full((B, T, F, K), float("nan"), dtype=dt, device=dev())
+    zs = torch.empty((B * lib.oiva_bin_groups(F) * K * 32,), dtype=torch.complex128, device=dev())
+    L.check(lib.oiva_demix_output_grouped(P(Xg), P(Wg), P(Cgd), P(zs), P(Y), B, T, F, M, K, code, stream()),
+            "oiva_demix_output_grouped")
+    torch.cuda.synchronize()
+    return Y.cpu().numpy()

@@ -262,6 +262,35 @@ def test_init_demix_eye_and_w0(M, K):
     assert rel_err(got, orc.init_demixing(Cx, K, W0=W0)) < 1e-11
 
 
+@pytest.mark.parametrize("M,K", [(4, 2), (6, 2), (3, 3), (8, 1), (6, 6), (7, 4), (1, 1), (16, 4), (8, 8)])
+def test_init_demix_grouped(M, K):
+    """The thread-per-bin initialisation that writes the grouped W_hat directly (identity and W0) against the oracle and
+    against oiva_init_demix; shapes outside the thread-per-bin set answer OIVA_ERR_UNSUPPORTED."""
+    B = 2
+    X = _mix(18, M, 1300, 80, B=B)  # F = 41: a ragged second group
+    F = X.shape[2]
+    Cx = np.stack([orc.input_covariance(X[b]) for b in range(B)])
+    got, status, rc = G.init_demix_grouped(Cx, K)
+    if M > 8 or (M > 6 and K > 4):
+        assert rc == L.ERR_UNSUPPORTED
+        return
+    assert rc == 0 and not status.any()
+    for b in range(B):
+        assert rel_err(got[b], orc.init_demixing(Cx[b], K)) < 1e-12
+        old, _ = G.init_demix(Cx[b], K, L.INIT_EYE)
+        assert rel_err(got[b], old) < 1e-12
+    rng = np.random.default_rng(19)
+    W0 = rng.standard_normal((B, F, M, K)) + 1j * rng.standard_normal((B, F, M, K))
+    got, status, rc = G.init_demix_grouped(Cx, K, W0=W0)
+    assert rc == 0
+    for b in range(B):
+        assert rel_err(got[b], orc.init_demixing(Cx[b], K, W0=W0[b])) < 1e-11
+    # a silent mixture: its J solve is singular, only its status word is set
+    Cx[1] = 0
+    _, status, rc = G.init_demix_grouped(Cx, K)
+    assert rc == 0 and status[0] == 0 and (status[1] & L.STATUS_SINGULAR or K == M)
+
+
 @pytest.mark.parametrize("M", [1, 2, 3, 4, 6, 8, 11, 16])
 def test_eigh(M):
     X = _mix(14, M, 1500, 32)[0]
@@ -313,3 +342,53 @@ def test_final_demix_and_projection_back(M, K, n_samples, dtype, proj_back):
             z = orc.projection_back(want, X128[b][:, :, 0])
             want = want * np.conj(z[None])
         assert rel_err(Y[b], want) < (1e-12 if dtype == np.complex128 else 1e-6)
+    # the single-launch version (filters from the grouped W_hat, projection-back scale computed per lane from the grouped
+    # covariance): same arithmetic in the same order as the three-kernel sequence above
+    Yg = G.demix_output_grouped(Xg, W, Cx, B, T, F, M, K, G.code_of(dtype), proj_back)
+    assert Yg.dtype == dtype and rel_err(Yg, Y) < (1e-14 if dtype == np.complex128 else 1e-6)
+
+
+@pytest.mark.parametrize("M,K,dtype", [(6, 2, np.complex128), (4, 2, np.complex128), (6, 2, np.complex64), (3, 3, np.complex128),
+                                       (5, 3, np.complex128), (8, 1, np.complex128), (4, 4, np.complex64), (2, 1, np.complex128),
+                                       (6, 3, np.complex128)])
+def test_fused_cov_sweep_equals_two_kernels(M, K, dtype, monkeypatch):
+    """oiva_cov_ip_update (one pass over X ending in the per-group sweep, covariances in registers) against
+    oiva_weighted_cov_ws + oiva_ip_update on the same state: same arithmetic in the same order -> bit-identical W_hat and
+    status words; needs >= 4096 bin groups (no frame splitting).  One mixture is silent (zero input -> singular bins): only
+    its status word may be set.  Sampled mixtures are checked against the oracle."""
+    from overiva_b200.core import DemixPlan
+
+    B, T, F = 2100, 23, 40  # NG = 2 -> 4200 groups, the second group of every mixture ragged (8 of 32 bins)
+    tdt = torch.complex128 if dtype == np.complex128 else torch.complex64
+    g = torch.Generator(device="cuda").manual_seed(7 + M * 10 + K)
+    rdt = torch.float64 if dtype == np.complex128 else torch.float32
+    S = torch.randn(B, T, F, K + 1, 2, generator=g, device="cuda", dtype=rdt)
+    S = torch.view_as_complex(S * (torch.rand(B, T, 1, K + 1, 1, generator=g, device="cuda", dtype=rdt) ** 3))
+    A = torch.view_as_complex(torch.randn(B, 1, F, M, K + 1, 2, generator=g, device="cuda", dtype=rdt))
+    N = torch.view_as_complex(torch.randn(B, T, F, M, 2, generator=g, device="cuda", dtype=rdt))
+    X = ((A @ S.unsqueeze(-1)).squeeze(-1) + 1e-2 * N).to(tdt).contiguous()
+    X[1234] = 0
+    out = {}
+    for path in ("fused", "two_kernels"):
+        if path == "two_kernels":
+            monkeypatch.setenv("OIVA_NO_COV_SWEEP", "1")
+        else:
+            monkeypatch.delenv("OIVA_NO_COV_SWEEP", raising=False)
+        plan = DemixPlan(B, T, F, M, K, L.MODEL_LAPLACE, X.dtype, X.device)
+        plan.load(X)
+        plan.init(L.INIT_EYE)
+        l0 = plan.launches
+        plan.iterate(3)
+        covered = K <= 3 and (M <= 5 or (M == 6 and K <= 2) or K == 1)  # (cov_sweep_supported; others fall back)
+        assert plan.launches - l0 == (9 if path == "fused" and covered else 12), (path, plan.launches - l0)
+        out[path] = (plan.filters().clone(), plan.status_vector().copy())
+        del plan
+    Wf, sf = out["fused"]
+    Wt, st = out["two_kernels"]
+    assert np.array_equal(sf, st) and sf[1234] != 0 and not np.any(np.delete(sf, 1234))
+    good = torch.ones(B, dtype=torch.bool, device=X.device)
+    good[1234] = False
+    assert torch.equal(Wf[good], Wt[good])
+    for b in (0, 2099):
+        _, Wo = orc.overiva(X[b].cpu().numpy().astype(np.complex128), n_src=K, n_iter=3, return_filters=True)
+        assert rel_err(Wf[b].cpu().numpy(), Wo) <= (1e-10 if dtype == np.complex128 else 1e-4)
