@@ -135,6 +135,12 @@ int oiva_sum_partials(const double* r2part, int n_chunks, double* r2, int n_batc
 int oiva_source_model(const double* r2part, int n_chunks, double* phi, double* wscale, int n_batch,
                       int n_frames, int n_src, int n_freq_total, int model, void* stream);
 
+/* oiva_source_model with n_batch * n_src zeroed words of device memory (left zeroed on return; NULL = none): where the
+ * frames are processed in parallel (long mixtures, or few (mixture, source) pairs) the last CTA of a pair then finishes it,
+ * one launch instead of two. */
+int oiva_source_model_ws(const double* r2part, int n_chunks, double* phi, double* wscale, unsigned* counters, int n_batch,
+                         int n_frames, int n_src, int n_freq_total, int model, void* stream);
+
 /* One sweep over the K sources, per bin, in order:  W[:, :K] *= wscale;  for s: w_s = (What^H V_s)^-1 e_s;
  * w_s /= sqrt(w_s^H V_s w_s);  J = (W^H C E1)^-1 (W^H C E2).   Wg: the W_hat matrices in the GROUPED layout
  * [gi][M*M][32] (oiva_group_rows of the (R,M,M) array), updated in place; Vg grouped; C (R,M,M) c128 full,
@@ -190,10 +196,10 @@ int oiva_demix_output(const void* Xg, const void* Weff, void* Y, int n_batch, in
                       int n_chan, int n_src, int dtype, void* stream);
 
 /* The same straight from the loop's grouped state: Wg = the grouped W_hat [gi][M*M][32] (columns :K are the filters).
- * With Cg (grouped lower-triangle input covariance) the projection-back scale z_k of oiva_projback_filters is computed
- * per bin and folded into the filters (same arithmetic and order); Cg == NULL: no projection back.  M <= 8: inside the
- * output kernel, one launch for overiva.py:192-199.  M >= 9: a small kernel writes the scales to zscratch
- * (n_batch * ceil(F/32) * n_src * 32 c128, device memory, required then) first. */
+ * With Cg (grouped lower-triangle input covariance) the projection-back scales z_k of oiva_projback_filters are computed
+ * per bin by a small kernel into zscratch (n_batch * ceil(F/32) * n_src * 32 c128 of device memory, required then; same
+ * arithmetic and order) and folded into the filters by the output kernel; Cg == NULL: no projection back.  Two launches,
+ * no row-major copies, for overiva.py:192-199. */
 int oiva_demix_output_grouped(const void* Xg, const void* Wg, const void* Cg, void* zscratch, void* Y, int n_batch,
                               int n_frames, int n_freq, int n_chan, int n_src, int dtype, void* stream);
 

@@ -56,6 +56,7 @@ SIGNATURES = {
     "oiva_ungroup_rows": (_i, [_p, _p, _i, _i, _i, _p]),
     "oiva_sum_partials": (_i, [_p, _i, _p, _i, _i, _i, _p]),
     "oiva_source_model": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "oiva_source_model_ws": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "oiva_ip_update": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "oiva_cov_ip_update": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "oiva_init_demix": (_i, [_p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _p]),

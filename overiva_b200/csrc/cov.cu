@@ -12,6 +12,7 @@ namespace oiva {
     int cov_launch_m##M(int dtype, int KC, const CovParams& p, cudaStream_t st, int* nsplit_out); \
     int cov_max_kc_m##M();                                                                                     \
     int cov_launch_tiled_m##M(int dtype, const CovParams& p, cudaStream_t st, int* nsplit_out);                \
+    int cov_launch_wbin_m##M(int KC, const CovParams& p, cudaStream_t st, int* nsplit_out);                   \
     int cov_sweep_launch_m##M(int dtype, int K, const CovParams& p, cudaStream_t st);                          \
     int relayout_cov_launch_m##M(int dtype, RelayoutCovParams p, int max_split, cudaStream_t st, int* nsplit_out);
 OIVA_DECL(1) OIVA_DECL(2) OIVA_DECL(3) OIVA_DECL(4) OIVA_DECL(5) OIVA_DECL(6) OIVA_DECL(7) OIVA_DECL(8)
@@ -88,9 +89,33 @@ extern "C" size_t oiva_weighted_cov_scratch_bytes(int n_batch, int n_frames, int
     return slots < 2 ? 0 : slots * vg;
 }
 
+static int weighted_cov_impl(const void* Xg, const double* phi, bool wbin, void* Vg, void* scratch, size_t scratch_bytes,
+                             int n_batch, int n_frames, int n_freq, int n_chan, int n_src, int dtype, void* stream);
+
 extern "C" int oiva_weighted_cov_ws(const void* Xg, const double* phi, void* Vg, void* scratch, size_t scratch_bytes,
                                     int n_batch, int n_frames, int n_freq, int n_chan, int n_src, int dtype,
                                     void* stream) {
+    return weighted_cov_impl(Xg, phi, false, Vg, scratch, scratch_bytes, n_batch, n_frames, n_freq, n_chan, n_src, dtype,
+                             stream);
+}
+
+// Weights per (source, frame, BIN): winv is a grouped array [gi][k][Tp][32] of float64 (Tp = oiva_frame_pitch(T); the
+// padding frames are never read).  complex128 samples, M <= 8.  V_k[f] = (1/T) sum_t winv_k(f, t) x(f, t) x(f, t)^H --
+// the auxiliary variable of ILRMA (pyroomacoustics.bss.ilrma as called at overiva_oneshot.py:331-339), whose source
+// model r_k(f, t) is a low-rank spectrogram instead of overiva's r_k(t).
+extern "C" int oiva_weighted_cov_binwise(const void* Xg, const double* winv, void* Vg, void* scratch, size_t scratch_bytes,
+                                         int n_batch, int n_frames, int n_freq, int n_chan, int n_src, void* stream) {
+    OIVA_REQUIRE(winv, "oiva_weighted_cov_binwise: null weights");
+    if (n_chan > 8) {
+        oiva_set_error("oiva_weighted_cov_binwise: implemented for n_chan <= 8 (got %d)", n_chan);
+        return OIVA_ERR_UNSUPPORTED;
+    }
+    return weighted_cov_impl(Xg, winv, true, Vg, scratch, scratch_bytes, n_batch, n_frames, n_freq, n_chan, n_src,
+                             OIVA_C128, stream);
+}
+
+static int weighted_cov_impl(const void* Xg, const double* phi, bool wbin, void* Vg, void* scratch, size_t scratch_bytes,
+                             int n_batch, int n_frames, int n_freq, int n_chan, int n_src, int dtype, void* stream) {
     using namespace oiva;
     OIVA_REQUIRE(Xg && Vg, "oiva_weighted_cov: null pointer");
     OIVA_REQUIRE(n_batch > 0 && n_frames > 0 && n_freq > 0 && n_chan >= 1 && n_chan <= OIVA_MAX_M && n_src >= 1,
@@ -144,7 +169,8 @@ extern "C" int oiva_weighted_cov_ws(const void* Xg, const double* phi, void* Vg,
     }();
     int k0 = 0;
     while (k0 < n_src) {
-        const bool tiled = !no_tiled && n_chan >= 9 && n_src - k0 >= 3 && (p.Vpart || p.nsplit == 1 || p.nsplit <= 0);
+        const bool tiled =
+            !wbin && !no_tiled && n_chan >= 9 && n_src - k0 >= 3 && (p.Vpart || p.nsplit == 1 || p.nsplit <= 0);
         int KC = tiled ? 4 : pick_chunk(n_src - k0, max_kc);
         p.k0 = k0;
         int rc = OIVA_ERR_INVALID;
@@ -156,6 +182,12 @@ extern "C" int oiva_weighted_cov_ws(const void* Xg, const double* phi, void* Vg,
 #define OIVA_CASE(M) case M: rc = cov_launch_tiled_m##M(dtype, q, st, &nsplit_used); break;
                 OIVA_CASE(9) OIVA_CASE(10) OIVA_CASE(11) OIVA_CASE(12) OIVA_CASE(13) OIVA_CASE(14) OIVA_CASE(15)
                 OIVA_CASE(16)
+#undef OIVA_CASE
+            }
+        } else if (wbin) {
+            switch (n_chan) {
+#define OIVA_CASE(M) case M: rc = cov_launch_wbin_m##M(KC, p, st, &nsplit_used); break;
+                OIVA_CASE(1) OIVA_CASE(2) OIVA_CASE(3) OIVA_CASE(4) OIVA_CASE(5) OIVA_CASE(6) OIVA_CASE(7) OIVA_CASE(8)
 #undef OIVA_CASE
             }
         } else {

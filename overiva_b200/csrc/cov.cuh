@@ -48,8 +48,12 @@ __host__ __device__ constexpr int cov_nep_max(int M, int KC) {
     int n = (OIVA_COV_REG_BUDGET - 2 * M) / (2 * KC);
     return n < 1 ? 1 : n;
 }
+// (3 parts would leave 6 of the 8 warps of a CTA running -- two 3-warp teams, two of the four schedulers with a single
+// warp: ncu showed the fp64 pipe 39 % busy at M = K = 6 -- so 3 is rounded up to 4: two 4-warp teams)
 __host__ __device__ constexpr int cov_parts(int M, int KC) {
-    return (oiva_tri(M) + cov_nep_max(M, KC) - 1) / cov_nep_max(M, KC);
+    return (oiva_tri(M) + cov_nep_max(M, KC) - 1) / cov_nep_max(M, KC) == 3
+               ? 4
+               : (oiva_tri(M) + cov_nep_max(M, KC) - 1) / cov_nep_max(M, KC);
 }
 // frames per stage (even): ~16 KB of fp64 samples for M <= 8 (many single-warp teams per SM), ~32 KB for the
 // blocked many-channel kernel (one big team per SM: fewer, larger hand-offs)
@@ -85,15 +89,20 @@ struct CovParams {
 // passes a policy whose run() consumes the accumulators in registers instead
 struct CovStoreEpilogue {};
 
-template <typename ST, int M, int KC, int P, int PART>
+// WBIN = false: one weight per (source, frame), phi (B, K, Tp) -- the IVA source models (overiva.py:152-173).
+// WBIN = true : one weight per (source, frame, BIN), a grouped array [gi][k][Tp][32] -- ILRMA's low-rank source model
+//               (1 / r_k(f, t)); the weights of a chunk are staged per lane next to the samples.
+template <typename ST, int M, int KC, int P, int PART, bool WBIN = false>
 struct CovPart {
     typedef typename StoreC<ST>::type XC;
     static constexpr int NE = oiva_tri(M);
     static constexpr int NEP = (NE + P - 1) / P;
     static constexpr int NACC = NEP;
     static constexpr int TC = cov_chunk_frames(M);  // frames per ring stage
+    static constexpr bool WB = WBIN;
+    static constexpr int WLANES = WBIN ? OIVA_GROUP : 1;  // weights per (source, frame) in a stage
 
-    // accumulate `nfr` (<= TC) frames of a staged chunk: xs = [TC][M][32] complex, ph = [KC][TC]
+    // accumulate `nfr` (<= TC) frames of a staged chunk: xs = [TC][M][32] complex, ph = [KC][TC] (or [KC][TC][32])
     __device__ static __forceinline__ void accumulate(cplx (&acc)[NEP][KC], const XC* __restrict__ xs,
                                                       const double* __restrict__ ph, int nfr, int lane, int) {
 #pragma unroll
@@ -104,7 +113,7 @@ struct CovPart {
 #pragma unroll
                 for (int c = 0; c < M; ++c) x[c] = widen(xs[(fr * M + c) * OIVA_GROUP + lane]);
 #pragma unroll
-                for (int k = 0; k < KC; ++k) w[k] = ph[k * TC + fr];
+                for (int k = 0; k < KC; ++k) w[k] = WBIN ? ph[(k * TC + fr) * OIVA_GROUP + lane] : ph[k * TC + fr];
                 static_for<NEP>([&](auto nc) {
                     constexpr int n = decltype(nc)::value;
                     constexpr int e = PART + n * P;
@@ -167,7 +176,8 @@ __device__ __forceinline__ void cov_team_body(const CovParams& p, unsigned char*
     const int S = p.stages;
     const int Tp = L.frame_pitch();
     constexpr size_t x_stage = (size_t)TC * M * OIVA_GROUP * sizeof(XC);
-    constexpr size_t stage_bytes = ((x_stage + (size_t)KC * TC * sizeof(double) + 127) / 128) * 128;
+    constexpr int WL = CP::WLANES;
+    constexpr size_t stage_bytes = ((x_stage + (size_t)KC * TC * WL * sizeof(double) + 127) / 128) * 128;
     uint64_t* full = reinterpret_cast<uint64_t*>(team_smem);
     uint64_t* empty = full + S;
     unsigned char* stage0 = team_smem + 128 * ((2 * S * sizeof(uint64_t) + 127) / 128);
@@ -190,9 +200,13 @@ __device__ __forceinline__ void cov_team_body(const CovParams& p, unsigned char*
         const int sp = pu - gi * nsplit;
         pc = nsplit == 1 ? 0 : (int)((long long)nchunks * sp / nsplit);
         pce = nsplit == 1 ? nchunks : (int)((long long)nchunks * (sp + 1) / nsplit);
-        const int b = gi / p.NGphi;
         psrc = Xg + (size_t)gi * group_elems + (size_t)pc * TC * frame_elems;
-        pphi = p.phi + (size_t)b * p.K * Tp + (size_t)pc * TC;
+        if constexpr (CP::WB) {  // per-bin weights: [gi][k][Tp][32]
+            pphi = p.phi + ((size_t)gi * p.K * Tp + (size_t)pc * TC) * OIVA_GROUP;
+        } else {
+            const int b = gi / p.NGphi;
+            pphi = p.phi + (size_t)b * p.K * Tp + (size_t)pc * TC;
+        }
     };
     auto issue = [&]() {
         while (pc >= pce) {
@@ -203,16 +217,16 @@ __device__ __forceinline__ void cov_team_body(const CovParams& p, unsigned char*
         const int nfr = min(TC, L.T - pc * TC);
         unsigned char* dst = stage0 + (size_t)pstage * stage_bytes;
         const uint32_t xb = (uint32_t)(nfr * frame_elems * sizeof(XC));
-        const uint32_t pb = (uint32_t)(((nfr + 1) & ~1) * sizeof(double));
+        const uint32_t pb = (uint32_t)((CP::WB ? nfr * OIVA_GROUP : ((nfr + 1) & ~1)) * sizeof(double));
         mbar_arrive_expect_tx(&full[pstage], xb + KC * pb);
         tma_load_1d(dst, psrc, xb, &full[pstage]);
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
             const int ks = min(p.k0 + k, p.K - 1);  // padded source slots re-read the last row (never written back)
-            tma_load_1d(dst + x_stage + (size_t)k * TC * sizeof(double), pphi + (size_t)ks * Tp, pb, &full[pstage]);
+            tma_load_1d(dst + x_stage + (size_t)k * TC * WL * sizeof(double), pphi + (size_t)ks * Tp * WL, pb, &full[pstage]);
         }
         psrc += (size_t)TC * frame_elems;
-        pphi += TC;
+        pphi += TC * WL;
         ++pc;
         if (++pstage == S) {
             pstage = 0;
@@ -265,20 +279,20 @@ __device__ __forceinline__ void cov_team_body(const CovParams& p, unsigned char*
     }
 }
 
-template <typename ST, int M, int KC, int P, int PART = 0>
+template <typename ST, int M, int KC, int P, bool WBIN, int PART = 0>
 struct CovDispatch {
     __device__ static __forceinline__ void run(int part, const CovParams& p, unsigned char* team_smem,
                                                long long team_global, long long n_teams_total, int lane) {
         if (part == PART)
-            cov_team_body<CovPart<ST, M, KC, P, PART>, ST, M, KC>(p, team_smem, team_global, n_teams_total, lane, PART == 0,
-                                                                 PART);
+            cov_team_body<CovPart<ST, M, KC, P, PART, WBIN>, ST, M, KC>(p, team_smem, team_global, n_teams_total, lane,
+                                                                       PART == 0, PART);
         else if constexpr (PART + 1 < P)
-            CovDispatch<ST, M, KC, P, PART + 1>::run(part, p, team_smem, team_global, n_teams_total, lane);
+            CovDispatch<ST, M, KC, P, WBIN, PART + 1>::run(part, p, team_smem, team_global, n_teams_total, lane);
     }
 };
 
 // blockDim.x = teams_per_cta * P * 32; dynamic smem = teams_per_cta * team_smem_bytes
-template <typename ST, int M, int KC, int P>
+template <typename ST, int M, int KC, int P, bool WBIN = false>
 __global__ void __launch_bounds__(cov_threads(P)) k_cov(const CovParams p, int teams_per_cta, int team_smem_bytes) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -294,8 +308,8 @@ __global__ void __launch_bounds__(cov_threads(P)) k_cov(const CovParams p, int t
         mbar_fence_init();
     }
     __syncthreads();
-    CovDispatch<ST, M, KC, P>::run(part, p, team_smem, (long long)blockIdx.x * teams_per_cta + team,
-                                            (long long)gridDim.x * teams_per_cta, lane);
+    CovDispatch<ST, M, KC, P, WBIN>::run(part, p, team_smem, (long long)blockIdx.x * teams_per_cta + team,
+                                         (long long)gridDim.x * teams_per_cta, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -317,6 +331,8 @@ struct CovBlock {
     static constexpr int NE = oiva_tri(M);
     static constexpr int NACC = COV_BT * COV_BT;
     static constexpr int TC = cov_chunk_frames(M);
+    static constexpr bool WB = false;
+    static constexpr int WLANES = 1;
 
     __device__ static __forceinline__ void coords(int part, int& bi, int& bj) {
         bi = 0;

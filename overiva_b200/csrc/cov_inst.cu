@@ -103,15 +103,19 @@ static int launch_common(Kern kern, CovParams p, cudaStream_t st, int P, int tea
     return OIVA_OK;
 }
 
-template <typename ST, int KC>
+template <typename ST, int KC, bool WBIN = false>
 static int launch(CovParams p, cudaStream_t st, int* nsplit_out) {
     constexpr int M = OIVA_COV_M;
     typedef typename StoreC<ST>::type XC;
     constexpr int TC = cov_chunk_frames(M);
     constexpr size_t x_stage = (size_t)TC * M * OIVA_GROUP * sizeof(XC);
-    constexpr size_t stage_bytes = ((x_stage + (size_t)KC * TC * sizeof(double) + 127) / 128) * 128;
+    constexpr size_t stage_bytes =
+        ((x_stage + (size_t)KC * TC * (WBIN ? OIVA_GROUP : 1) * sizeof(double) + 127) / 128) * 128;
     if constexpr (COV_USE_BLOCKS) {
-        if constexpr (KC > 2) {
+        if constexpr (WBIN) {
+            oiva_set_error("cov_launch: per-bin weights are implemented for M <= 8 (M=%d)", M);
+            return OIVA_ERR_UNSUPPORTED;
+        } else if constexpr (KC > 2) {
             oiva_set_error("cov_launch: blocked kernel (M=%d) takes source chunks of 1 or 2, not %d", M, KC);
             return OIVA_ERR_INVALID;
         } else {
@@ -131,7 +135,7 @@ static int launch(CovParams p, cudaStream_t st, int* nsplit_out) {
             oiva_set_error("cov_launch: (M=%d, KC=%d) is not instantiated (%d parts)", M, KC, P);
             return OIVA_ERR_INVALID;
         } else {
-            auto kern = k_cov<ST, M, KC, P>;
+            auto kern = k_cov<ST, M, KC, P, WBIN>;
             static OivaPerDeviceOnce attr_done;
             return launch_common(kern, p, st, P, cov_teams_per_cta(P), stage_bytes, TC, M, KC, attr_done, nsplit_out,
                                  [&](const CovParams& q, unsigned grid, int threads, size_t smem, int teams,
@@ -178,6 +182,25 @@ int OIVA_CAT(cov_launch_m, OIVA_COV_M)(int dtype, int KC, const CovParams& p, cu
             OIVA_COV_CASE(double, 8)
         }
     }
+    oiva_set_error("cov_launch: unsupported source chunk %d", KC);
+    return OIVA_ERR_INVALID;
+}
+
+// per-bin weights (ILRMA): complex128 storage, M <= 8
+int OIVA_CAT(cov_launch_wbin_m, OIVA_COV_M)(int KC, const CovParams& p, cudaStream_t st, int* nsplit_out) {
+    if (COV_USE_BLOCKS) {
+        oiva_set_error("cov_launch: per-bin weights are implemented for M <= 8");
+        return OIVA_ERR_UNSUPPORTED;
+    }
+#define OIVA_COV_WCASE(KC_) \
+    if (KC == KC_) return launch<double, KC_, true>(p, st, nsplit_out);
+    OIVA_COV_WCASE(1)
+    OIVA_COV_WCASE(2)
+    OIVA_COV_WCASE(3)
+    OIVA_COV_WCASE(4)
+    OIVA_COV_WCASE(6)
+    OIVA_COV_WCASE(8)
+#undef OIVA_COV_WCASE
     oiva_set_error("cov_launch: unsupported source chunk %d", KC);
     return OIVA_ERR_INVALID;
 }

@@ -25,7 +25,7 @@ struct oiva_plan {
     int Tp, NG;
     int es;  // bytes per real element of X / Y
     // workspace offsets
-    size_t off_xg, off_c, off_cg, off_what, off_wg, off_vg, off_weff, off_r2part, off_r2, off_phi, off_wscale, off_evals, off_status, off_covws, off_sync;
+    size_t off_xg, off_c, off_cg, off_what, off_wg, off_vg, off_weff, off_r2part, off_r2, off_phi, off_wscale, off_evals, off_status, off_covws, off_sync, off_smcount;
     int resident;  // the persistent single-launch loop: 0 = not tried yet, 1 = in use, -1 = shape does not fit
     size_t covws_bytes;
     size_t ws_bytes;
@@ -136,6 +136,7 @@ extern "C" int oiva_plan_create(oiva_plan_t** out, const oiva_plan_desc* desc) {
     p->covws_bytes = oiva_weighted_cov_scratch_bytes(d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.n_src);
     p->off_covws = o;   o += align_up(p->covws_bytes);
     p->off_sync = o;    o += align_up(oiva_loop_resident_sync_bytes(d.n_batch, d.n_freq));
+    p->off_smcount = o; o += align_up(sizeof(unsigned) * B * K);  // completion counters of the frame-parallel source model
     p->ws_bytes = o;
     p->spans = new std::vector<TimedSpan>();
     p->pool = new std::vector<cudaEvent_t>();
@@ -272,6 +273,9 @@ static int plan_load_impl(oiva_plan_t* p, const void* X, void* stream, bool full
     OIVA_REQUIRE(X, "oiva_plan_load: null X");
     const oiva_plan_desc& d = p->d;
     int rc;
+    // (the source model's completion counters must start at zero; they return to zero after every epoch)
+    OIVA_CUDA_CHECK(cudaMemsetAsync(p->ws + p->off_smcount, 0, sizeof(unsigned) * (size_t)d.n_batch * d.n_src,
+                                    (cudaStream_t)stream));
     static const bool no_fuse = [] {
         const char* v = getenv("OIVA_NO_RELAYOUT_COV");
         return v && *v && *v != '0';
@@ -301,6 +305,8 @@ static int plan_load_impl(oiva_plan_t* p, const void* X, void* stream, bool full
 
 extern "C" int oiva_plan_adopt_samples(oiva_plan_t* p, void* stream) {
     PLAN_READY(p, "oiva_plan_adopt_samples");
+    OIVA_CUDA_CHECK(cudaMemsetAsync(p->ws + p->off_smcount, 0, sizeof(unsigned) * (size_t)p->d.n_batch * p->d.n_src,
+                                    (cudaStream_t)stream));
     int rc = plan_input_cov(p, stream);
     if (rc) return rc;
     p->loaded = true;
@@ -374,8 +380,8 @@ static int plan_update_from(oiva_plan_t* p, const double* r2src, int nch, void* 
     const oiva_plan_desc& d = p->d;
     double* phi = (double*)(p->ws + p->off_phi);
     double* wscale = (double*)(p->ws + p->off_wscale);
-    int rc = oiva_source_model(r2src, nch, phi, wscale, d.n_batch, d.n_frames, d.n_src, p->n_freq_total, d.model,
-                               stream);
+    int rc = oiva_source_model_ws(r2src, nch, phi, wscale, (unsigned*)(p->ws + p->off_smcount), d.n_batch, d.n_frames,
+                                  d.n_src, p->n_freq_total, d.model, stream);
     if (rc) return rc;
     {
         // one kernel for covariance + sweep where the covariances of a bin fit its lane's registers (cov_sweep.cuh)
@@ -537,12 +543,11 @@ extern "C" int oiva_plan_output(oiva_plan_t* p, int proj_back, void* Y, void* st
     PLAN_INITED(p, "oiva_plan_output");
     OIVA_REQUIRE(Y, "oiva_plan_output: null Y");
     const oiva_plan_desc& d = p->d;
-    // one launch: the filters come from the grouped W_hat, the projection-back scale from the grouped C, per lane
-    // (off_weff doubles as the scratch of the projection-back scales for M >= 9)
+    // the filters come from the grouped W_hat, the projection-back scales from the grouped C (off_weff is their scratch)
     int rc = oiva_demix_output_grouped(p->ws + p->off_xg, p->ws + p->off_wg, proj_back ? p->ws + p->off_cg : nullptr,
                                        p->ws + p->off_weff, Y, d.n_batch, d.n_frames, d.n_freq, d.n_chan, d.n_src, d.dtype, stream);
     if (rc) return rc;
-    p->launches += 1;
+    p->launches += proj_back ? 2 : 1;
     return OIVA_OK;
 }
 

@@ -210,52 +210,96 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) k_eigh(const cplx* __restric
         Q[i] = cmake((i / M == i % M) ? 1.0 : 0.0, 0.0);
     }
     __syncwarp();
+    // Parallel-ordered Jacobi: a sweep is Me - 1 rounds (Me = M rounded up to even) of a round-robin tournament; the
+    // Me / 2 index pairs of a round are disjoint, so their rotations are computed from the same A and applied together --
+    // first to the columns (A <- A U, Q <- Q U), then to the rows (A <- U^H A) -- by all 32 lanes.  (The first version
+    // applied one rotation at a time with M of 32 lanes busy: 28 dependent steps per sweep at M = 8 instead of 7.)
     const double eps = 1.1e-16;
-    for (int sweep = 0; sweep < 40; ++sweep) {
+    constexpr int Me = M + (M & 1), NP = Me / 2;
+    __shared__ double sRot[SOLVE_WARPS][NP > 0 ? NP : 1][4];  // c, s, Re ph, Im ph  (c = 2: pair idle this round)
+    __shared__ int sPair[SOLVE_WARPS][NP > 0 ? NP : 1][2];
+    for (int sweep = 0; sweep < 40 && M > 1; ++sweep) {
         int rotated = 0;
-        for (int p = 0; p < M - 1; ++p) {
-            for (int q = p + 1; q < M; ++q) {
-                const cplx apq = A[p * M + q];
-                const double app = A[p * M + p].x, aqq = A[q * M + q].x;
-                const double g = hypot(apq.x, apq.y);
-                if (!(g > eps * sqrt(fabs(app * aqq))) || g < 1e-300) continue;  // warp-uniform
-                ++rotated;
-                const cplx ph = cmake(apq.x / g, apq.y / g);
-                const double tau = (aqq - app) / (2.0 * g);
-                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                const double c = 1.0 / sqrt(1.0 + t * t);
-                const double s = t * c;
-                const cplx sphc = cmake(s * ph.x, -s * ph.y);  // s conj(ph)
-                const cplx cphc = cmake(c * ph.x, -c * ph.y);  // c conj(ph)
-                __syncwarp();
-                // A <- A U, Q <- Q U (columns p, q)
-                if (lane < M) {
-                    const int r = lane;
-                    cplx ap = A[r * M + p], aq = A[r * M + q];
-                    A[r * M + p] = csub(cscale(ap, c), cmul(sphc, aq));
-                    A[r * M + q] = cadd(cscale(ap, s), cmul(cphc, aq));
-                    cplx qp = Q[r * M + p], qq = Q[r * M + q];
-                    Q[r * M + p] = csub(cscale(qp, c), cmul(sphc, qq));
-                    Q[r * M + q] = cadd(cscale(qp, s), cmul(cphc, qq));
-                }
-                __syncwarp();
-                // A <- U^H A (rows p, q)
-                if (lane < M) {
-                    const int r = lane;
-                    const cplx sph = cmake(s * ph.x, s * ph.y), cph = cmake(c * ph.x, c * ph.y);
-                    cplx ap = A[p * M + r], aq = A[q * M + r];
-                    A[p * M + r] = csub(cscale(ap, c), cmul(sph, aq));
-                    A[q * M + r] = cadd(cscale(ap, s), cmul(cph, aq));
-                }
-                __syncwarp();
+        for (int round = 0; round < Me - 1; ++round) {
+            if (lane < NP) {
+                int p, q;
                 if (lane == 0) {
-                    A[p * M + q] = cmake(0.0, 0.0);
-                    A[q * M + p] = cmake(0.0, 0.0);
-                    A[p * M + p].y = 0.0;
-                    A[q * M + q].y = 0.0;
+                    p = Me - 1;
+                    q = round;
+                } else {
+                    p = (round + lane) % (Me - 1);
+                    q = (round - lane + (Me - 1)) % (Me - 1);
                 }
-                __syncwarp();
+                if (p > q) {
+                    const int t = p;
+                    p = q;
+                    q = t;
+                }
+                double c = 2.0, sn = 0.0, phx = 1.0, phy = 0.0;
+                if (q < M) {  // (odd M: the pair with the padding index sits out)
+                    const cplx apq = A[p * M + q];
+                    const double app = A[p * M + p].x, aqq = A[q * M + q].x;
+                    const double g = hypot(apq.x, apq.y);
+                    if (g > eps * sqrt(fabs(app * aqq)) && !(g < 1e-300)) {
+                        phx = apq.x / g;
+                        phy = apq.y / g;
+                        const double tau = (aqq - app) / (2.0 * g);
+                        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        c = 1.0 / sqrt(1.0 + t * t);
+                        sn = t * c;
+                    }
+                }
+                sRot[warp][lane][0] = c;
+                sRot[warp][lane][1] = sn;
+                sRot[warp][lane][2] = phx;
+                sRot[warp][lane][3] = phy;
+                sPair[warp][lane][0] = p;
+                sPair[warp][lane][1] = q;
             }
+            __syncwarp();
+            bool any = false;
+            // columns p, q of A and Q, one (pair, row) per lane and pass
+            for (int it = lane; it < NP * M; it += 32) {
+                const int pr = it / M, r = it - pr * M;
+                const double c = sRot[warp][pr][0];
+                if (c > 1.5) continue;
+                any = true;
+                const double sn = sRot[warp][pr][1];
+                const cplx ph = cmake(sRot[warp][pr][2], sRot[warp][pr][3]);
+                const int p = sPair[warp][pr][0], q = sPair[warp][pr][1];
+                const cplx sphc = cmake(sn * ph.x, -sn * ph.y);  // s conj(ph)
+                const cplx cphc = cmake(c * ph.x, -c * ph.y);    // c conj(ph)
+                const cplx ap = A[r * M + p], aq = A[r * M + q];
+                A[r * M + p] = csub(cscale(ap, c), cmul(sphc, aq));
+                A[r * M + q] = cadd(cscale(ap, sn), cmul(cphc, aq));
+                const cplx qp = Q[r * M + p], qq = Q[r * M + q];
+                Q[r * M + p] = csub(cscale(qp, c), cmul(sphc, qq));
+                Q[r * M + q] = cadd(cscale(qp, sn), cmul(cphc, qq));
+            }
+            __syncwarp();
+            // rows p, q of A
+            for (int it = lane; it < NP * M; it += 32) {
+                const int pr = it / M, r = it - pr * M;
+                const double c = sRot[warp][pr][0];
+                if (c > 1.5) continue;
+                const double sn = sRot[warp][pr][1];
+                const cplx ph = cmake(sRot[warp][pr][2], sRot[warp][pr][3]);
+                const int p = sPair[warp][pr][0], q = sPair[warp][pr][1];
+                const cplx sph = cmake(sn * ph.x, sn * ph.y), cph = cmake(c * ph.x, c * ph.y);
+                const cplx ap = A[p * M + r], aq = A[q * M + r];
+                A[p * M + r] = csub(cscale(ap, c), cmul(sph, aq));
+                A[q * M + r] = cadd(cscale(ap, sn), cmul(cph, aq));
+            }
+            __syncwarp();
+            if (lane < NP && sRot[warp][lane][0] < 1.5) {
+                const int p = sPair[warp][lane][0], q = sPair[warp][lane][1];
+                A[p * M + q] = cmake(0.0, 0.0);
+                A[q * M + p] = cmake(0.0, 0.0);
+                A[p * M + p].y = 0.0;
+                A[q * M + q].y = 0.0;
+            }
+            __syncwarp();
+            if (__any_sync(0xffffffffu, any)) ++rotated;
         }
         if (rotated == 0) break;
     }

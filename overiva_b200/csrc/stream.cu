@@ -108,10 +108,51 @@ __global__ void __launch_bounds__(256) k_source_model(const double* __restrict__
 // arithmetic and summation orders: (1) the sum over the partials and the model function for chunks of frames in
 // parallel (r is parked in phi), (2) per (mixture, source) gamma -- lane tl adds r[tl], r[tl+32], ... in ascending
 // order, then the xor tree, exactly as above -- followed by phi = 1 / max(r / gamma, 1e-15) in place.
+// (ph: the r values of one (mixture, source), possibly written by other CTAs of the same launch: read through L2)
+__device__ __forceinline__ void source_finish_body(double* ph, double* __restrict__ wscale, int b, int k, int T, int Tp,
+                                                   int K, int model, double* red) {
+    if (threadIdx.x < 32) {
+        double lsum = 0.0;
+#pragma unroll 8
+        for (int t = threadIdx.x; t < T; t += 32) lsum += __ldcg(ph + t);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+        if (threadIdx.x == 0) red[0] = lsum;
+    }
+    __syncthreads();
+    const bool rescale = (model == OIVA_MODEL_LAPLACE || model == OIVA_MODEL_GAUSS || model == OIVA_MODEL_NONE);
+    const double gamma = rescale ? red[0] / (double)T : 1.0;
+    for (int t = threadIdx.x; t < Tp; t += 256) {
+        double r = 0.0;
+        if (t < T) {
+            r = __ldcg(ph + t) / gamma;
+            if (r < 1e-15) r = 1e-15;
+            r = 1.0 / r;
+        }
+        ph[t] = r;
+    }
+    if (threadIdx.x == 0 && wscale) {
+        double w = 1.0;
+        if (model == OIVA_MODEL_LAPLACE) w = 1.0 / gamma;
+        else if (model == OIVA_MODEL_GAUSS) w = 1.0 / sqrt(gamma);
+        wscale[(size_t)b * K + k] = w;
+    }
+}
+__global__ void __launch_bounds__(256) k_source_finish(double* __restrict__ phi, double* __restrict__ wscale, int T, int Tp,
+                                                       int K, int model) {
+    __shared__ double red[1];
+    const int b = blockIdx.x / K, k = blockIdx.x - b * K;
+    source_finish_body(phi + ((size_t)b * K + k) * Tp, wscale, b, k, T, Tp, K, model, red);
+}
 // (sm_chunk: frames per CTA of the first kernel, a multiple of 32)
+// counters != nullptr (one zeroed word per (mixture, source), left at zero again): the LAST CTA of a (mixture, source) to
+// finish its frames also runs the finishing step -- one launch for the whole source model.
 __global__ void __launch_bounds__(256) k_source_r(const double* __restrict__ part, int NCH, double* __restrict__ phi, int T,
-                                                  int Tp, int K, int F_total, int model, int sm_chunk) {
+                                                  int Tp, int K, int F_total, int model, int sm_chunk,
+                                                  unsigned* counters, double* __restrict__ wscale) {
     __shared__ double slice[8][32];
+    __shared__ double red[1];
+    __shared__ int is_last;
     const int b = blockIdx.x / K, k = blockIdx.x - b * K;
     const int tl = threadIdx.x & 31, cs = threadIdx.x >> 5;
     double* ph = phi + ((size_t)b * K + k) * Tp;
@@ -143,42 +184,22 @@ __global__ void __launch_bounds__(256) k_source_r(const double* __restrict__ par
         }
         __syncthreads();
     }
-}
-__global__ void __launch_bounds__(256) k_source_finish(double* __restrict__ phi, double* __restrict__ wscale, int T, int Tp,
-                                                       int K, int model) {
-    __shared__ double red[1];
-    const int b = blockIdx.x / K, k = blockIdx.x - b * K;
-    double* ph = phi + ((size_t)b * K + k) * Tp;
-    if (threadIdx.x < 32) {
-        double lsum = 0.0;
-#pragma unroll 8
-        for (int t = threadIdx.x; t < T; t += 32) lsum += ph[t];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
-        if (threadIdx.x == 0) red[0] = lsum;
+    if (!counters) return;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned old = atomicAdd(counters + blockIdx.x, 1u);
+        is_last = old == gridDim.y - 1;
+        if (is_last) {
+            counters[blockIdx.x] = 0;  // ready for the next epoch
+            __threadfence();
+        }
     }
     __syncthreads();
-    const bool rescale = (model == OIVA_MODEL_LAPLACE || model == OIVA_MODEL_GAUSS || model == OIVA_MODEL_NONE);
-    const double gamma = rescale ? red[0] / (double)T : 1.0;
-    for (int t = threadIdx.x; t < Tp; t += 256) {
-        double r = 0.0;
-        if (t < T) {
-            r = ph[t] / gamma;
-            if (r < 1e-15) r = 1e-15;
-            r = 1.0 / r;
-        }
-        ph[t] = r;
-    }
-    if (threadIdx.x == 0 && wscale) {
-        double w = 1.0;
-        if (model == OIVA_MODEL_LAPLACE) w = 1.0 / gamma;
-        else if (model == OIVA_MODEL_GAUSS) w = 1.0 / sqrt(gamma);
-        wscale[(size_t)b * K + k] = w;
-    }
+    if (is_last) source_finish_body(ph, wscale, b, k, T, Tp, K, model, red);
 }
 
 // projection-back scales from the grouped state, any M (runtime loops; thread per bin): z[gi][k][lane] with exactly the
-// arithmetic of k_projback_filters / projback_scale
+// arithmetic of k_projback_filters (solve.cu)
 __global__ void __launch_bounds__(128) k_projback_z(const cplx* __restrict__ Wg, const cplx* __restrict__ Cg,
                                                     cplx* __restrict__ Zg, long long G, int M, int K) {
     const int lane = threadIdx.x & 31;
@@ -254,8 +275,19 @@ extern "C" int oiva_sum_partials(const double* r2part, int n_chunks, double* r2,
     return OIVA_OK;
 }
 
+extern "C" int oiva_source_model_ws(const double* r2part, int n_chunks, double* phi, double* wscale, unsigned* counters,
+                                    int n_batch, int n_frames, int n_src, int n_freq_total, int model, void* stream);
+
 extern "C" int oiva_source_model(const double* r2part, int n_chunks, double* phi, double* wscale, int n_batch,
                                  int n_frames, int n_src, int n_freq_total, int model, void* stream) {
+    return oiva_source_model_ws(r2part, n_chunks, phi, wscale, nullptr, n_batch, n_frames, n_src, n_freq_total, model,
+                                stream);
+}
+
+// counters: n_batch * n_src zeroed words of device memory (left zeroed), or NULL.  With counters the frame-parallel form
+// is one launch (the last CTA of a (mixture, source) finishes it) instead of two.
+extern "C" int oiva_source_model_ws(const double* r2part, int n_chunks, double* phi, double* wscale, unsigned* counters,
+                                    int n_batch, int n_frames, int n_src, int n_freq_total, int model, void* stream) {
     OIVA_REQUIRE(r2part && phi && n_chunks >= 1, "oiva_source_model: bad arguments");
     OIVA_REQUIRE(n_batch > 0 && n_frames > 0 && n_src >= 1 && n_freq_total > 0, "oiva_source_model: bad shape");
     const int Tp = oiva_frame_pitch(n_frames);
@@ -268,11 +300,13 @@ extern "C" int oiva_source_model(const double* r2part, int n_chunks, double* phi
         const int sm_chunk = n_frames > 2048 ? 256 : 32;
         const int chunks = (Tp + sm_chunk - 1) / sm_chunk;
         OIVA_REQUIRE(chunks <= 65535, "oiva_source_model: too many frames");
-        k_source_r<<<dim3((unsigned)(n_batch * n_src), (unsigned)chunks), 256, 0, st>>>(r2part, n_chunks, phi, n_frames, Tp,
-                                                                                         n_src, n_freq_total, model, sm_chunk);
+        k_source_r<<<dim3((unsigned)(n_batch * n_src), (unsigned)chunks), 256, 0, st>>>(
+            r2part, n_chunks, phi, n_frames, Tp, n_src, n_freq_total, model, sm_chunk, counters, wscale);
         OIVA_LAUNCH_CHECK();
-        k_source_finish<<<(unsigned)(n_batch * n_src), 256, 0, st>>>(phi, wscale, n_frames, Tp, n_src, model);
-        OIVA_LAUNCH_CHECK();
+        if (!counters) {
+            k_source_finish<<<(unsigned)(n_batch * n_src), 256, 0, st>>>(phi, wscale, n_frames, Tp, n_src, model);
+            OIVA_LAUNCH_CHECK();
+        }
         return OIVA_OK;
     }
     k_source_model<<<(unsigned)(n_batch * n_src), 256, 0, st>>>(r2part, n_chunks, phi, wscale, n_frames, Tp, n_src,
@@ -291,8 +325,8 @@ extern "C" int oiva_demix_output(const void* Xg, const void* Weff, void* Y, int 
     return stream_launch(n_chan, KIND_OUTPUT, dtype, p, (long long)n_batch * p.L.NG, (cudaStream_t)stream);
 }
 
-// the final demix straight from the loop's grouped state: Y = (w_k z_k)^H x with the projection-back scale computed per
-// lane from the grouped covariance (Cg != NULL) -- one launch instead of ungroup + projback_filters + demix_output
+// the final demix straight from the loop's grouped state: Y = (w_k z_k)^H x with the projection-back scales computed per
+// bin from the grouped covariance (Cg != NULL) -- two launches, no row-major copies (was ungroup + projback + demix)
 extern "C" int oiva_demix_output_grouped(const void* Xg, const void* Wg, const void* Cg, void* zscratch, void* Y,
                                          int n_batch, int n_frames, int n_freq, int n_chan, int n_src, int dtype,
                                          void* stream) {
@@ -302,10 +336,8 @@ extern "C" int oiva_demix_output_grouped(const void* Xg, const void* Wg, const v
     OIVA_REQUIRE(n_src <= n_chan, "oiva_demix_output_grouped: n_src > n_chan");
     StreamParams p = make_params(Xg, Wg, n_chan, n_frames, n_freq, n_chan, n_src, 1);
     p.Y = Y;
-    if (Cg && n_chan <= PROJBACK_INLINE_MAX_M) {
-        p.Cg = (const cplx*)Cg;
-    } else if (Cg) {  // many channels: the scales in a small kernel of their own
-        OIVA_REQUIRE(zscratch, "oiva_demix_output_grouped: n_chan > %d needs zscratch", PROJBACK_INLINE_MAX_M);
+    if (Cg) {  // the scales in a small kernel of their own (thread per bin on the grouped arrays)
+        OIVA_REQUIRE(zscratch, "oiva_demix_output_grouped: projection back needs zscratch");
         const long long G = (long long)n_batch * p.L.NG;
         k_projback_z<<<(unsigned)((G + 3) / 4), 128, 0, (cudaStream_t)stream>>>((const cplx*)Wg, (const cplx*)Cg,
                                                                                   (cplx*)zscratch, G, n_chan, n_src);

@@ -14,6 +14,9 @@
 namespace oiva {
 
 constexpr int POWER_FB = 8;  // frames reduced together in the power kernel
+// one warp per chunk of KC sources, K <= 16: the block size bound of the one-warp-per-chunk kernels.  (A blanket bound of
+// 512 threads capped them at 128 registers: the KC = 3 and 4 variants with M >= 4 spilled their filters.)
+__host__ __device__ constexpr int stream_max_threads(int KC) { return 32 * ((OIVA_MAX_M + KC - 1) / KC); }
 
 // Sum over the 32 lanes (bins) of NF per-lane values (NF = 8, 4 or 2 frames): log2(NF) transposing exchanges (each halves
 // the live values), then plain xor sums.  Whatever NF, a frame's 32 values are added in the same order (partners at lane
@@ -51,12 +54,11 @@ struct StreamParams {
     double* r2part;   // (B, NG, K, Tp)
     void* Y;          // (B, T, F, K) interleaved complex ST
     void* Xr;         // grouped samples with K channels
-    const cplx* Cg;   // output kernels, M <= 8: grouped input covariance [gi][NE][32] -> projection back folded into the
-                      // filters inside the kernel (projback_scale)
-    const cplx* Zg;   // output kernels, M >= 9: the projection-back scales z [gi][K][32] from k_projback_z (the unrolled
-                      // in-kernel version is ~2 MB of code per channel count there, for kernels that run milliseconds)
+    const cplx* Zg;   // output kernels: projection-back scales z [gi][K][32] from k_projback_z (stream.cu), or nullptr.
+                      // (Computing z inside the output kernels was tried: the M x M products next to the filter
+                      // registers spill at the 128-register cap of these kernels from M = 5 on -- 66 ms instead of 3 ms
+                      // for the M = K = 8 output.)
 };
-constexpr int PROJBACK_INLINE_MAX_M = 8;
 
 // w_k <- w_k z_k with z from the grouped array of k_projback_z
 template <int M, int KC>
@@ -68,48 +70,6 @@ __device__ __forceinline__ void projback_apply(cplx (&w)[M][KC], const cplx* __r
 #pragma unroll
             for (int a = 0; a < M; ++a) w[a][k] = cmul(w[a][k], z);
         }
-    }
-}
-
-// Projection back folded into this lane's filters: w_k <- w_k z_k, z_k = (w_k^H C e_0) / (w_k^H C w_k), 1 where the
-// denominator is not positive (pyroomacoustics.bss.projection_back as called at overiva.py:197-199; no pass over Y:
-// sum_t conj(x_0) y_k = T w_k^H C e_0, sum_t |y_k|^2 = T w_k^H C w_k).  The arithmetic and its order are those of
-// k_projback_filters (solve.cu), which does the same on row-major arrays.  Cl: this lane's element 0 of Cg[gi].
-template <int M, int KC>
-__device__ __forceinline__ void projback_scale(cplx (&w)[M][KC], const cplx* __restrict__ Cl) {
-    cplx num[KC];
-    double den[KC];
-#pragma unroll
-    for (int k = 0; k < KC; ++k) {
-        num[k] = cmake(0.0, 0.0);
-        den[k] = 0.0;
-    }
-#pragma unroll
-    for (int a = 0; a < M; ++a) {
-        cplx crow[M];  // row a of the Hermitian C from its stored lower triangle
-#pragma unroll
-        for (int b = 0; b < M; ++b) {
-            const int hi = a >= b ? a : b, lo = a >= b ? b : a;
-            cplx v = ld_nc_c(Cl + (size_t)(hi * (hi + 1) / 2 + lo) * OIVA_GROUP);
-            if (a < b) v.y = -v.y;
-            crow[b] = v;
-        }
-#pragma unroll
-        for (int k = 0; k < KC; ++k) {
-            const cplx wa = w[a][k];
-            cfmac(num[k], wa, crow[0]);
-            cplx cw = cmake(0.0, 0.0);
-#pragma unroll
-            for (int b = 0; b < M; ++b) cfma(cw, crow[b], w[b][k]);
-            den[k] += wa.x * cw.x + wa.y * cw.y;  // Re(conj(w_a) (C w)_a)
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < KC; ++k) {
-        cplx z = cmake(1.0, 0.0);
-        if (den[k] > 0.0) z = cmake(num[k].x / den[k], num[k].y / den[k]);
-#pragma unroll
-        for (int a = 0; a < M; ++a) w[a][k] = cmul(w[a][k], z);
     }
 }
 
@@ -143,7 +103,7 @@ __device__ __forceinline__ void demix_frame(cplx (&y)[KC], const cplx (&x)[M], c
 // frame blocks of its split.  After |y|^2 the 32 lanes (bins) of POWER_FB frames are summed with a transposing
 // butterfly (each exchange halves the live values), the group's partial statistic goes to r2part.
 template <typename ST, int M, int KC>
-__global__ void __launch_bounds__(512) k_demix_power(const StreamParams p) {
+__global__ void __launch_bounds__(stream_max_threads(KC)) k_demix_power(const StreamParams p) {
     typedef typename StoreC<ST>::type XC;
     const GroupLayout& L = p.L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -196,9 +156,11 @@ __global__ void __launch_bounds__(512) k_demix_power(const StreamParams p) {
 // OUTPUT = false: the statistic (k_demix_power's result, same arithmetic); OUTPUT = true: the demixed samples Y
 // (k_demix_output's result).  Measured: DESIGN.md.
 // grid (G, nsplit); dynamic smem = 128 + 2 * POWER_FB * M * 32 * sizeof(XC)
-// (M >= 13 runs at most 12 warps -- <= 8 source chunks of 2, or <= 3 chunks x 4 sub-blocks -- and needs ~170 registers)
+// (M >= 13 runs at most 12 warps -- <= 8 source chunks of 2, or <= 3 chunks x 4 sub-blocks -- and needs ~170 registers;
+// otherwise the block size follows from the launcher's rule: >= 8 chunks x 1 sub-block, 4-7 chunks x 2, 1-3 chunks x 4)
 template <typename ST, int M, int KC, int FBW, bool OUTPUT>
-__global__ void __launch_bounds__(M >= 13 ? 384 : 512) k_demix_staged(const StreamParams p) {
+__global__ void __launch_bounds__(M >= 13 ? 384 : (FBW == 8 ? stream_max_threads(KC) : (FBW == 4 ? 448 : 384)))
+    k_demix_staged(const StreamParams p) {
     typedef typename StoreC<ST>::type XC;
     constexpr int NSUB = POWER_FB / FBW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -228,11 +190,7 @@ __global__ void __launch_bounds__(M >= 13 ? 384 : 512) k_demix_staged(const Stre
     cplx w[M][KC];
     load_filters<M, KC>(w, p, b * L.F + (bin_ok ? f : 0), gi, lane, bin_ok, k0);
     if constexpr (OUTPUT) {
-        if constexpr (M <= PROJBACK_INLINE_MAX_M) {
-            if (p.Cg) projback_scale<M, KC>(w, p.Cg + (size_t)gi * oiva_tri(M) * OIVA_GROUP + lane);
-        } else {
-            if (p.Zg) projback_apply<M, KC>(w, p.Zg + (size_t)gi * p.K * OIVA_GROUP + lane, k0, p.K);
-        }
+        if (p.Zg) projback_apply<M, KC>(w, p.Zg + (size_t)gi * p.K * OIVA_GROUP + lane, k0, p.K);
     }
     const XC* xg = reinterpret_cast<const XC*>(p.Xg) + (size_t)gi * L.group_elems();
     XC* Y = reinterpret_cast<XC*>(p.Y);
@@ -299,7 +257,7 @@ __global__ void __launch_bounds__(M >= 13 ? 384 : 512) k_demix_staged(const Stre
 
 // grid (G, nsplit), block = 32 * ceil(K/KC)
 template <typename ST, int M, int KC>
-__global__ void __launch_bounds__(512) k_demix_output(const StreamParams p) {
+__global__ void __launch_bounds__(stream_max_threads(KC)) k_demix_output(const StreamParams p) {
     typedef typename StoreC<ST>::type XC;
     const GroupLayout& L = p.L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -311,11 +269,7 @@ __global__ void __launch_bounds__(512) k_demix_output(const StreamParams p) {
     const int k0 = warp * KC;
     cplx w[M][KC];
     load_filters<M, KC>(w, p, b * L.F + (bin_ok ? f : 0), gi, lane, bin_ok, k0);
-    if constexpr (M <= PROJBACK_INLINE_MAX_M) {
-        if (p.Cg) projback_scale<M, KC>(w, p.Cg + (size_t)gi * oiva_tri(M) * OIVA_GROUP + lane);
-    } else {
-        if (p.Zg) projback_apply<M, KC>(w, p.Zg + (size_t)gi * p.K * OIVA_GROUP + lane, k0, p.K);
-    }
+    if (p.Zg) projback_apply<M, KC>(w, p.Zg + (size_t)gi * p.K * OIVA_GROUP + lane, k0, p.K);
     const XC* xg = reinterpret_cast<const XC*>(p.Xg) + (size_t)gi * L.group_elems();
     XC* Y = reinterpret_cast<XC*>(p.Y);
     const int t_begin = (int)((long long)L.T * blockIdx.y / p.nsplit);
@@ -337,7 +291,7 @@ __global__ void __launch_bounds__(512) k_demix_output(const StreamParams p) {
 
 // grid (G, nsplit), block = 32 * ceil(K/KC): writes Xr[gi][t][k][lane]
 template <typename ST, int M, int KC>
-__global__ void __launch_bounds__(512) k_project_rows(const StreamParams p) {
+__global__ void __launch_bounds__(stream_max_threads(KC)) k_project_rows(const StreamParams p) {
     typedef typename StoreC<ST>::type XC;
     const GroupLayout& L = p.L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

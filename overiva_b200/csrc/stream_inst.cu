@@ -16,8 +16,11 @@ namespace oiva {
 // (M >= 13: two sources per warp -- 64 filter values -- halve the shared-memory reads of the staged kernels)
 constexpr int kc_cap() { return OIVA_M >= 13 ? 2 : ((24 / OIVA_M) > 4 ? 4 : (24 / OIVA_M)); }
 static int pick_kc(int K) {
-    int kc = K < 4 ? K : 4;
-    return kc < kc_cap() ? kc : kc_cap();
+    // the fewest source chunks the register budget allows, then chunks of EQUAL size: the warps of a CTA share the
+    // staged frames and wait for each other, so K = 6 runs as 3 + 3 sources, not 4 + 2
+    const int cap = kc_cap() < 4 ? kc_cap() : 4;
+    const int chunks = (K + cap - 1) / cap;
+    return (K + chunks - 1) / chunks;
 }
 
 static int frame_splits(long long G, int units) {

@@ -9,7 +9,9 @@ from overiva_b200.core import DemixPlan
 from overiva_b200.synth import stft_domain_batch_torch
 
 SHAPES = {"cfg1": (1, 116, 2049, 4, 2), "cfg2": (1, 116, 2049, 6, 6), "cfg3": (1, 467, 2049, 8, 2),
-          "cfg5": (1, 14061, 2049, 16, 4), "cfg5_shard8": (1, 14061, 256, 16, 4), "cfg4_b64": (64, 116, 2049, 6, 2)}
+          "cfg5": (1, 14061, 2049, 16, 4), "cfg5_shard8": (1, 14061, 256, 16, 4), "cfg4_b64": (64, 116, 2049, 6, 2),
+          # determined AuxIVA batches of the paper sweep
+          "det4_b256": (256, 116, 2049, 4, 4), "det6_b256": (256, 116, 2049, 6, 6), "det8_b256": (256, 116, 2049, 8, 8)}
 dev = torch.device("cuda", 0)
 for name in (sys.argv[1].split(",") if len(sys.argv) > 1 else SHAPES):
     B, T, F, M, K = SHAPES[name]
