@@ -97,6 +97,13 @@ size_t oiva_weighted_cov_scratch_bytes(int n_batch, int n_frames, int n_freq, in
 int oiva_weighted_cov_ws(const void* Xg, const double* phi, void* Vg, void* scratch, size_t scratch_bytes,
                          int n_batch, int n_frames, int n_freq, int n_chan, int n_src, int dtype, void* stream);
 
+/* Weights per (source, frame, BIN): winv grouped [gi][k][Tp][32] float64.  V_k[f] = (1/T) sum_t winv_k(f,t) x x^H, the
+ * auxiliary variable of ILRMA (source model r_k(f,t), winv = 1/r).  complex128 samples, n_chan <= 8 (else
+ * OIVA_ERR_UNSUPPORTED); scratch as for oiva_weighted_cov_ws.
+ * replaces: the covariance inside pyroomacoustics.bss.ilrma (called at overiva_oneshot.py:331-339, overiva_sim.py:309-311). */
+int oiva_weighted_cov_binwise(const void* Xg, const double* winv, void* Vg, void* scratch, size_t scratch_bytes,
+                              int n_batch, int n_frames, int n_freq, int n_chan, int n_src, void* stream);
+
 /* oiva_relayout + the unweighted oiva_weighted_cov in ONE pass over X (read X once, write Xg and Cg): M <= 8, and for
  * complex64 an even F*M (16-byte aligned rows); oiva_relayout_cov_supported() tells.  Cg: grouped lower-triangle
  * covariance (oiva_unpack_cov gives the full matrices), bit-identical to the two-kernel path.  scratch as for
@@ -121,6 +128,11 @@ int oiva_unpack_cov(const void* Vg, void* V, int n_batch, int n_freq, int n_chan
  * Y is never materialised inside the loop. */
 int oiva_demix_power(const void* Xg, const void* W, int w_cols, int w_grouped, double* r2part, int n_batch,
                      int n_frames, int n_freq, int n_chan, int n_src, int dtype, void* stream);
+
+/* oiva_demix_power that also writes the per-bin powers |y_k(f,t)|^2: Pfull grouped [gi][k][Tp][32] float64 (padding
+ * frames and padded bins zero).  replaces: the demix + np.power(abs(Y), 2) of pyroomacoustics.bss.ilrma. */
+int oiva_demix_power_full(const void* Xg, const void* W, int w_cols, int w_grouped, double* r2part, double* Pfull,
+                          int n_batch, int n_frames, int n_freq, int n_chan, int n_src, int dtype, void* stream);
 
 /* r2[b][k][t] = sum_chunks r2part[b][chunk][k][t] (fixed order, deterministic).  Used on its own by the
  * frequency-sharded driver, which all-reduces r2 across ranks before oiva_source_model(n_chunks=1). */
@@ -233,6 +245,36 @@ int oiva_ogive_setup(const void* C, void* Cinv, double* cnorm, int* status, int 
 int oiva_ogive_a_from_w(const void* w, void* a, const void* C, int n_rows, int n_chan, void* stream);
 int oiva_ogive_switching(const void* a, const void* C, const double* cnorm, uint8_t* do_a, int n_rows,
                          int n_chan, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * ILRMA: the NMF source model around the shared demix / covariance / sweep kernels (csrc/ilrma.cu).
+ * replaces: pyroomacoustics.bss.ilrma(X, n_iter, n_components, proj_back, callback) as called at
+ * overiva_oneshot.py:331-339 and overiva_sim.py:309-311 (third-party, absent from the reference tree; restated from the
+ * published algorithm in oracle/ilrma_oracle.py -- parity unpinned).  Determined (n_src == n_chan), n_chan <= 8.
+ * Arrays (device, float64): Pg, iRg grouped [gi][k][Tp][32] (powers |y|^2 and 1 / r_k(f,t)); Tg grouped [gi][k][L][32]
+ * (NMF bases); Vn (B, K, Tp, L) (NMF activations); Vpart oiva_ilrma_vpart_bytes(); lam (B, K).  L = n_components <= 8.
+ * One epoch = oiva_ilrma_nmf -> oiva_weighted_cov_binwise(iRg) -> oiva_ip_update -> oiva_demix_power_full ->
+ * oiva_ilrma_rescale.
+ * ---------------------------------------------------------------------------------------------- */
+size_t oiva_ilrma_vpart_bytes(int n_batch, int n_frames, int n_freq, int n_src, int n_comp);
+/* T0 (B,K,F,L), V0 (B,K,T,L) row-major device arrays -> Tg, Vn and iRg = 1 / (T V^T) */
+int oiva_ilrma_set_model(const double* T0, const double* V0, double* Tg, double* Vn, double* iRg, int n_batch, int n_frames,
+                         int n_freq, int n_src, int n_comp, void* stream);
+int oiva_ilrma_get_model(const double* Tg, const double* Vn, double* Tout, double* Vout, int n_batch, int n_frames,
+                         int n_freq, int n_src, int n_comp, void* stream);
+/* the multiplicative updates of all K sources: T *= sqrt((P r^-2) V / (r^-1 V)), clamp at eps, r = T V^T;
+ * V *= sqrt((P r^-2)^T T / (r^-1)^T T), clamp, r = T V^T; iRg <- 1 / r */
+int oiva_ilrma_nmf(const double* Pg, double* iRg, double* Tg, double* Vn, double* Vpart, int n_batch, int n_frames,
+                   int n_freq, int n_src, int n_comp, double eps, void* stream);
+/* lam[b][k] = 1 / sqrt(mean_{f,t} P_k) from the statistic partials r2part (B,NG,K,Tp); then w_k *= lam (scale_w != 0),
+ * P_k, T_k *= lam^2, iR_k /= lam^2 */
+int oiva_ilrma_rescale(const double* r2part, double* lam, void* Wg, double* Pg, double* iRg, double* Tg, int n_batch,
+                       int n_frames, int n_freq, int n_chan, int n_src, int n_comp, int scale_w, void* stream);
+/* Zg [gi][K][32] c128 <- lam[b][k] (invert != 0: 1 / lam): a real per-source scale for oiva_demix_output_scaled */
+int oiva_ilrma_fill_scale(const double* lam, void* Zg, int n_batch, int n_freq, int n_src, int invert, void* stream);
+/* oiva_demix_output_grouped with caller-supplied per-bin scales Zg [gi][K][32] c128 (NULL: none): Y = (w_k z_k)^H x */
+int oiva_demix_output_scaled(const void* Xg, const void* Wg, const void* Zg, void* Y, int n_batch, int n_frames, int n_freq,
+                             int n_chan, int n_src, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * STFT analysis / synthesis on the device (the step either side of the loop in the reference's drivers).
@@ -354,6 +396,12 @@ int oiva_plan_status(oiva_plan_t* plan, void* stream);
 int oiva_plan_status_vector(oiva_plan_t* plan, int* status_host, void* stream);
 /* number of kernels launched by this plan since creation (bench.py's gpu_launches) */
 long long oiva_plan_launch_count(const oiva_plan_t* plan);
+/* device pointers into the bound workspace for callers that sequence kernels themselves on the plan's arrays (ILRMA):
+ * which = 0 grouped W_hat (G, M*M, 32) c128 | 1 grouped input covariance (G, NE, 32) | 2 grouped weighted covariances
+ * (G, K, NE, 32) | 3 statistic partials r2part (B, NG, K, Tp) f64 | 4 frame-split scratch of the covariance kernel
+ * (oiva_plan_scratch_bytes bytes; NULL if none) | 5 scratch for output scales (G, K, 32) c128 */
+void* oiva_plan_array(oiva_plan_t* plan, int which);
+size_t oiva_plan_scratch_bytes(const oiva_plan_t* plan);
 
 /* Optional per-kernel timing for the roofline report: when enabled, CUDA events are recorded on the
  * launching stream around every launch of the three loop kernels.  oiva_plan_read_timing() (call it after

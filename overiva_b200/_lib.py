@@ -83,6 +83,17 @@ SIGNATURES = {
     "oiva_loop_resident_sync_bytes": (_sz, [_i, _i]),
     "oiva_loop_resident": (_i, [_p, _p, _p, _p, _p, _p, _sz, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "oiva_fp64_peak": (_i, [_i, _i, _i, C.POINTER(C.c_double), _p]),
+    "oiva_demix_power_full": (_i, [_p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "oiva_weighted_cov_binwise": (_i, [_p, _p, _p, _p, _sz, _i, _i, _i, _i, _i, _p]),
+    "oiva_ilrma_vpart_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "oiva_ilrma_set_model": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "oiva_ilrma_get_model": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "oiva_ilrma_nmf": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _d, _p]),
+    "oiva_ilrma_rescale": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "oiva_ilrma_fill_scale": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "oiva_demix_output_scaled": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "oiva_plan_array": (_p, [_p, _i]),
+    "oiva_plan_scratch_bytes": (_sz, [_p]),
     "oiva_plan_create": (_i, [C.POINTER(_p), C.POINTER(PlanDesc)]),
     "oiva_plan_destroy": (None, [_p]),
     "oiva_plan_workspace_bytes": (_sz, [_p]),

@@ -227,6 +227,24 @@ extern "C" double* oiva_plan_r2(oiva_plan_t* p) { return (p && p->ws) ? (double*
 extern "C" size_t oiva_plan_r2_elems(const oiva_plan_t* p) {
     return p ? (size_t)p->d.n_batch * p->d.n_src * p->Tp : 0;
 }
+// device pointers into the bound workspace for callers that sequence kernels themselves on the plan's arrays (ILRMA):
+// which = 0 grouped W_hat (G, M*M, 32) c128 | 1 grouped input covariance Cg (G, NE, 32) | 2 grouped weighted covariances
+// Vg (G, K, NE, 32) | 3 statistic partials r2part (B, NG, K, Tp) f64 | 4 frame-split scratch of the covariance kernel
+// (oiva_plan_scratch_bytes) | 5 scratch of the output scales (G, K, 32) c128
+extern "C" void* oiva_plan_array(oiva_plan_t* p, int which) {
+    if (!p || !p->ws) return nullptr;
+    switch (which) {
+        case 0: return p->ws + p->off_wg;
+        case 1: return p->ws + p->off_cg;
+        case 2: return p->ws + p->off_vg;
+        case 3: return p->ws + p->off_r2part;
+        case 4: return p->covws_bytes ? p->ws + p->off_covws : nullptr;
+        case 5: return p->ws + p->off_weff;
+    }
+    return nullptr;
+}
+extern "C" size_t oiva_plan_scratch_bytes(const oiva_plan_t* p) { return p ? p->covws_bytes : 0; }
+
 extern "C" long long oiva_plan_launch_count(const oiva_plan_t* p) { return p ? p->launches : 0; }
 
 // input covariance C = (1/T) sum_t x x^H (overiva.py:87): grouped accumulation, then full row-major matrices

@@ -265,6 +265,21 @@ extern "C" int oiva_demix_power(const void* Xg, const void* W, int w_cols, int w
     return stream_launch(n_chan, KIND_POWER, dtype, p, (long long)n_batch * p.L.NG, (cudaStream_t)stream);
 }
 
+// the statistic AND the per-bin powers |y_k(f, t)|^2 (Pfull: grouped [gi][k][Tp][32] float64) in one pass: ILRMA's
+// spectrogram model needs every bin's power, its scale normalisation the sums (r2part).  W as for oiva_demix_power.
+extern "C" int oiva_demix_power_full(const void* Xg, const void* W, int w_cols, int w_grouped, double* r2part, double* Pfull,
+                                     int n_batch, int n_frames, int n_freq, int n_chan, int n_src, int dtype, void* stream) {
+    OIVA_REQUIRE(Xg && W && r2part && Pfull, "oiva_demix_power_full: null pointer");
+    OIVA_REQUIRE(w_cols >= n_src, "oiva_demix_power_full: w_cols %d < n_src %d", w_cols, n_src);
+    int rc = check_dims("oiva_demix_power_full", n_batch, n_frames, n_freq, n_chan, n_src);
+    if (rc) return rc;
+    OIVA_REQUIRE(n_src <= n_chan, "oiva_demix_power_full: n_src > n_chan");
+    StreamParams p = make_params(Xg, W, w_cols, n_frames, n_freq, n_chan, n_src, w_grouped);
+    p.r2part = r2part;
+    p.Pfull = Pfull;
+    return stream_launch(n_chan, KIND_POWER, dtype, p, (long long)n_batch * p.L.NG, (cudaStream_t)stream);
+}
+
 extern "C" int oiva_sum_partials(const double* r2part, int n_chunks, double* r2, int n_batch, int n_frames, int n_src,
                                  void* stream) {
     OIVA_REQUIRE(r2part && r2 && n_chunks >= 1, "oiva_sum_partials: bad arguments");
@@ -344,6 +359,20 @@ extern "C" int oiva_demix_output_grouped(const void* Xg, const void* Wg, const v
         OIVA_LAUNCH_CHECK();
         p.Zg = (const cplx*)zscratch;
     }
+    return stream_launch(n_chan, KIND_OUTPUT, dtype, p, (long long)n_batch * p.L.NG, (cudaStream_t)stream);
+}
+
+// oiva_demix_output_grouped with caller-supplied per-bin scales Zg [gi][K][32] c128 (NULL: none) instead of the
+// projection-back scales: Y = (w_k z_k)^H x
+extern "C" int oiva_demix_output_scaled(const void* Xg, const void* Wg, const void* Zg, void* Y, int n_batch, int n_frames,
+                                        int n_freq, int n_chan, int n_src, int dtype, void* stream) {
+    OIVA_REQUIRE(Xg && Wg && Y, "oiva_demix_output_scaled: null pointer");
+    int rc = check_dims("oiva_demix_output_scaled", n_batch, n_frames, n_freq, n_chan, n_src);
+    if (rc) return rc;
+    OIVA_REQUIRE(n_src <= n_chan, "oiva_demix_output_scaled: n_src > n_chan");
+    StreamParams p = make_params(Xg, Wg, n_chan, n_frames, n_freq, n_chan, n_src, 1);
+    p.Y = Y;
+    p.Zg = (const cplx*)Zg;
     return stream_launch(n_chan, KIND_OUTPUT, dtype, p, (long long)n_batch * p.L.NG, (cudaStream_t)stream);
 }
 

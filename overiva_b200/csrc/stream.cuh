@@ -54,6 +54,7 @@ struct StreamParams {
     double* r2part;   // (B, NG, K, Tp)
     void* Y;          // (B, T, F, K) interleaved complex ST
     void* Xr;         // grouped samples with K channels
+    double* Pfull;    // power kernels: |y_k(f, t)|^2 per bin, grouped [gi][k][Tp][32] (ILRMA's spectrogram model), or nullptr
     const cplx* Zg;   // output kernels: projection-back scales z [gi][K][32] from k_projback_z (stream.cu), or nullptr.
                       // (Computing z inside the output kernels was tried: the M x M products next to the filter
                       // registers spill at the 128-register cap of these kernels from M = 5 on -- 66 ms instead of 3 ms
@@ -137,6 +138,15 @@ __global__ void __launch_bounds__(stream_max_threads(KC)) k_demix_power(const St
 #pragma unroll
                 for (int k = 0; k < KC; ++k) v[k][j] = 0.0;
             }
+        }
+        if (p.Pfull) {  // (padding frames are written as zeros, padded bins hold zeros already)
+#pragma unroll
+            for (int k = 0; k < KC; ++k)
+                if (k0 + k < p.K) {
+#pragma unroll
+                    for (int j = 0; j < POWER_FB; ++j)
+                        p.Pfull[(((size_t)gi * p.K + k0 + k) * Tp + t0 + j) * OIVA_GROUP + lane] = v[k][j];
+                }
         }
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
@@ -245,6 +255,15 @@ __global__ void __launch_bounds__(M >= 13 ? 384 : (FBW == 8 ? stream_max_threads
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
         if constexpr (!OUTPUT) {
+            if (p.Pfull) {
+#pragma unroll
+                for (int k = 0; k < KC; ++k)
+                    if (k0 + k < p.K) {
+#pragma unroll
+                        for (int j = 0; j < FBW; ++j)
+                            p.Pfull[(((size_t)gi * p.K + k0 + k) * Tp + t0 + j) * OIVA_GROUP + lane] = v[k][j];
+                    }
+            }
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
                 const double sres = lane_sum_frames<FBW>(v[k], lane);
