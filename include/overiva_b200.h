@@ -314,6 +314,17 @@ int oiva_gram(const double* a, long long a_row_stride, long long a_sample_stride
               long long b_row_stride, long long b_sample_stride, int b_rows, long long n_samples, void* scratch,
               double* out, void* stream);
 
+/* Cross-correlations at lags 0 .. flen-1 (flen <= 1024): out (a_rows, a_rows + b_rows, flen) float64 with
+ * out[i][j][m] = sum_n s_i[n] s_j[n + m], s_i a row of a, s_j a row of a (j < a_rows) or of b; signals as for oiva_gram
+ * (element strides in doubles).  With a = references and b = estimates these are all the inner products
+ * mir_eval.separation.bss_eval_sources (the reference callback's metric, overiva_oneshot.py:263-284: 512-tap distortion
+ * filters) needs: the block-Toeplitz normal matrix and its right-hand sides.  Deterministic (fixed-order tile sums).
+ * scratch: oiva_xcorr_scratch_bytes(...) bytes. */
+size_t oiva_xcorr_scratch_bytes(int a_rows, int b_rows, long long n_samples, int flen);
+int oiva_xcorr(const double* a, long long a_row_stride, long long a_sample_stride, int a_rows, const double* b,
+               long long b_row_stride, long long b_sample_stride, int b_rows, long long n_samples, int flen, void* scratch,
+               double* out, void* stream);
+
 /* n_iter epochs of the loop (overiva.py:138-190) in ONE persistent cooperative launch, for inputs short enough that
  * every bin group's samples fit the shared memory of the SMs (one short mixture: BASELINE configs 1-2; M <= 8): the grid
  * stays resident, the samples are read from HBM once and kept in shared memory for all epochs, the epochs are separated

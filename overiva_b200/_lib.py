@@ -80,6 +80,8 @@ SIGNATURES = {
     "oiva_stft_synthesis": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "oiva_gram_scratch_bytes": (_sz, [_i, _ll]),
     "oiva_gram": (_i, [_p, _ll, _ll, _i, _p, _ll, _ll, _i, _ll, _p, _p, _p]),
+    "oiva_xcorr_scratch_bytes": (_sz, [_i, _i, _ll, _i]),
+    "oiva_xcorr": (_i, [_p, _ll, _ll, _i, _p, _ll, _ll, _i, _ll, _i, _p, _p, _p]),
     "oiva_loop_resident_sync_bytes": (_sz, [_i, _i]),
     "oiva_loop_resident": (_i, [_p, _p, _p, _p, _p, _p, _sz, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "oiva_fp64_peak": (_i, [_i, _i, _i, C.POINTER(C.c_double), _p]),

@@ -140,3 +140,72 @@ def bss_eval_sources(refs, ests, flen=512, compute_permutation=True):
         perm = np.arange(K)
     ks = np.arange(K)
     return sdr[perm, ks], sir[perm, ks], sar[perm, ks], perm
+
+
+def xcorr_reference(refs, ests, flen):
+    """numpy statement of what ``oiva_xcorr`` computes: c (K, K + J, flen) with ``c[i, j, m] = sum_n s_i[n] s_j[n + m]``
+    (s_i a reference, s_j a reference or an estimate), and the energies ee (J,) of the estimates."""
+    refs = np.atleast_2d(np.asarray(refs, dtype=np.float64))
+    ests = np.atleast_2d(np.asarray(ests, dtype=np.float64))
+    K, N = refs.shape
+    allsig = np.concatenate([refs, ests], axis=0)
+    nfft = 1 << int(np.ceil(np.log2(N + flen)))
+    Af = np.fft.rfft(allsig, nfft, axis=1)
+    c = np.empty((K, allsig.shape[0], flen))
+    for i in range(K):
+        c[i] = np.fft.irfft(np.conj(Af[i])[None] * Af, nfft, axis=1)[:, :flen]
+    return c, np.einsum("jn,jn->j", ests, ests)
+
+
+def bss_eval_sources_from_xcorr(c, ee, flen=None, compute_permutation=True):
+    """BSS Eval v3 with ``flen``-tap distortion filters from cross-correlations only.  c: (K, K + J, flen) as
+    ``xcorr_reference`` / the device kernel ``oiva_xcorr`` return it, ee: (J,) energies of the estimates.  Returns
+    ``(sdr, sir, sar, perm)`` exactly as ``bss_eval_sources``: with D the references delayed by 0..flen-1 samples,
+    G = D D^T is block Toeplitz in c[k, l], b_j = D e_j is c[k, K + j], and
+    ``|s_target|^2 = b_jk^T G_kk^-1 b_jk``, ``|P e_j|^2 = b_j^T G^-1 b_j``, ``|e_interf|^2 = |P e|^2 - |s_target|^2``,
+    ``|e_artif|^2 = |e|^2 - |P e|^2``, ``|e_interf + e_artif|^2 = |e|^2 - |s_target|^2`` (s_target and P e are
+    orthogonal projections of e on nested subspaces)."""
+    c = np.asarray(c, dtype=np.float64)
+    ee = np.asarray(ee, dtype=np.float64)
+    K, R, fl = c.shape
+    flen = fl if flen is None else int(flen)
+    J = R - K
+    idx = np.arange(flen)
+    lag = idx[:, None] - idx[None, :]
+    pos, alag = lag >= 0, np.abs(lag)
+    G = np.empty((K * flen, K * flen))
+    for k in range(K):
+        for l in range(K):
+            G[k * flen : (k + 1) * flen, l * flen : (l + 1) * flen] = np.where(pos, c[k, l][alag], c[l, k][alag])
+    B = c[:, K:, :flen].transpose(0, 2, 1).reshape(K * flen, J)  # column j: b_j
+
+    def quad(Gm, Bm):  # b^T G^-1 b per column
+        try:
+            X = np.linalg.solve(Gm, Bm)
+        except np.linalg.LinAlgError:
+            X = np.linalg.lstsq(Gm, Bm, rcond=None)[0]
+        return np.einsum("ij,ij->j", Bm, X)
+
+    pe2 = quad(G, B)
+    tiny = np.finfo(float).tiny
+    sdr = np.empty((J, K))
+    sir = np.empty((J, K))
+    sar = np.empty((J, K))
+    for k in range(K):
+        sl = slice(k * flen, (k + 1) * flen)
+        st2 = quad(G[sl, sl], B[sl])
+        for j in range(J):
+            sdr[j, k] = 10 * np.log10(max(st2[j], tiny) / max(ee[j] - st2[j], tiny))
+            sir[j, k] = 10 * np.log10(max(st2[j], tiny) / max(pe2[j] - st2[j], tiny))
+            sar[j, k] = 10 * np.log10(max(pe2[j], tiny) / max(ee[j] - pe2[j], tiny))
+    if compute_permutation:
+        best, perm = -np.inf, None
+        for cand in itertools.permutations(range(J), K):
+            score = np.mean([sir[cand[k], k] for k in range(K)])
+            if score > best:
+                best, perm = score, cand
+        perm = np.array(perm)
+    else:
+        perm = np.arange(K)
+    ks = np.arange(K)
+    return sdr[perm, ks], sir[perm, ks], sar[perm, ks], perm

@@ -78,6 +78,41 @@ def bss_eval_device(refs, ests):
     return bss_eval_from_gram(G, refs.shape[0])
 
 
+def xcorr(refs, ests, flen):
+    """Cross-correlations at lags 0..flen-1 on the device (``oiva_xcorr``): refs (K, N), ests (J, N) float64 CUDA tensors
+    (any strides) -> c (K, K + J, flen) CUDA with ``c[i, j, m] = sum_n s_i[n] s_j[n + m]``."""
+    lib = L.load()
+    for t in (refs, ests):
+        if not (t.is_cuda and t.dtype == torch.float64 and t.ndim == 2):
+            raise TypeError("xcorr needs 2-D float64 CUDA tensors")
+    if refs.shape[1] != ests.shape[1]:
+        raise ValueError("refs and ests must have the same length")
+    K, N = refs.shape
+    J = ests.shape[0]
+    dev = refs.device
+    with torch.cuda.device(dev):
+        scratch = torch.empty(lib.oiva_xcorr_scratch_bytes(K, J, N, int(flen)), dtype=torch.uint8, device=dev)
+        out = torch.empty((K, K + J, int(flen)), dtype=torch.float64, device=dev)
+        L.check(lib.oiva_xcorr(core._ptr(refs), refs.stride(0), refs.stride(1), K, core._ptr(ests), ests.stride(0),
+                               ests.stride(1), J, N, int(flen), core._ptr(scratch), core._ptr(out), core._stream_ptr(dev)),
+                "oiva_xcorr")
+    return out
+
+
+def bss_eval_sources_device(refs, ests, flen=512):
+    """``mir_eval.separation.bss_eval_sources`` (restated in ``metrics.bss_eval_sources``: distortion filters of ``flen``
+    taps) for CUDA tensors refs (K, N), ests (J, N): the pass over the audio -- cross-correlations at ``flen`` lags --
+    runs on the device, ``(K + J) K flen`` doubles go to the host, where the block-Toeplitz systems are solved.
+    -> (sdr, sir, sar, perm)."""
+    from . import metrics
+
+    n = min(refs.shape[1], ests.shape[1])
+    r, e = refs[:, :n], ests[:, :n]
+    c = xcorr(r, e, flen).cpu().numpy()
+    ee = torch.einsum("jn,jn->j", e, e).cpu().numpy()
+    return metrics.bss_eval_sources_from_xcorr(c, ee, flen)
+
+
 class ConvergenceMonitor:
     """``callback`` object for ``overiva`` / ``auxiva_pca`` / ``ogive`` (pass X as a CUDA tensor so that the
     estimates stay on the device).  After the run ``SDR`` / ``SIR`` hold one array per call, like the lists the
@@ -85,9 +120,11 @@ class ConvergenceMonitor:
 
     ref: (n_src_ref, n_samples, n_mics) or (n_src_ref, n_samples) clean source images (CUDA or numpy); scored at
     microphone 0.  ``delay``: samples to drop at the head of the synthesised estimate (``framesize // 2`` when the
-    analysis used the ``L - hop`` state-buffer padding, as the reference's STFT does; 0 for un-padded framing)."""
+    analysis used the ``L - hop`` state-buffer padding, as the reference's STFT does; 0 for un-padded framing).
+    ``filter_length``: taps of the metric's distortion filters (1, or 512 for mir_eval's ``bss_eval_sources``)."""
 
-    def __init__(self, ref, framesize=4096, hop=None, win_s=None, n_targets=None, reorder=True, delay=0, device=None):
+    def __init__(self, ref, framesize=4096, hop=None, win_s=None, n_targets=None, reorder=True, delay=0, device=None,
+                 filter_length=1):
         dev = core._require_cuda(device)
         r = ref if isinstance(ref, torch.Tensor) else torch.from_numpy(np.asarray(ref, dtype=np.float64))
         if r.ndim == 3:
@@ -99,6 +136,9 @@ class ConvergenceMonitor:
         self.n_targets = self.ref.shape[0] if n_targets is None else int(n_targets)
         self.reorder = bool(reorder)
         self.delay = int(delay)
+        # distortion-filter taps of the metric: 1 = the instantaneous decomposition (metrics.bss_eval, a Gram matrix);
+        # 512 = what the reference's callback computes with mir_eval (cross-correlations at 512 lags on the device)
+        self.filter_length = int(filter_length)
         self.SDR, self.SIR = [], []
 
     def __call__(self, Y, **kwargs):
@@ -109,6 +149,9 @@ class ConvergenceMonitor:
             y = y[:, torch.argsort(y.std(dim=0), descending=True)]
         m = min(y.shape[0] - self.delay, self.ref.shape[1])
         k = self.n_targets
-        sdr, sir, _ = bss_eval_device(self.ref[:k, :m], y[self.delay : self.delay + m, :k].T)
+        if self.filter_length > 1:
+            sdr, sir, _, _ = bss_eval_sources_device(self.ref[:k, :m], y[self.delay : self.delay + m, :k].T, self.filter_length)
+        else:
+            sdr, sir, _ = bss_eval_device(self.ref[:k, :m], y[self.delay : self.delay + m, :k].T)
         self.SDR.append(sdr)
         self.SIR.append(sir)

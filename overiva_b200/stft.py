@@ -192,7 +192,7 @@ def synthesis(X, L_, hop, win=None):
         return inp.give_back(y)
 
 
-_ALGOS = ("overiva", "auxiva", "auxiva_pca", "ogive")
+_ALGOS = ("overiva", "auxiva", "auxiva_pca", "ogive", "ilrma")
 
 
 def separate_batch(mix, n_src=None, n_iter=20, framesize=4096, hop=None, win_a=None, win_s=None, model="laplace",
@@ -366,6 +366,13 @@ def separate(mix, algo="overiva", n_src=None, n_iter=20, framesize=4096, hop=Non
                 Y = core.auxiva_pca(X[0], n_src, n_iter=n_iter, proj_back=proj_back, W0=W0, model=model,
                                     init_eig=init_eig, **algo_kwargs)
                 W = None
+            elif algo == "ilrma":  # overiva_oneshot.py:331-339
+                from .ilrma import ilrma
+
+                res = ilrma(X[0], n_src, n_iter=n_iter, proj_back=proj_back, W0=W0, return_filters=return_filters,
+                            **algo_kwargs)
+                Y, W = res if return_filters else (res, None)
+                W = W[None] if W is not None else None
             else:
                 res = core.ogive(X[0], n_iter=n_iter, proj_back=proj_back, W0=W0, model=model, init_eig=init_eig,
                                  return_filters=return_filters, **algo_kwargs)

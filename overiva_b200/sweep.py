@@ -92,8 +92,8 @@ def algorithms_for(parameters, n_targets):
             continue
         if name == "ogive" and n_targets != 1:
             continue
-        if name not in ("auxiva", "auxiva_pca", "overiva", "ogive"):
-            continue  # e.g. "ilrma": third-party in the reference (pra.bss.ilrma), not part of this path
+        if name not in ("auxiva", "auxiva_pca", "overiva", "ogive", "ilrma"):
+            continue
         out.append((full_name, name, dict(params["kwargs"])))
     return out
 
@@ -188,6 +188,10 @@ class GpuEngine:
             Y = core.auxiva_pca(Xb, n_src=n_targets, callback=cb, **kwargs)
         elif algo == "ogive":
             Y = core.ogive(Xb, callback=cb, **kwargs)
+        elif algo == "ilrma":  # overiva_sim.py:309-311: pra.bss.ilrma(X_mics, callback=cb, **kwargs)
+            from .ilrma import ilrma
+
+            Y = ilrma(Xb, callback=cb, **kwargs)
         else:
             raise ValueError(algo)
         torch.cuda.synchronize(self.device)
@@ -209,12 +213,14 @@ class GpuEngine:
             failed = (status & 1) != 0
             if failed.any():
                 Y[torch.from_numpy(failed).to(Y.device)] = float("nan")
-        elif algo in ("auxiva_pca", "ogive"):
+        elif algo in ("auxiva_pca", "ogive", "ilrma"):
+            from .ilrma import ilrma
+
             outs = []
             for b in range(B):
                 try:
                     outs.append(core.auxiva_pca(X[b], n_src=n_targets, **kwargs) if algo == "auxiva_pca"
-                                else core.ogive(X[b], **kwargs))
+                                else (core.ogive(X[b], **kwargs) if algo == "ogive" else ilrma(X[b], **kwargs)))
                 except np.linalg.LinAlgError:
                     failed[b] = True
                     outs.append(None)
@@ -250,6 +256,7 @@ def run(parameters=None, results_dir=None, batch=64, engine=None, progress=None)
         return algo_name not in overdet
 
     flen = int(parameters.get("bss_eval_filter_length", 1))  # 512 = mir_eval's bss_eval_sources (host, slower)
+    rng_state = np.random.get_state()  # (restored on return: ILRMA chunks reseed the global generator)
     for (n_targets, n_mics), idx in groups.items():
         algos = algorithms_for(parameters, n_targets)
         for c0 in range(0, len(idx), batch):
@@ -265,6 +272,11 @@ def run(parameters=None, results_dir=None, batch=64, engine=None, progress=None)
             recs = [[] for _ in chunk]
             monitored = bool(parameters.get("monitor_convergence", False))
             for full_name, algo, kwargs in algos:
+                if algo == "ilrma":
+                    # ILRMA draws its initial NMF factors from numpy's global generator.  The reference seeds it per task
+                    # (one_loop starts with np.random.seed(seed), overiva_sim.py:105); here the chunk's first seed does,
+                    # so that a sweep is reproducible whatever ran before it
+                    np.random.seed(args[chunk[0]][4] % (2**32))
                 if monitored:
                     # overiva_sim.py:272-284: the callback scores the estimate every 10 epochs; one mixture at a time
                     # (the batched entry point has no callback), the scoring itself stays on the device
@@ -304,6 +316,7 @@ def run(parameters=None, results_dir=None, batch=64, engine=None, progress=None)
                     progress(full_name, n_targets, n_mics, len(chunk), per_mix)
             for b, i in enumerate(chunk):
                 segments[i] = recs[b]
+    np.random.set_state(rng_state)
     if results_dir:
         os.makedirs(results_dir, exist_ok=True)
         with open(os.path.join(results_dir, "parameters.json"), "w") as f:

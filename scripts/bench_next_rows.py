@@ -80,3 +80,35 @@ print(json.dumps({
     "ms_per_callback_device": (t_dev - t_none) * 100, "ms_per_callback_host": (t_host - t_none) * 100,
     "final_sdr_device": [float(v) for v in mon.SDR[-1]], "calls": len(mon.SDR),
 }), flush=True)
+
+# ---- row 3b: the same monitor with mir_eval's 512-tap distortion filters (cross-correlations on the device) ----------
+t_dev512, mon512 = timed(lambda: monitor.ConvergenceMonitor(images, framesize=L_, delay=L_ - hop, filter_length=512), reps=2)
+
+
+def host_callback_512():
+    from overiva_b200.synth import istft
+
+    SDR = []
+
+    def cb(Y):
+        y = istft(Y.cpu().numpy(), L_, hop)
+        y = y[:, np.argsort(np.std(y, axis=0))[::-1]]
+        m = min(y.shape[0] - (L_ - hop), images.shape[1])
+        sdr, sir, _, _ = metrics.bss_eval_sources(images[:2, :m, 0], y[L_ - hop : L_ - hop + m, :2].T, flen=512)
+        SDR.append(sdr)
+
+    cb.SDR = SDR
+    return cb
+
+
+t0 = time.perf_counter()
+hcb512 = host_callback_512()
+ob.overiva(Xd, n_src=2, n_iter=10, callback=hcb512)  # one callback (epoch 0) is enough to time the host metric
+torch.cuda.synchronize()
+t_host512_one = time.perf_counter() - t0
+print(json.dumps({
+    "row": "monitor_512tap", "workload": "one 15 s mixture, M=4 K=2, n_iter=100 -> 10 callbacks, bss_eval_sources with 512 taps",
+    "ms_device_monitor_512": t_dev512 * 1e3, "ms_per_callback_device_512": (t_dev512 - t_none) * 100,
+    "ms_per_callback_host_512": t_host512_one * 1e3, "final_sdr_device_512": [float(v) for v in mon512.SDR[-1]],
+    "first_sdr_host_512": [float(v) for v in hcb512.SDR[0]], "first_sdr_device_512": [float(v) for v in mon512.SDR[0]],
+}), flush=True)

@@ -62,3 +62,45 @@ def test_delayed_gram_matches_direct_computation():
     D = np.stack([np.concatenate([np.zeros(a), refs[k], np.zeros(flen - 1 - a)]) for k in range(2) for a in range(flen)])
     assert np.allclose(G, D @ D.T, atol=1e-9)
     assert pad.shape == (2, 4)
+
+
+@pytest.mark.parametrize("flen,K", [(1, 2), (8, 2), (64, 3)])
+def test_bss_eval_sources_from_cross_correlations(flen, K):
+    """Every quantity of the filter-based metric is a function of cross-correlations at flen lags: the route the device
+    monitor takes (oiva_xcorr + host solves) gives the same numbers as the signal-domain restatement."""
+    refs, rng = _sources(K, 2500, 10 + flen)
+    ests = rng.standard_normal((K, K)) @ refs + 0.3 * rng.standard_normal((K, 2500))
+    ests[0] = np.convolve(ests[0], rng.standard_normal(4))[:2500]
+    c, ee = metrics.xcorr_reference(refs, ests, flen)
+    # the definition, directly
+    for i, j, m in [(0, 1, 0), (K - 1, K, flen - 1), (1, 0, flen // 2)]:
+        sj = np.concatenate([refs, ests])[j]
+        assert np.isclose(c[i, j, m], np.dot(refs[i][: 2500 - m], sj[m:]), rtol=1e-9, atol=1e-9)
+    got = metrics.bss_eval_sources_from_xcorr(c, ee, flen)
+    want = metrics.bss_eval_sources(refs, ests, flen=flen)
+    assert np.array_equal(got[3], want[3])
+    for a, b in zip(got[:3], want[:3]):
+        assert np.allclose(a, b, atol=1e-6), (a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flen,N", [(1, 1000), (32, 5000), (512, 40000), (1000, 3000)])
+def test_device_xcorr_and_filter_metric(flen, N):
+    import torch
+
+    from overiva_b200 import monitor
+
+    K = 2
+    refs, rng = _sources(K, N, 20 + flen)
+    ests = rng.standard_normal((K, K)) @ refs + 0.2 * rng.standard_normal((K, N))
+    rd, ed = torch.from_numpy(refs).cuda(), torch.from_numpy(ests.T.copy()).cuda().T  # (estimates with a sample-major stride)
+    c = monitor.xcorr(rd, ed, flen).cpu().numpy()
+    cw, ee = metrics.xcorr_reference(refs, ests, flen)
+    assert c.shape == cw.shape and np.allclose(c, cw, rtol=1e-10, atol=1e-8 * np.abs(cw).max())
+    assert np.array_equal(c, monitor.xcorr(rd, ed, flen).cpu().numpy())  # deterministic
+    if flen <= 512:
+        got = monitor.bss_eval_sources_device(rd, ed, flen)
+        want = metrics.bss_eval_sources(refs, ests, flen=flen)
+        assert np.array_equal(got[3], want[3])
+        for a, b in zip(got[:3], want[:3]):
+            assert np.allclose(a, b, atol=1e-5), (a, b)

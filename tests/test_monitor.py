@@ -73,3 +73,28 @@ def test_monitor_as_callback_matches_host_evaluation():
         sdr, sir, _ = metrics.bss_eval(images[:, :m, 0], y[L_ - hop : L_ - hop + m, :2].T)
         assert np.allclose(mon.SDR[i], sdr, atol=1e-6) and np.allclose(mon.SIR[i], sir, atol=1e-6)
     assert np.mean(mon.SIR[-1]) > np.mean(mon.SIR[0])
+
+
+@pytest.mark.gpu
+def test_monitor_with_512_tap_filters_matches_host_bss_eval_sources():
+    """filter_length = 512: the metric the reference's callback computes (mir_eval.separation.bss_eval_sources,
+    overiva_oneshot.py:263-284), cross-correlations on the device, Toeplitz systems on the host."""
+    import overiva_b200 as ob
+
+    L_, hop = 256, 128
+    mix, images = convolutive_mixture(6, 3, 2, duration=2.0, fs=8000, n_interferers=2, rt60=0.05, env_shape=2.0,
+                                      env_block=0.02)
+    wa = so.hann(L_)
+    ws = so.compute_synthesis_window(wa, hop)
+    X = so.analysis(mix, L_, hop, win=wa, pad_front=L_ - hop)
+    mon = monitor.ConvergenceMonitor(images, framesize=L_, delay=L_ - hop, filter_length=512)
+    ob.overiva(torch.from_numpy(X).cuda(), n_src=2, n_iter=11, callback=mon)
+    assert len(mon.SDR) == 2
+    seen = []
+    orc.overiva(X, n_src=2, n_iter=11, callback=lambda Yc: seen.append(Yc.copy()))
+    for i, Yc in enumerate(seen):
+        y = so.synthesis(Yc, L_, hop, win=ws)
+        y = y[:, np.argsort(np.std(y, axis=0))[::-1]]
+        m = min(y.shape[0] - (L_ - hop), images.shape[1])
+        sdr, sir, _, _ = metrics.bss_eval_sources(images[:2, :m, 0], y[L_ - hop : L_ - hop + m, :2].T, flen=512)
+        assert np.allclose(mon.SDR[i], sdr, atol=1e-4) and np.allclose(mon.SIR[i], sir, atol=1e-4), (mon.SDR[i], sdr)

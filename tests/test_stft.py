@@ -253,7 +253,11 @@ def test_separate_batch_filters_and_errors():
     yt = gst.separate(torch.from_numpy(mixes[0]).cuda(), n_src=2, framesize=64)
     assert yt.is_cuda and rel_err(yt.cpu().numpy(), y[0]) < 1e-11
     with pytest.raises(ValueError, match="No such algorithm"):
-        gst.separate(mixes[0], algo="ilrma")
+        gst.separate(mixes[0], algo="fastica")
+    # ILRMA through the audio-in / audio-out call (overiva_oneshot.py:331-339): determined, 3 outputs
+    np.random.seed(5)
+    yi = gst.separate(mixes[0], algo="ilrma", framesize=64, n_iter=5, n_components=2)
+    assert yi.shape[1] == 3 and np.all(np.isfinite(yi))
     with pytest.raises(ValueError, match="one mixture at a time"):
         gst.separate(mixes, algo="ogive", framesize=64)
     with pytest.raises(ValueError, match="n_src"):

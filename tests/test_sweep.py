@@ -8,6 +8,7 @@ import os
 import numpy as np
 import pytest
 
+from oracle import ilrma_oracle as ilo
 from oracle import overiva_oracle as orc
 from oracle import stft_oracle as so
 from overiva_b200 import sweep
@@ -54,14 +55,16 @@ class OracleEngine:
         fn = {"auxiva": lambda x: orc.overiva(x, callback=cb, **kwargs),
               "overiva": lambda x: orc.overiva(x, n_src=n_targets, callback=cb, **kwargs),
               "auxiva_pca": lambda x: orc.auxiva_pca(x, n_src=n_targets, callback=cb, **kwargs),
-              "ogive": lambda x: orc.ogive(x, callback=cb, **kwargs)}[algo]
+              "ogive": lambda x: orc.ogive(x, callback=cb, **kwargs),
+              "ilrma": lambda x: ilo.ilrma(x, callback=cb, **kwargs)}[algo]
         Y = fn(Xb)
         cb(Y)
         return Y, 0.25, sdrs, sirs
 
     def run(self, algo, X, n_targets, kwargs):
         fn = {"auxiva": lambda x: orc.overiva(x, **kwargs), "overiva": lambda x: orc.overiva(x, n_src=n_targets, **kwargs),
-              "auxiva_pca": lambda x: orc.auxiva_pca(x, n_src=n_targets, **kwargs), "ogive": lambda x: orc.ogive(x, **kwargs)}[algo]
+              "auxiva_pca": lambda x: orc.auxiva_pca(x, n_src=n_targets, **kwargs), "ogive": lambda x: orc.ogive(x, **kwargs),
+              "ilrma": lambda x: ilo.ilrma(x, **kwargs)}[algo]
         outs, failed = [], np.zeros(len(X), dtype=bool)
         for b, x in enumerate(X):
             try:
@@ -91,8 +94,10 @@ def test_generate_arguments_follows_the_reference_enumeration():
 
 def test_algorithm_selection_rules():
     names = lambda n: [a[0] for a in sweep.algorithms_for(PARAMS, n)]
-    assert names(1) == ["auxiva_laplace", "overiva_gauss", "ogive_laplace"]  # no PCA for a single target
-    assert names(2) == ["auxiva_laplace", "overiva_gauss", "auxiva_pca_laplace"]  # OGIVE only for one target
+    assert names(1) == ["auxiva_laplace", "overiva_gauss", "ogive_laplace", "ilrma"]  # no PCA for a single target
+    assert names(2) == ["auxiva_laplace", "overiva_gauss", "auxiva_pca_laplace", "ilrma"]  # OGIVE only for one target
+    unknown = dict(PARAMS, algorithm_kwargs={"x": {"algo": "fastica", "kwargs": {}}})
+    assert sweep.algorithms_for(unknown, 2) == []  # one_loop's `else: continue` (overiva_sim.py:316-317)
 
 
 def test_sweep_records_and_files(tmp_path):
@@ -121,7 +126,7 @@ def test_sweep_records_and_files(tmp_path):
     assert json.load(open(os.path.join(tmp_path, "parameters.json")))["fs"] == 8000
     assert json.load(open(os.path.join(tmp_path, "arguments.json"))) == args
     rows = sweep.summarise(segs, p["fs"])
-    assert {r["algorithm"] for r in rows} == {"auxiva_laplace", "overiva_gauss", "auxiva_pca_laplace", "ogive_laplace"}
+    assert {r["algorithm"] for r in rows} == {"auxiva_laplace", "overiva_gauss", "auxiva_pca_laplace", "ogive_laplace", "ilrma"}
     assert all(r["runtime_per_s"] == pytest.approx(0.5 / 3200 * 8000) for r in rows)
     assert seen and seen[0][0] == "auxiva_laplace"
 
