@@ -270,6 +270,12 @@ int oiva_ilrma_nmf(const double* Pg, double* iRg, double* Tg, double* Vn, double
  * P_k, T_k *= lam^2, iR_k /= lam^2 */
 int oiva_ilrma_rescale(const double* r2part, double* lam, void* Wg, double* Pg, double* iRg, double* Tg, int n_batch,
                        int n_frames, int n_freq, int n_chan, int n_src, int n_comp, int scale_w, void* stream);
+/* n_epochs whole epochs (nmf -> weighted_cov_binwise -> ip_update -> demix_power_full -> rescale) in one call; C / Cg:
+ * the input covariance, row-major (R,M,M) and grouped, as for oiva_ip_update; scratch as for oiva_weighted_cov_ws */
+int oiva_ilrma_iterate(const void* Xg, void* Wg, void* Vg, const void* C, const void* Cg, double* r2part, void* scratch,
+                       size_t scratch_bytes, double* Pg, double* iRg, double* Tg, double* Vn, double* Vpart, double* lam,
+                       int* status, int n_batch, int n_frames, int n_freq, int n_chan, int n_comp, double eps, int n_epochs,
+                       void* stream);
 /* Zg [gi][K][32] c128 <- lam[b][k] (invert != 0: 1 / lam): a real per-source scale for oiva_demix_output_scaled */
 int oiva_ilrma_fill_scale(const double* lam, void* Zg, int n_batch, int n_freq, int n_src, int invert, void* stream);
 /* oiva_demix_output_grouped with caller-supplied per-bin scales Zg [gi][K][32] c128 (NULL: none): Y = (w_k z_k)^H x */

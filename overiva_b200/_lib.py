@@ -92,6 +92,7 @@ SIGNATURES = {
     "oiva_ilrma_get_model": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "oiva_ilrma_nmf": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _d, _p]),
     "oiva_ilrma_rescale": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "oiva_ilrma_iterate": (_i, [_p, _p, _p, _p, _p, _p, _p, _sz, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _d, _i, _p]),
     "oiva_ilrma_fill_scale": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "oiva_demix_output_scaled": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "oiva_plan_array": (_p, [_p, _i]),

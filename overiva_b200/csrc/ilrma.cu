@@ -338,3 +338,28 @@ extern "C" int oiva_ilrma_fill_scale(const double* lam, void* Zg, int n_batch, i
     OIVA_LAUNCH_CHECK();
     return OIVA_OK;
 }
+
+// n_epochs whole epochs in one library call (the Python loop cost ~7 ctypes round trips per epoch, of the order of the
+// GPU work itself for one mixture): NMF updates -> covariance with per-bin weights -> determined IP sweep -> demix with
+// per-bin powers -> scale normalisation.  Pointers as for the individual calls; C (row-major) / Cg as for oiva_ip_update.
+extern "C" int oiva_ilrma_iterate(const void* Xg, void* Wg, void* Vg, const void* C, const void* Cg, double* r2part,
+                                  void* scratch, size_t scratch_bytes, double* Pg, double* iRg, double* Tg, double* Vn,
+                                  double* Vpart, double* lam, int* status, int n_batch, int n_frames, int n_freq, int n_chan,
+                                  int n_comp, double eps, int n_epochs, void* stream) {
+    OIVA_REQUIRE(Xg && Wg && Vg && C && Cg && r2part && Pg && iRg && Tg && Vn && Vpart && lam && status,
+                 "oiva_ilrma_iterate: null pointer");
+    const int K = n_chan;
+    for (int e = 0; e < n_epochs; ++e) {
+        int rc = oiva_ilrma_nmf(Pg, iRg, Tg, Vn, Vpart, n_batch, n_frames, n_freq, K, n_comp, eps, stream);
+        if (rc) return rc;
+        rc = oiva_weighted_cov_binwise(Xg, iRg, Vg, scratch, scratch_bytes, n_batch, n_frames, n_freq, n_chan, K, stream);
+        if (rc) return rc;
+        rc = oiva_ip_update(Wg, Vg, C, Cg, nullptr, status, n_batch, n_freq, n_chan, K, stream);
+        if (rc) return rc;
+        rc = oiva_demix_power_full(Xg, Wg, n_chan, 1, r2part, Pg, n_batch, n_frames, n_freq, n_chan, K, OIVA_C128, stream);
+        if (rc) return rc;
+        rc = oiva_ilrma_rescale(r2part, lam, Wg, Pg, iRg, Tg, n_batch, n_frames, n_freq, n_chan, K, n_comp, 1, stream);
+        if (rc) return rc;
+    }
+    return OIVA_OK;
+}

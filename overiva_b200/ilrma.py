@@ -94,19 +94,25 @@ def ilrma(X, n_src=None, n_iter=20, proj_back=False, W0=None, n_components=2, re
                             "oiva_demix_output_scaled")
                 return Y[0].to(inp.dev.dtype)
 
+            def epochs(n):  # nmf -> covariance with per-bin weights -> sweep -> demix + powers -> rescale, n times
+                L.check(lib.oiva_ilrma_iterate(xg, Wg, Vg, C.c_void_p(lib.oiva_plan_cov(plan.h)), Cg, r2part, scratch,
+                                               scratch_bytes, P(Pg), P(iRg), P(Tg), P(Vn), P(Vpart), P(lam),
+                                               C.c_void_p(lib.oiva_plan_status_ptr(plan.h)), 1, T, F, M, Lc, _EPS, int(n), st),
+                        "oiva_ilrma_iterate")
+
             power()
-            for epoch in range(int(n_iter)):
-                if callback is not None and epoch % 10 == 0:
-                    plan.raise_on_failure()
-                    callback(inp.give_back(current_output()))
-                L.check(lib.oiva_ilrma_nmf(P(Pg), P(iRg), P(Tg), P(Vn), P(Vpart), 1, T, F, K, Lc, _EPS, st), "oiva_ilrma_nmf")
-                L.check(lib.oiva_weighted_cov_binwise(xg, P(iRg), Vg, scratch, scratch_bytes, 1, T, F, M, K, st),
-                        "oiva_weighted_cov_binwise")
-                L.check(lib.oiva_ip_update(Wg, Vg, C.c_void_p(lib.oiva_plan_cov(plan.h)), Cg, None,
-                                           C.c_void_p(lib.oiva_plan_status_ptr(plan.h)), 1, F, M, K, st), "oiva_ip_update")
-                power()
-                L.check(lib.oiva_ilrma_rescale(r2part, P(lam), Wg, P(Pg), P(iRg), P(Tg), 1, T, F, M, K, Lc, 1, st),
-                        "oiva_ilrma_rescale")
+            n_iter = int(n_iter)
+            if callback is None:
+                epochs(n_iter)
+            else:  # every 10th epoch, before its update (the cadence of overiva.py:142)
+                epoch = 0
+                while epoch < n_iter:
+                    if epoch % 10 == 0:
+                        plan.raise_on_failure()
+                        callback(inp.give_back(current_output()))
+                    step = min(10 - epoch % 10, n_iter - epoch)
+                    epochs(step)
+                    epoch += step
             Y = current_output()
             W = plan.filters()[0] if return_filters else None
             plan.raise_on_failure()
