@@ -56,10 +56,18 @@ static int launch_common(Kern kern, CovParams p, cudaStream_t st, int P, int tea
     if (teams < 1) teams = 1;
     // measured on B200 (cfg4 shape): 2 stages x 8 single-warp teams per SM reaches 0.92 of the copy bandwidth,
     // 3-4 stages x 5 teams 0.70: more resident warps beat a deeper ring (profiles/r01_notes.md)
-    int S = env_int("OIVA_COV_STAGES", teams_max == 1 ? 4 : 2);
+    const size_t budget = 200 * 1024;
+    // ring depth: 2 stages for the 8 single-warp teams of the bench shape (their 16 stages fill the budget); shapes with
+    // fewer, multi-warp teams (K >= 3 at M >= 6, M = 8, ...) leave shared memory unused at 2 stages -- they get as many
+    // stages as fit, up to 4 (more chunks in flight per team: these teams are latency-bound, not bandwidth-bound)
+    int S = env_int("OIVA_COV_STAGES", 0);
+    if (S <= 0) {
+        S = teams_max == 1 ? 4 : 2;
+        const size_t bar = 128 * ((2 * 4 * sizeof(uint64_t) + 127) / 128);
+        while (S < 4 && (size_t)teams * (bar + (size_t)(S + 1) * stage_bytes) <= budget) ++S;
+    }
     if (S < 2) S = 2;
     size_t team_smem = 0, smem = 0;
-    const size_t budget = 200 * 1024;
     for (;;) {
         team_smem = 128 * ((2 * S * sizeof(uint64_t) + 127) / 128) + (size_t)S * stage_bytes;
         if (teams * team_smem <= budget) break;
