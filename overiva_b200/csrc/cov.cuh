@@ -102,12 +102,15 @@ struct CovPart {
     static constexpr bool WB = WBIN;
     static constexpr int WLANES = WBIN ? OIVA_GROUP : 1;  // weights per (source, frame) in a stage
 
-    // accumulate `nfr` (<= TC) frames of a staged chunk: xs = [TC][M][32] complex, ph = [KC][TC] (or [KC][TC][32])
+    // accumulate `nfr` (<= TC) frames of a staged chunk: xs = [TC][M][32] complex, ph = [KC][TC] (or [KC][TC][32]).
+    // WHOLE: a complete chunk -- no per-frame test, so the loads of a frame can be scheduled over the arithmetic of the
+    // previous one (every chunk but a group's last is complete).
+    template <bool WHOLE = false>
     __device__ static __forceinline__ void accumulate(cplx (&acc)[NEP][KC], const XC* __restrict__ xs,
                                                       const double* __restrict__ ph, int nfr, int lane, int) {
 #pragma unroll
         for (int fr = 0; fr < TC; ++fr) {
-            if (fr < nfr) {
+            if (WHOLE || fr < nfr) {
                 cplx x[M];
                 double w[KC];
 #pragma unroll
@@ -258,8 +261,12 @@ __device__ __forceinline__ void cov_team_body(const CovParams& p, unsigned char*
             if (leader && pu < u_end) issue();
             mbar_wait(&full[cstage], cphase);
             const unsigned char* src = stage0 + (size_t)cstage * stage_bytes;
-            CP::accumulate(acc, reinterpret_cast<const XC*>(src), reinterpret_cast<const double*>(src + x_stage), nfr, lane,
-                           part);
+            if (nfr == TC)
+                CP::template accumulate<true>(acc, reinterpret_cast<const XC*>(src),
+                                              reinterpret_cast<const double*>(src + x_stage), nfr, lane, part);
+            else
+                CP::template accumulate<false>(acc, reinterpret_cast<const XC*>(src),
+                                               reinterpret_cast<const double*>(src + x_stage), nfr, lane, part);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[cstage]);
             if (++cstage == S) {
@@ -340,6 +347,7 @@ struct CovBlock {
         bj = part - bi * (bi + 1) / 2;
     }
 
+    template <bool WHOLE = false>
     __device__ static __forceinline__ void accumulate(cplx (&acc)[NACC][KC], const XC* __restrict__ xs,
                                                       const double* __restrict__ ph, int nfr, int lane, int part) {
         int bi, bj;
@@ -348,7 +356,7 @@ struct CovBlock {
         const XC* xj0 = xs + (size_t)(bj * COV_BT) * OIVA_GROUP + lane;
 #pragma unroll
         for (int fr = 0; fr < TC; ++fr) {
-            if (fr < nfr) {
+            if (WHOLE || fr < nfr) {
                 cplx xi[COV_BT], xj[COV_BT];
                 double w[KC];
 #pragma unroll

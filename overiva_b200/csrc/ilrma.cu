@@ -39,6 +39,8 @@ __global__ void __launch_bounds__(128) k_ilrma_update_T(const double* __restrict
     double num[ILRMA_MAX_L], den[ILRMA_MAX_L], tv[ILRMA_MAX_L];
 #pragma unroll
     for (int l = 0; l < ILRMA_MAX_L; ++l) num[l] = den[l] = 0.0;
+    // (unrolled: the loads of several frames are in flight at once -- one mixture has ~100 warps here, pure latency)
+#pragma unroll 8
     for (int t = 0; t < T; ++t) {
         const double p = P[(size_t)t * OIVA_GROUP], ir = iR[(size_t)t * OIVA_GROUP];
         const double a = p * ir * ir;
@@ -58,6 +60,8 @@ __global__ void __launch_bounds__(128) k_ilrma_update_T(const double* __restrict
             tv[l] = bin_ok ? x : 0.0;
             Tl[(size_t)l * OIVA_GROUP] = tv[l];
         }
+    // (unrolled: the loads of several frames are in flight at once -- one mixture has ~100 warps here, pure latency)
+#pragma unroll 8
     for (int t = 0; t < T; ++t) {
         double r = 0.0;
 #pragma unroll
@@ -80,6 +84,8 @@ __global__ void __launch_bounds__(128) k_ilrma_V_partial(const double* __restric
 #pragma unroll
     for (int l = 0; l < ILRMA_MAX_L; ++l) tv[l] = l < L ? Tg[((size_t)w * L + l) * OIVA_GROUP + lane] : 0.0;
     double* out = Vpart + (size_t)w * Tp * 2 * L;
+    // (unrolled: the loads of several frames are in flight at once -- one mixture has ~100 warps here, pure latency)
+#pragma unroll 8
     for (int t = 0; t < T; ++t) {
         const double p = P[(size_t)t * OIVA_GROUP], ir = iR[(size_t)t * OIVA_GROUP];
         const double a = p * ir * ir;
@@ -139,6 +145,7 @@ __global__ void __launch_bounds__(128) k_ilrma_model(double* __restrict__ iRg, c
     double tv[ILRMA_MAX_L];
 #pragma unroll
     for (int l = 0; l < ILRMA_MAX_L; ++l) tv[l] = l < L ? Tg[((size_t)w * L + l) * OIVA_GROUP + lane] : 0.0;
+#pragma unroll 8
     for (int t = 0; t < Tp; ++t) {
         double r = 0.0;
 #pragma unroll
@@ -220,6 +227,8 @@ __global__ void __launch_bounds__(128) k_ilrma_rescale(const double* __restrict_
     }
     double* P = Pg + (size_t)w * Tp * OIVA_GROUP + lane;
     double* iR = iRg + (size_t)w * Tp * OIVA_GROUP + lane;
+    // (unrolled: the loads of several frames are in flight at once -- one mixture has ~100 warps here, pure latency)
+#pragma unroll 8
     for (int t = 0; t < T; ++t) {
         P[(size_t)t * OIVA_GROUP] *= la2;
         iR[(size_t)t * OIVA_GROUP] *= ila2;

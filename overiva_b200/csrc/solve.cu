@@ -358,6 +358,8 @@ static int bins_per_cta() {
 namespace oiva {
 int ip_update_tpb(int M, int K, cplx* What, const cplx* Vg, const cplx* Cg, const double* wscale, int* status, int F,
                   int NG, long long G, cudaStream_t st);
+int ip_update_pair(int M, int K, cplx* Wg, const cplx* Vg, const double* wscale, int* status, int F, int NG, long long G,
+                   cudaStream_t st);
 }
 
 extern "C" int oiva_ip_update(void* What, const void* V, const void* C, const void* Cg, const double* wscale,
@@ -373,6 +375,9 @@ extern "C" int oiva_ip_update(void* What, const void* V, const void* C, const vo
         const int NG = oiva_bin_groups(n_freq);
         int rc = ip_update_tpb(n_chan, n_src, (cplx*)What, (const cplx*)V, (const cplx*)Cg, wscale, status, n_freq, NG,
                                (long long)n_batch * NG, st);
+        if (rc != OIVA_ERR_INVALID) return rc;
+        // determined sweep of 7 / 8 channels: two lanes per bin (solve_pair.cuh)
+        rc = ip_update_pair(n_chan, n_src, (cplx*)What, (const cplx*)V, wscale, status, n_freq, NG, (long long)n_batch * NG, st);
         if (rc != OIVA_ERR_INVALID) return rc;
     }
     OIVA_DISPATCH_M(n_chan, {

@@ -1,6 +1,7 @@
 // Instantiations + launcher of the thread-per-bin IP sweep (solve_tpb.cuh) for M <= 6, K <= M and M = 7, 8 with K <= 4.
 #include <stdlib.h>
 
+#include "solve_pair.cuh"
 #include "solve_tpb.cuh"
 
 namespace oiva {
@@ -31,6 +32,17 @@ int ip_update_tpb(int M, int K, cplx* What, const cplx* Vg, const cplx* Cg, cons
     OIVA_TPB(8, 1) OIVA_TPB(8, 2) OIVA_TPB(8, 3) OIVA_TPB(8, 4)
 #undef OIVA_TPB
     return OIVA_ERR_INVALID;
+}
+
+// the determined sweep of 7 / 8 channels with two lanes per bin (solve_pair.cuh); OIVA_ERR_INVALID for other shapes
+int ip_update_pair(int M, int K, cplx* Wg, const cplx* Vg, const double* wscale, int* status, int F, int NG, long long G,
+                   cudaStream_t st) {
+    if (K != M || (M != 7 && M != 8)) return OIVA_ERR_INVALID;
+    const unsigned grid = (unsigned)((2 * G + PAIR_WARPS - 1) / PAIR_WARPS);
+    if (M == 7) k_ip_update_pair<7><<<grid, PAIR_WARPS * 32, 0, st>>>(Wg, Vg, wscale, status, F, NG, G);
+    else k_ip_update_pair<8><<<grid, PAIR_WARPS * 32, 0, st>>>(Wg, Vg, wscale, status, F, NG, G);
+    OIVA_LAUNCH_CHECK();
+    return OIVA_OK;
 }
 
 template <int M, int K>
