@@ -101,6 +101,9 @@ struct CovPart {
     static constexpr int TC = cov_chunk_frames(M);  // frames per ring stage
     static constexpr bool WB = WBIN;
     static constexpr int WLANES = WBIN ? OIVA_GROUP : 1;  // weights per (source, frame) in a stage
+    // the branch-free whole-chunk path (below) pays up to 6 channels (bench shape 2.21 -> 2.10 ms per launch, M = K = 4
+    // 0.77 -> 0.71, M = K = 6 2.39 -> 2.35); with 8 channel values live per frame it costs (M = K = 8: 5.53 -> 6.16 ms)
+    static constexpr bool USE_WHOLE = M <= 6;
 
     // accumulate `nfr` (<= TC) frames of a staged chunk: xs = [TC][M][32] complex, ph = [KC][TC] (or [KC][TC][32]).
     // WHOLE: a complete chunk -- no per-frame test, so the loads of a frame can be scheduled over the arithmetic of the
@@ -261,7 +264,7 @@ __device__ __forceinline__ void cov_team_body(const CovParams& p, unsigned char*
             if (leader && pu < u_end) issue();
             mbar_wait(&full[cstage], cphase);
             const unsigned char* src = stage0 + (size_t)cstage * stage_bytes;
-            if (nfr == TC)
+            if (CP::USE_WHOLE && nfr == TC)
                 CP::template accumulate<true>(acc, reinterpret_cast<const XC*>(src),
                                               reinterpret_cast<const double*>(src + x_stage), nfr, lane, part);
             else
@@ -340,6 +343,7 @@ struct CovBlock {
     static constexpr int TC = cov_chunk_frames(M);
     static constexpr bool WB = false;
     static constexpr int WLANES = 1;
+    static constexpr bool USE_WHOLE = false;
 
     __device__ static __forceinline__ void coords(int part, int& bi, int& bj) {
         bi = 0;

@@ -14,6 +14,7 @@ namespace oiva {
 
 // sources per warp: the lane keeps 2*M*KC doubles of filters in registers
 // (M >= 13: two sources per warp -- 64 filter values -- halve the shared-memory reads of the staged kernels)
+// (four sources per warp at M = 8 -- K = 8 as two chunks instead of three -- measured slower: 2.96 vs 2.70 ms per 256 mixtures)
 constexpr int kc_cap() { return OIVA_M >= 13 ? 2 : ((24 / OIVA_M) > 4 ? 4 : (24 / OIVA_M)); }
 static int pick_kc(int K) {
     // the fewest source chunks the register budget allows, then chunks of EQUAL size: the warps of a CTA share the
