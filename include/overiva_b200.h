@@ -398,9 +398,12 @@ int oiva_plan_filters(oiva_plan_t* plan, void* W, void* stream);
 int oiva_plan_run(oiva_plan_t* plan, const void* X, int init_mode, const void* W0, int n_iter, int proj_back, void* Y,
                   void* W, void* stream);
 /* device pointers into the workspace (for tests and wrappers) */
-void* oiva_plan_what(oiva_plan_t* plan);    /* (R,M,M) c128 row-major; refreshed from the grouped state by
-                                               oiva_plan_init / oiva_plan_output / oiva_plan_filters */
-void* oiva_plan_cov(oiva_plan_t* plan);     /* (R,M,M) c128, full */
+void* oiva_plan_what(oiva_plan_t* plan);    /* (R,M,M) c128 row-major copy of W_hat: written by oiva_plan_filters and by
+                                               an oiva_plan_init that takes the row-major path (eig; shapes outside
+                                               the thread-per-bin kernels); the loop itself works on the grouped array
+                                               (oiva_plan_array(plan, 0)) */
+void* oiva_plan_cov(oiva_plan_t* plan);     /* (R,M,M) c128, full: valid after oiva_plan_load / oiva_plan_adopt_samples
+                                               (oiva_plan_run produces it only when something on its path reads it) */
 void* oiva_plan_samples(oiva_plan_t* plan); /* Xg */
 /* the status words: n_batch ints, one per mixture.  The CALLER zeroes them after oiva_plan_bind (the workspace is
  * uninitialised memory; oiva_plan_reset_status does it); they then accumulate (atomic OR) over everything the plan
