@@ -98,7 +98,9 @@ struct CovPart {
     static constexpr int NE = oiva_tri(M);
     static constexpr int NEP = (NE + P - 1) / P;
     static constexpr int NACC = NEP;
-    static constexpr int TC = cov_chunk_frames(M);  // frames per ring stage
+    // frames per ring stage.  (Stages twice as long for the four-warp teams of the many-source shapes -- half as many
+    // hand-offs -- measured much slower: M = K = 6 2.35 -> 3.67 ms, M = K = 8 5.5 -> 9.1 ms per 256 mixtures.)
+    static constexpr int TC = cov_chunk_frames(M);
     static constexpr bool WB = WBIN;
     static constexpr int WLANES = WBIN ? OIVA_GROUP : 1;  // weights per (source, frame) in a stage
     // the branch-free whole-chunk path (below) pays up to 6 channels (bench shape 2.21 -> 2.10 ms per launch, M = K = 4

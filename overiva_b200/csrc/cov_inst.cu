@@ -145,7 +145,11 @@ static int launch(CovParams p, cudaStream_t st, int* nsplit_out) {
         } else {
             auto kern = k_cov<ST, M, KC, P, WBIN>;
             static OivaPerDeviceOnce attr_done;
-            return launch_common(kern, p, st, P, cov_teams_per_cta(P), stage_bytes, TC, M, KC, attr_done, nsplit_out,
+            constexpr int TCP = CovPart<ST, M, KC, P, 0, WBIN>::TC;  // (longer stages for four-warp teams)
+            constexpr size_t x_stage_p = (size_t)TCP * M * OIVA_GROUP * sizeof(XC);
+            constexpr size_t stage_bytes_p =
+                ((x_stage_p + (size_t)KC * TCP * (WBIN ? OIVA_GROUP : 1) * sizeof(double) + 127) / 128) * 128;
+            return launch_common(kern, p, st, P, cov_teams_per_cta(P), stage_bytes_p, TCP, M, KC, attr_done, nsplit_out,
                                  [&](const CovParams& q, unsigned grid, int threads, size_t smem, int teams,
                                      int team_smem) { kern<<<grid, threads, smem, st>>>(q, teams, team_smem); });
         }
