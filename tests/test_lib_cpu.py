@@ -119,3 +119,25 @@ def test_drop_in_modules_expose_reference_signatures():
     assert sig.parameters["n_iter"].default == 4000 and sig.parameters["tol"].default == 1e-3
     sig = inspect.signature(m_pca.auxiva_pca)
     assert list(sig.parameters) == ["X", "n_src", "kwargs"]  # auxiva_pca.py:30
+    # the drivers' baseline: pra.bss.ilrma(X, n_iter=..., n_components=2, proj_back=True, callback=...)
+    # (overiva_oneshot.py:331-339); the leading parameters and defaults are pyroomacoustics'
+    from overiva_b200 import ilrma
+
+    sig = inspect.signature(ilrma)
+    assert list(sig.parameters)[:8] == ["X", "n_src", "n_iter", "proj_back", "W0", "n_components", "return_filters",
+                                        "callback"]
+    assert sig.parameters["n_iter"].default == 20 and sig.parameters["n_components"].default == 2
+    assert sig.parameters["proj_back"].default is False
+
+
+def test_host_pipeline_chunk_schedule():
+    """The host pipelines start and end with small chunks (only the first copy in and the last loop + copy out are not
+    overlapped by anything); every schedule covers the batch exactly, in order, with chunks no larger than asked."""
+    from overiva_b200.core import _chunk_schedule
+
+    for B in (1, 5, 31, 32, 33, 100, 191, 192, 193, 512, 4096):
+        for chunk in (1, 4, 8, 32, 64):
+            s = _chunk_schedule(B, chunk)
+            assert sum(s) == B and all(0 < n <= chunk for n in s), (B, chunk, s)
+    assert _chunk_schedule(512, 32)[:5] == [4, 4, 8, 16, 32] and _chunk_schedule(512, 32)[-4:] == [16, 8, 4, 4]
+    assert _chunk_schedule(100, 32) == [32, 32, 32, 4]  # short batches: plain chunks
