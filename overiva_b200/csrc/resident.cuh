@@ -12,14 +12,15 @@
 //     second barrier) -> gamma, phi and the W scale for the slice's frames -> weighted covariance of the slice from shared memory (per-warp partial sums to an L2-resident scratch)
 //     -> the LAST CTA of a bin group to arrive adds the partial sums in a fixed order and runs the group's IP sweep
 //     with C, V_s and W_hat staged in shared memory so that the dependent chain never waits for L2 (K < M: thread per
-//     bin, exactly the arithmetic of k_ip_update_tpb; K = M: a lane group per bin over all 8 warps, the arithmetic of
-//     k_ip_update), then releases the group's epoch flag; the other CTAs of the group spin on it.
+//     bin, exactly the arithmetic of k_ip_update_tpb; K = M: two lanes per bin, the arithmetic of k_ip_update_pair),
+//     then releases the group's epoch flag; the other CTAs of the group spin on it.
 //   All cross-CTA traffic (statistic partials, covariance partials, W_hat) is a few hundred KB per epoch and stays in L2.
 // Results are deterministic (fixed summation orders everywhere) and agree with the multi-kernel path to rounding
 // (same statistic arithmetic; the covariance sums frames in different sub-ranges).
 #pragma once
 #include "cov.cuh"
 #include "solve.cuh"
+#include "solve_pair.cuh"
 #include "solve_tpb.cuh"
 #include "stream.cuh"
 
@@ -398,57 +399,27 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
             __syncthreads();
             if constexpr (K == M && M >= 3) {
                 // determined case: the in-thread LU of the thread-per-bin sweep is one long dependent chain per source
-                // (config 2: ~6 us x 6 sources with 31 warps of the GPU idle).  Here all 8 warps take part: a group
-                // of G = next_pow2(M) lanes owns a bin, one row of [W_hat^H V_s | e_s] per lane, Gauss-Jordan with
-                // shuffle pivoting (solve.cuh, the arithmetic of k_ip_update) -- ~M times shorter chains.
-                constexpr int GL = Grp<M>::G, BPW = Grp<M>::BINS;
-                int singular = 0;
+                // (config 2: ~6 us x 6 sources).  Two lanes per bin instead (solve_pair.cuh: half of the rows each in
+                // registers, one exchange with the partner lane per pivot): warps 0 and 1 cover the 32 bins.  (Measured
+                // equal to the lane-group Gauss-Jordan over all 8 warps this loop used first -- config 2: 1.258 vs 1.257 ms
+                // per 20 epochs: fewer shuffles per pivot, three times the row-building work per lane -- and kept because
+                // it shares its code with the batched kernel.)
                 for (uint32_t i = tid; i < (uint32_t)(M * M * OIVA_GROUP); i += RES_THREADS)  // W *= wscale   overiva.py:161-167
                     sW[i] = cscale(sW[i], sWs[(i / OIVA_GROUP) % M]);
                 __syncthreads();
+                bool singular = false;
+                const int pl = (warp & 1) * 16 + (lane & 15), ph = lane >> 4;  // (warps 0, 1: bin and row half)
+                const bool pok = g * OIVA_GROUP + pl < L.F;
 #pragma unroll 1
                 for (int s = 0; s < K; ++s) {
-                    for (int bin0 = warp * BPW; bin0 < OIVA_GROUP; bin0 += RES_WARPS * BPW) {
-                        const int l = bin0 + lane / GL, gl = lane % GL;
-                        const bool rv = gl < M;
-                        const bool lv = g * OIVA_GROUP + l < L.F;  // padded bins keep their zero W_hat (nothing is written)
-                        auto Wat = [&](int r, int c) -> cplx& { return sW[(size_t)(r * M + c) * OIVA_GROUP + l]; };
-                        auto Vat = [&](int r, int c) { return herm_load<false>(sV + l, r, c); };
-                        cplx A[M + 1];
-#pragma unroll
-                        for (int c = 0; c <= M; ++c) A[c] = cmake(0.0, 0.0);
-                        if (rv) {
-                            for (int j = 0; j < M; ++j) {
-                                const cplx a = Wat(j, gl);
-#pragma unroll
-                                for (int c = 0; c < M; ++c) cfmac(A[c], a, Vat(j, c));
-                            }
-                            if (gl == s) A[M] = cmake(1.0, 0.0);
-                        }
-                        const int col = gauss_jordan<M, GL>(A, M, gl, lane, rv, singular);
-                        __syncwarp();
-                        if (col >= 0 && lv) Wat(col, s) = A[M];
-                        __syncwarp();
-                        cplx wi = cmake(0.0, 0.0), u = cmake(0.0, 0.0);  // w_s /= sqrt(w_s^H V_s w_s)    overiva.py:185-186
-                        if (rv) {
-                            wi = Wat(gl, s);
-#pragma unroll
-                            for (int j = 0; j < M; ++j) cfma(u, Vat(gl, j), Wat(j, s));
-                        }
-                        const cplx d = group_sum<GL>(cmulc(wi, u));
-                        const cplx inv = crecip(csqrt_(d));
-                        __syncwarp();
-                        if (rv && lv) Wat(gl, s) = cmul(wi, inv);
-                        __syncwarp();
-                        if (singular && lv) atomicOr(p.status + b, OIVA_STATUS_SINGULAR);
-                        singular = 0;
-                    }
+                    if (warp < 2) PairSweep<M, false>::source(WLane{sW + pl}, sV + pl, s, ph, pok, singular);
                     __syncthreads();
                     if (s + 1 < K) {
                         reduce_source(s + 1, sV, 0, RES_THREADS);
                         __syncthreads();
                     }
                 }
+                if (warp < 2 && singular && pok) atomicOr(p.status + b, OIVA_STATUS_SINGULAR);
                 bool bad = false;
                 for (uint32_t i = tid; i < (uint32_t)(M * M * OIVA_GROUP); i += RES_THREADS)
                     if (g * OIVA_GROUP + (int)(i % OIVA_GROUP) < L.F && (!isfinite(sW[i].x) || !isfinite(sW[i].y))) bad = true;

@@ -10,7 +10,8 @@
 // pivoting over the 8 rows -- the local candidate of each lane by selects, ONE exchange with the partner lane per pivot
 // (magnitude, then the normalised pivot row), elimination in the lane's other rows; the solution component of a row is
 // written to W_hat by the lane that holds it; the normalisation w^H V w is summed as (rows 0-3) + (rows 4-7).  7 channels
-// run as an 8 x 8 system with an identity row / column.  Same pivot rule as LAPACK's zgetrf (largest |re| + |im|, the
+// run as an 8 x 8 system with an identity row / column.  The per-source body (PairSweep) is shared with the resident
+// single-mixture loop, which runs it on shared memory for every determined shape with M >= 3.  Same pivot rule as LAPACK's zgetrf (largest |re| + |im|, the
 // lower row index wins a tie), so the result agrees with the other sweep kernels to rounding.
 #pragma once
 #include "solve_tpb.cuh"
@@ -19,40 +20,16 @@ namespace oiva {
 
 constexpr int PAIR_WARPS = 4;
 
-template <int M>
-__global__ void __launch_bounds__(PAIR_WARPS * 32) k_ip_update_pair(cplx* __restrict__ Wg, const cplx* __restrict__ Vg,
-                                                                    const double* __restrict__ wscale, int* status, int F,
-                                                                    int NG, long long G) {
-    static_assert(M == 7 || M == 8, "two lanes per bin: 7 or 8 channels");
-    constexpr int N = 8, RH = 4, NE = oiva_tri(M), K = M;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long hw = (long long)blockIdx.x * PAIR_WARPS + warp;  // half-group
-    if (hw >= 2 * G) return;                                         // whole warp
-    const long long gi = hw >> 1;
-    const int h = lane >> 4;                                 // which four rows this lane holds
-    const int l32 = (int)(hw & 1) * 16 + (lane & 15);        // the bin's lane position inside its group
-    const long long b = gi / NG;
-    const bool ok = (int)(gi - b * NG) * OIVA_GROUP + l32 < F;  // (padded bins run along -- the shuffles need every lane --
-                                                                 //  on the zeros stored there, and write nothing)
-    const WLane Wm = {Wg + (size_t)gi * M * M * OIVA_GROUP + l32};
-    const cplx* Vl = Vg + (size_t)gi * K * NE * OIVA_GROUP + l32;
+// One source of the determined sweep for the bin shared by lanes l and l ^ 16 of a warp (h = which half of the rows this
+// lane holds).  Wm / Vs: the bin's W_hat and the lower triangle of V_s in a grouped array (global memory, NC = true, or
+// shared memory, NC = false: the resident single-mixture loop).  M odd runs as an (M + 1) x (M + 1) system with an
+// identity row / column.  Every lane of the warp must call it (shuffles); `ok` = false lanes write nothing.
+template <int M, bool NC>
+struct PairSweep {
+    static constexpr int RH = (M + 1) / 2, N = 2 * RH;
 
-    if (wscale && ok) {  // W /= gamma (laplace) or sqrt(gamma) (gauss): this lane's rows      overiva.py:161-167
-#pragma unroll
-        for (int i = 0; i < RH; ++i) {
-            const int j = h * RH + i;
-            if (j < M) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) Wm[j * M + k] = cscale(Wm[j * M + k], wscale[b * K + k]);
-            }
-        }
-    }
-    __syncwarp();
-    bool singular = false;
-#pragma unroll 1
-    for (int s = 0; s < K; ++s) {
-        const cplx* Vs = Vl + (size_t)s * NE * OIVA_GROUP;
-        // rows r = 4h + i of A = W_hat^H V_s (A[r][c] = sum_j conj(W[j][r]) V[j][c]), right-hand side e_s
+    __device__ static __forceinline__ void source(WLane Wm, const cplx* Vs, int s, int h, bool ok, bool& singular) {
+        // rows r = RH h + i of A = W_hat^H V_s (A[r][c] = sum_j conj(W[j][r]) V[j][c]), right-hand side e_s
         cplx A[RH][N], rhs[RH];
 #pragma unroll
         for (int i = 0; i < RH; ++i) {
@@ -60,13 +37,13 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_ip_update_pair(cplx* __rest
             for (int c = 0; c < N; ++c) A[i][c] = cmake(0.0, 0.0);
             const int r = h * RH + i;
             rhs[i] = cmake(r == s ? 1.0 : 0.0, 0.0);
-            if (M < N && r == N - 1) A[i][N - 1] = cmake(1.0, 0.0);  // 7 channels: identity row / column 7
+            if (M < N && r == N - 1) A[i][N - 1] = cmake(1.0, 0.0);  // odd M: identity row / column N - 1
         }
 #pragma unroll
         for (int j = 0; j < M; ++j) {
             cplx vrow[M];
 #pragma unroll
-            for (int c = 0; c < M; ++c) vrow[c] = herm_load<true>(Vs, j, c);
+            for (int c = 0; c < M; ++c) vrow[c] = herm_load<NC>(Vs, j, c);
 #pragma unroll
             for (int i = 0; i < RH; ++i) {
                 const int r = h * RH + i;
@@ -77,9 +54,14 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_ip_update_pair(cplx* __rest
                 }
             }
         }
-        // Gauss-Jordan with partial pivoting over the 8 rows of the pair
-        bool used[RH] = {false, false, false, false};
-        int col_of[RH] = {0, 0, 0, 0};
+        // Gauss-Jordan with partial pivoting over the N rows of the pair
+        bool used[RH];
+        int col_of[RH];
+#pragma unroll
+        for (int i = 0; i < RH; ++i) {
+            used[i] = false;
+            col_of[i] = 0;
+        }
         static_for<N>([&](auto cc) {
             constexpr int c = decltype(cc)::value;
             double best = -1.0;
@@ -93,10 +75,9 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_ip_update_pair(cplx* __rest
                 }
             }
             const double pbest = __shfl_xor_sync(0xffffffffu, best, 16);
-            const bool mine = best > pbest || (best == pbest && h == 0) || (pbest != pbest && h == 0);
-            const bool any_valid = (mine ? best : pbest) > 0.0;
-            if (!any_valid) singular = true;  // zero or NaN pivot column
-            // this lane's candidate row (columns c..7 and the right-hand side), normalised by its pivot element
+            const bool mine = best > pbest || (best == pbest && h == 0);  // (a tie goes to the lower row index)
+            if (!((mine ? best : pbest) > 0.0)) singular = true;          // zero or NaN pivot column
+            // this lane's candidate row (columns c..N-1 and the right-hand side), normalised by its pivot element
             cplx cand[N + 1];
 #pragma unroll
             for (int col = c; col < N; ++col) {
@@ -161,29 +142,63 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_ip_update_pair(cplx* __rest
         cplx dpart = cmake(0.0, 0.0);
 #pragma unroll
         for (int r = 0; r < M; ++r) {
-            if ((r >> 2) == h) {
+            if (r / RH == h) {
                 cplx u = cmake(0.0, 0.0);
 #pragma unroll
-                for (int j = 0; j < M; ++j) cfma(u, herm_load<true>(Vs, r, j), w[j]);
+                for (int j = 0; j < M; ++j) cfma(u, herm_load<NC>(Vs, r, j), w[j]);
                 cfmac(dpart, w[r], u);
             }
         }
         const cplx dother = shfl_xor_c(dpart, 16);
-        const cplx d = h == 0 ? cadd(dpart, dother) : cadd(dother, dpart);  // (rows 0-3) + (rows 4-7) on both lanes
+        const cplx d = h == 0 ? cadd(dpart, dother) : cadd(dother, dpart);  // (first half of the rows) + (second half)
         const cplx inv = crecip(csqrt_(d));
         __syncwarp();  // (every lane has read the un-normalised column before anybody overwrites it)
         if (ok) {
 #pragma unroll
             for (int r = 0; r < M; ++r)
-                if ((r >> 2) == h) Wm[r * M + s] = cmul(w[r], inv);
+                if (r / RH == h) Wm[r * M + s] = cmul(w[r], inv);
         }
         __syncwarp();
     }
+};
+
+template <int M>
+__global__ void __launch_bounds__(PAIR_WARPS * 32) k_ip_update_pair(cplx* __restrict__ Wg, const cplx* __restrict__ Vg,
+                                                                    const double* __restrict__ wscale, int* status, int F,
+                                                                    int NG, long long G) {
+    static_assert(M == 7 || M == 8, "instantiated for the shapes the thread-per-bin sweep does not cover");
+    constexpr int RH = PairSweep<M, true>::RH, NE = oiva_tri(M), K = M;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long hw = (long long)blockIdx.x * PAIR_WARPS + warp;  // half-group
+    if (hw >= 2 * G) return;                                         // whole warp
+    const long long gi = hw >> 1;
+    const int h = lane >> 4;                                 // which half of the rows this lane holds
+    const int l32 = (int)(hw & 1) * 16 + (lane & 15);        // the bin's lane position inside its group
+    const long long b = gi / NG;
+    const bool ok = (int)(gi - b * NG) * OIVA_GROUP + l32 < F;  // (padded bins run along -- the shuffles need every lane --
+                                                                 //  on the zeros stored there, and write nothing)
+    const WLane Wm = {Wg + (size_t)gi * M * M * OIVA_GROUP + l32};
+    const cplx* Vl = Vg + (size_t)gi * K * NE * OIVA_GROUP + l32;
+
+    if (wscale && ok) {  // W /= gamma (laplace) or sqrt(gamma) (gauss): this lane's rows      overiva.py:161-167
+#pragma unroll
+        for (int i = 0; i < RH; ++i) {
+            const int j = h * RH + i;
+            if (j < M) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) Wm[j * M + k] = cscale(Wm[j * M + k], wscale[b * K + k]);
+            }
+        }
+    }
+    __syncwarp();
+    bool singular = false;
+#pragma unroll 1
+    for (int s = 0; s < K; ++s) PairSweep<M, true>::source(Wm, Vl + (size_t)s * NE * OIVA_GROUP, s, h, ok, singular);
     if (ok) {
         bool bad = false;
 #pragma unroll
         for (int r = 0; r < M; ++r)
-            if ((r >> 2) == h) {
+            if (r / RH == h) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     const cplx v = Wm[r * M + k];
