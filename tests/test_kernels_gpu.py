@@ -392,3 +392,51 @@ def test_fused_cov_sweep_equals_two_kernels(M, K, dtype, monkeypatch):
     for b in (0, 2099):
         _, Wo = orc.overiva(X[b].cpu().numpy().astype(np.complex128), n_src=K, n_iter=3, return_filters=True)
         assert rel_err(Wf[b].cpu().numpy(), Wo) <= (1e-10 if dtype == np.complex128 else 1e-4)
+
+
+@pytest.mark.parametrize("M,K,n_samples", [(2, 2, 1500), (4, 4, 2300), (6, 6, 1200), (8, 8, 900), (5, 3, 30000), (7, 1, 1500)])
+def test_weighted_covariance_per_bin_weights_and_power_output(M, K, n_samples):
+    """ILRMA's two kernel-level additions: the covariance with one weight per (source, frame, BIN) -- staged per lane next
+    to the samples -- and the per-bin power output of the statistic kernel, against numpy."""
+    lib = L.load()
+    B = 2
+    frame = 16 if n_samples > 20000 else 80  # (30000 samples at frame 16: few bins, many frames -> frame splits)
+    X = _mix(41, M, n_samples, frame, np.complex128, B=B)
+    _, T, F, _ = X.shape
+    NG, Tp = lib.oiva_bin_groups(F), lib.oiva_frame_pitch(T)
+    rng = np.random.default_rng(43)
+    winv = rng.gamma(1.0, 1.0, size=(B, K, F, T)) + 0.05
+    # grouped weights [gi][k][Tp][32], zero on padded bins / frames
+    wg = np.zeros((B, NG, K, Tp, 32))
+    pad = np.zeros((B, K, NG * 32, Tp))
+    pad[:, :, :F, :T] = winv
+    wg[:] = pad.reshape(B, K, NG, 32, Tp).transpose(0, 2, 1, 4, 3)
+    Xg = G.grouped(X)
+    wd = G.to_dev(wg)
+    Vg = torch.full((lib.oiva_grouped_cov_bytes(B, F, M, K) // 8,), float("nan"), dtype=torch.float64, device=G.dev())
+    ws_bytes = lib.oiva_weighted_cov_scratch_bytes(B, T, F, M, K)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=G.dev())
+    L.check(lib.oiva_weighted_cov_binwise(G.P(Xg), G.P(wd), G.P(Vg), G.P(ws) if ws_bytes else None, ws_bytes, B, T, F, M, K,
+                                          G.stream()), "oiva_weighted_cov_binwise")
+    V = torch.empty((B, F, K, M, M), dtype=torch.complex128, device=G.dev())
+    L.check(lib.oiva_unpack_cov(G.P(Vg), G.P(V), B, F, M, K, G.stream()), "oiva_unpack_cov")
+    torch.cuda.synchronize()
+    V = V.cpu().numpy()
+    for b in range(B):
+        for k in range(K):
+            want = np.einsum("tfm,ft,tfn->fmn", X[b], winv[b, k], np.conj(X[b])) / T
+            assert rel_err(V[b, :, k], want) < 1e-12, (b, k)
+    # per-bin powers |w_k^H x|^2 and their sums over the bins
+    W = rng.standard_normal((B, F, M, K)) + 1j * rng.standard_normal((B, F, M, K))
+    Wd = G.to_dev(W.astype(np.complex128))
+    part = torch.full((B, NG, K, Tp), np.nan, dtype=torch.float64, device=G.dev())
+    Pg = torch.full((B, NG, K, Tp, 32), np.nan, dtype=torch.float64, device=G.dev())
+    L.check(lib.oiva_demix_power_full(G.P(Xg), G.P(Wd), K, 0, G.P(part), G.P(Pg), B, T, F, M, K, L.C128, G.stream()),
+            "oiva_demix_power_full")
+    torch.cuda.synchronize()
+    Pw = np.abs(np.einsum("btfm,bfmk->bkft", X, np.conj(W))) ** 2  # (B, K, F, T)
+    Pgot = Pg.cpu().numpy().transpose(0, 2, 1, 4, 3).reshape(B, K, NG * 32, Tp)
+    assert rel_err(Pgot[:, :, :F, :T], Pw) < 1e-13
+    assert not Pgot[:, :, F:, :].any() and not Pgot[:, :, :, T:].any()  # padded bins / frames are written as zeros
+    r2 = part.cpu().numpy().sum(axis=1)[:, :, :T]
+    assert rel_err(r2, Pw.sum(axis=2)) < 1e-13
