@@ -239,6 +239,12 @@ int oiva_ogive_update(void* w, void* a, double* lambda_a, const void* V, const v
 int oiva_ogive_update_gated(void* w, void* a, double* lambda_a, const void* V, const void* C, const void* Cinv,
                             const uint8_t* do_a, double step_size, double* delta_hist, int epoch, double tol,
                             int n_rows, int n_chan, void* stream);
+/* n_epochs epochs of the loop in one call (oiva_demix_power -> oiva_source_model -> oiva_weighted_cov_ws (K = 1) ->
+ * oiva_unpack_cov -> oiva_ogive_update_gated with epoch = epoch0 + e); work arrays as for those calls.   ive.py:191-241 */
+int oiva_ogive_iterate(const void* Xg, void* w, void* a, double* lambda_a, double* r2part, double* phi, void* Vg,
+                       void* cov_scratch, size_t cov_scratch_bytes, void* V, const void* C, const void* Cinv,
+                       const uint8_t* do_a, double step_size, double* delta_hist, int epoch0, int n_epochs, double tol,
+                       int n_frames, int n_freq, int n_chan, int model, int dtype, void* stream);
 /* OGIVE set-up: Cinv = C^-1 (ive.py:98), cnorm (R,) = ||C||_F (ive.py:99); a from w (ive.py:132-135,168);
  * switching criterion masks (ive.py:142-161). */
 int oiva_ogive_setup(const void* C, void* Cinv, double* cnorm, int* status, int n_rows, int n_chan, void* stream);

@@ -69,6 +69,7 @@ SIGNATURES = {
     "oiva_compose_filters": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "oiva_ogive_update": (_i, [_p, _p, _p, _p, _p, _p, _p, _d, _p, _i, _i, _p]),
     "oiva_ogive_update_gated": (_i, [_p, _p, _p, _p, _p, _p, _p, _d, _p, _i, _d, _i, _i, _p]),
+    "oiva_ogive_iterate": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _sz, _p, _p, _p, _p, _d, _p, _i, _i, _d, _i, _i, _i, _i, _i, _p]),
     "oiva_ogive_setup": (_i, [_p, _p, _p, _p, _i, _i, _p]),
     "oiva_ogive_a_from_w": (_i, [_p, _p, _p, _i, _i, _p]),
     "oiva_ogive_switching": (_i, [_p, _p, _p, _p, _i, _i, _p]),

@@ -794,26 +794,26 @@ def ogive(X, n_iter=4000, step_size=0.1, tol=1e-3, update="demix", proj_back=Tru
         def converged(upto):  # ive.py:238-241 for the epochs run so far (one small D2H copy)
             return upto > 0 and float(dhist[upto - 1].item()) < tol
 
-        for epoch in range(n_iter):
-            # the stopping rule is evaluated on the device every epoch (oiva_ogive_update_gated freezes the state at
-            # the epoch the reference breaks at); the host only looks every SYNC_EVERY epochs
+        # the stopping rule is evaluated on the device every epoch (oiva_ogive_update_gated freezes the state at the epoch
+        # the reference breaks at); the host only looks every SYNC_EVERY epochs.  Epochs run in blocks of 10 (one library
+        # call each: oiva_ogive_iterate): the switching criterion (ive.py:187-188, every 10th epoch), the callback
+        # (ive.py:194-200, every 100th) and the convergence check all fall on block boundaries.
+        BLOCK = 10
+        epoch = 0
+        while epoch < n_iter:
             if epoch % SYNC_EVERY == 0 and converged(epoch):
                 break
-            if update == "switching" and epoch % 10 == 0:  # ive.py:187-188
+            if update == "switching":  # (epoch % 10 == 0 here)
                 L.check(lib.oiva_ogive_switching(_ptr(a), _ptr(Cx), _ptr(cnorm), _ptr(do_a), F, M, st),
                         "oiva_ogive_switching")
-            if callback is not None and epoch % 100 == 0:  # ive.py:194-200
+            if callback is not None and epoch % 100 == 0:
                 callback(inp.give_back(project(w)))
-            L.check(lib.oiva_demix_power(plan.samples_ptr, _ptr(w), 1, 0, _ptr(r2part), 1, T, F, M, 1, code, st),
-                    "oiva_demix_power")
-            L.check(lib.oiva_source_model(_ptr(r2part), nch, _ptr(phi), None, 1, T, 1, F, mcode, st),
-                    "oiva_source_model")
-            L.check(lib.oiva_weighted_cov_ws(plan.samples_ptr, _ptr(phi), _ptr(Vg), _ptr(cov_ws), cov_ws_bytes, 1, T, F,
-                                             M, 1, code, st), "oiva_weighted_cov_ws")
-            L.check(lib.oiva_unpack_cov(_ptr(Vg), _ptr(V), 1, F, M, 1, st), "oiva_unpack_cov")
-            L.check(lib.oiva_ogive_update_gated(_ptr(w), _ptr(a), _ptr(lam), _ptr(V), _ptr(Cx), _ptr(Cinv), _ptr(do_a),
-                                                float(step_size), _ptr(dhist), epoch, float(tol), F, M, st),
-                    "oiva_ogive_update_gated")
+            n_blk = min(BLOCK, n_iter - epoch)
+            L.check(lib.oiva_ogive_iterate(plan.samples_ptr, _ptr(w), _ptr(a), _ptr(lam), _ptr(r2part), _ptr(phi), _ptr(Vg),
+                                           _ptr(cov_ws), cov_ws_bytes, _ptr(V), _ptr(Cx), _ptr(Cinv), _ptr(do_a),
+                                           float(step_size), _ptr(dhist), epoch, n_blk, float(tol), T, F, M, mcode, code, st),
+                    "oiva_ogive_iterate")
+            epoch += n_blk
         Y = project(w)
         plan.raise_on_failure()
         Yo = inp.give_back(Y)

@@ -234,3 +234,31 @@ extern "C" int oiva_ogive_update_gated(void* w, void* a, double* lambda_a, const
     OIVA_LAUNCH_CHECK();
     return OIVA_OK;
 }
+
+// n_epochs epochs of the OGIVE loop in one library call (ive.py:191-241 without the callback / switching steps, which
+// the caller places between blocks): statistic -> source model -> weighted covariance (K = 1) -> full matrices ->
+// gated update.  The Python loop paid five ctypes round trips per epoch, of the order of the GPU work for one mixture.
+// Xg: grouped samples; w (F, M) c128 row-major filters; r2part (NG, Tp), phi (Tp), Vg, cov scratch, V (F, M, M): work
+// arrays as for the individual calls; epoch0: index of the first epoch (row of delta_hist).
+extern "C" int oiva_ogive_iterate(const void* Xg, void* w, void* a, double* lambda_a, double* r2part, double* phi, void* Vg,
+                                  void* cov_scratch, size_t cov_scratch_bytes, void* V, const void* C, const void* Cinv,
+                                  const uint8_t* do_a, double step_size, double* delta_hist, int epoch0, int n_epochs,
+                                  double tol, int n_frames, int n_freq, int n_chan, int model, int dtype, void* stream) {
+    OIVA_REQUIRE(Xg && w && a && lambda_a && r2part && phi && Vg && V && C && Cinv && do_a && delta_hist,
+                 "oiva_ogive_iterate: null pointer");
+    const int NG = oiva_bin_groups(n_freq);
+    for (int e = 0; e < n_epochs; ++e) {
+        int rc = oiva_demix_power(Xg, w, 1, 0, r2part, 1, n_frames, n_freq, n_chan, 1, dtype, stream);
+        if (rc) return rc;
+        rc = oiva_source_model(r2part, NG, phi, nullptr, 1, n_frames, 1, n_freq, model, stream);
+        if (rc) return rc;
+        rc = oiva_weighted_cov_ws(Xg, phi, Vg, cov_scratch, cov_scratch_bytes, 1, n_frames, n_freq, n_chan, 1, dtype, stream);
+        if (rc) return rc;
+        rc = oiva_unpack_cov(Vg, V, 1, n_freq, n_chan, 1, stream);
+        if (rc) return rc;
+        rc = oiva_ogive_update_gated(w, a, lambda_a, V, C, Cinv, do_a, step_size, delta_hist, epoch0 + e, tol, n_freq, n_chan,
+                                     stream);
+        if (rc) return rc;
+    }
+    return OIVA_OK;
+}
