@@ -1,4 +1,5 @@
 // C entry point of the persistent single-launch epoch loop (include/overiva_b200.h: oiva_loop_resident).
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "resident.cuh"
@@ -104,9 +105,45 @@ extern "C" int oiva_loop_resident(const void* Xg, void* Wg, const void* Cg, doub
     p.F_total = n_freq_total > 0 ? n_freq_total : n_freq;
     p.slice_cap = ch.slice_cap;
     p.v_bufs = ch.v_bufs;
+    {
+        const char* v = getenv("OIVA_RES_POLL");  // (read per call: profiles compare the modes in one process)
+        p.poll = v ? atoi(v) : 2;
+        v = getenv("OIVA_RES_CLUSTER");
+        p.cluster = v ? atoi(v) : 1;
+    }
     p.invT = 1.0 / (double)n_frames;
     OIVA_CUDA_CHECK(cudaMemsetAsync(sync, 0, oiva_loop_resident_sync_bytes(n_batch, n_freq), st));
     const unsigned grid = (unsigned)(p.G * ch.SG);
+    p.trace = nullptr;
+    if (const char* path = getenv("OIVA_RES_TRACE")) {
+        // profiling only: one synchronous launch with clock64 stamps of every CTA's phases, written to `path` as text
+        // (cta epoch stamp0..stamp9, in SM cycles); the stamps add CTA barriers, so the traced launch is a little slower
+        const size_t n = (size_t)grid * n_iter * RES_TRACE_POINTS;
+        OIVA_CUDA_CHECK(cudaMalloc(&p.trace, n * sizeof(long long)));
+        OIVA_CUDA_CHECK(cudaMemsetAsync(p.trace, 0, n * sizeof(long long), st));
+        int rc = OIVA_ERR_UNSUPPORTED;
+        switch (n_chan) {
+#define OIVA_CASE(M_) case M_: rc = resident_launch_m##M_(dtype, n_src, p, grid, ch.smem, st); break;
+            OIVA_CASE(1) OIVA_CASE(2) OIVA_CASE(3) OIVA_CASE(4) OIVA_CASE(5) OIVA_CASE(6) OIVA_CASE(7) OIVA_CASE(8)
+#undef OIVA_CASE
+        }
+        if (rc == OIVA_OK && cudaStreamSynchronize(st) == cudaSuccess) {
+            long long* h = (long long*)malloc(n * sizeof(long long));
+            if (h && cudaMemcpy(h, p.trace, n * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+                if (FILE* f = fopen(path, "w")) {
+                    for (size_t i = 0; i < (size_t)grid * n_iter; ++i) {
+                        fprintf(f, "%zu %zu", i / n_iter, i % n_iter);
+                        for (int j = 0; j < RES_TRACE_POINTS; ++j) fprintf(f, " %lld", h[i * RES_TRACE_POINTS + j]);
+                        fprintf(f, "\n");
+                    }
+                    fclose(f);
+                }
+            }
+            free(h);
+        }
+        cudaFree(p.trace);
+        return rc;
+    }
     switch (n_chan) {
 #define OIVA_CASE(M_) case M_: return resident_launch_m##M_(dtype, n_src, p, grid, ch.smem, st);
         OIVA_CASE(1) OIVA_CASE(2) OIVA_CASE(3) OIVA_CASE(4) OIVA_CASE(5) OIVA_CASE(6) OIVA_CASE(7) OIVA_CASE(8)

@@ -28,6 +28,7 @@ namespace oiva {
 
 constexpr int RES_WARPS = 8;
 constexpr int RES_THREADS = RES_WARPS * 32;
+constexpr int RES_TRACE_POINTS = 10;  // stamps per CTA and epoch when ResidentParams::trace is set
 constexpr int RES_SYNC_HEADER = 8;  // sync[0]: grid-barrier counter; [8 + gi]: arrivals of group gi; [8 + G + gi]: its flag
 
 struct ResidentParams {
@@ -44,6 +45,9 @@ struct ResidentParams {
     int B, SG, n_iter, model, F_total;
     int slice_cap;    // frames a slice can hold (= max over slices)
     int v_bufs;       // 1 or 2 shared-memory buffers for the reduced V_s
+    int cluster;      // 1: the SG CTAs of a bin group form a thread-block cluster and hand over through cluster barriers
+    long long* trace; // null, or (grid, n_iter, RES_TRACE_POINTS) clock64 stamps of thread 0 (OIVA_RES_TRACE, profiling only)
+    int poll;         // how waiters spin: 0 acquire loads, 1 relaxed loads + one fence, 2 relaxed loads + one acquire load
     double invT;
 };
 
@@ -61,6 +65,24 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// spin until *p >= target. An acquire load invalidates L1 on every iteration; the relaxed modes pay that once.
+__device__ __forceinline__ void spin_until_ge(const unsigned* p, unsigned target, int mode) {
+    if (mode == 0) {
+        while (ld_acquire_u32(p) < target) {
+        }
+    } else {
+        while (ld_relaxed_u32(p) < target) {
+        }
+        if (mode == 1) fence_acquire_gpu();
+        else (void)ld_acquire_u32(p);
+    }
+}
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -72,16 +94,27 @@ __device__ __forceinline__ unsigned atom_acq_rel_add_u32(unsigned* p, unsigned v
     asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
     return old;
 }
+#define OIVA_RES_STAMP(n)                                                                                    \
+    do {                                                                                                     \
+        if (p.trace) {                                                                                       \
+            __syncthreads();                                                                                 \
+            if (threadIdx.x == 0) p.trace[((size_t)blockIdx.x * p.n_iter + epoch) * RES_TRACE_POINTS + (n)] = clock64(); \
+        }                                                                                                    \
+    } while (0)
+// all threads of the cluster; release/acquire at cluster scope orders the partial sums and W (st.cg / ld.cg, L2) between
+// the CTAs of a bin group without a round trip through a flag in global memory
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // all CTAs of the (cooperative, co-resident) grid; `target` = gridDim.x * (number of barriers so far).
 // One release-add and an acquire spin by thread 0 between two CTA barriers: the CTA barrier orders the other threads'
 // writes before thread 0's release and thread 0's acquire before their later reads (causality order is cumulative), so
 // no separate __threadfence() is needed (the first version had two per barrier: MEMBAR.SC.GPU at 3.3 us per barrier).
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target, int mode) {
     __syncthreads();
     if (threadIdx.x == 0) {
         red_release_add_u32(counter, 1u);
-        while (ld_acquire_u32(counter) < target) {
-        }
+        spin_until_ge(counter, target, mode);
     }
     __syncthreads();
 }
@@ -224,6 +257,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
     unsigned n_bar = 0;
 #pragma unroll 1
     for (int epoch = 0; epoch < p.n_iter; ++epoch) {
+        OIVA_RES_STAMP(0);
         // ---- (1) statistic of the slice: r2part[gi][k][t] = sum over the 32 bins |w_k^H x|^2      overiva.py:140,152-155
         {
             cplx w[M][K];
@@ -272,10 +306,12 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                 }
             }
         }
-        grid_barrier(bar_counter, (++n_bar) * gridDim.x);
+        OIVA_RES_STAMP(1);
+        grid_barrier(bar_counter, (++n_bar) * gridDim.x, p.poll);
+        OIVA_RES_STAMP(2);
 
-        // ---- (2) r[b][k][t] = model(sum over the bin groups); the summation order is k_source_model's (8 interleaved
-        //      slices, then a fixed tree)                                                           overiva.py:152-155
+        // ---- (2) r[b][k][t] = model(sum over the bin groups): interleaved slices of the groups per lane, then a fixed
+        //      tree -- deterministic; k_source_model's order when a mixture has at most 16 groups   overiva.py:152-155
         auto model_fn = [&](double s) {
             switch (p.model) {
                 case OIVA_MODEL_LAPLACE: return 2.0 * sqrt(s);
@@ -285,12 +321,18 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
         };
         {
             // the (k, t) pairs are dealt round-robin to the CTAs, r goes through rbuf (L2) and a second grid barrier.
-            // (Every CTA summing all partials of its mixture itself -- one barrier less -- measured slower at config 1:
-            // 0.47 vs 0.41 ms per 20 epochs; the 130 CTAs re-read K * T * NG partials each, 8 of every 32-byte sector.)
+            // (Every CTA summing the partials itself instead -- one grid barrier less -- measured no faster, twice: all
+            // frames per CTA, 8 of every 32-byte sector used: 0.47 vs 0.41 ms per 20 epochs of config 1; only the CTA's own
+            // frames, coalesced, gamma sums exchanged through the cluster's shared memory: 5400 cycles for the sums where
+            // this phase and its barrier take 2800 + 2700, and 17400 at config 2 -- 130 CTAs pull the same lines out of L2.)
             const long long n_pairs = (long long)p.B * K * T;
-            const int sub = lane >> 3, cs = lane & 7;
-            for (long long q0 = ((long long)blockIdx.x * RES_WARPS + warp) * 4; q0 < n_pairs;
-                 q0 += (long long)gridDim.x * RES_WARPS * 4) {
+            // lanes per pair: 8 (four pairs per warp), or the whole warp when a mixture has more than 16 bin groups -- one
+            // L2 latency instead of three for the 65 groups of a 2049-bin mixture; the warps are dealt CTA-first so that
+            // a short list of pairs spreads over all SMs
+            const int lp = L.NG > 16 ? 32 : 8, ppw = 32 / lp;
+            const int sub = lane / lp, cs = lane % lp;
+            const long long w0 = (long long)warp * gridDim.x + blockIdx.x;
+            for (long long q0 = w0 * ppw; q0 < n_pairs; q0 += (long long)gridDim.x * RES_WARPS * ppw) {
                 const long long q = q0 + sub;
                 const bool ok = q < n_pairs;
                 const long long qq = ok ? q : 0;
@@ -301,14 +343,20 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                 if (ok) {
                     const double* src = p.r2part + ((size_t)pb * L.NG * K + k) * Tp + t;
 #pragma unroll 4
-                    for (int ch = cs; ch < L.NG; ch += 8) sum += __ldcg(src + (size_t)ch * K * Tp);
+                    for (int ch = cs; ch < L.NG; ch += lp) sum += __ldcg(src + (size_t)ch * K * Tp);
                 }
                 sum += __shfl_xor_sync(0xffffffffu, sum, 1);
                 sum += __shfl_xor_sync(0xffffffffu, sum, 2);
                 sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+                if (lp == 32) {
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+                }
                 if (ok && cs == 0) __stcg(p.rbuf + ((size_t)pb * K + k) * Tp + t, model_fn(sum));
             }
-            grid_barrier(bar_counter, (++n_bar) * gridDim.x);
+            OIVA_RES_STAMP(3);
+            grid_barrier(bar_counter, (++n_bar) * gridDim.x, p.poll);
+            OIVA_RES_STAMP(4);
         }
 
         // ---- (3) gamma = mean_t r, phi = 1 / max(r / gamma, 1e-15) for the slice's frames, W scale   overiva.py:158-173
@@ -342,6 +390,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
             sPhi[k * pitch + fr] = 1.0 / r;
         }
         __syncthreads();
+        OIVA_RES_STAMP(5);
 
         // ---- (4) weighted covariance of the slice, per-warp partial sums to the L2 scratch            overiva.py:179
         {
@@ -351,47 +400,61 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
             cplx* dst = p.Vpart + ((size_t)slot * p.G + gi) * grp_cov;
             ResCovDispatch<ST, M, K, RC::P>::run(part, sX, sPhi, pitch, f0, f1, dst, p.invT, lane);
         }
-        __syncthreads();
-        if (tid == 0) {  // (acq_rel: publishes this CTA's partial sums, and the last arriver sees everybody else's)
-            const unsigned old = atom_acq_rel_add_u32(arrive, 1u);
-            sFlag[0] = (old == (unsigned)(p.SG * (epoch + 1) - 1)) ? 1 : 0;
+        bool owner;
+        OIVA_RES_STAMP(6);
+        if (p.cluster) {  // (the first CTA of the cluster sums and sweeps)
+            cluster_barrier();
+            owner = sl == 0;
+        } else {
+            __syncthreads();
+            if (tid == 0) {  // (acq_rel: publishes this CTA's partial sums, and the last arriver sees everybody else's)
+                const unsigned old = atom_acq_rel_add_u32(arrive, 1u);
+                sFlag[0] = (old == (unsigned)(p.SG * (epoch + 1) - 1)) ? 1 : 0;
+            }
+            __syncthreads();
+            owner = sFlag[0] != 0;
         }
-        __syncthreads();
 
-        if (sFlag[0]) {
+        OIVA_RES_STAMP(7);
+        if (owner) {
             // ---- (5) last CTA of the group: fixed-order sum of the partial covariances + the IP sweep   overiva.py:176-190
             const int n_slots = p.SG * RC::FW;
             // (the slots are added in ascending order, as k_cov_sum_partials does; the loads of 8 slots are issued
             // before the first add -- one L2 latency per 8 slots instead of one per slot: ncu showed the other CTAs of
             // the group waiting 30 % of the epoch for this loop when it was a plain load-add chain)
+            // Two elements per thread and round: 16 loads in flight, so the 320 elements of config 1 (16 slots) take
+            // two L2 latencies instead of four and the 672 of config 2 (8 slots) two instead of three.
             auto reduce_source = [&](int s, cplx* out, int first_thread, int n_threads) {
-                for (uint32_t i = tid - first_thread; i < MAT_ELEMS; i += n_threads) {
+                const size_t slot_stride = (size_t)p.G * grp_cov;
+                for (uint32_t i = tid - first_thread; i < MAT_ELEMS; i += 2 * n_threads) {
+                    const uint32_t i2 = i + n_threads;
+                    const bool two = i2 < MAT_ELEMS;
                     const cplx* src = p.Vpart + (size_t)gi * grp_cov + (size_t)s * MAT_ELEMS + i;
-                    const size_t slot_stride = (size_t)p.G * grp_cov;
-                    cplx acc = cmake(0.0, 0.0);
+                    const cplx* src2 = src + (two ? n_threads : 0);
+                    cplx acc = cmake(0.0, 0.0), acc2 = cmake(0.0, 0.0);
                     for (int sp0 = 0; sp0 < n_slots; sp0 += 8) {
-                        cplx v[8];
+                        cplx v[8], v2[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            v[j] = sp0 + j < n_slots ? __ldcg(src + (size_t)(sp0 + j) * slot_stride) : cmake(0.0, 0.0);
-                        if (sp0 == 0) {
-                            acc = v[0];
+                        for (int j = 0; j < 8; ++j) {
+                            const bool in = sp0 + j < n_slots;
+                            v[j] = in ? __ldcg(src + (size_t)(sp0 + j) * slot_stride) : cmake(0.0, 0.0);
+                            v2[j] = in && two ? __ldcg(src2 + (size_t)(sp0 + j) * slot_stride) : cmake(0.0, 0.0);
+                        }
 #pragma unroll
-                            for (int j = 1; j < 8; ++j)
-                                if (j < n_slots) {
-                                    acc.x += v[j].x;
-                                    acc.y += v[j].y;
-                                }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                if (sp0 + j < n_slots) {
-                                    acc.x += v[j].x;
-                                    acc.y += v[j].y;
-                                }
+                        for (int j = 0; j < 8; ++j) {
+                            if (sp0 == 0 && j == 0) {  // (the first slot starts the sum: no 0.0 + x, which would turn -0.0 into +0.0)
+                                acc = v[0];
+                                acc2 = v2[0];
+                            } else if (sp0 + j < n_slots) {
+                                acc.x += v[j].x;
+                                acc.y += v[j].y;
+                                acc2.x += v2[j].x;
+                                acc2.y += v2[j].y;
+                            }
                         }
                     }
                     out[i] = acc;
+                    if (two) out[i2] = acc2;
                 }
             };
             for (uint32_t i = tid; i < (uint32_t)(M * M * OIVA_GROUP); i += RES_THREADS) sW[i] = __ldcg(Wgrp + i);
@@ -452,15 +515,17 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
             }
             __syncthreads();
             for (uint32_t i = tid; i < (uint32_t)(M * M * OIVA_GROUP); i += RES_THREADS) __stcg(Wgrp + i, sW[i]);
-            __syncthreads();
-            if (tid == 0) st_release_u32(flag, (unsigned)(epoch + 1));
-        } else {
-            if (tid == 0) {
-                while (ld_acquire_u32(flag) < (unsigned)(epoch + 1)) {
-                }
+            if (!p.cluster) {
+                __syncthreads();
+                if (tid == 0) st_release_u32(flag, (unsigned)(epoch + 1));
             }
+        } else if (!p.cluster) {
+            if (tid == 0) spin_until_ge(flag, (unsigned)(epoch + 1), p.poll);
             __syncthreads();
         }
+        OIVA_RES_STAMP(8);
+        if (p.cluster) cluster_barrier();
+        OIVA_RES_STAMP(9);
     }
 }
 

@@ -29,8 +29,38 @@ static int launch_res(const ResidentParams& p, unsigned grid, size_t smem, cudaS
             return OIVA_ERR_UNSUPPORTED;
         }
         ResidentParams q = p;
-        void* args[] = {(void*)&q};
-        OIVA_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(RES_THREADS), args, smem, st));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(RES_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attrs[2];
+        attrs[0].id = cudaLaunchAttributeCooperative;
+        attrs[0].val.cooperative = 1;
+        attrs[1].id = cudaLaunchAttributeClusterDimension;
+        attrs[1].val.clusterDim.x = (unsigned)p.SG;
+        attrs[1].val.clusterDim.y = 1;
+        attrs[1].val.clusterDim.z = 1;
+        cfg.attrs = attrs;
+        if (q.cluster && p.SG > 1) {  // the slices of a bin group as one cluster, when that many clusters are co-resident
+            cfg.numAttrs = 2;
+            int n_clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg) != cudaSuccess ||
+                (long long)n_clusters * p.SG < (long long)grid) {
+                (void)cudaGetLastError();
+                q.cluster = 0;
+            }
+        } else {
+            q.cluster = 0;
+        }
+        if (q.cluster) {
+            cfg.numAttrs = 2;
+            if (cudaLaunchKernelEx(&cfg, kern, q) == cudaSuccess) return OIVA_OK;
+            (void)cudaGetLastError();  // (cooperative + cluster refused: the flag hand-over needs neither)
+            q.cluster = 0;
+        }
+        cfg.numAttrs = 1;
+        OIVA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, q));
         return OIVA_OK;
     }
 }

@@ -251,8 +251,8 @@ __device__ __forceinline__ void ip_source_reduced_tri(WLane Wm, cplx (&Lm)[oiva_
             djj = fma(-l.x, l.x, fma(-l.y, l.y, djj));
         });
         if (!(djj > 0.0)) singular = true;  // not positive definite (or NaN)
-        const double ljj = sqrt(djj);
-        dinv[j] = 1.0 / ljj;
+        dinv[j] = rsqrt(djj);  // 1 / L[j][j]: one MUFU.RSQ64H + 4 fp64 operations where sqrt and a division are ~3x that,
+                               // on the critical path of every pivot (1 ulp, like the two roundings it replaces)
         static_for<M - 1 - j>([&](auto ic) {
             constexpr int i = j + 1 + decltype(ic)::value;
             cplx v = Lm[i * (i + 1) / 2 + j];
@@ -290,7 +290,7 @@ __device__ __forceinline__ void ip_source_reduced_tri(WLane Wm, cplx (&Lm)[oiva_
         });
         q[i] = cscale(v, dinv[i]);
     });
-    const double inv = 1.0 / sqrt(den);  // w^H V_s w = |y|^2 is real positive                 overiva.py:185-186
+    const double inv = rsqrt(den);  // w^H V_s w = |y|^2 is real positive                      overiva.py:185-186
 #pragma unroll
     for (int i = 0; i < M; ++i) Wm[i * M + s] = cscale(q[i], inv);
 }
