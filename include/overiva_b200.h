@@ -63,6 +63,7 @@ extern "C" {
 
 #define OIVA_STATUS_SINGULAR 1
 #define OIVA_STATUS_NONFINITE 2
+#define OIVA_STATUS_STALLED 4 /* a hand-over inside the single-launch loop timed out (never expected): results invalid */
 
 int oiva_version(void);
 const char* oiva_last_error(void);

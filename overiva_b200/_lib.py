@@ -17,7 +17,7 @@ ERR_INVALID, ERR_NOMEM, ERR_STATE, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3, -4, -
 C128, C64 = 0, 1
 MODEL_LAPLACE, MODEL_GAUSS, MODEL_NONE, MODEL_OGIVE_LAPLACE, MODEL_OGIVE_GAUSS = 0, 1, 2, 3, 4
 INIT_EYE, INIT_EIG, INIT_W0 = 0, 1, 2
-STATUS_SINGULAR, STATUS_NONFINITE = 1, 2
+STATUS_SINGULAR, STATUS_NONFINITE, STATUS_STALLED = 1, 2, 4
 
 
 class PlanDesc(C.Structure):

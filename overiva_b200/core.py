@@ -286,10 +286,15 @@ def raise_for_status(status):
     * ``STATUS_NONFINITE`` alone (NaN / Inf in the demixing matrices without a singular pivot, e.g. an all-zero
       input where gamma = 0): the reference silently returns NaN arrays (numpy emits RuntimeWarnings); so does this
       implementation, with one ``RuntimeWarning``.
+    * ``STATUS_STALLED`` (a hand-over inside the single-launch loop timed out -- a bug or a broken device, never the
+      data): ``RuntimeError``.
     Any other value is a corrupted status word and raises ``RuntimeError``."""
     status = np.atleast_1d(np.asarray(status))
-    if np.any((status < 0) | (status > (L.STATUS_SINGULAR | L.STATUS_NONFINITE))):
-        raise RuntimeError("corrupt status words %r" % (status[(status < 0) | (status > 3)][:8],))
+    if np.any((status < 0) | (status > 7)):
+        raise RuntimeError("corrupt status words %r" % (status[(status < 0) | (status > 7)][:8],))
+    if np.any(status & L.STATUS_STALLED):
+        raise RuntimeError("the single-launch loop stalled waiting for another thread block (OIVA_STATUS_STALLED); "
+                           "the results are invalid -- rerun with OIVA_NO_RESIDENT=1 and report this")
     sing = np.nonzero(status & L.STATUS_SINGULAR)[0]
     if sing.size:
         if status.size == 1:

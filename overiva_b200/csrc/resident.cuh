@@ -29,6 +29,8 @@ namespace oiva {
 constexpr int RES_WARPS = 8;
 constexpr int RES_THREADS = RES_WARPS * 32;
 constexpr int RES_TRACE_POINTS = 10;  // stamps per CTA and epoch when ResidentParams::trace is set
+constexpr int RES_TAG_MAX_GROUPS = 160;    // bin groups per mixture the tagged statistic sum holds in registers (5 per lane)
+constexpr unsigned RES_SPIN_LIMIT = 1u << 21;  // polls (~1 us each) before a waiter gives up and reports OIVA_STATUS_STALLED
 constexpr int RES_SYNC_HEADER = 8;  // sync[0]: grid-barrier counter; [8 + gi]: arrivals of group gi; [8 + G + gi]: its flag
 
 struct ResidentParams {
@@ -47,6 +49,7 @@ struct ResidentParams {
     int v_bufs;       // 1 or 2 shared-memory buffers for the reduced V_s
     int cluster;      // 1: the SG CTAs of a bin group form a thread-block cluster and hand over through cluster barriers
     long long* trace; // null, or (grid, n_iter, RES_TRACE_POINTS) clock64 stamps of thread 0 (OIVA_RES_TRACE, profiling only)
+    int tagged;       // 1: no grid barrier inside the epoch -- the statistic words carry the epoch's parity in their sign bit
     int poll;         // how waiters spin: 0 acquire loads, 1 relaxed loads + one fence, 2 relaxed loads + one acquire load
     double invT;
 };
@@ -101,6 +104,36 @@ __device__ __forceinline__ unsigned atom_acq_rel_add_u32(unsigned* p, unsigned v
             if (threadIdx.x == 0) p.trace[((size_t)blockIdx.x * p.n_iter + epoch) * RES_TRACE_POINTS + (n)] = clock64(); \
         }                                                                                                    \
     } while (0)
+// ---- statistic words that announce themselves ----------------------------------------------------------------------
+// r2part and r are sums of squares / norms: never negative, so the sign bit is free.  A producer stores the value of epoch
+// e with sign bit e & 1 (one 8-byte relaxed store: value and flag cannot be seen apart); a consumer polls the word itself
+// until the sign is the epoch's and strips it.  That replaces "store, release, count, spin on the counter, load" -- a grid
+// barrier, ~2700 cycles twice per epoch -- by the store and the load.  Nobody can lap anybody: a producer reaches epoch
+// e + 1 only through phase (3) of epoch e, which needs every r of its mixture, each published only after its summing warp
+// has read every r2part word it covers.
+__device__ __forceinline__ double ld_relaxed_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_f64(double* p, double v) {
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+// (In PTX on purpose: written as C++ bit operations the compiler recognises fabs(), emits abs.f64 -- an arithmetic DADD in
+// SASS, which turns a NaN into the canonical NaN, sign bit SET -- and a NaN statistic of a singular mixture would carry
+// the wrong parity for ever.  The integer instructions keep the NaN a NaN and make its sign ours.)
+__device__ __forceinline__ double tag_word(double v, unsigned parity) {
+    double r;
+    asm volatile(
+        "{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tand.b32 hi, hi, 0x7fffffff;\n\tor.b32 hi, hi, %2;\n\t"
+        "mov.b64 %0, {lo, hi};\n\t}"
+        : "=d"(r)
+        : "d"(v), "r"(parity << 31));
+    return r;
+}
+__device__ __forceinline__ bool tag_is(double v, unsigned parity) {
+    return ((unsigned)__double2hiint(v) >> 31) == parity;
+}
 // all threads of the cluster; release/acquire at cluster scope orders the partial sums and W (st.cg / ld.cg, L2) between
 // the CTAs of a bin group without a round trip through a flag in global memory
 __device__ __forceinline__ void cluster_barrier() {
@@ -255,8 +288,32 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
     mbar_wait(bar, 0);
 
     unsigned n_bar = 0;
+    bool stalled = false;
+    // the (k, t) pairs of the statistic sum are dealt to the warps of the grid, CTA-first so that a short list spreads over
+    // all SMs; lanes per pair: 8 (four pairs per warp), or the whole warp when a mixture has more than 16 bin groups (one
+    // L2 latency instead of three for the 65 groups of a 2049-bin mixture)
+    const long long n_pairs = (long long)p.B * K * T;
+    const int lp = L.NG > 16 ? 32 : 8, ppw = 32 / lp;
+    const int pair_sub = lane / lp, pair_cs = lane % lp;
+    const long long pair_q0 = ((long long)warp * gridDim.x + blockIdx.x) * ppw + pair_sub;
+    const long long pair_step = (long long)gridDim.x * RES_WARPS * ppw;
+    if (p.tagged) {  // every word this CTA will produce starts as "epoch -1" (sign set), then ONE grid barrier per launch
+        double* r2g = p.r2part + (size_t)gi * K * Tp;
+        for (int i = tid; i < K * nfr; i += RES_THREADS) {
+            const int k = i / nfr, fr = i - k * nfr;
+            st_relaxed_f64(r2g + (size_t)k * Tp + t0 + fr, -1.0);
+        }
+        if (pair_cs == 0)
+            for (long long q = pair_q0; q < n_pairs; q += pair_step) {
+                const long long pb = q / ((long long)K * T);
+                const int rem = (int)(q - pb * K * T);
+                st_relaxed_f64(p.rbuf + ((size_t)pb * K + rem / T) * Tp + rem % T, -1.0);
+            }
+        grid_barrier(bar_counter, (++n_bar) * gridDim.x, p.poll);
+    }
 #pragma unroll 1
     for (int epoch = 0; epoch < p.n_iter; ++epoch) {
+        const unsigned par = (unsigned)epoch & 1u;
         OIVA_RES_STAMP(0);
         // ---- (1) statistic of the slice: r2part[gi][k][t] = sum over the 32 bins |w_k^H x|^2      overiva.py:140,152-155
         {
@@ -302,12 +359,15 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                     s += __shfl_xor_sync(0xffffffffu, s, 2);
                     s += __shfl_xor_sync(0xffffffffu, s, 1);
                     const int j = lane >> 2;
-                    if ((lane & 3) == 0 && fb + j < nfr) __stcg(r2g + (size_t)k * Tp + t0 + fb + j, s);
+                    if ((lane & 3) == 0 && fb + j < nfr) {
+                        if (p.tagged) st_relaxed_f64(r2g + (size_t)k * Tp + t0 + fb + j, tag_word(s, par));
+                        else __stcg(r2g + (size_t)k * Tp + t0 + fb + j, s);
+                    }
                 }
             }
         }
         OIVA_RES_STAMP(1);
-        grid_barrier(bar_counter, (++n_bar) * gridDim.x, p.poll);
+        if (!p.tagged) grid_barrier(bar_counter, (++n_bar) * gridDim.x, p.poll);
         OIVA_RES_STAMP(2);
 
         // ---- (2) r[b][k][t] = model(sum over the bin groups): interleaved slices of the groups per lane, then a fixed
@@ -325,25 +385,40 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
             // frames per CTA, 8 of every 32-byte sector used: 0.47 vs 0.41 ms per 20 epochs of config 1; only the CTA's own
             // frames, coalesced, gamma sums exchanged through the cluster's shared memory: 5400 cycles for the sums where
             // this phase and its barrier take 2800 + 2700, and 17400 at config 2 -- 130 CTAs pull the same lines out of L2.)
-            const long long n_pairs = (long long)p.B * K * T;
-            // lanes per pair: 8 (four pairs per warp), or the whole warp when a mixture has more than 16 bin groups -- one
-            // L2 latency instead of three for the 65 groups of a 2049-bin mixture; the warps are dealt CTA-first so that
-            // a short list of pairs spreads over all SMs
-            const int lp = L.NG > 16 ? 32 : 8, ppw = 32 / lp;
-            const int sub = lane / lp, cs = lane % lp;
-            const long long w0 = (long long)warp * gridDim.x + blockIdx.x;
-            for (long long q0 = w0 * ppw; q0 < n_pairs; q0 += (long long)gridDim.x * RES_WARPS * ppw) {
-                const long long q = q0 + sub;
-                const bool ok = q < n_pairs;
-                const long long qq = ok ? q : 0;
+            for (long long q = pair_q0 - pair_sub; q < n_pairs; q += pair_step) {  // (whole warps: the shuffles below)
+                const long long qs = q + pair_sub;
+                const bool ok = qs < n_pairs;
+                const long long qq = ok ? qs : 0;
                 const long long pb = qq / ((long long)K * T);
                 const int rem = (int)(qq - pb * K * T);
                 const int k = rem / T, t = rem - k * T;
+                const double* src = p.r2part + ((size_t)pb * L.NG * K + k) * Tp + t;
                 double sum = 0.0;
-                if (ok) {
-                    const double* src = p.r2part + ((size_t)pb * L.NG * K + k) * Tp + t;
+                if (p.tagged) {
+                    constexpr int NV = RES_TAG_MAX_GROUPS / 32;
+                    double v[NV];
+                    unsigned spins = 0;
+                    for (;;) {  // all of the lane's words in flight together, again until each carries this epoch's sign
+                        bool all = true;
+#pragma unroll
+                        for (int j = 0; j < NV; ++j) {
+                            const int ch = pair_cs + j * lp;
+                            if (ok && ch < L.NG) {
+                                v[j] = ld_relaxed_f64(src + (size_t)ch * K * Tp);
+                                all = all && tag_is(v[j], par);
+                            } else {
+                                v[j] = 0.0;
+                            }
+                        }
+                        if (all || stalled) break;
+                        if (++spins > RES_SPIN_LIMIT) stalled = true;
+                    }
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) sum += fabs(v[j]);
+                    __syncwarp();
+                } else if (ok) {
 #pragma unroll 4
-                    for (int ch = cs; ch < L.NG; ch += lp) sum += __ldcg(src + (size_t)ch * K * Tp);
+                    for (int ch = pair_cs; ch < L.NG; ch += lp) sum += __ldcg(src + (size_t)ch * K * Tp);
                 }
                 sum += __shfl_xor_sync(0xffffffffu, sum, 1);
                 sum += __shfl_xor_sync(0xffffffffu, sum, 2);
@@ -352,25 +427,49 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                     sum += __shfl_xor_sync(0xffffffffu, sum, 8);
                     sum += __shfl_xor_sync(0xffffffffu, sum, 16);
                 }
-                if (ok && cs == 0) __stcg(p.rbuf + ((size_t)pb * K + k) * Tp + t, model_fn(sum));
+                if (ok && pair_cs == 0) {
+                    double* dst = p.rbuf + ((size_t)pb * K + k) * Tp + t;
+                    if (p.tagged) st_relaxed_f64(dst, tag_word(model_fn(sum), par));
+                    else __stcg(dst, model_fn(sum));
+                }
             }
             OIVA_RES_STAMP(3);
-            grid_barrier(bar_counter, (++n_bar) * gridDim.x, p.poll);
+            if (!p.tagged) grid_barrier(bar_counter, (++n_bar) * gridDim.x, p.poll);
             OIVA_RES_STAMP(4);
         }
 
         // ---- (3) gamma = mean_t r, phi = 1 / max(r / gamma, 1e-15) for the slice's frames, W scale   overiva.py:158-173
         const double* rglob = p.rbuf + (size_t)b * K * Tp;
-        auto r_at = [&](int k, int t) { return __ldcg(rglob + (size_t)k * Tp + t); };
+        // (tagged words: warp k waits for row k here, everybody else reads it after the CTA barrier below)
+        auto r_at = [&](int k, int t) {
+            return p.tagged ? fabs(ld_relaxed_f64(rglob + (size_t)k * Tp + t)) : __ldcg(rglob + (size_t)k * Tp + t);
+        };
         if (warp < K) {
             double lsum = 0.0;
             for (int tt = 0; tt < Tp; tt += 128) {  // 4 loads in flight, added in ascending order (+0.0 beyond T)
                 double v[4];
+                unsigned spins = 0;
+                for (;;) {
+                    bool all = true;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int t = tt + 32 * j + lane;
-                    v[j] = t < T ? r_at(warp, t) : 0.0;
+                    for (int j = 0; j < 4; ++j) {
+                        const int t = tt + 32 * j + lane;
+                        if (t < T) {
+                            if (p.tagged) {
+                                v[j] = ld_relaxed_f64(rglob + (size_t)warp * Tp + t);
+                                all = all && tag_is(v[j], par);
+                                v[j] = fabs(v[j]);
+                            } else {
+                                v[j] = __ldcg(rglob + (size_t)warp * Tp + t);
+                            }
+                        } else {
+                            v[j] = 0.0;
+                        }
+                    }
+                    if (all || stalled) break;
+                    if (++spins > RES_SPIN_LIMIT) stalled = true;
                 }
+                __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 4; ++j) lsum += v[j];
             }
@@ -527,6 +626,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
         if (p.cluster) cluster_barrier();
         OIVA_RES_STAMP(9);
     }
+    if (stalled) atomicOr(p.status + b, OIVA_STATUS_STALLED);
 }
 
 }  // namespace oiva

@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""A/B of the resident loop's hand-over modes: 20-epoch loop time of the short BASELINE shapes, modes interleaved, median
-of 15; also checks the demixing matrices are bit-identical across modes.  Modes (OIVA_RES_CLUSTER, OIVA_RES_POLL):
-"f0" flag hand-over + acquire polls, "f1" relaxed polls + fence, "f2" relaxed polls + one acquire load, "c2" the slices
-of a bin group as a thread-block cluster (cluster barriers instead of the arrive counter and the flag; every CTA sums the
-statistic of its own frames and the gamma sums meet in the cluster's shared memory: one grid barrier per epoch)."""
+"""A/B of the resident loop's synchronisation modes: 20-epoch loop time of the short BASELINE shapes, modes interleaved,
+median of 15; also checks the demixing matrices are bit-identical across modes.  Modes (OIVA_RES_CLUSTER, OIVA_RES_POLL,
+OIVA_RES_TAGGED): "f0" flag hand-over inside a bin group + acquire polls, "f2" relaxed polls + one acquire load, "c2" the
+slices of a bin group as a thread-block cluster (cluster barriers instead of the arrive counter and the flag), "f2t" /
+"c2t" the same with the statistic words tagged by the epoch's parity in their sign bit instead of two grid barriers per
+epoch."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -18,12 +19,12 @@ for name, (B, T, F, M, K) in SHAPES.items():
     X = stft_domain_batch_torch(B, T, F, M, K, seed=3, device=dev, chunk=1)
     plan = DemixPlan(B, T, F, M, K, L.MODEL_LAPLACE, torch.complex128, dev)
     plan.load(X)
-    MODES = {"f0": ("0", "0"), "f2": ("0", "2"), "c2": ("1", "2")}
+    MODES = {"f0": ("0", "0", "0"), "f2": ("0", "2", "0"), "c2": ("1", "2", "0"), "f2t": ("0", "2", "1"), "c2t": ("1", "2", "1")}
     times = {m: [] for m in MODES}
     Ws = {}
     for rep in range(16):
-        for mode, (cl, po) in MODES.items():
-            os.environ["OIVA_RES_CLUSTER"], os.environ["OIVA_RES_POLL"] = cl, po
+        for mode, (cl, po, ta) in MODES.items():
+            os.environ["OIVA_RES_CLUSTER"], os.environ["OIVA_RES_POLL"], os.environ["OIVA_RES_TAGGED"] = cl, po, ta
             plan.init(L.INIT_EYE); torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); plan.iterate(20); e1.record(); torch.cuda.synchronize()
