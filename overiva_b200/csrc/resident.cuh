@@ -139,6 +139,15 @@ __device__ __forceinline__ bool tag_is(double v, unsigned parity) {
 __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// the complex number at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ cplx ld_dsmem_c(const cplx* local, unsigned rank) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(local);
+    uint32_t ra;
+    cplx v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(ra) : "memory");
+    return v;
+}
 // all CTAs of the (cooperative, co-resident) grid; `target` = gridDim.x * (number of barriers so far).
 // One release-add and an acquire spin by thread 0 between two CTA barriers: the CTA barrier orders the other threads'
 // writes before thread 0's release and thread 0's acquire before their later reads (causality order is cumulative), so
@@ -315,13 +324,23 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
     for (int epoch = 0; epoch < p.n_iter; ++epoch) {
         const unsigned par = (unsigned)epoch & 1u;
         OIVA_RES_STAMP(0);
+        // ---- (0) this epoch's W_hat in shared memory.  In a cluster it never leaves the chip between epochs: the first CTA
+        //      sweeps in place and keeps it, the others copy it out of that CTA's shared memory after the hand-over
+        //      barrier; global memory gets the last epoch's only.
+        const bool w_via_l2 = !p.cluster && p.SG > 1;  // (flag hand-over: the sweeping CTA changes from epoch to epoch)
+        if (w_via_l2 || epoch == 0) {
+            for (uint32_t i = tid; i < (uint32_t)(M * M * OIVA_GROUP); i += RES_THREADS) sW[i] = __ldcg(Wgrp + i);
+        } else if (p.cluster && sl != 0) {
+            for (uint32_t i = tid; i < (uint32_t)(M * M * OIVA_GROUP); i += RES_THREADS) sW[i] = ld_dsmem_c(sW + i, 0u);
+        }
+        __syncthreads();
         // ---- (1) statistic of the slice: r2part[gi][k][t] = sum over the 32 bins |w_k^H x|^2      overiva.py:140,152-155
         {
             cplx w[M][K];
 #pragma unroll
             for (int c = 0; c < M; ++c)
 #pragma unroll
-                for (int k = 0; k < K; ++k) w[c][k] = __ldcg(Wgrp + (size_t)(c * M + k) * OIVA_GROUP + lane);
+                for (int k = 0; k < K; ++k) w[c][k] = sW[(c * M + k) * OIVA_GROUP + lane];
             double* r2g = p.r2part + (size_t)gi * K * Tp;
             for (int blk = warp; blk * POWER_FB < nfr; blk += RES_WARPS) {
                 const int fb = blk * POWER_FB;
@@ -556,8 +575,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                     if (two) out[i2] = acc2;
                 }
             };
-            for (uint32_t i = tid; i < (uint32_t)(M * M * OIVA_GROUP); i += RES_THREADS) sW[i] = __ldcg(Wgrp + i);
-            reduce_source(0, sV, 0, RES_THREADS);
+            reduce_source(0, sV, 0, RES_THREADS);  // (sW holds this epoch's W_hat since phase (0))
             __syncthreads();
             if constexpr (K == M && M >= 3) {
                 // determined case: the in-thread LU of the thread-per-bin sweep is one long dependent chain per source
@@ -613,7 +631,8 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                 }
             }
             __syncthreads();
-            for (uint32_t i = tid; i < (uint32_t)(M * M * OIVA_GROUP); i += RES_THREADS) __stcg(Wgrp + i, sW[i]);
+            if (w_via_l2 || epoch == p.n_iter - 1)
+                for (uint32_t i = tid; i < (uint32_t)(M * M * OIVA_GROUP); i += RES_THREADS) __stcg(Wgrp + i, sW[i]);
             if (!p.cluster) {
                 __syncthreads();
                 if (tid == 0) st_release_u32(flag, (unsigned)(epoch + 1));

@@ -132,6 +132,45 @@ def test_resident_loop_equals_kernel_loop(M, K, model, dtype, n_samples, frame, 
         assert np.array_equal(out["resident"][1], out["resident_again"][1])
 
 
+@pytest.mark.parametrize("M,K,n_samples,frame,nb", [(4, 2, 30000, 512, 1), (6, 6, 20000, 512, 1), (4, 2, 1500, 64, 3)])
+def test_resident_loop_synchronisation_modes_agree(M, K, n_samples, frame, nb, monkeypatch):
+    """The resident loop's hand-over variants -- thread-block clusters or flags in global memory inside a bin group,
+    sign-tagged statistic words or two grid barriers per epoch -- move the same numbers in the same order: bit-identical
+    demixing matrices (the fallbacks stay usable: OIVA_RES_CLUSTER=0, OIVA_RES_TAGGED=0)."""
+    from overiva_b200 import _lib as L
+    from overiva_b200.core import DemixPlan
+
+    X = np.stack([small_test_mixture(70 + b, M, 2, n_samples=n_samples, frame=frame, hop=frame // 2) for b in range(nb)])
+    Xd = torch.from_numpy(X).cuda()
+    B, T, F, _ = X.shape
+    out = {}
+    for cluster in ("1", "0"):
+        for tagged in ("1", "0"):
+            monkeypatch.setenv("OIVA_RES_CLUSTER", cluster)
+            monkeypatch.setenv("OIVA_RES_TAGGED", tagged)
+            plan = DemixPlan(B, T, F, M, K, L.MODEL_LAPLACE, Xd.dtype, Xd.device)
+            plan.load(Xd)
+            plan.init(L.INIT_EYE)
+            l0 = plan.launches
+            plan.iterate(9)  # (odd: the last epoch's parity differs from the first's)
+            assert plan.launches - l0 == 1
+            plan.iterate(4)  # a second launch on the words the first one left behind
+            plan.raise_on_failure()
+            out[cluster, tagged] = plan.filters().cpu().numpy()
+    for key, W in out.items():
+        assert np.array_equal(W, out["1", "1"]), key
+
+
+def test_resident_loop_singular_mixture_does_not_stall():
+    """A rank-deficient mixture fills the statistic with NaNs; the sign-tagged words must still carry the epoch's parity
+    (a NaN that went through an arithmetic instruction comes back as the canonical NaN, sign bit set): LinAlgError like
+    the reference, not a stalled loop."""
+    X = small_test_mixture(81, 4, 2, n_samples=30000, frame=512, hop=256)
+    X[:, :, 3] = X[:, :, 0]
+    with pytest.raises(np.linalg.LinAlgError):
+        ob.overiva(X, n_src=2, n_iter=7)
+
+
 def test_batch_equals_single_and_is_deterministic():
     Xs = np.stack([small_test_mixture(200 + b, 6, 2, n_samples=2000, frame=64, hop=32) for b in range(5)])
     Yb, Wb = ob.overiva_batch(Xs, n_src=2, n_iter=10, return_filters=True)
