@@ -44,7 +44,7 @@ static bool resident_choose(int B, int T, int F, int M, int K, int dtype, int ma
     for (; SG >= 1; --SG) {
         if ((size_t)SG * fw * vg > scratch_bytes) continue;
         const int cap = (T + SG - 1) / SG;
-        for (int vb = (K == M && M >= 3) ? 1 : 2; vb >= 1; --vb) {  // (the determined sweep uses all warps: one V buffer)
+        for (int vb = 2; vb >= 1; --vb) {  // (two V buffers: the next source's partial sums are added during a sweep)
             const ResSmem lay = res_smem_layout(M, K, cap, vb, esz);
             if (lay.total <= RES_MAX_SMEM) {
                 out->SG = SG;

@@ -28,7 +28,7 @@ namespace oiva {
 
 constexpr int RES_WARPS = 8;
 constexpr int RES_THREADS = RES_WARPS * 32;
-constexpr int RES_TRACE_POINTS = 10;  // stamps per CTA and epoch when ResidentParams::trace is set
+constexpr int RES_TRACE_POINTS = 14;  // stamps per CTA and epoch when ResidentParams::trace is set
 constexpr int RES_TAG_MAX_GROUPS = 160;    // bin groups per mixture the tagged statistic sum holds in registers (5 per lane)
 constexpr unsigned RES_SPIN_LIMIT = 1u << 21;  // polls (~1 us each) before a waiter gives up and reports OIVA_STATUS_STALLED
 constexpr int RES_SYNC_HEADER = 8;  // sync[0]: grid-barrier counter; [8 + gi]: arrivals of group gi; [8 + G + gi]: its flag
@@ -577,6 +577,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
             };
             reduce_source(0, sV, 0, RES_THREADS);  // (sW holds this epoch's W_hat since phase (0))
             __syncthreads();
+            OIVA_RES_STAMP(10);
             if constexpr (K == M && M >= 3) {
                 // determined case: the in-thread LU of the thread-per-bin sweep is one long dependent chain per source
                 // (config 2: ~6 us x 6 sources).  Two lanes per bin instead (solve_pair.cuh: half of the rows each in
@@ -592,9 +593,15 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                 const bool pok = g * OIVA_GROUP + pl < L.F;
 #pragma unroll 1
                 for (int s = 0; s < K; ++s) {
-                    if (warp < 2) PairSweep<M, false>::source(WLane{sW + pl}, sV + pl, s, ph, pok, singular);
+                    // (with a second V buffer the six idle warps sum the next source's partial covariances meanwhile:
+                    // config 2 spent 3200 of every 10900 cycles per source in that sum, profiles/r02_res_trace.jsonl)
+                    const cplx* cur = sV + (size_t)(p.v_bufs == 2 ? (s & 1) : 0) * MAT_ELEMS;
+                    if (warp < 2) PairSweep<M, false>::source(WLane{sW + pl}, cur + pl, s, ph, pok, singular);
+                    else if (p.v_bufs == 2 && s + 1 < K)
+                        reduce_source(s + 1, sV + (size_t)((s + 1) & 1) * MAT_ELEMS, 64, RES_THREADS - 64);
                     __syncthreads();
-                    if (s + 1 < K) {
+                    if (s < 3) OIVA_RES_STAMP(11 + s);
+                    if (p.v_bufs == 1 && s + 1 < K) {
                         reduce_source(s + 1, sV, 0, RES_THREADS);
                         __syncthreads();
                     }
@@ -623,6 +630,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                         reduce_source(s + 1, sV, 0, RES_THREADS);
                         __syncthreads();
                     }
+                    if (s < 3) OIVA_RES_STAMP(11 + s);
                 }
                 if (warp == 0 && bin_ok) {
                     const bool bad = ip_sweep_nonfinite<M, K>(Wm);

@@ -27,6 +27,8 @@ for name, (B, T, F, M, K) in SHAPES.items():
     cta, ep, st = a[:, 0], a[:, 1], a[:, 2:]
     grid = int(cta.max()) + 1
     SG = grid // (B * ((F + 31) // 32))
+    sub = st[:, 10:]  # inside phase 5 (owner only): after the sum of source 0 | (determined: W rescale) | source 0 | ...
+    st = st[:, :10]
     d = np.diff(st, axis=1)
     keep = ep >= 5
     out = {"config": name, "grid": grid, "slices_per_group": SG, "unit": "SM cycles (median over CTAs and epochs 5..19)"}
@@ -35,5 +37,11 @@ for name, (B, T, F, M, K) in SHAPES.items():
         if m.any():
             out[who] = {PHASES[j]: float(np.median(d[m, j])) for j in range(len(PHASES))}
             out[who]["epoch"] = float(np.median(st[m, -1] - st[m, 0]))
+            if who == "owner":
+                pts = np.concatenate([st[m, 7:8], sub[m]], axis=1)
+                names = (["sum of source 0", "W rescale + pair sweep of source 0 (|| sum of source 1)", "pair sweep of source 1", "pair sweep of source 2"] if M == K and M >= 3 else
+                         ["sum of source 0", "sweep of source 0 (|| sum of source 1)", "sweep of source 1", "sweep of source 2"])
+                out["inside phase 5"] = {names[j]: float(np.median(pts[:, j + 1] - pts[:, j])) for j in range(4)
+                                         if np.all(pts[:, j + 1] > 0)}
     print(json.dumps(out), flush=True)
     del plan, X
