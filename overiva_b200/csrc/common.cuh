@@ -88,6 +88,21 @@ __device__ __forceinline__ cplx crecip(cplx a) {
     double s = 1.0 / fma(a.x, a.x, a.y * a.y);
     return make_double2(a.x * s, -a.y * s);
 }
+// 1 / x for the pivots of the sweeps: MUFU.RCP64H (23 bits) and two Newton steps, ~70 cycles of dependent latency where
+// the IEEE division is ~200 (reciprocal seed, four refinements, a range check with a slow path); within 1 ulp for normal
+// x.  x = 0 or Inf gives NaN instead of Inf / 0: both only occur behind a pivot test that has already flagged the bin.
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ cplx crecip_fast(cplx a) {
+    const double s = rcp_fast(fma(a.x, a.x, a.y * a.y));
+    return make_double2(a.x * s, -a.y * s);
+}
 // principal square root
 __device__ __forceinline__ cplx csqrt_(cplx a) {
     if (a.y == 0.0) {
@@ -101,6 +116,19 @@ __device__ __forceinline__ cplx csqrt_(cplx a) {
     }
     double im = copysign(sqrt(0.5 * (m - a.x)), a.y);
     return make_double2(a.y / (2.0 * im), im);
+}
+// 1 / sqrt(d), principal branch, for the normalisation w^H V w of the sweeps (overiva.py:185-186): V is positive definite,
+// so Re d > 0 and Im d is rounding noise.  sqrt(d) = (re, Im d / (2 re)) with re^2 = (|d| + Re d) / 2, and
+// 1 / sqrt(d) = conj(sqrt(d)) / |d|: two rsqrt and a few multiplications (~220 cycles of latency) where hypot, two square
+// roots and a division are ~700.  Anything else (Re d <= 0, NaN, squares out of range) takes the general formula.
+__device__ __forceinline__ cplx crsqrt_pos(cplx d) {
+    const double n2 = fma(d.x, d.x, d.y * d.y);
+    if (!(d.x > 0.0) || !(n2 < 1e300) || !(n2 > 1e-300)) return crecip(csqrt_(d));
+    const double rinv = rsqrt(n2);     // 1 / |d|
+    const double t = 0.5 * fma(n2, rinv, d.x);  // re^2
+    const double tinv = rsqrt(t);      // 1 / re
+    const double re = t * tinv, im = 0.5 * d.y * tinv;
+    return make_double2(re * rinv, -im * rinv);
 }
 
 __device__ __forceinline__ cplx shfl_c(cplx v, int src) {

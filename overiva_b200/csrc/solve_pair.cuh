@@ -98,7 +98,11 @@ struct PairSweep {
                 }
                 cand[N] = v;
             }
-            const cplx inv = crecip(cand[c]);
+            // (the fast reciprocal only on shared memory: in the batched kernel, at the register limit with M = 8, it
+            // lets ptxas overlap the pivots and spill 2 KB per thread -- sweep 3.2 -> 4.6 ms per 256 mixtures)
+            cplx inv;
+            if constexpr (NC) inv = crecip(cand[c]);
+            else inv = crecip_fast(cand[c]);
 #pragma unroll
             for (int col = c + 1; col <= N; ++col) cand[col] = cmul(cand[col], inv);
             // the winner's row reaches both lanes
@@ -151,7 +155,7 @@ struct PairSweep {
         }
         const cplx dother = shfl_xor_c(dpart, 16);
         const cplx d = h == 0 ? cadd(dpart, dother) : cadd(dother, dpart);  // (first half of the rows) + (second half)
-        const cplx inv = crecip(csqrt_(d));
+        const cplx inv = crsqrt_pos(d);
         __syncwarp();  // (every lane has read the un-normalised column before anybody overwrites it)
         if (ok) {
 #pragma unroll

@@ -78,7 +78,7 @@ __device__ __forceinline__ void lu_solve(cplx (&A)[N][N], cplx (&rhs)[N][NR], bo
 #pragma unroll
             for (int q = 0; q < NR; ++q) cswap_if(sw, rhs[c][q], rhs[r][q]);
         }
-        const cplx rinv = crecip(A[c][c]);
+        const cplx rinv = crecip_fast(A[c][c]);
         // normalise the pivot row (U gets a unit diagonal), eliminate below
 #pragma unroll
         for (int c2 = c + 1; c2 < N; ++c2) A[c][c2] = cmul(A[c][c2], rinv);
@@ -188,7 +188,7 @@ __device__ __forceinline__ void ip_source_full_v(WLane Wm, const VGet& vget, int
         for (int j = 0; j < M; ++j) cfma(u, vget(i, j), rhs[j][0]);
         cfmac(d, rhs[i][0], u);
     }
-    const cplx inv = crecip(csqrt_(d));
+    const cplx inv = crsqrt_pos(d);
 #pragma unroll
     for (int i = 0; i < M; ++i) Wm[i * M + s] = cmul(rhs[i][0], inv);
 }
