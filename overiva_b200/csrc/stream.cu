@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(256) k_source_model(const double* __restrict__
         const int t = t0 + tl;  // Tp is a multiple of 32
         double s = 0.0;
         if (t < T) {
-#pragma unroll 4
-            for (int ch = cs; ch < NCH; ch += 8) s += pb[(size_t)ch * K * Tp + t];
+#pragma unroll 16
+            for (int ch = cs; ch < NCH; ch += 8) s += pb[(size_t)ch * K * Tp + t];  // (one batch of loads for 65 groups)
         }
         slice[cs][tl] = s;
         __syncthreads();
@@ -198,35 +198,47 @@ __global__ void __launch_bounds__(256) k_source_r(const double* __restrict__ par
     if (is_last) source_finish_body(ph, wscale, b, k, T, Tp, K, model, red);
 }
 
-// projection-back scales from the grouped state, any M (runtime loops; thread per bin): z[gi][k][lane] with exactly the
-// arithmetic of k_projback_filters (solve.cu)
+// projection-back scales from the grouped state, any M: z[gi][k][lane] with exactly the arithmetic of k_projback_filters
+// (solve.cu).  One thread per (bin, source) -- blockIdx.y = k; the source's column of W_hat and one row of C at a time in
+// registers, all of a row's loads in flight together.  (The first version walked a, b with one dependent load per step: 25 us
+// for the 2049 bins of config 3, a quarter of its output step.)
 __global__ void __launch_bounds__(128) k_projback_z(const cplx* __restrict__ Wg, const cplx* __restrict__ Cg,
                                                     cplx* __restrict__ Zg, long long G, int M, int K) {
     const int lane = threadIdx.x & 31;
     const long long gi = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int k = blockIdx.y;
     if (gi >= G) return;
     const cplx* Wl = Wg + (size_t)gi * M * M * OIVA_GROUP + lane;
     const cplx* Cl = Cg + (size_t)gi * (M * (M + 1) / 2) * OIVA_GROUP + lane;
-    auto Cat = [&](int a, int b) {
-        const int hi = a >= b ? a : b, lo = a >= b ? b : a;
-        cplx v = ld_nc_c(Cl + (size_t)(hi * (hi + 1) / 2 + lo) * OIVA_GROUP);
-        if (a < b) v.y = -v.y;
-        return v;
-    };
-    for (int k = 0; k < K; ++k) {
-        cplx num = cmake(0.0, 0.0);
-        double den = 0.0;
-        for (int a = 0; a < M; ++a) {
-            const cplx wa = Wl[(size_t)(a * M + k) * OIVA_GROUP];
-            cfmac(num, wa, Cat(a, 0));
-            cplx cw = cmake(0.0, 0.0);
-            for (int b = 0; b < M; ++b) cfma(cw, Cat(a, b), Wl[(size_t)(b * M + k) * OIVA_GROUP]);
-            den += wa.x * cw.x + wa.y * cw.y;
+    cplx wk[OIVA_MAX_M];
+#pragma unroll
+    for (int b = 0; b < OIVA_MAX_M; ++b) wk[b] = b < M ? Wl[(size_t)(b * M + k) * OIVA_GROUP] : cmake(0.0, 0.0);
+    cplx num = cmake(0.0, 0.0);
+    double den = 0.0;
+    for (int a = 0; a < M; ++a) {
+        cplx crow[OIVA_MAX_M];  // C[a][b]
+#pragma unroll
+        for (int b = 0; b < OIVA_MAX_M; ++b) {
+            if (b < M) {
+                const int hi = a >= b ? a : b, lo = a >= b ? b : a;
+                cplx v = ld_nc_c(Cl + (size_t)(hi * (hi + 1) / 2 + lo) * OIVA_GROUP);
+                if (a < b) v.y = -v.y;
+                crow[b] = v;
+            } else {
+                crow[b] = cmake(0.0, 0.0);
+            }
         }
-        cplx z = cmake(1.0, 0.0);
-        if (den > 0.0) z = cmake(num.x / den, num.y / den);
-        Zg[((size_t)gi * K + k) * OIVA_GROUP + lane] = z;
+        const cplx wa = Wl[(size_t)(a * M + k) * OIVA_GROUP];
+        cfmac(num, wa, crow[0]);
+        cplx cw = cmake(0.0, 0.0);
+#pragma unroll
+        for (int b = 0; b < OIVA_MAX_M; ++b)
+            if (b < M) cfma(cw, crow[b], wk[b]);
+        den += wa.x * cw.x + wa.y * cw.y;
     }
+    cplx z = cmake(1.0, 0.0);
+    if (den > 0.0) z = cmake(num.x / den, num.y / den);
+    Zg[((size_t)gi * K + k) * OIVA_GROUP + lane] = z;
 }
 
 }  // namespace oiva
@@ -354,7 +366,7 @@ extern "C" int oiva_demix_output_grouped(const void* Xg, const void* Wg, const v
     if (Cg) {  // the scales in a small kernel of their own (thread per bin on the grouped arrays)
         OIVA_REQUIRE(zscratch, "oiva_demix_output_grouped: projection back needs zscratch");
         const long long G = (long long)n_batch * p.L.NG;
-        k_projback_z<<<(unsigned)((G + 3) / 4), 128, 0, (cudaStream_t)stream>>>((const cplx*)Wg, (const cplx*)Cg,
+        k_projback_z<<<dim3((unsigned)((G + 3) / 4), (unsigned)n_src), 128, 0, (cudaStream_t)stream>>>((const cplx*)Wg, (const cplx*)Cg,
                                                                                   (cplx*)zscratch, G, n_chan, n_src);
         OIVA_LAUNCH_CHECK();
         p.Zg = (const cplx*)zscratch;
