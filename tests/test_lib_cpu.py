@@ -141,3 +141,30 @@ def test_host_pipeline_chunk_schedule():
             assert sum(s) == B and all(0 < n <= chunk for n in s), (B, chunk, s)
     assert _chunk_schedule(512, 32)[:5] == [4, 4, 8, 16, 32] and _chunk_schedule(512, 32)[-4:] == [16, 8, 4, 4]
     assert _chunk_schedule(100, 32) == [32, 32, 32, 4]  # short batches: plain chunks
+
+
+def test_status_words_map_to_the_reference_error_behaviour():
+    """Host logic of the per-mixture status words: singular -> LinAlgError (np.linalg.solve in overiva.py:98,182),
+    non-finite alone -> a RuntimeWarning and NaN results like the reference, a stalled single-launch loop or a corrupt
+    word -> RuntimeError."""
+    import warnings
+
+    from overiva_b200.core import raise_for_status
+
+    raise_for_status(np.zeros(4, dtype=np.int32))
+    with pytest.raises(np.linalg.LinAlgError, match="Singular matrix"):
+        raise_for_status(np.array([L.STATUS_SINGULAR], dtype=np.int32))
+    with pytest.raises(np.linalg.LinAlgError, match="mixture 2 of 3"):
+        raise_for_status(np.array([0, L.STATUS_NONFINITE, L.STATUS_SINGULAR | L.STATUS_NONFINITE], dtype=np.int32))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        raise_for_status(np.array([0, L.STATUS_NONFINITE], dtype=np.int32))
+    assert len(w) == 1 and issubclass(w[0].category, RuntimeWarning)
+    with pytest.raises(RuntimeError, match="stalled"):
+        raise_for_status(np.array([0, L.STATUS_STALLED | L.STATUS_SINGULAR], dtype=np.int32))
+    with pytest.raises(RuntimeError, match="corrupt"):
+        raise_for_status(np.array([8], dtype=np.int32))
+    src = open(HEADER).read()
+    for name, val in (("OIVA_STATUS_SINGULAR", L.STATUS_SINGULAR), ("OIVA_STATUS_NONFINITE", L.STATUS_NONFINITE),
+                      ("OIVA_STATUS_STALLED", L.STATUS_STALLED)):
+        assert re.search(r"#define %s %d\b" % (name, val), src), name
