@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(256) k_source_model(const double* __restrict__
         const int t = t0 + tl;  // Tp is a multiple of 32
         double s = 0.0;
         if (t < T) {
-#pragma unroll 16
-            for (int ch = cs; ch < NCH; ch += 8) s += pb[(size_t)ch * K * Tp + t];  // (one batch of loads for 65 groups)
+#pragma unroll 4
+            for (int ch = cs; ch < NCH; ch += 8) s += pb[(size_t)ch * K * Tp + t];
         }
         slice[cs][tl] = s;
         __syncthreads();
