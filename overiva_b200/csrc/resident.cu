@@ -108,6 +108,8 @@ extern "C" int oiva_loop_resident(const void* Xg, void* Wg, const void* Cg, doub
     {
         const char* v = getenv("OIVA_RES_POLL");  // (read per call: profiles compare the modes in one process)
         p.poll = v ? atoi(v) : 2;
+        v = getenv("OIVA_RES_TRACKED");
+        p.tracked = v ? atoi(v) : 1;
         v = getenv("OIVA_RES_TAGGED");
         p.tagged = (v ? atoi(v) : 1) && p.L.NG <= RES_TAG_MAX_GROUPS;
         v = getenv("OIVA_RES_CLUSTER");

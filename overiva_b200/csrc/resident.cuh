@@ -49,6 +49,7 @@ struct ResidentParams {
     int v_bufs;       // 1 or 2 shared-memory buffers for the reduced V_s
     int cluster;      // 1: the SG CTAs of a bin group form a thread-block cluster and hand over through cluster barriers
     long long* trace; // null, or (grid, n_iter, RES_TRACE_POINTS) clock64 stamps of thread 0 (OIVA_RES_TRACE, profiling only)
+    int tracked;      // 1: determined sweep with the inverse of W_hat carried along (one Cholesky per source, no LU)
     int tagged;       // 1: no grid barrier inside the epoch -- the statistic words carry the epoch's parity in their sign bit
     int poll;         // how waiters spin: 0 acquire loads, 1 relaxed loads + one fence, 2 relaxed loads + one acquire load
     double invT;
@@ -133,6 +134,9 @@ __device__ __forceinline__ double tag_word(double v, unsigned parity) {
 }
 __device__ __forceinline__ bool tag_is(double v, unsigned parity) {
     return ((unsigned)__double2hiint(v) >> 31) == parity;
+}
+__device__ __forceinline__ void named_barrier(int id, int n_threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 // all threads of the cluster; release/acquire at cluster scope orders the partial sums and W (st.cg / ld.cg, L2) between
 // the CTAs of a bin group without a round trip through a flag in global memory
@@ -245,8 +249,9 @@ __host__ __device__ inline ResSmem res_smem_layout(int M, int K, int slice_cap, 
 }
 
 // grid = G * SG CTAs of 256 threads (cooperative launch); CTA c owns slice s = c % SG of bin group gi = c / SG
-template <typename ST, int M, int K>
+template <typename ST, int M, int K, bool TRACKED = false>
 __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const ResidentParams p) {
+    static_assert(!TRACKED || (K == M && M >= 3), "the tracked-inverse sweep is the determined one");
     typedef typename StoreC<ST>::type XC;
     typedef ResCfg<M, K> RC;
     constexpr int NE = RC::NE;
@@ -575,8 +580,10 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                     if (two) out[i2] = acc2;
                 }
             };
-            reduce_source(0, sV, 0, RES_THREADS);  // (sW holds this epoch's W_hat since phase (0))
-            __syncthreads();
+            if constexpr (!TRACKED) {
+                reduce_source(0, sV, 0, RES_THREADS);  // (sW holds this epoch's W_hat since phase (0))
+                __syncthreads();
+            }
             OIVA_RES_STAMP(10);
             if constexpr (K == M && M >= 3) {
                 // determined case: the in-thread LU of the thread-per-bin sweep is one long dependent chain per source
@@ -586,11 +593,116 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                 // per 20 epochs: fewer shuffles per pivot, three times the row-building work per lane -- and kept because
                 // it shares its code with the batched kernel.)
                 for (uint32_t i = tid; i < (uint32_t)(M * M * OIVA_GROUP); i += RES_THREADS)  // W *= wscale   overiva.py:161-167
-                    sW[i] = cscale(sW[i], sWs[(i / OIVA_GROUP) % M]);
+                    if (g * OIVA_GROUP + (int)(i % OIVA_GROUP) < L.F)  // (padded bins keep their W: nothing renormalises it)
+                        sW[i] = cscale(sW[i], sWs[(i / OIVA_GROUP) % M]);
                 __syncthreads();
                 bool singular = false;
                 const int pl = (warp & 1) * 16 + (lane & 15), ph = lane >> 4;  // (warps 0, 1: bin and row half)
                 const bool pok = g * OIVA_GROUP + pl < L.F;
+                if constexpr (TRACKED) {
+                    // w_s = (W^H V_s)^-1 e_s = V_s^-1 (W^-H e_s): W^-H e_s is the conjugate of row s of A = W^-1, and
+                    // A follows the new column s of W by a rank-one update (A u = A w - e_s since A W = I):
+                    //   v = A w,  A[s] /= v_s,  A[i] -= v_i A[s]  (i != s).
+                    // So a source costs one Cholesky of V_s and O(M^2) instead of forming W^H V_s and an LU with
+                    // pivoting; A is recomputed from W at the start of every epoch's sweep (no drift beyond M updates).
+                    // Warp 1 keeps A in registers, warp 0 factors V_s while warp 1 is still updating A for the previous
+                    // source; they exchange q and w through the (otherwise unused) shared-memory copy of C.
+                    // (Each role runs its own copy of the source loop -- in one loop the allocator kept warp 1's A alive
+                    // across warp 0's Cholesky and spilled 1.7 KB per thread; the roles meet at barrier 3, all 256 threads,
+                    // once per source.  Needs both V buffers: the launcher falls back to the pair sweep otherwise.)
+                    cplx* mail = sC;  // [2 M][32]: q, then w
+                    if (warp == 1) {
+                        cplx Ainv[M][M];
+#pragma unroll
+                        for (int j = 0; j < M; ++j)
+#pragma unroll
+                            for (int k = 0; k < M; ++k) Ainv[j][k] = sW[(j * M + k) * OIVA_GROUP + lane];
+                        invert_inplace<M>(Ainv, singular);  // (while warps 2-7 add the partial sums of source 0)
+                        named_barrier(3, RES_THREADS);
+#pragma unroll 1
+                        for (int s = 0; s < K; ++s) {
+#pragma unroll
+                            for (int j = 0; j < M; ++j) {  // q = conj(A[s][:])
+                                cplx a = Ainv[0][j];
+#pragma unroll
+                                for (int i = 1; i < M; ++i) {
+                                    a.x = s == i ? Ainv[i][j].x : a.x;
+                                    a.y = s == i ? Ainv[i][j].y : a.y;
+                                }
+                                mail[j * OIVA_GROUP + lane] = cconj(a);
+                            }
+                            named_barrier(1, 64);
+                            named_barrier(2, 64);
+                            cplx v[M];  // v = A w (w read from the mailbox one component at a time)
+#pragma unroll
+                            for (int i = 0; i < M; ++i) v[i] = cmake(0.0, 0.0);
+#pragma unroll
+                            for (int j = 0; j < M; ++j) {
+                                const cplx wj = mail[(M + j) * OIVA_GROUP + lane];
+#pragma unroll
+                                for (int i = 0; i < M; ++i) cfma(v[i], Ainv[i][j], wj);
+                            }
+                            cplx vs = v[0];
+#pragma unroll
+                            for (int i = 1; i < M; ++i) {
+                                vs.x = s == i ? v[i].x : vs.x;
+                                vs.y = s == i ? v[i].y : vs.y;
+                            }
+                            if (!(fabs(vs.x) + fabs(vs.y) > 0.0)) singular = true;
+                            const cplx vinv = crecip_fast(vs);
+#pragma unroll
+                            for (int j = 0; j < M; ++j) {  // column j of A: A[s][j] /= v_s, A[i][j] -= v_i A[s][j]
+                                cplx a = Ainv[0][j];
+#pragma unroll
+                                for (int i = 1; i < M; ++i) {
+                                    a.x = s == i ? Ainv[i][j].x : a.x;
+                                    a.y = s == i ? Ainv[i][j].y : a.y;
+                                }
+                                const cplx asj = cmul(a, vinv);
+#pragma unroll
+                                for (int i = 0; i < M; ++i) {
+                                    cplx t = Ainv[i][j];
+                                    cfms(t, v[i], asj);
+                                    Ainv[i][j].x = s == i ? asj.x : t.x;
+                                    Ainv[i][j].y = s == i ? asj.y : t.y;
+                                }
+                            }
+                            named_barrier(3, RES_THREADS);
+                        }
+                    } else if (warp == 0) {
+                        named_barrier(3, RES_THREADS);
+#pragma unroll 1
+                        for (int s = 0; s < K; ++s) {
+                            const cplx* cur = sV + (size_t)(s & 1) * MAT_ELEMS;
+                            cplx Lm[NE];
+#pragma unroll
+                            for (int e = 0; e < NE; ++e) Lm[e] = cur[e * OIVA_GROUP + lane];
+                            double dinv[M];
+                            chol_factor<M>(Lm, dinv, singular);
+                            named_barrier(1, 64);
+                            cplx q[M];
+#pragma unroll
+                            for (int j = 0; j < M; ++j) q[j] = mail[j * OIVA_GROUP + lane];
+                            chol_solve_normalise<M>(Lm, dinv, q);
+#pragma unroll
+                            for (int j = 0; j < M; ++j) {
+                                if (bin_ok) sW[(j * M + s) * OIVA_GROUP + lane] = q[j];
+                                mail[(M + j) * OIVA_GROUP + lane] = q[j];
+                            }
+                            named_barrier(2, 64);
+                            named_barrier(3, RES_THREADS);
+                        }
+                    } else {
+                        reduce_source(0, sV, 64, RES_THREADS - 64);
+                        named_barrier(3, RES_THREADS);
+#pragma unroll 1
+                        for (int s = 0; s < K; ++s) {
+                            if (s + 1 < K) reduce_source(s + 1, sV + (size_t)((s + 1) & 1) * MAT_ELEMS, 64, RES_THREADS - 64);
+                            named_barrier(3, RES_THREADS);
+                        }
+                    }
+                    if (warp < 2 && singular && bin_ok) atomicOr(p.status + b, OIVA_STATUS_SINGULAR);
+                } else {
 #pragma unroll 1
                 for (int s = 0; s < K; ++s) {
                     // (with a second V buffer the six idle warps sum the next source's partial covariances meanwhile:
@@ -607,6 +719,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                     }
                 }
                 if (warp < 2 && singular && pok) atomicOr(p.status + b, OIVA_STATUS_SINGULAR);
+                }
                 bool bad = false;
                 for (uint32_t i = tid; i < (uint32_t)(M * M * OIVA_GROUP); i += RES_THREADS)
                     if (g * OIVA_GROUP + (int)(i % OIVA_GROUP) < L.F && (!isfinite(sW[i].x) || !isfinite(sW[i].y))) bad = true;

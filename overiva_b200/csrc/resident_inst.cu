@@ -18,8 +18,15 @@ static int launch_res(const ResidentParams& p, unsigned grid, size_t smem, cudaS
     if constexpr (K > M || (M >= 7 && K > 4)) {
         return OIVA_ERR_UNSUPPORTED;
     } else {
-        auto kern = k_loop_resident<ST, M, K>;
-        OIVA_SET_MAX_SMEM_ONCE(kern, 232448);
+        // (the tracked-inverse determined sweep is a kernel of its own: inside the one kernel its registers spilled and
+        // slowed the other phases -- config 2 loop 1.12 -> 1.23 ms with the switch off)
+        constexpr bool CAN_TRACK = K == M && M >= 3;
+        auto kern = k_loop_resident<ST, M, K, false>;
+        if constexpr (CAN_TRACK) {
+            if (p.tracked && p.v_bufs == 2) kern = k_loop_resident<ST, M, K, true>;
+        }
+        // (two kernels share this call site: set the attribute per launch -- it is cheap -- instead of once per device)
+        OIVA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         int dev = 0, sms = 0, occ = 0;
         OIVA_CUDA_CHECK(cudaGetDevice(&dev));
         OIVA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

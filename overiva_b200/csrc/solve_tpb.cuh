@@ -197,6 +197,130 @@ __device__ __forceinline__ void ip_source_full(WLane Wm, const cplx* sV, int s, 
     ip_source_full_v<M>(Wm, HermFromMemory<NC>{sV}, s, singular);
 }
 
+// ---- Cholesky pieces shared by the overdetermined update and the tracked-inverse determined sweep ----------------
+// V = L L^H in place on the packed lower triangle (row-major, e = i(i+1)/2 + j); dinv[j] = 1 / L[j][j].  (static_for: the
+// triple loop must be unrolled completely so that Lm is indexed with constants and stays in registers -- with
+// "#pragma unroll" alone ptxas kept a 336-byte local-memory copy of it at M = 6)
+template <int M>
+__device__ __forceinline__ void chol_factor(cplx (&Lm)[oiva_tri(M)], double (&dinv)[M], bool& singular) {
+    static_for<M>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        double djj = Lm[j * (j + 1) / 2 + j].x;
+        static_for<j>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            const cplx l = Lm[j * (j + 1) / 2 + k];
+            djj = fma(-l.x, l.x, fma(-l.y, l.y, djj));
+        });
+        if (!(djj > 0.0)) singular = true;  // not positive definite (or NaN)
+        dinv[j] = rsqrt(djj);  // 1 / L[j][j]: one MUFU.RSQ64H + 4 fp64 operations where sqrt and a division are ~3x that,
+                               // on the critical path of every pivot (1 ulp, like the two roundings it replaces)
+        static_for<M - 1 - j>([&](auto ic) {
+            constexpr int i = j + 1 + decltype(ic)::value;
+            cplx v = Lm[i * (i + 1) / 2 + j];
+            static_for<j>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                // v -= L[i][k] conj(L[j][k])
+                const cplx a = Lm[i * (i + 1) / 2 + k], bb = Lm[j * (j + 1) / 2 + k];
+                v.x = fma(-a.x, bb.x, fma(-a.y, bb.y, v.x));
+                v.y = fma(-a.y, bb.x, fma(a.x, bb.y, v.y));
+            });
+            Lm[i * (i + 1) / 2 + j] = cscale(v, dinv[j]);
+        });
+    });
+}
+// q <- V^-1 q / sqrt(q^H V^-1 q) from the factor: L y = q, |y|^2 (= w^H V w, real: overiva.py:185-186), L^H w = y
+template <int M>
+__device__ __forceinline__ void chol_solve_normalise(const cplx (&Lm)[oiva_tri(M)], const double (&dinv)[M], cplx (&q)[M]) {
+    static_for<M>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        cplx v = q[i];
+        static_for<i>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            cfms(v, Lm[i * (i + 1) / 2 + k], q[k]);
+        });
+        q[i] = cscale(v, dinv[i]);
+    });
+    // normalisation: w^H V w = w^H L L^H w = |L^H w|^2 = |y|^2 -- available before the back substitution
+    double den = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) den = fma(q[i].x, q[i].x, fma(q[i].y, q[i].y, den));
+    static_for<M>([&](auto iic) {
+        constexpr int i = M - 1 - decltype(iic)::value;
+        cplx v = q[i];
+        static_for<M - 1 - i>([&](auto kc) {
+            constexpr int k = i + 1 + decltype(kc)::value;
+            cfms_conj(v, Lm[k * (k + 1) / 2 + i], q[k]);  // L^H[i][k] = conj(L[k][i])
+        });
+        q[i] = cscale(v, dinv[i]);
+    });
+    const double inv = rsqrt(den);
+#pragma unroll
+    for (int i = 0; i < M; ++i) q[i] = cscale(q[i], inv);
+}
+
+// A <- A^-1 in place (registers): Gauss-Jordan with partial pivoting (zgetrf's rule: largest |re| + |im| in the column, the
+// lower row wins a tie), the row swaps undone on the columns at the end.  For the tracked-inverse determined sweep below.
+template <int M>
+__device__ __forceinline__ void invert_inplace(cplx (&A)[M][M], bool& singular) {
+    int perm[M];
+    static_for<M>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        double best = fabs(A[c][c].x) + fabs(A[c][c].y);
+        int p = c;
+        static_for<M - 1 - c>([&](auto ic) {
+            constexpr int i = c + 1 + decltype(ic)::value;
+            const double m = fabs(A[i][c].x) + fabs(A[i][c].y);
+            if (m > best) {
+                best = m;
+                p = i;
+            }
+        });
+        if (!(best > 0.0)) singular = true;
+        perm[c] = p;
+        static_for<M - 1 - c>([&](auto ic) {  // rows c <-> p
+            constexpr int i = c + 1 + decltype(ic)::value;
+            const bool sw = p == i;
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                const cplx t = A[i][j], u = A[c][j];
+                A[i][j].x = sw ? u.x : t.x;
+                A[i][j].y = sw ? u.y : t.y;
+                A[c][j].x = sw ? t.x : u.x;
+                A[c][j].y = sw ? t.y : u.y;
+            }
+        });
+        const cplx piv = crecip_fast(A[c][c]);
+        A[c][c] = cmake(1.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < M; ++j) A[c][j] = cmul(A[c][j], piv);
+        static_for<M>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            if constexpr (i != c) {
+                const cplx f = A[i][c];
+                A[i][c] = cmake(0.0, 0.0);
+#pragma unroll
+                for (int j = 0; j < M; ++j) cfms(A[i][j], f, A[c][j]);
+            }
+        });
+    });
+    static_for<M>([&](auto cc) {  // (P W)^-1 = W^-1 P^T: the swaps on the columns, last one first
+        constexpr int c = M - 1 - decltype(cc)::value;
+        const int p = perm[c];
+        static_for<M - 1 - c>([&](auto jc) {
+            constexpr int j = c + 1 + decltype(jc)::value;
+            const bool sw = p == j;
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                const cplx t = A[i][j], u = A[i][c];
+                A[i][j].x = sw ? u.x : t.x;
+                A[i][j].y = sw ? u.y : t.y;
+                A[i][c].x = sw ? t.x : u.x;
+                A[i][c].y = sw ? t.y : u.y;
+            }
+        });
+    });
+}
+
 // ---- one IP update, overdetermined case (K < M) ------------------------------------------------------------
 // (W_hat^H V)^-1 e_s = V^-1 q with q = W_hat^-H e_s.  Because W_hat = [W | (J; -I)], q follows from a K x K
 // system:  q1 = (W1^H + W2^H J^H)^-1 e_s,  q2 = J^H q1   (W1 / W2: top K / bottom M-K rows of W);  then V w = q is
@@ -238,61 +362,11 @@ __device__ __forceinline__ void ip_source_reduced_tri(WLane Wm, cplx (&Lm)[oiva_
             q[K + r] = acc;
         }
     }
-    // Cholesky V = L L^H in place on the lower triangle.  (static_for: the triple loop must be unrolled completely so
-    // that Lm is indexed with constants and stays in registers -- with "#pragma unroll" alone ptxas kept a 336-byte
-    // local-memory copy of it at M = 6)
     double dinv[M];
-    static_for<M>([&](auto jc) {
-        constexpr int j = decltype(jc)::value;
-        double djj = Lm[j * (j + 1) / 2 + j].x;
-        static_for<j>([&](auto kc) {
-            constexpr int k = decltype(kc)::value;
-            const cplx l = Lm[j * (j + 1) / 2 + k];
-            djj = fma(-l.x, l.x, fma(-l.y, l.y, djj));
-        });
-        if (!(djj > 0.0)) singular = true;  // not positive definite (or NaN)
-        dinv[j] = rsqrt(djj);  // 1 / L[j][j]: one MUFU.RSQ64H + 4 fp64 operations where sqrt and a division are ~3x that,
-                               // on the critical path of every pivot (1 ulp, like the two roundings it replaces)
-        static_for<M - 1 - j>([&](auto ic) {
-            constexpr int i = j + 1 + decltype(ic)::value;
-            cplx v = Lm[i * (i + 1) / 2 + j];
-            static_for<j>([&](auto kc) {
-                constexpr int k = decltype(kc)::value;
-                // v -= L[i][k] conj(L[j][k])
-                const cplx a = Lm[i * (i + 1) / 2 + k], bb = Lm[j * (j + 1) / 2 + k];
-                v.x = fma(-a.x, bb.x, fma(-a.y, bb.y, v.x));
-                v.y = fma(-a.y, bb.x, fma(a.x, bb.y, v.y));
-            });
-            Lm[i * (i + 1) / 2 + j] = cscale(v, dinv[j]);
-        });
-    });
-    // forward: L y = q
-    static_for<M>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        cplx v = q[i];
-        static_for<i>([&](auto kc) {
-            constexpr int k = decltype(kc)::value;
-            cfms(v, Lm[i * (i + 1) / 2 + k], q[k]);
-        });
-        q[i] = cscale(v, dinv[i]);
-    });
-    // normalisation: w^H V w = w^H L L^H w = |L^H w|^2 = |y|^2 -- available before the back substitution
-    double den = 0.0;
+    chol_factor<M>(Lm, dinv, singular);
+    chol_solve_normalise<M>(Lm, dinv, q);
 #pragma unroll
-    for (int i = 0; i < M; ++i) den = fma(q[i].x, q[i].x, fma(q[i].y, q[i].y, den));
-    // backward: L^H w = y
-    static_for<M>([&](auto iic) {
-        constexpr int i = M - 1 - decltype(iic)::value;
-        cplx v = q[i];
-        static_for<M - 1 - i>([&](auto kc) {
-            constexpr int k = i + 1 + decltype(kc)::value;
-            cfms_conj(v, Lm[k * (k + 1) / 2 + i], q[k]);  // L^H[i][k] = conj(L[k][i])
-        });
-        q[i] = cscale(v, dinv[i]);
-    });
-    const double inv = rsqrt(den);  // w^H V_s w = |y|^2 is real positive                      overiva.py:185-186
-#pragma unroll
-    for (int i = 0; i < M; ++i) Wm[i * M + s] = cscale(q[i], inv);
+    for (int i = 0; i < M; ++i) Wm[i * M + s] = q[i];
 }
 template <int M, int K, bool NC = true>
 __device__ __forceinline__ void ip_source_reduced(WLane Wm, const cplx* sV, int s, bool& singular) {

@@ -4,7 +4,7 @@ median of 15; also checks the demixing matrices are bit-identical across modes. 
 OIVA_RES_TAGGED): "f0" flag hand-over inside a bin group + acquire polls, "f2" relaxed polls + one acquire load, "c2" the
 slices of a bin group as a thread-block cluster (cluster barriers instead of the arrive counter and the flag), "f2t" /
 "c2t" the same with the statistic words tagged by the epoch's parity in their sign bit instead of two grid barriers per
-epoch."""
+epoch, "c2t+inv" with the tracked-inverse determined sweep (OIVA_RES_TRACKED; not bit-identical: another factorisation)."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -19,12 +19,14 @@ for name, (B, T, F, M, K) in SHAPES.items():
     X = stft_domain_batch_torch(B, T, F, M, K, seed=3, device=dev, chunk=1)
     plan = DemixPlan(B, T, F, M, K, L.MODEL_LAPLACE, torch.complex128, dev)
     plan.load(X)
-    MODES = {"f0": ("0", "0", "0"), "f2": ("0", "2", "0"), "c2": ("1", "2", "0"), "f2t": ("0", "2", "1"), "c2t": ("1", "2", "1")}
+    MODES = {"f0": ("0", "0", "0", "0"), "c2": ("1", "2", "0", "0"), "f2t": ("0", "2", "1", "0"), "c2t": ("1", "2", "1", "0"),
+             "c2t+inv": ("1", "2", "1", "1")}
     times = {m: [] for m in MODES}
     Ws = {}
     for rep in range(16):
-        for mode, (cl, po, ta) in MODES.items():
+        for mode, (cl, po, ta, tr) in MODES.items():
             os.environ["OIVA_RES_CLUSTER"], os.environ["OIVA_RES_POLL"], os.environ["OIVA_RES_TAGGED"] = cl, po, ta
+            os.environ["OIVA_RES_TRACKED"] = tr
             plan.init(L.INIT_EYE); torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); plan.iterate(20); e1.record(); torch.cuda.synchronize()

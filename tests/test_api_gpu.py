@@ -161,6 +161,26 @@ def test_resident_loop_synchronisation_modes_agree(M, K, n_samples, frame, nb, m
         assert np.array_equal(W, out["1", "1"]), key
 
 
+@pytest.mark.parametrize("M,n_samples,frame", [(6, 20000, 512), (4, 30000, 512), (3, 9000, 128), (5, 12000, 256)])
+def test_resident_loop_tracked_inverse_sweep(M, n_samples, frame, monkeypatch):
+    """Determined shapes in the resident loop: w_s = V_s^-1 (W^-H e_s) with W^-1 carried along by rank-one updates
+    (one Cholesky per source) against the pair sweep that forms W^H V_s and solves it with a pivoted LU
+    (OIVA_RES_TRACKED=0) -- the same numbers up to rounding, and both within the tolerance of the oracle."""
+    X = small_test_mixture(90 + M, M, 2, n_samples=n_samples, frame=frame, hop=frame // 2)
+    Yo, Wo = orc.overiva(X, n_iter=15, return_filters=True)
+    out = {}
+    for tracked in ("1", "0"):
+        monkeypatch.setenv("OIVA_RES_TRACKED", tracked)
+        out[tracked] = ob.overiva(X, n_iter=15, return_filters=True)
+        assert rel_err(out[tracked][0], Yo) <= FP64_TOL and rel_err(out[tracked][1], Wo) <= FP64_TOL
+    assert rel_err(out["1"][1], out["0"][1]) <= 1e-11
+    bad = X.copy()
+    bad[:, :, M - 1] = bad[:, :, 0]  # rank-deficient: the reference's np.linalg.solve raises
+    monkeypatch.setenv("OIVA_RES_TRACKED", "1")
+    with pytest.raises(np.linalg.LinAlgError):
+        ob.overiva(bad, n_iter=6)
+
+
 def test_resident_loop_singular_mixture_does_not_stall():
     """A rank-deficient mixture fills the statistic with NaNs; the sign-tagged words must still carry the epoch's parity
     (a NaN that went through an arithmetic instruction comes back as the canonical NaN, sign bit set): LinAlgError like
