@@ -607,99 +607,98 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                     // pivoting; A is recomputed from W at the start of every epoch's sweep (no drift beyond M updates).
                     // Warp 1 keeps A in registers, warp 0 factors V_s while warp 1 is still updating A for the previous
                     // source; they exchange q and w through the (otherwise unused) shared-memory copy of C.
-                    // (Each role runs its own copy of the source loop -- in one loop the allocator kept warp 1's A alive
-                    // across warp 0's Cholesky and spilled 1.7 KB per thread; the roles meet at barrier 3, all 256 threads,
-                    // once per source.  Needs both V buffers: the launcher falls back to the pair sweep otherwise.)
+                    // One register array serves both roles -- warp 1: A (M x M, loop-carried); warp 0: the Cholesky
+                    // factor of V_s in its first NE entries -- so the allocator does not keep A alive next to warp 0's
+                    // working set (separate arrays spilled 1.7 KB per thread); every barrier is executed at ONE program
+                    // point by all of its participants (barriers 1 and 2: warps 0 and 1; __syncthreads: the block).
+                    // Needs both V buffers: the launcher falls back to the pair sweep otherwise.
+                    static_assert(NE + 0 <= M * M, "the factor fits the shared register array");
                     cplx* mail = sC;  // [2 M][32]: q, then w
+                    cplx st[M * M];
                     if (warp == 1) {
-                        cplx Ainv[M][M];
 #pragma unroll
-                        for (int j = 0; j < M; ++j)
-#pragma unroll
-                            for (int k = 0; k < M; ++k) Ainv[j][k] = sW[(j * M + k) * OIVA_GROUP + lane];
-                        invert_inplace<M>(Ainv, singular);  // (while warps 2-7 add the partial sums of source 0)
-                        named_barrier(3, RES_THREADS);
-#pragma unroll 1
-                        for (int s = 0; s < K; ++s) {
-#pragma unroll
-                            for (int j = 0; j < M; ++j) {  // q = conj(A[s][:])
-                                cplx a = Ainv[0][j];
-#pragma unroll
-                                for (int i = 1; i < M; ++i) {
-                                    a.x = s == i ? Ainv[i][j].x : a.x;
-                                    a.y = s == i ? Ainv[i][j].y : a.y;
-                                }
-                                mail[j * OIVA_GROUP + lane] = cconj(a);
-                            }
-                            named_barrier(1, 64);
-                            named_barrier(2, 64);
-                            cplx v[M];  // v = A w (w read from the mailbox one component at a time)
-#pragma unroll
-                            for (int i = 0; i < M; ++i) v[i] = cmake(0.0, 0.0);
-#pragma unroll
-                            for (int j = 0; j < M; ++j) {
-                                const cplx wj = mail[(M + j) * OIVA_GROUP + lane];
-#pragma unroll
-                                for (int i = 0; i < M; ++i) cfma(v[i], Ainv[i][j], wj);
-                            }
-                            cplx vs = v[0];
-#pragma unroll
-                            for (int i = 1; i < M; ++i) {
-                                vs.x = s == i ? v[i].x : vs.x;
-                                vs.y = s == i ? v[i].y : vs.y;
-                            }
-                            if (!(fabs(vs.x) + fabs(vs.y) > 0.0)) singular = true;
-                            const cplx vinv = crecip_fast(vs);
-#pragma unroll
-                            for (int j = 0; j < M; ++j) {  // column j of A: A[s][j] /= v_s, A[i][j] -= v_i A[s][j]
-                                cplx a = Ainv[0][j];
-#pragma unroll
-                                for (int i = 1; i < M; ++i) {
-                                    a.x = s == i ? Ainv[i][j].x : a.x;
-                                    a.y = s == i ? Ainv[i][j].y : a.y;
-                                }
-                                const cplx asj = cmul(a, vinv);
-#pragma unroll
-                                for (int i = 0; i < M; ++i) {
-                                    cplx t = Ainv[i][j];
-                                    cfms(t, v[i], asj);
-                                    Ainv[i][j].x = s == i ? asj.x : t.x;
-                                    Ainv[i][j].y = s == i ? asj.y : t.y;
-                                }
-                            }
-                            named_barrier(3, RES_THREADS);
-                        }
-                    } else if (warp == 0) {
-                        named_barrier(3, RES_THREADS);
-#pragma unroll 1
-                        for (int s = 0; s < K; ++s) {
-                            const cplx* cur = sV + (size_t)(s & 1) * MAT_ELEMS;
-                            cplx Lm[NE];
-#pragma unroll
-                            for (int e = 0; e < NE; ++e) Lm[e] = cur[e * OIVA_GROUP + lane];
-                            double dinv[M];
-                            chol_factor<M>(Lm, dinv, singular);
-                            named_barrier(1, 64);
-                            cplx q[M];
-#pragma unroll
-                            for (int j = 0; j < M; ++j) q[j] = mail[j * OIVA_GROUP + lane];
-                            chol_solve_normalise<M>(Lm, dinv, q);
-#pragma unroll
-                            for (int j = 0; j < M; ++j) {
-                                if (bin_ok) sW[(j * M + s) * OIVA_GROUP + lane] = q[j];
-                                mail[(M + j) * OIVA_GROUP + lane] = q[j];
-                            }
-                            named_barrier(2, 64);
-                            named_barrier(3, RES_THREADS);
-                        }
+                        for (int i = 0; i < M * M; ++i) st[i] = sW[i * OIVA_GROUP + lane];  // A = W (row-major j M + k)
+                        invert_inplace<M>(st, singular);  // (while warps 2-7 add the partial sums of source 0)
                     } else {
-                        reduce_source(0, sV, 64, RES_THREADS - 64);
-                        named_barrier(3, RES_THREADS);
+#pragma unroll
+                        for (int i = 0; i < M * M; ++i) st[i] = cmake(0.0, 0.0);
+                        if (warp >= 2) reduce_source(0, sV, 64, RES_THREADS - 64);
+                    }
+                    __syncthreads();
 #pragma unroll 1
-                        for (int s = 0; s < K; ++s) {
+                    for (int s = 0; s < K; ++s) {
+                        if (warp >= 2) {
                             if (s + 1 < K) reduce_source(s + 1, sV + (size_t)((s + 1) & 1) * MAT_ELEMS, 64, RES_THREADS - 64);
-                            named_barrier(3, RES_THREADS);
+                        } else {
+                            double dinv[M];
+                            if (warp == 1) {
+#pragma unroll
+                                for (int j = 0; j < M; ++j) {  // q = conj(A[s][:])
+                                    cplx a = st[j];
+#pragma unroll
+                                    for (int i = 1; i < M; ++i) {
+                                        a.x = s == i ? st[i * M + j].x : a.x;
+                                        a.y = s == i ? st[i * M + j].y : a.y;
+                                    }
+                                    mail[j * OIVA_GROUP + lane] = cconj(a);
+                                }
+                            } else {
+                                const cplx* cur = sV + (size_t)(s & 1) * MAT_ELEMS;
+#pragma unroll
+                                for (int e = 0; e < NE; ++e) st[e] = cur[e * OIVA_GROUP + lane];
+                                chol_factor<M>(st, dinv, singular);
+                            }
+                            named_barrier(1, 64);
+                            if (warp == 0) {
+                                cplx q[M];
+#pragma unroll
+                                for (int j = 0; j < M; ++j) q[j] = mail[j * OIVA_GROUP + lane];
+                                chol_solve_normalise<M>(st, dinv, q);
+#pragma unroll
+                                for (int j = 0; j < M; ++j) {
+                                    if (bin_ok) sW[(j * M + s) * OIVA_GROUP + lane] = q[j];
+                                    mail[(M + j) * OIVA_GROUP + lane] = q[j];
+                                }
+                            }
+                            named_barrier(2, 64);
+                            if (warp == 1) {
+                                cplx v[M];  // v = A w (w read from the mailbox one component at a time)
+#pragma unroll
+                                for (int i = 0; i < M; ++i) v[i] = cmake(0.0, 0.0);
+#pragma unroll
+                                for (int j = 0; j < M; ++j) {
+                                    const cplx wj = mail[(M + j) * OIVA_GROUP + lane];
+#pragma unroll
+                                    for (int i = 0; i < M; ++i) cfma(v[i], st[i * M + j], wj);
+                                }
+                                cplx vs = v[0];
+#pragma unroll
+                                for (int i = 1; i < M; ++i) {
+                                    vs.x = s == i ? v[i].x : vs.x;
+                                    vs.y = s == i ? v[i].y : vs.y;
+                                }
+                                if (!(fabs(vs.x) + fabs(vs.y) > 0.0)) singular = true;
+                                const cplx vinv = crecip_fast(vs);
+#pragma unroll
+                                for (int j = 0; j < M; ++j) {  // column j of A: A[s][j] /= v_s, A[i][j] -= v_i A[s][j]
+                                    cplx a = st[j];
+#pragma unroll
+                                    for (int i = 1; i < M; ++i) {
+                                        a.x = s == i ? st[i * M + j].x : a.x;
+                                        a.y = s == i ? st[i * M + j].y : a.y;
+                                    }
+                                    const cplx asj = cmul(a, vinv);
+#pragma unroll
+                                    for (int i = 0; i < M; ++i) {
+                                        cplx t = st[i * M + j];
+                                        cfms(t, v[i], asj);
+                                        st[i * M + j].x = s == i ? asj.x : t.x;
+                                        st[i * M + j].y = s == i ? asj.y : t.y;
+                                    }
+                                }
+                            }
                         }
+                        __syncthreads();
                     }
                     if (warp < 2 && singular && bin_ok) atomicOr(p.status + b, OIVA_STATUS_SINGULAR);
                 } else {

@@ -201,8 +201,9 @@ __device__ __forceinline__ void ip_source_full(WLane Wm, const cplx* sV, int s, 
 // V = L L^H in place on the packed lower triangle (row-major, e = i(i+1)/2 + j); dinv[j] = 1 / L[j][j].  (static_for: the
 // triple loop must be unrolled completely so that Lm is indexed with constants and stays in registers -- with
 // "#pragma unroll" alone ptxas kept a 336-byte local-memory copy of it at M = 6)
-template <int M>
-__device__ __forceinline__ void chol_factor(cplx (&Lm)[oiva_tri(M)], double (&dinv)[M], bool& singular) {
+// (LArr: any array of at least oiva_tri(M) complex numbers indexed with constants)
+template <int M, typename LArr>
+__device__ __forceinline__ void chol_factor(LArr& Lm, double (&dinv)[M], bool& singular) {
     static_for<M>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
         double djj = Lm[j * (j + 1) / 2 + j].x;
@@ -229,8 +230,8 @@ __device__ __forceinline__ void chol_factor(cplx (&Lm)[oiva_tri(M)], double (&di
     });
 }
 // q <- V^-1 q / sqrt(q^H V^-1 q) from the factor: L y = q, |y|^2 (= w^H V w, real: overiva.py:185-186), L^H w = y
-template <int M>
-__device__ __forceinline__ void chol_solve_normalise(const cplx (&Lm)[oiva_tri(M)], const double (&dinv)[M], cplx (&q)[M]) {
+template <int M, typename LArr>
+__device__ __forceinline__ void chol_solve_normalise(const LArr& Lm, const double (&dinv)[M], cplx (&q)[M]) {
     static_for<M>([&](auto ic) {
         constexpr int i = decltype(ic)::value;
         cplx v = q[i];
@@ -258,18 +259,18 @@ __device__ __forceinline__ void chol_solve_normalise(const cplx (&Lm)[oiva_tri(M
     for (int i = 0; i < M; ++i) q[i] = cscale(q[i], inv);
 }
 
-// A <- A^-1 in place (registers): Gauss-Jordan with partial pivoting (zgetrf's rule: largest |re| + |im| in the column, the
+// A <- A^-1 in place (registers, row-major flat array Af[i M + j]): Gauss-Jordan with partial pivoting (zgetrf's rule: largest |re| + |im| in the column, the
 // lower row wins a tie), the row swaps undone on the columns at the end.  For the tracked-inverse determined sweep below.
 template <int M>
-__device__ __forceinline__ void invert_inplace(cplx (&A)[M][M], bool& singular) {
+__device__ __forceinline__ void invert_inplace(cplx (&Af)[M * M], bool& singular) {
     int perm[M];
     static_for<M>([&](auto cc) {
         constexpr int c = decltype(cc)::value;
-        double best = fabs(A[c][c].x) + fabs(A[c][c].y);
+        double best = fabs(Af[(c) * M + (c)].x) + fabs(Af[(c) * M + (c)].y);
         int p = c;
         static_for<M - 1 - c>([&](auto ic) {
             constexpr int i = c + 1 + decltype(ic)::value;
-            const double m = fabs(A[i][c].x) + fabs(A[i][c].y);
+            const double m = fabs(Af[(i) * M + (c)].x) + fabs(Af[(i) * M + (c)].y);
             if (m > best) {
                 best = m;
                 p = i;
@@ -282,24 +283,24 @@ __device__ __forceinline__ void invert_inplace(cplx (&A)[M][M], bool& singular) 
             const bool sw = p == i;
 #pragma unroll
             for (int j = 0; j < M; ++j) {
-                const cplx t = A[i][j], u = A[c][j];
-                A[i][j].x = sw ? u.x : t.x;
-                A[i][j].y = sw ? u.y : t.y;
-                A[c][j].x = sw ? t.x : u.x;
-                A[c][j].y = sw ? t.y : u.y;
+                const cplx t = Af[(i) * M + (j)], u = Af[(c) * M + (j)];
+                Af[(i) * M + (j)].x = sw ? u.x : t.x;
+                Af[(i) * M + (j)].y = sw ? u.y : t.y;
+                Af[(c) * M + (j)].x = sw ? t.x : u.x;
+                Af[(c) * M + (j)].y = sw ? t.y : u.y;
             }
         });
-        const cplx piv = crecip_fast(A[c][c]);
-        A[c][c] = cmake(1.0, 0.0);
+        const cplx piv = crecip_fast(Af[(c) * M + (c)]);
+        Af[(c) * M + (c)] = cmake(1.0, 0.0);
 #pragma unroll
-        for (int j = 0; j < M; ++j) A[c][j] = cmul(A[c][j], piv);
+        for (int j = 0; j < M; ++j) Af[(c) * M + (j)] = cmul(Af[(c) * M + (j)], piv);
         static_for<M>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
             if constexpr (i != c) {
-                const cplx f = A[i][c];
-                A[i][c] = cmake(0.0, 0.0);
+                const cplx f = Af[(i) * M + (c)];
+                Af[(i) * M + (c)] = cmake(0.0, 0.0);
 #pragma unroll
-                for (int j = 0; j < M; ++j) cfms(A[i][j], f, A[c][j]);
+                for (int j = 0; j < M; ++j) cfms(Af[(i) * M + (j)], f, Af[(c) * M + (j)]);
             }
         });
     });
@@ -311,11 +312,11 @@ __device__ __forceinline__ void invert_inplace(cplx (&A)[M][M], bool& singular) 
             const bool sw = p == j;
 #pragma unroll
             for (int i = 0; i < M; ++i) {
-                const cplx t = A[i][j], u = A[i][c];
-                A[i][j].x = sw ? u.x : t.x;
-                A[i][j].y = sw ? u.y : t.y;
-                A[i][c].x = sw ? t.x : u.x;
-                A[i][c].y = sw ? t.y : u.y;
+                const cplx t = Af[(i) * M + (j)], u = Af[(i) * M + (c)];
+                Af[(i) * M + (j)].x = sw ? u.x : t.x;
+                Af[(i) * M + (j)].y = sw ? u.y : t.y;
+                Af[(i) * M + (c)].x = sw ? t.x : u.x;
+                Af[(i) * M + (c)].y = sw ? t.y : u.y;
             }
         });
     });
