@@ -615,6 +615,25 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                     static_assert(NE + 0 <= M * M, "the factor fits the shared register array");
                     cplx* mail = sC;  // [2 M][32]: q, then w
                     cplx st[M * M];
+                    double dinv[M];
+                    auto extract_q = [&](int s) {  // warp 1: q = conj(A[s][:]) into the mailbox
+#pragma unroll
+                        for (int j = 0; j < M; ++j) {
+                            cplx a = st[j];
+#pragma unroll
+                            for (int i = 1; i < M; ++i) {
+                                a.x = s == i ? st[i * M + j].x : a.x;
+                                a.y = s == i ? st[i * M + j].y : a.y;
+                            }
+                            mail[j * OIVA_GROUP + lane] = cconj(a);
+                        }
+                    };
+                    auto factor = [&](int s) {  // warp 0: Cholesky of V_s (buffer s & 1) in registers
+                        const cplx* cur = sV + (size_t)(s & 1) * MAT_ELEMS;
+#pragma unroll
+                        for (int e = 0; e < NE; ++e) st[e] = cur[e * OIVA_GROUP + lane];
+                        chol_factor<M>(st, dinv, singular);
+                    };
                     if (warp == 1) {
 #pragma unroll
                         for (int i = 0; i < M * M; ++i) st[i] = sW[i * OIVA_GROUP + lane];  // A = W (row-major j M + k)
@@ -624,31 +643,20 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                         for (int i = 0; i < M * M; ++i) st[i] = cmake(0.0, 0.0);
                         if (warp >= 2) reduce_source(0, sV, 64, RES_THREADS - 64);
                     }
+#pragma unroll
+                    for (int i = 0; i < M; ++i) dinv[i] = 0.0;
                     __syncthreads();
+                    // Software pipeline over the sources: while warp 1 folds w_s into A and extracts q_{s+1}, warp 0
+                    // already factors V_{s+1} and the other warps add the partial sums of source s + 2 (into the buffer
+                    // V_s was factored from).  Per source the chain is solve -> max(update, Cholesky) instead of
+                    // Cholesky -> solve -> update.
+                    if (warp == 1) extract_q(0);
+                    else if (warp == 0) factor(0);
+                    else if (1 < K) reduce_source(1, sV + MAT_ELEMS, 64, RES_THREADS - 64);
 #pragma unroll 1
                     for (int s = 0; s < K; ++s) {
-                        if (warp >= 2) {
-                            if (s + 1 < K) reduce_source(s + 1, sV + (size_t)((s + 1) & 1) * MAT_ELEMS, 64, RES_THREADS - 64);
-                        } else {
-                            double dinv[M];
-                            if (warp == 1) {
-#pragma unroll
-                                for (int j = 0; j < M; ++j) {  // q = conj(A[s][:])
-                                    cplx a = st[j];
-#pragma unroll
-                                    for (int i = 1; i < M; ++i) {
-                                        a.x = s == i ? st[i * M + j].x : a.x;
-                                        a.y = s == i ? st[i * M + j].y : a.y;
-                                    }
-                                    mail[j * OIVA_GROUP + lane] = cconj(a);
-                                }
-                            } else {
-                                const cplx* cur = sV + (size_t)(s & 1) * MAT_ELEMS;
-#pragma unroll
-                                for (int e = 0; e < NE; ++e) st[e] = cur[e * OIVA_GROUP + lane];
-                                chol_factor<M>(st, dinv, singular);
-                            }
-                            named_barrier(1, 64);
+                        if (warp < 2) {
+                            named_barrier(1, 64);  // q_s is in the mailbox, V_s is factored
                             if (warp == 0) {
                                 cplx q[M];
 #pragma unroll
@@ -660,46 +668,52 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                                     mail[(M + j) * OIVA_GROUP + lane] = q[j];
                                 }
                             }
-                            named_barrier(2, 64);
-                            if (warp == 1) {
-                                cplx v[M];  // v = A w (w read from the mailbox one component at a time)
+                            named_barrier(2, 64);  // w_s is in the mailbox
+                        }
+                        __syncthreads();  // V_{s+1} is summed; V_s's buffer is free
+                        if (warp == 1) {
+                            cplx v[M];  // v = A w (w read from the mailbox one component at a time)
 #pragma unroll
-                                for (int i = 0; i < M; ++i) v[i] = cmake(0.0, 0.0);
+                            for (int i = 0; i < M; ++i) v[i] = cmake(0.0, 0.0);
 #pragma unroll
-                                for (int j = 0; j < M; ++j) {
-                                    const cplx wj = mail[(M + j) * OIVA_GROUP + lane];
+                            for (int j = 0; j < M; ++j) {
+                                const cplx wj = mail[(M + j) * OIVA_GROUP + lane];
 #pragma unroll
-                                    for (int i = 0; i < M; ++i) cfma(v[i], st[i * M + j], wj);
-                                }
-                                cplx vs = v[0];
+                                for (int i = 0; i < M; ++i) cfma(v[i], st[i * M + j], wj);
+                            }
+                            cplx vs = v[0];
+#pragma unroll
+                            for (int i = 1; i < M; ++i) {
+                                vs.x = s == i ? v[i].x : vs.x;
+                                vs.y = s == i ? v[i].y : vs.y;
+                            }
+                            if (!(fabs(vs.x) + fabs(vs.y) > 0.0)) singular = true;
+                            const cplx vinv = crecip_fast(vs);
+#pragma unroll
+                            for (int j = 0; j < M; ++j) {  // column j of A: A[s][j] /= v_s, A[i][j] -= v_i A[s][j]
+                                cplx a = st[j];
 #pragma unroll
                                 for (int i = 1; i < M; ++i) {
-                                    vs.x = s == i ? v[i].x : vs.x;
-                                    vs.y = s == i ? v[i].y : vs.y;
+                                    a.x = s == i ? st[i * M + j].x : a.x;
+                                    a.y = s == i ? st[i * M + j].y : a.y;
                                 }
-                                if (!(fabs(vs.x) + fabs(vs.y) > 0.0)) singular = true;
-                                const cplx vinv = crecip_fast(vs);
+                                const cplx asj = cmul(a, vinv);
 #pragma unroll
-                                for (int j = 0; j < M; ++j) {  // column j of A: A[s][j] /= v_s, A[i][j] -= v_i A[s][j]
-                                    cplx a = st[j];
-#pragma unroll
-                                    for (int i = 1; i < M; ++i) {
-                                        a.x = s == i ? st[i * M + j].x : a.x;
-                                        a.y = s == i ? st[i * M + j].y : a.y;
-                                    }
-                                    const cplx asj = cmul(a, vinv);
-#pragma unroll
-                                    for (int i = 0; i < M; ++i) {
-                                        cplx t = st[i * M + j];
-                                        cfms(t, v[i], asj);
-                                        st[i * M + j].x = s == i ? asj.x : t.x;
-                                        st[i * M + j].y = s == i ? asj.y : t.y;
-                                    }
+                                for (int i = 0; i < M; ++i) {
+                                    cplx t = st[i * M + j];
+                                    cfms(t, v[i], asj);
+                                    st[i * M + j].x = s == i ? asj.x : t.x;
+                                    st[i * M + j].y = s == i ? asj.y : t.y;
                                 }
                             }
+                            if (s + 1 < K) extract_q(s + 1);
+                        } else if (warp == 0) {
+                            if (s + 1 < K) factor(s + 1);
+                        } else if (s + 2 < K) {
+                            reduce_source(s + 2, sV + (size_t)(s & 1) * MAT_ELEMS, 64, RES_THREADS - 64);
                         }
-                        __syncthreads();
                     }
+                    __syncthreads();
                     if (warp < 2 && singular && bin_ok) atomicOr(p.status + b, OIVA_STATUS_SINGULAR);
                 } else {
 #pragma unroll 1
