@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_loop_resident(const Resident
                     // working set (separate arrays spilled 1.7 KB per thread); every barrier is executed at ONE program
                     // point by all of its participants (barriers 1 and 2: warps 0 and 1; __syncthreads: the block).
                     // Needs both V buffers: the launcher falls back to the pair sweep otherwise.
-                    static_assert(NE + 0 <= M * M, "the factor fits the shared register array");
+                    static_assert(NE <= M * M, "the factor fits the shared register array");
                     cplx* mail = sC;  // [2 M][32]: q, then w
                     cplx st[M * M];
                     double dinv[M];
